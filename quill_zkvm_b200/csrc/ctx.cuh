@@ -1,0 +1,112 @@
+// Context shared by the C-ABI entry points: one device, one stream, a scratch arena, cached constants.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/quill_b200.h"
+
+struct ncclComm;
+
+struct qz_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  std::string err;
+  uint64_t launches = 0;
+
+  // scratch arena: bump allocation out of cached device blocks, reset at the start of every API call
+  struct Block {
+    void* p;
+    size_t cap, off;
+  };
+  std::vector<Block> blocks;
+
+  // per-degree interpolation matrices (device), keyed by degree
+  std::map<int, void*> vinv;
+
+  cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+  float last_ms[2] = {0.f, 0.f};
+  float kernel_ms_accum = 0.f;
+
+  // pinned staging for small results
+  void* pinned = nullptr;
+  size_t pinned_cap = 0;
+
+  ncclComm* comm = nullptr;
+  int rank = 0, nranks = 1;
+
+  int fail(int status, const char* what, cudaError_t ce = cudaSuccess) {
+    char buf[512];
+    if (ce != cudaSuccess)
+      snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(ce));
+    else
+      snprintf(buf, sizeof buf, "%s", what);
+    err = buf;
+    return status;
+  }
+
+  void arena_reset() {
+    if (blocks.size() > 1) {  // coalesce into one block for the next call
+      size_t total = 0;
+      for (auto& b : blocks) {
+        total += b.cap;
+        cudaFree(b.p);
+      }
+      blocks.clear();
+      void* p = nullptr;
+      if (cudaMalloc(&p, total) == cudaSuccess) blocks.push_back(Block{p, total, 0});
+    }
+    for (auto& b : blocks) b.off = 0;
+  }
+  void* arena_alloc(size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes == 0) bytes = 256;
+    for (auto& b : blocks)
+      if (b.cap - b.off >= bytes) {
+        void* r = (char*)b.p + b.off;
+        b.off += bytes;
+        return r;
+      }
+    size_t cap = bytes < ((size_t)64 << 20) ? ((size_t)64 << 20) : bytes;
+    void* p = nullptr;
+    if (cudaMalloc(&p, cap) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    blocks.push_back(Block{p, cap, bytes});
+    return p;
+  }
+  void* pinned_buf(size_t bytes) {
+    if (bytes > pinned_cap) {
+      if (pinned) cudaFreeHost(pinned);
+      pinned = nullptr;
+      pinned_cap = 0;
+      size_t cap = bytes < 65536 ? 65536 : bytes;
+      if (cudaMallocHost(&pinned, cap) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+      }
+      pinned_cap = cap;
+    }
+    return pinned;
+  }
+};
+
+#define QZ_CUDA(ctx, call)                                              \
+  do {                                                                  \
+    cudaError_t e_ = (call);                                            \
+    if (e_ != cudaSuccess) return (ctx)->fail(QZ_ERR_CUDA, #call, e_);  \
+  } while (0)
+
+// kernel launch with launch accounting; errors surface at the next QZ_CUDA / sync
+#define QZ_LAUNCH(ctx, kernel, grid, block, smem, ...)                        \
+  do {                                                                        \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);          \
+    (ctx)->launches++;                                                        \
+    cudaError_t e_ = cudaPeekAtLastError();                                   \
+    if (e_ != cudaSuccess) return (ctx)->fail(QZ_ERR_CUDA, #kernel, e_);      \
+  } while (0)

@@ -1,0 +1,242 @@
+// BN254 Fr / Fq arithmetic for sm_100a: 8x32-bit limbs, Montgomery form (R = 2^256), values always in [0, p).
+//
+// This is the arithmetic ark-ff 0.5.0 supplies to the reference (Fr at hyperplonk/src/piops/sumcheck.rs:53-92,
+// Fq under ark-ec's group law used by pcs/src/kzg.rs:72).  Byte layout of an element equals arkworks' in-memory
+// layout (4 x u64 little-endian Montgomery limbs == 8 x u32), so host buffers cross the C ABI without conversion.
+//
+// Multiplication is a word-serial Montgomery product on the 32-bit integer multiply pipe.  Per multiplier word b_i the
+// partial products a_j*b_i with j even occupy disjoint 64-bit lanes (columns j, j+1), as do the ones with j odd, so
+// each half-row is one carry chain of mad.lo.cc / madc.hi.cc pairs with no per-product carry fix-up; ptxas fuses
+// each lo/hi pair into a single IMAD.WIDE.U32 with predicate carry.  Because p < 2^254 the running value stays
+// below 2p < 2^255, so the accumulator never needs a tenth word and the final reduction is one conditional subtract.
+#pragma once
+#include <cstdint>
+#include "ff_consts.cuh"
+
+namespace qz {
+
+#define QZ_DEV __device__ __forceinline__
+
+template <class P>
+struct Fp {
+  uint32_t v[8];
+};
+
+// one half-row:  t[0..7] += {a0,a1,a2,a3} (each a 32-bit word occupying lane (2i, 2i+1)) * b ;  carry -> t8
+//   last == false:  t8 += carry   (t8 may be non-zero)
+QZ_DEV void mad_chain_even(uint32_t& t0, uint32_t& t1, uint32_t& t2, uint32_t& t3, uint32_t& t4, uint32_t& t5,
+                           uint32_t& t6, uint32_t& t7, uint32_t& t8, uint32_t a0, uint32_t a1, uint32_t a2,
+                           uint32_t a3, uint32_t b) {
+  asm volatile(
+      "mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+      "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+      "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+      "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+      "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+      "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+      "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+      "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+      "addc.u32 %8, %8, 0;\n\t"
+      : "+r"(t0), "+r"(t1), "+r"(t2), "+r"(t3), "+r"(t4), "+r"(t5), "+r"(t6), "+r"(t7), "+r"(t8)
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+}
+// the odd half-row ends exactly at the top word: no carry can leave it (value < 2^288)
+QZ_DEV void mad_chain_odd(uint32_t& t1, uint32_t& t2, uint32_t& t3, uint32_t& t4, uint32_t& t5, uint32_t& t6,
+                          uint32_t& t7, uint32_t& t8, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                          uint32_t b) {
+  asm volatile(
+      "mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+      "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+      "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+      "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+      "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+      "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+      "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+      "madc.hi.u32 %7, %11, %12, %7;\n\t"
+      : "+r"(t1), "+r"(t2), "+r"(t3), "+r"(t4), "+r"(t5), "+r"(t6), "+r"(t7), "+r"(t8)
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+}
+
+// r = a - p if a >= p else a   (a < 2p)
+template <class P>
+QZ_DEV void fp_reduce_once(uint32_t r[8], const uint32_t a[8]) {
+  uint32_t d[8], borrow;
+  asm volatile(
+      "sub.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;\n\t"
+      : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(borrow)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(P::MOD(0)),
+        "r"(P::MOD(1)), "r"(P::MOD(2)), "r"(P::MOD(3)), "r"(P::MOD(4)), "r"(P::MOD(5)), "r"(P::MOD(6)),
+        "r"(P::MOD(7)));
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = borrow ? a[i] : d[i];
+}
+
+template <class P>
+QZ_DEV Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+  uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, t6 = 0, t7 = 0, t8 = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint32_t bi = b.v[i];
+    mad_chain_even(t0, t1, t2, t3, t4, t5, t6, t7, t8, a.v[0], a.v[2], a.v[4], a.v[6], bi);
+    mad_chain_odd(t1, t2, t3, t4, t5, t6, t7, t8, a.v[1], a.v[3], a.v[5], a.v[7], bi);
+    const uint32_t m = t0 * P::INV;
+    mad_chain_even(t0, t1, t2, t3, t4, t5, t6, t7, t8, P::MOD(0), P::MOD(2), P::MOD(4), P::MOD(6), m);
+    mad_chain_odd(t1, t2, t3, t4, t5, t6, t7, t8, P::MOD(1), P::MOD(3), P::MOD(5), P::MOD(7), m);
+    // t0 == 0 now: shift down one word
+    t0 = t1; t1 = t2; t2 = t3; t3 = t4; t4 = t5; t5 = t6; t6 = t7; t7 = t8; t8 = 0;
+  }
+  const uint32_t t[8] = {t0, t1, t2, t3, t4, t5, t6, t7};
+  Fp<P> r;
+  fp_reduce_once<P>(r.v, t);
+  return r;
+}
+
+template <class P>
+QZ_DEV Fp<P> fp_sqr(const Fp<P>& a) {
+  return fp_mul<P>(a, a);
+}
+
+template <class P>
+QZ_DEV Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) {
+  uint32_t s[8];
+  asm volatile(
+      "add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;\n\t"
+      : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7])
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+        "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+  Fp<P> r;
+  fp_reduce_once<P>(r.v, s);
+  return r;
+}
+
+template <class P>
+QZ_DEV Fp<P> fp_sub(const Fp<P>& a, const Fp<P>& b) {
+  uint32_t d[8], mask;
+  asm volatile(
+      "sub.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;\n\t"
+      : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(mask)
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+        "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+  // mask = 0xffffffff when a < b: add p back
+  Fp<P> r;
+  asm volatile(
+      "add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;\n\t"
+      : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
+        "=r"(r.v[7])
+      : "r"(d[0]), "r"(d[1]), "r"(d[2]), "r"(d[3]), "r"(d[4]), "r"(d[5]), "r"(d[6]), "r"(d[7]),
+        "r"(P::MOD(0) & mask), "r"(P::MOD(1) & mask), "r"(P::MOD(2) & mask), "r"(P::MOD(3) & mask),
+        "r"(P::MOD(4) & mask), "r"(P::MOD(5) & mask), "r"(P::MOD(6) & mask), "r"(P::MOD(7) & mask));
+  return r;
+}
+
+template <class P>
+QZ_DEV Fp<P> fp_zero() {
+  Fp<P> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = 0;
+  return r;
+}
+template <class P>
+QZ_DEV Fp<P> fp_one() {
+  Fp<P> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = P::ONE(i);
+  return r;
+}
+template <class P>
+QZ_DEV bool fp_is_zero(const Fp<P>& a) {
+  return (a.v[0] | a.v[1] | a.v[2] | a.v[3] | a.v[4] | a.v[5] | a.v[6] | a.v[7]) == 0;
+}
+template <class P>
+QZ_DEV bool fp_eq(const Fp<P>& a, const Fp<P>& b) {
+  uint32_t x = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) x |= a.v[i] ^ b.v[i];
+  return x == 0;
+}
+template <class P>
+QZ_DEV Fp<P> fp_neg(const Fp<P>& a) {
+  return fp_sub<P>(fp_zero<P>(), a);
+}
+template <class P>
+QZ_DEV Fp<P> fp_dbl(const Fp<P>& a) {
+  return fp_add<P>(a, a);
+}
+// Montgomery -> canonical limbs (multiply by 1)
+template <class P>
+QZ_DEV Fp<P> fp_from_mont(const Fp<P>& a) {
+  Fp<P> one_raw = fp_zero<P>();
+  one_raw.v[0] = 1;
+  return fp_mul<P>(a, one_raw);
+}
+// canonical limbs (any value < 2^256, not necessarily < p) -> Montgomery, fully reduced.
+// fp_mul needs its FIRST operand < p (it bounds the running sum); the second may be any 256-bit value.
+template <class P>
+QZ_DEV Fp<P> fp_to_mont(const Fp<P>& a) {
+  Fp<P> r2;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r2.v[i] = P::R2(i);
+  return fp_mul<P>(r2, a);
+}
+// a^(p-2); 0 -> 0.  Rare path (affine conversion, interpolation constants): plain square-and-multiply.
+template <class P>
+__device__ __noinline__ Fp<P> fp_inv(const Fp<P>& a) {
+  Fp<P> acc = fp_one<P>();
+  for (int i = 255; i >= 0; i--) {
+    acc = fp_sqr<P>(acc);
+    if ((P::PM2(i >> 5) >> (i & 31)) & 1) acc = fp_mul<P>(acc, a);
+  }
+  return acc;
+}
+
+// 128-bit vectorised global access: an element is two uint4
+template <class P>
+QZ_DEV Fp<P> fp_load(const void* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 lo = q[0], hi = q[1];
+  Fp<P> r;
+  r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
+  r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+  return r;
+}
+template <class P>
+QZ_DEV void fp_store(void* p, const Fp<P>& a) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+  q[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+}
+
+typedef Fp<FrParams> Fr;
+typedef Fp<FqParams> Fq;
+
+}  // namespace qz

@@ -1,0 +1,618 @@
+// KZG commit = multi-scalar multiplication over BN254 G1, Pippenger style, for sm_100a.
+//
+// Reference: KZG::commit (pcs/src/kzg.rs:61-73), whose work is ark-ec 0.5.0's VariableBaseMSM::msm_unchecked on the
+// affine-normalised SRS; KZG::open (pcs/src/kzg.rs:75-96); KZG::trusted_setup's G1 powers (pcs/src/kzg.rs:35-59).
+//
+// Pipeline (all on the device, one stream):
+//   1. msm_digits        scalar: Montgomery -> canonical -> signed c-bit digits; one (key, value) per (window, scalar)
+//                        key = window << c | |digit|, value = point index | sign << 31
+//   2. radix sort        (key, value) pairs by key (cub::DeviceRadixSort) -> every bucket's points are contiguous
+//   3. msm_bounds        first / last position of every key in the sorted list
+//   4. msm_accumulate    the hot kernel: the sorted list is cut into fixed chunks of ACC_CHUNK entries, one thread per
+//                        chunk, XYZZ += affine (8M + 2S) per entry with the next base prefetched; load is balanced
+//                        whatever the scalar distribution.  A chunk's first / last runs may be partial buckets and go
+//                        to per-chunk slots, interior runs are complete buckets and are written in place.
+//   5. msm_bucket_finish per bucket: add the partial runs of the chunks it spans
+//   6. msm_bucket_reduce per window: sum_b b * B_b by segmented running sums + a tree reduction
+//   7. msm_combine       Horner over windows (c doublings each) + one inversion to affine
+// Bases are normalised to affine ONCE at SRS upload; the reference re-normalises on every commit (kzg.rs:67-71).
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include "ctx.cuh"
+#include "ec.cuh"
+#include "msm.cuh"
+
+namespace qz {
+
+constexpr int ACC_CHUNK = 32;        // sorted entries per accumulate thread
+constexpr int ACC_THREADS = 128;
+constexpr int RED_SEG = 32;          // buckets per bucket-reduce thread
+constexpr uint32_t KEY_NONE = 0xffffffffu;
+
+// ---- 1. digits ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) msm_digits(const uint4* scalars, uint32_t n, int c, int W, uint32_t* keys,
+                                                  uint32_t* vals) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Fr k = fp_from_mont<FrParams>(fp_load<FrParams>(scalars + 2 * (size_t)i));
+  const uint32_t mask = (1u << c) - 1, half = 1u << (c - 1);
+  uint32_t carry = 0;
+  for (int w = 0; w < W; w++) {
+    const int bit = w * c, limb = bit >> 5, off = bit & 31;
+    uint64_t two = 0;
+    if (limb < 8) two = k.v[limb];
+    if (limb + 1 < 8) two |= (uint64_t)k.v[limb + 1] << 32;
+    uint32_t d = ((uint32_t)(two >> off) & mask) + carry;
+    uint32_t neg = 0;
+    carry = 0;
+    if (d > half) {  // d in (2^(c-1), 2^c]  ->  -(2^c - d), carry one into the next window
+      d = (1u << c) - d;
+      neg = 1;
+      carry = 1;
+    }
+    keys[(size_t)w * n + i] = ((uint32_t)w << c) | d;
+    vals[(size_t)w * n + i] = i | (neg << 31);
+  }
+}
+
+// ---- 3. bucket boundaries ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) msm_bounds(const uint32_t* keys, uint64_t m, uint32_t* first, uint32_t* last) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+    const uint32_t k = keys[i];
+    if (i == 0 || keys[i - 1] != k) first[k] = (uint32_t)i;
+    if (i + 1 == m || keys[i + 1] != k) last[k] = (uint32_t)(i + 1);
+  }
+}
+
+// ---- 4. accumulate ----------------------------------------------------------------------------------------------------------
+QZ_DEV Affine load_base(const uint8_t* bases, uint32_t val) {
+  Affine a = affine_load(bases + (size_t)(val & 0x7fffffffu) * 64);
+  if (val >> 31) a.y = fp_neg<FqParams>(a.y);
+  return a;
+}
+QZ_DEV uint32_t bucket_slot(uint32_t key, int c) {  // dense slot of a non-zero digit: window * 2^(c-1) + |d| - 1
+  const uint32_t w = key >> c, d = key & ((1u << c) - 1);
+  return (w << (c - 1)) + d - 1;
+}
+
+__global__ void __launch_bounds__(ACC_THREADS) msm_accumulate(const uint32_t* keys, const uint32_t* vals, uint64_t m,
+                                                              const uint8_t* bases, int c, uint8_t* buckets,
+                                                              uint8_t* heads, uint8_t* tails, uint32_t* head_key,
+                                                              uint32_t* tail_key) {
+  const uint64_t chunk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t begin = chunk * ACC_CHUNK;
+  if (begin >= m) return;
+  const uint64_t end = begin + ACC_CHUNK < m ? begin + ACC_CHUNK : m;
+  const uint32_t dmask = (1u << c) - 1;
+  Xyzz acc = xyzz_identity();
+  uint32_t cur_key = keys[begin];
+  bool first = true;
+  uint32_t hk = KEY_NONE, tk = KEY_NONE;
+  uint32_t nk = cur_key, nv = vals[begin];
+  Affine npt = (nk & dmask) ? load_base(bases, nv) : Affine{fp_zero<FqParams>(), fp_zero<FqParams>()};
+  for (uint64_t j = begin; j < end; j++) {
+    const uint32_t k = nk;
+    const Affine pt = npt;
+    if (j + 1 < end) {  // prefetch the next entry's base while this one is added
+      nk = keys[j + 1];
+      nv = vals[j + 1];
+      if (nk & dmask) npt = load_base(bases, nv);
+    }
+    if (k != cur_key) {  // the run of cur_key ended inside the chunk
+      if (cur_key & dmask) {
+        if (first) {  // it started at the chunk border: possibly the tail end of a bucket begun in earlier chunks
+          xyzz_store(heads + chunk * 128, acc);
+          hk = cur_key;
+        } else {  // strictly interior: a complete bucket
+          xyzz_store(buckets + (size_t)bucket_slot(cur_key, c) * 128, acc);
+        }
+      }
+      acc = xyzz_identity();
+      cur_key = k;
+      first = false;
+    }
+    if (k & dmask) acc = xyzz_add_affine(acc, pt);
+  }
+  if (cur_key & dmask) {  // the last run touches the chunk's end and may continue in the next chunk
+    if (first) {
+      xyzz_store(heads + chunk * 128, acc);
+      hk = cur_key;
+    } else {
+      xyzz_store(tails + chunk * 128, acc);
+      tk = cur_key;
+    }
+  }
+  head_key[chunk] = hk;
+  tail_key[chunk] = tk;
+}
+
+// ---- 5. finish buckets that span chunk borders ----------------------------------------------------------------------
+__global__ void __launch_bounds__(128) msm_bucket_finish(const uint32_t* first, const uint32_t* last, uint64_t m, int c,
+                                                         int W, const uint8_t* heads, const uint8_t* tails,
+                                                         const uint32_t* head_key, const uint32_t* tail_key,
+                                                         uint8_t* buckets) {
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t per_w = 1u << (c - 1);
+  if (slot >= (uint32_t)W * per_w) return;
+  const uint32_t key = ((slot >> (c - 1)) << c) | ((slot & (per_w - 1)) + 1);
+  const uint64_t s = first[key], e = last[key];
+  if (s == e) return;  // empty bucket: buckets[] was zero-filled = identity
+  const uint64_t c0 = s / ACC_CHUNK, c1 = (e - 1) / ACC_CHUNK;
+  const uint64_t c0_end = (c0 + 1) * ACC_CHUNK < m ? (c0 + 1) * ACC_CHUNK : m;
+  if (c0 == c1 && s > c0 * ACC_CHUNK && e < c0_end) return;  // interior run: written in place by msm_accumulate
+  Xyzz sum = xyzz_identity();
+  for (uint64_t ch = c0; ch <= c1; ch++) {
+    Xyzz p;
+    if (head_key[ch] == key) {
+      xyzz_load(p, heads + ch * 128);
+      sum = xyzz_add(sum, p);
+    }
+    if (tail_key[ch] == key) {
+      xyzz_load(p, tails + ch * 128);
+      sum = xyzz_add(sum, p);
+    }
+  }
+  xyzz_store(buckets + (size_t)slot * 128, sum);
+}
+
+// ---- 6. bucket reduction: window sum = sum_{b=1..2^(c-1)} b * B_b ----------------------------------------------------------
+// thread t of a window owns buckets (digits) lo+1 .. lo+seg with lo = t*seg:  sum_j (lo + j) B_{lo+j} = acc + lo * S
+__global__ void __launch_bounds__(128) msm_bucket_reduce(const uint8_t* buckets, int c, int W, int seg, uint8_t* partial) {
+  const uint32_t per_w = 1u << (c - 1), threads_per_w = per_w / seg;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (uint32_t)W * threads_per_w) return;
+  const uint32_t w = t / threads_per_w, tw = t % threads_per_w, lo = tw * seg;
+  const uint8_t* base = buckets + ((size_t)w * per_w + lo) * 128;
+  Xyzz running = xyzz_identity(), acc = xyzz_identity();
+  for (int j = seg - 1; j >= 0; j--) {
+    Xyzz b;
+    xyzz_load(b, base + (size_t)j * 128);
+    running = xyzz_add(running, b);
+    acc = xyzz_add(acc, running);
+  }
+  if (lo && !xyzz_is_identity(running)) {  // + lo * S (double-and-add, lo < 2^15)
+    Xyzz mul = xyzz_identity();
+    for (int bit = 31 - __clz(lo); bit >= 0; bit--) {
+      mul = xyzz_dbl(mul);
+      if ((lo >> bit) & 1) mul = xyzz_add(mul, running);
+    }
+    acc = xyzz_add(acc, mul);
+  }
+  xyzz_store(partial + (size_t)t * 128, acc);
+}
+// one block per window: tree-sum of that window's partials
+__global__ void __launch_bounds__(128) msm_window_sum(const uint8_t* partial, uint32_t per_window, uint8_t* window_sums) {
+  __shared__ __align__(16) uint8_t sh[128 * 128];
+  const uint32_t w = blockIdx.x;
+  Xyzz acc = xyzz_identity();
+  for (uint32_t i = threadIdx.x; i < per_window; i += blockDim.x) {
+    Xyzz p;
+    xyzz_load(p, partial + ((size_t)w * per_window + i) * 128);
+    acc = xyzz_add(acc, p);
+  }
+  xyzz_store(sh + threadIdx.x * 128, acc);
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      Xyzz a, b;
+      xyzz_load(a, sh + threadIdx.x * 128);
+      xyzz_load(b, sh + (threadIdx.x + s) * 128);
+      xyzz_store(sh + threadIdx.x * 128, xyzz_add(a, b));
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    Xyzz r;
+    xyzz_load(r, sh);
+    xyzz_store(window_sums + (size_t)w * 128, r);
+  }
+}
+
+// ---- 7. window combine + affine conversion --------------------------------------------------------------------------------
+__global__ void msm_combine(const uint8_t* window_sums, int c, int W, uint8_t* out_xyzz, uint8_t* out_affine) {
+  Xyzz total;
+  xyzz_load(total, window_sums + (size_t)(W - 1) * 128);
+  for (int w = W - 2; w >= 0; w--) {
+    for (int j = 0; j < c; j++) total = xyzz_dbl(total);
+    Xyzz p;
+    xyzz_load(p, window_sums + (size_t)w * 128);
+    total = xyzz_add(total, p);
+  }
+  if (out_xyzz) xyzz_store(out_xyzz, total);
+  if (out_affine) affine_store(out_affine, xyzz_to_affine(total));
+}
+// sum of `n` XYZZ points (multi-GPU: the gathered per-rank partial sums) -> affine
+__global__ void msm_sum_points(const uint8_t* pts, int n, uint8_t* out_affine) {
+  Xyzz total = xyzz_identity();
+  for (int i = 0; i < n; i++) {
+    Xyzz p;
+    xyzz_load(p, pts + (size_t)i * 128);
+    total = xyzz_add(total, p);
+  }
+  affine_store(out_affine, xyzz_to_affine(total));
+}
+
+// ---- SRS generation: points[i] = tau^i * g (kzg.rs:44-47), fixed-base 8-bit windows -------------------------------------
+// table[w*255 + d-1] = (d << 8w) * g, affine
+__global__ void srs_table_bases(Affine g, uint8_t* pow_bases /*32 affine: 2^(8w) g*/) {
+  const int w = threadIdx.x;
+  if (w >= 32) return;
+  Xyzz p = xyzz_from_affine(g);
+  for (int i = 0; i < 8 * w; i++) p = xyzz_dbl(p);
+  affine_store(pow_bases + w * 64, xyzz_to_affine(p));
+}
+__global__ void srs_table_fill(const uint8_t* pow_bases, uint8_t* table) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 32 * 255) return;
+  const int w = idx / 255, d = idx % 255 + 1;
+  const Affine b = affine_load(pow_bases + w * 64);
+  Xyzz acc = xyzz_identity();
+  for (int bit = 7; bit >= 0; bit--) {
+    acc = xyzz_dbl(acc);
+    if ((d >> bit) & 1) acc = xyzz_add_affine(acc, b);
+  }
+  affine_store(table + (size_t)idx * 64, xyzz_to_affine(acc));
+}
+constexpr int SRS_CHUNK = 8;
+__global__ void __launch_bounds__(128) srs_generate(const uint8_t* table, Fr tau, uint64_t n, uint8_t* out) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t begin = t * SRS_CHUNK;
+  if (begin >= n) return;
+  // tau^begin by square-and-multiply
+  Fr ti = fp_one<FrParams>();
+  for (int bit = 63 - __clzll(begin | 1); bit >= 0; bit--) {
+    ti = fp_sqr<FrParams>(ti);
+    if ((begin >> bit) & 1) ti = fp_mul<FrParams>(ti, tau);
+  }
+  const uint64_t end = begin + SRS_CHUNK < n ? begin + SRS_CHUNK : n;
+  for (uint64_t i = begin; i < end; i++) {
+    const Fr k = fp_from_mont<FrParams>(ti);
+    Xyzz acc = xyzz_identity();
+    for (int w = 0; w < 32; w++) {
+      const uint32_t d = (k.v[w >> 2] >> (8 * (w & 3))) & 0xffu;
+      if (d) acc = xyzz_add_affine(acc, affine_load(table + (size_t)(w * 255 + d - 1) * 64));
+    }
+    affine_store(out + i * 64, xyzz_to_affine(acc));
+    ti = fp_mul<FrParams>(ti, tau);
+  }
+}
+
+// ---- KZG::open pieces (kzg.rs:75-96) -----------------------------------------------------------------------------------------------
+// The quotient of p(X) - p(x) by (X - x) is q_{i-1} = p_i + x q_i, i.e. q_{i-1} = sum_{j >= i} p_j x^{j-i}: a suffix
+// scan with multiplier x.  Three passes over chunks of OPEN_CHUNK coefficients:
+//   A. per chunk: local Horner value  h_c = sum_{j in chunk} p_j x^{j - start_c}
+//   B. one block: carry_c = value entering chunk c from the right = sum_{c' > c} h_{c'} x^{start_{c'} - end_c}
+//   C. per chunk: rerun the recurrence with the carry, writing q; chunk 0's final value is y = p(x).
+constexpr int OPEN_CHUNK = 64;
+__global__ void __launch_bounds__(128) open_local(const uint4* p, uint64_t n, Fr x, Fr* h) {
+  const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t begin = c * OPEN_CHUNK;
+  if (begin >= n) return;
+  const uint64_t end = begin + OPEN_CHUNK < n ? begin + OPEN_CHUNK : n;
+  Fr acc = fp_zero<FrParams>();
+  for (uint64_t j = end; j-- > begin;) acc = fp_add<FrParams>(fp_mul<FrParams>(acc, x), fp_load<FrParams>(p + 2 * j));
+  h[c] = acc;
+}
+// serial-over-chunks carry pass with one thread per stripe would be O(n/CHUNK); instead: block-wide scan in two levels
+__global__ void __launch_bounds__(1) open_carry_serial(const Fr* h, uint64_t nchunks, Fr xL, Fr* carry) {
+  // carry[c] = sum_{c' > c} h[c'] * xL^(c' - c - 1); all chunks but possibly the last are full, and the last chunk's
+  // h is multiplied only by powers belonging to the full chunks to its left, so xL = x^OPEN_CHUNK throughout.
+  Fr acc = fp_zero<FrParams>();
+  for (uint64_t c = nchunks; c-- > 0;) {
+    carry[c] = acc;
+    acc = fp_add<FrParams>(fp_mul<FrParams>(acc, xL), h[c]);
+  }
+}
+__global__ void __launch_bounds__(256) open_carry_level(const Fr* h, uint64_t nchunks, Fr xL, int group, Fr* group_h) {
+  // level-2 local values over groups of `group` chunks
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t begin = g * group;
+  if (begin >= nchunks) return;
+  const uint64_t end = begin + group < nchunks ? begin + group : nchunks;
+  Fr acc = fp_zero<FrParams>();
+  for (uint64_t c = end; c-- > begin;) acc = fp_add<FrParams>(fp_mul<FrParams>(acc, xL), h[c]);
+  group_h[g] = acc;
+}
+__global__ void __launch_bounds__(256) open_carry_expand(const Fr* h, uint64_t nchunks, Fr xL, int group,
+                                                        const Fr* group_carry, Fr* carry) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t begin = g * group;
+  if (begin >= nchunks) return;
+  const uint64_t end = begin + group < nchunks ? begin + group : nchunks;
+  Fr acc = group_carry[g];
+  for (uint64_t c = end; c-- > begin;) {
+    carry[c] = acc;
+    acc = fp_add<FrParams>(fp_mul<FrParams>(acc, xL), h[c]);
+  }
+}
+__global__ void __launch_bounds__(128) open_write(const uint4* p, uint64_t n, Fr x, const Fr* carry, uint4* q, Fr* y) {
+  const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t begin = c * OPEN_CHUNK;
+  if (begin >= n) return;
+  const uint64_t end = begin + OPEN_CHUNK < n ? begin + OPEN_CHUNK : n;
+  Fr acc = carry[c];  // = q_{end-1} (the value of the recurrence entering this chunk from the right)
+  for (uint64_t j = end; j-- > begin;) {
+    // invariant: acc = q_j (with q_{n-1} = 0);  q_{j-1} = p_j + x q_j
+    acc = fp_add<FrParams>(fp_mul<FrParams>(acc, x), fp_load<FrParams>(p + 2 * j));
+    if (j > 0) fp_store<FrParams>(q + 2 * (j - 1), acc);
+    else *y = acc;  // the remainder of the division = p(x)
+  }
+}
+__global__ void fr_pow_small(Fr x, uint32_t e, Fr* out) {
+  Fr acc = fp_one<FrParams>();
+  for (int bit = 31; bit >= 0; bit--) {
+    acc = fp_sqr<FrParams>(acc);
+    if ((e >> bit) & 1) acc = fp_mul<FrParams>(acc, x);
+  }
+  *out = acc;
+}
+
+}  // namespace qz
+
+using namespace qz;
+
+namespace qz {
+
+// window size: minimise n*W mixed adds (10 mults) + W * 2^(c-1) * 2 full adds (14 mults) in the reduction
+static int pick_window(size_t n) {
+  int best = 4;
+  double best_cost = 1e300;
+  for (int c = 4; c <= 16; c++) {
+    int W = (256 + c - 1) / c;
+    double cost = (double)n * W * 10.0 + (double)W * (double)(1u << (c - 1)) * 2.0 * 14.0 * 4.0;  // reduce is latency-bound: weight x4
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = c;
+    }
+  }
+  return best;
+}
+
+// scalars_dev: n Montgomery Fr on the device.  Writes the result as XYZZ (128 B, device) and/or affine (64 B, device).
+int msm_device(qz_ctx* ctx, const uint8_t* bases, const uint4* scalars_dev, size_t n, uint8_t* out_xyzz_dev,
+               uint8_t* out_affine_dev) {
+  cudaStream_t st = ctx->stream;
+  if (n == 0) {  // empty sum = identity (reachable: commit(&[]) for the quotient of a constant, mlpcs.rs:321-393)
+    if (out_xyzz_dev) QZ_CUDA(ctx, cudaMemsetAsync(out_xyzz_dev, 0, 128, st));
+    if (out_affine_dev) QZ_CUDA(ctx, cudaMemsetAsync(out_affine_dev, 0, 64, st));
+    return QZ_OK;
+  }
+  if (n >= ((size_t)1 << 31)) return ctx->fail(QZ_ERR_INVALID_ARG, "MSM size must be below 2^31");
+  const int c = pick_window(n);
+  const int W = (256 + c - 1) / c;
+  const uint64_t m = (uint64_t)W * n;
+  if (m >= ((uint64_t)1 << 32)) return ctx->fail(QZ_ERR_INVALID_ARG, "MSM too large for 32-bit positions");
+  const uint32_t n_keys = (uint32_t)W << c, per_w = 1u << (c - 1), n_slots = (uint32_t)W * per_w;
+  const uint64_t n_chunks = (m + ACC_CHUNK - 1) / ACC_CHUNK;
+  int key_bits = c;
+  while ((1u << (key_bits - c)) < (uint32_t)W) key_bits++;
+
+  uint32_t* keys = (uint32_t*)ctx->arena_alloc(4 * m);
+  uint32_t* vals = (uint32_t*)ctx->arena_alloc(4 * m);
+  uint32_t* keys2 = (uint32_t*)ctx->arena_alloc(4 * m);
+  uint32_t* vals2 = (uint32_t*)ctx->arena_alloc(4 * m);
+  uint32_t* first = (uint32_t*)ctx->arena_alloc(4 * (size_t)n_keys * 2);
+  uint8_t* buckets = (uint8_t*)ctx->arena_alloc((size_t)n_slots * 128);
+  uint8_t* heads = (uint8_t*)ctx->arena_alloc(n_chunks * 128);
+  uint8_t* tails = (uint8_t*)ctx->arena_alloc(n_chunks * 128);
+  uint32_t* head_key = (uint32_t*)ctx->arena_alloc(n_chunks * 4);
+  uint32_t* tail_key = (uint32_t*)ctx->arena_alloc(n_chunks * 4);
+  const int seg = per_w >= RED_SEG ? RED_SEG : (int)per_w;
+  const uint32_t red_threads = n_slots / seg, per_window_parts = per_w / seg;
+  uint8_t* partial = (uint8_t*)ctx->arena_alloc((size_t)red_threads * 128);
+  uint8_t* window_sums = (uint8_t*)ctx->arena_alloc((size_t)W * 128);
+  size_t sort_bytes = 0;
+  cub::DoubleBuffer<uint32_t> dk(keys, keys2), dv(vals, vals2);
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, dk, dv, (int64_t)m, 0, key_bits, st);
+  void* sort_tmp = ctx->arena_alloc(sort_bytes);
+  if (!keys || !vals || !keys2 || !vals2 || !first || !buckets || !heads || !tails || !head_key || !tail_key ||
+      !partial || !window_sums || !sort_tmp)
+    return ctx->fail(QZ_ERR_ALLOC, "MSM scratch");
+  uint32_t* last = first + n_keys;
+
+  QZ_LAUNCH(ctx, msm_digits, (unsigned)((n + 255) / 256), 256, 0, scalars_dev, (uint32_t)n, c, W, keys, vals);
+  QZ_CUDA(ctx, cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, dk, dv, (int64_t)m, 0, key_bits, st));
+  ctx->launches += 2 + (key_bits + 7) / 8;  // CUB: histogram + one onesweep pass per 8 key bits (approximate)
+  const uint32_t* skeys = dk.Current();
+  const uint32_t* svals = dv.Current();
+  QZ_CUDA(ctx, cudaMemsetAsync(first, 0, 4 * (size_t)n_keys * 2, st));
+  QZ_CUDA(ctx, cudaMemsetAsync(buckets, 0, (size_t)n_slots * 128, st));
+  {
+    unsigned grid = (unsigned)std::min<uint64_t>((m + 255) / 256, (uint64_t)ctx->sm_count * 16);
+    QZ_LAUNCH(ctx, msm_bounds, grid, 256, 0, skeys, m, first, last);
+  }
+  QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k0, st));
+  QZ_LAUNCH(ctx, msm_accumulate, (unsigned)((n_chunks + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, skeys, svals,
+            m, bases, c, buckets, heads, tails, head_key, tail_key);
+  QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k1, st));
+  QZ_LAUNCH(ctx, msm_bucket_finish, (n_slots + 127) / 128, 128, 0, first, last, m, c, W, heads, tails, head_key,
+            tail_key, buckets);
+  QZ_LAUNCH(ctx, msm_bucket_reduce, (red_threads + 127) / 128, 128, 0, buckets, c, W, seg, partial);
+  QZ_LAUNCH(ctx, msm_window_sum, W, 128, 0, partial, per_window_parts, window_sums);
+  QZ_LAUNCH(ctx, msm_combine, 1, 1, 0, window_sums, c, W, out_xyzz_dev, out_affine_dev);
+  return QZ_OK;
+}
+
+int msm_sum_points_launch(qz_ctx* ctx, const uint8_t* pts_dev, int n, uint8_t* out_affine_dev) {
+  QZ_LAUNCH(ctx, msm_sum_points, 1, 1, 0, pts_dev, n, out_affine_dev);
+  return QZ_OK;
+}
+
+}  // namespace qz
+
+extern "C" {
+
+int qz_srs_upload(qz_ctx* ctx, const uint8_t* xy, size_t n, qz_srs** out) {
+  if (!ctx || !out || (n && !xy)) return QZ_ERR_INVALID_ARG;
+  QZ_CUDA(ctx, cudaSetDevice(ctx->device));
+  qz_srs* s = new (std::nothrow) qz_srs{ctx, nullptr, n};
+  if (!s) return ctx->fail(QZ_ERR_ALLOC, "srs handle");
+  cudaError_t e = cudaMalloc((void**)&s->bases, n ? n * 64 : 64);
+  if (e != cudaSuccess) {
+    delete s;
+    return ctx->fail(QZ_ERR_ALLOC, "cudaMalloc(srs)", e);
+  }
+  if (n) {
+    e = cudaMemcpyAsync(s->bases, xy, n * 64, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      cudaFree(s->bases);
+      delete s;
+      return ctx->fail(QZ_ERR_CUDA, "srs upload", e);
+    }
+  }
+  *out = s;
+  return QZ_OK;
+}
+
+int qz_srs_generate(qz_ctx* ctx, const uint8_t g_xy[64], const uint8_t tau[32], size_t n, qz_srs** out) {
+  if (!ctx || !out || !g_xy || !tau) return QZ_ERR_INVALID_ARG;
+  QZ_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->arena_reset();
+  qz_srs* s = new (std::nothrow) qz_srs{ctx, nullptr, n};
+  if (!s) return ctx->fail(QZ_ERR_ALLOC, "srs handle");
+  cudaError_t e = cudaMalloc((void**)&s->bases, n ? n * 64 : 64);
+  if (e != cudaSuccess) {
+    delete s;
+    return ctx->fail(QZ_ERR_ALLOC, "cudaMalloc(srs)", e);
+  }
+  uint8_t* pow_bases = (uint8_t*)ctx->arena_alloc(32 * 64);
+  uint8_t* table = (uint8_t*)ctx->arena_alloc((size_t)32 * 255 * 64);
+  if (!pow_bases || !table) {
+    cudaFree(s->bases);
+    delete s;
+    return ctx->fail(QZ_ERR_ALLOC, "srs table");
+  }
+  Affine g;
+  memcpy(g.x.v, g_xy, 32);
+  memcpy(g.y.v, g_xy + 32, 32);
+  Fr t;
+  memcpy(t.v, tau, 32);
+  *out = s;  // handed to the caller even on a later launch error so it can be freed
+  QZ_LAUNCH(ctx, srs_table_bases, 1, 32, 0, g, pow_bases);
+  QZ_LAUNCH(ctx, srs_table_fill, (32 * 255 + 127) / 128, 128, 0, pow_bases, table);
+  if (n) {
+    uint64_t threads = (n + SRS_CHUNK - 1) / SRS_CHUNK;
+    QZ_LAUNCH(ctx, srs_generate, (unsigned)((threads + 127) / 128), 128, 0, table, t, (uint64_t)n, s->bases);
+  }
+  QZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return QZ_OK;
+}
+
+void qz_srs_free(qz_srs* s) {
+  if (!s) return;
+  cudaSetDevice(s->ctx->device);
+  cudaFree(s->bases);
+  delete s;
+}
+size_t qz_srs_len(const qz_srs* s) { return s ? s->n : 0; }
+
+int qz_srs_download(qz_ctx* ctx, const qz_srs* s, size_t first, size_t count, uint8_t* out_xy) {
+  if (!ctx || !s || !out_xy || first + count > s->n) return QZ_ERR_INVALID_ARG;
+  if (!count) return QZ_OK;
+  QZ_CUDA(ctx, cudaMemcpyAsync(out_xy, s->bases + first * 64, count * 64, cudaMemcpyDeviceToHost, ctx->stream));
+  QZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return QZ_OK;
+}
+
+int qz_msm(qz_ctx* ctx, const qz_srs* srs, const void* scalars, size_t n_scalars, int on_device, uint8_t out_xy[64]) {
+  if (!ctx || !srs || !out_xy || (n_scalars && !scalars)) return QZ_ERR_INVALID_ARG;
+  QZ_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->arena_reset();
+  const size_t n = std::min(n_scalars, srs->n);  // msm_unchecked zips to the shorter slice
+  cudaStream_t st = ctx->stream;
+  QZ_CUDA(ctx, cudaEventRecord(ctx->ev_call0, st));
+  const uint4* sdev = (const uint4*)scalars;
+  if (!on_device && n) {
+    void* p = ctx->arena_alloc(32 * n);
+    if (!p) return ctx->fail(QZ_ERR_ALLOC, "scalars");
+    QZ_CUDA(ctx, cudaMemcpyAsync(p, scalars, 32 * n, cudaMemcpyHostToDevice, st));
+    sdev = (const uint4*)p;
+  }
+  uint8_t* out_dev = (uint8_t*)ctx->arena_alloc(64);
+  if (!out_dev) return ctx->fail(QZ_ERR_ALLOC, "result");
+  QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k0, st));
+  QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k1, st));
+  int rc = msm_device(ctx, srs->bases, sdev, n, nullptr, out_dev);
+  if (rc) return rc;
+  QZ_CUDA(ctx, cudaMemcpyAsync(out_xy, out_dev, 64, cudaMemcpyDeviceToHost, st));
+  QZ_CUDA(ctx, cudaEventRecord(ctx->ev_call1, st));
+  QZ_CUDA(ctx, cudaStreamSynchronize(st));
+  cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev_call0, ctx->ev_call1);
+  cudaEventElapsedTime(&ctx->last_ms[1], ctx->ev_k0, ctx->ev_k1);
+  return QZ_OK;
+}
+
+int qz_kzg_commit(qz_ctx* ctx, const qz_srs* srs, const void* coeffs, size_t n_coeffs, int on_device,
+                  uint8_t out_xy[64]) {
+  if (!ctx || !srs) return QZ_ERR_INVALID_ARG;
+  if (n_coeffs > srs->n) return ctx->fail(QZ_ERR_DEGREE, "Polynomial degree exceeds max degree");  // kzg.rs:62-65
+  return qz_msm(ctx, srs, coeffs, n_coeffs, on_device, out_xy);
+}
+
+int qz_kzg_open(qz_ctx* ctx, const qz_srs* srs, const void* coeffs, size_t n_coeffs, int on_device, const uint8_t x[32],
+                uint8_t out_y[32], uint8_t out_proof_xy[64]) {
+  if (!ctx || !srs || !x || !out_y || !out_proof_xy || (n_coeffs && !coeffs)) return QZ_ERR_INVALID_ARG;
+  // the quotient has n_coeffs - 1 coefficients; commit() asserts it fits the SRS (kzg.rs:62-65 via :89)
+  if (n_coeffs > srs->n + 1) return ctx->fail(QZ_ERR_DEGREE, "Polynomial degree exceeds max degree");
+  QZ_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->arena_reset();
+  cudaStream_t st = ctx->stream;
+  QZ_CUDA(ctx, cudaEventRecord(ctx->ev_call0, st));
+  QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k0, st));
+  QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k1, st));
+  uint8_t* res = (uint8_t*)ctx->arena_alloc(128);  // y (32) ‖ pad ‖ proof (64)
+  if (!res) return ctx->fail(QZ_ERR_ALLOC, "result");
+  QZ_CUDA(ctx, cudaMemsetAsync(res, 0, 128, st));
+  if (n_coeffs > 0) {
+    const uint4* pdev = (const uint4*)coeffs;
+    if (!on_device) {
+      void* p = ctx->arena_alloc(32 * n_coeffs);
+      if (!p) return ctx->fail(QZ_ERR_ALLOC, "coeffs");
+      QZ_CUDA(ctx, cudaMemcpyAsync(p, coeffs, 32 * n_coeffs, cudaMemcpyHostToDevice, st));
+      pdev = (const uint4*)p;
+    }
+    Fr xv;
+    memcpy(xv.v, x, 32);
+    const uint64_t n = n_coeffs, nchunks = (n + OPEN_CHUNK - 1) / OPEN_CHUNK;
+    const int group = 64;
+    const uint64_t ngroups = (nchunks + group - 1) / group;
+    Fr* h = (Fr*)ctx->arena_alloc(32 * nchunks);
+    Fr* carry = (Fr*)ctx->arena_alloc(32 * nchunks);
+    Fr* gh = (Fr*)ctx->arena_alloc(32 * ngroups);
+    Fr* gcarry = (Fr*)ctx->arena_alloc(32 * ngroups);
+    Fr* pw = (Fr*)ctx->arena_alloc(64);
+    uint4* q = (uint4*)ctx->arena_alloc(32 * std::max<uint64_t>(1, n - 1));
+    if (!h || !carry || !gh || !gcarry || !pw || !q) return ctx->fail(QZ_ERR_ALLOC, "open scratch");
+    QZ_LAUNCH(ctx, fr_pow_small, 1, 1, 0, xv, (uint32_t)OPEN_CHUNK, pw);
+    QZ_LAUNCH(ctx, fr_pow_small, 1, 1, 0, xv, (uint32_t)(OPEN_CHUNK * group), pw + 1);
+    Fr xL, xG;
+    QZ_CUDA(ctx, cudaMemcpyAsync(&xL, pw, 32, cudaMemcpyDeviceToHost, st));
+    QZ_CUDA(ctx, cudaMemcpyAsync(&xG, pw + 1, 32, cudaMemcpyDeviceToHost, st));
+    QZ_CUDA(ctx, cudaStreamSynchronize(st));
+    QZ_LAUNCH(ctx, open_local, (unsigned)((nchunks + 127) / 128), 128, 0, pdev, n, xv, h);
+    QZ_LAUNCH(ctx, open_carry_level, (unsigned)((ngroups + 255) / 256), 256, 0, h, nchunks, xL, group, gh);
+    QZ_LAUNCH(ctx, open_carry_serial, 1, 1, 0, gh, ngroups, xG, gcarry);
+    QZ_LAUNCH(ctx, open_carry_expand, (unsigned)((ngroups + 255) / 256), 256, 0, h, nchunks, xL, group, gcarry, carry);
+    QZ_LAUNCH(ctx, open_write, (unsigned)((nchunks + 127) / 128), 128, 0, pdev, n, xv, carry, q, (Fr*)res);
+    // commit(q): trailing zero coefficients contribute nothing, so trimming (DensePolynomial) is value-neutral
+    const size_t qn = std::min<size_t>(n - 1, srs->n);
+    int rc = msm_device(ctx, srs->bases, q, qn, nullptr, res + 64);
+    if (rc) return rc;
+  }
+  uint8_t* pin = (uint8_t*)ctx->pinned_buf(128);
+  if (!pin) return ctx->fail(QZ_ERR_ALLOC, "pinned");
+  QZ_CUDA(ctx, cudaMemcpyAsync(pin, res, 128, cudaMemcpyDeviceToHost, st));
+  QZ_CUDA(ctx, cudaEventRecord(ctx->ev_call1, st));
+  QZ_CUDA(ctx, cudaStreamSynchronize(st));
+  memcpy(out_y, pin, 32);
+  memcpy(out_proof_xy, pin + 64, 64);
+  cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev_call0, ctx->ev_call1);
+  cudaEventElapsedTime(&ctx->last_ms[1], ctx->ev_k0, ctx->ev_k1);
+  return QZ_OK;
+}
+
+}  // extern "C"

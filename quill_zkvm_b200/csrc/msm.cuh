@@ -1,0 +1,20 @@
+// Internal interface of the MSM pipeline (msm.cu), shared with the multi-GPU layer (comm.cu).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include "ctx.cuh"
+
+struct qz_srs {
+  qz_ctx* ctx;
+  uint8_t* bases;  // n affine G1 points on the device, 64 B each (x ‖ y Montgomery; all-zero = infinity)
+  size_t n;
+};
+
+namespace qz {
+// sum_i scalars[i] * bases[i], i < n; scalars are Montgomery Fr on the device.  The result is written to device
+// memory as XYZZ (128 B) and/or affine (64 B); either pointer may be null.  Asynchronous on ctx->stream.
+int msm_device(qz_ctx* ctx, const uint8_t* bases, const uint4* scalars_dev, size_t n, uint8_t* out_xyzz_dev,
+               uint8_t* out_affine_dev);
+// affine(sum of n XYZZ points on the device) -> out_affine_dev (64 B)
+int msm_sum_points_launch(qz_ctx* ctx, const uint8_t* pts_dev, int n, uint8_t* out_affine_dev);
+}  // namespace qz

@@ -1,0 +1,629 @@
+// Linear-time sumcheck / zero-check prover on the device.
+//
+// Reference: SumcheckProof::prove (hyperplonk/src/piops/sumcheck.rs:28-114), ZeroCheckProof::prove
+// (hyperplonk/src/piops/zerocheck.rs:14-49), fast_eq_eval_hypercube (hyperplonk/src/utils/eq_eval.rs:6-31).
+//
+// Structure (B200-first, not a translation of the reference's per-pair DensePolynomial loop):
+//   * the tables stay in HBM for the whole proof; a round is ONE streaming pass that folds the previous round's
+//     challenge into the tables (reads 4 consecutive elements, writes 2) and, in the same pass, evaluates the round
+//     polynomial at X = 0..d on the freshly folded pairs -- 128 B of HBM traffic per input element over the proof;
+//   * per-thread partial sums -> warp shuffles -> one partial per block -> a one-block "finalize" kernel that sums the
+//     partials, interpolates to monomial coefficients, serialises them and runs the blake3 transcript ON THE DEVICE,
+//     leaving the next challenge in device memory: no host round trip between rounds;
+//   * once a table is down to 2^SC_TAIL_LOG elements a single block finishes all remaining rounds in one launch.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+#include "ctx.cuh"
+#include "sumcheck.cuh"
+
+namespace qz {
+
+constexpr int SC_TAIL_LOG = 11;
+constexpr int SC_THREADS = 256;
+
+// ---- loads ---------------------------------------------------------------------------------------------------------------
+QZ_DEV Fr ld_elem(const uint4* base, uint64_t e) { return fp_load<FrParams>(base + 2 * e); }
+QZ_DEV void st_elem(uint4* base, uint64_t e, const Fr& v) { fp_store<FrParams>(base + 2 * e, v); }
+
+// fetch pair p of table t, folding the pending challenge first when `fold` (sumcheck.rs:81-92 fused into the next
+// round's pass): lo' = a0 + r (a1 - a0), hi' = a2 + r (a3 - a2), both written to the half-size table.
+QZ_DEV void fetch_pair(const uint4* in, uint4* out, uint64_t p, bool fold, const Fr& r, Fr& lo, Fr& hi) {
+  if (fold) {
+    Fr a0 = ld_elem(in, 4 * p), a1 = ld_elem(in, 4 * p + 1), a2 = ld_elem(in, 4 * p + 2), a3 = ld_elem(in, 4 * p + 3);
+    lo = fp_add<FrParams>(a0, fp_mul<FrParams>(r, fp_sub<FrParams>(a1, a0)));
+    hi = fp_add<FrParams>(a2, fp_mul<FrParams>(r, fp_sub<FrParams>(a3, a2)));
+    st_elem(out, 2 * p, lo);
+    st_elem(out, 2 * p + 1, hi);
+  } else {
+    lo = ld_elem(in, 2 * p);
+    hi = ld_elem(in, 2 * p + 1);
+  }
+}
+
+// ---- round kernel, fast path: h = g_0 * g_1 * ... * g_{K-1} --------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(SC_THREADS) sc_round_prod(ScTables tabs, uint64_t n_pairs, int fold,
+                                                           const ScHead* head, Fr* partials) {
+  __shared__ Fr s_warp[32];
+  Fr acc[K + 1];
+#pragma unroll
+  for (int x = 0; x <= K; x++) acc[x] = fp_zero<FrParams>();
+  Fr r = fp_zero<FrParams>();
+  if (fold) r = head->r;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += stride) {
+    Fr cur[K], df[K];
+#pragma unroll
+    for (int t = 0; t < K; t++) {
+      Fr hi;
+      fetch_pair(tabs.in[t], tabs.out[t], p, fold != 0, r, cur[t], hi);
+      df[t] = fp_sub<FrParams>(hi, cur[t]);
+    }
+#pragma unroll
+    for (int x = 0; x <= K; x++) {
+      Fr prod = cur[0];
+#pragma unroll
+      for (int t = 1; t < K; t++) prod = fp_mul<FrParams>(prod, cur[t]);
+      acc[x] = fp_add<FrParams>(acc[x], prod);
+      if (x < K) {
+#pragma unroll
+        for (int t = 0; t < K; t++) cur[t] = fp_add<FrParams>(cur[t], df[t]);  // g_t(x+1) = g_t(x) + (hi - lo)
+      }
+    }
+  }
+#pragma unroll
+  for (int x = 0; x <= K; x++) block_sum_to(acc[x], s_warp, &partials[(size_t)blockIdx.x * (K + 1) + x]);
+}
+
+// ---- round kernel, generic expression tree -----------------------------------------------------------------------------------
+QZ_DEV void generic_pair(const ScTables& tabs, uint64_t p, bool fold, const Fr& r, const uint32_t* s_ops,
+                         uint32_t n_ops, int k, int d, const Fr* consts, Fr* acc) {
+  Fr cur[SC_MAX_K], df[SC_MAX_K];
+  for (int t = 0; t < k; t++) {
+    Fr hi;
+    fetch_pair(tabs.in[t], tabs.out[t], p, fold, r, cur[t], hi);
+    df[t] = fp_sub<FrParams>(hi, cur[t]);
+  }
+  for (int x = 0; x <= d; x++) {
+    acc[x] = fp_add<FrParams>(acc[x], sc_eval_program(s_ops, n_ops, consts, cur));
+    if (x < d)
+      for (int t = 0; t < k; t++) cur[t] = fp_add<FrParams>(cur[t], df[t]);
+  }
+}
+
+__global__ void __launch_bounds__(SC_THREADS) sc_round_generic(ScTables tabs, uint64_t n_pairs, int fold,
+                                                              const ScHead* head, const ScProgram* prog,
+                                                              const Fr* consts, Fr* partials) {
+  __shared__ Fr s_warp[32];
+  __shared__ uint32_t s_ops[SC_MAX_OPS];
+  const uint32_t n_ops = prog->n_ops;
+  const int d = (int)prog->degree, k = (int)prog->k;
+  for (uint32_t i = threadIdx.x; i < n_ops; i += blockDim.x) s_ops[i] = prog->ops[i];
+  __syncthreads();
+  Fr acc[SC_MAX_COEFFS];
+  for (int x = 0; x <= d; x++) acc[x] = fp_zero<FrParams>();
+  Fr r = fp_zero<FrParams>();
+  if (fold) r = head->r;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += stride)
+    generic_pair(tabs, p, fold != 0, r, s_ops, n_ops, k, d, consts, acc);
+  for (int x = 0; x <= d; x++) block_sum_to(acc[x], s_warp, &partials[(size_t)blockIdx.x * (d + 1) + x]);
+}
+
+// ---- finalize: sum `n_parts` partial vectors, close the round (transcript on the device) -----------------------------------
+__global__ void __launch_bounds__(SC_THREADS) sc_finalize(const Fr* partials, int n_parts, int d, ScHead* head,
+                                                         const Fr* vinv, Fr* out_coeffs_row, uint32_t* out_len,
+                                                         Fr* out_point_slot, int max_coeffs) {
+  __shared__ Fr s_warp[32];
+  __shared__ Fr s_evals[SC_MAX_COEFFS];
+  __shared__ Fr s_coef[SC_MAX_COEFFS];
+  __shared__ __align__(16) uint8_t s_msg[8 + 32 * SC_MAX_COEFFS];
+  for (int x = 0; x <= d; x++) {
+    Fr v = fp_zero<FrParams>();
+    for (int b = threadIdx.x; b < n_parts; b += blockDim.x) v = fp_add<FrParams>(v, partials[(size_t)b * (d + 1) + x]);
+    block_sum_to(v, s_warp, &s_evals[x]);
+  }
+  sc_round_close(head, vinv, d, s_evals, s_coef, s_msg, out_coeffs_row, out_len, out_point_slot, max_coeffs);
+}
+
+// reduce block partials to one vector per rank (sharded mode: the vectors are all-gathered, then sc_finalize)
+__global__ void __launch_bounds__(SC_THREADS) sc_reduce_partials(const Fr* partials, int n_parts, int d, Fr* out) {
+  __shared__ Fr s_warp[32];
+  for (int x = 0; x <= d; x++) {
+    Fr v = fp_zero<FrParams>();
+    for (int b = threadIdx.x; b < n_parts; b += blockDim.x) v = fp_add<FrParams>(v, partials[(size_t)b * (d + 1) + x]);
+    block_sum_to(v, s_warp, &out[x]);
+  }
+}
+
+// ---- tail: one block runs every remaining round -------------------------------------------------------------------------------
+// in[t]: current tables of `size` elements; bufa/bufb: scratch of >= size/2 elements per table.
+struct ScTailBufs {
+  uint4* a[SC_MAX_K];
+  uint4* b[SC_MAX_K];
+};
+__global__ void __launch_bounds__(SC_THREADS) sc_tail(ScTables tabs, ScTailBufs bufs, uint64_t size, int pending_fold,
+                                                     ScHead* head, const ScProgram* prog, const Fr* consts,
+                                                     const Fr* vinv, Fr* out_coeffs, uint32_t* out_lens,
+                                                     Fr* out_point, int round, int max_coeffs) {
+  __shared__ Fr s_warp[32];
+  __shared__ Fr s_evals[SC_MAX_COEFFS];
+  __shared__ Fr s_coef[SC_MAX_COEFFS];
+  __shared__ __align__(16) uint8_t s_msg[8 + 32 * SC_MAX_COEFFS];
+  __shared__ uint32_t s_ops[SC_MAX_OPS];
+  const uint32_t n_ops = prog->n_ops;
+  const int d = (int)prog->degree, k = (int)prog->k;
+  for (uint32_t i = threadIdx.x; i < n_ops; i += blockDim.x) s_ops[i] = prog->ops[i];
+  __syncthreads();
+  const uint4* cur[SC_MAX_K];
+  for (int t = 0; t < k; t++) cur[t] = tabs.in[t];
+  int flip = 0;
+  while (true) {
+    if (pending_fold) {  // sumcheck.rs:81-92
+      const Fr r = head->r;
+      for (int t = 0; t < k; t++) {
+        uint4* dst = flip ? bufs.b[t] : bufs.a[t];
+        for (uint64_t p = threadIdx.x; p < size / 2; p += blockDim.x) {
+          Fr lo = ld_elem(cur[t], 2 * p), hi = ld_elem(cur[t], 2 * p + 1);
+          st_elem(dst, p, fp_add<FrParams>(lo, fp_mul<FrParams>(r, fp_sub<FrParams>(hi, lo))));
+        }
+        cur[t] = dst;
+      }
+      flip ^= 1;
+      size >>= 1;
+      __syncthreads();
+    }
+    if (size == 1) break;
+    // round polynomial over size/2 pairs (sumcheck.rs:53-70)
+    Fr acc[SC_MAX_COEFFS];
+    for (int x = 0; x <= d; x++) acc[x] = fp_zero<FrParams>();
+    ScTables view;
+    for (int t = 0; t < k; t++) {
+      view.in[t] = cur[t];
+      view.out[t] = nullptr;
+    }
+    const Fr zero = fp_zero<FrParams>();
+    for (uint64_t p = threadIdx.x; p < size / 2; p += blockDim.x)
+      generic_pair(view, p, false, zero, s_ops, n_ops, k, d, consts, acc);
+    for (int x = 0; x <= d; x++) block_sum_to(acc[x], s_warp, &s_evals[x]);
+    sc_round_close(head, vinv, d, s_evals, s_coef, s_msg, out_coeffs + (size_t)round * max_coeffs, out_lens + round,
+                   out_point + round, max_coeffs);
+    round++;
+    pending_fold = 1;
+  }
+  if (threadIdx.x == 0) {  // sumcheck.rs:94-100: h(g_1(r), ..., g_k(r))
+    Fr fin[SC_MAX_K];
+    for (int t = 0; t < k; t++) fin[t] = ld_elem(cur[t], 0);
+    head->evaluation = sc_eval_program(s_ops, n_ops, consts, fin);
+  }
+}
+
+// ---- small helper kernels ---------------------------------------------------------------------------------------------------------
+// absorb num_vars (u64 LE) and claimed_sum (sumcheck.rs:35-36)
+__global__ void sc_header(ScHead* head, uint64_t num_vars, Fr claimed_sum) {
+  uint8_t b[32];
+  for (int i = 0; i < 8; i++) b[i] = (uint8_t)(num_vars >> (8 * i));
+  tr_absorb(head->tstate, b, 8);
+  fr_to_le_bytes(claimed_sum, b);
+  tr_absorb(head->tstate, b, 32);
+}
+// zerocheck.rs:20-22: n challenges drawn before the sumcheck header
+__global__ void zc_draw_point(ScHead* head, int n, Fr* z) {
+  for (int i = 0; i < n; i++) z[i] = tr_draw_fr(head->tstate);
+}
+// eq(x, z) tables over the low `a` variables and the remaining high variables
+__global__ void eq_half_tables(const Fr* z, int n, int a, Fr* lo_tab, Fr* hi_tab) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t nlo = (uint64_t)1 << a, nhi = (uint64_t)1 << (n - a);
+  if (i >= nlo + nhi) return;
+  const bool is_lo = i < nlo;
+  const uint64_t idx = is_lo ? i : i - nlo;
+  const int first = is_lo ? 0 : a, cnt = is_lo ? a : n - a;
+  Fr acc = fp_one<FrParams>();
+  const Fr one = fp_one<FrParams>();
+  for (int j = 0; j < cnt; j++) {
+    Fr zj = z[first + j];
+    Fr f = ((idx >> j) & 1) ? zj : fp_sub<FrParams>(one, zj);
+    acc = fp_mul<FrParams>(acc, f);
+  }
+  (is_lo ? lo_tab : hi_tab)[idx] = acc;
+}
+// eq_eval.rs:6-31: table[i] = prod_j (bit_j(i) ? z_j : 1 - z_j) = lo_tab[i mod 2^a] * hi_tab[i >> a]
+// `base` is the global index of out[0] (a rank's shard of the table starts at rank * shard_len).
+__global__ void __launch_bounds__(256) eq_expand(const Fr* lo_tab, const Fr* hi_tab, int a, uint64_t base,
+                                                uint64_t n_elems, uint4* out) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, mask = ((uint64_t)1 << a) - 1;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += stride) {
+    const uint64_t g = base + i;
+    st_elem(out, i, fp_mul<FrParams>(lo_tab[g & mask], hi_tab[g >> a]));
+  }
+}
+// zerocheck.rs:34-40: evaluation <- evaluation / eq_eval(z, point)
+__global__ void zc_finish(ScHead* head, const Fr* z, const Fr* point, int n) {
+  const Fr one = fp_one<FrParams>();
+  Fr e = one;
+  for (int i = 0; i < n; i++) {  // eq_eval.rs:33-43
+    Fr x = z[i], r = point[i];
+    Fr term = fp_add<FrParams>(fp_mul<FrParams>(x, r),
+                               fp_mul<FrParams>(fp_sub<FrParams>(one, x), fp_sub<FrParams>(one, r)));
+    e = fp_mul<FrParams>(e, term);
+  }
+  head->evaluation = fp_mul<FrParams>(head->evaluation, fp_inv<FrParams>(e));
+}
+// Inverse Vandermonde on nodes 0..d: vinv[i*(d+1)+j] = coefficient of X^i in the Lagrange basis polynomial L_j
+__global__ void sc_build_vinv(int d, Fr* vinv) {
+  const int j = threadIdx.x;
+  if (j > d) return;
+  Fr small[SC_MAX_COEFFS];  // Montgomery form of 0..d
+  small[0] = fp_zero<FrParams>();
+  for (int i = 1; i <= d; i++) small[i] = fp_add<FrParams>(small[i - 1], fp_one<FrParams>());
+  Fr c[SC_MAX_COEFFS];  // numerator prod_{m != j} (X - m)
+  c[0] = fp_one<FrParams>();
+  int len = 1;
+  Fr denom = fp_one<FrParams>();
+  for (int m = 0; m <= d; m++) {
+    if (m == j) continue;
+    c[len] = fp_zero<FrParams>();
+    for (int i = len; i >= 0; i--) {  // c <- c * (X - m)
+      Fr lower = i > 0 ? c[i - 1] : fp_zero<FrParams>();
+      c[i] = fp_sub<FrParams>(lower, fp_mul<FrParams>(small[m], c[i]));
+    }
+    len++;
+    Fr diff = j > m ? small[j - m] : fp_neg<FrParams>(small[m - j]);
+    denom = fp_mul<FrParams>(denom, diff);
+  }
+  Fr inv = fp_inv<FrParams>(denom);
+  for (int i = 0; i <= d; i++) vinv[i * (d + 1) + j] = fp_mul<FrParams>(c[i], inv);
+}
+__global__ void sc_set_state(ScHead* head, const uint8_t* state) {
+  for (int i = 0; i < 32; i++) head->tstate[i] = state[i];
+  head->r = fp_zero<FrParams>();
+  head->evaluation = fp_zero<FrParams>();
+}
+
+}  // namespace qz
+
+// =====================================================================================================================
+// host side
+// =====================================================================================================================
+using namespace qz;
+
+namespace {
+
+struct Compiled {
+  ScProgram prog;
+  std::vector<uint32_t> active;  // active[j] = original table index of dense input j
+  int product_k = 0;             // > 0: h is a product of `product_k` distinct inputs (fast path)
+};
+
+// VirtualPolyExpr -> postfix program over densely renumbered inputs; degree: Input 1, Const 0, Add max, Mul sum
+int compile_expr(qz_ctx* ctx, const qz_expr_node* nodes, size_t n_nodes, size_t k, size_t n_consts, Compiled& out) {
+  if (n_nodes == 0) return ctx->fail(QZ_ERR_EXPR, "empty expression");
+  std::vector<int> remap(k, -1);
+  std::vector<uint32_t> ops;
+  bool ok = true;
+  bool pure_product = true;
+  std::vector<uint32_t> prod_inputs;
+  struct Rec {
+    const qz_expr_node* nodes;
+    size_t n_nodes, k, n_consts;
+    std::vector<int>& remap;
+    std::vector<uint32_t>& active;
+    std::vector<uint32_t>& ops;
+    bool& ok;
+    bool& pure_product;
+    std::vector<uint32_t>& prod_inputs;
+    int max_stack = 0;
+    // returns degree; depth = current stack height before evaluating this node
+    int go(size_t idx, int depth, int guard) {
+      if (!ok || idx >= n_nodes || guard > 4096 || ops.size() > (size_t)SC_MAX_OPS) {
+        ok = false;
+        return 0;
+      }
+      const qz_expr_node& e = nodes[idx];
+      if (depth + 1 > max_stack) max_stack = depth + 1;
+      switch (e.op) {
+        case QZ_EX_INPUT: {
+          if (e.a >= k) {
+            ok = false;
+            return 0;
+          }
+          if (remap[e.a] < 0) {
+            remap[e.a] = (int)active.size();
+            active.push_back(e.a);
+          }
+          ops.push_back((SC_OP_IN << 16) | (uint32_t)remap[e.a]);
+          prod_inputs.push_back(e.a);
+          return 1;
+        }
+        case QZ_EX_CONST: {
+          if (e.a >= n_consts || e.a > 0xffff) {
+            ok = false;
+            return 0;
+          }
+          ops.push_back((SC_OP_CONST << 16) | e.a);
+          pure_product = false;
+          return 0;
+        }
+        case QZ_EX_ADD:
+        case QZ_EX_MUL: {
+          if (e.a >= idx || e.b >= idx) {  // children must precede parents
+            ok = false;
+            return 0;
+          }
+          int da = go(e.a, depth, guard + 1), db = go(e.b, depth + 1, guard + 1);
+          ops.push_back(((e.op == QZ_EX_ADD ? SC_OP_ADD : SC_OP_MUL) << 16));
+          if (e.op == QZ_EX_ADD) pure_product = false;
+          return e.op == QZ_EX_ADD ? std::max(da, db) : da + db;
+        }
+        default: ok = false; return 0;
+      }
+    }
+  } rec{nodes, n_nodes, k, n_consts, remap, out.active, ops, ok, pure_product, prod_inputs};
+  int deg = rec.go(n_nodes - 1, 0, 0);
+  if (!ok) return ctx->fail(QZ_ERR_EXPR, "malformed expression tree");
+  if (ops.size() > (size_t)SC_MAX_OPS) return ctx->fail(QZ_ERR_EXPR, "expression too large (ops)");
+  if (rec.max_stack > SC_MAX_STACK) return ctx->fail(QZ_ERR_EXPR, "expression too deep (stack)");
+  if (out.active.size() > (size_t)SC_MAX_K) return ctx->fail(QZ_ERR_EXPR, "too many tables referenced by h");
+  if (deg > SC_MAX_DEG) return ctx->fail(QZ_ERR_EXPR, "expression degree too high");
+  memset(&out.prog, 0, sizeof out.prog);
+  out.prog.n_ops = (uint32_t)ops.size();
+  out.prog.degree = (uint32_t)deg;
+  out.prog.k = (uint32_t)out.active.size();
+  out.prog.n_consts = (uint32_t)n_consts;
+  memcpy(out.prog.ops, ops.data(), ops.size() * 4);
+  out.product_k = 0;
+  if (pure_product && prod_inputs.size() == out.active.size() && prod_inputs.size() >= 1 && prod_inputs.size() <= 4)
+    out.product_k = (int)prod_inputs.size();  // distinct inputs, each used once
+  return QZ_OK;
+}
+
+int get_vinv(qz_ctx* ctx, int d, Fr** out) {
+  auto it = ctx->vinv.find(d);
+  if (it != ctx->vinv.end()) {
+    *out = (Fr*)it->second;
+    return QZ_OK;
+  }
+  void* p = nullptr;
+  QZ_CUDA(ctx, cudaMalloc(&p, sizeof(Fr) * (d + 1) * (d + 1)));
+  QZ_LAUNCH(ctx, sc_build_vinv, 1, 64, 0, d, (Fr*)p);
+  ctx->vinv[d] = p;
+  *out = (Fr*)p;
+  return QZ_OK;
+}
+
+int round_grid(qz_ctx* ctx, uint64_t n_pairs, int blocks_per_sm) {
+  uint64_t want = (n_pairs + SC_THREADS - 1) / SC_THREADS;
+  uint64_t cap = (uint64_t)ctx->sm_count * blocks_per_sm;
+  return (int)std::max<uint64_t>(1, std::min(want, cap));
+}
+
+}  // namespace
+
+namespace qz {
+
+int comm_allgather(qz_ctx* ctx, const void* send, void* recv, size_t bytes);  // comm.cu
+
+// elements [base, base + n_elems) of eq(., z) over n variables
+int eq_table_device(qz_ctx* ctx, int n, const Fr* z_dev, uint4* out_dev, uint64_t base, uint64_t n_elems) {
+  const int a = n / 2;
+  Fr* lo_tab = (Fr*)ctx->arena_alloc(sizeof(Fr) << a);
+  Fr* hi_tab = (Fr*)ctx->arena_alloc(sizeof(Fr) << (n - a));
+  if (!lo_tab || !hi_tab) return ctx->fail(QZ_ERR_ALLOC, "eq table scratch");
+  const uint64_t small = ((uint64_t)1 << a) + ((uint64_t)1 << (n - a));
+  QZ_LAUNCH(ctx, eq_half_tables, (unsigned)((small + 127) / 128), 128, 0, z_dev, n, a, lo_tab, hi_tab);
+  int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n_elems + 255) / 256, (uint64_t)ctx->sm_count * 8));
+  QZ_LAUNCH(ctx, eq_expand, grid, 256, 0, lo_tab, hi_tab, a, base, n_elems, out_dev);
+  return QZ_OK;
+}
+
+// The whole proof.  `sharded`: `tables` hold this rank's contiguous shard, elements [rank * 2^num_vars / nranks, ...),
+// i.e. the tables are split by the top variables so every (2p, 2p+1) pair is local (sumcheck.rs:56-57).
+int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tables, int tables_on_device,
+                 const qz_expr_node* nodes, size_t n_nodes, const uint8_t* consts, size_t n_consts,
+                 const uint8_t* claimed_sum, uint8_t* state, size_t max_coeffs, uint8_t* out_coeffs,
+                 uint32_t* out_lens, uint8_t* out_point, uint8_t* out_eval, bool zerocheck, uint8_t* out_z,
+                 bool sharded) {
+  if (!ctx || !state || !out_eval || (num_vars && (!out_coeffs || !out_lens || !out_point)))
+    return ctx ? ctx->fail(QZ_ERR_INVALID_ARG, "null pointer") : QZ_ERR_INVALID_ARG;
+  if (num_vars > (size_t)SC_MAX_VARS - 1 || (k && !tables) || (n_nodes && !nodes) || (n_consts && !consts))
+    return ctx->fail(QZ_ERR_INVALID_ARG, "bad sizes");
+  if (!zerocheck && !claimed_sum) return ctx->fail(QZ_ERR_INVALID_ARG, "claimed_sum is null");
+  if (zerocheck && num_vars && !out_z) return ctx->fail(QZ_ERR_INVALID_ARG, "out_z is null");
+  QZ_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->arena_reset();
+
+  // h, or h_hat = Mul(h, Input(eq)) with eq appended as the last store polynomial (zerocheck.rs:27-29)
+  std::vector<qz_expr_node> nd(nodes, nodes + n_nodes);
+  size_t k_total = k;
+  if (zerocheck) {
+    if (n_nodes == 0) return ctx->fail(QZ_ERR_EXPR, "empty expression");
+    uint32_t root = (uint32_t)n_nodes - 1;
+    nd.push_back(qz_expr_node{QZ_EX_INPUT, (uint32_t)k, 0});
+    nd.push_back(qz_expr_node{QZ_EX_MUL, root, root + 1});
+    k_total = k + 1;
+  }
+  Compiled cp;
+  int rc = compile_expr(ctx, nd.data(), nd.size(), k_total, n_consts, cp);
+  if (rc) return rc;
+  const int d = (int)cp.prog.degree, ka = (int)cp.prog.k;
+  if ((size_t)d + 1 > max_coeffs) return ctx->fail(QZ_ERR_EXPR, "deg(h)+1 exceeds max_coeffs");
+  const int mc = (int)max_coeffs;
+  const int G = sharded ? ctx->nranks : 1;
+  if (((uint64_t)1 << num_vars) < (uint64_t)G) return ctx->fail(QZ_ERR_INVALID_ARG, "fewer table entries than ranks");
+  const uint64_t N = ((uint64_t)1 << num_vars) / G;  // entries per table held by this rank
+
+  cudaStream_t st = ctx->stream;
+  QZ_CUDA(ctx, cudaEventRecord(ctx->ev_call0, st));
+
+  // device-resident proof state and outputs
+  ScHead* head = (ScHead*)ctx->arena_alloc(sizeof(ScHead));
+  uint8_t* d_state_in = (uint8_t*)ctx->arena_alloc(32);
+  Fr* d_coeffs = (Fr*)ctx->arena_alloc(sizeof(Fr) * std::max<size_t>(1, num_vars * max_coeffs));
+  uint32_t* d_lens = (uint32_t*)ctx->arena_alloc(4 * std::max<size_t>(1, num_vars));
+  Fr* d_point = (Fr*)ctx->arena_alloc(sizeof(Fr) * std::max<size_t>(1, num_vars));
+  Fr* d_z = (Fr*)ctx->arena_alloc(sizeof(Fr) * std::max<size_t>(1, num_vars));
+  ScProgram* d_prog = (ScProgram*)ctx->arena_alloc(sizeof(ScProgram));
+  Fr* d_consts = (Fr*)ctx->arena_alloc(sizeof(Fr) * std::max<size_t>(1, n_consts));
+  if (!head || !d_state_in || !d_coeffs || !d_lens || !d_point || !d_z || !d_prog || !d_consts)
+    return ctx->fail(QZ_ERR_ALLOC, "sumcheck state");
+  QZ_CUDA(ctx, cudaMemcpyAsync(d_state_in, state, 32, cudaMemcpyHostToDevice, st));
+  QZ_CUDA(ctx, cudaMemcpyAsync(d_prog, &cp.prog, sizeof(ScProgram), cudaMemcpyHostToDevice, st));
+  if (n_consts) QZ_CUDA(ctx, cudaMemcpyAsync(d_consts, consts, 32 * n_consts, cudaMemcpyHostToDevice, st));
+  QZ_LAUNCH(ctx, sc_set_state, 1, 1, 0, head, d_state_in);
+
+  // tables referenced by h: device copies (host input) or the caller's device buffers
+  ScTables tabs;
+  memset(&tabs, 0, sizeof tabs);
+  int eq_slot = -1;
+  for (int j = 0; j < ka; j++) {
+    uint32_t orig = cp.active[j];
+    if (zerocheck && orig == k) {
+      eq_slot = j;
+      continue;
+    }
+    if (!tables[orig]) return ctx->fail(QZ_ERR_INVALID_ARG, "null table");
+    if (tables_on_device) {
+      tabs.in[j] = (const uint4*)tables[orig];
+    } else {
+      void* p = ctx->arena_alloc(32 * N);
+      if (!p) return ctx->fail(QZ_ERR_ALLOC, "table copy");
+      QZ_CUDA(ctx, cudaMemcpyAsync(p, tables[orig], 32 * N, cudaMemcpyHostToDevice, st));
+      tabs.in[j] = (const uint4*)p;
+    }
+  }
+  if (zerocheck) {
+    QZ_LAUNCH(ctx, zc_draw_point, 1, 1, 0, head, (int)num_vars, d_z);  // zerocheck.rs:20-22
+    if (eq_slot >= 0) {
+      void* p = ctx->arena_alloc(32 * N);
+      if (!p) return ctx->fail(QZ_ERR_ALLOC, "eq table");
+      rc = eq_table_device(ctx, (int)num_vars, d_z, (uint4*)p, (uint64_t)ctx->rank * N * (G > 1), N);  // zerocheck.rs:25
+      if (rc) return rc;
+      tabs.in[eq_slot] = (const uint4*)p;
+    }
+  }
+  {
+    Fr cs;
+    memset(&cs, 0, sizeof cs);
+    if (!zerocheck) memcpy(cs.v, claimed_sum, 32);
+    QZ_LAUNCH(ctx, sc_header, 1, 1, 0, head, (uint64_t)num_vars, cs);  // sumcheck.rs:35-36
+  }
+
+  if (num_vars > 0) {
+    Fr* vinv = nullptr;
+    rc = get_vinv(ctx, d, &vinv);
+    if (rc) return rc;
+    // ping-pong scratch: A holds N/2 elements per table, B holds N/4
+    uint4 *bufA[SC_MAX_K], *bufB[SC_MAX_K];
+    for (int j = 0; j < ka; j++) {
+      bufA[j] = (uint4*)ctx->arena_alloc(32 * std::max<uint64_t>(1, N / 2));
+      bufB[j] = (uint4*)ctx->arena_alloc(32 * std::max<uint64_t>(1, N / 4));
+      if (!bufA[j] || !bufB[j]) return ctx->fail(QZ_ERR_ALLOC, "fold scratch");
+    }
+    // occupancy-sized grids for the streaming rounds
+    int bps = 1;
+    if (cp.product_k == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sc_round_prod<1>, SC_THREADS, 0);
+    else if (cp.product_k == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sc_round_prod<2>, SC_THREADS, 0);
+    else if (cp.product_k == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sc_round_prod<3>, SC_THREADS, 0);
+    else if (cp.product_k == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sc_round_prod<4>, SC_THREADS, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sc_round_generic, SC_THREADS, 0);
+    if (bps < 1) bps = 1;
+    Fr* partials = (Fr*)ctx->arena_alloc(sizeof(Fr) * (size_t)ctx->sm_count * bps * (d + 1));
+    Fr* rank_evals = (Fr*)ctx->arena_alloc(sizeof(Fr) * (d + 1));
+    Fr* all_evals = (Fr*)ctx->arena_alloc(sizeof(Fr) * (size_t)(d + 1) * G);
+    if (!partials || !rank_evals || !all_evals) return ctx->fail(QZ_ERR_ALLOC, "partials");
+
+    uint64_t size = N;  // current (pre-fold) table size
+    int pending = 0, round = 0, flip = 0;
+    ctx->kernel_ms_accum = 0.f;
+    QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k0, st));
+    while (size * G > ((uint64_t)1 << SC_TAIL_LOG)) {
+      const uint64_t n_pairs = pending ? size / 4 : size / 2;
+      for (int j = 0; j < ka; j++) tabs.out[j] = flip ? bufB[j] : bufA[j];
+      const int grid = round_grid(ctx, n_pairs, bps);
+      switch (cp.product_k) {
+        case 1: QZ_LAUNCH(ctx, sc_round_prod<1>, grid, SC_THREADS, 0, tabs, n_pairs, pending, head, partials); break;
+        case 2: QZ_LAUNCH(ctx, sc_round_prod<2>, grid, SC_THREADS, 0, tabs, n_pairs, pending, head, partials); break;
+        case 3: QZ_LAUNCH(ctx, sc_round_prod<3>, grid, SC_THREADS, 0, tabs, n_pairs, pending, head, partials); break;
+        case 4: QZ_LAUNCH(ctx, sc_round_prod<4>, grid, SC_THREADS, 0, tabs, n_pairs, pending, head, partials); break;
+        default:
+          QZ_LAUNCH(ctx, sc_round_generic, grid, SC_THREADS, 0, tabs, n_pairs, pending, head, d_prog, d_consts,
+                    partials);
+      }
+      if (G == 1) {
+        QZ_LAUNCH(ctx, sc_finalize, 1, SC_THREADS, 0, partials, grid, d, head, vinv, d_coeffs + (size_t)round * mc,
+                  d_lens + round, d_point + round, mc);
+      } else {  // every rank sums all ranks' partial evaluations and runs the same transcript
+        QZ_LAUNCH(ctx, sc_reduce_partials, 1, SC_THREADS, 0, partials, grid, d, rank_evals);
+        rc = comm_allgather(ctx, rank_evals, all_evals, sizeof(Fr) * (d + 1));
+        if (rc) return rc;
+        QZ_LAUNCH(ctx, sc_finalize, 1, SC_THREADS, 0, all_evals, G, d, head, vinv, d_coeffs + (size_t)round * mc,
+                  d_lens + round, d_point + round, mc);
+      }
+      if (pending) {
+        for (int j = 0; j < ka; j++) tabs.in[j] = tabs.out[j];
+        flip ^= 1;
+        size >>= 1;
+      }
+      pending = 1;
+      round++;
+    }
+    QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k1, st));
+    ScTailBufs tb;
+    memset(&tb, 0, sizeof tb);
+    if (G > 1) {
+      // gather the ranks' shards (rank order = index order): every rank finishes the remaining rounds redundantly
+      for (int j = 0; j < ka; j++) {
+        uint4* full = (uint4*)ctx->arena_alloc(32 * size * G);
+        if (!full) return ctx->fail(QZ_ERR_ALLOC, "gathered tables");
+        rc = comm_allgather(ctx, tabs.in[j], full, 32 * size);
+        if (rc) return rc;
+        tabs.in[j] = full;
+      }
+      size *= G;
+    }
+    // the tail's scratch must not alias its input: input is bufA/bufB[flip^1], the gathered copy, or the caller's tables
+    for (int j = 0; j < ka; j++) {
+      tb.a[j] = G > 1 ? (uint4*)ctx->arena_alloc(32 * (((uint64_t)1 << SC_TAIL_LOG) / 2)) : (flip ? bufB[j] : bufA[j]);
+      tb.b[j] = (uint4*)ctx->arena_alloc(32 * (((uint64_t)1 << SC_TAIL_LOG) / 2));
+      if (!tb.a[j] || !tb.b[j]) return ctx->fail(QZ_ERR_ALLOC, "tail scratch");
+    }
+    QZ_LAUNCH(ctx, sc_tail, 1, SC_THREADS, 0, tabs, tb, size, pending, head, d_prog, d_consts, vinv, d_coeffs, d_lens,
+              d_point, round, mc);
+  }
+  if (zerocheck && num_vars > 0) QZ_LAUNCH(ctx, zc_finish, 1, 1, 0, head, d_z, d_point, (int)num_vars);
+
+  // results -> pinned staging -> caller
+  const size_t coeff_bytes = 32 * num_vars * max_coeffs, lens_bytes = 4 * num_vars, pt_bytes = 32 * num_vars;
+  uint8_t* pin = (uint8_t*)ctx->pinned_buf(sizeof(ScHead) + coeff_bytes + lens_bytes + 2 * pt_bytes);
+  if (!pin) return ctx->fail(QZ_ERR_ALLOC, "pinned staging");
+  size_t off = 0;
+  QZ_CUDA(ctx, cudaMemcpyAsync(pin, head, sizeof(ScHead), cudaMemcpyDeviceToHost, st));
+  off += sizeof(ScHead);
+  if (num_vars) {
+    QZ_CUDA(ctx, cudaMemcpyAsync(pin + off, d_coeffs, coeff_bytes, cudaMemcpyDeviceToHost, st));
+    QZ_CUDA(ctx, cudaMemcpyAsync(pin + off + coeff_bytes, d_lens, lens_bytes, cudaMemcpyDeviceToHost, st));
+    QZ_CUDA(ctx, cudaMemcpyAsync(pin + off + coeff_bytes + lens_bytes, d_point, pt_bytes, cudaMemcpyDeviceToHost, st));
+    if (zerocheck)
+      QZ_CUDA(ctx, cudaMemcpyAsync(pin + off + coeff_bytes + lens_bytes + pt_bytes, d_z, pt_bytes,
+                                   cudaMemcpyDeviceToHost, st));
+  }
+  QZ_CUDA(ctx, cudaEventRecord(ctx->ev_call1, st));
+  QZ_CUDA(ctx, cudaStreamSynchronize(st));
+  const ScHead* h = (const ScHead*)pin;
+  memcpy(state, h->tstate, 32);
+  memcpy(out_eval, h->evaluation.v, 32);
+  if (num_vars) {
+    memcpy(out_coeffs, pin + off, coeff_bytes);
+    memcpy(out_lens, pin + off + coeff_bytes, lens_bytes);
+    memcpy(out_point, pin + off + coeff_bytes + lens_bytes, pt_bytes);
+    if (zerocheck) memcpy(out_z, pin + off + coeff_bytes + lens_bytes + pt_bytes, pt_bytes);
+  }
+  cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev_call0, ctx->ev_call1);
+  if (num_vars > 0) cudaEventElapsedTime(&ctx->last_ms[1], ctx->ev_k0, ctx->ev_k1);
+  else ctx->last_ms[1] = 0.f;
+  return QZ_OK;
+}
+
+}  // namespace qz

@@ -1,0 +1,130 @@
+"""CPU, world_size 2 over gloo: the sharding the multi-GPU path uses, with the oracle standing in for the
+device.  MSM: per-rank partial sums over contiguous index ranges, gathered and added with the group law.  Sumcheck:
+tables split by the top variable; per round the ranks exchange partial round polynomials and run the same transcript;
+when one entry per rank is left the shards are gathered and the last rounds are replayed by every rank."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import coracle as co  # noqa: E402
+from oracle import pyref as py  # noqa: E402
+from quill_zkvm_b200 import parallel  # noqa: E402
+
+FR = py.FR
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gather_obj(obj, world):
+    out = [None] * world
+    dist.all_gather_object(out, obj)
+    return out
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # bootstrap: the 128-byte id produced on rank 0 reaches every rank
+        uid = np.arange(128, dtype=np.uint8) if rank == 0 else np.zeros(128, dtype=np.uint8)
+        assert parallel.broadcast_bytes(uid).tolist() == list(range(128))
+
+        # ---- MSM sharding ----
+        n = 96
+        gen = py.g1_mul(py.G1_GEN, 5)
+        srs = co.srs_generate(co.g1_to_bytes(gen), co.fr1(4242), n, threads=1)
+        rng = np.random.default_rng(3)
+        sc = co.to_mont([int(x) for x in rng.integers(1, 1 << 62, size=n)])
+        lo, hi = parallel.shard_range(n, rank, world)
+        part = co.msm(srs[lo:hi], sc[lo:hi], mode=1)
+        parts = _gather_obj(part.tobytes(), world)
+        total = np.zeros(64, dtype=np.uint8)
+        for p in parts:
+            total = co.g1_add(total, np.frombuffer(p, dtype=np.uint8).copy())
+        full = co.msm(srs, sc, mode=1)
+        assert total.tobytes() == full.tobytes()
+
+        # ---- sumcheck sharding ----
+        nv, k = 5, 3
+        import random
+        rnd = random.Random(9)
+        tabs = [[rnd.randrange(FR) for _ in range(1 << nv)] for _ in range(k)]
+        h = py.e_mul(py.e_mul(py.e_in(0), py.e_in(1)), py.e_in(2))
+        claimed = sum(a * b * c for a, b, c in zip(*tabs)) % FR
+        want = py.sumcheck_prove(nv, tabs, h, claimed, py.Transcript(b"shard"))
+        lo, hi = parallel.table_shard_range(nv, rank, world)
+        gs = [t[lo:hi] for t in tabs]
+        tr = py.Transcript(b"shard")
+        tr.append_usize(nv)
+        tr.append_fr(claimed)
+        polys, point = [], []
+        while len(gs[0]) > 1:  # local rounds: every pair (2p, 2p+1) is inside the shard
+            msg = []
+            for p in range(len(gs[0]) // 2):
+                lin = [py.trim([g[2 * p], g[2 * p + 1] - g[2 * p]]) for g in gs]
+                msg = py.poly_add(msg, py.expr_eval_poly(h, lin))
+            total_msg = []
+            for m in _gather_obj(msg, world):  # the per-round exchange: deg+1 field elements per rank
+                total_msg = py.poly_add(total_msg, m)
+            tr.append_fr_vec(total_msg)
+            polys.append(total_msg)
+            r = tr.draw_field_element()
+            point.append(r)
+            gs = [[(g[2 * p] + r * (g[2 * p + 1] - g[2 * p])) % FR for p in range(len(g) // 2)] for g in gs]
+        # one entry per rank left: gather (rank order = index order) and finish on every rank
+        rest = _gather_obj([g[0] for g in gs], world)
+        gs = [[rest[rk][t] for rk in range(world)] for t in range(k)]
+        ev = 0
+        while len(gs[0]) > 1 or not polys or len(polys) < nv:
+            msg = []
+            for p in range(len(gs[0]) // 2):
+                lin = [py.trim([g[2 * p], g[2 * p + 1] - g[2 * p]]) for g in gs]
+                msg = py.poly_add(msg, py.expr_eval_poly(h, lin))
+            tr.append_fr_vec(msg)
+            polys.append(msg)
+            r = tr.draw_field_element()
+            point.append(r)
+            gs = [[(g[2 * p] + r * (g[2 * p + 1] - g[2 * p])) % FR for p in range(len(g) // 2)] for g in gs]
+            if len(gs[0]) == 1:
+                ev = py.expr_eval_point(h, [g[0] for g in gs])
+                break
+        assert (polys, point, ev) == want
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharding_world2_gloo():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+def test_shard_ranges_partition():
+    for n in (1, 7, 96, 1 << 10):
+        for w in (1, 2, 4, 8):
+            spans = [parallel.shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+    assert parallel.table_shard_range(5, 1, 2) == (16, 32)
+    with pytest.raises(AssertionError):
+        parallel.table_shard_range(1, 0, 4)
