@@ -1,0 +1,165 @@
+"""GPU parity: KZG commit (MSM), KZG open and the SRS generator against the oracle, bit-exact; edge cases the
+reference accepts (empty input, truncation, zero scalars, identity result, repeated / opposite points, infinity
+in the SRS); BASELINE.json sizes through the closed form commit(p) = p(tau) * g."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import quill_zkvm_b200 as q
+from oracle import coracle as co
+from oracle import pyref as py
+from tests import util
+
+pytestmark = pytest.mark.gpu
+FR = py.FR
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
+hx = lambda s: int(s, 16)  # noqa: E731
+GEN = py.g1_mul(py.G1_GEN, 7)
+TAU = 0x1234567890ABCDEF1234567890ABCDEF
+
+
+@pytest.fixture(scope="module")
+def kzg_big(ctx):
+    k = q.KZG.trusted_setup(ctx, (1 << 20) - 1, co.g1_to_bytes(GEN), co.fr1(TAU))
+    yield k
+    k.srs.free()
+
+
+def test_reference_kzg_test_golden(ctx):
+    g = G["kzg_test"]
+    kzg = q.KZG.trusted_setup(ctx, 4, co.g1_to_bytes(GEN), co.fr1(TAU))
+    assert kzg.max_degree == 4
+    pts = kzg.srs.download()
+    assert [co.g1_from_bytes(pts[i]) for i in range(5)] == [(hx(p[0]), hx(p[1])) for p in g["srs"]]
+    poly = co.to_mont([2, 1, 3])  # kzg.rs:128
+    com = kzg.commit(poly)
+    assert co.g1_from_bytes(com) == (hx(g["commitment"][0]), hx(g["commitment"][1]))
+    assert ctx.g1_serialize(com).hex() == g["commitment_bytes"]
+    pr = kzg.open(poly, co.fr1(5))
+    assert co.from_mont(pr.y)[0] == 82 == hx(g["y"])
+    assert co.g1_from_bytes(pr.proof) == (hx(g["proof"][0]), hx(g["proof"][1]))
+    with pytest.raises(AssertionError):  # kzg.rs:62-65
+        kzg.commit(co.to_mont([1] * 6))
+    kzg.srs.free()
+
+
+def test_msm64_golden_and_uploaded_srs(ctx):
+    g = G["msm64"]
+    srs = co.srs_generate(co.g1_to_bytes(GEN), co.fr1(TAU), 64, threads=2)
+    kzg = q.KZG.from_points(ctx, srs)
+    sc = co.to_mont([hx(s) for s in g["scalars"]])
+    assert co.g1_from_bytes(kzg.commit(sc)) == (hx(g["result"][0]), hx(g["result"][1]))
+    kzg.srs.free()
+
+
+def test_edge_cases(ctx):
+    srs = co.srs_generate(co.g1_to_bytes(GEN), co.fr1(TAU), 40, threads=2)
+    kzg = q.KZG.from_points(ctx, srs)
+    ident = np.zeros(64, dtype=np.uint8)
+    assert np.array_equal(kzg.commit(np.zeros((0, 32), np.uint8)), ident)          # commit(&[]) = identity
+    assert ctx.g1_serialize(ident) == bytes(63) + b"\x40"
+    assert np.array_equal(kzg.commit(co.to_mont([0] * 17)), ident)                  # all-zero scalars
+    sc = util.rand_fr(64, 5)
+    assert np.array_equal(kzg.msm_unchecked(sc), co.msm(srs, sc[:40]))              # msm_unchecked truncates
+    assert np.array_equal(kzg.commit(sc[:7]), co.msm(srs[:7], sc[:7]))
+    for v in ([1], [FR - 1], [1, 1, 1], [2, 1, 3], [FR - 1] * 40, [1 << 253] * 3):
+        s = co.to_mont(v)
+        assert np.array_equal(kzg.commit(s), co.msm(srs, s)), v
+    kzg.srs.free()
+    # repeated and opposite points: doubling / cancellation inside buckets and in the reduction
+    p = srs[3]
+    neg = co.g1_to_bytes(py.g1_neg(co.g1_from_bytes(p)))
+    pts = np.stack([p] * 50 + [neg] * 50 + [srs[4]] * 33)
+    kz = q.KZG.from_points(ctx, pts)
+    for seed in range(3):
+        s = np.concatenate([co.to_mont([3] * 50), co.to_mont([3] * 50), util.rand_fr(33, seed)])
+        assert np.array_equal(kz.commit(s), co.msm(pts, s))
+    s = co.to_mont([5] * 50 + [5] * 50 + [0] * 33)
+    assert np.array_equal(kz.commit(s), ident)
+    kz.srs.free()
+    # the point at infinity inside the SRS (tau = 0 makes every power but the first the identity)
+    pts = np.stack([srs[0], np.zeros(64, np.uint8), srs[2], np.zeros(64, np.uint8)])
+    kz = q.KZG.from_points(ctx, pts)
+    s = util.rand_fr(4, 9)
+    assert np.array_equal(kz.commit(s), co.msm(pts, s))
+    kz.srs.free()
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 100, 1000, 4097, 1 << 14, 1 << 16])
+def test_msm_sizes_vs_oracle(ctx, kzg_big, n):
+    """random scalars, SRS prefix of the device-generated powers; oracle = Pippenger on the host"""
+    bases = kzg_big.srs.download(0, n)
+    sc = util.rand_fr(n, 1000 + n)
+    got = kzg_big.commit(sc)
+    assert np.array_equal(got, co.msm(bases, sc, mode=1, threads=os.cpu_count() or 1))
+    assert co.g1_on_curve(got)
+
+
+def test_srs_generator_spot_checks(ctx, kzg_big):
+    n = len(kzg_big.srs)
+    g = co.g1_to_bytes(GEN)
+    for i in [0, 1, 2, 7, 8, 9, 255, 256, 65535, 65536, n - 1]:
+        want = co.g1_mul(g, co.fr1(pow(TAU, i, FR)))
+        assert np.array_equal(kzg_big.srs.download(i, 1)[0], want), i
+
+
+def test_small_and_skewed_scalars(ctx, kzg_big):
+    """witness-like inputs: tiny values and long runs of equal scalars put most points in a few buckets"""
+    n = 5000
+    bases = kzg_big.srs.download(0, n)
+    rnd = random.Random(3)
+    for vals in ([rnd.randrange(2) for _ in range(n)], [rnd.randrange(256) for _ in range(n)], [1] * n,
+                 [FR - 1] * n, [rnd.choice([0, 1, FR - 1, 1 << 128]) for _ in range(n)]):
+        s = co.to_mont(vals)
+        assert np.array_equal(kzg_big.commit(s), co.msm(bases, s, mode=1, threads=os.cpu_count() or 1))
+
+
+def test_msm_2_20_closed_form(ctx, kzg_big):
+    """BASELINE.json config 2: 2^20 random scalars.  commit(p) = p(tau) * g, with p(tau) from the oracle's Horner."""
+    n = 1 << 20
+    buf = ctx.random_fr(n, 2020)
+    sc = buf.download().reshape(-1, 32)
+    got_dev = kzg_big.commit(buf)
+    got_host = kzg_big.commit(sc)
+    buf.free()
+    y, _ = co.kzg_open_quotient(sc, co.fr1(TAU))
+    want = co.g1_mul(co.g1_to_bytes(GEN), y)
+    assert np.array_equal(got_dev, want) and np.array_equal(got_host, want)
+    # linearity: commit(a) + commit(b) == commit(a + b)
+    b2 = util.rand_fr(n, 7)
+    s = co.field_op(0, 0, sc, b2)
+    assert np.array_equal(co.g1_add(got_dev, kzg_big.commit(b2)), kzg_big.commit(s))
+
+
+def test_kzg_open_vs_oracle(ctx, kzg_big):
+    for n in (1, 2, 3, 63, 64, 65, 4096, 4097, 100000):
+        poly = util.rand_fr(n, 40 + n)
+        x = util.rand_fr(1, n)[0]
+        pr = kzg_big.open(poly, x)
+        y, qpoly = co.kzg_open_quotient(poly, x)
+        assert np.array_equal(pr.y, y), n
+        bases = kzg_big.srs.download(0, max(n - 1, 1))
+        assert np.array_equal(pr.proof, co.msm(bases, qpoly, mode=1, threads=os.cpu_count() or 1)), n
+    # constant polynomial: quotient is zero, proof is the identity (reachable from mlpcs.rs:321-393)
+    pr = kzg_big.open(co.to_mont([9]), co.fr1(4))
+    assert co.from_mont(pr.y)[0] == 9 and not pr.proof.any()
+    # trailing zero coefficients do not change anything (DensePolynomial trims them)
+    a = kzg_big.open(co.to_mont([1, 2, 3, 0, 0]), co.fr1(11))
+    b = kzg_big.open(co.to_mont([1, 2, 3]), co.fr1(11))
+    assert np.array_equal(a.y, b.y) and np.array_equal(a.proof, b.proof)
+
+
+def test_msm_2_24_closed_form(ctx):
+    """the size BASELINE.json's metric is quoted on"""
+    n = 1 << 24
+    kzg = q.KZG.trusted_setup(ctx, n - 1, co.g1_to_bytes(GEN), co.fr1(TAU))
+    buf = ctx.random_fr(n, 2424)
+    sc = buf.download().reshape(-1, 32)
+    got = kzg.commit(buf)
+    buf.free()
+    kzg.srs.free()
+    y, _ = co.kzg_open_quotient(sc, co.fr1(TAU))
+    assert np.array_equal(got, co.g1_mul(co.g1_to_bytes(GEN), y))
