@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric (BASELINE.json): KZG-commit MSM points/s and sumcheck field-elems/s
+at 2^24, on N B200s of one node, with the host-CPU restatement of the reference timed beside it.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (sm_100a CUDA path through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port), host cores
+
+One JSON line on stdout.  Top-level value = MSM points/s (inputs resident in HBM); `sumcheck` holds the second half of
+the metric; `e2e` = the same MSM through the public API from pinned HOST buffers (H2D + D2H inside the timed region).
+A step = one KZG commit of 2^log_n scalars (MSM loop) / one sumcheck proof over three 2^log_n tables (sumcheck loop);
+both loops are timed separately, each bracketed by barrier + synchronize, max over ranks.  N > 1 shards the SAME 2^log_n
+problem (strong scaling): MSM by index range, sumcheck tables by the top variables.
+Inputs (0.5 GiB scalars + 1 GiB bases; 1.5 GiB tables) are far larger than the 126 MB L2, so no flush is needed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FR = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+TAU = 0x1234567890ABCDEF1234567890ABCDEF
+MSM_LIMB_PRODUCTS_PER_POINT = 20480  # 16 windows x (8M + 2S) x 128 32x32->64 products per Montgomery mult
+SC_BYTES_PER_ELEM = 128              # 4 * 32 B per input table element over the whole proof
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def product_expr(q, k):
+    e = q.VirtualPolyExpr.Input(0)
+    for i in range(1, k):
+        e = e * q.VirtualPolyExpr.Input(i)
+    return e
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's CPU algorithm for the path (oracle port; the arkworks binary cannot be built: no Rust toolchain),
+    on the box's host cores.  Each step is a bounded sample: KZG::commit (pcs/src/kzg.rs:61-73, including its per-call
+    SRS normalisation) on 2^ref_log_n points, and SumcheckProof::prove on three 2^ref_sc_log_n tables."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+
+    from oracle import coracle as co
+    from oracle import pyref as py
+    from tests import util
+
+    cores = os.cpu_count() or 1
+    n = 1 << args.ref_log_n
+    g = co.g1_to_bytes(py.g1_mul(py.G1_GEN, 7))
+    srs = co.srs_generate(g, co.fr1(TAU), n, threads=cores)
+    sc = util.rand_fr(n, 1)
+    nsc = 1 << args.ref_sc_log_n
+    tabs = [util.rand_fr(nsc, 10 + t) for t in range(3)]
+    nodes, consts = util.expr_product(3)
+    t_msm, t_sc, t_norm = [], [], []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        _, s_norm, s_msm = co.kzg_commit_reference_shape(srs, sc, threads=cores)
+        t1 = time.perf_counter()
+        co.sumcheck_prove(args.ref_sc_log_n, tabs, nodes, consts, co.fr1(1), co.transcript_new(b"sumcheck_bench"),
+                          max_coeffs=8, threads=cores)
+        t2 = time.perf_counter()
+        if it >= args.warmup:
+            t_msm.append(t1 - t0)
+            t_sc.append(t2 - t1)
+            t_norm.append(s_norm)
+    ms = 1e3 * sum(t_msm) / len(t_msm)
+    v = n / (ms * 1e-3)
+    sc_ms = 1e3 * sum(t_sc) / len(t_sc)
+    sc_v = 3 * nsc / (sc_ms * 1e-3)
+    sample = (f"KZG::commit of 2^{args.ref_log_n} coefficients (SRS normalisation {1e3 * sum(t_norm) / len(t_norm):.0f} ms "
+              f"of the step, single-threaded as in the reference, + Pippenger over {cores} threads); "
+              f"sumcheck over three 2^{args.ref_sc_log_n} tables over {cores} threads")
+    line = {
+        "impl": "reference", "metric": f"KZG MSM points/s (sumcheck field-elems/s in `sumcheck`)", "value": v,
+        "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (254-bit modular integer)",
+        "data": "synthetic", "config": {"workload": f"KZG commit MSM + degree-3 sumcheck, CPU sample of the 2^{args.log_n} workload",
+                                         "msm_log_n": args.ref_log_n, "sumcheck_log_n": args.ref_sc_log_n},
+        "cpu_baseline": {"value": v, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "sumcheck": {"value": sc_v, "unit": "field-elems/s", "ms_per_step": sc_ms,
+                     "e2e": {"value": sc_v, "unit": "field-elems/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_baseline(args):
+    """Oracle port timed on the host, rank 0 at N=1 only: 1 thread (faithful: the reference has no rayon / `parallel`)."""
+    import numpy as np
+
+    from oracle import coracle as co
+    from oracle import pyref as py
+    from tests import util
+
+    cores = os.cpu_count() or 1
+    n = 1 << args.cpu_log_n
+    g = co.g1_to_bytes(py.g1_mul(py.G1_GEN, 7))
+    srs = co.srs_generate(g, co.fr1(TAU), n, threads=cores)
+    sc = util.rand_fr(n, 1)
+    t0 = time.perf_counter()
+    _, s_norm, s_msm = co.kzg_commit_reference_shape(srs, sc, threads=1)
+    t_commit = time.perf_counter() - t0
+    nsc = 1 << args.cpu_sc_log_n
+    tabs = [util.rand_fr(nsc, 10 + t) for t in range(3)]
+    nodes, consts = util.expr_product(3)
+    t0 = time.perf_counter()
+    co.sumcheck_prove(args.cpu_sc_log_n, tabs, nodes, consts, co.fr1(1), co.transcript_new(b"sumcheck_bench"),
+                      max_coeffs=8, threads=1)
+    t_sc = time.perf_counter() - t0
+    return {
+        "value": n / t_commit, "unit": "points/s", "cores": 1, "kind": "port",
+        "sample": (f"KZG::commit (kzg.rs:61-73) of 2^{args.cpu_log_n} coefficients, 1 thread: {t_commit:.2f} s "
+                   f"({s_norm:.2f} s per-call SRS normalisation + {s_msm:.2f} s Pippenger); sumcheck prove over three "
+                   f"2^{args.cpu_sc_log_n} tables, 1 thread: {t_sc:.2f} s"),
+        "msm_only_points_per_s": n / s_msm,
+        "sumcheck": {"value": 3 * nsc / t_sc, "unit": "field-elems/s", "cores": 1},
+        "host_cores_available": cores,
+    }
+
+
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import quill_zkvm_b200 as q
+    from quill_zkvm_b200 import parallel
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.Stream()
+    ctx = q.Context(local, stream.cuda_stream)
+    if world > 1:
+        parallel.init_comm(ctx)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    FQ = 21888242871839275222246405745257275088696311157297823662689037894645226208583
+
+    def mont(v, mod=FR):
+        return np.frombuffer(((v % mod) * (1 << 256) % mod).to_bytes(32, "little"), dtype=np.uint8).copy()
+
+    n = 1 << args.log_n
+    lo, hi = parallel.shard_range(n, rank, world)
+    n_loc = hi - lo
+    g_bytes = np.concatenate([mont(1, FQ), mont(2, FQ)])  # the standard generator (1, 2)
+    if lo:
+        g_bytes = ctx.g1_mul(g_bytes.reshape(1, 64), mont(pow(TAU, lo, FR)).reshape(1, 32))[0]  # g * tau^lo on the device
+    kzg = q.KZG.trusted_setup(ctx, n_loc - 1, g_bytes, mont(TAU))  # SRS shard: g * tau^(lo + i)
+    scal_dev = ctx.random_fr(n_loc, 0x5155494C4C + rank)
+    pin_scal = torch.empty(n_loc * 32, dtype=torch.uint8, pin_memory=True)
+    scal_host = pin_scal.numpy()
+    scal_host[:] = scal_dev.download()
+    commit = (kzg.msm_sharded if world > 1 else kzg.commit)
+
+    sampler = ClockSampler(local)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed_loop(fn, steps, warmup, collect=None):
+        with torch.cuda.stream(stream):
+            for _ in range(warmup):
+                fn()
+            barrier()
+            l0 = ctx.kernel_launches
+            ev0.record(stream)
+            for _ in range(steps):
+                fn()
+                if collect is not None:
+                    collect.append(ctx.last_elapsed_ms(1))
+            ev1.record(stream)
+            barrier()
+            return max_over_ranks(ev0.elapsed_time(ev1) / steps), ctx.kernel_launches - l0
+
+    if rank == 0:
+        sampler.start()
+    # ---- MSM: device-resident scalars (value) and pinned-host scalars (e2e) ----
+    acc_ms: list = []
+    results = {}
+    msm_ms, msm_launches = timed_loop(lambda: results.__setitem__("dev", commit(scal_dev)), args.steps, args.warmup, acc_ms)
+    e2e_ms, _ = timed_loop(lambda: results.__setitem__("host", commit(scal_host.reshape(-1, 32))), args.steps, args.warmup)
+    assert np.array_equal(results["dev"], results["host"]), "device-resident and host-input commitments differ"
+
+    # ---- sumcheck: three 2^log_n tables, degree-3 product ----
+    nv = args.log_n
+    slo, shi = parallel.table_shard_range(nv, rank, world)
+    t_loc = shi - slo
+    tabs_dev = [ctx.random_fr(t_loc, 1000 * (t + 1) + rank) for t in range(3)]
+    pins = [torch.empty(t_loc * 32, dtype=torch.uint8, pin_memory=True) for _ in range(3)]
+    tabs_host = [p.numpy().reshape(-1, 32) for p in pins]
+    for th, td in zip(tabs_host, tabs_dev):
+        th[:] = td.download().reshape(-1, 32)
+    claimed = mont(12345)
+
+    def make_store(tabs):
+        st = q.VirtualPolynomialStore(nv if world == 1 else nv)
+        st.num_vars = nv
+        st.polynomials = list(tabs)  # shards when world > 1 (allocate_polynomial would insist on 2^nv entries)
+        st.virtual_polys = [product_expr(q, 3)]
+        return st
+
+    st_dev, st_host = make_store(tabs_dev), make_store(tabs_host)
+    sc_out = {}
+
+    def prove(store, key):
+        tr = q.Transcript(b"sumcheck_bench", ctx)
+        sc_out[key] = q.SumcheckProof.prove(ctx, nv, store, 0, claimed, tr, sharded=world > 1)
+        sc_out[key + "_state"] = tr.state.copy()
+
+    rounds_ms: list = []
+    sc_ms, sc_launches = timed_loop(lambda: prove(st_dev, "dev"), args.steps, args.warmup, rounds_ms)
+    sc_e2e_ms, _ = timed_loop(lambda: prove(st_host, "host"), args.steps, args.warmup)
+    assert sc_out["dev_state"].tobytes() == sc_out["host_state"].tobytes()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline denominators ----
+    imad_peak = ctx.bench_imad(0)  # 32x32->64 multiply-accumulates per second (IMAD.WIDE carry chains), measured now
+    hbm_peak, hbm_src = peaks()
+    out_bytes = nv * (33 * 32 + 4 + 32) + 32 + 32 + 64
+
+    if rank == 0:
+        acc_avg = sum(acc_ms) / len(acc_ms)
+        rounds_avg = sum(rounds_ms) / len(rounds_ms)
+        msm_v = n / (msm_ms * 1e-3)
+        sc_v = 3 * n / (sc_ms * 1e-3)
+        line = {
+            "metric": "KZG MSM points/s (sumcheck field-elems/s in `sumcheck`)",
+            "value": msm_v, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": msm_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32x8 (254-bit modular integer)", "data": "synthetic",
+            "config": {"workload": f"KZG commit MSM of 2^{args.log_n} random Fr scalars on a tau-power SRS + linear-time "
+                                   f"sumcheck over a degree-3 product of three 2^{args.log_n}-entry tables (BN254)",
+                       "log_n": args.log_n, "sharding": f"index ranges / top variables over {world} GPU(s)",
+                       "l2": "inputs (>= 1.5 GiB) exceed the 126 MB L2; no flush needed"},
+            "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "points/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": n_loc * 32 * world, "d2h_bytes_per_step": 64 * world},
+            "roofline": {
+                "kernel": "msm_accumulate", "bound": "int32-imad (integer multiply pipe; not hbm / tensor, see DESIGN.md)",
+                "achieved": n_loc * MSM_LIMB_PRODUCTS_PER_POINT / (acc_avg * 1e-3) / 1e12, "peak": imad_peak / 1e12,
+                "unit": "T limb-MAC/s", "frac": n_loc * MSM_LIMB_PRODUCTS_PER_POINT / (acc_avg * 1e-3) / imad_peak,
+                "kernel_ms": acc_avg, "kernel_share_of_step": acc_avg / msm_ms, "traffic": None,
+                "peak_source": "qz_bench_imad measured in this run"},
+            "sumcheck": {
+                "value": sc_v, "unit": "field-elems/s", "ms_per_step": sc_ms, "gpu_launches": sc_launches // args.steps,
+                "e2e": {"value": 3 * n / (sc_e2e_ms * 1e-3), "unit": "field-elems/s", "ms_per_step": sc_e2e_ms,
+                        "h2d_bytes_per_step": 3 * t_loc * 32 * world, "d2h_bytes_per_step": out_bytes * world},
+                "roofline": {"kernel": "sc_round_prod<3> (streaming rounds, fold fused)", "bound": "hbm",
+                             "achieved": SC_BYTES_PER_ELEM * 3 * t_loc / (rounds_avg * 1e-3) / 1e9, "peak": hbm_peak,
+                             "unit": "GB/s", "frac": SC_BYTES_PER_ELEM * 3 * t_loc / (rounds_avg * 1e-3) / 1e9 / hbm_peak,
+                             "kernel_ms": rounds_avg, "kernel_share_of_step": rounds_avg / sc_ms, "traffic": None,
+                             "peak_source": hbm_src},
+            },
+            "gpu_launches": msm_launches // args.steps,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line))
+    for b in tabs_dev + [scal_dev]:
+        b.free()
+    kzg.srs.free()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log-n", type=int, default=24, help="problem size 2^log_n (BASELINE.json metric: 24)")
+    ap.add_argument("--cpu-log-n", type=int, default=18, help="CPU baseline MSM sample size")
+    ap.add_argument("--cpu-sc-log-n", type=int, default=20, help="CPU baseline sumcheck sample size")
+    ap.add_argument("--ref-log-n", type=int, default=18, help="--impl reference: MSM sample size per step")
+    ap.add_argument("--ref-sc-log-n", type=int, default=20, help="--impl reference: sumcheck sample size per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = max(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()
