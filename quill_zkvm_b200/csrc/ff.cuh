@@ -99,6 +99,115 @@ QZ_DEV Fp<P> fp_mul_inline(const Fp<P>& a, const Fp<P>& b) {
   return r;
 }
 
+// ---- shift-free multiplier -------------------------------------------------------------------------------------------
+// fp_mul_inline above shifts the accumulator by one word per row; because IMAD.WIDE needs even-aligned register pairs,
+// ptxas pays for that with ~136 MOVs per product.  This variant keeps TWO accumulators, E holding the 64-bit lanes
+// that start at even columns and O the lanes that start at odd columns (value = E + O * 2^32).  Dividing by 2^32 after a
+// row turns O into the new E for free and E's upper three lanes into the new O's lower three; that one-lane move is
+// folded into the next row's multiply-add (destination lane j = product + old lane j+1).  E's stray low word (column
+// 0 of the new frame) is added to the new E and its carry enters the new O's chain, which starts exactly one column up.
+QZ_DEV void mul4(uint32_t* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+  asm volatile(
+      "mul.lo.u32 %0, %8, %12;\n\t"
+      "mul.hi.u32 %1, %8, %12;\n\t"
+      "mul.lo.u32 %2, %9, %12;\n\t"
+      "mul.hi.u32 %3, %9, %12;\n\t"
+      "mul.lo.u32 %4, %10, %12;\n\t"
+      "mul.hi.u32 %5, %10, %12;\n\t"
+      "mul.lo.u32 %6, %11, %12;\n\t"
+      "mul.hi.u32 %7, %11, %12;\n\t"
+      : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+}
+// d[0..7] += {a0..a3} * b as four 64-bit lanes in one carry chain; the carry out of the top lane is added to `top`
+QZ_DEV void cmad4_top(uint32_t* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b, uint32_t& top) {
+  asm volatile(
+      "mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+      "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+      "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+      "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+      "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+      "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+      "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+      "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+      "addc.u32 %8, %8, 0;\n\t"
+      : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]), "+r"(d[4]), "+r"(d[5]), "+r"(d[6]), "+r"(d[7]), "+r"(top)
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+}
+// same, for the accumulator whose top lane ends at the highest column: no carry can leave it
+QZ_DEV void cmad4(uint32_t* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+  asm volatile(
+      "mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+      "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+      "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+      "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+      "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+      "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+      "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+      "madc.hi.u32 %7, %11, %12, %7;\n\t"
+      : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]), "+r"(d[4]), "+r"(d[5]), "+r"(d[6]), "+r"(d[7])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+}
+// e0 += x[1] (the stray word), then x lane j = {a0..a3}[j] * b + old x lane j+1 (+ carry), top lane = product + carry
+QZ_DEV void madc4_rshift(uint32_t* x, uint32_t& e0, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+  asm volatile(
+      "add.cc.u32 %8, %8, %1;\n\t"
+      "madc.lo.cc.u32 %0, %9, %13, %2;\n\t"
+      "madc.hi.cc.u32 %1, %9, %13, %3;\n\t"
+      "madc.lo.cc.u32 %2, %10, %13, %4;\n\t"
+      "madc.hi.cc.u32 %3, %10, %13, %5;\n\t"
+      "madc.lo.cc.u32 %4, %11, %13, %6;\n\t"
+      "madc.hi.cc.u32 %5, %11, %13, %7;\n\t"
+      "madc.lo.cc.u32 %6, %12, %13, 0;\n\t"
+      "madc.hi.u32 %7, %12, %13, 0;\n\t"
+      : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]), "+r"(e0)
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+}
+
+template <class P>
+QZ_DEV void mont_reduce_row(uint32_t* ev, uint32_t* od) {  // ev: even lanes (column 0 first), od: odd lanes
+  const uint32_t m = ev[0] * P::INV;
+  cmad4(od, P::MOD(1), P::MOD(3), P::MOD(5), P::MOD(7), m);
+  cmad4_top(ev, P::MOD(0), P::MOD(2), P::MOD(4), P::MOD(6), m, od[7]);
+}
+
+template <class P>
+QZ_DEV Fp<P> fp_mul_v1(const Fp<P>& a, const Fp<P>& b) {
+  uint32_t X[8], Y[8];
+  mul4(X, a.v[0], a.v[2], a.v[4], a.v[6], b.v[0]);
+  mul4(Y, a.v[1], a.v[3], a.v[5], a.v[7], b.v[0]);
+  mont_reduce_row<P>(X, Y);
+#pragma unroll
+  for (int i = 1; i < 8; i += 2) {
+    // even lanes X, odd lanes Y  ->  even lanes Y, odd lanes X
+    madc4_rshift(X, Y[0], a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
+    cmad4_top(Y, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i], X[7]);
+    mont_reduce_row<P>(Y, X);
+    if (i + 1 < 8) {
+      madc4_rshift(Y, X[0], a.v[1], a.v[3], a.v[5], a.v[7], b.v[i + 1]);
+      cmad4_top(X, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i + 1], Y[7]);
+      mont_reduce_row<P>(X, Y);
+    }
+  }
+  // after rows 0..7 the even lanes are in Y (Y[0] == 0) and the odd lanes in X: result = X + Y[1..7]
+  uint32_t t[8];
+  asm volatile(
+      "add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, 0;\n\t"
+      : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7])
+      : "r"(X[0]), "r"(X[1]), "r"(X[2]), "r"(X[3]), "r"(X[4]), "r"(X[5]), "r"(X[6]), "r"(X[7]), "r"(Y[1]), "r"(Y[2]),
+        "r"(Y[3]), "r"(Y[4]), "r"(Y[5]), "r"(Y[6]), "r"(Y[7]));
+  Fp<P> r;
+  fp_reduce_once<P>(r.v, t);
+  return r;
+}
+
 // The multiplier is ~350 SASS instructions (5.6 KB); a mixed point addition inlines 10 of them.  ncu (r01) shows
 // "no_instruction" as the top stall of msm_accumulate, but calling ONE out-of-line copy per field (-DQZ_OUTLINE_MUL)
 // measured no faster for the MSM (63.3 vs 62.2 ms at 2^24) and 14% slower for the sumcheck rounds, so inlining stays
@@ -106,12 +215,12 @@ QZ_DEV Fp<P> fp_mul_inline(const Fp<P>& a, const Fp<P>& b) {
 #ifdef QZ_OUTLINE_MUL
 template <class P>
 __device__ __noinline__ Fp<P> fp_mul(const Fp<P> a, const Fp<P> b) {
-  return fp_mul_inline<P>(a, b);
+  return fp_mul_v1<P>(a, b);
 }
 #else
 template <class P>
 QZ_DEV Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
-  return fp_mul_inline<P>(a, b);
+  return fp_mul_v1<P>(a, b);  // 542 vs 610 SMSP-cycles per warp-product in tools/mulbench.cu (floor: 528)
 }
 #endif
 
