@@ -29,7 +29,7 @@ struct ScTables {
 
 // proof state that lives on the device for the whole proof
 struct ScHead {
-  uint8_t tstate[32];  // Transcript.state
+  alignas(16) uint8_t tstate[32];  // Transcript.state
   Fr r;                // challenge of the last closed round (pending fold)
   Fr evaluation;       // EvaluationClaim.evaluation
 };
@@ -87,6 +87,110 @@ static __device__ __noinline__ Fr tr_draw_fr(uint8_t* state) {
   return fr_from_48_le_bytes(c);
 }
 
+// ---- word-oriented transcript for the per-round critical path -------------------------------------------------------------
+// The byte-oriented routines above cost ~25 us per call on one device thread (local-memory byte traffic).  Every message
+// on the sumcheck path is a whole number of 32-bit words and, with the 32-byte state in front, fits one blake3 chunk
+// (<= 1024 bytes) for round polynomials of up to 30 coefficients, so the hot path hashes straight from a word buffer:
+// buf[0..8) = state, buf[8..) = message, zero padded to a multiple of 16 words.
+// The finalize step runs once per launch on ONE thread, so it executes cold: a fully unrolled compression (7 rounds x 8 G,
+// ~1000 straight-line instructions per call site) made instruction fetch the dominant cost (ncu r01: 77k cycles for
+// 13.7k instructions).  This copy is a loop over the rounds with the message schedule in a table, compiled once.
+__device__ __constant__ uint8_t B3_SCHEDULE[7][16] = {
+    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {2, 6, 3, 10, 7, 0, 4, 13, 1, 11, 12, 5, 9, 14, 15, 8},
+    {3, 4, 10, 12, 13, 2, 7, 14, 6, 5, 9, 0, 11, 15, 8, 1}, {10, 7, 12, 9, 14, 3, 13, 15, 4, 0, 11, 2, 5, 8, 1, 6},
+    {12, 13, 9, 11, 15, 10, 14, 8, 7, 2, 5, 3, 0, 1, 6, 4}, {9, 14, 11, 5, 8, 12, 15, 1, 13, 3, 0, 10, 2, 6, 4, 7},
+    {11, 15, 5, 0, 1, 9, 8, 6, 14, 10, 2, 12, 3, 4, 7, 13}};
+#define QZ_G(a, b, c, d, mx, my)      \
+  a = a + b + (mx);                   \
+  d = __funnelshift_r(d ^ a, d ^ a, 16); \
+  c = c + d;                          \
+  b = __funnelshift_r(b ^ c, b ^ c, 12); \
+  a = a + b + (my);                   \
+  d = __funnelshift_r(d ^ a, d ^ a, 8);  \
+  c = c + d;                          \
+  b = __funnelshift_r(b ^ c, b ^ c, 7);
+// cv <- first 8 words of compress(cv, m, counter 0, len, flags); out12 (optional) <- first 12 words of the output block
+static __device__ __noinline__ void b3_compress_loop(uint32_t* cv, const uint32_t* m, uint32_t block_len, uint32_t flags,
+                                                     uint32_t* out12) {
+  uint32_t s0 = cv[0], s1 = cv[1], s2 = cv[2], s3 = cv[3], s4 = cv[4], s5 = cv[5], s6 = cv[6], s7 = cv[7];
+  uint32_t s8 = Blake3::iv(0), s9 = Blake3::iv(1), s10 = Blake3::iv(2), s11 = Blake3::iv(3);
+  uint32_t s12 = 0, s13 = 0, s14 = block_len, s15 = flags;
+#pragma unroll 1
+  for (int r = 0; r < 7; r++) {
+    const uint8_t* sch = B3_SCHEDULE[r];
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = m[sch[i]];
+    QZ_G(s0, s4, s8, s12, w[0], w[1])
+    QZ_G(s1, s5, s9, s13, w[2], w[3])
+    QZ_G(s2, s6, s10, s14, w[4], w[5])
+    QZ_G(s3, s7, s11, s15, w[6], w[7])
+    QZ_G(s0, s5, s10, s15, w[8], w[9])
+    QZ_G(s1, s6, s11, s12, w[10], w[11])
+    QZ_G(s2, s7, s8, s13, w[12], w[13])
+    QZ_G(s3, s4, s9, s14, w[14], w[15])
+  }
+  if (out12) {
+    out12[8] = s8 ^ cv[0];
+    out12[9] = s9 ^ cv[1];
+    out12[10] = s10 ^ cv[2];
+    out12[11] = s11 ^ cv[3];
+  }
+  cv[0] = s0 ^ s8;  cv[1] = s1 ^ s9;  cv[2] = s2 ^ s10;  cv[3] = s3 ^ s11;
+  cv[4] = s4 ^ s12; cv[5] = s5 ^ s13; cv[6] = s6 ^ s14;  cv[7] = s7 ^ s15;
+  if (out12)
+    for (int i = 0; i < 8; i++) out12[i] = cv[i];
+}
+#undef QZ_G
+// single-chunk hash of `total_bytes` bytes held as words in buf (zero padded to a multiple of 16 words);
+// out8 <- digest words; out12 (optional) <- first 48 bytes of the XOF output
+static __device__ __noinline__ void b3_single_chunk(const uint32_t* buf, uint32_t total_bytes, uint32_t* out8, uint32_t* out12) {
+  uint32_t cv[8];
+  for (int i = 0; i < 8; i++) cv[i] = Blake3::iv(i);
+  const uint32_t nblocks = total_bytes == 0 ? 1 : (total_bytes + 63) / 64;
+#pragma unroll 1
+  for (uint32_t b = 0; b < nblocks; b++) {
+    const bool last = b + 1 == nblocks;
+    const uint32_t flags = (b == 0 ? Blake3::F_CHUNK_START : 0u) | (last ? (Blake3::F_CHUNK_END | Blake3::F_ROOT) : 0u);
+    b3_compress_loop(cv, buf + 16 * b, last ? total_bytes - 64 * b : 64u, flags, last ? out12 : nullptr);
+  }
+  if (out8)
+    for (int i = 0; i < 8; i++) out8[i] = cv[i];
+}
+// state <- blake3(state ‖ msg): msg = buf[8 .. 8 + msg_bytes/4), zero padded by the caller up to a 64-byte boundary
+static __device__ __noinline__ void tr_absorb_words(uint32_t* state, uint32_t* buf, uint32_t msg_bytes) {
+  for (int i = 0; i < 8; i++) buf[i] = state[i];
+  if (32 + msg_bytes <= 1024) {
+    b3_single_chunk(buf, 32 + msg_bytes, state, nullptr);
+  } else {  // multi-chunk message: general tree hash over the same bytes (little-endian words == bytes)
+    uint8_t o[32];
+    Blake3::hash(reinterpret_cast<const uint8_t*>(buf), 32 + msg_bytes, o, 32);
+    for (int i = 0; i < 8; i++)
+      state[i] = (uint32_t)o[4 * i] | ((uint32_t)o[4 * i + 1] << 8) | ((uint32_t)o[4 * i + 2] << 16) | ((uint32_t)o[4 * i + 3] << 24);
+  }
+}
+// draw_field_element::<Fr> (transcript.rs:49-75) on words: XOF-48 of state ‖ "challenge", re-absorb, reduce mod r
+static __device__ __noinline__ Fr tr_draw_fr_words(uint32_t* state) {
+  uint32_t buf[32], c[12];
+  for (int i = 0; i < 32; i++) buf[i] = 0;
+  for (int i = 0; i < 8; i++) buf[i] = state[i];
+  buf[8] = 0x6c616863u;   // "chal"
+  buf[9] = 0x676e656cu;   // "leng"
+  buf[10] = 0x00000065u;  // "e"
+  b3_single_chunk(buf, 41, nullptr, c);  // first 48 bytes of the root output block
+  for (int i = 0; i < 12; i++) buf[8 + i] = c[i];
+  b3_single_chunk(buf, 80, state, nullptr);
+  Fr lo, hi, r2, r3;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    lo.v[i] = c[i];
+    hi.v[i] = i < 4 ? c[8 + i] : 0u;
+    r2.v[i] = FrParams::R2(i);
+    r3.v[i] = FrParams::R3(i);
+  }
+  return fp_add<FrParams>(fp_mul<FrParams>(r2, lo), fp_mul<FrParams>(r3, hi));
+}
+
 // ---- reductions ------------------------------------------------------------------------------------------------------
 QZ_DEV Fr warp_sum(Fr v) {
 #pragma unroll
@@ -132,15 +236,20 @@ static __device__ __noinline__ Fr sc_eval_program(const uint32_t* ops, uint32_t 
 
 // Close a round (sumcheck.rs:67-78): evaluations at X = 0..d (shared s_evals) -> monomial coefficients, trimmed
 // length, absorb `len ‖ coeffs`, squeeze the challenge.  Called by every thread of the block; blockDim.x > d.
-QZ_DEV void sc_round_close(ScHead* head, const Fr* vinv, int d, const Fr* s_evals, Fr* s_coef, uint8_t* s_msg,
+// s_msg: SC_MSG_WORDS words of shared memory: [0..8) state, [8..10) u64 length, then 8 words per coefficient.
+constexpr int SC_MSG_WORDS = ((10 + 8 * SC_MAX_COEFFS + 15) / 16) * 16;
+QZ_DEV void sc_round_close(ScHead* head, const Fr* vinv, int d, const Fr* s_evals, Fr* s_coef, uint32_t* s_msg,
                            Fr* out_coeffs_row, uint32_t* out_len, Fr* out_point_slot, int max_coeffs) {
   const int t = threadIdx.x;
   if (t <= d) {
     Fr acc = fp_zero<FrParams>();
+#pragma unroll 1
     for (int j = 0; j <= d; j++) acc = fp_add<FrParams>(acc, fp_mul<FrParams>(vinv[t * (d + 1) + j], s_evals[j]));
     s_coef[t] = acc;
     out_coeffs_row[t] = acc;
-    fr_to_le_bytes(acc, s_msg + 8 + 32 * t);
+    const Fr can = fp_from_mont<FrParams>(acc);  // ark-serialize: 32 B little-endian canonical
+#pragma unroll
+    for (int i = 0; i < 8; i++) s_msg[10 + 8 * t + i] = can.v[i];
   } else if (t < max_coeffs) {
     out_coeffs_row[t] = fp_zero<FrParams>();
   }
@@ -149,9 +258,12 @@ QZ_DEV void sc_round_close(ScHead* head, const Fr* vinv, int d, const Fr* s_eval
     int len = d + 1;
     while (len > 0 && fp_is_zero<FrParams>(s_coef[len - 1])) len--;  // DensePolynomial trims trailing zeros
     *out_len = (uint32_t)len;
-    for (int i = 0; i < 8; i++) s_msg[i] = i == 0 ? (uint8_t)len : 0;  // u64 LE length prefix
-    tr_absorb(head->tstate, s_msg, 8 + 32 * len);                     // :73
-    Fr r = tr_draw_fr(head->tstate);                                   // :77
+    s_msg[8] = (uint32_t)len;  // u64 LE length prefix
+    s_msg[9] = 0;
+    for (int i = 10 + 8 * len; i < ((10 + 8 * len + 15) / 16) * 16; i++) s_msg[i] = 0;  // pad the last block
+    uint32_t* state = reinterpret_cast<uint32_t*>(head->tstate);
+    tr_absorb_words(state, s_msg, 8 + 32 * len);  // :73
+    Fr r = tr_draw_fr_words(state);               // :77
     head->r = r;
     *out_point_slot = r;
   }

@@ -1,0 +1,43 @@
+// Single-thread latency of the per-round serial pieces (development tool).
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "sumcheck.cuh"
+using namespace qz;
+
+__global__ void klat(uint32_t* state_g, long long* t, Fr* sink) {
+  __shared__ uint32_t s_msg[SC_MSG_WORDS];
+  if (threadIdx.x != 0) return;
+  uint32_t* state = state_g;
+  for (int i = 0; i < SC_MSG_WORDS; i++) s_msg[i] = i * 2654435761u;
+  for (int i = 10 + 32; i < 48; i++) s_msg[i] = 0;
+  long long t0 = clock64();
+  tr_absorb_words(state, s_msg, 8 + 32 * 4);
+  long long t1 = clock64();
+  Fr r = tr_draw_fr_words(state);
+  long long t2 = clock64();
+  Fr a = r, b = r;
+  for (int i = 0; i < 8; i++) a = fp_mul<FrParams>(a, b);
+  long long t3 = clock64();
+  for (int i = 0; i < 8; i++) a = fp_add<FrParams>(fp_mul<FrParams>(a, b), r);
+  long long t4 = clock64();
+  uint32_t out[16];
+  b3_single_chunk(s_msg, 64, out, nullptr);
+  long long t5 = clock64();
+  a.v[0] ^= out[3];
+  *sink = a;
+  t[0] = t1 - t0; t[1] = t2 - t1; t[2] = t3 - t2; t[3] = t4 - t3; t[4] = t5 - t4;
+}
+
+int main() {
+  uint32_t* st; long long* t; Fr* sink;
+  cudaMalloc(&st, 32); cudaMalloc(&t, 64); cudaMalloc(&sink, 32);
+  cudaMemset(st, 1, 32);
+  for (int rep = 0; rep < 3; rep++) {
+    klat<<<1, 32>>>(st, t, sink);
+    long long h[5];
+    cudaMemcpy(h, t, 40, cudaMemcpyDeviceToHost);
+    printf("absorb(3 blocks) %lld cyc | draw_fr %lld cyc | 8 dependent mul %lld cyc | 8 mul+add %lld | 1 compress %lld cyc   %s\n", h[0], h[1], h[2], h[3], h[4],
+           cudaGetErrorString(cudaGetLastError()));
+  }
+  return 0;
+}
