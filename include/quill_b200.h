@@ -7,6 +7,8 @@
  *   KZG::open                          pcs/src/kzg.rs:75-96          -> qz_kzg_open
  *   KZG::trusted_setup (G1 powers)     pcs/src/kzg.rs:35-59          -> qz_srs_upload, qz_srs_generate
  *   MultilinearPCS::commit             pcs/src/mlpcs.rs:188-190      -> qz_kzg_commit
+ *   MultilinearPCS::open               pcs/src/mlpcs.rs:83-124,191-198 -> qz_mlpcs_open
+ *   compute_s_polynomial               pcs/src/ipa.rs:122-157        -> qz_compute_s_polynomial
  *   SumcheckProof::prove               hyperplonk/src/piops/sumcheck.rs:28-114   -> qz_sumcheck_prove
  *   ZeroCheckProof::prove              hyperplonk/src/piops/zerocheck.rs:14-49   -> qz_zerocheck_prove
  *   fast_eq_eval_hypercube             hyperplonk/src/utils/eq_eval.rs:6-31      -> qz_eq_table
@@ -111,6 +113,20 @@ int qz_kzg_commit(qz_ctx* ctx, const qz_srs* srs, const void* coeffs, size_t n_c
  * (:85) has no output and is not reproduced. */
 int qz_kzg_open(qz_ctx* ctx, const qz_srs* srs, const void* coeffs, size_t n_coeffs, int coeffs_on_device,
                 const uint8_t x[32], uint8_t out_y[32], uint8_t out_proof_xy[64]);
+
+/* ---- multilinear PCS opening -- pcs/src/mlpcs.rs, pcs/src/ipa.rs ------------------------------------------------- */
+/* MLEvalProof::prove(poly, eval_point, kzg, transcript) (mlpcs.rs:83-124): P_r (= eq table of the point), evaluation
+ * <poly, P_r>, S polynomial (NTT), commit(S), transcript (absorb point, evaluation, S commitment; squeeze r), and the
+ * four KZG openings of poly and S at r and 1/r -- five MSMs, everything resident on the device.
+ *   out_openings   4 x [x (32) ‖ y (32) ‖ proof (64)] in the order poly_opening, poly_opening_inv, s_opening,
+ *                  s_opening_inv (mlpcs.rs:109-113)
+ * QZ_ERR_DEGREE where the reference's commit would panic (S or a quotient longer than the SRS). */
+int qz_mlpcs_open(qz_ctx* ctx, const qz_srs* srs, const void* poly, size_t n, int poly_on_device, const uint8_t* point,
+                  size_t n_point, uint8_t state[32], uint8_t out_evaluation[32], uint8_t out_s_comm[64],
+                  uint8_t out_openings[512]);
+/* InnerProductProof::compute_s_polynomial (ipa.rs:122-157): writes max(n1, n2) - 1 coefficients to `out` (host), NOT
+ * trimmed (the reference's DensePolynomial drops trailing zeros; they do not change any commitment or opening). */
+int qz_compute_s_polynomial(qz_ctx* ctx, const uint8_t* p1, size_t n1, const uint8_t* p2, size_t n2, uint8_t* out);
 
 /* ---- sumcheck / zero-check -- hyperplonk/src/piops/{sumcheck,zerocheck}.rs ------------------------------------- */
 /* SumcheckProof::prove(num_vars, store, h, claimed_sum, transcript) (sumcheck.rs:28-114).

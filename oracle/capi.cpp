@@ -303,4 +303,50 @@ void orc_expr_eval_point(const uint32_t* nodes, size_t n_nodes, const uint8_t* c
   st_fr(out_mont, h.eval_point(g.data()));
 }
 
+
+// InnerProductProof::compute_s_polynomial (pcs/src/ipa.rs:122-157); out has room for max(n1, n2) - 1 elements
+void orc_compute_s_polynomial(const uint8_t* p1, size_t n1, const uint8_t* p2, size_t n2, uint8_t* out, size_t* out_len) {
+  std::vector<Fr> a(n1), b(n2);
+  for (size_t i = 0; i < n1; i++) a[i] = ld_fr(p1 + 32 * i);
+  for (size_t i = 0; i < n2; i++) b[i] = ld_fr(p2 + 32 * i);
+  std::vector<Fr> sp = compute_s_polynomial(a, b);
+  for (size_t i = 0; i < sp.size(); i++) st_fr(out + 32 * i, sp[i]);
+  *out_len = sp.size();
+}
+// P_r coefficients (pcs/src/mlpcs.rs:68-78), trimmed; out has room for 2^n elements
+void orc_compute_pr(const uint8_t* point, size_t n, uint8_t* out, size_t* out_len) {
+  std::vector<Fr> pt(n);
+  for (size_t i = 0; i < n; i++) pt[i] = ld_fr(point + 32 * i);
+  std::vector<Fr> pr = compute_pr(pt.data(), n);
+  for (size_t i = 0; i < pr.size(); i++) st_fr(out + 32 * i, pr[i]);
+  *out_len = pr.size();
+}
+// MLEvalProof::prove (pcs/src/mlpcs.rs:83-124) on an affine SRS.  out: evaluation (32) ‖ s_comm (64) ‖ 4 x [x (32) ‖ y (32)
+// ‖ proof (64)] in the order poly_opening, poly_opening_inv, s_opening, s_opening_inv = 608 bytes.  rc 1 = degree too large.
+int orc_mlpcs_open(const uint8_t* bases_xy, size_t n_bases, const uint8_t* poly, size_t len, const uint8_t* point,
+                   size_t n_point, uint8_t state[32], int threads, uint8_t* out) {
+  std::vector<G1Affine> srs(n_bases);
+  for (size_t i = 0; i < n_bases; i++) srs[i] = ld_aff(bases_xy + 64 * i);
+  std::vector<Fr> pt(n_point);
+  for (size_t i = 0; i < n_point; i++) pt[i] = ld_fr(point + 32 * i);
+  Transcript tr(state);
+  MlEvalProof pf;
+  try {
+    pf = mlpcs_open(srs, (const Fr*)poly, len, pt.data(), n_point, tr, threads);
+  } catch (const std::exception&) {
+    return 1;
+  }
+  st_fr(out, pf.evaluation);
+  st_aff(out + 32, pf.s_comm);
+  const KzgOpening* ops[4] = {&pf.poly_opening, &pf.poly_opening_inv, &pf.s_opening, &pf.s_opening_inv};
+  for (int i = 0; i < 4; i++) {
+    uint8_t* o = out + 96 + 128 * i;
+    st_fr(o, ops[i]->x);
+    st_fr(o + 32, ops[i]->y);
+    st_aff(o + 64, ops[i]->proof);
+  }
+  memcpy(state, tr.state, 32);
+  return 0;
+}
+
 }  // extern "C"

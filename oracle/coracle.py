@@ -34,6 +34,7 @@ def lib():
         _LIB.orc_sumcheck_verify.restype = C.c_int
         _LIB.orc_g1_on_curve.restype = C.c_int
         _LIB.orc_kzg_commit_reference_shape.restype = C.c_int
+        _LIB.orc_mlpcs_open.restype = C.c_int
     return _LIB
 
 
@@ -244,3 +245,35 @@ def expr_eval_point(nodes, consts, g: np.ndarray) -> np.ndarray:
     lib().orc_expr_eval_point(_p(nd), C.c_size_t(nd.shape[0]), _p(cs), C.c_size_t(cs.shape[0]), _p(g),
                               C.c_size_t(g.shape[0]), _p(out))
     return out
+
+
+def compute_s_polynomial(p1: np.ndarray, p2: np.ndarray) -> np.ndarray:
+    p1 = np.ascontiguousarray(p1, dtype=np.uint8).reshape(-1, 32)
+    p2 = np.ascontiguousarray(p2, dtype=np.uint8).reshape(-1, 32)
+    out = np.zeros((max(p1.shape[0], p2.shape[0], 1), 32), dtype=np.uint8)
+    n = C.c_size_t(0)
+    lib().orc_compute_s_polynomial(_p(p1), C.c_size_t(p1.shape[0]), _p(p2), C.c_size_t(p2.shape[0]), _p(out), C.byref(n))
+    return out[: n.value]
+
+
+def compute_pr(point: np.ndarray) -> np.ndarray:
+    point = np.ascontiguousarray(point, dtype=np.uint8).reshape(-1, 32)
+    out = np.zeros((1 << point.shape[0], 32), dtype=np.uint8)
+    n = C.c_size_t(0)
+    lib().orc_compute_pr(_p(point), C.c_size_t(point.shape[0]), _p(out), C.byref(n))
+    return out[: n.value]
+
+
+def mlpcs_open(bases: np.ndarray, poly: np.ndarray, point: np.ndarray, state: np.ndarray, threads: int = 1):
+    """MLEvalProof::prove (pcs/src/mlpcs.rs:83-124).  Returns dict(evaluation, s_comm, openings=[(x, y, proof) x 4])."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8).reshape(-1, 64)
+    poly = np.ascontiguousarray(poly, dtype=np.uint8).reshape(-1, 32)
+    point = np.ascontiguousarray(point, dtype=np.uint8).reshape(-1, 32)
+    out = np.zeros(608, dtype=np.uint8)
+    rc = lib().orc_mlpcs_open(_p(bases), C.c_size_t(bases.shape[0]), _p(poly), C.c_size_t(poly.shape[0]), _p(point),
+                              C.c_size_t(point.shape[0]), _p(state), C.c_int(threads), _p(out))
+    if rc:
+        raise AssertionError("Polynomial degree exceeds max degree")
+    ops = [(out[96 + 128 * i: 128 + 128 * i].copy(), out[128 + 128 * i: 160 + 128 * i].copy(),
+            out[160 + 128 * i: 224 + 128 * i].copy()) for i in range(4)]
+    return dict(evaluation=out[:32].copy(), s_comm=out[32:96].copy(), openings=ops)

@@ -296,4 +296,135 @@ inline void kzg_open_quotient(const Fr* poly, size_t len, const Fr& x, Fr& y, st
   while (!q.empty() && q.back().is_zero()) q.pop_back();
 }
 
+
+// ---- radix-2 NTT over Fr (stands in for ark-poly's FFT-backed `&DensePolynomial * &DensePolynomial`) ---------
+// The product of two polynomials does not depend on which primitive root of unity is used.
+inline Fr root_of_unity(int log_n) {  // primitive 2^log_n-th root: 5^((r-1)/2^28) squared down; 5 generates Fr*
+  static const Fr root28 = [] {
+    u64 e[4];
+    memcpy(e, FrTag::MOD, 32);
+    e[0] -= 1;
+    for (int i = 0; i < 4; i++) e[i] = (e[i] >> 28) | (i < 3 ? e[i + 1] << 36 : 0);
+    return Fr::from_u64(5).pow(e);
+  }();
+  Fr w = root28;
+  for (int i = 28; i > log_n; i--) w = w.sqr();
+  return w;
+}
+inline void ntt(std::vector<Fr>& a, bool inverse) {
+  const size_t n = a.size();
+  int log_n = 0;
+  while (((size_t)1 << log_n) < n) log_n++;
+  for (size_t i = 1, j = 0; i < n; i++) {  // bit reversal
+    size_t bit = n >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) std::swap(a[i], a[j]);
+  }
+  for (int s = 1; s <= log_n; s++) {
+    Fr w = root_of_unity(s);
+    if (inverse) w = w.inverse();
+    const size_t half = (size_t)1 << (s - 1);
+    std::vector<Fr> tw(half);
+    tw[0] = Fr::one();
+    for (size_t j = 1; j < half; j++) tw[j] = tw[j - 1] * w;
+    for (size_t i = 0; i < n; i += 2 * half)
+      for (size_t j = 0; j < half; j++) {
+        Fr u = a[i + j], v = a[i + j + half] * tw[j];
+        a[i + j] = u + v;
+        a[i + j + half] = u - v;
+      }
+  }
+  if (inverse) {
+    Fr ninv = Fr::from_u64((u64)n).inverse();
+    for (auto& x : a) x *= ninv;
+  }
+}
+inline std::vector<Fr> poly_mul_ntt(const std::vector<Fr>& a, const std::vector<Fr>& b) {
+  if (a.empty() || b.empty()) return {};
+  size_t need = a.size() + b.size() - 1, m = 1;
+  while (m < need) m <<= 1;
+  std::vector<Fr> fa(a), fb(b);
+  fa.resize(m, Fr::zero());
+  fb.resize(m, Fr::zero());
+  ntt(fa, false);
+  ntt(fb, false);
+  for (size_t i = 0; i < m; i++) fa[i] *= fb[i];
+  ntt(fa, true);
+  fa.resize(need);
+  return fa;
+}
+inline void trim_vec(std::vector<Fr>& v) {
+  while (!v.empty() && v.back().is_zero()) v.pop_back();
+}
+
+// ---- pcs/src/ipa.rs:122-157 ------------------------------------------------------------------------------------
+inline std::vector<Fr> compute_s_polynomial(const std::vector<Fr>& p1, const std::vector<Fr>& p2) {
+  const size_t L = std::max(p1.size(), p2.size());
+  if (L == 0) return {};
+  std::vector<Fr> f(p1), g(p2);
+  f.resize(L, Fr::zero());
+  g.resize(L, Fr::zero());
+  std::vector<Fr> fr(f.rbegin(), f.rend()), gr(g.rbegin(), g.rend());
+  // DensePolynomial::from_coefficients_* trims; products of trimmed polys, then h is re-padded to 2L-1 (:152)
+  std::vector<Fr> ft(f), gt(g), frt(fr), grt(gr);
+  trim_vec(ft), trim_vec(gt), trim_vec(frt), trim_vec(grt);
+  std::vector<Fr> h1 = poly_mul_ntt(ft, grt), h2 = poly_mul_ntt(frt, gt);
+  std::vector<Fr> h(2 * L - 1, Fr::zero());
+  for (size_t i = 0; i < h1.size(); i++) h[i] += h1[i];
+  for (size_t i = 0; i < h2.size(); i++) h[i] += h2[i];
+  std::vector<Fr> sc(h.begin() + (h.size() / 2 + 1), h.end());  // :153
+  trim_vec(sc);
+  return sc;
+}
+
+// ---- pcs/src/mlpcs.rs:52-78: coefficients of P_r (= eq table of r, LSB-first), trailing zeros trimmed -------------
+inline std::vector<Fr> compute_pr(const Fr* r, size_t n) {
+  std::vector<Fr> pr = fast_eq_eval_hypercube(n, r);
+  trim_vec(pr);
+  return pr;
+}
+
+struct KzgOpening {
+  Fr x, y;
+  G1Affine proof;
+};
+struct MlEvalProof {
+  Fr evaluation;
+  G1Affine s_comm;
+  KzgOpening poly_opening, poly_opening_inv, s_opening, s_opening_inv;
+};
+// KZG::open on an affine SRS (kzg.rs:75-96)
+inline KzgOpening kzg_open(const std::vector<G1Affine>& srs, const Fr* poly, size_t len, const Fr& x, int threads) {
+  KzgOpening o;
+  o.x = x;
+  std::vector<Fr> q;
+  kzg_open_quotient(poly, len, x, o.y, q);
+  if (q.size() > srs.size()) throw std::runtime_error("Polynomial degree exceeds max degree");
+  o.proof = msm_pippenger(srs.data(), q.data(), q.size(), threads).into_affine();
+  return o;
+}
+// ---- pcs/src/mlpcs.rs:83-124 -----------------------------------------------------------------------------------------
+inline MlEvalProof mlpcs_open(const std::vector<G1Affine>& srs, const Fr* poly, size_t len, const Fr* point, size_t n,
+                              Transcript& tr, int threads) {
+  MlEvalProof pf;
+  std::vector<Fr> pr = compute_pr(point, n);
+  pf.evaluation = Fr::zero();
+  for (size_t i = 0; i < std::min(len, pr.size()); i++) pf.evaluation += poly[i] * pr[i];  // :91-94
+  std::vector<Fr> pv(poly, poly + len);
+  std::vector<Fr> s = compute_s_polynomial(pv, pr);  // :96
+  if (s.size() > srs.size() || len > srs.size()) throw std::runtime_error("Polynomial degree exceeds max degree");
+  pf.s_comm = msm_pippenger(srs.data(), s.data(), s.size(), threads).into_affine();  // :97
+  tr.append_fr_vec(point, n);       // :100 (&[F]: length-prefixed)
+  tr.append_fr(pf.evaluation);      // :101
+  tr.append_g1(pf.s_comm);          // :102
+  Fr r = tr.draw_field_element();   // :105
+  Fr r_inv = r.inverse();           // :107
+  pf.poly_opening = kzg_open(srs, poly, len, r, threads);          // :109-113
+  pf.poly_opening_inv = kzg_open(srs, poly, len, r_inv, threads);
+  pf.s_opening = kzg_open(srs, s.data(), s.size(), r, threads);
+  pf.s_opening_inv = kzg_open(srs, s.data(), s.size(), r_inv, threads);
+  return pf;
+}
+
 }  // namespace orc

@@ -21,7 +21,7 @@ SYMBOLS = [
     "qz_transcript_new", "qz_transcript_append_bytes", "qz_transcript_draw_challenge", "qz_transcript_draw_fr",
     "qz_transcript_append_fr", "qz_transcript_append_g1", "qz_g1_serialize",
     "qz_srs_upload", "qz_srs_generate", "qz_srs_free", "qz_srs_len", "qz_srs_download",
-    "qz_msm", "qz_kzg_commit", "qz_kzg_open",
+    "qz_msm", "qz_kzg_commit", "qz_kzg_open", "qz_mlpcs_open", "qz_compute_s_polynomial",
     "qz_sumcheck_prove", "qz_zerocheck_prove", "qz_eq_table",
     "qz_comm_unique_id", "qz_comm_init", "qz_msm_sharded", "qz_sumcheck_prove_sharded",
     "qz_last_elapsed_ms", "qz_bench_imad", "qz_bench_fp_mul",
@@ -91,6 +91,8 @@ def load():
     lib.qz_msm.argtypes = [vp, vp, vp, sz, i32, vp]
     lib.qz_kzg_commit.argtypes = [vp, vp, vp, sz, i32, vp]
     lib.qz_kzg_open.argtypes = [vp, vp, vp, sz, i32, vp, vp, vp]
+    lib.qz_mlpcs_open.argtypes = [vp, vp, vp, sz, i32, vp, sz, vp, vp, vp, vp]
+    lib.qz_compute_s_polynomial.argtypes = [vp, vp, sz, vp, sz, vp]
     sc = [vp, sz, sz, vp, i32, vp, sz, vp, sz, vp, vp, sz, vp, vp, vp, vp]
     lib.qz_sumcheck_prove.argtypes = sc
     lib.qz_sumcheck_prove_sharded.argtypes = sc

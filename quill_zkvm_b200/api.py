@@ -235,6 +235,18 @@ class KZGOpeningProof:
     proof: np.ndarray  # G1, 64 B
 
 
+@dataclass
+class MLEvalProof:
+    """pcs/src/mlpcs.rs:32-44."""
+    evaluation_point: np.ndarray
+    evaluation: np.ndarray
+    s_comm: np.ndarray
+    poly_opening: KZGOpeningProof
+    poly_opening_inv: KZGOpeningProof
+    s_opening: KZGOpeningProof
+    s_opening_inv: KZGOpeningProof
+
+
 class KZG:
     """pcs/src/kzg.rs:10-96, prover side.  `g1_points` live on the device, normalised once."""
 
@@ -290,6 +302,31 @@ class KZG:
             raise AssertionError("Polynomial degree exceeds max degree")
         self.ctx.check(rc)
         return KZGOpeningProof(x.copy(), y, pr)
+
+    def open_multilinear(self, poly, eval_point: np.ndarray, transcript: "Transcript") -> "MLEvalProof":
+        """MultilinearPCS::open (pcs/src/mlpcs.rs:191-198) = MLEvalProof::prove (mlpcs.rs:83-124)."""
+        ptr, on_dev, n = self._coeffs(poly)
+        pt = _u8(eval_point, (-1, 32))
+        ev = np.zeros(32, dtype=np.uint8)
+        sc = np.zeros(64, dtype=np.uint8)
+        ops = np.zeros((4, 128), dtype=np.uint8)
+        rc = self.ctx.lib.qz_mlpcs_open(self.ctx.h, self.srs.h, ptr, n, int(on_dev), _ptr(pt) if pt.shape[0] else None,
+                                        pt.shape[0], _ptr(transcript.state), _ptr(ev), _ptr(sc), _ptr(ops))
+        if rc == _lib.QZ_ERR_DEGREE:
+            raise AssertionError("Polynomial degree exceeds max degree")
+        self.ctx.check(rc)
+        o = [KZGOpeningProof(ops[i, :32].copy(), ops[i, 32:64].copy(), ops[i, 64:].copy()) for i in range(4)]
+        return MLEvalProof(pt.copy(), ev, sc, o[0], o[1], o[2], o[3])
+
+    def compute_s_polynomial(self, p1: np.ndarray, p2: np.ndarray) -> np.ndarray:
+        """InnerProductProof::compute_s_polynomial (pcs/src/ipa.rs:122-157), coefficients not trimmed."""
+        p1, p2 = _u8(p1, (-1, 32)), _u8(p2, (-1, 32))
+        L = max(p1.shape[0], p2.shape[0])
+        out = np.zeros((max(L - 1, 0), 32), dtype=np.uint8)
+        if L >= 2:
+            self.ctx.check(self.ctx.lib.qz_compute_s_polynomial(self.ctx.h, _ptr(p1) if p1.shape[0] else None, p1.shape[0],
+                                                                _ptr(p2) if p2.shape[0] else None, p2.shape[0], _ptr(out)))
+        return out
 
     def _coeffs(self, p):
         if isinstance(p, DeviceBuffer):

@@ -80,6 +80,15 @@ struct qz_ctx {
     blocks.push_back(Block{p, cap, bytes});
     return p;
   }
+  // nested scratch: offsets at the time of the mark are restored on release (blocks added later are emptied)
+  std::vector<size_t> arena_mark() const {
+    std::vector<size_t> m;
+    for (auto& b : blocks) m.push_back(b.off);
+    return m;
+  }
+  void arena_release(const std::vector<size_t>& m) {
+    for (size_t i = 0; i < blocks.size(); i++) blocks[i].off = i < m.size() ? m[i] : 0;
+  }
   void* pinned_buf(size_t bytes) {
     if (bytes > pinned_cap) {
       if (pinned) cudaFreeHost(pinned);

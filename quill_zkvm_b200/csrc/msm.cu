@@ -287,7 +287,8 @@ __global__ void __launch_bounds__(128) srs_generate(const uint8_t* table, Fr tau
 //   B. one block: carry_c = value entering chunk c from the right = sum_{c' > c} h_{c'} x^{start_{c'} - end_c}
 //   C. per chunk: rerun the recurrence with the carry, writing q; chunk 0's final value is y = p(x).
 constexpr int OPEN_CHUNK = 64;
-__global__ void __launch_bounds__(128) open_local(const uint4* p, uint64_t n, Fr x, Fr* h) {
+__global__ void __launch_bounds__(128) open_local(const uint4* p, uint64_t n, const Fr* xp, Fr* h) {
+  const Fr x = *xp;
   const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t begin = c * OPEN_CHUNK;
   if (begin >= n) return;
@@ -297,7 +298,8 @@ __global__ void __launch_bounds__(128) open_local(const uint4* p, uint64_t n, Fr
   h[c] = acc;
 }
 // serial-over-chunks carry pass with one thread per stripe would be O(n/CHUNK); instead: block-wide scan in two levels
-__global__ void __launch_bounds__(1) open_carry_serial(const Fr* h, uint64_t nchunks, Fr xL, Fr* carry) {
+__global__ void __launch_bounds__(1) open_carry_serial(const Fr* h, uint64_t nchunks, const Fr* xLp, Fr* carry) {
+  const Fr xL = *xLp;
   // carry[c] = sum_{c' > c} h[c'] * xL^(c' - c - 1); all chunks but possibly the last are full, and the last chunk's
   // h is multiplied only by powers belonging to the full chunks to its left, so xL = x^OPEN_CHUNK throughout.
   Fr acc = fp_zero<FrParams>();
@@ -306,7 +308,9 @@ __global__ void __launch_bounds__(1) open_carry_serial(const Fr* h, uint64_t nch
     acc = fp_add<FrParams>(fp_mul<FrParams>(acc, xL), h[c]);
   }
 }
-__global__ void __launch_bounds__(256) open_carry_level(const Fr* h, uint64_t nchunks, Fr xL, int group, Fr* group_h) {
+__global__ void __launch_bounds__(256) open_carry_level(const Fr* h, uint64_t nchunks, const Fr* xLp, int group,
+                                                       Fr* group_h) {
+  const Fr xL = *xLp;
   // level-2 local values over groups of `group` chunks
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t begin = g * group;
@@ -316,8 +320,9 @@ __global__ void __launch_bounds__(256) open_carry_level(const Fr* h, uint64_t nc
   for (uint64_t c = end; c-- > begin;) acc = fp_add<FrParams>(fp_mul<FrParams>(acc, xL), h[c]);
   group_h[g] = acc;
 }
-__global__ void __launch_bounds__(256) open_carry_expand(const Fr* h, uint64_t nchunks, Fr xL, int group,
+__global__ void __launch_bounds__(256) open_carry_expand(const Fr* h, uint64_t nchunks, const Fr* xLp, int group,
                                                         const Fr* group_carry, Fr* carry) {
+  const Fr xL = *xLp;
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t begin = g * group;
   if (begin >= nchunks) return;
@@ -328,7 +333,9 @@ __global__ void __launch_bounds__(256) open_carry_expand(const Fr* h, uint64_t n
     acc = fp_add<FrParams>(fp_mul<FrParams>(acc, xL), h[c]);
   }
 }
-__global__ void __launch_bounds__(128) open_write(const uint4* p, uint64_t n, Fr x, const Fr* carry, uint4* q, Fr* y) {
+__global__ void __launch_bounds__(128) open_write(const uint4* p, uint64_t n, const Fr* xp, const Fr* carry, uint4* q,
+                                                  Fr* y) {
+  const Fr x = *xp;
   const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t begin = c * OPEN_CHUNK;
   if (begin >= n) return;
@@ -341,7 +348,8 @@ __global__ void __launch_bounds__(128) open_write(const uint4* p, uint64_t n, Fr
     else *y = acc;  // the remainder of the division = p(x)
   }
 }
-__global__ void fr_pow_small(Fr x, uint32_t e, Fr* out) {
+__global__ void fr_pow_small(const Fr* xp, uint32_t e, Fr* out) {
+  const Fr x = *xp;
   Fr acc = fp_one<FrParams>();
   for (int bit = 31; bit >= 0; bit--) {
     acc = fp_sqr<FrParams>(acc);
@@ -381,6 +389,7 @@ int msm_device(qz_ctx* ctx, const uint8_t* bases, const uint4* scalars_dev, size
     return QZ_OK;
   }
   if (n >= ((size_t)1 << 31)) return ctx->fail(QZ_ERR_INVALID_ARG, "MSM size must be below 2^31");
+  auto mark = ctx->arena_mark();
   const int c = pick_window(n);
   const int W = (256 + c - 1) / c;
   const uint64_t m = (uint64_t)W * n;
@@ -433,7 +442,44 @@ int msm_device(qz_ctx* ctx, const uint8_t* bases, const uint4* scalars_dev, size
   QZ_LAUNCH(ctx, msm_bucket_reduce, (red_threads + 127) / 128, 128, 0, buckets, c, W, seg, partial);
   QZ_LAUNCH(ctx, msm_window_sum, W, 128, 0, partial, per_window_parts, window_sums);
   QZ_LAUNCH(ctx, msm_combine, 1, 1, 0, window_sums, c, W, out_xyzz_dev, out_affine_dev);
+  ctx->arena_release(mark);  // stream order keeps the scratch valid for the kernels enqueued above
   return QZ_OK;
+}
+
+// KZG::open (kzg.rs:75-96) with everything on the device: x is read from device memory, y (32 B) and the affine proof
+// (64 B) are written to device memory.  Asynchronous on ctx->stream; scratch is released on return (stream order keeps
+// it valid for the kernels already enqueued).
+int kzg_open_device(qz_ctx* ctx, const uint8_t* bases, size_t srs_n, const uint4* pdev, size_t n_coeffs, const Fr* x_dev,
+                    Fr* y_dev, uint8_t* proof_affine_dev) {
+  cudaStream_t st = ctx->stream;
+  if (n_coeffs == 0) {  // zero polynomial: y = 0, quotient = 0, proof = identity
+    QZ_CUDA(ctx, cudaMemsetAsync(y_dev, 0, 32, st));
+    QZ_CUDA(ctx, cudaMemsetAsync(proof_affine_dev, 0, 64, st));
+    return QZ_OK;
+  }
+  auto mark = ctx->arena_mark();
+  const uint64_t n = n_coeffs, nchunks = (n + OPEN_CHUNK - 1) / OPEN_CHUNK;
+  const int group = 64;
+  const uint64_t ngroups = (nchunks + group - 1) / group;
+  Fr* h = (Fr*)ctx->arena_alloc(32 * nchunks);
+  Fr* carry = (Fr*)ctx->arena_alloc(32 * nchunks);
+  Fr* gh = (Fr*)ctx->arena_alloc(32 * ngroups);
+  Fr* gcarry = (Fr*)ctx->arena_alloc(32 * ngroups);
+  Fr* pw = (Fr*)ctx->arena_alloc(64);
+  uint4* q = (uint4*)ctx->arena_alloc(32 * std::max<uint64_t>(1, n - 1));
+  if (!h || !carry || !gh || !gcarry || !pw || !q) return ctx->fail(QZ_ERR_ALLOC, "open scratch");
+  QZ_LAUNCH(ctx, fr_pow_small, 1, 1, 0, x_dev, (uint32_t)OPEN_CHUNK, pw);
+  QZ_LAUNCH(ctx, fr_pow_small, 1, 1, 0, x_dev, (uint32_t)(OPEN_CHUNK * group), pw + 1);
+  QZ_LAUNCH(ctx, open_local, (unsigned)((nchunks + 127) / 128), 128, 0, pdev, n, x_dev, h);
+  QZ_LAUNCH(ctx, open_carry_level, (unsigned)((ngroups + 255) / 256), 256, 0, h, nchunks, pw, group, gh);
+  QZ_LAUNCH(ctx, open_carry_serial, 1, 1, 0, gh, ngroups, pw + 1, gcarry);
+  QZ_LAUNCH(ctx, open_carry_expand, (unsigned)((ngroups + 255) / 256), 256, 0, h, nchunks, pw, group, gcarry, carry);
+  QZ_LAUNCH(ctx, open_write, (unsigned)((nchunks + 127) / 128), 128, 0, pdev, n, x_dev, carry, q, y_dev);
+  // commit(q): trailing zero coefficients contribute nothing, so trimming (DensePolynomial) is value-neutral
+  const size_t qn = std::min<size_t>(n - 1, srs_n);
+  int rc = msm_device(ctx, bases, q, qn, nullptr, proof_affine_dev);
+  ctx->arena_release(mark);
+  return rc;
 }
 
 int msm_sum_points_launch(qz_ctx* ctx, const uint8_t* pts_dev, int n, uint8_t* out_affine_dev) {
@@ -564,48 +610,22 @@ int qz_kzg_open(qz_ctx* ctx, const qz_srs* srs, const void* coeffs, size_t n_coe
   QZ_CUDA(ctx, cudaEventRecord(ctx->ev_call0, st));
   QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k0, st));
   QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k1, st));
-  uint8_t* res = (uint8_t*)ctx->arena_alloc(128);  // y (32) ‖ pad ‖ proof (64)
+  uint8_t* res = (uint8_t*)ctx->arena_alloc(192);  // y (32) ‖ x (32) ‖ proof (64)
   if (!res) return ctx->fail(QZ_ERR_ALLOC, "result");
-  QZ_CUDA(ctx, cudaMemsetAsync(res, 0, 128, st));
-  if (n_coeffs > 0) {
-    const uint4* pdev = (const uint4*)coeffs;
-    if (!on_device) {
-      void* p = ctx->arena_alloc(32 * n_coeffs);
-      if (!p) return ctx->fail(QZ_ERR_ALLOC, "coeffs");
-      QZ_CUDA(ctx, cudaMemcpyAsync(p, coeffs, 32 * n_coeffs, cudaMemcpyHostToDevice, st));
-      pdev = (const uint4*)p;
-    }
-    Fr xv;
-    memcpy(xv.v, x, 32);
-    const uint64_t n = n_coeffs, nchunks = (n + OPEN_CHUNK - 1) / OPEN_CHUNK;
-    const int group = 64;
-    const uint64_t ngroups = (nchunks + group - 1) / group;
-    Fr* h = (Fr*)ctx->arena_alloc(32 * nchunks);
-    Fr* carry = (Fr*)ctx->arena_alloc(32 * nchunks);
-    Fr* gh = (Fr*)ctx->arena_alloc(32 * ngroups);
-    Fr* gcarry = (Fr*)ctx->arena_alloc(32 * ngroups);
-    Fr* pw = (Fr*)ctx->arena_alloc(64);
-    uint4* q = (uint4*)ctx->arena_alloc(32 * std::max<uint64_t>(1, n - 1));
-    if (!h || !carry || !gh || !gcarry || !pw || !q) return ctx->fail(QZ_ERR_ALLOC, "open scratch");
-    QZ_LAUNCH(ctx, fr_pow_small, 1, 1, 0, xv, (uint32_t)OPEN_CHUNK, pw);
-    QZ_LAUNCH(ctx, fr_pow_small, 1, 1, 0, xv, (uint32_t)(OPEN_CHUNK * group), pw + 1);
-    Fr xL, xG;
-    QZ_CUDA(ctx, cudaMemcpyAsync(&xL, pw, 32, cudaMemcpyDeviceToHost, st));
-    QZ_CUDA(ctx, cudaMemcpyAsync(&xG, pw + 1, 32, cudaMemcpyDeviceToHost, st));
-    QZ_CUDA(ctx, cudaStreamSynchronize(st));
-    QZ_LAUNCH(ctx, open_local, (unsigned)((nchunks + 127) / 128), 128, 0, pdev, n, xv, h);
-    QZ_LAUNCH(ctx, open_carry_level, (unsigned)((ngroups + 255) / 256), 256, 0, h, nchunks, xL, group, gh);
-    QZ_LAUNCH(ctx, open_carry_serial, 1, 1, 0, gh, ngroups, xG, gcarry);
-    QZ_LAUNCH(ctx, open_carry_expand, (unsigned)((ngroups + 255) / 256), 256, 0, h, nchunks, xL, group, gcarry, carry);
-    QZ_LAUNCH(ctx, open_write, (unsigned)((nchunks + 127) / 128), 128, 0, pdev, n, xv, carry, q, (Fr*)res);
-    // commit(q): trailing zero coefficients contribute nothing, so trimming (DensePolynomial) is value-neutral
-    const size_t qn = std::min<size_t>(n - 1, srs->n);
-    int rc = msm_device(ctx, srs->bases, q, qn, nullptr, res + 64);
-    if (rc) return rc;
+  QZ_CUDA(ctx, cudaMemsetAsync(res, 0, 192, st));
+  QZ_CUDA(ctx, cudaMemcpyAsync(res + 32, x, 32, cudaMemcpyHostToDevice, st));
+  const uint4* pdev = (const uint4*)coeffs;
+  if (!on_device && n_coeffs) {
+    void* p = ctx->arena_alloc(32 * n_coeffs);
+    if (!p) return ctx->fail(QZ_ERR_ALLOC, "coeffs");
+    QZ_CUDA(ctx, cudaMemcpyAsync(p, coeffs, 32 * n_coeffs, cudaMemcpyHostToDevice, st));
+    pdev = (const uint4*)p;
   }
-  uint8_t* pin = (uint8_t*)ctx->pinned_buf(128);
+  int rc = kzg_open_device(ctx, srs->bases, srs->n, pdev, n_coeffs, (const Fr*)(res + 32), (Fr*)res, res + 64);
+  if (rc) return rc;
+  uint8_t* pin = (uint8_t*)ctx->pinned_buf(192);
   if (!pin) return ctx->fail(QZ_ERR_ALLOC, "pinned");
-  QZ_CUDA(ctx, cudaMemcpyAsync(pin, res, 128, cudaMemcpyDeviceToHost, st));
+  QZ_CUDA(ctx, cudaMemcpyAsync(pin, res, 192, cudaMemcpyDeviceToHost, st));
   QZ_CUDA(ctx, cudaEventRecord(ctx->ev_call1, st));
   QZ_CUDA(ctx, cudaStreamSynchronize(st));
   memcpy(out_y, pin, 32);

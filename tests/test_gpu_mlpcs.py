@@ -1,0 +1,106 @@
+"""GPU parity: MultilinearPCS::open (MLEvalProof::prove, pcs/src/mlpcs.rs:83-124) and the S polynomial
+(pcs/src/ipa.rs:122-157) against the oracle, bit-exact, on the reference's test shapes (mlpcs.rs:245-474,
+ipa.rs:214-298) and larger seeded ones."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+import quill_zkvm_b200 as q
+from oracle import coracle as co
+from oracle import pyref as py
+from tests import util
+
+pytestmark = pytest.mark.gpu
+FR = py.FR
+GEN = py.g1_mul(py.G1_GEN, 7)
+TAU = 0x1234567890ABCDEF1234567890ABCDEF
+NCPU = os.cpu_count() or 1
+
+
+@pytest.fixture(scope="module")
+def kzg(ctx):
+    k = q.KZG.trusted_setup(ctx, (1 << 17) - 1, co.g1_to_bytes(GEN), co.fr1(TAU))
+    yield k
+    k.srs.free()
+
+
+def _trim(a):
+    n = a.shape[0]
+    while n and not a[n - 1].any():
+        n -= 1
+    return a[:n]
+
+
+@pytest.mark.parametrize("n1,n2", [(1, 1), (2, 2), (3, 3), (3, 2), (2, 5), (5, 9), (64, 64), (1000, 1000), (4097, 300),
+                                   (1 << 15, 1 << 15)])
+def test_s_polynomial_vs_oracle(ctx, kzg, n1, n2):
+    a, b = util.rand_fr(n1, n1), util.rand_fr(n2, 7 * n2 + 1)
+    got = kzg.compute_s_polynomial(a, b)
+    want = co.compute_s_polynomial(a, b)
+    assert got.shape[0] == max(n1, n2) - 1
+    assert np.array_equal(_trim(got), want)
+
+
+def test_s_polynomial_reference_answers(ctx, kzg):
+    """ipa.rs:214-298: [1,2,3].[4,5,6] and the mismatched-degree case"""
+    assert co.from_mont(kzg.compute_s_polynomial(co.to_mont([1, 2, 3]), co.to_mont([4, 5, 6]))) == py.compute_s_polynomial([1, 2, 3], [4, 5, 6])
+    got = co.from_mont(kzg.compute_s_polynomial(co.to_mont([1, 2, 3]), co.to_mont([4, 5])))
+    assert got == py.compute_s_polynomial([1, 2, 3], [4, 5])
+    # sparse inputs whose S has trailing zeros
+    a = co.to_mont([1, 0, 0, 0, 0, 0, 0, 0])
+    b = co.to_mont([0, 0, 0, 0, 0, 1])
+    assert np.array_equal(_trim(kzg.compute_s_polynomial(a, b)), co.compute_s_polynomial(a, b))
+
+
+def _check_open(ctx, kzg, poly, point, domain=b"mlpcs"):
+    tr = q.Transcript(domain, ctx)
+    pf = kzg.open_multilinear(poly, point, tr)
+    st = co.transcript_new(domain)
+    n_srs = len(kzg.srs)
+    want = co.mlpcs_open(kzg.srs.download(0, min(n_srs, max(poly.shape[0], 1 << point.shape[0]) + 1)), poly, point, st,
+                         threads=NCPU)
+    assert np.array_equal(pf.evaluation, want["evaluation"])
+    assert np.array_equal(pf.s_comm, want["s_comm"])
+    for got, (x, y, proof) in zip([pf.poly_opening, pf.poly_opening_inv, pf.s_opening, pf.s_opening_inv], want["openings"]):
+        assert np.array_equal(got.x, x) and np.array_equal(got.y, y) and np.array_equal(got.proof, proof)
+    assert tr.state.tobytes() == st.tobytes()
+    return pf
+
+
+def test_reference_mlpcs_tests(ctx, kzg):
+    rnd = random.Random(1)
+    # test_mlpcs_proof (mlpcs.rs:245-319): 5 variables, evaluation == DenseMultilinearExtension::evaluate
+    poly = util.rand_fr(32, 5)
+    point = util.rand_fr(5, 6)
+    pf = _check_open(ctx, kzg, poly, point)
+    assert np.array_equal(pf.evaluation, co.mle_evaluate(poly, point))
+    # test_mlpcs_zero_opening / _zero_one_opening (mlpcs.rs:321-393): degenerate P_r (a monomial)
+    poly = util.rand_fr(8, 7)
+    for pt in ([0, 0, 0], [0, 1, 0], [1, 1, 1], [1, 0, 1]):
+        pf = _check_open(ctx, kzg, poly, co.to_mont(pt))
+        idx = sum(b << i for i, b in enumerate(pt))
+        assert np.array_equal(pf.evaluation, poly[idx])
+    # test_mlpcs_degree_bound (mlpcs.rs:395-474): a 2^5 polynomial opened at a 3-variable point evaluates the 2^3 prefix
+    poly = util.rand_fr(32, 8)
+    point = util.rand_fr(3, 9)
+    pf = _check_open(ctx, kzg, poly, point)
+    assert np.array_equal(pf.evaluation, co.mle_evaluate(poly[:8], point))
+    # a point with more variables than the polynomial has entries (P_r longer than the polynomial)
+    _check_open(ctx, kzg, util.rand_fr(5, 10), util.rand_fr(4, 11))
+
+
+@pytest.mark.parametrize("n", [1, 10, 14, 16])
+def test_mlpcs_open_sizes(ctx, kzg, n):
+    poly = util.rand_fr(1 << n, 100 + n)
+    point = util.rand_fr(n, 200 + n)
+    pf = _check_open(ctx, kzg, poly, point, b"test_pcs_interface")
+    assert np.array_equal(pf.evaluation, co.mle_evaluate(poly, point))
+
+
+def test_mlpcs_degree_error(ctx):
+    small = q.KZG.trusted_setup(ctx, 7, co.g1_to_bytes(GEN), co.fr1(TAU))
+    with pytest.raises(AssertionError):
+        small.open_multilinear(util.rand_fr(32, 1), util.rand_fr(5, 2), q.Transcript(b"x", ctx))
+    small.srs.free()
