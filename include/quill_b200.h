@@ -12,6 +12,7 @@
  *   SumcheckProof::prove               hyperplonk/src/piops/sumcheck.rs:28-114   -> qz_sumcheck_prove
  *   ZeroCheckProof::prove              hyperplonk/src/piops/zerocheck.rs:14-49   -> qz_zerocheck_prove
  *   fast_eq_eval_hypercube             hyperplonk/src/utils/eq_eval.rs:6-31      -> qz_eq_table
+ *   logup denominators                 hyperplonk/src/piops/multiset_check.rs:43-95 -> qz_logup_denominators
  *   Transcript                         transcript/src/transcript.rs:14-75        -> qz_transcript_*
  *
  * Data conventions (all little-endian):
@@ -147,6 +148,13 @@ int qz_zerocheck_prove(qz_ctx* ctx, size_t num_vars, size_t k, const void* const
                        const qz_expr_node* nodes, size_t n_nodes, const uint8_t* consts, size_t n_consts,
                        uint8_t state[32], size_t max_coeffs, uint8_t* out_coeffs, uint32_t* out_lens,
                        uint8_t* out_point, uint8_t out_eval[32], uint8_t* out_z);
+/* Logup denominators (hyperplonk/src/piops/multiset_check.rs:43-95): out[i] = m(row_i) / (gamma + h(row_i)) for every row of
+ * the store, with h and the optional multiplicities expression m (n_nodes_m = 0 means m = 1, "Equality" mode) given as
+ * flattened VirtualPolyExpr over the same tables and the same consts array.  Batch inversion on the device.
+ * QZ_ERR_INVALID_ARG if some gamma + h(row) is zero (the reference panics on `.inverse().unwrap()`). */
+int qz_logup_denominators(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tables, int tables_on_device,
+                          const qz_expr_node* nodes_h, size_t n_nodes_h, const qz_expr_node* nodes_m, size_t n_nodes_m,
+                          const uint8_t* consts, size_t n_consts, const uint8_t gamma[32], void* out, int out_on_device);
 /* fast_eq_eval_hypercube(n, point) (eq_eval.rs:6-31) -> 2^n Fr written to `out` (host, or device if out_on_device). */
 int qz_eq_table(qz_ctx* ctx, size_t n, const uint8_t* point, void* out, int out_on_device);
 

@@ -349,4 +349,25 @@ int orc_mlpcs_open(const uint8_t* bases_xy, size_t n_bases, const uint8_t* poly,
   return 0;
 }
 
+
+// Logup denominators (hyperplonk/src/piops/multiset_check.rs:43-95): out[i] = m(row_i) / (gamma + h(row_i)); n_nodes_m = 0
+// means Equality mode (no multiplicities).  rc 1 = a denominator is zero (the reference panics on unwrap).
+int orc_logup_denominators(size_t num_vars, size_t k, const uint8_t* const* tables_mont, const uint32_t* nodes_h,
+                           size_t n_nodes_h, const uint32_t* nodes_m, size_t n_nodes_m, const uint8_t* consts_mont,
+                           size_t n_consts, const uint8_t* gamma_mont, uint8_t* out_mont) {
+  Expr h = ld_expr(nodes_h, n_nodes_h, consts_mont, n_consts);
+  Expr m = ld_expr(nodes_m, n_nodes_m, consts_mont, n_consts);
+  Fr gamma = ld_fr(gamma_mont);
+  std::vector<Fr> g(k);
+  for (size_t i = 0; i < ((size_t)1 << num_vars); i++) {
+    for (size_t t = 0; t < k; t++) g[t] = ld_fr(tables_mont[t] + 32 * i);  // :46-50
+    Fr d = gamma + h.eval_point(g.data());                                   // :51
+    if (d.is_zero()) return 1;
+    Fr v = d.inverse();
+    if (n_nodes_m) v *= m.eval_point(g.data());                              // :85-87
+    st_fr(out_mont + 32 * i, v);
+  }
+  return 0;
+}
+
 }  // extern "C"

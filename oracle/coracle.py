@@ -35,6 +35,7 @@ def lib():
         _LIB.orc_g1_on_curve.restype = C.c_int
         _LIB.orc_kzg_commit_reference_shape.restype = C.c_int
         _LIB.orc_mlpcs_open.restype = C.c_int
+        _LIB.orc_logup_denominators.restype = C.c_int
     return _LIB
 
 
@@ -277,3 +278,18 @@ def mlpcs_open(bases: np.ndarray, poly: np.ndarray, point: np.ndarray, state: np
     ops = [(out[96 + 128 * i: 128 + 128 * i].copy(), out[128 + 128 * i: 160 + 128 * i].copy(),
             out[160 + 128 * i: 224 + 128 * i].copy()) for i in range(4)]
     return dict(evaluation=out[:32].copy(), s_comm=out[32:96].copy(), openings=ops)
+
+
+def logup_denominators(num_vars, tables, nodes_h, nodes_m, consts, gamma):
+    """multiset_check.rs:43-95.  nodes_m = [] for Equality mode.  Raises ZeroDivisionError like the reference's unwrap."""
+    tabs = [np.ascontiguousarray(t, dtype=np.uint8).reshape(-1, 32) for t in tables]
+    ptrs = (C.c_void_p * len(tabs))(*[t.ctypes.data for t in tabs])
+    nh, cs = _expr_arrays(nodes_h, consts)
+    nm = np.ascontiguousarray(np.array(nodes_m, dtype=np.uint32).reshape(-1, 3))
+    out = np.zeros((1 << num_vars, 32), dtype=np.uint8)
+    rc = lib().orc_logup_denominators(C.c_size_t(num_vars), C.c_size_t(len(tabs)), ptrs, _p(nh), C.c_size_t(nh.shape[0]),
+                                      _p(nm), C.c_size_t(nm.shape[0]), _p(cs), C.c_size_t(cs.shape[0]),
+                                      _p(np.ascontiguousarray(gamma, dtype=np.uint8)), _p(out))
+    if rc:
+        raise ZeroDivisionError("inverse of zero")
+    return out

@@ -6,5 +6,5 @@ hand-written sm_100a CUDA kernels inside libquill_b200.so; there is no CPU fallb
 from ._lib import QuillError, load  # noqa: F401
 from .api import (  # noqa: F401
     Context, DeviceBuffer, EvaluationClaim, KZG, KZGOpeningProof, MLEvalProof, SRS, SumcheckProof, Transcript,
-    VirtualPolyExpr, VirtualPolynomialStore, ZeroCheckProof, fast_eq_eval_hypercube,
+    VirtualPolyExpr, VirtualPolynomialStore, ZeroCheckProof, fast_eq_eval_hypercube, logup_denominators,
 )

@@ -22,7 +22,7 @@ SYMBOLS = [
     "qz_transcript_append_fr", "qz_transcript_append_g1", "qz_g1_serialize",
     "qz_srs_upload", "qz_srs_generate", "qz_srs_free", "qz_srs_len", "qz_srs_download",
     "qz_msm", "qz_kzg_commit", "qz_kzg_open", "qz_mlpcs_open", "qz_compute_s_polynomial",
-    "qz_sumcheck_prove", "qz_zerocheck_prove", "qz_eq_table",
+    "qz_sumcheck_prove", "qz_zerocheck_prove", "qz_eq_table", "qz_logup_denominators",
     "qz_comm_unique_id", "qz_comm_init", "qz_msm_sharded", "qz_sumcheck_prove_sharded",
     "qz_last_elapsed_ms", "qz_bench_imad", "qz_bench_fp_mul",
     "qz_test_field_op", "qz_test_g1_add", "qz_test_g1_mul",
@@ -98,6 +98,7 @@ def load():
     lib.qz_sumcheck_prove_sharded.argtypes = sc
     lib.qz_zerocheck_prove.argtypes = [vp, sz, sz, vp, i32, vp, sz, vp, sz, vp, sz, vp, vp, vp, vp, vp]
     lib.qz_eq_table.argtypes = [vp, sz, vp, vp, i32]
+    lib.qz_logup_denominators.argtypes = [vp, sz, sz, vp, i32, vp, sz, vp, sz, vp, sz, vp, vp, i32]
     lib.qz_comm_unique_id.argtypes = [vp]
     lib.qz_comm_init.argtypes = [vp, vp, i32, i32]
     lib.qz_msm_sharded.argtypes = [vp, vp, vp, sz, i32, vp]

@@ -495,3 +495,27 @@ def fast_eq_eval_hypercube(ctx: Context, n: int, point: np.ndarray) -> np.ndarra
     out = np.zeros((1 << n, 32), dtype=np.uint8)
     ctx.check(ctx.lib.qz_eq_table(ctx.h, n, _ptr(point) if n else None, _ptr(out), 0))
     return out
+
+
+def logup_denominators(ctx: Context, store: VirtualPolynomialStore, h: int, gamma: np.ndarray,
+                       multiplicities: Optional[int] = None) -> np.ndarray:
+    """hyperplonk/src/piops/multiset_check.rs:43-95: out[i] = m(row_i) / (gamma + h(row_i)); raises like the reference's
+    `.inverse().unwrap()` when a denominator is zero."""
+    nh, ch = store.virtual_polys[h].flatten()
+    consts = ch
+    nm = np.zeros((0, 3), dtype=np.uint32)
+    if multiplicities is not None:
+        nm, cm = store.virtual_polys[multiplicities].flatten()
+        nm = nm.copy()
+        nm[nm[:, 0] == 1, 1] += ch.shape[0]  # Const indices of m follow h's in the shared consts array
+        consts = np.concatenate([ch, cm]) if cm.shape[0] else ch
+    tabs, k, on_dev = store._tables()
+    out = np.zeros((1 << store.num_vars, 32), dtype=np.uint8)
+    rc = ctx.lib.qz_logup_denominators(ctx.h, store.num_vars, k, tabs, on_dev, _ptr(nh), nh.shape[0],
+                                       _ptr(np.ascontiguousarray(nm)) if nm.shape[0] else None, nm.shape[0],
+                                       _ptr(np.ascontiguousarray(consts)) if consts.shape[0] else None, consts.shape[0],
+                                       _ptr(_u8(gamma, (32,))), _ptr(out), 0)
+    if rc == _lib.QZ_ERR_INVALID_ARG and b"zero" in ctx.lib.qz_last_error(ctx.h):
+        raise ZeroDivisionError("called `Option::unwrap()` on a `None` value (inverse of zero)")
+    ctx.check(rc)
+    return out

@@ -18,6 +18,9 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
                  bool sharded);
 int eq_table_device(qz_ctx* ctx, int n, const Fr* z_dev, uint4* out_dev, uint64_t base, uint64_t n_elems);
 void comm_destroy(qz_ctx* ctx);
+int logup_denominators_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tables, int tables_on_device,
+                           const qz_expr_node* nodes_h, size_t n_nodes_h, const qz_expr_node* nodes_m, size_t n_nodes_m,
+                           const uint8_t* consts, size_t n_consts, const uint8_t* gamma, void* out, int out_on_device);
 
 // ---- small kernels behind the transcript / test hooks ----------------------------------------------------------------
 __global__ void k_draw_fr(uint8_t* state, Fr* out) { *out = tr_draw_fr(state); }
@@ -346,6 +349,13 @@ int qz_zerocheck_prove(qz_ctx* ctx, size_t num_vars, size_t k, const void* const
   if (!ctx) return QZ_ERR_INVALID_ARG;
   return sumcheck_run(ctx, num_vars, k, tables, tables_on_device, nodes, n_nodes, consts, n_consts, nullptr, state,
                       max_coeffs, out_coeffs, out_lens, out_point, out_eval, true, out_z, false);
+}
+int qz_logup_denominators(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tables, int tables_on_device,
+                          const qz_expr_node* nodes_h, size_t n_nodes_h, const qz_expr_node* nodes_m, size_t n_nodes_m,
+                          const uint8_t* consts, size_t n_consts, const uint8_t gamma[32], void* out, int out_on_device) {
+  if (!ctx) return QZ_ERR_INVALID_ARG;
+  return logup_denominators_run(ctx, num_vars, k, tables, tables_on_device, nodes_h, n_nodes_h, nodes_m, n_nodes_m, consts,
+                                n_consts, gamma, out, out_on_device);
 }
 int qz_eq_table(qz_ctx* c, size_t n, const uint8_t* point, void* out, int out_on_device) {
   if (!c || (n && !point) || !out || n >= (size_t)SC_MAX_VARS) return QZ_ERR_INVALID_ARG;

@@ -312,6 +312,52 @@ __global__ void sc_set_state(ScHead* head, const uint8_t* state) {
   head->evaluation = fp_zero<FrParams>();
 }
 
+
+// ---- logup denominators (hyperplonk/src/piops/multiset_check.rs:43-95) -----------------------------------------------------------
+// out[i] = m(row_i) / (gamma + h(row_i)).  The reference inverts every row separately (`.inverse().unwrap()`, :51,:63);
+// here a thread owns LOGUP_CHAIN rows strided by the block size (coalesced), multiplies them up, inverts once
+// (Montgomery's trick: 3 products per row + one Fermat inversion per chain) and walks back.  A zero denominator makes
+// the reference panic; it is reported through `err`.
+constexpr int LOGUP_CHAIN = 32;
+__global__ void __launch_bounds__(128) logup_denominators(ScTables tabs, uint64_t n_rows, const ScProgram* prog_h,
+                                                         const ScProgram* prog_m, const Fr* consts, Fr gamma,
+                                                         uint4* out, uint4* scratch, int* err) {
+  __shared__ uint32_t s_ops[2][SC_MAX_OPS];
+  const uint32_t nh = prog_h->n_ops, nm = prog_m ? prog_m->n_ops : 0;
+  const int k = (int)prog_h->k;  // both programs index the same dense table list
+  for (uint32_t i = threadIdx.x; i < nh; i += blockDim.x) s_ops[0][i] = prog_h->ops[i];
+  for (uint32_t i = threadIdx.x; i < nm; i += blockDim.x) s_ops[1][i] = prog_m->ops[i];
+  __syncthreads();
+  const uint64_t tile = (uint64_t)blockIdx.x * blockDim.x * LOGUP_CHAIN;
+  Fr prod = fp_one<FrParams>();
+  int cnt = 0;
+  for (int j = 0; j < LOGUP_CHAIN; j++) {
+    const uint64_t i = tile + (uint64_t)j * blockDim.x + threadIdx.x;
+    if (i >= n_rows) break;
+    Fr vals[SC_MAX_K];
+    for (int t = 0; t < k; t++) vals[t] = ld_elem(tabs.in[t], i);
+    const Fr v = fp_add<FrParams>(gamma, sc_eval_program(s_ops[0], nh, consts, vals));
+    if (fp_is_zero<FrParams>(v)) atomicExch(err, 1);
+    st_elem(scratch, i, prod);  // product of the chain's earlier denominators
+    st_elem(out, i, v);
+    prod = fp_mul<FrParams>(prod, v);
+    cnt++;
+  }
+  Fr inv = fp_inv<FrParams>(prod);
+  for (int j = cnt - 1; j >= 0; j--) {
+    const uint64_t i = tile + (uint64_t)j * blockDim.x + threadIdx.x;
+    const Fr v = ld_elem(out, i);
+    Fr d = fp_mul<FrParams>(inv, ld_elem(scratch, i));  // 1 / v_j
+    inv = fp_mul<FrParams>(inv, v);
+    if (nm) {
+      Fr vals[SC_MAX_K];
+      for (int t = 0; t < k; t++) vals[t] = ld_elem(tabs.in[t], i);
+      d = fp_mul<FrParams>(d, sc_eval_program(s_ops[1], nm, consts, vals));  // :85-87
+    }
+    st_elem(out, i, d);
+  }
+}
+
 }  // namespace qz
 
 // =====================================================================================================================
@@ -445,6 +491,98 @@ int eq_table_device(qz_ctx* ctx, int n, const Fr* z_dev, uint4* out_dev, uint64_
   QZ_LAUNCH(ctx, eq_half_tables, (unsigned)((small + 127) / 128), 128, 0, z_dev, n, a, lo_tab, hi_tab);
   int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n_elems + 255) / 256, (uint64_t)ctx->sm_count * 8));
   QZ_LAUNCH(ctx, eq_expand, grid, 256, 0, lo_tab, hi_tab, a, base, n_elems, out_dev);
+  return QZ_OK;
+}
+
+// multiset_check.rs:43-95: out[i] = m(row_i) / (gamma + h(row_i)); m omitted (n_nodes_m == 0) means 1
+int logup_denominators_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tables, int tables_on_device,
+                           const qz_expr_node* nodes_h, size_t n_nodes_h, const qz_expr_node* nodes_m, size_t n_nodes_m,
+                           const uint8_t* consts, size_t n_consts, const uint8_t* gamma, void* out, int out_on_device) {
+  if (!ctx || !gamma || !out || (k && !tables) || !nodes_h || n_nodes_h == 0 || (n_consts && !consts) ||
+      num_vars >= (size_t)SC_MAX_VARS)
+    return ctx ? ctx->fail(QZ_ERR_INVALID_ARG, "bad arguments") : QZ_ERR_INVALID_ARG;
+  QZ_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->arena_reset();
+  cudaStream_t st = ctx->stream;
+  const uint64_t N = (uint64_t)1 << num_vars;
+  // both expressions are compiled against ONE dense table list: compile m after h, sharing the remap, by joining them
+  // under a throw-away Add root and splitting the program at the boundary
+  Compiled ch, cm;
+  int rc;
+  std::vector<qz_expr_node> joined(nodes_h, nodes_h + n_nodes_h);
+  if (n_nodes_m) {
+    const uint32_t off = (uint32_t)n_nodes_h;
+    for (size_t i = 0; i < n_nodes_m; i++) {
+      qz_expr_node e = nodes_m[i];
+      if (e.op == QZ_EX_ADD || e.op == QZ_EX_MUL) {
+        e.a += off;
+        e.b += off;
+      }
+      joined.push_back(e);
+    }
+    joined.push_back(qz_expr_node{QZ_EX_ADD, off - 1, (uint32_t)joined.size() - 1});
+  }
+  Compiled cj;
+  rc = compile_expr(ctx, joined.data(), joined.size(), k, n_consts, cj);
+  if (rc) return rc;
+  // recompile each part on its own, then rewrite its Input indices into the joint numbering
+  auto remap_to_joint = [&](Compiled& c) {
+    for (uint32_t i = 0; i < c.prog.n_ops; i++) {
+      uint32_t op = c.prog.ops[i];
+      if ((op >> 16) == SC_OP_IN) {
+        uint32_t orig = c.active[op & 0xffffu], dense = 0;
+        for (uint32_t j = 0; j < cj.active.size(); j++)
+          if (cj.active[j] == orig) dense = j;
+        c.prog.ops[i] = (SC_OP_IN << 16) | dense;
+      }
+    }
+    c.prog.k = cj.prog.k;
+  };
+  rc = compile_expr(ctx, nodes_h, n_nodes_h, k, n_consts, ch);
+  if (rc) return rc;
+  remap_to_joint(ch);
+  if (n_nodes_m) {
+    rc = compile_expr(ctx, nodes_m, n_nodes_m, k, n_consts, cm);
+    if (rc) return rc;
+    remap_to_joint(cm);
+  }
+  const int ka = (int)cj.prog.k;
+  ScTables tabs;
+  memset(&tabs, 0, sizeof tabs);
+  for (int j = 0; j < ka; j++) {
+    const uint32_t orig = cj.active[j];
+    if (!tables[orig]) return ctx->fail(QZ_ERR_INVALID_ARG, "null table");
+    if (tables_on_device) {
+      tabs.in[j] = (const uint4*)tables[orig];
+    } else {
+      void* p = ctx->arena_alloc(32 * N);
+      if (!p) return ctx->fail(QZ_ERR_ALLOC, "table copy");
+      QZ_CUDA(ctx, cudaMemcpyAsync(p, tables[orig], 32 * N, cudaMemcpyHostToDevice, st));
+      tabs.in[j] = (const uint4*)p;
+    }
+  }
+  ScProgram* d_ph = (ScProgram*)ctx->arena_alloc(sizeof(ScProgram));
+  ScProgram* d_pm = n_nodes_m ? (ScProgram*)ctx->arena_alloc(sizeof(ScProgram)) : nullptr;
+  Fr* d_consts = (Fr*)ctx->arena_alloc(32 * std::max<size_t>(1, n_consts));
+  uint4* d_out = out_on_device ? (uint4*)out : (uint4*)ctx->arena_alloc(32 * N);
+  uint4* d_scratch = (uint4*)ctx->arena_alloc(32 * N);
+  int* d_err = (int*)ctx->arena_alloc(4);
+  if (!d_ph || (n_nodes_m && !d_pm) || !d_consts || !d_out || !d_scratch || !d_err)
+    return ctx->fail(QZ_ERR_ALLOC, "logup scratch");
+  QZ_CUDA(ctx, cudaMemcpyAsync(d_ph, &ch.prog, sizeof(ScProgram), cudaMemcpyHostToDevice, st));
+  if (n_nodes_m) QZ_CUDA(ctx, cudaMemcpyAsync(d_pm, &cm.prog, sizeof(ScProgram), cudaMemcpyHostToDevice, st));
+  if (n_consts) QZ_CUDA(ctx, cudaMemcpyAsync(d_consts, consts, 32 * n_consts, cudaMemcpyHostToDevice, st));
+  QZ_CUDA(ctx, cudaMemsetAsync(d_err, 0, 4, st));
+  Fr g;
+  memcpy(g.v, gamma, 32);
+  const uint64_t per_block = (uint64_t)128 * LOGUP_CHAIN;
+  QZ_LAUNCH(ctx, logup_denominators, (unsigned)((N + per_block - 1) / per_block), 128, 0, tabs, N, d_ph, d_pm, d_consts, g,
+            d_out, d_scratch, d_err);
+  int err = 0;
+  QZ_CUDA(ctx, cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, st));
+  if (!out_on_device) QZ_CUDA(ctx, cudaMemcpyAsync(out, d_out, 32 * N, cudaMemcpyDeviceToHost, st));
+  QZ_CUDA(ctx, cudaStreamSynchronize(st));
+  if (err) return ctx->fail(QZ_ERR_INVALID_ARG, "logup denominator is zero (the reference panics on inverse().unwrap())");
   return QZ_OK;
 }
 
