@@ -99,6 +99,10 @@ int qz_g1_serialize(qz_ctx* ctx, const uint8_t xy[64], uint8_t out[64]);
 int qz_srs_upload(qz_ctx* ctx, const uint8_t* xy, size_t n, qz_srs** out);
 /* Build g * tau^i, i < n, on the device (kzg.rs:44-47) from an affine generator and tau (Montgomery Fr). */
 int qz_srs_generate(qz_ctx* ctx, const uint8_t g_xy[64], const uint8_t tau[32], size_t n, qz_srs** out);
+/* Optional, once per SRS: store 2^(c w) * P_i for every window w (W x the SRS in HBM; 12 GiB at 2^24 with c = 22) so that all
+ * windows of a scalar share one bucket set -- fewer additions per point, one bucket reduction, no window-combine doublings.
+ * window_bits = 0 picks c from the SRS size.  Later MSMs use the table whenever the cost model says it is cheaper. */
+int qz_srs_precompute(qz_ctx* ctx, qz_srs* srs, int window_bits);
 void qz_srs_free(qz_srs* srs);
 size_t qz_srs_len(const qz_srs* srs);
 int qz_srs_download(qz_ctx* ctx, const qz_srs* srs, size_t first, size_t count, uint8_t* out_xy);

@@ -20,7 +20,7 @@ SYMBOLS = [
     "qz_dev_alloc", "qz_dev_free", "qz_dev_upload", "qz_dev_download", "qz_dev_random_fr",
     "qz_transcript_new", "qz_transcript_append_bytes", "qz_transcript_draw_challenge", "qz_transcript_draw_fr",
     "qz_transcript_append_fr", "qz_transcript_append_g1", "qz_g1_serialize",
-    "qz_srs_upload", "qz_srs_generate", "qz_srs_free", "qz_srs_len", "qz_srs_download",
+    "qz_srs_upload", "qz_srs_generate", "qz_srs_precompute", "qz_srs_free", "qz_srs_len", "qz_srs_download",
     "qz_msm", "qz_kzg_commit", "qz_kzg_open", "qz_mlpcs_open", "qz_compute_s_polynomial",
     "qz_sumcheck_prove", "qz_zerocheck_prove", "qz_eq_table", "qz_logup_denominators",
     "qz_comm_unique_id", "qz_comm_init", "qz_msm_sharded", "qz_sumcheck_prove_sharded",
@@ -83,6 +83,7 @@ def load():
     lib.qz_g1_serialize.argtypes = [vp, vp, vp]
     lib.qz_srs_upload.argtypes = [vp, vp, sz, C.POINTER(vp)]
     lib.qz_srs_generate.argtypes = [vp, vp, vp, sz, C.POINTER(vp)]
+    lib.qz_srs_precompute.argtypes = [vp, vp, i32]
     lib.qz_srs_free.argtypes = [vp]
     lib.qz_srs_free.restype = None
     lib.qz_srs_len.argtypes = [vp]

@@ -268,6 +268,11 @@ class KZG:
         ctx.check(ctx.lib.qz_srs_generate(ctx.h, _ptr(_u8(g1, (64,))), _ptr(_u8(tau, (32,))), max_degree + 1, C.byref(h)))
         return cls(ctx, SRS(ctx, h))
 
+    def precompute(self, window_bits: int = 0) -> "KZG":
+        """One-time: store the window multiples 2^(c w) P_i on the device (qz_srs_precompute)."""
+        self.ctx.check(self.ctx.lib.qz_srs_precompute(self.ctx.h, self.srs.h, window_bits))
+        return self
+
     def commit(self, polynomial) -> np.ndarray:
         """kzg.rs:61-73.  Raises AssertionError like the reference's assert! when the polynomial is too long."""
         ptr, on_dev, n = self._coeffs(polynomial)

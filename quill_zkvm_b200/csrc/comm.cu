@@ -129,7 +129,7 @@ int qz_msm_sharded(qz_ctx* ctx, const qz_srs* srs, const void* scalars, size_t n
   uint8_t* all = (uint8_t*)ctx->arena_alloc((size_t)128 * ctx->nranks);
   uint8_t* out_dev = (uint8_t*)ctx->arena_alloc(64);
   if (!mine || !all || !out_dev) return ctx->fail(QZ_ERR_ALLOC, "result");
-  int rc = msm_device(ctx, srs->bases, sdev, n, mine, nullptr);
+  int rc = msm_device(ctx, srs, sdev, n, mine, nullptr);
   if (rc) return rc;
   rc = comm_allgather(ctx, mine, all, 128);
   if (rc) return rc;

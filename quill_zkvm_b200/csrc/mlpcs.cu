@@ -364,7 +364,7 @@ int qz_mlpcs_open(qz_ctx* ctx, const qz_srs* srs, const void* poly, size_t n, in
     s_commit_len = t;
   }
   if (n > srs->n + 1) return ctx->fail(QZ_ERR_DEGREE, "Polynomial degree exceeds max degree");  // open(poly): quotient
-  rc = msm_device(ctx, srs->bases, d_s, s_commit_len, nullptr, d_scomm);  // mlpcs.rs:97
+  rc = msm_device(ctx, srs, d_s, s_commit_len, nullptr, d_scomm);  // mlpcs.rs:97
   if (rc) return rc;
   QZ_LAUNCH(ctx, mlpcs_transcript, 1, 1, 0, d_state, d_point, (int)n_point, (const Fr*)d_eval, d_scomm, d_r);
   // poly_opening, poly_opening_inv, s_opening, s_opening_inv (mlpcs.rs:109-113)
@@ -373,9 +373,9 @@ int qz_mlpcs_open(qz_ctx* ctx, const qz_srs* srs, const void* poly, size_t n, in
     const Fr* x = d_r + (i & 1);
     QZ_CUDA(ctx, cudaMemcpyAsync(o, x, 32, cudaMemcpyDeviceToDevice, st));
     if (i < 2)
-      rc = kzg_open_device(ctx, srs->bases, srs->n, pdev, n, x, (Fr*)(o + 32), o + 64);
+      rc = kzg_open_device(ctx, srs, pdev, n, x, (Fr*)(o + 32), o + 64);
     else
-      rc = kzg_open_device(ctx, srs->bases, srs->n, d_s, s_commit_len, x, (Fr*)(o + 32), o + 64);
+      rc = kzg_open_device(ctx, srs, d_s, s_commit_len, x, (Fr*)(o + 32), o + 64);
     if (rc) return rc;
   }
   uint8_t* pin = (uint8_t*)ctx->pinned_buf(96 + 512 + 32);

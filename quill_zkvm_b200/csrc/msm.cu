@@ -32,8 +32,10 @@ constexpr int RED_SEG = 32;          // buckets per bucket-reduce thread
 constexpr uint32_t KEY_NONE = 0xffffffffu;
 
 // ---- 1. digits ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) msm_digits(const uint4* scalars, uint32_t n, int c, int W, uint32_t* keys,
-                                                  uint32_t* vals) {
+// collapse_stride != 0: all windows share one bucket set (key = |digit|) and the value addresses the precomputed
+// multiple 2^(c w) P_i stored at index w * collapse_stride + i (see srs_precompute)
+__global__ void __launch_bounds__(256) msm_digits(const uint4* scalars, uint32_t n, int c, int W, uint32_t collapse_stride,
+                                                  uint32_t* keys, uint32_t* vals) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const Fr k = fp_from_mont<FrParams>(fp_load<FrParams>(scalars + 2 * (size_t)i));
@@ -52,8 +54,8 @@ __global__ void __launch_bounds__(256) msm_digits(const uint4* scalars, uint32_t
       neg = 1;
       carry = 1;
     }
-    keys[(size_t)w * n + i] = ((uint32_t)w << c) | d;
-    vals[(size_t)w * n + i] = i | (neg << 31);
+    keys[(size_t)w * n + i] = collapse_stride ? d : (((uint32_t)w << c) | d);
+    vals[(size_t)w * n + i] = ((uint32_t)w * collapse_stride + i) | (neg << 31);
   }
 }
 
@@ -183,14 +185,17 @@ __global__ void __launch_bounds__(128) msm_bucket_reduce(const uint8_t* buckets,
   }
   xyzz_store(partial + (size_t)t * 128, acc);
 }
-// one block per window: tree-sum of that window's partials
-__global__ void __launch_bounds__(128) msm_window_sum(const uint8_t* partial, uint32_t per_window, uint8_t* window_sums) {
+// tree-sum of XYZZ points: block (w, j) adds elements [j * SUM_SPAN, (j + 1) * SUM_SPAN) of window w's `per_in` inputs
+// and writes output j of `per_out`; applied repeatedly until one point per window is left
+constexpr uint32_t SUM_SPAN = 1024;
+__global__ void __launch_bounds__(128) msm_block_sum(const uint8_t* in, uint32_t per_in, uint32_t per_out, uint8_t* out) {
   __shared__ __align__(16) uint8_t sh[128 * 128];
-  const uint32_t w = blockIdx.x;
+  const uint32_t w = blockIdx.x / per_out, j = blockIdx.x % per_out;
+  const uint32_t begin = j * SUM_SPAN, end = begin + SUM_SPAN < per_in ? begin + SUM_SPAN : per_in;
   Xyzz acc = xyzz_identity();
-  for (uint32_t i = threadIdx.x; i < per_window; i += blockDim.x) {
+  for (uint32_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
     Xyzz p;
-    xyzz_load(p, partial + ((size_t)w * per_window + i) * 128);
+    xyzz_load(p, in + ((size_t)w * per_in + i) * 128);
     acc = xyzz_add(acc, p);
   }
   xyzz_store(sh + threadIdx.x * 128, acc);
@@ -207,7 +212,7 @@ __global__ void __launch_bounds__(128) msm_window_sum(const uint8_t* partial, ui
   if (threadIdx.x == 0) {
     Xyzz r;
     xyzz_load(r, sh);
-    xyzz_store(window_sums + (size_t)w * 128, r);
+    xyzz_store(out + ((size_t)w * per_out + j) * 128, r);
   }
 }
 
@@ -277,6 +282,24 @@ __global__ void __launch_bounds__(128) srs_generate(const uint8_t* table, Fr tau
     }
     affine_store(out + i * 64, xyzz_to_affine(acc));
     ti = fp_mul<FrParams>(ti, tau);
+  }
+}
+
+// pre[w * n + i] = 2^(c w) * P_i (affine), w < W: with these multiples every window of a scalar lands in ONE shared set
+// of buckets, so an MSM needs ceil(256 / c) * n mixed additions with a c far larger than a per-window bucket array
+// would allow (c = 22, 12 additions per point at n = 2^24 instead of 16), one bucket reduction and no window-combine
+// doublings.  It costs W x the SRS in HBM (12 GiB at 2^24): a trade a 180 GB part can make.
+__global__ void __launch_bounds__(128) srs_precompute(const uint8_t* bases, uint64_t n, int c, int W, uint8_t* pre) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Affine p = affine_load(bases + i * 64);
+  affine_store(pre + i * 64, p);
+  Xyzz acc = xyzz_from_affine(p);
+  for (int w = 1; w < W; w++) {
+    for (int j = 0; j < c; j++) acc = xyzz_dbl(acc);
+    const Affine a = xyzz_to_affine(acc);
+    affine_store(pre + ((uint64_t)w * n + i) * 64, a);
+    acc = xyzz_from_affine(a);
   }
 }
 
@@ -364,23 +387,29 @@ using namespace qz;
 
 namespace qz {
 
-// window size: minimise n*W mixed adds (10 mults) + W * 2^(c-1) * 2 full adds (14 mults) in the reduction
+// cost model (in field multiplications): n*W mixed adds (10) + the bucket reduction, 2 full adds (14) per bucket, which
+// is latency-bound and therefore weighted x4
+static double msm_cost(size_t n, int c, bool collapsed) {
+  const int W = (256 + c - 1) / c;
+  const double buckets = (double)(1ull << (c - 1)) * (collapsed ? 1 : W);
+  return (double)n * W * 10.0 + buckets * 2.0 * 14.0 * 4.0;
+}
 static int pick_window(size_t n) {
   int best = 4;
-  double best_cost = 1e300;
-  for (int c = 4; c <= 16; c++) {
-    int W = (256 + c - 1) / c;
-    double cost = (double)n * W * 10.0 + (double)W * (double)(1u << (c - 1)) * 2.0 * 14.0 * 4.0;  // reduce is latency-bound: weight x4
-    if (cost < best_cost) {
-      best_cost = cost;
-      best = c;
-    }
-  }
+  for (int c = 4; c <= 16; c++)
+    if (msm_cost(n, c, false) < msm_cost(n, best, false)) best = c;
+  return best;
+}
+int pick_precompute_window(size_t n) {
+  int best = 8;
+  for (int c = 8; c <= 24; c++)
+    if (msm_cost(n, c, true) < msm_cost(n, best, true)) best = c;
   return best;
 }
 
 // scalars_dev: n Montgomery Fr on the device.  Writes the result as XYZZ (128 B, device) and/or affine (64 B, device).
-int msm_device(qz_ctx* ctx, const uint8_t* bases, const uint4* scalars_dev, size_t n, uint8_t* out_xyzz_dev,
+// `srs` supplies the bases and, when present and cheaper by the cost model, the precomputed window multiples.
+int msm_device(qz_ctx* ctx, const qz_srs* srs, const uint4* scalars_dev, size_t n, uint8_t* out_xyzz_dev,
                uint8_t* out_affine_dev) {
   cudaStream_t st = ctx->stream;
   if (n == 0) {  // empty sum = identity (reachable: commit(&[]) for the quotient of a constant, mlpcs.rs:321-393)
@@ -390,9 +419,13 @@ int msm_device(qz_ctx* ctx, const uint8_t* bases, const uint4* scalars_dev, size
   }
   if (n >= ((size_t)1 << 31)) return ctx->fail(QZ_ERR_INVALID_ARG, "MSM size must be below 2^31");
   auto mark = ctx->arena_mark();
-  const int c = pick_window(n);
-  const int W = (256 + c - 1) / c;
-  const uint64_t m = (uint64_t)W * n;
+  int c = pick_window(n);
+  const bool collapsed = srs->pre && msm_cost(n, srs->pre_c, true) < msm_cost(n, c, false);
+  if (collapsed) c = srs->pre_c;
+  const int Wd = (256 + c - 1) / c;       // digits per scalar
+  const int W = collapsed ? 1 : Wd;       // bucket sets
+  const uint8_t* bases = collapsed ? srs->pre : srs->bases;
+  const uint64_t m = (uint64_t)Wd * n;
   if (m >= ((uint64_t)1 << 32)) return ctx->fail(QZ_ERR_INVALID_ARG, "MSM too large for 32-bit positions");
   const uint32_t n_keys = (uint32_t)W << c, per_w = 1u << (c - 1), n_slots = (uint32_t)W * per_w;
   const uint64_t n_chunks = (m + ACC_CHUNK - 1) / ACC_CHUNK;
@@ -412,17 +445,19 @@ int msm_device(qz_ctx* ctx, const uint8_t* bases, const uint4* scalars_dev, size
   const int seg = per_w >= RED_SEG ? RED_SEG : (int)per_w;
   const uint32_t red_threads = n_slots / seg, per_window_parts = per_w / seg;
   uint8_t* partial = (uint8_t*)ctx->arena_alloc((size_t)red_threads * 128);
+  uint8_t* partial2 = (uint8_t*)ctx->arena_alloc((size_t)W * ((per_window_parts + SUM_SPAN - 1) / SUM_SPAN) * 128);
   uint8_t* window_sums = (uint8_t*)ctx->arena_alloc((size_t)W * 128);
   size_t sort_bytes = 0;
   cub::DoubleBuffer<uint32_t> dk(keys, keys2), dv(vals, vals2);
   cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, dk, dv, (int64_t)m, 0, key_bits, st);
   void* sort_tmp = ctx->arena_alloc(sort_bytes);
   if (!keys || !vals || !keys2 || !vals2 || !first || !buckets || !heads || !tails || !head_key || !tail_key ||
-      !partial || !window_sums || !sort_tmp)
+      !partial || !partial2 || !window_sums || !sort_tmp)
     return ctx->fail(QZ_ERR_ALLOC, "MSM scratch");
   uint32_t* last = first + n_keys;
 
-  QZ_LAUNCH(ctx, msm_digits, (unsigned)((n + 255) / 256), 256, 0, scalars_dev, (uint32_t)n, c, W, keys, vals);
+  QZ_LAUNCH(ctx, msm_digits, (unsigned)((n + 255) / 256), 256, 0, scalars_dev, (uint32_t)n, c, Wd,
+            collapsed ? (uint32_t)srs->n : 0u, keys, vals);
   QZ_CUDA(ctx, cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, dk, dv, (int64_t)m, 0, key_bits, st));
   ctx->launches += 2 + (key_bits + 7) / 8;  // CUB: histogram + one onesweep pass per 8 key bits (approximate)
   const uint32_t* skeys = dk.Current();
@@ -440,7 +475,20 @@ int msm_device(qz_ctx* ctx, const uint8_t* bases, const uint4* scalars_dev, size
   QZ_LAUNCH(ctx, msm_bucket_finish, (n_slots + 127) / 128, 128, 0, first, last, m, c, W, heads, tails, head_key,
             tail_key, buckets);
   QZ_LAUNCH(ctx, msm_bucket_reduce, (red_threads + 127) / 128, 128, 0, buckets, c, W, seg, partial);
-  QZ_LAUNCH(ctx, msm_window_sum, W, 128, 0, partial, per_window_parts, window_sums);
+  {  // per window: per_window_parts partial sums -> 1
+    const uint8_t* in = partial;
+    uint32_t per_in = per_window_parts;
+    uint8_t* bufs[2] = {partial2, partial};
+    int flip = 0;
+    while (per_in > SUM_SPAN) {
+      const uint32_t per_out = (per_in + SUM_SPAN - 1) / SUM_SPAN;
+      QZ_LAUNCH(ctx, msm_block_sum, (unsigned)W * per_out, 128, 0, in, per_in, per_out, bufs[flip]);
+      in = bufs[flip];
+      per_in = per_out;
+      flip ^= 1;
+    }
+    QZ_LAUNCH(ctx, msm_block_sum, (unsigned)W, 128, 0, in, per_in, 1u, window_sums);
+  }
   QZ_LAUNCH(ctx, msm_combine, 1, 1, 0, window_sums, c, W, out_xyzz_dev, out_affine_dev);
   ctx->arena_release(mark);  // stream order keeps the scratch valid for the kernels enqueued above
   return QZ_OK;
@@ -449,7 +497,7 @@ int msm_device(qz_ctx* ctx, const uint8_t* bases, const uint4* scalars_dev, size
 // KZG::open (kzg.rs:75-96) with everything on the device: x is read from device memory, y (32 B) and the affine proof
 // (64 B) are written to device memory.  Asynchronous on ctx->stream; scratch is released on return (stream order keeps
 // it valid for the kernels already enqueued).
-int kzg_open_device(qz_ctx* ctx, const uint8_t* bases, size_t srs_n, const uint4* pdev, size_t n_coeffs, const Fr* x_dev,
+int kzg_open_device(qz_ctx* ctx, const qz_srs* srs, const uint4* pdev, size_t n_coeffs, const Fr* x_dev,
                     Fr* y_dev, uint8_t* proof_affine_dev) {
   cudaStream_t st = ctx->stream;
   if (n_coeffs == 0) {  // zero polynomial: y = 0, quotient = 0, proof = identity
@@ -476,8 +524,8 @@ int kzg_open_device(qz_ctx* ctx, const uint8_t* bases, size_t srs_n, const uint4
   QZ_LAUNCH(ctx, open_carry_expand, (unsigned)((ngroups + 255) / 256), 256, 0, h, nchunks, pw, group, gcarry, carry);
   QZ_LAUNCH(ctx, open_write, (unsigned)((nchunks + 127) / 128), 128, 0, pdev, n, x_dev, carry, q, y_dev);
   // commit(q): trailing zero coefficients contribute nothing, so trimming (DensePolynomial) is value-neutral
-  const size_t qn = std::min<size_t>(n - 1, srs_n);
-  int rc = msm_device(ctx, bases, q, qn, nullptr, proof_affine_dev);
+  const size_t qn = std::min<size_t>(n - 1, srs->n);
+  int rc = msm_device(ctx, srs, q, qn, nullptr, proof_affine_dev);
   ctx->arena_release(mark);
   return rc;
 }
@@ -494,7 +542,7 @@ extern "C" {
 int qz_srs_upload(qz_ctx* ctx, const uint8_t* xy, size_t n, qz_srs** out) {
   if (!ctx || !out || (n && !xy)) return QZ_ERR_INVALID_ARG;
   QZ_CUDA(ctx, cudaSetDevice(ctx->device));
-  qz_srs* s = new (std::nothrow) qz_srs{ctx, nullptr, n};
+  qz_srs* s = new (std::nothrow) qz_srs{ctx, nullptr, n, nullptr, 0, 0};
   if (!s) return ctx->fail(QZ_ERR_ALLOC, "srs handle");
   cudaError_t e = cudaMalloc((void**)&s->bases, n ? n * 64 : 64);
   if (e != cudaSuccess) {
@@ -518,7 +566,7 @@ int qz_srs_generate(qz_ctx* ctx, const uint8_t g_xy[64], const uint8_t tau[32], 
   if (!ctx || !out || !g_xy || !tau) return QZ_ERR_INVALID_ARG;
   QZ_CUDA(ctx, cudaSetDevice(ctx->device));
   ctx->arena_reset();
-  qz_srs* s = new (std::nothrow) qz_srs{ctx, nullptr, n};
+  qz_srs* s = new (std::nothrow) qz_srs{ctx, nullptr, n, nullptr, 0, 0};
   if (!s) return ctx->fail(QZ_ERR_ALLOC, "srs handle");
   cudaError_t e = cudaMalloc((void**)&s->bases, n ? n * 64 : 64);
   if (e != cudaSuccess) {
@@ -548,10 +596,34 @@ int qz_srs_generate(qz_ctx* ctx, const uint8_t g_xy[64], const uint8_t tau[32], 
   return QZ_OK;
 }
 
+int qz_srs_precompute(qz_ctx* ctx, qz_srs* s, int window_bits) {
+  if (!ctx || !s || window_bits < 0 || window_bits > 24 || (window_bits && window_bits < 4)) return QZ_ERR_INVALID_ARG;
+  if (s->n == 0) return QZ_OK;
+  QZ_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int c = window_bits ? window_bits : pick_precompute_window(s->n);
+  const int W = (256 + c - 1) / c;
+  if ((uint64_t)W * s->n >= ((uint64_t)1 << 31)) return ctx->fail(QZ_ERR_INVALID_ARG, "precomputed table index exceeds 31 bits");
+  if (s->pre) {
+    cudaFree(s->pre);
+    s->pre = nullptr;
+  }
+  cudaError_t e = cudaMalloc((void**)&s->pre, (size_t)W * s->n * 64);
+  if (e != cudaSuccess) {
+    s->pre = nullptr;
+    return ctx->fail(QZ_ERR_ALLOC, "precomputed window multiples", e);
+  }
+  s->pre_c = c;
+  s->pre_W = W;
+  QZ_LAUNCH(ctx, srs_precompute, (unsigned)((s->n + 127) / 128), 128, 0, s->bases, (uint64_t)s->n, c, W, s->pre);
+  QZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return QZ_OK;
+}
+
 void qz_srs_free(qz_srs* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);
   cudaFree(s->bases);
+  if (s->pre) cudaFree(s->pre);
   delete s;
 }
 size_t qz_srs_len(const qz_srs* s) { return s ? s->n : 0; }
@@ -582,7 +654,7 @@ int qz_msm(qz_ctx* ctx, const qz_srs* srs, const void* scalars, size_t n_scalars
   if (!out_dev) return ctx->fail(QZ_ERR_ALLOC, "result");
   QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k0, st));
   QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k1, st));
-  int rc = msm_device(ctx, srs->bases, sdev, n, nullptr, out_dev);
+  int rc = msm_device(ctx, srs, sdev, n, nullptr, out_dev);
   if (rc) return rc;
   QZ_CUDA(ctx, cudaMemcpyAsync(out_xy, out_dev, 64, cudaMemcpyDeviceToHost, st));
   QZ_CUDA(ctx, cudaEventRecord(ctx->ev_call1, st));
@@ -621,7 +693,7 @@ int qz_kzg_open(qz_ctx* ctx, const qz_srs* srs, const void* coeffs, size_t n_coe
     QZ_CUDA(ctx, cudaMemcpyAsync(p, coeffs, 32 * n_coeffs, cudaMemcpyHostToDevice, st));
     pdev = (const uint4*)p;
   }
-  int rc = kzg_open_device(ctx, srs->bases, srs->n, pdev, n_coeffs, (const Fr*)(res + 32), (Fr*)res, res + 64);
+  int rc = kzg_open_device(ctx, srs, pdev, n_coeffs, (const Fr*)(res + 32), (Fr*)res, res + 64);
   if (rc) return rc;
   uint8_t* pin = (uint8_t*)ctx->pinned_buf(192);
   if (!pin) return ctx->fail(QZ_ERR_ALLOC, "pinned");

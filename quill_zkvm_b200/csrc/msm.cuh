@@ -9,15 +9,17 @@ struct qz_srs {
   qz_ctx* ctx;
   uint8_t* bases;  // n affine G1 points on the device, 64 B each (x ‖ y Montgomery; all-zero = infinity)
   size_t n;
+  uint8_t* pre;    // optional: pre_W x n affine points, pre[w * n + i] = 2^(pre_c * w) * bases[i] (qz_srs_precompute)
+  int pre_c, pre_W;
 };
 
 namespace qz {
-// sum_i scalars[i] * bases[i], i < n; scalars are Montgomery Fr on the device.  The result is written to device
+// sum_i scalars[i] * srs->bases[i], i < n; scalars are Montgomery Fr on the device.  The result is written to device
 // memory as XYZZ (128 B) and/or affine (64 B); either pointer may be null.  Asynchronous on ctx->stream.
-int msm_device(qz_ctx* ctx, const uint8_t* bases, const uint4* scalars_dev, size_t n, uint8_t* out_xyzz_dev,
+int msm_device(qz_ctx* ctx, const qz_srs* srs, const uint4* scalars_dev, size_t n, uint8_t* out_xyzz_dev,
                uint8_t* out_affine_dev);
 // KZG::open on the device: x read from device memory, y (32 B) and the affine proof (64 B) written to device memory
-int kzg_open_device(qz_ctx* ctx, const uint8_t* bases, size_t srs_n, const uint4* pdev, size_t n_coeffs,
+int kzg_open_device(qz_ctx* ctx, const qz_srs* srs, const uint4* pdev, size_t n_coeffs,
                     const Fp<FrParams>* x_dev, Fp<FrParams>* y_dev, uint8_t* proof_affine_dev);
 // affine(sum of n XYZZ points on the device) -> out_affine_dev (64 B)
 int msm_sum_points_launch(qz_ctx* ctx, const uint8_t* pts_dev, int n, uint8_t* out_affine_dev);

@@ -163,3 +163,37 @@ def test_msm_2_24_closed_form(ctx):
     kzg.srs.free()
     y, _ = co.kzg_open_quotient(sc, co.fr1(TAU))
     assert np.array_equal(got, co.g1_mul(co.g1_to_bytes(GEN), y))
+
+
+@pytest.mark.parametrize("c", [4, 8, 13, 16, 0])
+def test_precomputed_windows_small(ctx, c):
+    """qz_srs_precompute: every window shares one bucket set; results must not change"""
+    n = 3000
+    srs = co.srs_generate(co.g1_to_bytes(GEN), co.fr1(TAU), n, threads=4)
+    srs[7] = 0  # a point at infinity inside the SRS
+    kz = q.KZG.from_points(ctx, srs).precompute(c)
+    rnd = random.Random(c)
+    cases = [util.rand_fr(n, 3 + c), co.to_mont([rnd.randrange(4) for _ in range(n)]), co.to_mont([FR - 1] * n),
+             util.rand_fr(17, 1), np.zeros((0, 32), np.uint8), co.to_mont([1])]
+    for s in cases:
+        assert np.array_equal(kz.commit(s), co.msm(srs, s, mode=1, threads=os.cpu_count() or 1))
+    pr = kz.open(cases[0], co.fr1(12345))
+    y, qpoly = co.kzg_open_quotient(cases[0], co.fr1(12345))
+    assert np.array_equal(pr.y, y) and np.array_equal(pr.proof, co.msm(srs, qpoly, mode=1, threads=4))
+    kz.srs.free()
+
+
+def test_precomputed_windows_2_20_and_2_24(ctx):
+    for logn in (20, 24):
+        n = 1 << logn
+        kzg = q.KZG.trusted_setup(ctx, n - 1, co.g1_to_bytes(GEN), co.fr1(TAU)).precompute()
+        buf = ctx.random_fr(n, 31 + logn)
+        sc = buf.download().reshape(-1, 32)
+        got = kzg.commit(buf)
+        half = kzg.commit(sc[: n // 2 + 3])  # a shorter polynomial on the same table
+        buf.free()
+        kzg.srs.free()
+        y, _ = co.kzg_open_quotient(sc, co.fr1(TAU))
+        assert np.array_equal(got, co.g1_mul(co.g1_to_bytes(GEN), y)), logn
+        y2, _ = co.kzg_open_quotient(sc[: n // 2 + 3], co.fr1(TAU))
+        assert np.array_equal(half, co.g1_mul(co.g1_to_bytes(GEN), y2)), logn
