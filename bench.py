@@ -230,7 +230,7 @@ def run_gpu(args):
         g_bytes = ctx.g1_mul(g_bytes.reshape(1, 64), mont(pow(TAU, lo, FR)).reshape(1, 32))[0]  # g * tau^lo on the device
     kzg = q.KZG.trusted_setup(ctx, n_loc - 1, g_bytes, mont(TAU))  # SRS shard: g * tau^(lo + i)
     if not args.no_precompute:
-        kzg.precompute()  # one-time, like the SRS upload: window multiples 2^(c w) P_i resident in HBM
+        kzg.precompute(args.precompute_bits)  # one-time, like the SRS upload: window multiples 2^(c w) P_i in HBM
     scal_dev = ctx.random_fr(n_loc, 0x5155494C4C + rank)
     pin_scal = torch.empty(n_loc * 32, dtype=torch.uint8, pin_memory=True)
     scal_host = pin_scal.numpy()
@@ -360,6 +360,7 @@ def main():
     ap.add_argument("--ref-sc-log-n", type=int, default=20, help="--impl reference: sumcheck sample size per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-precompute", action="store_true", help="MSM without the precomputed window multiples")
+    ap.add_argument("--precompute-bits", type=int, default=0, help="window bits of the precomputed table (0 = auto)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = max(args.warmup, 1)

@@ -33,6 +33,8 @@ if what in ("sumcheck", "zerocheck"):
 else:
     g = np.concatenate([mont(1, FQ), mont(2, FQ)])
     kzg = q.KZG.trusted_setup(ctx, (1 << n) - 1, g, mont(0x1234567))
+    if len(sys.argv) > 3 and sys.argv[3] == "pre":
+        kzg.precompute()
     sc = ctx.random_fr(1 << n, 9)
     for rep in range(2):
         kzg.commit(sc)

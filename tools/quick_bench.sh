@@ -1,7 +1,7 @@
 #!/bin/bash
 # quick GPU check used during development: gpu tests (optional) + bench summary
 if [ "$1" == "test" ]; then timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/t_all.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/t_all.log; fi
-python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_q.log 2>gpurun_out/bench_q.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_q.err
+python bench.py --steps 3 --warmup 3 --no-cpu-baseline $QB_ARGS > gpurun_out/bench_q.log 2>gpurun_out/bench_q.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_q.err
 python - <<'PY'
 import json
 d=json.loads(open("gpurun_out/bench_q.log").read().strip().splitlines()[-1])
