@@ -29,6 +29,8 @@ FR = 218882428718392752222464057452572750885483644004160343436982041865758084956
 TAU = 0x1234567890ABCDEF1234567890ABCDEF
 MSM_LIMB_PRODUCTS_PER_POINT = 20480  # 16 windows x (8M + 2S) x 128 32x32->64 products per Montgomery mult
 SC_BYTES_PER_ELEM = 128              # 4 * 32 B per input table element over the whole proof
+MSM_TRAFFIC_BYTES = None             # dram bytes of msm_accumulate from the last ncu --set full capture (profiles/), if any
+SC_TRAFFIC_BYTES = None
 
 
 def peaks():
@@ -263,6 +265,24 @@ def run_gpu(args):
     msm_ms, msm_launches = timed_loop(lambda: results.__setitem__("dev", commit(scal_dev)), args.steps, args.warmup, acc_ms)
     e2e_ms, _ = timed_loop(lambda: results.__setitem__("host", commit(scal_host.reshape(-1, 32))), args.steps, args.warmup)
     assert np.array_equal(results["dev"], results["host"]), "device-resident and host-input commitments differ"
+    msm_c, msm_digits, msm_shared, msm_adds = (ctx.last_stat(i) for i in range(4))
+
+    # ---- config 4: multilinear PCS commit + open (MLEvalProof::prove: 5 MSMs + NTT), N = 1 only ----
+    mlpcs = None
+    if world == 1 and args.mlpcs_log_n > 0:
+        nm = min(args.mlpcs_log_n, args.log_n)
+        poly = ctx.random_fr(1 << nm, 777)
+        point = np.frombuffer(b"".join(((i * 0x9E3779B97F4A7C15 + 12345) % FR).to_bytes(32, "little") for i in range(nm)),
+                              dtype=np.uint8).reshape(nm, 32).copy()
+
+        def commit_open():
+            results["ml_c"] = kzg.commit(poly)
+            results["ml_o"] = kzg.open_multilinear(poly, point, q.Transcript(b"mlpcs_bench", ctx))
+
+        ml_ms, ml_launches = timed_loop(commit_open, max(1, args.steps // 2), 1)
+        mlpcs = {"value": ml_ms * 1e-3, "unit": "s per commit+open", "log_n": nm, "gpu_launches": ml_launches // max(1, args.steps // 2),
+                 "workload": f"MultilinearPCS::commit + ::open of a 2^{nm}-entry MLE (6 MSMs, eq table, NTT 2^{nm + 1}, 4 quotients)"}
+        poly.free()
 
     # ---- sumcheck: three 2^log_n tables, degree-3 product ----
     nv = args.log_n
@@ -321,8 +341,12 @@ def run_gpu(args):
                 "kernel": "msm_accumulate", "bound": "int32-imad (integer multiply pipe; not hbm / tensor, see DESIGN.md)",
                 "achieved": n_loc * MSM_LIMB_PRODUCTS_PER_POINT / (acc_avg * 1e-3) / 1e12, "peak": imad_peak / 1e12,
                 "unit": "T limb-MAC/s", "frac": n_loc * MSM_LIMB_PRODUCTS_PER_POINT / (acc_avg * 1e-3) / imad_peak,
-                "kernel_ms": acc_avg, "kernel_share_of_step": acc_avg / msm_ms, "traffic": None,
-                "peak_source": "qz_bench_imad measured in this run"},
+                "model": "SURVEY 8(d) canonical model: 16 windows x (8M+2S) x 128 limb products = 20480 per point",
+                "executed": {"window_bits": msm_c, "mixed_adds_per_point": msm_digits, "shared_bucket_set": bool(msm_shared),
+                             "limb_macs_per_point": msm_digits * 1280,
+                             "frac_of_peak": msm_adds * 1280 / (acc_avg * 1e-3) / imad_peak},
+                "kernel_ms": acc_avg, "kernel_share_of_step": acc_avg / msm_ms, "traffic": MSM_TRAFFIC_BYTES,
+                "peak_source": "qz_bench_imad (IMAD.WIDE.U32 carry chains) measured in this run"},
             "sumcheck": {
                 "value": sc_v, "unit": "field-elems/s", "ms_per_step": sc_ms, "gpu_launches": sc_launches // args.steps,
                 "e2e": {"value": 3 * n / (sc_e2e_ms * 1e-3), "unit": "field-elems/s", "ms_per_step": sc_e2e_ms,
@@ -330,12 +354,14 @@ def run_gpu(args):
                 "roofline": {"kernel": "sc_round_prod<3> (streaming rounds, fold fused)", "bound": "hbm",
                              "achieved": SC_BYTES_PER_ELEM * 3 * t_loc / (rounds_avg * 1e-3) / 1e9, "peak": hbm_peak,
                              "unit": "GB/s", "frac": SC_BYTES_PER_ELEM * 3 * t_loc / (rounds_avg * 1e-3) / 1e9 / hbm_peak,
-                             "kernel_ms": rounds_avg, "kernel_share_of_step": rounds_avg / sc_ms, "traffic": None,
+                             "kernel_ms": rounds_avg, "kernel_share_of_step": rounds_avg / sc_ms, "traffic": SC_TRAFFIC_BYTES,
                              "peak_source": hbm_src},
             },
             "gpu_launches": msm_launches // args.steps,
             "clocks": clocks,
         }
+        if mlpcs:
+            line["mlpcs_commit_open"] = mlpcs
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line))
@@ -358,6 +384,7 @@ def main():
     ap.add_argument("--cpu-sc-log-n", type=int, default=20, help="CPU baseline sumcheck sample size")
     ap.add_argument("--ref-log-n", type=int, default=18, help="--impl reference: MSM sample size per step")
     ap.add_argument("--ref-sc-log-n", type=int, default=20, help="--impl reference: sumcheck sample size per step")
+    ap.add_argument("--mlpcs-log-n", type=int, default=22, help="config 4: MLPCS commit+open size (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-precompute", action="store_true", help="MSM without the precomputed window multiples")
     ap.add_argument("--precompute-bits", type=int, default=0, help="window bits of the precomputed table (0 = auto)")

@@ -183,6 +183,9 @@ int qz_sumcheck_prove_sharded(qz_ctx* ctx, size_t num_vars, size_t k, const void
 /* CUDA-event timing of the most recent call on this context, on the context's stream (milliseconds):
  *   which = 0 whole call (device side), 1 dominant kernel(s) only (sumcheck round kernels / MSM bucket accumulation) */
 float qz_last_elapsed_ms(qz_ctx* ctx, int which);
+/* shape of the most recent MSM on this context: which = 0 window bits c, 1 digits (mixed additions) per scalar,
+ * 2 whether the precomputed shared bucket set was used (0/1), 3 total mixed additions */
+double qz_last_stat(const qz_ctx* ctx, int which);
 /* integer-pipe micro-benchmark: returns 32x32->64 multiply-accumulates per second sustained by all SMs (the MSM
  * roofline denominator).  variant 0 = IMAD.WIDE.U32 carry chains as used by the field multiplier, 1 = 32-bit IMAD. */
 int qz_bench_imad(qz_ctx* ctx, int variant, double* out_ops_per_s);

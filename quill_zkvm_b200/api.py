@@ -71,6 +71,9 @@ class Context:
     def last_elapsed_ms(self, which: int = 0) -> float:
         return float(self.lib.qz_last_elapsed_ms(self.h, which))
 
+    def last_stat(self, which: int) -> float:
+        return float(self.lib.qz_last_stat(self.h, which))
+
     # -- device buffers ------------------------------------------------------------------------------------------
     def alloc(self, nbytes: int) -> "DeviceBuffer":
         p = C.c_void_p()

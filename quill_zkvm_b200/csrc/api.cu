@@ -222,6 +222,7 @@ void qz_ctx_destroy(qz_ctx* c) {
 
 const char* qz_last_error(const qz_ctx* c) { return c ? c->err.c_str() : "null context"; }
 uint64_t qz_kernel_launches(const qz_ctx* c) { return c ? c->launches : 0; }
+double qz_last_stat(const qz_ctx* c, int which) { return c && which >= 0 && which < 4 ? c->last_stat[which] : -1.0; }
 float qz_last_elapsed_ms(qz_ctx* c, int which) { return c && which >= 0 && which < 2 ? c->last_ms[which] : -1.f; }
 
 int qz_ctx_sync(qz_ctx* c) {

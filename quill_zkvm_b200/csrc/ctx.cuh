@@ -30,6 +30,7 @@ struct qz_ctx {
 
   cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
   float last_ms[2] = {0.f, 0.f};
+  double last_stat[4] = {0, 0, 0, 0};  // last MSM: window bits, digits per scalar, shared bucket set (0/1), mixed additions
   float kernel_ms_accum = 0.f;
 
   // pinned staging for small results

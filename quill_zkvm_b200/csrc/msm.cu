@@ -428,6 +428,10 @@ int msm_device(qz_ctx* ctx, const qz_srs* srs, const uint4* scalars_dev, size_t 
   const int W = collapsed ? 1 : Wd;       // bucket sets
   const uint8_t* bases = collapsed ? srs->pre : srs->bases;
   const uint64_t m = (uint64_t)Wd * n;
+  ctx->last_stat[0] = c;
+  ctx->last_stat[1] = Wd;
+  ctx->last_stat[2] = collapsed ? 1 : 0;
+  ctx->last_stat[3] = (double)m;
   if (m >= ((uint64_t)1 << 32)) return ctx->fail(QZ_ERR_INVALID_ARG, "MSM too large for 32-bit positions");
   const uint32_t n_keys = (uint32_t)W << c, per_w = 1u << (c - 1), n_slots = (uint32_t)W * per_w;
   const uint64_t n_chunks = (m + ACC_CHUNK - 1) / ACC_CHUNK;
