@@ -94,12 +94,7 @@ static __device__ __noinline__ Fr tr_draw_fr(uint8_t* state) {
 // buf[0..8) = state, buf[8..) = message, zero padded to a multiple of 16 words.
 // The finalize step runs once per launch on ONE thread, so it executes cold: a fully unrolled compression (7 rounds x 8 G,
 // ~1000 straight-line instructions per call site) made instruction fetch the dominant cost (ncu r01: 77k cycles for
-// 13.7k instructions).  This copy is a loop over the rounds with the message schedule in a table, compiled once.
-__device__ __constant__ uint8_t B3_SCHEDULE[7][16] = {
-    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {2, 6, 3, 10, 7, 0, 4, 13, 1, 11, 12, 5, 9, 14, 15, 8},
-    {3, 4, 10, 12, 13, 2, 7, 14, 6, 5, 9, 0, 11, 15, 8, 1}, {10, 7, 12, 9, 14, 3, 13, 15, 4, 0, 11, 2, 5, 8, 1, 6},
-    {12, 13, 9, 11, 15, 10, 14, 8, 7, 2, 5, 3, 0, 1, 6, 4}, {9, 14, 11, 5, 8, 12, 15, 1, 13, 3, 0, 10, 2, 6, 4, 7},
-    {11, 15, 5, 0, 1, 9, 8, 6, 14, 10, 2, 12, 3, 4, 7, 13}};
+// 13.7k instructions).  This copy is a loop over the rounds (the message is permuted in registers between rounds), compiled once.
 #define QZ_G(a, b, c, d, mx, my)      \
   a = a + b + (mx);                   \
   d = __funnelshift_r(d ^ a, d ^ a, 16); \
@@ -115,12 +110,11 @@ static __device__ __noinline__ void b3_compress_loop(uint32_t* cv, const uint32_
   uint32_t s0 = cv[0], s1 = cv[1], s2 = cv[2], s3 = cv[3], s4 = cv[4], s5 = cv[5], s6 = cv[6], s7 = cv[7];
   uint32_t s8 = Blake3::iv(0), s9 = Blake3::iv(1), s10 = Blake3::iv(2), s11 = Blake3::iv(3);
   uint32_t s12 = 0, s13 = 0, s14 = block_len, s15 = flags;
-#pragma unroll 1
-  for (int r = 0; r < 7; r++) {
-    const uint8_t* sch = B3_SCHEDULE[r];
-    uint32_t w[16];
+  uint32_t w[16];
 #pragma unroll
-    for (int i = 0; i < 16; i++) w[i] = m[sch[i]];
+  for (int i = 0; i < 16; i++) w[i] = m[i];
+#pragma unroll 1
+  for (int r = 0; r < 7; r++) {  // one copy of the round in the instruction stream; the message stays in registers
     QZ_G(s0, s4, s8, s12, w[0], w[1])
     QZ_G(s1, s5, s9, s13, w[2], w[3])
     QZ_G(s2, s6, s10, s14, w[4], w[5])
@@ -129,6 +123,11 @@ static __device__ __noinline__ void b3_compress_loop(uint32_t* cv, const uint32_
     QZ_G(s1, s6, s11, s12, w[10], w[11])
     QZ_G(s2, s7, s8, s13, w[12], w[13])
     QZ_G(s3, s4, s9, s14, w[14], w[15])
+    // message permutation between rounds
+    const uint32_t t0 = w[2], t1 = w[6], t2 = w[3], t3 = w[10], t4 = w[7], t5 = w[0], t6 = w[4], t7 = w[13];
+    const uint32_t t8 = w[1], t9 = w[11], t10 = w[12], t11 = w[5], t12 = w[9], t13 = w[14], t14 = w[15], t15 = w[8];
+    w[0] = t0; w[1] = t1; w[2] = t2; w[3] = t3; w[4] = t4; w[5] = t5; w[6] = t6; w[7] = t7;
+    w[8] = t8; w[9] = t9; w[10] = t10; w[11] = t11; w[12] = t12; w[13] = t13; w[14] = t14; w[15] = t15;
   }
   if (out12) {
     out12[8] = s8 ^ cv[0];
