@@ -374,3 +374,185 @@ def mlpcs_open(kzg: KZG, poly, eval_point, tr: Transcript):
         poly_opening=kzg.open(poly, r), poly_opening_inv=kzg.open(poly, r_inv),
         s_opening=kzg.open(s, r), s_opening_inv=kzg.open(s, r_inv),
     )
+
+
+# ---------------------------------------------------------------- logup multiset / permutation check, HyperPlonk driver
+def multiset_prove(store_tables, num_vars, h_left, h_right, tr: Transcript, kzg: KZG, multiplicities=None):
+    """hyperplonk/src/piops/multiset_check.rs:28-182.  `store_tables` (list of int tables) is extended in place like the
+    reference's `&mut store`.  Returns (proof dict, evaluation point)."""
+    n = 1 << num_vars
+    gamma = tr.draw_field_element()  # :40
+    rows = lambda i: [t[i] for t in store_tables]  # noqa: E731
+    left = [fr_inv(gamma + expr_eval_point(h_left, rows(i))) for i in range(n)]  # :43-53
+    right = [fr_inv(gamma + expr_eval_point(h_right, rows(i))) for i in range(n)]  # :55-65
+    if multiplicities is not None:  # :67-95
+        right = [r * expr_eval_point(multiplicities, rows(i)) % FR for i, r in enumerate(right)]
+    c_left, c_right = kzg.commit(left), kzg.commit(right)  # :98-99
+    tr.append_g1(c_left)
+    tr.append_g1(c_right)
+    lam = tr.draw_field_element()  # :104-105
+    alpha = tr.draw_field_element()
+    dl, dr = len(store_tables), len(store_tables) + 1  # :108-109
+    store_tables.append(left)
+    store_tables.append(right)
+    m = multiplicities if multiplicities is not None else e_const(1)
+    zc = e_add(e_sub(e_mul(e_in(dl), e_add(e_const(gamma), h_left)), e_const(1)),
+               e_mul(e_const(lam), e_sub(e_mul(e_in(dr), e_add(e_const(gamma), h_right)), m)))  # :132-141
+    z = [tr.draw_field_element() for _ in range(num_vars)]  # :144-146
+    eq = len(store_tables)
+    store_tables.append(fast_eq_eval_hypercube(num_vars, z))  # :149-150
+    h_hat = e_mul(zc, e_in(eq))  # :152-153
+    h_hat = e_mul(h_hat, e_const(alpha))  # :156
+    h_hat = e_add(h_hat, e_in(dl))  # :157
+    h_hat = e_add(h_hat, e_mul(e_const(FR - 1), e_in(dr)))  # :158
+    r_polys, point, _ev = sumcheck_prove(num_vars, store_tables, h_hat, 0, tr)  # :162-163
+    o_left = mlpcs_open(kzg, left, point, tr)  # :167-170
+    o_right = mlpcs_open(kzg, right, point, tr)
+    return dict(denom_left_commitment=c_left, denom_right_commitment=c_right, r_polys=r_polys,
+                opening_proof_denom_left=o_left, opening_proof_denom_right=o_right), point
+
+
+def permutation_prove(store_tables, num_vars, h_left, h_right, id_indices, permutation_indices, tr: Transcript, kzg: KZG):
+    """hyperplonk/src/piops/permutation_check.rs:13-58"""
+    assert len(id_indices) == 1 << num_vars and len(permutation_indices) == 1 << num_vars
+    id_ref, perm_ref = len(store_tables), len(store_tables) + 1
+    store_tables.append(list(id_indices))
+    store_tables.append(list(permutation_indices))
+    alpha = tr.draw_field_element()
+    hl = e_add(e_mul(h_left, e_const(alpha)), e_in(id_ref))
+    hr = e_add(e_mul(h_right, e_const(alpha)), e_in(perm_ref))
+    return multiset_prove(store_tables, num_vars, hl, hr, tr, kzg)
+
+
+class TransitionCircuit:
+    """hyperplonk/src/frontend/transition_circuit.rs:26-151 on Python ints / tuple expressions."""
+
+    def __init__(self, num_rows):
+        self.num_columns, self.num_rows = 0, num_rows
+        self.state_cells, self.recurring, self.boundary = [], [], []
+
+    def allocate_witness_cell(self):
+        self.num_columns += 1
+        return self.num_columns - 1
+
+    def allocate_state_cell(self):
+        c, n = self.allocate_witness_cell(), self.allocate_witness_cell()
+        self.state_cells.append((c, n))
+        return c, n
+
+    def num_cols(self):
+        p = 1
+        while p < self.num_columns:
+            p *= 2
+        return p
+
+    def public_values(self):
+        pub = [[0] * self.num_rows for _ in self.boundary]
+        for i, (row, _) in enumerate(self.boundary):
+            pub[i][row] = 1
+        return pub
+
+    def zero_check_expressions(self):
+        return list(self.recurring) + [e_mul(e_in(i + self.num_cols()), c) for i, (_r, c) in enumerate(self.boundary)]
+
+    def permutation(self):
+        n = self.num_rows * self.num_cols()
+        perm = list(range(n))
+        for cur, nxt in self.state_cells:
+            for row in range(self.num_rows - 1):
+                frm, to = nxt * self.num_rows + row, cur * self.num_rows + row + 1
+                perm[frm], perm[to] = to, frm
+        return [i + 1 for i in range(n)], [p + 1 for p in perm]
+
+    def check_constraints(self, witness):
+        for row in range(self.num_rows):
+            vals = [col[row] for col in witness]
+            for c in self.recurring:
+                assert expr_eval_point(c, vals) == 0, f"recurring constraint violated at row {row}"
+        for row, c in self.boundary:
+            assert expr_eval_point(c, [col[row] for col in witness]) == 0, f"boundary constraint violated at row {row}"
+        for cur, nxt in self.state_cells:
+            for row in range(self.num_rows - 1):
+                assert witness[nxt][row] == witness[cur][row + 1], "copy constraint violated"
+
+
+def hyperplonk_prove(circuits, witness_traces, kzg: KZG):
+    """hyperplonk/src/proof/proof.rs:63-301 (preprocess_trace's prover key + prove).  Returns a dict with the
+    commitments, per-trace proofs and the final transcript state."""
+    tr = Transcript(b"hyperplonk_proof")  # :245
+    comms, fulls = [], []
+    for c, witness in zip(circuits, witness_traces):  # :250-284
+        assert len(witness) == c.num_cols()
+        c.check_constraints(witness)
+        full = [v for col in witness for v in col]
+        com = kzg.commit(full)
+        tr.append_g1(com)
+        comms.append(com)
+        fulls.append(full)
+    proofs = []
+    for c, witness, full in zip(circuits, witness_traces, fulls):  # prove_trace :145-237
+        log2_rows, log2_cols = c.num_rows.bit_length() - 1, c.num_cols().bit_length() - 1
+        tables = [list(col) for col in witness] + c.public_values()
+        alpha = tr.draw_field_element()
+        zc_expr = e_const(0)
+        for i, e in enumerate(c.zero_check_expressions()):
+            zc_expr = e_add(zc_expr, e_mul(e_const(pow(alpha, i, FR)), e))
+        zc_polys, zc_point, zc_eval, zc_z = zerocheck_prove(log2_rows, tables, zc_expr, tr)
+        ids, perm = c.permutation()
+        store2 = [list(full)]
+        perm_proof, perm_point = permutation_prove(store2, log2_rows + log2_cols, e_in(0), e_in(0), ids, perm, tr, kzg)
+        openings_zc = []
+        for col in range(c.num_cols()):
+            point = list(zc_point) + [(col >> i) & 1 for i in range(log2_cols)]
+            openings_zc.append(mlpcs_open(kzg, full, point, tr))
+        openings_pub = [mlpcs_open(kzg, p, zc_point, tr) for p in c.public_values()]
+        o_id = mlpcs_open(kzg, ids, perm_point, tr)
+        o_perm = mlpcs_open(kzg, perm, perm_point, tr)
+        o_trace = mlpcs_open(kzg, full, perm_point, tr)
+        proofs.append(dict(zc_polys=zc_polys, zc_point=zc_point, zc_eval=zc_eval, permutation=perm_proof,
+                           perm_point=perm_point, openings_zero_check=openings_zc, openings_public=openings_pub,
+                           opening_id=o_id, opening_permutation=o_perm, opening_permutation_trace=o_trace))
+    return dict(witness_commitment=comms, trace_proofs=proofs, state_end=tr.state.hex())
+
+
+def fibonacci_circuit_and_trace(num_rows=8):
+    """hyperplonk/tests/test_basic_proof.rs:17-52"""
+    c = TransitionCircuit(num_rows)
+    s1, s2 = c.allocate_state_cell(), c.allocate_state_cell()
+    c.boundary.append((0, e_in(s1[0])))
+    c.boundary.append((0, e_sub(e_in(s2[0]), e_const(1))))
+    c.recurring.append(e_sub(e_in(s2[1]), e_add(e_in(s1[0]), e_in(s2[0]))))
+    c.recurring.append(e_sub(e_in(s1[1]), e_in(s2[0])))
+    w = [[0] * num_rows for _ in range(c.num_cols())]
+    for row in range(num_rows):
+        if row == 0:
+            w[s1[0]][0], w[s2[0]][0], w[s1[1]][0], w[s2[1]][0] = 0, 1, 1, 1
+        else:
+            w[s1[0]][row] = w[s1[1]][row - 1]
+            w[s2[0]][row] = w[s2[1]][row - 1]
+            w[s1[1]][row] = w[s2[0]][row]
+            w[s2[1]][row] = (w[s2[0]][row] + w[s1[0]][row]) % FR
+    return c, w
+
+
+def modified_fibonacci_circuit_and_trace(num_rows=8):
+    """hyperplonk/tests/test_basic_proof.rs:54-105: f(n) = f(n-1) + f(n-1) * f(n-2), 5 columns padded to 8"""
+    c = TransitionCircuit(num_rows)
+    s1, s2 = c.allocate_state_cell(), c.allocate_state_cell()
+    tmp = c.allocate_witness_cell()
+    c.boundary.append((0, e_sub(e_in(s1[0]), e_const(1))))
+    c.boundary.append((0, e_sub(e_in(s2[0]), e_const(1))))
+    c.recurring.append(e_sub(e_in(tmp), e_mul(e_in(s1[0]), e_in(s2[0]))))
+    c.recurring.append(e_sub(e_in(s2[1]), e_add(e_in(s1[0]), e_in(tmp))))
+    c.recurring.append(e_sub(e_in(s1[1]), e_in(s2[0])))
+    w = [[0] * num_rows for _ in range(c.num_cols())]
+    for row in range(num_rows):
+        if row == 0:
+            w[s1[0]][0], w[s2[0]][0] = 1, 1
+        else:
+            w[s1[0]][row] = w[s1[1]][row - 1]
+            w[s2[0]][row] = w[s2[1]][row - 1]
+        w[s1[1]][row] = w[s2[0]][row]
+        w[tmp][row] = w[s1[0]][row] * w[s2[0]][row] % FR
+        w[s2[1]][row] = (w[s1[0]][row] + w[tmp][row]) % FR
+    return c, w

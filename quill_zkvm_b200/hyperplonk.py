@@ -1,0 +1,287 @@
+"""Callers of the hot path: logup multiset / permutation check and the HyperPlonk prove driver,
+orchestrated on the host exactly as the reference does, with every heavy step on the device through the C ABI:
+
+  MultisetEqualityProof::prove   hyperplonk/src/piops/multiset_check.rs:28-182
+  PermutationCheckProof::prove   hyperplonk/src/piops/permutation_check.rs:13-58
+  HyperPlonk::{preprocess,prove} hyperplonk/src/proof/proof.rs:63-301
+  TransitionCircuit              hyperplonk/src/frontend/transition_circuit.rs:26-151 (builder + Circuit impl)
+
+Host glue touches only O(#constraints) scalars (powers of the batching challenge, 0/1 column bits) with Python ints;
+tables, commitments, sumchecks and openings are computed by the CUDA library.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from .api import (Context, EvaluationClaim, KZG, MLEvalProof, SumcheckProof, Transcript, VirtualPolyExpr,
+                  VirtualPolynomialStore, ZeroCheckProof, fast_eq_eval_hypercube, logup_denominators)
+
+FR = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+_R = 1 << 256
+_RINV = pow(_R, -1, FR)
+
+
+def fr_mont(v: int) -> np.ndarray:
+    """int -> 32-byte Montgomery Fr (host glue for constants)."""
+    return np.frombuffer(((v % FR) * _R % FR).to_bytes(32, "little"), dtype=np.uint8).copy()
+
+
+def fr_int(b: np.ndarray) -> int:
+    return int.from_bytes(np.ascontiguousarray(b, dtype=np.uint8).tobytes(), "little") * _RINV % FR
+
+
+def fr_table(vals) -> np.ndarray:
+    return np.stack([fr_mont(v) for v in vals]) if len(vals) else np.zeros((0, 32), dtype=np.uint8)
+
+
+def Const(v: int) -> VirtualPolyExpr:
+    return VirtualPolyExpr.Const(fr_mont(v))
+
+
+def Sub(a: VirtualPolyExpr, b: VirtualPolyExpr) -> VirtualPolyExpr:
+    """`a - b` on VirtualPolyExpr: Add(a, Mul(Const(-1), b)) (virtual_polynomial.rs:67-77)."""
+    return a + (Const(FR - 1) * b)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@dataclass
+class MultisetEqualityProof:
+    """multiset_check.rs:17-24"""
+    denom_left_commitment: np.ndarray
+    denom_right_commitment: np.ndarray
+    sumcheck_proof: SumcheckProof
+    opening_proof_denom_left: MLEvalProof
+    opening_proof_denom_right: MLEvalProof
+
+    @staticmethod
+    def prove(ctx: Context, store: VirtualPolynomialStore, h_left: int, h_right: int, transcript: Transcript, pcs: KZG,
+              multiplicities: Optional[int] = None) -> Tuple["MultisetEqualityProof", np.ndarray]:
+        """multiset_check.rs:28-182.  multiplicities=None is LookupMode::Equality, else Subset."""
+        num_vars = store.num_vars
+        gamma = transcript.draw_field_element()  # :40
+        left = logup_denominators(ctx, store, h_left, gamma)  # :43-53
+        right = logup_denominators(ctx, store, h_right, gamma, multiplicities)  # :55-95
+        c_left = pcs.commit(left)  # :98-99
+        c_right = pcs.commit(right)
+        transcript.append_g1(c_left)  # :100-101
+        transcript.append_g1(c_right)
+        lam = transcript.draw_field_element()  # :104-105
+        alpha = transcript.draw_field_element()
+        dl = store.allocate_polynomial(left)  # :108-109
+        dr = store.allocate_polynomial(right)
+        m = store.virtual_polys[multiplicities] if multiplicities is not None else Const(1)  # :128-131
+        g = VirtualPolyExpr.Const(gamma)
+        # :132-141   dl * (gamma + h_left) - 1 + lambda * (dr * (gamma + h_right) - m)
+        zc = Sub(VirtualPolyExpr.Input(dl) * (g + store.virtual_polys[h_left]), Const(1)) + (
+            VirtualPolyExpr.Const(lam) * Sub(VirtualPolyExpr.Input(dr) * (g + store.virtual_polys[h_right]), m))
+        z = np.stack([transcript.draw_field_element() for _ in range(num_vars)]) if num_vars else np.zeros((0, 32), np.uint8)  # :144-146
+        eq = store.allocate_polynomial(fast_eq_eval_hypercube(ctx, num_vars, z))  # :149-150
+        h_hat = store.new_virtual_from_expr(zc)  # :152-153
+        store.mul_in_place(h_hat, eq)
+        store.mul_const_in_place(h_hat, alpha)  # :156-158
+        store.add_in_place(h_hat, dl)
+        store.sub_in_place(h_hat, dr, fr_mont(FR - 1))
+        sc, claim = SumcheckProof.prove(ctx, num_vars, store, h_hat, fr_mont(0), transcript)  # :162-163
+        point = claim.point
+        o_left = pcs.open_multilinear(left, point, transcript)  # :167-170
+        o_right = pcs.open_multilinear(right, point, transcript)
+        return MultisetEqualityProof(c_left, c_right, sc, o_left, o_right), point
+
+
+@dataclass
+class PermutationCheckProof:
+    """permutation_check.rs:8-10"""
+    multiset_equality_proof: MultisetEqualityProof
+
+    @staticmethod
+    def prove(ctx: Context, store: VirtualPolynomialStore, h_left: int, h_right: int, id_indices: np.ndarray,
+              permutation_indices: np.ndarray, transcript: Transcript, pcs: KZG):
+        """permutation_check.rs:13-58"""
+        assert id_indices.shape[0] == 1 << store.num_vars and permutation_indices.shape[0] == 1 << store.num_vars
+        id_ref = store.allocate_polynomial(id_indices)  # :27-28
+        perm_ref = store.allocate_polynomial(permutation_indices)
+        alpha = transcript.draw_field_element()  # :30
+        hl = store.new_virtual_from_virtual(h_left)  # :33-35  id + alpha * h_left
+        store.mul_const_in_place(hl, alpha)
+        store.add_in_place(hl, id_ref)
+        hr = store.new_virtual_from_virtual(h_right)  # :38-40
+        store.mul_const_in_place(hr, alpha)
+        store.add_in_place(hr, perm_ref)
+        proof, point = MultisetEqualityProof.prove(ctx, store, hl, hr, transcript, pcs)  # :42-50
+        return PermutationCheckProof(proof), point
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class TransitionCircuit:
+    """frontend/transition_circuit.rs:26-151: state cells copied row i -> i+1, recurring and boundary constraints."""
+
+    def __init__(self, num_rows: int):
+        self.num_columns = 0
+        self.num_rows_ = num_rows
+        self.state_cells: List[Tuple[int, int]] = []
+        self.recurring_constraints: List[VirtualPolyExpr] = []
+        self.boundary_constraints: List[Tuple[int, VirtualPolyExpr]] = []
+
+    def allocate_witness_cell(self) -> int:
+        self.num_columns += 1
+        return self.num_columns - 1
+
+    def allocate_state_cell(self) -> Tuple[int, int]:
+        cur, nxt = self.allocate_witness_cell(), self.allocate_witness_cell()
+        self.state_cells.append((cur, nxt))
+        return cur, nxt
+
+    def enforce_constraint(self, e: VirtualPolyExpr):
+        self.recurring_constraints.append(e)
+
+    def enforce_boundary_constraint(self, row: int, e: VirtualPolyExpr):
+        self.boundary_constraints.append((row, e))
+
+    # Circuit trait (proof/circuit.rs:21-74)
+    def num_rows(self) -> int:
+        return self.num_rows_
+
+    def num_cols(self) -> int:
+        return 1 << max(self.num_columns - 1, 0).bit_length() if self.num_columns > 1 else 1  # next_power_of_two
+
+    def num_public_columns(self) -> int:
+        return len(self.boundary_constraints)
+
+    def public_values(self) -> List[List[int]]:  # :96-102
+        pub = [[0] * self.num_rows_ for _ in self.boundary_constraints]
+        for i, (row, _) in enumerate(self.boundary_constraints):
+            pub[i][row] = 1
+        return pub
+
+    def zero_check_expressions(self) -> List[VirtualPolyExpr]:  # :104-122
+        out = list(self.recurring_constraints)
+        for i, (_row, c) in enumerate(self.boundary_constraints):
+            out.append(VirtualPolyExpr.Input(i + self.num_cols()) * c)
+        return out
+
+    def permutation(self) -> Tuple[List[int], List[int]]:  # :124-151
+        n = self.num_rows_ * self.num_cols()
+        assert n & (n - 1) == 0
+        perm = list(range(n))
+        for cur, nxt in self.state_cells:
+            for row in range(self.num_rows_ - 1):
+                frm, to = nxt * self.num_rows_ + row, cur * self.num_rows_ + row + 1
+                perm[frm], perm[to] = to, frm
+        return [i + 1 for i in range(n)], [p + 1 for p in perm]  # +1: no zero values
+
+
+@dataclass
+class TraceProof:
+    """proof/proof.rs:17-25"""
+    zero_check_proof: ZeroCheckProof
+    permutation_check_proof: PermutationCheckProof
+    openings_zero_check: List[MLEvalProof]
+    openings_public: List[MLEvalProof]
+    opening_id: MLEvalProof
+    opening_permutation: MLEvalProof
+    opening_permutation_trace: MLEvalProof
+
+
+@dataclass
+class HyperPlonkProof:
+    witness_commitment: List[np.ndarray]
+    trace_proofs: List[TraceProof]
+    transcript_state: bytes = b""  # final Fiat-Shamir state (not in the reference struct; exposed for parity checks)
+
+
+@dataclass
+class _TracePK:
+    id_poly: np.ndarray
+    permutation_poly: np.ndarray
+    public_values: List[np.ndarray]
+
+
+@dataclass
+class _TraceVK:
+    circuit: TransitionCircuit
+    public_columns_commitments: List[np.ndarray]
+    id_commitment: np.ndarray
+    permutation_commitment: np.ndarray
+
+
+class HyperPlonk:
+    """proof/proof.rs:12-15, 63-301"""
+
+    def __init__(self, ctx: Context, trace_pks, trace_vks):
+        self.ctx, self.trace_pks, self.trace_vks = ctx, trace_pks, trace_vks
+
+    @staticmethod
+    def preprocess(ctx: Context, circuits: List[TransitionCircuit], pcs: KZG) -> "HyperPlonk":
+        pks, vks = [], []
+        for c in circuits:  # preprocess_trace, :63-122
+            rows, cols = c.num_rows(), c.num_cols()
+            assert rows & (rows - 1) == 0, "Number of rows must be a power of two"
+            assert cols & (cols - 1) == 0, "Number of columns must be a power of two"
+            n = rows * cols
+            pub = []
+            for col in c.public_values():
+                assert len(col) == rows, "Public column length mismatch"
+                pub.append(fr_table(col + [0] * (n - rows)))  # padded to the full trace size (:77-86)
+            pub_comms = [pcs.commit(p) for p in pub]
+            ids, perm = c.permutation()
+            assert len(ids) == n and len(perm) == n
+            id_t, perm_t = fr_table(ids), fr_table(perm)
+            vks.append(_TraceVK(c, pub_comms, pcs.commit(id_t), pcs.commit(perm_t)))
+            pks.append(_TracePK(id_t, perm_t, pub))
+        return HyperPlonk(ctx, pks, vks)
+
+    def _prove_trace(self, pcs: KZG, witness: List[np.ndarray], full_witness: np.ndarray, transcript: Transcript,
+                     pk: _TracePK, circuit: TransitionCircuit) -> TraceProof:
+        ctx = self.ctx
+        log2_rows, log2_cols = circuit.num_rows().bit_length() - 1, circuit.num_cols().bit_length() - 1
+        store = VirtualPolynomialStore(log2_rows)  # :156-162
+        for col in witness:
+            store.allocate_polynomial(col)
+        public = [fr_table(p) for p in circuit.public_values()]
+        for p in public:
+            store.allocate_polynomial(p)
+        exprs = circuit.zero_check_expressions()  # :165-175
+        alpha = fr_int(transcript.draw_field_element())
+        zc_expr = Const(0)
+        for i, e in enumerate(exprs):
+            zc_expr = zc_expr + (Const(pow(alpha, i, FR)) * e)
+        zc_virtual = store.new_virtual_from_expr(zc_expr)
+        zero_check_proof, zc_claim = ZeroCheckProof.prove(ctx, store, zc_virtual, transcript)  # :178-180
+        store2 = VirtualPolynomialStore(log2_rows + log2_cols)  # :184-196
+        w_idx = store2.allocate_polynomial(full_witness)
+        w_virtual = store2.new_virtual_from_input(w_idx)
+        perm_proof, perm_point = PermutationCheckProof.prove(ctx, store2, w_virtual, w_virtual, pk.id_poly,
+                                                             pk.permutation_poly, transcript, pcs)
+        openings_zc = []  # :202-210: column bits appended as the HIGH variables of the column-major witness
+        for col in range(circuit.num_cols()):
+            bits = fr_table([(col >> i) & 1 for i in range(log2_cols)])
+            point = np.concatenate([zc_claim.point, bits]) if log2_cols else zc_claim.point
+            openings_zc.append(pcs.open_multilinear(full_witness, point, transcript))
+        openings_pub = [pcs.open_multilinear(public[i], zc_claim.point, transcript)  # :214-219 (un-padded columns)
+                        for i in range(circuit.num_public_columns())]
+        o_id = pcs.open_multilinear(pk.id_poly, perm_point, transcript)  # :222-226
+        o_perm = pcs.open_multilinear(pk.permutation_poly, perm_point, transcript)
+        o_trace = pcs.open_multilinear(full_witness, perm_point, transcript)
+        return TraceProof(zero_check_proof, perm_proof, openings_zc, openings_pub, o_id, o_perm, o_trace)
+
+    def prove(self, pcs: KZG, witness_traces: List[List[np.ndarray]]) -> HyperPlonkProof:
+        """proof.rs:239-301.  witness_traces[t][c] is column c of trace t as a (rows, 32) Montgomery array."""
+        ctx = self.ctx
+        transcript = Transcript(b"hyperplonk_proof", ctx)  # :245
+        comms, fulls = [], []
+        for witness, vk in zip(witness_traces, self.trace_vks):  # :250-284
+            c = vk.circuit
+            assert len(witness) == c.num_cols(), "Witness columns length mismatch"
+            for col in witness:
+                assert col.shape[0] == c.num_rows(), "Witness column row length mismatch"
+            full = np.ascontiguousarray(np.concatenate(witness))  # column-major (:270)
+            com = pcs.commit(full)
+            transcript.append_g1(com)
+            comms.append(com)
+            fulls.append(full)
+        proofs = [self._prove_trace(pcs, witness_traces[i], fulls[i], transcript, self.trace_pks[i], self.trace_vks[i].circuit)
+                  for i in range(len(witness_traces))]
+        return HyperPlonkProof(comms, proofs, transcript.state.tobytes())

@@ -93,6 +93,21 @@ out["pr"] = dict(r000=[H(c) for c in py.compute_pr([0, 0, 0])], r101=[H(c) for c
 out["s_poly"] = dict(a123_b456=[H(c) for c in py.compute_s_polynomial([1, 2, 3], [4, 5, 6])],
                      a123_b45=[H(c) for c in py.compute_s_polynomial([1, 2, 3], [4, 5])])
 
+# ---- HyperPlonk driver on the reference's integration-test circuits (hyperplonk/tests/test_basic_proof.rs:17-196) -----------------
+from oracle import fastkzg  # noqa: E402  (C++ oracle for the MSMs; same sums)
+
+fastkzg.install_fast_s_polynomial()
+c1, w1 = py.fibonacci_circuit_and_trace()
+c2, w2 = py.modified_fibonacci_circuit_and_trace()
+okzg = fastkzg.FastKZG(64, g, tau)
+hp1 = py.hyperplonk_prove([c1], [w1], okzg)
+hp2 = py.hyperplonk_prove([c1, c2], [w1, w2], okzg)
+out["hyperplonk"] = dict(
+    fibonacci=dict(state_end=hp1["state_end"], witness_commitment=py.ser_g1(hp1["witness_commitment"][0]).hex(),
+                   zc_round0=[H(c) for c in hp1["trace_proofs"][0]["zc_polys"][0]],
+                   perm_point=[H(x) for x in hp1["trace_proofs"][0]["perm_point"]]),
+    multitrace=dict(state_end=hp2["state_end"]))
+
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden.json")
 json.dump(out, open(path, "w"), indent=1)
 print("wrote", path, os.path.getsize(path), "bytes")

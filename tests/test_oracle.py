@@ -262,3 +262,33 @@ def test_mlpcs_open_evaluation_matches_mle():
     pt = [rnd.randrange(FR) for _ in range(n)]
     proof = py.mlpcs_open(kz, poly, pt, py.Transcript(b"mlpcs"))
     assert proof["evaluation"] == py.mle_evaluate(poly, pt)
+
+
+def test_hyperplonk_restatement_golden():
+    """proof.rs:63-301 via the Python restatement on the reference's Fibonacci circuits; also checks that the witness
+    really satisfies the circuit and that a broken copy constraint is caught (transition_circuit.rs:153-205)."""
+    from oracle import fastkzg
+
+    fastkzg.install_fast_s_polynomial()
+    k = G["kzg_test"]
+    gen = (hx(k["g"][0]), hx(k["g"][1]))
+    okzg = fastkzg.FastKZG(64, gen, hx(k["tau"]))
+    c1, w1 = py.fibonacci_circuit_and_trace()
+    c2, w2 = py.modified_fibonacci_circuit_and_trace()
+    assert c1.num_cols() == 4 and c2.num_cols() == 8 and len(c1.public_values()) == 2
+    ids, perm = c1.permutation()
+    assert sorted(perm) == ids == list(range(1, 33))  # a permutation of 1..32, no zeros (circuit.rs warning)
+    h1 = py.hyperplonk_prove([c1], [w1], okzg)
+    g = G["hyperplonk"]["fibonacci"]
+    assert h1["state_end"] == g["state_end"]
+    assert py.ser_g1(h1["witness_commitment"][0]).hex() == g["witness_commitment"]
+    assert h1["trace_proofs"][0]["zc_polys"][0] == [hx(c) for c in g["zc_round0"]]
+    h2 = py.hyperplonk_prove([c1, c2], [w1, w2], okzg)
+    assert h2["state_end"] == G["hyperplonk"]["multitrace"]["state_end"]
+    # every zero-check round polynomial of a satisfied circuit sums to the running claim starting from 0
+    tp = h1["trace_proofs"][0]
+    assert (py.poly_eval(tp["zc_polys"][0], 0) + py.poly_eval(tp["zc_polys"][0], 1)) % FR == 0
+    bad = [list(col) for col in w1]
+    bad[1][3] = 99
+    with pytest.raises(AssertionError):
+        c1.check_constraints(bad)
