@@ -183,6 +183,70 @@ def cpu_baseline(args):
     }
 
 
+def bench_hyperplonk(ctx, q, log_rows, g_bytes, tau_mont, timed_loop):
+    """BASELINE.json config 5 shape: two traces (Fibonacci, 4 columns; modified Fibonacci, 5 columns padded to 8) of
+    2^log_rows rows each, proved with HyperPlonk::prove (zero-check + logup permutation check + MLPCS openings)."""
+    import numpy as np
+
+    from quill_zkvm_b200 import hyperplonk as hp
+
+    rows = 1 << log_rows
+    In, C = q.VirtualPolyExpr.Input, hp.Const
+
+    def fib():
+        c = hp.TransitionCircuit(rows)
+        s1, s2 = c.allocate_state_cell(), c.allocate_state_cell()
+        c.enforce_boundary_constraint(0, In(s1[0]))
+        c.enforce_boundary_constraint(0, hp.Sub(In(s2[0]), C(1)))
+        c.enforce_constraint(hp.Sub(In(s2[1]), In(s1[0]) + In(s2[0])))
+        c.enforce_constraint(hp.Sub(In(s1[1]), In(s2[0])))
+        w = [[0] * rows for _ in range(c.num_cols())]
+        a, b = 0, 1
+        for r in range(rows):
+            w[s1[0]][r], w[s2[0]][r] = a, b
+            a, b = b, (a + b) % FR
+            w[s1[1]][r], w[s2[1]][r] = a, b
+        return c, w
+
+    def modfib():
+        c = hp.TransitionCircuit(rows)
+        s1, s2 = c.allocate_state_cell(), c.allocate_state_cell()
+        t = c.allocate_witness_cell()
+        c.enforce_boundary_constraint(0, hp.Sub(In(s1[0]), C(1)))
+        c.enforce_boundary_constraint(0, hp.Sub(In(s2[0]), C(1)))
+        c.enforce_constraint(hp.Sub(In(t), In(s1[0]) * In(s2[0])))
+        c.enforce_constraint(hp.Sub(In(s2[1]), In(s1[0]) + In(t)))
+        c.enforce_constraint(hp.Sub(In(s1[1]), In(s2[0])))
+        w = [[0] * rows for _ in range(c.num_cols())]
+        a, b = 1, 1
+        for r in range(rows):
+            w[s1[0]][r], w[s2[0]][r] = a, b
+            w[t][r] = a * b % FR
+            a, b = b, (a + a * b) % FR
+            w[s1[1]][r], w[s2[1]][r] = a, b
+        return c, w
+
+    def to_table(col):  # canonical bytes via Python, Montgomery conversion on the device
+        raw = np.frombuffer(b"".join(v.to_bytes(32, "little") for v in col), dtype=np.uint8).reshape(-1, 32)
+        return ctx.field_op(0, 4, raw)
+
+    circuits, witnesses = [], []
+    for mk in (fib, modfib):
+        c, w = mk()
+        circuits.append(c)
+        witnesses.append([to_table(col) for col in w])
+    max_degree = max(c.num_cols() * c.num_rows() for c in circuits)
+    kzg = q.KZG.trusted_setup(ctx, max_degree, g_bytes, tau_mont)
+    prover = hp.HyperPlonk.preprocess(ctx, circuits, kzg)
+    out = {}
+    ms, launches = timed_loop(lambda: out.__setitem__("p", prover.prove(kzg, witnesses)), 1, 1)
+    kzg.srs.free()
+    return {"value": ms * 1e-3, "unit": "s per proof", "rows_per_trace": rows, "traces": 2, "columns": [4, 8],
+            "gpu_launches": launches, "workload": "HyperPlonk::prove of Fibonacci + modified-Fibonacci transition circuits "
+            "(2 witness commits, 2 zero-checks, 2 logup permutation checks, 2 x (cols + public + 5) MLPCS openings)",
+            "final_transcript_state": out["p"].transcript_state.hex()}
+
+
 def run_gpu(args):
     import numpy as np
     import torch
@@ -284,6 +348,11 @@ def run_gpu(args):
                  "workload": f"MultilinearPCS::commit + ::open of a 2^{nm}-entry MLE (6 MSMs, eq table, NTT 2^{nm + 1}, 4 quotients)"}
         poly.free()
 
+    # ---- config 5: HyperPlonk prove of two transition-circuit traces (Fibonacci + modified Fibonacci), N = 1 only ----
+    hplonk = None
+    if world == 1 and args.hyperplonk_log_rows > 0:
+        hplonk = bench_hyperplonk(ctx, q, args.hyperplonk_log_rows, g_bytes, mont(TAU), timed_loop)
+
     # ---- sumcheck: three 2^log_n tables, degree-3 product ----
     nv = args.log_n
     slo, shi = parallel.table_shard_range(nv, rank, world)
@@ -362,6 +431,8 @@ def run_gpu(args):
         }
         if mlpcs:
             line["mlpcs_commit_open"] = mlpcs
+        if hplonk:
+            line["hyperplonk_prove"] = hplonk
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line))
@@ -385,6 +456,8 @@ def main():
     ap.add_argument("--ref-log-n", type=int, default=18, help="--impl reference: MSM sample size per step")
     ap.add_argument("--ref-sc-log-n", type=int, default=20, help="--impl reference: sumcheck sample size per step")
     ap.add_argument("--mlpcs-log-n", type=int, default=22, help="config 4: MLPCS commit+open size (0 = skip)")
+    ap.add_argument("--hyperplonk-log-rows", type=int, default=14,
+                    help="config 5: rows per trace of the two-trace HyperPlonk proof (0 = skip; BASELINE names 20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-precompute", action="store_true", help="MSM without the precomputed window multiples")
     ap.add_argument("--precompute-bits", type=int, default=0, help="window bits of the precomputed table (0 = auto)")

@@ -37,6 +37,17 @@ def fr_table(vals) -> np.ndarray:
     return np.stack([fr_mont(v) for v in vals]) if len(vals) else np.zeros((0, 32), dtype=np.uint8)
 
 
+def small_int_table(ctx: Context, vals) -> np.ndarray:
+    """Montgomery table of non-negative integers < 2^64 (ids, permutation indices, selector bits): canonical limbs are
+    laid out with numpy and converted on the device (element-wise to_mont), avoiding a Python big-int loop."""
+    v = np.ascontiguousarray(vals, dtype=np.uint64)
+    raw = np.zeros((v.shape[0], 4), dtype=np.uint64)
+    raw[:, 0] = v
+    if v.shape[0] == 0:
+        return np.zeros((0, 32), dtype=np.uint8)
+    return ctx.field_op(0, 4, raw.view(np.uint8).reshape(-1, 32))
+
+
 def Const(v: int) -> VirtualPolyExpr:
     return VirtualPolyExpr.Const(fr_mont(v))
 
@@ -224,11 +235,11 @@ class HyperPlonk:
             pub = []
             for col in c.public_values():
                 assert len(col) == rows, "Public column length mismatch"
-                pub.append(fr_table(col + [0] * (n - rows)))  # padded to the full trace size (:77-86)
+                pub.append(small_int_table(ctx, col + [0] * (n - rows)))  # padded to the full trace size (:77-86)
             pub_comms = [pcs.commit(p) for p in pub]
             ids, perm = c.permutation()
             assert len(ids) == n and len(perm) == n
-            id_t, perm_t = fr_table(ids), fr_table(perm)
+            id_t, perm_t = small_int_table(ctx, ids), small_int_table(ctx, perm)
             vks.append(_TraceVK(c, pub_comms, pcs.commit(id_t), pcs.commit(perm_t)))
             pks.append(_TracePK(id_t, perm_t, pub))
         return HyperPlonk(ctx, pks, vks)
@@ -240,7 +251,7 @@ class HyperPlonk:
         store = VirtualPolynomialStore(log2_rows)  # :156-162
         for col in witness:
             store.allocate_polynomial(col)
-        public = [fr_table(p) for p in circuit.public_values()]
+        public = [small_int_table(ctx, p) for p in circuit.public_values()]
         for p in public:
             store.allocate_polynomial(p)
         exprs = circuit.zero_check_expressions()  # :165-175
