@@ -236,7 +236,7 @@ def bench_hyperplonk(ctx, q, log_rows, g_bytes, tau_mont, timed_loop):
         circuits.append(c)
         witnesses.append([to_table(col) for col in w])
     max_degree = max(c.num_cols() * c.num_rows() for c in circuits)
-    kzg = q.KZG.trusted_setup(ctx, max_degree, g_bytes, tau_mont)
+    kzg = q.KZG.trusted_setup(ctx, max_degree, g_bytes, tau_mont).precompute()
     prover = hp.HyperPlonk.preprocess(ctx, circuits, kzg)
     out = {}
     ms, launches = timed_loop(lambda: out.__setitem__("p", prover.prove(kzg, witnesses)), 1, 1)

@@ -141,8 +141,13 @@ class Context:
 
 
 class DeviceBuffer:
-    def __init__(self, ctx: Context, ptr: int, nbytes: int):
-        self.ctx, self.ptr, self.nbytes = ctx, ptr, nbytes
+    def __init__(self, ctx: Context, ptr: int, nbytes: int, owner: bool = True):
+        self.ctx, self.ptr, self.nbytes, self.owner = ctx, ptr, nbytes, owner
+
+    def view(self, offset: int, nbytes: int) -> "DeviceBuffer":
+        """Non-owning window [offset, offset + nbytes) of this buffer (e.g. one column of a column-major witness)."""
+        assert 0 <= offset and offset + nbytes <= self.nbytes
+        return DeviceBuffer(self.ctx, self.ptr + offset, nbytes, owner=False)
 
     def download(self) -> np.ndarray:
         out = np.zeros(self.nbytes, dtype=np.uint8)
@@ -150,9 +155,9 @@ class DeviceBuffer:
         return out
 
     def free(self):
-        if self.ptr:
+        if self.ptr and self.owner:
             self.ctx.lib.qz_dev_free(self.ctx.h, self.ptr)
-            self.ptr = None
+        self.ptr = None
 
 
 def _table_ptr(t):
@@ -496,17 +501,21 @@ class ZeroCheckProof:
         return ZeroCheckProof(num_vars, sc, z[:num_vars].copy()), EvaluationClaim(point[:num_vars].copy(), ev)
 
 
-def fast_eq_eval_hypercube(ctx: Context, n: int, point: np.ndarray) -> np.ndarray:
-    """hyperplonk/src/utils/eq_eval.rs:6-31 -> (2^n, 32)."""
+def fast_eq_eval_hypercube(ctx: Context, n: int, point: np.ndarray, device: bool = False):
+    """hyperplonk/src/utils/eq_eval.rs:6-31 -> (2^n, 32) host array, or a DeviceBuffer when device=True."""
     point = _u8(point, (-1, 32))
     assert point.shape[0] == n
+    if device:
+        buf = ctx.alloc(32 << n)
+        ctx.check(ctx.lib.qz_eq_table(ctx.h, n, _ptr(point) if n else None, buf.ptr, 1))
+        return buf
     out = np.zeros((1 << n, 32), dtype=np.uint8)
     ctx.check(ctx.lib.qz_eq_table(ctx.h, n, _ptr(point) if n else None, _ptr(out), 0))
     return out
 
 
 def logup_denominators(ctx: Context, store: VirtualPolynomialStore, h: int, gamma: np.ndarray,
-                       multiplicities: Optional[int] = None) -> np.ndarray:
+                       multiplicities: Optional[int] = None, device: bool = False):
     """hyperplonk/src/piops/multiset_check.rs:43-95: out[i] = m(row_i) / (gamma + h(row_i)); raises like the reference's
     `.inverse().unwrap()` when a denominator is zero."""
     nh, ch = store.virtual_polys[h].flatten()
@@ -518,11 +527,11 @@ def logup_denominators(ctx: Context, store: VirtualPolynomialStore, h: int, gamm
         nm[nm[:, 0] == 1, 1] += ch.shape[0]  # Const indices of m follow h's in the shared consts array
         consts = np.concatenate([ch, cm]) if cm.shape[0] else ch
     tabs, k, on_dev = store._tables()
-    out = np.zeros((1 << store.num_vars, 32), dtype=np.uint8)
+    out = ctx.alloc(32 << store.num_vars) if device else np.zeros((1 << store.num_vars, 32), dtype=np.uint8)
     rc = ctx.lib.qz_logup_denominators(ctx.h, store.num_vars, k, tabs, on_dev, _ptr(nh), nh.shape[0],
                                        _ptr(np.ascontiguousarray(nm)) if nm.shape[0] else None, nm.shape[0],
                                        _ptr(np.ascontiguousarray(consts)) if consts.shape[0] else None, consts.shape[0],
-                                       _ptr(_u8(gamma, (32,))), _ptr(out), 0)
+                                       _ptr(_u8(gamma, (32,))), out.ptr if device else _ptr(out), int(device))
     if rc == _lib.QZ_ERR_INVALID_ARG and b"zero" in ctx.lib.qz_last_error(ctx.h):
         raise ZeroDivisionError("called `Option::unwrap()` on a `None` value (inverse of zero)")
     ctx.check(rc)

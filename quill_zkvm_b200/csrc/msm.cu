@@ -7,14 +7,14 @@
 //   1. msm_digits        scalar: Montgomery -> canonical -> signed c-bit digits; one (key, value) per (window, scalar)
 //                        key = window << c | |digit|, value = point index | sign << 31
 //   2. radix sort        (key, value) pairs by key (cub::DeviceRadixSort) -> every bucket's points are contiguous
-//   3. msm_bounds        first / last position of every key in the sorted list
-//   4. msm_accumulate    the hot kernel: the sorted list is cut into fixed chunks of ACC_CHUNK entries, one thread per
+//   3. msm_accumulate    the hot kernel: the sorted list is cut into fixed chunks of ACC_CHUNK entries, one thread per
 //                        chunk, XYZZ += affine (8M + 2S) per entry with the next base prefetched; load is balanced
 //                        whatever the scalar distribution.  A chunk's first / last runs may be partial buckets and go
-//                        to per-chunk slots, interior runs are complete buckets and are written in place.
-//   5. msm_bucket_finish per bucket: add the partial runs of the chunks it spans
-//   6. msm_bucket_reduce per window: sum_b b * B_b by segmented running sums + a tree reduction
-//   7. msm_combine       Horner over windows (c doublings each) + one inversion to affine
+//                        to a list of partial runs, interior runs are complete buckets and are written in place.
+//   4. msm_partials_reduce  the list of partial runs is reduced by the same chunked rule, level by level, until it
+//                        fits one chunk: no thread ever walks a whole bucket, however skewed the scalars are
+//   5. msm_bucket_reduce per window: sum_b b * B_b by segmented running sums + a tree reduction
+//   6. msm_combine       Horner over windows (c doublings each) + one inversion to affine
 // Bases are normalised to affine ONCE at SRS upload; the reference re-normalises on every commit (kzg.rs:67-71).
 #include <cub/cub.cuh>
 #include <algorithm>
@@ -59,16 +59,6 @@ __global__ void __launch_bounds__(256) msm_digits(const uint4* scalars, uint32_t
   }
 }
 
-// ---- 3. bucket boundaries ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) msm_bounds(const uint32_t* keys, uint64_t m, uint32_t* first, uint32_t* last) {
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
-    const uint32_t k = keys[i];
-    if (i == 0 || keys[i - 1] != k) first[k] = (uint32_t)i;
-    if (i + 1 == m || keys[i + 1] != k) last[k] = (uint32_t)(i + 1);
-  }
-}
-
 // ---- 4. accumulate ----------------------------------------------------------------------------------------------------------
 QZ_DEV Affine load_base(const uint8_t* bases, uint32_t val) {
   Affine a = affine_load(bases + (size_t)(val & 0x7fffffffu) * 64);
@@ -80,13 +70,16 @@ QZ_DEV uint32_t bucket_slot(uint32_t key, int c) {  // dense slot of a non-zero 
   return (w << (c - 1)) + d - 1;
 }
 
+// Partial runs go to a list of (key, XYZZ) slots, two per chunk: slot 2*chunk = the run touching the chunk's start,
+// slot 2*chunk + 1 = the run touching its end (KEY_NONE = empty).  Keys of non-empty slots are non-decreasing.
 __global__ void __launch_bounds__(ACC_THREADS) msm_accumulate(const uint32_t* keys, const uint32_t* vals, uint64_t m,
                                                               const uint8_t* bases, int c, uint8_t* buckets,
-                                                              uint8_t* heads, uint8_t* tails, uint32_t* head_key,
-                                                              uint32_t* tail_key) {
+                                                              uint8_t* ppts, uint32_t* pkeys) {
   const uint64_t chunk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t begin = chunk * ACC_CHUNK;
   if (begin >= m) return;
+  uint8_t* heads = ppts;             // slot 2*chunk
+  uint8_t* tails = ppts + 128;       // slot 2*chunk + 1
   const uint64_t end = begin + ACC_CHUNK < m ? begin + ACC_CHUNK : m;
   const uint32_t dmask = (1u << c) - 1;
   Xyzz acc = xyzz_identity();
@@ -106,7 +99,7 @@ __global__ void __launch_bounds__(ACC_THREADS) msm_accumulate(const uint32_t* ke
     if (k != cur_key) {  // the run of cur_key ended inside the chunk
       if (cur_key & dmask) {
         if (first) {  // it started at the chunk border: possibly the tail end of a bucket begun in earlier chunks
-          xyzz_store(heads + chunk * 128, acc);
+          xyzz_store(heads + chunk * 256, acc);
           hk = cur_key;
         } else {  // strictly interior: a complete bucket
           xyzz_store(buckets + (size_t)bucket_slot(cur_key, c) * 128, acc);
@@ -120,44 +113,67 @@ __global__ void __launch_bounds__(ACC_THREADS) msm_accumulate(const uint32_t* ke
   }
   if (cur_key & dmask) {  // the last run touches the chunk's end and may continue in the next chunk
     if (first) {
-      xyzz_store(heads + chunk * 128, acc);
+      xyzz_store(heads + chunk * 256, acc);
       hk = cur_key;
     } else {
-      xyzz_store(tails + chunk * 128, acc);
+      xyzz_store(tails + chunk * 256, acc);
       tk = cur_key;
     }
   }
-  head_key[chunk] = hk;
-  tail_key[chunk] = tk;
+  pkeys[2 * chunk] = hk;
+  pkeys[2 * chunk + 1] = tk;
 }
 
-// ---- 5. finish buckets that span chunk borders ----------------------------------------------------------------------
-__global__ void __launch_bounds__(128) msm_bucket_finish(const uint32_t* first, const uint32_t* last, uint64_t m, int c,
-                                                         int W, const uint8_t* heads, const uint8_t* tails,
-                                                         const uint32_t* head_key, const uint32_t* tail_key,
-                                                         uint8_t* buckets) {
-  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t per_w = 1u << (c - 1);
-  if (slot >= (uint32_t)W * per_w) return;
-  const uint32_t key = ((slot >> (c - 1)) << c) | ((slot & (per_w - 1)) + 1);
-  const uint64_t s = first[key], e = last[key];
-  if (s == e) return;  // empty bucket: buckets[] was zero-filled = identity
-  const uint64_t c0 = s / ACC_CHUNK, c1 = (e - 1) / ACC_CHUNK;
-  const uint64_t c0_end = (c0 + 1) * ACC_CHUNK < m ? (c0 + 1) * ACC_CHUNK : m;
-  if (c0 == c1 && s > c0 * ACC_CHUNK && e < c0_end) return;  // interior run: written in place by msm_accumulate
-  Xyzz sum = xyzz_identity();
-  for (uint64_t ch = c0; ch <= c1; ch++) {
-    Xyzz p;
-    if (head_key[ch] == key) {
-      xyzz_load(p, heads + ch * 128);
-      sum = xyzz_add(sum, p);
+// ---- 5. merge the partial runs, level by level ---------------------------------------------------------------------
+// The partial list is cut into chunks of PART_CHUNK slots, one thread per chunk, and reduced by the same rule as the
+// points were: a run of equal keys strictly inside a chunk is a complete bucket (written in place), the runs touching
+// the chunk's ends go to the next level's list.  At the level that fits one chunk every run is complete.  The depth is
+// log_{PART_CHUNK/2}(#chunks) and every level is fully parallel, so one huge bucket (all scalars equal, selector
+// columns, small witness values) costs no more than a uniform distribution.
+constexpr int PART_CHUNK = 64;
+__global__ void __launch_bounds__(128) msm_partials_reduce(const uint32_t* pkeys_in, const uint8_t* ppts_in, uint64_t n_in,
+                                                           int c, uint8_t* buckets, uint32_t* pkeys_out, uint8_t* ppts_out,
+                                                           int last_level) {
+  const uint64_t chunk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t begin = chunk * PART_CHUNK;
+  if (begin >= n_in) return;
+  const uint64_t end = begin + PART_CHUNK < n_in ? begin + PART_CHUNK : n_in;
+  Xyzz acc = xyzz_identity();
+  uint32_t cur = KEY_NONE, hk = KEY_NONE, tk = KEY_NONE;
+  bool first = true;
+  for (uint64_t i = begin; i < end; i++) {
+    const uint32_t k = pkeys_in[i];
+    if (k == KEY_NONE) continue;
+    if (cur != KEY_NONE && k != cur) {  // the run of `cur` ended inside the chunk
+      if (first && !last_level) {
+        xyzz_store(ppts_out + chunk * 256, acc);
+        hk = cur;
+      } else {
+        xyzz_store(buckets + (size_t)bucket_slot(cur, c) * 128, acc);
+      }
+      acc = xyzz_identity();
+      first = false;
     }
-    if (tail_key[ch] == key) {
-      xyzz_load(p, tails + ch * 128);
-      sum = xyzz_add(sum, p);
+    cur = k;
+    Xyzz p;
+    xyzz_load(p, ppts_in + i * 128);
+    acc = xyzz_add(acc, p);
+  }
+  if (cur != KEY_NONE) {
+    if (last_level) {
+      xyzz_store(buckets + (size_t)bucket_slot(cur, c) * 128, acc);
+    } else if (first) {
+      xyzz_store(ppts_out + chunk * 256, acc);
+      hk = cur;
+    } else {
+      xyzz_store(ppts_out + chunk * 256 + 128, acc);
+      tk = cur;
     }
   }
-  xyzz_store(buckets + (size_t)slot * 128, sum);
+  if (!last_level) {
+    pkeys_out[2 * chunk] = hk;
+    pkeys_out[2 * chunk + 1] = tk;
+  }
 }
 
 // ---- 6. bucket reduction: window sum = sum_{b=1..2^(c-1)} b * B_b ----------------------------------------------------------
@@ -442,13 +458,16 @@ int msm_device(qz_ctx* ctx, const qz_srs* srs, const uint4* scalars_dev, size_t 
   uint32_t* vals = (uint32_t*)ctx->arena_alloc(4 * m);
   uint32_t* keys2 = (uint32_t*)ctx->arena_alloc(4 * m);
   uint32_t* vals2 = (uint32_t*)ctx->arena_alloc(4 * m);
-  uint32_t* first = (uint32_t*)ctx->arena_alloc(4 * (size_t)n_keys * 2);
   uint8_t* buckets = (uint8_t*)ctx->arena_alloc((size_t)n_slots * 128);
-  uint8_t* heads = (uint8_t*)ctx->arena_alloc(n_chunks * 128);
-  uint8_t* tails = (uint8_t*)ctx->arena_alloc(n_chunks * 128);
-  uint32_t* head_key = (uint32_t*)ctx->arena_alloc(n_chunks * 4);
-  uint32_t* tail_key = (uint32_t*)ctx->arena_alloc(n_chunks * 4);
-  const int seg = per_w >= RED_SEG ? RED_SEG : (int)per_w;
+  // partial-run lists: level 0 has two slots per accumulate chunk, level k+1 two per PART_CHUNK slots of level k
+  const uint64_t n_part0 = 2 * n_chunks, n_part1 = 2 * ((n_part0 + PART_CHUNK - 1) / PART_CHUNK);
+  uint8_t* ppts_a = (uint8_t*)ctx->arena_alloc(n_part0 * 128);
+  uint32_t* pkeys_a = (uint32_t*)ctx->arena_alloc(n_part0 * 4);
+  uint8_t* ppts_b = (uint8_t*)ctx->arena_alloc(n_part1 * 128);
+  uint32_t* pkeys_b = (uint32_t*)ctx->arena_alloc(n_part1 * 4);
+  // small problems are latency-bound: shorter running-sum segments (more threads, shorter dependent chains)
+  const int seg_want = n_slots <= (1u << 17) ? 8 : RED_SEG;
+  const int seg = per_w >= (uint32_t)seg_want ? seg_want : (int)per_w;
   const uint32_t red_threads = n_slots / seg, per_window_parts = per_w / seg;
   uint8_t* partial = (uint8_t*)ctx->arena_alloc((size_t)red_threads * 128);
   uint8_t* partial2 = (uint8_t*)ctx->arena_alloc((size_t)W * ((per_window_parts + SUM_SPAN - 1) / SUM_SPAN) * 128);
@@ -457,10 +476,10 @@ int msm_device(qz_ctx* ctx, const qz_srs* srs, const uint4* scalars_dev, size_t 
   cub::DoubleBuffer<uint32_t> dk(keys, keys2), dv(vals, vals2);
   cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, dk, dv, (int64_t)m, 0, key_bits, st);
   void* sort_tmp = ctx->arena_alloc(sort_bytes);
-  if (!keys || !vals || !keys2 || !vals2 || !first || !buckets || !heads || !tails || !head_key || !tail_key ||
-      !partial || !partial2 || !window_sums || !sort_tmp)
+  if (!keys || !vals || !keys2 || !vals2 || !buckets || !ppts_a || !pkeys_a || !ppts_b || !pkeys_b || !partial ||
+      !partial2 || !window_sums || !sort_tmp)
     return ctx->fail(QZ_ERR_ALLOC, "MSM scratch");
-  uint32_t* last = first + n_keys;
+  (void)n_keys;
 
   QZ_LAUNCH(ctx, msm_digits, (unsigned)((n + 255) / 256), 256, 0, scalars_dev, (uint32_t)n, c, Wd,
             collapsed ? (uint32_t)srs->n : 0u, keys, vals);
@@ -468,18 +487,33 @@ int msm_device(qz_ctx* ctx, const qz_srs* srs, const uint4* scalars_dev, size_t 
   ctx->launches += 2 + (key_bits + 7) / 8;  // CUB: histogram + one onesweep pass per 8 key bits (approximate)
   const uint32_t* skeys = dk.Current();
   const uint32_t* svals = dv.Current();
-  QZ_CUDA(ctx, cudaMemsetAsync(first, 0, 4 * (size_t)n_keys * 2, st));
   QZ_CUDA(ctx, cudaMemsetAsync(buckets, 0, (size_t)n_slots * 128, st));
-  {
-    unsigned grid = (unsigned)std::min<uint64_t>((m + 255) / 256, (uint64_t)ctx->sm_count * 16);
-    QZ_LAUNCH(ctx, msm_bounds, grid, 256, 0, skeys, m, first, last);
-  }
   QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k0, st));
   QZ_LAUNCH(ctx, msm_accumulate, (unsigned)((n_chunks + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, skeys, svals,
-            m, bases, c, buckets, heads, tails, head_key, tail_key);
+            m, bases, c, buckets, ppts_a, pkeys_a);
   QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k1, st));
-  QZ_LAUNCH(ctx, msm_bucket_finish, (n_slots + 127) / 128, 128, 0, first, last, m, c, W, heads, tails, head_key,
-            tail_key, buckets);
+  {  // merge partial runs level by level until one chunk holds them all
+    const uint32_t* kin = pkeys_a;
+    const uint8_t* pin = ppts_a;
+    uint32_t* kout = pkeys_b;
+    uint8_t* pout = ppts_b;
+    uint64_t n_in = n_part0;
+    while (true) {
+      const uint64_t chunks = (n_in + PART_CHUNK - 1) / PART_CHUNK;
+      const int last_level = chunks == 1;
+      QZ_LAUNCH(ctx, msm_partials_reduce, (unsigned)((chunks + 127) / 128), 128, 0, kin, pin, n_in, c, buckets, kout, pout,
+                last_level);
+      if (last_level) break;
+      n_in = 2 * chunks;
+      // ping-pong: the output of this level (<= n_part1 slots) becomes the input; the other buffer is large enough
+      const uint32_t* tk = kin;
+      const uint8_t* tp = pin;
+      kin = kout;
+      pin = pout;
+      kout = const_cast<uint32_t*>(tk);
+      pout = const_cast<uint8_t*>(tp);
+    }
+  }
   QZ_LAUNCH(ctx, msm_bucket_reduce, (red_threads + 127) / 128, 128, 0, buckets, c, W, seg, partial);
   {  // per window: per_window_parts partial sums -> 1
     const uint8_t* in = partial;

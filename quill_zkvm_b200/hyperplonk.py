@@ -16,12 +16,17 @@ from typing import List, Optional, Tuple
 
 import numpy as np
 
-from .api import (Context, EvaluationClaim, KZG, MLEvalProof, SumcheckProof, Transcript, VirtualPolyExpr,
+from .api import (Context, DeviceBuffer, EvaluationClaim, KZG, MLEvalProof, SumcheckProof, Transcript, VirtualPolyExpr,
                   VirtualPolynomialStore, ZeroCheckProof, fast_eq_eval_hypercube, logup_denominators)
 
 FR = 21888242871839275222246405745257275088548364400416034343698204186575808495617
 _R = 1 << 256
 _RINV = pow(_R, -1, FR)
+
+
+def _host_ptr(a: np.ndarray):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a.ctypes.data
 
 
 def fr_mont(v: int) -> np.ndarray:
@@ -72,9 +77,10 @@ class MultisetEqualityProof:
               multiplicities: Optional[int] = None) -> Tuple["MultisetEqualityProof", np.ndarray]:
         """multiset_check.rs:28-182.  multiplicities=None is LookupMode::Equality, else Subset."""
         num_vars = store.num_vars
+        on_dev = bool(store.polynomials) and isinstance(store.polynomials[0], DeviceBuffer)  # keep new tables where the store lives
         gamma = transcript.draw_field_element()  # :40
-        left = logup_denominators(ctx, store, h_left, gamma)  # :43-53
-        right = logup_denominators(ctx, store, h_right, gamma, multiplicities)  # :55-95
+        left = logup_denominators(ctx, store, h_left, gamma, device=on_dev)  # :43-53
+        right = logup_denominators(ctx, store, h_right, gamma, multiplicities, device=on_dev)  # :55-95
         c_left = pcs.commit(left)  # :98-99
         c_right = pcs.commit(right)
         transcript.append_g1(c_left)  # :100-101
@@ -89,7 +95,8 @@ class MultisetEqualityProof:
         zc = Sub(VirtualPolyExpr.Input(dl) * (g + store.virtual_polys[h_left]), Const(1)) + (
             VirtualPolyExpr.Const(lam) * Sub(VirtualPolyExpr.Input(dr) * (g + store.virtual_polys[h_right]), m))
         z = np.stack([transcript.draw_field_element() for _ in range(num_vars)]) if num_vars else np.zeros((0, 32), np.uint8)  # :144-146
-        eq = store.allocate_polynomial(fast_eq_eval_hypercube(ctx, num_vars, z))  # :149-150
+        eq_tab = fast_eq_eval_hypercube(ctx, num_vars, z, device=on_dev)
+        eq = store.allocate_polynomial(eq_tab)  # :149-150
         h_hat = store.new_virtual_from_expr(zc)  # :152-153
         store.mul_in_place(h_hat, eq)
         store.mul_const_in_place(h_hat, alpha)  # :156-158
@@ -99,6 +106,9 @@ class MultisetEqualityProof:
         point = claim.point
         o_left = pcs.open_multilinear(left, point, transcript)  # :167-170
         o_right = pcs.open_multilinear(right, point, transcript)
+        if on_dev:
+            for b in (left, right, eq_tab):
+                b.free()
         return MultisetEqualityProof(c_left, c_right, sc, o_left, o_right), point
 
 
@@ -111,7 +121,7 @@ class PermutationCheckProof:
     def prove(ctx: Context, store: VirtualPolynomialStore, h_left: int, h_right: int, id_indices: np.ndarray,
               permutation_indices: np.ndarray, transcript: Transcript, pcs: KZG):
         """permutation_check.rs:13-58"""
-        assert id_indices.shape[0] == 1 << store.num_vars and permutation_indices.shape[0] == 1 << store.num_vars
+        assert id_indices.nbytes == 32 << store.num_vars and permutation_indices.nbytes == 32 << store.num_vars
         id_ref = store.allocate_polynomial(id_indices)  # :27-28
         perm_ref = store.allocate_polynomial(permutation_indices)
         alpha = transcript.draw_field_element()  # :30
@@ -205,8 +215,8 @@ class HyperPlonkProof:
 
 @dataclass
 class _TracePK:
-    id_poly: np.ndarray
-    permutation_poly: np.ndarray
+    id_poly: DeviceBuffer
+    permutation_poly: DeviceBuffer
     public_values: List[np.ndarray]
 
 
@@ -239,19 +249,22 @@ class HyperPlonk:
             pub_comms = [pcs.commit(p) for p in pub]
             ids, perm = c.permutation()
             assert len(ids) == n and len(perm) == n
-            id_t, perm_t = small_int_table(ctx, ids), small_int_table(ctx, perm)
+            id_t, perm_t = ctx.upload(small_int_table(ctx, ids)), ctx.upload(small_int_table(ctx, perm))  # resident for prove()
             vks.append(_TraceVK(c, pub_comms, pcs.commit(id_t), pcs.commit(perm_t)))
             pks.append(_TracePK(id_t, perm_t, pub))
         return HyperPlonk(ctx, pks, vks)
 
-    def _prove_trace(self, pcs: KZG, witness: List[np.ndarray], full_witness: np.ndarray, transcript: Transcript,
-                     pk: _TracePK, circuit: TransitionCircuit) -> TraceProof:
+    def _prove_trace(self, pcs: KZG, full_witness: DeviceBuffer, transcript: Transcript, pk: _TracePK,
+                     circuit: TransitionCircuit) -> TraceProof:
+        """prove_trace (:145-237).  The trace stays in HBM: `full_witness` is the column-major witness on the device and
+        every column handed to the zero-check is a window of it."""
         ctx = self.ctx
         log2_rows, log2_cols = circuit.num_rows().bit_length() - 1, circuit.num_cols().bit_length() - 1
+        col_bytes = 32 * circuit.num_rows()
         store = VirtualPolynomialStore(log2_rows)  # :156-162
-        for col in witness:
-            store.allocate_polynomial(col)
-        public = [small_int_table(ctx, p) for p in circuit.public_values()]
+        for col in range(circuit.num_cols()):
+            store.allocate_polynomial(full_witness.view(col * col_bytes, col_bytes))
+        public = [ctx.upload(small_int_table(ctx, p)) for p in circuit.public_values()]
         for p in public:
             store.allocate_polynomial(p)
         exprs = circuit.zero_check_expressions()  # :165-175
@@ -269,13 +282,15 @@ class HyperPlonk:
         openings_zc = []  # :202-210: column bits appended as the HIGH variables of the column-major witness
         for col in range(circuit.num_cols()):
             bits = fr_table([(col >> i) & 1 for i in range(log2_cols)])
-            point = np.concatenate([zc_claim.point, bits]) if log2_cols else zc_claim.point
+            point = np.concatenate([zc_claim.point, bits.reshape(-1, 32)]) if log2_cols else zc_claim.point
             openings_zc.append(pcs.open_multilinear(full_witness, point, transcript))
         openings_pub = [pcs.open_multilinear(public[i], zc_claim.point, transcript)  # :214-219 (un-padded columns)
                         for i in range(circuit.num_public_columns())]
         o_id = pcs.open_multilinear(pk.id_poly, perm_point, transcript)  # :222-226
         o_perm = pcs.open_multilinear(pk.permutation_poly, perm_point, transcript)
         o_trace = pcs.open_multilinear(full_witness, perm_point, transcript)
+        for p in public:
+            p.free()
         return TraceProof(zero_check_proof, perm_proof, openings_zc, openings_pub, o_id, o_perm, o_trace)
 
     def prove(self, pcs: KZG, witness_traces: List[List[np.ndarray]]) -> HyperPlonkProof:
@@ -288,11 +303,15 @@ class HyperPlonk:
             assert len(witness) == c.num_cols(), "Witness columns length mismatch"
             for col in witness:
                 assert col.shape[0] == c.num_rows(), "Witness column row length mismatch"
-            full = np.ascontiguousarray(np.concatenate(witness))  # column-major (:270)
+            full = ctx.alloc(32 * c.num_cols() * c.num_rows())  # column-major (:270), uploaded once and kept resident
+            for j, col in enumerate(witness):
+                ctx.check(ctx.lib.qz_dev_upload(ctx.h, full.ptr + j * 32 * c.num_rows(), _host_ptr(col), 32 * c.num_rows()))
             com = pcs.commit(full)
             transcript.append_g1(com)
             comms.append(com)
             fulls.append(full)
-        proofs = [self._prove_trace(pcs, witness_traces[i], fulls[i], transcript, self.trace_pks[i], self.trace_vks[i].circuit)
+        proofs = [self._prove_trace(pcs, fulls[i], transcript, self.trace_pks[i], self.trace_vks[i].circuit)
                   for i in range(len(witness_traces))]
+        for f in fulls:
+            f.free()
         return HyperPlonkProof(comms, proofs, transcript.state.tobytes())
