@@ -29,8 +29,11 @@ FR = 218882428718392752222464057452572750885483644004160343436982041865758084956
 TAU = 0x1234567890ABCDEF1234567890ABCDEF
 MSM_LIMB_PRODUCTS_PER_POINT = 20480  # 16 windows x (8M + 2S) x 128 32x32->64 products per Montgomery mult
 SC_BYTES_PER_ELEM = 128              # 4 * 32 B per input table element over the whole proof
-MSM_TRAFFIC_BYTES = None             # dram bytes of msm_accumulate from the last ncu --set full capture (profiles/), if any
-SC_TRAFFIC_BYTES = None
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the last ncu --set full captures (profiles/r01_ncu_*.txt,
+# 2^24, one GPU): msm_accumulate 27.96 + 1.11 GB (algorithmic 14.5 GB: a 64-byte gather fetches a 128-byte line);
+# sumcheck streaming rounds: round 0 = 1.614 GB, round 1 = 2.392 GB, later rounds halve -> 6.40 GB (algorithmic 6.44 GB)
+MSM_TRAFFIC_BYTES = 29.07e9
+SC_TRAFFIC_BYTES = 6.40e9
 
 
 def peaks():
@@ -414,7 +417,8 @@ def run_gpu(args):
                 "executed": {"window_bits": msm_c, "mixed_adds_per_point": msm_digits, "shared_bucket_set": bool(msm_shared),
                              "limb_macs_per_point": msm_digits * 1280,
                              "frac_of_peak": msm_adds * 1280 / (acc_avg * 1e-3) / imad_peak},
-                "kernel_ms": acc_avg, "kernel_share_of_step": acc_avg / msm_ms, "traffic": MSM_TRAFFIC_BYTES,
+                "kernel_ms": acc_avg, "kernel_share_of_step": acc_avg / msm_ms,
+                "traffic": MSM_TRAFFIC_BYTES if (world == 1 and args.log_n == 24 and not args.no_precompute) else None,
                 "peak_source": "qz_bench_imad (IMAD.WIDE.U32 carry chains) measured in this run"},
             "sumcheck": {
                 "value": sc_v, "unit": "field-elems/s", "ms_per_step": sc_ms, "gpu_launches": sc_launches // args.steps,
@@ -423,7 +427,7 @@ def run_gpu(args):
                 "roofline": {"kernel": "sc_round_prod<3> (streaming rounds, fold fused)", "bound": "hbm",
                              "achieved": SC_BYTES_PER_ELEM * 3 * t_loc / (rounds_avg * 1e-3) / 1e9, "peak": hbm_peak,
                              "unit": "GB/s", "frac": SC_BYTES_PER_ELEM * 3 * t_loc / (rounds_avg * 1e-3) / 1e9 / hbm_peak,
-                             "kernel_ms": rounds_avg, "kernel_share_of_step": rounds_avg / sc_ms, "traffic": SC_TRAFFIC_BYTES,
+                             "kernel_ms": rounds_avg, "kernel_share_of_step": rounds_avg / sc_ms, "traffic": SC_TRAFFIC_BYTES if (world == 1 and args.log_n == 24) else None,
                              "peak_source": hbm_src},
             },
             "gpu_launches": msm_launches // args.steps,
