@@ -210,7 +210,7 @@ void qz_ctx_destroy(qz_ctx* c) {
   cudaStreamSynchronize(c->stream);
   comm_destroy(c);
   for (auto& b : c->blocks) cudaFree(b.p);
-  for (auto& kv : c->vinv) cudaFree(kv.second);
+  for (auto& kv : c->cache) cudaFree(kv.second);
   if (c->pinned) cudaFreeHost(c->pinned);
   cudaEventDestroy(c->ev_call0);
   cudaEventDestroy(c->ev_call1);

@@ -25,8 +25,8 @@ struct qz_ctx {
   };
   std::vector<Block> blocks;
 
-  // per-degree interpolation matrices (device), keyed by degree
-  std::map<int, void*> vinv;
+  // cached device constants: interpolation matrices keyed by degree (< 1000), NTT twiddle tables keyed by 1000 + log2 size
+  std::map<int, void*> cache;
 
   cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
   float last_ms[2] = {0.f, 0.f};

@@ -178,15 +178,15 @@ __global__ void mlpcs_transcript(uint8_t* state, const Fr* point, int n, const F
 // ---- host side ---------------------------------------------------------------------------------------------------------------
 static int get_twiddles(qz_ctx* ctx, int log_m, Fr** out) {
   // cached per context (same map as the interpolation matrices, keys offset by 1000) for the last size used
-  auto it = ctx->vinv.find(1000 + log_m);
-  if (it != ctx->vinv.end()) {
+  auto it = ctx->cache.find(1000 + log_m);
+  if (it != ctx->cache.end()) {
     *out = (Fr*)it->second;
     return QZ_OK;
   }
-  for (auto i = ctx->vinv.begin(); i != ctx->vinv.end();) {  // keep one table at a time (up to 2 GiB at 2^27)
+  for (auto i = ctx->cache.begin(); i != ctx->cache.end();) {  // keep one table at a time (up to 2 GiB at 2^27)
     if (i->first >= 1000) {
       cudaFree(i->second);
-      i = ctx->vinv.erase(i);
+      i = ctx->cache.erase(i);
     } else {
       ++i;
     }
@@ -196,7 +196,7 @@ static int get_twiddles(qz_ctx* ctx, int log_m, Fr** out) {
   cudaError_t e = cudaMalloc(&p, 32 * count);
   if (e != cudaSuccess) return ctx->fail(QZ_ERR_ALLOC, "twiddle table", e);
   QZ_LAUNCH(ctx, ntt_twiddles, (unsigned)((count + 32 * 128 - 1) / (32 * 128)), 128, 0, log_m, count, (Fr*)p);
-  ctx->vinv[1000 + log_m] = p;
+  ctx->cache[1000 + log_m] = p;
   *out = (Fr*)p;
   return QZ_OK;
 }

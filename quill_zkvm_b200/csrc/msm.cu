@@ -72,7 +72,7 @@ QZ_DEV uint32_t bucket_slot(uint32_t key, int c) {  // dense slot of a non-zero 
 
 // Partial runs go to a list of (key, XYZZ) slots, two per chunk: slot 2*chunk = the run touching the chunk's start,
 // slot 2*chunk + 1 = the run touching its end (KEY_NONE = empty).  Keys of non-empty slots are non-decreasing.
-__global__ void __launch_bounds__(ACC_THREADS) msm_accumulate(const uint32_t* keys, const uint32_t* vals, uint64_t m,
+__global__ void __launch_bounds__(ACC_THREADS, 4) msm_accumulate(const uint32_t* keys, const uint32_t* vals, uint64_t m,
                                                               const uint8_t* bases, int c, uint8_t* buckets,
                                                               uint8_t* ppts, uint32_t* pkeys) {
   const uint64_t chunk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

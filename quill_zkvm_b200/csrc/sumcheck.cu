@@ -456,15 +456,15 @@ int compile_expr(qz_ctx* ctx, const qz_expr_node* nodes, size_t n_nodes, size_t 
 }
 
 int get_vinv(qz_ctx* ctx, int d, Fr** out) {
-  auto it = ctx->vinv.find(d);
-  if (it != ctx->vinv.end()) {
+  auto it = ctx->cache.find(d);
+  if (it != ctx->cache.end()) {
     *out = (Fr*)it->second;
     return QZ_OK;
   }
   void* p = nullptr;
   QZ_CUDA(ctx, cudaMalloc(&p, sizeof(Fr) * (d + 1) * (d + 1)));
   QZ_LAUNCH(ctx, sc_build_vinv, 1, 64, 0, d, (Fr*)p);
-  ctx->vinv[d] = p;
+  ctx->cache[d] = p;
   *out = (Fr*)p;
   return QZ_OK;
 }
