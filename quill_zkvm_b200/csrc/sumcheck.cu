@@ -42,64 +42,68 @@ QZ_DEV void fetch_pair(const uint4* in, uint4* out, uint64_t p, bool fold, const
 }
 
 // ---- round kernel, fast path: h = g_0 * g_1 * ... * g_{K-1} --------------------------------------------------------------
+// one pair of the product fast path: h = g_0 * ... * g_{K-1}.  Tables are taken two at a time: g_a(X) g_b(X) is a
+// quadratic whose coefficients cost 3 products (lo*lo, hi*hi, df*df); its values at X = 0..K then follow by forward
+// differences (adds only).  The per-X product over the pairs (and a leftover linear factor when K is odd) costs the
+// remaining multiplications: 7 instead of 8 for K = 3, 11 instead of 15 for K = 4.
+template <int K>
+QZ_DEV void prod_pair(const ScTables& tabs, uint64_t p, bool fold, const Fr& r, Fr* acc) {
+  constexpr int NP = K / 2;
+  Fr val[NP > 0 ? NP : 1], dl[NP > 0 ? NP : 1], q22[NP > 0 ? NP : 1], lin, lin_df;
+#pragma unroll
+  for (int t = 0; t < NP; t++) {
+    Fr lo0, hi0, lo1, hi1;
+    fetch_pair(tabs.in[2 * t], tabs.out[2 * t], p, fold, r, lo0, hi0);
+    fetch_pair(tabs.in[2 * t + 1], tabs.out[2 * t + 1], p, fold, r, lo1, hi1);
+    const Fr q0 = fp_mul<FrParams>(lo0, lo1);                                                   // q(0)
+    const Fr q1v = fp_mul<FrParams>(hi0, hi1);                                                  // q(1)
+    const Fr q2 = fp_mul<FrParams>(fp_sub<FrParams>(hi0, lo0), fp_sub<FrParams>(hi1, lo1));     // X^2 coefficient
+    val[t] = q0;
+    dl[t] = fp_sub<FrParams>(q1v, q0);  // q(1) - q(0)
+    q22[t] = fp_dbl<FrParams>(q2);      // second difference
+  }
+  if (K & 1) {
+    Fr hi;
+    fetch_pair(tabs.in[K - 1], tabs.out[K - 1], p, fold, r, lin, hi);
+    lin_df = fp_sub<FrParams>(hi, lin);
+  }
+#pragma unroll
+  for (int x = 0; x <= K; x++) {
+    Fr prod;
+    if (NP > 0) {
+      prod = val[0];
+#pragma unroll
+      for (int t = 1; t < NP; t++) prod = fp_mul<FrParams>(prod, val[t]);
+      if (K & 1) prod = fp_mul<FrParams>(prod, lin);
+    } else {
+      prod = lin;
+    }
+    acc[x] = fp_add<FrParams>(acc[x], prod);
+    if (x < K) {
+#pragma unroll
+      for (int t = 0; t < NP; t++) {
+        val[t] = fp_add<FrParams>(val[t], dl[t]);   // q(x+1) = q(x) + (q(x+1) - q(x))
+        dl[t] = fp_add<FrParams>(dl[t], q22[t]);    // first difference grows by 2*q2
+      }
+      if (K & 1) lin = fp_add<FrParams>(lin, lin_df);
+    }
+  }
+}
+
+// ---- round kernel, fast path ---------------------------------------------------------------------------------------------
 template <int K>
 __global__ void __launch_bounds__(SC_THREADS, (K <= 3 ? 2 : 1)) sc_round_prod(ScTables tabs, uint64_t n_pairs, int fold,
-                                                           const ScHead* head, Fr* partials) {
-  __shared__ Fr s_warp[32];
+                                                                            const ScHead* head, Fr* partials) {
+  __shared__ Fr s_part[(SC_THREADS / 32) * (K + 1)];
   Fr acc[K + 1];
 #pragma unroll
   for (int x = 0; x <= K; x++) acc[x] = fp_zero<FrParams>();
   Fr r = fp_zero<FrParams>();
   if (fold) r = head->r;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += stride) {
-    // Tables are taken two at a time: g_a(X) g_b(X) is a quadratic whose coefficients cost 3 products (lo*lo, hi*hi,
-    // df*df); its values at X = 0..K then follow by forward differences (adds only).  The per-X product over the
-    // pairs (and a leftover linear factor when K is odd) costs the remaining multiplications: 7 instead of 8 for
-    // K = 3, 11 instead of 15 for K = 4.
-    constexpr int NP = K / 2;
-    Fr val[NP > 0 ? NP : 1], dl[NP > 0 ? NP : 1], q22[NP > 0 ? NP : 1], lin, lin_df;
-#pragma unroll
-    for (int t = 0; t < NP; t++) {
-      Fr lo0, hi0, lo1, hi1;
-      fetch_pair(tabs.in[2 * t], tabs.out[2 * t], p, fold != 0, r, lo0, hi0);
-      fetch_pair(tabs.in[2 * t + 1], tabs.out[2 * t + 1], p, fold != 0, r, lo1, hi1);
-      const Fr q0 = fp_mul<FrParams>(lo0, lo1);                                                   // q(0)
-      const Fr q1v = fp_mul<FrParams>(hi0, hi1);                                                  // q(1)
-      const Fr q2 = fp_mul<FrParams>(fp_sub<FrParams>(hi0, lo0), fp_sub<FrParams>(hi1, lo1));     // X^2 coefficient
-      val[t] = q0;
-      dl[t] = fp_sub<FrParams>(q1v, q0);  // q(1) - q(0)
-      q22[t] = fp_dbl<FrParams>(q2);      // second difference
-    }
-    if (K & 1) {
-      Fr hi;
-      fetch_pair(tabs.in[K - 1], tabs.out[K - 1], p, fold != 0, r, lin, hi);
-      lin_df = fp_sub<FrParams>(hi, lin);
-    }
-#pragma unroll
-    for (int x = 0; x <= K; x++) {
-      Fr prod;
-      if (NP > 0) {
-        prod = val[0];
-#pragma unroll
-        for (int t = 1; t < NP; t++) prod = fp_mul<FrParams>(prod, val[t]);
-        if (K & 1) prod = fp_mul<FrParams>(prod, lin);
-      } else {
-        prod = lin;
-      }
-      acc[x] = fp_add<FrParams>(acc[x], prod);
-      if (x < K) {
-#pragma unroll
-        for (int t = 0; t < NP; t++) {
-          val[t] = fp_add<FrParams>(val[t], dl[t]);   // q(x+1) = q(x) + (q(x+1) - q(x))
-          dl[t] = fp_add<FrParams>(dl[t], q22[t]);    // first difference grows by 2*q2
-        }
-        if (K & 1) lin = fp_add<FrParams>(lin, lin_df);
-      }
-    }
-  }
-#pragma unroll
-  for (int x = 0; x <= K; x++) block_sum_to(acc[x], s_warp, &partials[(size_t)blockIdx.x * (K + 1) + x]);
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += stride)
+    prod_pair<K>(tabs, p, fold != 0, r, acc);
+  block_sum_many(acc, K + 1, s_part, &partials[(size_t)blockIdx.x * (K + 1)]);
 }
 
 // ---- round kernel, generic expression tree -----------------------------------------------------------------------------------
@@ -121,7 +125,7 @@ QZ_DEV void generic_pair(const ScTables& tabs, uint64_t p, bool fold, const Fr& 
 __global__ void __launch_bounds__(SC_THREADS) sc_round_generic(ScTables tabs, uint64_t n_pairs, int fold,
                                                               const ScHead* head, const ScProgram* prog,
                                                               const Fr* consts, Fr* partials) {
-  __shared__ Fr s_warp[32];
+  __shared__ Fr s_part[(SC_THREADS / 32) * SC_MAX_COEFFS];
   __shared__ uint32_t s_ops[SC_MAX_OPS];
   const uint32_t n_ops = prog->n_ops;
   const int d = (int)prog->degree, k = (int)prog->k;
@@ -134,33 +138,34 @@ __global__ void __launch_bounds__(SC_THREADS) sc_round_generic(ScTables tabs, ui
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += stride)
     generic_pair(tabs, p, fold != 0, r, s_ops, n_ops, k, d, consts, acc);
-  for (int x = 0; x <= d; x++) block_sum_to(acc[x], s_warp, &partials[(size_t)blockIdx.x * (d + 1) + x]);
+  block_sum_many(acc, d + 1, s_part, &partials[(size_t)blockIdx.x * (d + 1)]);
 }
 
 // ---- finalize: sum `n_parts` partial vectors, close the round (transcript on the device) -----------------------------------
 __global__ void __launch_bounds__(SC_THREADS) sc_finalize(const Fr* partials, int n_parts, int d, ScHead* head,
                                                          const Fr* vinv, Fr* out_coeffs_row, uint32_t* out_len,
                                                          Fr* out_point_slot, int max_coeffs) {
-  __shared__ Fr s_warp[32];
+  __shared__ Fr s_part[(SC_THREADS / 32) * SC_MAX_COEFFS];
   __shared__ Fr s_evals[SC_MAX_COEFFS];
   __shared__ Fr s_coef[SC_MAX_COEFFS];
+  __shared__ Fr s_prod[SC_PROD_SLOTS];
   __shared__ __align__(16) uint32_t s_msg[SC_MSG_WORDS];
-  for (int x = 0; x <= d; x++) {
-    Fr v = fp_zero<FrParams>();
-    for (int b = threadIdx.x; b < n_parts; b += blockDim.x) v = fp_add<FrParams>(v, partials[(size_t)b * (d + 1) + x]);
-    block_sum_to(v, s_warp, &s_evals[x]);
-  }
-  sc_round_close(head, vinv, d, s_evals, s_coef, s_msg, out_coeffs_row, out_len, out_point_slot, max_coeffs);
+  Fr v[SC_MAX_COEFFS];
+  for (int x = 0; x <= d; x++) v[x] = fp_zero<FrParams>();
+  for (int b = threadIdx.x; b < n_parts; b += blockDim.x)
+    for (int x = 0; x <= d; x++) v[x] = fp_add<FrParams>(v[x], partials[(size_t)b * (d + 1) + x]);
+  block_sum_many(v, d + 1, s_part, s_evals);
+  sc_round_close(head, vinv, d, s_evals, s_coef, s_msg, s_prod, out_coeffs_row, out_len, out_point_slot, max_coeffs);
 }
 
 // reduce block partials to one vector per rank (sharded mode: the vectors are all-gathered, then sc_finalize)
 __global__ void __launch_bounds__(SC_THREADS) sc_reduce_partials(const Fr* partials, int n_parts, int d, Fr* out) {
-  __shared__ Fr s_warp[32];
-  for (int x = 0; x <= d; x++) {
-    Fr v = fp_zero<FrParams>();
-    for (int b = threadIdx.x; b < n_parts; b += blockDim.x) v = fp_add<FrParams>(v, partials[(size_t)b * (d + 1) + x]);
-    block_sum_to(v, s_warp, &out[x]);
-  }
+  __shared__ Fr s_part[(SC_THREADS / 32) * SC_MAX_COEFFS];
+  Fr v[SC_MAX_COEFFS];
+  for (int x = 0; x <= d; x++) v[x] = fp_zero<FrParams>();
+  for (int b = threadIdx.x; b < n_parts; b += blockDim.x)
+    for (int x = 0; x <= d; x++) v[x] = fp_add<FrParams>(v[x], partials[(size_t)b * (d + 1) + x]);
+  block_sum_many(v, d + 1, s_part, out);
 }
 
 // ---- tail: one block runs every remaining round -------------------------------------------------------------------------------
@@ -169,58 +174,62 @@ struct ScTailBufs {
   uint4* a[SC_MAX_K];
   uint4* b[SC_MAX_K];
 };
+// KP > 0: h is a product of KP distinct tables (same fast path as sc_round_prod); KP == 0: interpret the program
+template <int KP>
 __global__ void __launch_bounds__(SC_THREADS) sc_tail(ScTables tabs, ScTailBufs bufs, uint64_t size, int pending_fold,
                                                      ScHead* head, const ScProgram* prog, const Fr* consts,
                                                      const Fr* vinv, Fr* out_coeffs, uint32_t* out_lens,
                                                      Fr* out_point, int round, int max_coeffs) {
-  __shared__ Fr s_warp[32];
+  __shared__ Fr s_part[(SC_THREADS / 32) * SC_MAX_COEFFS];
   __shared__ Fr s_evals[SC_MAX_COEFFS];
   __shared__ Fr s_coef[SC_MAX_COEFFS];
+  __shared__ Fr s_prod[SC_PROD_SLOTS];
   __shared__ __align__(16) uint32_t s_msg[SC_MSG_WORDS];
   __shared__ uint32_t s_ops[SC_MAX_OPS];
   const uint32_t n_ops = prog->n_ops;
   const int d = (int)prog->degree, k = (int)prog->k;
   for (uint32_t i = threadIdx.x; i < n_ops; i += blockDim.x) s_ops[i] = prog->ops[i];
   __syncthreads();
-  const uint4* cur[SC_MAX_K];
-  for (int t = 0; t < k; t++) cur[t] = tabs.in[t];
+  ScTables view;
+  for (int t = 0; t < k; t++) view.in[t] = tabs.in[t];
   int flip = 0;
-  while (true) {
-    if (pending_fold) {  // sumcheck.rs:81-92
-      const Fr r = head->r;
-      for (int t = 0; t < k; t++) {
-        uint4* dst = flip ? bufs.b[t] : bufs.a[t];
-        for (uint64_t p = threadIdx.x; p < size / 2; p += blockDim.x) {
-          Fr lo = ld_elem(cur[t], 2 * p), hi = ld_elem(cur[t], 2 * p + 1);
-          st_elem(dst, p, fp_add<FrParams>(lo, fp_mul<FrParams>(r, fp_sub<FrParams>(hi, lo))));
-        }
-        cur[t] = dst;
-      }
-      flip ^= 1;
-      size >>= 1;
-      __syncthreads();
-    }
-    if (size == 1) break;
-    // round polynomial over size/2 pairs (sumcheck.rs:53-70)
+  // `size` elements per table with (pending_fold) the last challenge still to be folded in.  Each round is ONE pass:
+  // fold (reads 4, writes 2) fused with the evaluation of the new pairs, exactly like the streaming kernel.
+  while (!(pending_fold && size == 2) && size > 1) {
+    const uint64_t n_pairs = pending_fold ? size / 4 : size / 2;
+    for (int t = 0; t < k; t++) view.out[t] = flip ? bufs.b[t] : bufs.a[t];
+    Fr r = fp_zero<FrParams>();
+    if (pending_fold) r = head->r;
     Fr acc[SC_MAX_COEFFS];
     for (int x = 0; x <= d; x++) acc[x] = fp_zero<FrParams>();
-    ScTables view;
-    for (int t = 0; t < k; t++) {
-      view.in[t] = cur[t];
-      view.out[t] = nullptr;
+    for (uint64_t p = threadIdx.x; p < n_pairs; p += blockDim.x) {
+      if (KP > 0)
+        prod_pair<(KP > 0 ? KP : 1)>(view, p, pending_fold != 0, r, acc);
+      else
+        generic_pair(view, p, pending_fold != 0, r, s_ops, n_ops, k, d, consts, acc);
     }
-    const Fr zero = fp_zero<FrParams>();
-    for (uint64_t p = threadIdx.x; p < size / 2; p += blockDim.x)
-      generic_pair(view, p, false, zero, s_ops, n_ops, k, d, consts, acc);
-    for (int x = 0; x <= d; x++) block_sum_to(acc[x], s_warp, &s_evals[x]);
-    sc_round_close(head, vinv, d, s_evals, s_coef, s_msg, out_coeffs + (size_t)round * max_coeffs, out_lens + round,
-                   out_point + round, max_coeffs);
+    block_sum_many(acc, d + 1, s_part, s_evals);
+    sc_round_close(head, vinv, d, s_evals, s_coef, s_msg, s_prod, out_coeffs + (size_t)round * max_coeffs,
+                   out_lens + round, out_point + round, max_coeffs);
     round++;
+    if (pending_fold) {
+      for (int t = 0; t < k; t++) view.in[t] = view.out[t];
+      flip ^= 1;
+      size >>= 1;
+    }
     pending_fold = 1;
   }
-  if (threadIdx.x == 0) {  // sumcheck.rs:94-100: h(g_1(r), ..., g_k(r))
+  if (threadIdx.x == 0) {  // sumcheck.rs:81-100: last fold, then h(g_1(r), ..., g_k(r))
     Fr fin[SC_MAX_K];
-    for (int t = 0; t < k; t++) fin[t] = ld_elem(cur[t], 0);
+    const Fr r = head->r;
+    for (int t = 0; t < k; t++) {
+      Fr lo = ld_elem(view.in[t], 0);
+      if (pending_fold && size == 2) {
+        const Fr hi = ld_elem(view.in[t], 1);
+        lo = fp_add<FrParams>(lo, fp_mul<FrParams>(r, fp_sub<FrParams>(hi, lo)));
+      }
+      fin[t] = lo;
+    }
     head->evaluation = sc_eval_program(s_ops, n_ops, consts, fin);
   }
 }
@@ -757,8 +766,13 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
       tb.b[j] = (uint4*)ctx->arena_alloc(32 * (((uint64_t)1 << SC_TAIL_LOG) / 2));
       if (!tb.a[j] || !tb.b[j]) return ctx->fail(QZ_ERR_ALLOC, "tail scratch");
     }
-    QZ_LAUNCH(ctx, sc_tail, 1, SC_THREADS, 0, tabs, tb, size, pending, head, d_prog, d_consts, vinv, d_coeffs, d_lens,
-              d_point, round, mc);
+    switch (cp.product_k) {
+      case 1: QZ_LAUNCH(ctx, sc_tail<1>, 1, SC_THREADS, 0, tabs, tb, size, pending, head, d_prog, d_consts, vinv, d_coeffs, d_lens, d_point, round, mc); break;
+      case 2: QZ_LAUNCH(ctx, sc_tail<2>, 1, SC_THREADS, 0, tabs, tb, size, pending, head, d_prog, d_consts, vinv, d_coeffs, d_lens, d_point, round, mc); break;
+      case 3: QZ_LAUNCH(ctx, sc_tail<3>, 1, SC_THREADS, 0, tabs, tb, size, pending, head, d_prog, d_consts, vinv, d_coeffs, d_lens, d_point, round, mc); break;
+      case 4: QZ_LAUNCH(ctx, sc_tail<4>, 1, SC_THREADS, 0, tabs, tb, size, pending, head, d_prog, d_consts, vinv, d_coeffs, d_lens, d_point, round, mc); break;
+      default: QZ_LAUNCH(ctx, sc_tail<0>, 1, SC_THREADS, 0, tabs, tb, size, pending, head, d_prog, d_consts, vinv, d_coeffs, d_lens, d_point, round, mc);
+    }
   }
   if (zerocheck && num_vars > 0) QZ_LAUNCH(ctx, zc_finish, 1, 1, 0, head, d_z, d_point, (int)num_vars);
 

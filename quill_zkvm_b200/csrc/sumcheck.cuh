@@ -215,6 +215,24 @@ QZ_DEV void block_sum_to(Fr v, Fr* s_warp, Fr* dst) {
   __syncthreads();
 }
 
+// sum n values per thread over the block with ONE pair of barriers: warps reduce by shuffles, lane 0 parks the warp's
+// n sums in s_part[warp * n + x], then thread x adds the per-warp sums.  dst[x] written by thread x (x < n).
+// s_part: (blockDim.x / 32) * n Fr of shared memory.  Ends with a barrier.
+QZ_DEV void block_sum_many(const Fr* vals, int n, Fr* s_part, Fr* dst) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+  for (int x = 0; x < n; x++) {
+    const Fr v = warp_sum(vals[x]);
+    if (lane == 0) s_part[warp * n + x] = v;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < n) {
+    Fr v = s_part[threadIdx.x];
+    for (int w = 1; w < nwarps; w++) v = fp_add<FrParams>(v, s_part[w * n + threadIdx.x]);
+    dst[threadIdx.x] = v;
+  }
+  __syncthreads();
+}
+
 // ---- expression interpreter (virtual_polynomial.rs:22-37 evaluated on scalars) ---------------------------------------
 static __device__ __noinline__ Fr sc_eval_program(const uint32_t* ops, uint32_t n_ops, const Fr* consts, const Fr* vals) {
   Fr stack[SC_MAX_STACK];
@@ -237,13 +255,26 @@ static __device__ __noinline__ Fr sc_eval_program(const uint32_t* ops, uint32_t 
 // length, absorb `len ‖ coeffs`, squeeze the challenge.  Called by every thread of the block; blockDim.x > d.
 // s_msg: SC_MSG_WORDS words of shared memory: [0..8) state, [8..10) u64 length, then 8 words per coefficient.
 constexpr int SC_MSG_WORDS = ((10 + 8 * SC_MAX_COEFFS + 15) / 16) * 16;
-QZ_DEV void sc_round_close(ScHead* head, const Fr* vinv, int d, const Fr* s_evals, Fr* s_coef, uint32_t* s_msg,
+constexpr int SC_PROD_SLOTS = 256;
+QZ_DEV void sc_round_close(ScHead* head, const Fr* vinv, int d, const Fr* s_evals, Fr* s_coef, uint32_t* s_msg, Fr* s_prod,
                            Fr* out_coeffs_row, uint32_t* out_len, Fr* out_point_slot, int max_coeffs) {
   const int t = threadIdx.x;
+  const int n1 = d + 1;
+  // coefficient i = sum_j vinv[i][j] * e[j]: the (d+1)^2 products are independent, so when they fit the block each
+  // thread does one (s_prod: SC_PROD_SLOTS Fr of shared memory)
+  const bool wide = n1 * n1 <= (int)blockDim.x && n1 * n1 <= SC_PROD_SLOTS;
+  if (wide) {
+    if (t < n1 * n1) s_prod[t] = fp_mul<FrParams>(vinv[t], s_evals[t % n1]);
+    __syncthreads();
+  }
   if (t <= d) {
     Fr acc = fp_zero<FrParams>();
+    if (wide) {
+      for (int j = 0; j <= d; j++) acc = fp_add<FrParams>(acc, s_prod[t * n1 + j]);
+    } else {
 #pragma unroll 1
-    for (int j = 0; j <= d; j++) acc = fp_add<FrParams>(acc, fp_mul<FrParams>(vinv[t * (d + 1) + j], s_evals[j]));
+      for (int j = 0; j <= d; j++) acc = fp_add<FrParams>(acc, fp_mul<FrParams>(vinv[t * (d + 1) + j], s_evals[j]));
+    }
     s_coef[t] = acc;
     out_coeffs_row[t] = acc;
     const Fr can = fp_from_mont<FrParams>(acc);  // ark-serialize: 32 B little-endian canonical
