@@ -171,8 +171,8 @@ class TransitionCircuit:
     def num_public_columns(self) -> int:
         return len(self.boundary_constraints)
 
-    def public_values(self) -> List[List[int]]:  # :96-102
-        pub = [[0] * self.num_rows_ for _ in self.boundary_constraints]
+    def public_values(self) -> List[np.ndarray]:  # :96-102 (one 0/1 selector column per boundary constraint)
+        pub = [np.zeros(self.num_rows_, dtype=np.uint64) for _ in self.boundary_constraints]
         for i, (row, _) in enumerate(self.boundary_constraints):
             pub[i][row] = 1
         return pub
@@ -183,15 +183,16 @@ class TransitionCircuit:
             out.append(VirtualPolyExpr.Input(i + self.num_cols()) * c)
         return out
 
-    def permutation(self) -> Tuple[List[int], List[int]]:  # :124-151
-        n = self.num_rows_ * self.num_cols()
+    def permutation(self) -> Tuple[np.ndarray, np.ndarray]:  # :124-151
+        n, rows = self.num_rows_ * self.num_cols(), self.num_rows_
         assert n & (n - 1) == 0
-        perm = list(range(n))
-        for cur, nxt in self.state_cells:
-            for row in range(self.num_rows_ - 1):
-                frm, to = nxt * self.num_rows_ + row, cur * self.num_rows_ + row + 1
-                perm[frm], perm[to] = to, frm
-        return [i + 1 for i in range(n)], [p + 1 for p in perm]  # +1: no zero values
+        perm = np.arange(n, dtype=np.uint64)
+        r = np.arange(rows - 1, dtype=np.uint64)
+        for cur, nxt in self.state_cells:  # (next, row) <-> (current, row + 1), applied in order like the reference's loop
+            frm, to = nxt * rows + r, cur * rows + r + 1
+            perm[frm] = to
+            perm[to] = frm
+        return np.arange(1, n + 1, dtype=np.uint64), perm + 1  # +1: no zero values
 
 
 @dataclass
@@ -245,7 +246,7 @@ class HyperPlonk:
             pub = []
             for col in c.public_values():
                 assert len(col) == rows, "Public column length mismatch"
-                pub.append(small_int_table(ctx, col + [0] * (n - rows)))  # padded to the full trace size (:77-86)
+                pub.append(small_int_table(ctx, np.concatenate([col, np.zeros(n - rows, dtype=np.uint64)])))  # :77-86
             pub_comms = [pcs.commit(p) for p in pub]
             ids, perm = c.permutation()
             assert len(ids) == n and len(perm) == n
