@@ -4,6 +4,7 @@
 // Montgomery limbs (the in-memory layout of ark_bn254::Fr), G1 affine points are x‖y (64 B, Montgomery) with
 // (0,0) standing for the point at infinity, transcript state is the 32-byte blake3 state in/out.
 #include <chrono>
+#include "pairing.hpp"
 #include "protocol.hpp"
 
 using namespace orc;
@@ -368,6 +369,49 @@ int orc_logup_denominators(size_t num_vars, size_t k, const uint8_t* const* tabl
     st_fr(out_mont + 32 * i, v);
   }
   return 0;
+}
+
+// ---- verifier side: G2 and the pairing (pcs/src/kzg.rs:49-52, 98-108) ---------------------------------------
+// G2 affine = x.c0 ‖ x.c1 ‖ y.c0 ‖ y.c1 (128 B, Montgomery Fq), all-zero = infinity.
+static G2Affine ld_g2(const uint8_t* p) {
+  G2Affine a;
+  memcpy(a.x.c0.l, p, 32);
+  memcpy(a.x.c1.l, p + 32, 32);
+  memcpy(a.y.c0.l, p + 64, 32);
+  memcpy(a.y.c1.l, p + 96, 32);
+  a.inf = a.x.is_zero() && a.y.is_zero();
+  return a;
+}
+static void st_g2(uint8_t* p, const G2Affine& a) {
+  if (a.inf) {
+    memset(p, 0, 128);
+    return;
+  }
+  memcpy(p, a.x.c0.l, 32);
+  memcpy(p + 32, a.x.c1.l, 32);
+  memcpy(p + 64, a.y.c0.l, 32);
+  memcpy(p + 96, a.y.c1.l, 32);
+}
+void orc_g2_generator(uint8_t out[128]) { st_g2(out, g2_generator()); }
+int orc_g2_on_curve(const uint8_t* a) { return ld_g2(a).on_curve() ? 1 : 0; }
+void orc_g2_add(const uint8_t* a, const uint8_t* b, uint8_t* out) { st_g2(out, ld_g2(a).add(ld_g2(b))); }
+void orc_g2_neg(const uint8_t* a, uint8_t* out) { st_g2(out, ld_g2(a).neg()); }
+void orc_g2_mul(const uint8_t* a, const uint8_t* scalar_mont, uint8_t* out) {
+  st_g2(out, ld_g2(a).mul(ld_fr(scalar_mont)));
+}
+// out = prod_i e(P_i, Q_i) as 12 Montgomery Fq coefficients; returns 1 when the product is one
+int orc_pairing_product(const uint8_t* g1s, const uint8_t* g2s, size_t n, const uint8_t* final_exp, size_t exp_len,
+                        uint8_t* out_fq12) {
+  std::vector<G1Affine> ps(n);
+  std::vector<G2Affine> qs(n);
+  for (size_t i = 0; i < n; i++) {
+    ps[i] = ld_aff(g1s + 64 * i);
+    qs[i] = ld_g2(g2s + 128 * i);
+  }
+  Fq12 f = pairing_product(ps.data(), qs.data(), n, final_exp, exp_len);
+  if (out_fq12)
+    for (int i = 0; i < 12; i++) memcpy(out_fq12 + 32 * i, f.c[i].l, 32);
+  return f == Fq12::one() ? 1 : 0;
 }
 
 }  // extern "C"

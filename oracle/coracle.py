@@ -20,7 +20,7 @@ _LIB = None
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("capi.cpp", "field.hpp", "g1.hpp", "blake3_ref.hpp", "protocol.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("capi.cpp", "field.hpp", "g1.hpp", "pairing.hpp", "blake3_ref.hpp", "protocol.hpp")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     return so
@@ -36,6 +36,8 @@ def lib():
         _LIB.orc_kzg_commit_reference_shape.restype = C.c_int
         _LIB.orc_mlpcs_open.restype = C.c_int
         _LIB.orc_logup_denominators.restype = C.c_int
+        _LIB.orc_g2_on_curve.restype = C.c_int
+        _LIB.orc_pairing_product.restype = C.c_int
     return _LIB
 
 
@@ -293,3 +295,47 @@ def logup_denominators(num_vars, tables, nodes_h, nodes_m, consts, gamma):
     if rc:
         raise ZeroDivisionError("inverse of zero")
     return out
+
+
+# ---- verifier side: G2 and the pairing (pcs/src/kzg.rs:49-52, 98-108) ---------------------------------------------
+# G2 affine = (128,) bytes x.c0 ‖ x.c1 ‖ y.c0 ‖ y.c1 (Montgomery Fq), all-zero = infinity.
+FINAL_EXP = ((FQ ** 12 - 1) // FR).to_bytes(((FQ ** 12 - 1) // FR).bit_length() // 8 + 1, "little")
+
+
+def g2_generator() -> np.ndarray:
+    out = np.zeros(128, dtype=np.uint8)
+    lib().orc_g2_generator(_p(out))
+    return out
+
+
+def g2_on_curve(a) -> bool:
+    return bool(lib().orc_g2_on_curve(_p(np.ascontiguousarray(a))))
+
+
+def g2_add(a, b) -> np.ndarray:
+    out = np.zeros(128, dtype=np.uint8)
+    lib().orc_g2_add(_p(np.ascontiguousarray(a)), _p(np.ascontiguousarray(b)), _p(out))
+    return out
+
+
+def g2_neg(a) -> np.ndarray:
+    out = np.zeros(128, dtype=np.uint8)
+    lib().orc_g2_neg(_p(np.ascontiguousarray(a)), _p(out))
+    return out
+
+
+def g2_mul(a, scalar_mont) -> np.ndarray:
+    out = np.zeros(128, dtype=np.uint8)
+    lib().orc_g2_mul(_p(np.ascontiguousarray(a)), _p(np.ascontiguousarray(scalar_mont)), _p(out))
+    return out
+
+
+def pairing_product(g1s, g2s):
+    """prod_i e(P_i, Q_i): (is_one, the Fq12 value as 12 canonical ints)."""
+    g1s = np.ascontiguousarray(np.asarray(g1s, dtype=np.uint8).reshape(-1, 64))
+    g2s = np.ascontiguousarray(np.asarray(g2s, dtype=np.uint8).reshape(-1, 128))
+    assert g1s.shape[0] == g2s.shape[0]
+    e = np.frombuffer(FINAL_EXP, dtype=np.uint8).copy()
+    out = np.zeros((12, 32), dtype=np.uint8)
+    one = lib().orc_pairing_product(_p(g1s), _p(g2s), C.c_size_t(g1s.shape[0]), _p(e), C.c_size_t(e.shape[0]), _p(out))
+    return bool(one), from_mont(out, FQ)
