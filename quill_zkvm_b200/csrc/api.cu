@@ -60,7 +60,23 @@ __global__ void k_field_op(int op, const uint4* a, const uint4* b, uint4* out, s
     case 2: r = fp_mul<P>(x, y); break;
     case 3: r = fp_inv<P>(x); break;
     case 4: r = fp_to_mont<P>(x); break;
-    default: r = fp_from_mont<P>(x); break;
+    case 5: r = fp_from_mont<P>(x); break;
+    case 6: {  // deferred reduction: x*y + x*x + y*y from one wide accumulator
+      FpWide w;
+      wide_zero(w);
+      wide_mul_acc<P>(w, x, y);
+      wide_mul_acc<P>(w, x, x);
+      wide_mul_acc<P>(w, y, y);
+      r = wide_reduce<P>(w);
+      break;
+    }
+    default: {  // 4096 * (x*y): the accumulator's 17th word in use
+      FpWide w;
+      wide_zero(w);
+      for (int j = 0; j < 4096; j++) wide_mul_acc<P>(w, x, y);
+      r = wide_reduce<P>(w);
+      break;
+    }
   }
   fp_store<P>(out + 2 * i, r);
 }
@@ -376,7 +392,7 @@ int qz_eq_table(qz_ctx* c, size_t n, const uint8_t* point, void* out, int out_on
 
 // ---- test hooks -----------------------------------------------------------------------------------------------------------------------
 int qz_test_field_op(qz_ctx* c, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
-  if (!c || !a || !out || op < 0 || op > 5 || field < 0 || field > 1) return QZ_ERR_INVALID_ARG;
+  if (!c || !a || !out || op < 0 || op > 7 || field < 0 || field > 1) return QZ_ERR_INVALID_ARG;
   if (n == 0) return QZ_OK;
   c->arena_reset();
   uint4* da = (uint4*)c->arena_alloc(32 * n);

@@ -317,6 +317,97 @@ template <class P>
 QZ_DEV Fp<P> fp_dbl(const Fp<P>& a) {
   return fp_add<P>(a, a);
 }
+// ---- deferred reduction -------------------------------------------------------------------------------------------------
+// A sum of products  sum_i a_i * b_i  that is only ever needed mod p can skip the Montgomery reduction of every term:
+// the 512-bit products (64 IMAD.WIDE each instead of 128) are added into a 17-word accumulator and reduced once.
+// 17 words hold 2^36 products of values < p < 2^254.
+struct FpWide {
+  uint32_t w[17];
+};
+QZ_DEV void wide_zero(FpWide& acc) {
+#pragma unroll
+  for (int i = 0; i < 17; i++) acc.w[i] = 0;
+}
+// acc += a * b  (plain integer product of the two Montgomery residues)
+template <class P>
+QZ_DEV void wide_mul_acc(FpWide& acc, const Fp<P>& a, const Fp<P>& b) {
+  // E[k] holds column k in 64-bit lanes that start at even columns, O[k] column k+1 in lanes that start at odd columns;
+  // a row's carry out of its top lane lands in a word no earlier row has filled with more than a carry.
+  uint32_t E[17], O[15];
+#pragma unroll
+  for (int i = 0; i < 17; i++) E[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 15; i++) O[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    cmad4_top(&E[i], a.v[0], a.v[2], a.v[4], a.v[6], b.v[i], E[i + 8]);
+    cmad4_top(&O[i], a.v[1], a.v[3], a.v[5], a.v[7], b.v[i], O[i + 8]);
+    cmad4_top(&O[i], a.v[0], a.v[2], a.v[4], a.v[6], b.v[i + 1], O[i + 8]);
+    cmad4_top(&E[i + 2], a.v[1], a.v[3], a.v[5], a.v[7], b.v[i + 1], E[i + 10]);
+  }
+  // acc += E + (O << 32); the product is below 2^512, so E[16] is zero and O ends at column 15
+  asm volatile(
+      "add.cc.u32 %0, %0, %17;\n\t"
+      "addc.cc.u32 %1, %1, %18;\n\t"
+      "addc.cc.u32 %2, %2, %19;\n\t"
+      "addc.cc.u32 %3, %3, %20;\n\t"
+      "addc.cc.u32 %4, %4, %21;\n\t"
+      "addc.cc.u32 %5, %5, %22;\n\t"
+      "addc.cc.u32 %6, %6, %23;\n\t"
+      "addc.cc.u32 %7, %7, %24;\n\t"
+      "addc.cc.u32 %8, %8, %25;\n\t"
+      "addc.cc.u32 %9, %9, %26;\n\t"
+      "addc.cc.u32 %10, %10, %27;\n\t"
+      "addc.cc.u32 %11, %11, %28;\n\t"
+      "addc.cc.u32 %12, %12, %29;\n\t"
+      "addc.cc.u32 %13, %13, %30;\n\t"
+      "addc.cc.u32 %14, %14, %31;\n\t"
+      "addc.cc.u32 %15, %15, %32;\n\t"
+      "addc.u32 %16, %16, 0;\n\t"
+      : "+r"(acc.w[0]), "+r"(acc.w[1]), "+r"(acc.w[2]), "+r"(acc.w[3]), "+r"(acc.w[4]), "+r"(acc.w[5]), "+r"(acc.w[6]),
+        "+r"(acc.w[7]), "+r"(acc.w[8]), "+r"(acc.w[9]), "+r"(acc.w[10]), "+r"(acc.w[11]), "+r"(acc.w[12]),
+        "+r"(acc.w[13]), "+r"(acc.w[14]), "+r"(acc.w[15]), "+r"(acc.w[16])
+      : "r"(E[0]), "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(E[9]),
+        "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]));
+  asm volatile(
+      "add.cc.u32 %0, %0, %16;\n\t"
+      "addc.cc.u32 %1, %1, %17;\n\t"
+      "addc.cc.u32 %2, %2, %18;\n\t"
+      "addc.cc.u32 %3, %3, %19;\n\t"
+      "addc.cc.u32 %4, %4, %20;\n\t"
+      "addc.cc.u32 %5, %5, %21;\n\t"
+      "addc.cc.u32 %6, %6, %22;\n\t"
+      "addc.cc.u32 %7, %7, %23;\n\t"
+      "addc.cc.u32 %8, %8, %24;\n\t"
+      "addc.cc.u32 %9, %9, %25;\n\t"
+      "addc.cc.u32 %10, %10, %26;\n\t"
+      "addc.cc.u32 %11, %11, %27;\n\t"
+      "addc.cc.u32 %12, %12, %28;\n\t"
+      "addc.cc.u32 %13, %13, %29;\n\t"
+      "addc.cc.u32 %14, %14, %30;\n\t"
+      "addc.u32 %15, %15, 0;\n\t"
+      : "+r"(acc.w[1]), "+r"(acc.w[2]), "+r"(acc.w[3]), "+r"(acc.w[4]), "+r"(acc.w[5]), "+r"(acc.w[6]), "+r"(acc.w[7]),
+        "+r"(acc.w[8]), "+r"(acc.w[9]), "+r"(acc.w[10]), "+r"(acc.w[11]), "+r"(acc.w[12]), "+r"(acc.w[13]),
+        "+r"(acc.w[14]), "+r"(acc.w[15]), "+r"(acc.w[16])
+      : "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]), "r"(O[9]),
+        "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]));
+}
+// (sum of products) * R^-1 mod p, i.e. the sum of the Montgomery products:  T = lo + mid R + top R^2  ->  lo R^-1 + mid + top R
+template <class P>
+QZ_DEV Fp<P> wide_reduce(const FpWide& acc) {
+  Fp<P> lo, mid, top = fp_zero<P>(), raw_one = fp_zero<P>(), r2;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    lo.v[i] = acc.w[i];
+    mid.v[i] = acc.w[8 + i];
+    r2.v[i] = P::R2(i);
+  }
+  top.v[0] = acc.w[16];
+  raw_one.v[0] = 1;
+  // fp_mul's first operand must be < p, the second may be any 256-bit value
+  return fp_add<P>(fp_add<P>(fp_mul<P>(raw_one, lo), fp_mul<P>(fp_one<P>(), mid)), fp_mul<P>(r2, top));
+}
+
 // Montgomery -> canonical limbs (multiply by 1)
 template <class P>
 QZ_DEV Fp<P> fp_from_mont(const Fp<P>& a) {

@@ -21,6 +21,10 @@ namespace qz {
 
 constexpr int SC_TAIL_LOG = 11;
 constexpr int SC_THREADS = 256;
+constexpr int SC_WIDE_THREADS = 128;  // deferred-reduction round kernel: 168 registers, 3 blocks per SM
+#ifndef QZ_SC_WIDE_BPS
+#define QZ_SC_WIDE_BPS 3
+#endif
 
 // ---- loads ---------------------------------------------------------------------------------------------------------------
 QZ_DEV Fr ld_elem(const uint4* base, uint64_t e) { return fp_load<FrParams>(base + 2 * e); }
@@ -41,44 +45,94 @@ QZ_DEV void fetch_pair(const uint4* in, uint4* out, uint64_t p, bool fold, const
   }
 }
 
+// The same in two steps for the streaming kernels: all loads of a pair are issued before any arithmetic so that one
+// memory round trip, not one per table, is exposed per pair (FOLD is a compile-time flag there: no branch splits the
+// block the scheduler can hoist loads across).
+template <bool FOLD>
+struct RawPair {
+  Fr e[FOLD ? 4 : 2];
+};
+template <bool FOLD>
+QZ_DEV void load_raw(const uint4* in, uint64_t p, RawPair<FOLD>& raw) {
+#pragma unroll
+  for (int j = 0; j < (FOLD ? 4 : 2); j++) raw.e[j] = ld_elem(in, (FOLD ? 4 : 2) * p + j);
+}
+template <bool FOLD>
+QZ_DEV void finish_pair(const RawPair<FOLD>& raw, uint4* out, uint64_t p, const Fr& r, Fr& lo, Fr& hi) {
+  if (FOLD) {
+    lo = fp_add<FrParams>(raw.e[0], fp_mul<FrParams>(r, fp_sub<FrParams>(raw.e[1], raw.e[0])));
+    hi = fp_add<FrParams>(raw.e[FOLD ? 2 : 0], fp_mul<FrParams>(r, fp_sub<FrParams>(raw.e[FOLD ? 3 : 1], raw.e[FOLD ? 2 : 0])));
+    st_elem(out, 2 * p, lo);
+    st_elem(out, 2 * p + 1, hi);
+  } else {
+    lo = raw.e[0];
+    hi = raw.e[1];
+  }
+}
+
 // ---- round kernel, fast path: h = g_0 * g_1 * ... * g_{K-1} --------------------------------------------------------------
 // one pair of the product fast path: h = g_0 * ... * g_{K-1}.  Tables are taken two at a time: g_a(X) g_b(X) is a
 // quadratic whose coefficients cost 3 products (lo*lo, hi*hi, df*df); its values at X = 0..K then follow by forward
 // differences (adds only).  The per-X product over the pairs (and a leftover linear factor when K is odd) costs the
 // remaining multiplications: 7 instead of 8 for K = 3, 11 instead of 15 for K = 4.
-template <int K>
-QZ_DEV void prod_pair(const ScTables& tabs, uint64_t p, bool fold, const Fr& r, Fr* acc) {
+// per-thread running sums of h at X = 0..K.  WIDE (K >= 3 only): the last multiplication of every term only feeds the
+// sum, so its Montgomery reduction is deferred: the 512-bit products accumulate in 17-word sums that are reduced once
+// per thread (ff.cuh "deferred reduction") -- 64 instead of 128 multiply-adds for 4 of the 13 products of a K = 3 pair.
+// The reduction costs 3 products per sum, so passes with only a few pairs per thread use the narrow sums.
+template <int K, bool WIDE>
+struct ProdAcc {
+  static_assert(!WIDE || K >= 3, "nothing to defer below three factors");
+  FpWide wide[WIDE ? K + 1 : 1];
+  Fr narrow[WIDE ? 1 : K + 1];
+  QZ_DEV void init() {
+    if (WIDE) {
+#pragma unroll
+      for (int x = 0; x <= K; x++) wide_zero(wide[x]);
+    } else {
+#pragma unroll
+      for (int x = 0; x <= K; x++) narrow[x] = fp_zero<FrParams>();
+    }
+  }
+  QZ_DEV void add_product(int x, const Fr& a, const Fr& b) {
+    if (WIDE)
+      wide_mul_acc<FrParams>(wide[WIDE ? x : 0], a, b);
+    else
+      add_value(x, fp_mul<FrParams>(a, b));
+  }
+  QZ_DEV void add_value(int x, const Fr& v) { narrow[WIDE ? 0 : x] = fp_add<FrParams>(narrow[WIDE ? 0 : x], v); }
+  QZ_DEV Fr get(int x) const { return WIDE ? wide_reduce<FrParams>(wide[WIDE ? x : 0]) : narrow[WIDE ? 0 : x]; }
+};
+
+// core of a pair once the K (lo, hi) values are in registers
+template <int K, bool WIDE>
+QZ_DEV void prod_core(const Fr* lo, const Fr* hi, ProdAcc<K, WIDE>& acc) {
   constexpr int NP = K / 2;
   Fr val[NP > 0 ? NP : 1], dl[NP > 0 ? NP : 1], q22[NP > 0 ? NP : 1], lin, lin_df;
 #pragma unroll
   for (int t = 0; t < NP; t++) {
-    Fr lo0, hi0, lo1, hi1;
-    fetch_pair(tabs.in[2 * t], tabs.out[2 * t], p, fold, r, lo0, hi0);
-    fetch_pair(tabs.in[2 * t + 1], tabs.out[2 * t + 1], p, fold, r, lo1, hi1);
-    const Fr q0 = fp_mul<FrParams>(lo0, lo1);                                                   // q(0)
-    const Fr q1v = fp_mul<FrParams>(hi0, hi1);                                                  // q(1)
-    const Fr q2 = fp_mul<FrParams>(fp_sub<FrParams>(hi0, lo0), fp_sub<FrParams>(hi1, lo1));     // X^2 coefficient
+    const Fr q0 = fp_mul<FrParams>(lo[2 * t], lo[2 * t + 1]);                                   // q(0)
+    const Fr q1v = fp_mul<FrParams>(hi[2 * t], hi[2 * t + 1]);                                  // q(1)
+    const Fr q2 = fp_mul<FrParams>(fp_sub<FrParams>(hi[2 * t], lo[2 * t]),
+                                   fp_sub<FrParams>(hi[2 * t + 1], lo[2 * t + 1]));             // X^2 coefficient
     val[t] = q0;
     dl[t] = fp_sub<FrParams>(q1v, q0);  // q(1) - q(0)
     q22[t] = fp_dbl<FrParams>(q2);      // second difference
   }
   if (K & 1) {
-    Fr hi;
-    fetch_pair(tabs.in[K - 1], tabs.out[K - 1], p, fold, r, lin, hi);
-    lin_df = fp_sub<FrParams>(hi, lin);
+    lin = lo[K - 1];
+    lin_df = fp_sub<FrParams>(hi[K - 1], lin);
   }
 #pragma unroll
   for (int x = 0; x <= K; x++) {
-    Fr prod;
-    if (NP > 0) {
-      prod = val[0];
+    if (K >= 3) {
+      // all factors but the last are multiplied with full reductions; the last product goes to the running sum
+      Fr prod = val[0];
 #pragma unroll
-      for (int t = 1; t < NP; t++) prod = fp_mul<FrParams>(prod, val[t]);
-      if (K & 1) prod = fp_mul<FrParams>(prod, lin);
+      for (int t = 1; t < NP - ((K & 1) ? 0 : 1); t++) prod = fp_mul<FrParams>(prod, val[t]);
+      acc.add_product(x, prod, (K & 1) ? lin : val[NP - 1]);
     } else {
-      prod = lin;
+      acc.add_value(x, NP > 0 ? val[0] : lin);
     }
-    acc[x] = fp_add<FrParams>(acc[x], prod);
     if (x < K) {
 #pragma unroll
       for (int t = 0; t < NP; t++) {
@@ -90,20 +144,38 @@ QZ_DEV void prod_pair(const ScTables& tabs, uint64_t p, bool fold, const Fr& r, 
   }
 }
 
-// ---- round kernel, fast path ---------------------------------------------------------------------------------------------
-template <int K>
-__global__ void __launch_bounds__(SC_THREADS, (K <= 3 ? 2 : 1)) sc_round_prod(ScTables tabs, uint64_t n_pairs, int fold,
-                                                                            const ScHead* head, Fr* partials) {
-  __shared__ Fr s_part[(SC_THREADS / 32) * (K + 1)];
-  Fr acc[K + 1];
+// tail kernel: `fold` is a run-time flag, tables fetched one after the other
+template <int K, bool WIDE>
+QZ_DEV void prod_pair(const ScTables& tabs, uint64_t p, bool fold, const Fr& r, ProdAcc<K, WIDE>& acc) {
+  Fr lo[K], hi[K];
 #pragma unroll
-  for (int x = 0; x <= K; x++) acc[x] = fp_zero<FrParams>();
+  for (int t = 0; t < K; t++) fetch_pair(tabs.in[t], tabs.out[t], p, fold, r, lo[t], hi[t]);
+  prod_core<K, WIDE>(lo, hi, acc);
+}
+
+// ---- round kernel, fast path ---------------------------------------------------------------------------------------------
+template <int K, bool WIDE, bool FOLD>
+__global__ void __launch_bounds__(WIDE ? SC_WIDE_THREADS : SC_THREADS, (WIDE ? QZ_SC_WIDE_BPS : K <= 3 ? 2 : 1))
+    sc_round_prod(ScTables tabs, uint64_t n_pairs, const ScHead* head, Fr* partials) {
+  __shared__ Fr s_part[(SC_THREADS / 32) * (K + 1)];
+  ProdAcc<K, WIDE> acc;
+  acc.init();
   Fr r = fp_zero<FrParams>();
-  if (fold) r = head->r;
+  if (FOLD) r = head->r;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += stride)
-    prod_pair<K>(tabs, p, fold != 0, r, acc);
-  block_sum_many(acc, K + 1, s_part, &partials[(size_t)blockIdx.x * (K + 1)]);
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += stride) {
+    RawPair<FOLD> raw[K];
+#pragma unroll
+    for (int t = 0; t < K; t++) load_raw<FOLD>(tabs.in[t], p, raw[t]);
+    Fr lo[K], hi[K];
+#pragma unroll
+    for (int t = 0; t < K; t++) finish_pair<FOLD>(raw[t], tabs.out[t], p, r, lo[t], hi[t]);
+    prod_core<K, WIDE>(lo, hi, acc);
+  }
+  Fr sums[K + 1];
+#pragma unroll
+  for (int x = 0; x <= K; x++) sums[x] = acc.get(x);
+  block_sum_many(sums, K + 1, s_part, &partials[(size_t)blockIdx.x * (K + 1)]);
 }
 
 // ---- round kernel, generic expression tree -----------------------------------------------------------------------------------
@@ -201,11 +273,16 @@ __global__ void __launch_bounds__(SC_THREADS) sc_tail(ScTables tabs, ScTailBufs 
     Fr r = fp_zero<FrParams>();
     if (pending_fold) r = head->r;
     Fr acc[SC_MAX_COEFFS];
-    for (int x = 0; x <= d; x++) acc[x] = fp_zero<FrParams>();
-    for (uint64_t p = threadIdx.x; p < n_pairs; p += blockDim.x) {
-      if (KP > 0)
-        prod_pair<(KP > 0 ? KP : 1)>(view, p, pending_fold != 0, r, acc);
-      else
+    if (KP > 0) {
+      constexpr int KX = KP > 0 ? KP : 1;
+      ProdAcc<KX, false> pa;
+      pa.init();
+      for (uint64_t p = threadIdx.x; p < n_pairs; p += blockDim.x) prod_pair<KX, false>(view, p, pending_fold != 0, r, pa);
+#pragma unroll
+      for (int x = 0; x <= KX; x++) acc[x] = pa.get(x);
+    } else {
+      for (int x = 0; x <= d; x++) acc[x] = fp_zero<FrParams>();
+      for (uint64_t p = threadIdx.x; p < n_pairs; p += blockDim.x)
         generic_pair(view, p, pending_fold != 0, r, s_ops, n_ops, k, d, consts, acc);
     }
     block_sum_many(acc, d + 1, s_part, s_evals);
@@ -478,8 +555,8 @@ int get_vinv(qz_ctx* ctx, int d, Fr** out) {
   return QZ_OK;
 }
 
-int round_grid(qz_ctx* ctx, uint64_t n_pairs, int blocks_per_sm) {
-  uint64_t want = (n_pairs + SC_THREADS - 1) / SC_THREADS;
+int round_grid(qz_ctx* ctx, uint64_t n_pairs, int blocks_per_sm, int threads = SC_THREADS) {
+  uint64_t want = (n_pairs + threads - 1) / threads;
   uint64_t cap = (uint64_t)ctx->sm_count * blocks_per_sm;
   return (int)std::max<uint64_t>(1, std::min(want, cap));
 }
@@ -700,13 +777,19 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
     }
     // occupancy-sized grids for the streaming rounds
     int bps = 1;
-    if (cp.product_k == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sc_round_prod<1>, SC_THREADS, 0);
-    else if (cp.product_k == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sc_round_prod<2>, SC_THREADS, 0);
-    else if (cp.product_k == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sc_round_prod<3>, SC_THREADS, 0);
-    else if (cp.product_k == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sc_round_prod<4>, SC_THREADS, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sc_round_generic, SC_THREADS, 0);
+    int bps_wide = 0;  // > 0: a deferred-reduction variant of the round kernel exists for this product
+    if (cp.product_k == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sc_round_prod<1, false, true>, SC_THREADS, 0);
+    else if (cp.product_k == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sc_round_prod<2, false, true>, SC_THREADS, 0);
+    else if (cp.product_k == 3) {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sc_round_prod<3, false, true>, SC_THREADS, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_wide, sc_round_prod<3, true, true>, SC_WIDE_THREADS, 0);
+    } else if (cp.product_k == 4) {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sc_round_prod<4, false, true>, SC_THREADS, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_wide, sc_round_prod<4, true, true>, SC_WIDE_THREADS, 0);
+    } else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sc_round_generic, SC_THREADS, 0);
     if (bps < 1) bps = 1;
-    Fr* partials = (Fr*)ctx->arena_alloc(sizeof(Fr) * (size_t)ctx->sm_count * bps * (d + 1));
+    if (getenv("QZ_SC_NARROW")) bps_wide = 0;  // measurement switch: force the fully reduced sums
+    Fr* partials = (Fr*)ctx->arena_alloc(sizeof(Fr) * (size_t)ctx->sm_count * std::max(bps, bps_wide) * (d + 1));
     Fr* rank_evals = (Fr*)ctx->arena_alloc(sizeof(Fr) * (d + 1));
     Fr* all_evals = (Fr*)ctx->arena_alloc(sizeof(Fr) * (size_t)(d + 1) * G);
     if (!partials || !rank_evals || !all_evals) return ctx->fail(QZ_ERR_ALLOC, "partials");
@@ -718,12 +801,25 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
     while (size * G > ((uint64_t)1 << SC_TAIL_LOG)) {
       const uint64_t n_pairs = pending ? size / 4 : size / 2;
       for (int j = 0; j < ka; j++) tabs.out[j] = flip ? bufB[j] : bufA[j];
-      const int grid = round_grid(ctx, n_pairs, bps);
+      // deferred reduction pays once a thread sums several pairs (its one-off reduction is 3 products per sum)
+      const bool wide = bps_wide > 0 && n_pairs >= (uint64_t)8 * SC_WIDE_THREADS * ctx->sm_count * bps_wide;
+      const int grid = wide ? round_grid(ctx, n_pairs, bps_wide, SC_WIDE_THREADS) : round_grid(ctx, n_pairs, bps);
+#define QZ_ROUND_PROD(K, W, T)                                                                                  \
+  do {                                                                                                          \
+    if (pending) QZ_LAUNCH(ctx, (sc_round_prod<K, W, true>), grid, T, 0, tabs, n_pairs, head, partials);         \
+    else QZ_LAUNCH(ctx, (sc_round_prod<K, W, false>), grid, T, 0, tabs, n_pairs, head, partials);                \
+  } while (0)
       switch (cp.product_k) {
-        case 1: QZ_LAUNCH(ctx, sc_round_prod<1>, grid, SC_THREADS, 0, tabs, n_pairs, pending, head, partials); break;
-        case 2: QZ_LAUNCH(ctx, sc_round_prod<2>, grid, SC_THREADS, 0, tabs, n_pairs, pending, head, partials); break;
-        case 3: QZ_LAUNCH(ctx, sc_round_prod<3>, grid, SC_THREADS, 0, tabs, n_pairs, pending, head, partials); break;
-        case 4: QZ_LAUNCH(ctx, sc_round_prod<4>, grid, SC_THREADS, 0, tabs, n_pairs, pending, head, partials); break;
+        case 1: QZ_ROUND_PROD(1, false, SC_THREADS); break;
+        case 2: QZ_ROUND_PROD(2, false, SC_THREADS); break;
+        case 3:
+          if (wide) QZ_ROUND_PROD(3, true, SC_WIDE_THREADS);
+          else QZ_ROUND_PROD(3, false, SC_THREADS);
+          break;
+        case 4:
+          if (wide) QZ_ROUND_PROD(4, true, SC_WIDE_THREADS);
+          else QZ_ROUND_PROD(4, false, SC_THREADS);
+          break;
         default:
           QZ_LAUNCH(ctx, sc_round_generic, grid, SC_THREADS, 0, tabs, n_pairs, pending, head, d_prog, d_consts,
                     partials);

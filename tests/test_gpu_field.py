@@ -38,6 +38,17 @@ def test_field_ops_bit_exact(ctx, field, mod):
 
 
 @pytest.mark.parametrize("field,mod", [(0, FR), (1, FQ)])
+def test_deferred_reduction_accumulator(ctx, field, mod):
+    """sums of unreduced 512-bit products reduced once (ff.cuh wide_mul_acc / wide_reduce) equal the sums of
+    Montgomery products, including when the accumulator's 17th word is in use"""
+    a = _edge_and_random(mod, 2048, 21 + field)
+    b = list(reversed(_edge_and_random(mod, 2048, 23 + field)))
+    A, B = co.to_mont(a, mod), co.to_mont(b, mod)
+    assert co.from_mont(ctx.field_op(field, 6, A, B), mod) == [(x * y + x * x + y * y) % mod for x, y in zip(a, b)]
+    assert co.from_mont(ctx.field_op(field, 7, A, B), mod) == [4096 * x * y % mod for x, y in zip(a, b)]
+
+
+@pytest.mark.parametrize("field,mod", [(0, FR), (1, FQ)])
 def test_field_inverse(ctx, field, mod):
     a = _edge_and_random(mod, 64, 9)
     A = co.to_mont(a, mod)
