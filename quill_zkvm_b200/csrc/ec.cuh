@@ -3,7 +3,8 @@
 // performs under VariableBaseMSM::msm_unchecked (called at pcs/src/kzg.rs:72).  The result of an MSM is a group
 // element, so the choice of coordinates cannot change the affine point that is finally serialised.
 //
-// Mixed addition XYZZ + affine costs 8M + 2S and is the unit of work of bucket accumulation.  Every routine here is
+// Mixed addition XYZZ + affine costs 8M + 2S (Y3 = R (Q - X3) - Y1 PPP as one fused two-product reduction, i.e. 9.5
+// multiplications' worth of multiply-adds) and is the unit of work of bucket accumulation.  Every routine here is
 // COMPLETE: the P == +-Q and identity cases are detected (values are canonical, so equality is a limb compare) and
 // routed to doubling / identity, because bucket reduction and tiny inputs hit them deterministically.
 #pragma once
@@ -80,7 +81,7 @@ QZ_DEV Xyzz xyzz_dbl_affine(const Affine& a) {
   Fq xx = fp_sqr<FqParams>(a.x), m = fp_add<FqParams>(fp_dbl<FqParams>(xx), xx);
   Xyzz r;
   r.x = fp_sub<FqParams>(fp_sqr<FqParams>(m), fp_dbl<FqParams>(s));
-  r.y = fp_sub<FqParams>(fp_mul<FqParams>(m, fp_sub<FqParams>(s, r.x)), fp_mul<FqParams>(w, a.y));
+  r.y = fp_mul2_add<FqParams>(m, fp_sub<FqParams>(s, r.x), fp_neg<FqParams>(w), a.y);  // m (s - x3) - w y
   r.zz = v;
   r.zzz = w;
   return r;
@@ -92,7 +93,7 @@ QZ_DEV Xyzz xyzz_dbl(const Xyzz& p) {
   Fq xx = fp_sqr<FqParams>(p.x), m = fp_add<FqParams>(fp_dbl<FqParams>(xx), xx);
   Xyzz r;
   r.x = fp_sub<FqParams>(fp_sqr<FqParams>(m), fp_dbl<FqParams>(s));
-  r.y = fp_sub<FqParams>(fp_mul<FqParams>(m, fp_sub<FqParams>(s, r.x)), fp_mul<FqParams>(w, p.y));
+  r.y = fp_mul2_add<FqParams>(m, fp_sub<FqParams>(s, r.x), fp_neg<FqParams>(w), p.y);  // m (s - x3) - w y
   r.zz = fp_mul<FqParams>(v, p.zz);
   r.zzz = fp_mul<FqParams>(w, p.zzz);
   return r;
@@ -110,7 +111,7 @@ QZ_DEV Xyzz xyzz_add_affine(const Xyzz& p, const Affine& a) {
   Fq pp = fp_sqr<FqParams>(pp_), ppp = fp_mul<FqParams>(pp_, pp), q = fp_mul<FqParams>(p.x, pp);
   Xyzz r;
   r.x = fp_sub<FqParams>(fp_sub<FqParams>(fp_sqr<FqParams>(rr), ppp), fp_dbl<FqParams>(q));
-  r.y = fp_sub<FqParams>(fp_mul<FqParams>(rr, fp_sub<FqParams>(q, r.x)), fp_mul<FqParams>(p.y, ppp));
+  r.y = fp_mul2_add<FqParams>(rr, fp_sub<FqParams>(q, r.x), fp_neg<FqParams>(p.y), ppp);  // r (q - x3) - y1 ppp, one reduction
   r.zz = fp_mul<FqParams>(p.zz, pp);
   r.zzz = fp_mul<FqParams>(p.zzz, ppp);
   return r;
@@ -129,7 +130,7 @@ QZ_DEV Xyzz xyzz_add(const Xyzz& p1, const Xyzz& p2) {
   Fq pp = fp_sqr<FqParams>(pp_), ppp = fp_mul<FqParams>(pp_, pp), q = fp_mul<FqParams>(u1, pp);
   Xyzz r;
   r.x = fp_sub<FqParams>(fp_sub<FqParams>(fp_sqr<FqParams>(rr), ppp), fp_dbl<FqParams>(q));
-  r.y = fp_sub<FqParams>(fp_mul<FqParams>(rr, fp_sub<FqParams>(q, r.x)), fp_mul<FqParams>(s1, ppp));
+  r.y = fp_mul2_add<FqParams>(rr, fp_sub<FqParams>(q, r.x), fp_neg<FqParams>(s1), ppp);
   r.zz = fp_mul<FqParams>(fp_mul<FqParams>(p1.zz, p2.zz), pp);
   r.zzz = fp_mul<FqParams>(fp_mul<FqParams>(p1.zzz, p2.zzz), ppp);
   return r;

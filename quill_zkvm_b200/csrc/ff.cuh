@@ -208,6 +208,51 @@ QZ_DEV Fp<P> fp_mul_v1(const Fp<P>& a, const Fp<P>& b) {
   return r;
 }
 
+// a*b + c*d with ONE Montgomery reduction: both product rows enter the running sum before the reduction row, so the
+// pair costs 8 x 24 = 192 multiply-adds instead of 256.  With a, c < p the running sum stays below 3p < 2^256
+// (t' < (t + 3p(2^32 - 1)) / 2^32), so the same nine columns suffice and two conditional subtractions finish.
+template <class P>
+QZ_DEV Fp<P> fp_mul2_add(const Fp<P>& a, const Fp<P>& b, const Fp<P>& c, const Fp<P>& d) {
+  uint32_t X[8], Y[8];
+  mul4(X, a.v[0], a.v[2], a.v[4], a.v[6], b.v[0]);
+  mul4(Y, a.v[1], a.v[3], a.v[5], a.v[7], b.v[0]);
+  cmad4(Y, c.v[1], c.v[3], c.v[5], c.v[7], d.v[0]);
+  cmad4_top(X, c.v[0], c.v[2], c.v[4], c.v[6], d.v[0], Y[7]);
+  mont_reduce_row<P>(X, Y);
+#pragma unroll
+  for (int i = 1; i < 8; i += 2) {
+    madc4_rshift(X, Y[0], a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
+    cmad4_top(Y, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i], X[7]);
+    cmad4(X, c.v[1], c.v[3], c.v[5], c.v[7], d.v[i]);
+    cmad4_top(Y, c.v[0], c.v[2], c.v[4], c.v[6], d.v[i], X[7]);
+    mont_reduce_row<P>(Y, X);
+    if (i + 1 < 8) {
+      madc4_rshift(Y, X[0], a.v[1], a.v[3], a.v[5], a.v[7], b.v[i + 1]);
+      cmad4_top(X, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i + 1], Y[7]);
+      cmad4(Y, c.v[1], c.v[3], c.v[5], c.v[7], d.v[i + 1]);
+      cmad4_top(X, c.v[0], c.v[2], c.v[4], c.v[6], d.v[i + 1], Y[7]);
+      mont_reduce_row<P>(X, Y);
+    }
+  }
+  uint32_t t[8], u[8];
+  asm volatile(
+      "add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, 0;\n\t"
+      : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7])
+      : "r"(X[0]), "r"(X[1]), "r"(X[2]), "r"(X[3]), "r"(X[4]), "r"(X[5]), "r"(X[6]), "r"(X[7]), "r"(Y[1]), "r"(Y[2]),
+        "r"(Y[3]), "r"(Y[4]), "r"(Y[5]), "r"(Y[6]), "r"(Y[7]));
+  Fp<P> r;
+  fp_reduce_once<P>(u, t);
+  fp_reduce_once<P>(r.v, u);
+  return r;
+}
+
 // The multiplier is ~350 SASS instructions (5.6 KB); a mixed point addition inlines 10 of them.  ncu (r01) shows
 // "no_instruction" as the top stall of msm_accumulate, but calling ONE out-of-line copy per field (-DQZ_OUTLINE_MUL)
 // measured no faster for the MSM (63.3 vs 62.2 ms at 2^24) and 14% slower for the sumcheck rounds, so inlining stays

@@ -7,7 +7,7 @@
 //   1. msm_digits        scalar: Montgomery -> canonical -> signed c-bit digits; one (key, value) per (window, scalar)
 //                        key = window << c | |digit|, value = point index | sign << 31
 //   2. radix sort        (key, value) pairs by key (cub::DeviceRadixSort) -> every bucket's points are contiguous
-//   3. msm_accumulate    the hot kernel: the sorted list is cut into fixed chunks of ACC_CHUNK entries, one thread per
+//   3. msm_accumulate    the hot kernel: the sorted list is cut into fixed chunks of 32..128 entries, one thread per
 //                        chunk, XYZZ += affine (8M + 2S) per entry with the next base prefetched; load is balanced
 //                        whatever the scalar distribution.  A chunk's first / last runs may be partial buckets and go
 //                        to a list of partial runs, interior runs are complete buckets and are written in place.
@@ -26,7 +26,8 @@
 
 namespace qz {
 
-constexpr int ACC_CHUNK = 32;        // sorted entries per accumulate thread
+constexpr int ACC_CHUNK_MIN = 32;    // sorted entries per accumulate thread: 32 .. 128, longer for large inputs (every
+constexpr int ACC_CHUNK_MAX = 128;   // chunk leaves up to two partial runs behind, each a full addition to merge later)
 constexpr int ACC_THREADS = 128;
 constexpr int RED_SEG = 32;          // buckets per bucket-reduce thread
 constexpr uint32_t KEY_NONE = 0xffffffffu;
@@ -73,14 +74,14 @@ QZ_DEV uint32_t bucket_slot(uint32_t key, int c) {  // dense slot of a non-zero 
 // Partial runs go to a list of (key, XYZZ) slots, two per chunk: slot 2*chunk = the run touching the chunk's start,
 // slot 2*chunk + 1 = the run touching its end (KEY_NONE = empty).  Keys of non-empty slots are non-decreasing.
 __global__ void __launch_bounds__(ACC_THREADS, 4) msm_accumulate(const uint32_t* keys, const uint32_t* vals, uint64_t m,
-                                                              const uint8_t* bases, int c, uint8_t* buckets,
-                                                              uint8_t* ppts, uint32_t* pkeys) {
+                                                              int chunk_len, const uint8_t* bases, int c,
+                                                              uint8_t* buckets, uint8_t* ppts, uint32_t* pkeys) {
   const uint64_t chunk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t begin = chunk * ACC_CHUNK;
+  const uint64_t begin = chunk * chunk_len;
   if (begin >= m) return;
   uint8_t* heads = ppts;             // slot 2*chunk
   uint8_t* tails = ppts + 128;       // slot 2*chunk + 1
-  const uint64_t end = begin + ACC_CHUNK < m ? begin + ACC_CHUNK : m;
+  const uint64_t end = begin + chunk_len < m ? begin + chunk_len : m;
   const uint32_t dmask = (1u << c) - 1;
   Xyzz acc = xyzz_identity();
   uint32_t cur_key = keys[begin];
@@ -450,7 +451,10 @@ int msm_device(qz_ctx* ctx, const qz_srs* srs, const uint4* scalars_dev, size_t 
   ctx->last_stat[3] = (double)m;
   if (m >= ((uint64_t)1 << 32)) return ctx->fail(QZ_ERR_INVALID_ARG, "MSM too large for 32-bit positions");
   const uint32_t n_keys = (uint32_t)W << c, per_w = 1u << (c - 1), n_slots = (uint32_t)W * per_w;
-  const uint64_t n_chunks = (m + ACC_CHUNK - 1) / ACC_CHUNK;
+  // chunk length: at least ~16 chunks per resident accumulate thread, else the minimum
+  int chunk_len = (int)std::min<uint64_t>(ACC_CHUNK_MAX, m / ((uint64_t)ctx->sm_count * 4 * ACC_THREADS * 16));
+  chunk_len = std::max(ACC_CHUNK_MIN, chunk_len / 32 * 32);
+  const uint64_t n_chunks = (m + chunk_len - 1) / chunk_len;
   int key_bits = c;
   while ((1u << (key_bits - c)) < (uint32_t)W) key_bits++;
 
@@ -490,7 +494,7 @@ int msm_device(qz_ctx* ctx, const qz_srs* srs, const uint4* scalars_dev, size_t 
   QZ_CUDA(ctx, cudaMemsetAsync(buckets, 0, (size_t)n_slots * 128, st));
   QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k0, st));
   QZ_LAUNCH(ctx, msm_accumulate, (unsigned)((n_chunks + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, skeys, svals,
-            m, bases, c, buckets, ppts_a, pkeys_a);
+            m, chunk_len, bases, c, buckets, ppts_a, pkeys_a);
   QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k1, st));
   {  // merge partial runs level by level until one chunk holds them all
     const uint32_t* kin = pkeys_a;
