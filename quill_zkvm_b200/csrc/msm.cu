@@ -131,7 +131,9 @@ __global__ void __launch_bounds__(ACC_THREADS, 4) msm_accumulate(const uint32_t*
 // the chunk's ends go to the next level's list.  At the level that fits one chunk every run is complete.  The depth is
 // log_{PART_CHUNK/2}(#chunks) and every level is fully parallel, so one huge bucket (all scalars equal, selector
 // columns, small witness values) costs no more than a uniform distribution.
-constexpr int PART_CHUNK = 64;
+// A level is latency-bound (a full addition is ~5 us on a lone warp and a thread adds its slots serially), so the
+// chunks are short: every level divides the list by PART_CHUNK / 2 in about PART_CHUNK addition latencies.
+constexpr int PART_CHUNK = 8;
 __global__ void __launch_bounds__(128) msm_partials_reduce(const uint32_t* pkeys_in, const uint8_t* ppts_in, uint64_t n_in,
                                                            int c, uint8_t* buckets, uint32_t* pkeys_out, uint8_t* ppts_out,
                                                            int last_level) {
@@ -470,7 +472,8 @@ int msm_device(qz_ctx* ctx, const qz_srs* srs, const uint4* scalars_dev, size_t 
   uint8_t* ppts_b = (uint8_t*)ctx->arena_alloc(n_part1 * 128);
   uint32_t* pkeys_b = (uint32_t*)ctx->arena_alloc(n_part1 * 4);
   // small problems are latency-bound: shorter running-sum segments (more threads, shorter dependent chains)
-  const int seg_want = n_slots <= (1u << 17) ? 8 : RED_SEG;
+  // large bucket sets: one wave of threads (2^15 x 64 buckets at c = 22) beats two waves of shorter chains
+  const int seg_want = n_slots <= (1u << 17) ? 8 : n_slots >= (1u << 21) ? 2 * RED_SEG : RED_SEG;
   const int seg = per_w >= (uint32_t)seg_want ? seg_want : (int)per_w;
   const uint32_t red_threads = n_slots / seg, per_window_parts = per_w / seg;
   uint8_t* partial = (uint8_t*)ctx->arena_alloc((size_t)red_threads * 128);
