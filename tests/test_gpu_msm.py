@@ -197,3 +197,16 @@ def test_precomputed_windows_2_20_and_2_24(ctx):
         assert np.array_equal(got, co.g1_mul(co.g1_to_bytes(GEN), y)), logn
         y2, _ = co.kzg_open_quotient(sc[: n // 2 + 3], co.fr1(TAU))
         assert np.array_equal(half, co.g1_mul(co.g1_to_bytes(GEN), y2)), logn
+
+
+def test_msm_2_26_closed_form(ctx):
+    """the upper end of north_star's range (2^16..2^26): 4 GiB of bases, 2 GiB of scalars; commit(p) = p(tau) * g"""
+    n = 1 << 26
+    kzg = q.KZG.trusted_setup(ctx, n - 1, co.g1_to_bytes(GEN), co.fr1(TAU))
+    buf = ctx.random_fr(n, 2626)
+    got = kzg.commit(buf)
+    sc = buf.download().reshape(-1, 32)
+    buf.free()
+    kzg.srs.free()
+    y, _ = co.kzg_open_quotient(sc, co.fr1(TAU))
+    assert np.array_equal(got, co.g1_mul(co.g1_to_bytes(GEN), y))

@@ -235,3 +235,34 @@ def test_baseline_sizes_product3(ctx, n):
     ok, vp, ve = co.sumcheck_verify(n, co.fr1(true_sum), coeffs, np.array([p.shape[0] for p in sc2.r_polys], np.uint32),
                                     co.transcript_new(b"v"))
     assert ok and np.array_equal(ve, claim2.evaluation)
+
+
+def test_2_26_product3_verifier_and_mle(ctx):
+    """the upper end of north_star's range (2^16..2^26; 3 x 2 GiB of tables).  The oracle prover would take minutes, so
+    this checks the size-independent properties: the reference's verifier (sumcheck.rs:116-150) accepts the transcript
+    with the true sum and reproduces the prover's point and claim, and the claim equals the product of the tables'
+    MLE evaluations at that point (the reference's own acceptance test, sumcheck.rs:216-229)."""
+    n = 26
+    bufs = [ctx.random_fr(1 << n, 2600 + t) for t in range(3)]
+    store = q.VirtualPolynomialStore(n)
+    for b in bufs:
+        store.allocate_polynomial(b)
+    h = store.new_virtual_from_expr(util.to_qexpr(*util.expr_product(3)))
+    sc, _ = q.SumcheckProof.prove(ctx, n, store, h, co.fr1(1), q.Transcript(b"probe", ctx))
+    c0 = co.from_mont(sc.r_polys[0])
+    true_sum = (2 * c0[0] + sum(c0[1:])) % FR  # s_0(0) + s_0(1)
+    tr = q.Transcript(b"sumcheck_bench", ctx)
+    sc, claim = q.SumcheckProof.prove(ctx, n, store, h, co.fr1(true_sum), tr)
+    coeffs = np.zeros((n, 8, 32), dtype=np.uint8)
+    for j, p in enumerate(sc.r_polys):
+        coeffs[j, : p.shape[0]] = p
+    st = co.transcript_new(b"sumcheck_bench")
+    ok, vp, ve = co.sumcheck_verify(n, co.fr1(true_sum), coeffs, np.array([p.shape[0] for p in sc.r_polys], np.uint32), st)
+    assert ok and np.array_equal(vp, claim.point) and np.array_equal(ve, claim.evaluation)
+    assert st.tobytes() == tr.state.tobytes()
+    prod = None
+    for b in bufs:
+        ev = co.mle_evaluate(b.download().reshape(-1, 32), claim.point)
+        b.free()
+        prod = ev if prod is None else co.field_op(0, 2, prod, ev)
+    assert np.array_equal(prod.reshape(32), claim.evaluation)
