@@ -46,6 +46,8 @@ def test_deferred_reduction_accumulator(ctx, field, mod):
     A, B = co.to_mont(a, mod), co.to_mont(b, mod)
     assert co.from_mont(ctx.field_op(field, 6, A, B), mod) == [(x * y + x * x + y * y) % mod for x, y in zip(a, b)]
     assert co.from_mont(ctx.field_op(field, 7, A, B), mod) == [4096 * x * y % mod for x, y in zip(a, b)]
+    # dedicated squaring (36 limb products + a separate reduction)
+    assert co.from_mont(ctx.field_op(field, 9, A), mod) == [x * x % mod for x in a]
     # fused two-product multiplier (one Montgomery reduction for a*b + c*d), used by the group law's Y3
     assert co.from_mont(ctx.field_op(field, 8, A, B), mod) == [(x * y + (x + y) * (x - y)) % mod for x, y in zip(a, b)]
 
