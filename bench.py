@@ -351,10 +351,13 @@ def run_gpu(args):
                  "workload": f"MultilinearPCS::commit + ::open of a 2^{nm}-entry MLE (6 MSMs, eq table, NTT 2^{nm + 1}, 4 quotients)"}
         poly.free()
 
-    # ---- config 5: HyperPlonk prove of two transition-circuit traces (Fibonacci + modified Fibonacci), N = 1 only ----
+    # ---- config 5: HyperPlonk prove of two transition-circuit traces (Fibonacci + modified Fibonacci); with N > 1 every
+    # rank holds the traces and the full SRS and the MLPCS openings (5 MSMs each) are dealt to the ranks ----
     hplonk = None
-    if world == 1 and args.hyperplonk_log_rows > 0:
-        hplonk = bench_hyperplonk(ctx, q, args.hyperplonk_log_rows, g_bytes, mont(TAU), timed_loop)
+    if args.hyperplonk_log_rows > 0:
+        hplonk = bench_hyperplonk(ctx, q, args.hyperplonk_log_rows, np.concatenate([mont(1, FQ), mont(2, FQ)]), mont(TAU),
+                                  timed_loop)
+        hplonk["n_gpus"] = world
 
     # ---- sumcheck: three 2^log_n tables, degree-3 product ----
     nv = args.log_n

@@ -129,6 +129,17 @@ int qz_kzg_open(qz_ctx* ctx, const qz_srs* srs, const void* coeffs, size_t n_coe
 int qz_mlpcs_open(qz_ctx* ctx, const qz_srs* srs, const void* poly, size_t n, int poly_on_device, const uint8_t* point,
                   size_t n_point, uint8_t state[32], uint8_t out_evaluation[32], uint8_t out_s_comm[64],
                   uint8_t out_openings[512]);
+/* The same opening in the two halves its Fiat-Shamir challenge separates, so that independent openings (HyperPlonk issues
+ * num_cols + num_public + 5 per trace, proof.rs:202-226, multiset_check.rs:167-170) can be spread over GPUs:
+ *   begin   P_r, evaluation, S, commit(S) (mlpcs.rs:86-97); S stays on the device in *out_s_dev (release it with
+ *           qz_dev_free), *out_s_len is the length its commitment and openings use
+ *   (caller: absorb point, evaluation, S commitment; squeeze r -- mlpcs.rs:100-105, the qz_transcript_* calls)
+ *   finish  the four KZG openings of poly and S at r and 1/r (mlpcs.rs:107-113), layout as in qz_mlpcs_open */
+int qz_mlpcs_open_begin(qz_ctx* ctx, const qz_srs* srs, const void* poly, size_t n, int poly_on_device,
+                        const uint8_t* point, size_t n_point, uint8_t out_evaluation[32], uint8_t out_s_comm[64],
+                        void** out_s_dev, size_t* out_s_len);
+int qz_mlpcs_open_finish(qz_ctx* ctx, const qz_srs* srs, const void* poly, size_t n, int poly_on_device,
+                         const void* s_dev, size_t s_len, const uint8_t r[32], uint8_t out_openings[512]);
 /* InnerProductProof::compute_s_polynomial (ipa.rs:122-157): writes max(n1, n2) - 1 coefficients to `out` (host), NOT
  * trimmed (the reference's DensePolynomial drops trailing zeros; they do not change any commitment or opening). */
 int qz_compute_s_polynomial(qz_ctx* ctx, const uint8_t* p1, size_t n1, const uint8_t* p2, size_t n2, uint8_t* out);
@@ -178,6 +189,10 @@ int qz_sumcheck_prove_sharded(qz_ctx* ctx, size_t num_vars, size_t k, const void
                               int tables_on_device, const qz_expr_node* nodes, size_t n_nodes, const uint8_t* consts,
                               size_t n_consts, const uint8_t claimed_sum[32], uint8_t state[32], size_t max_coeffs,
                               uint8_t* out_coeffs, uint32_t* out_lens, uint8_t* out_point, uint8_t out_eval[32]);
+
+/* All-gather of `bytes` host bytes per rank into `recv` (nranks * bytes, rank-major) over the library's communicator:
+ * the exchange of (evaluation, S commitment) and of finished openings between the halves above. */
+int qz_comm_allgather_host(qz_ctx* ctx, const void* send, void* recv, size_t bytes);
 
 /* ---- measurement hooks ---------------------------------------------------------------------------------------------- */
 /* CUDA-event timing of the most recent call on this context, on the context's stream (milliseconds):

@@ -21,9 +21,10 @@ SYMBOLS = [
     "qz_transcript_new", "qz_transcript_append_bytes", "qz_transcript_draw_challenge", "qz_transcript_draw_fr",
     "qz_transcript_append_fr", "qz_transcript_append_g1", "qz_g1_serialize",
     "qz_srs_upload", "qz_srs_generate", "qz_srs_precompute", "qz_srs_free", "qz_srs_len", "qz_srs_download",
-    "qz_msm", "qz_kzg_commit", "qz_kzg_open", "qz_mlpcs_open", "qz_compute_s_polynomial",
+    "qz_msm", "qz_kzg_commit", "qz_kzg_open", "qz_mlpcs_open", "qz_mlpcs_open_begin", "qz_mlpcs_open_finish",
+    "qz_compute_s_polynomial",
     "qz_sumcheck_prove", "qz_zerocheck_prove", "qz_eq_table", "qz_logup_denominators",
-    "qz_comm_unique_id", "qz_comm_init", "qz_msm_sharded", "qz_sumcheck_prove_sharded",
+    "qz_comm_unique_id", "qz_comm_init", "qz_msm_sharded", "qz_sumcheck_prove_sharded", "qz_comm_allgather_host",
     "qz_last_elapsed_ms", "qz_last_stat", "qz_bench_imad", "qz_bench_fp_mul",
     "qz_test_field_op", "qz_test_g1_add", "qz_test_g1_mul",
 ]
@@ -93,6 +94,8 @@ def load():
     lib.qz_kzg_commit.argtypes = [vp, vp, vp, sz, i32, vp]
     lib.qz_kzg_open.argtypes = [vp, vp, vp, sz, i32, vp, vp, vp]
     lib.qz_mlpcs_open.argtypes = [vp, vp, vp, sz, i32, vp, sz, vp, vp, vp, vp]
+    lib.qz_mlpcs_open_begin.argtypes = [vp, vp, vp, sz, i32, vp, sz, vp, vp, C.POINTER(vp), C.POINTER(sz)]
+    lib.qz_mlpcs_open_finish.argtypes = [vp, vp, vp, sz, i32, vp, sz, vp, vp]
     lib.qz_compute_s_polynomial.argtypes = [vp, vp, sz, vp, sz, vp]
     sc = [vp, sz, sz, vp, i32, vp, sz, vp, sz, vp, vp, sz, vp, vp, vp, vp]
     lib.qz_sumcheck_prove.argtypes = sc
@@ -103,6 +106,7 @@ def load():
     lib.qz_comm_unique_id.argtypes = [vp]
     lib.qz_comm_init.argtypes = [vp, vp, i32, i32]
     lib.qz_msm_sharded.argtypes = [vp, vp, vp, sz, i32, vp]
+    lib.qz_comm_allgather_host.argtypes = [vp, vp, vp, sz]
     lib.qz_last_elapsed_ms.argtypes = [vp, i32]
     lib.qz_last_elapsed_ms.restype = C.c_float
     lib.qz_last_stat.argtypes = [vp, i32]

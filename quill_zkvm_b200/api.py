@@ -114,6 +114,17 @@ class Context:
         self.check(self.lib.qz_comm_init(self.h, _ptr(_u8(unique_id)), rank, nranks))
         self.rank, self.nranks = rank, nranks
 
+    def allgather(self, mine: np.ndarray) -> np.ndarray:
+        """All-gather a small uint8 array over the library's communicator -> (nranks, len)."""
+        mine = _u8(mine).reshape(-1)
+        n = getattr(self, "nranks", 1)
+        out = np.zeros((n, mine.shape[0]), dtype=np.uint8)
+        if n == 1:
+            out[0] = mine
+        elif mine.shape[0]:
+            self.check(self.lib.qz_comm_allgather_host(self.h, _ptr(mine), _ptr(out), mine.shape[0]))
+        return out
+
     # -- test hooks ----------------------------------------------------------------------------------------------------
     def field_op(self, field: int, op: int, a: np.ndarray, b: Optional[np.ndarray] = None) -> np.ndarray:
         a = _u8(a, (-1, 32))
@@ -191,6 +202,12 @@ class Transcript:
         """append_serializable(&Fr): 32-byte canonical little-endian (conversion from Montgomery on the device)."""
         self.ctx.check(self.lib.qz_transcript_append_fr(self.ctx.h, _ptr(self.state), _ptr(_u8(fr, (32,)))))
 
+    def append_fr_vec(self, frs: np.ndarray):
+        """append_serializable(&[Fr]) / &Vec<Fr>: u64 LE length, then each element canonical (mlpcs.rs:100)."""
+        frs = _u8(frs, (-1, 32))
+        body = self.ctx.field_op(0, 5, frs).tobytes() if frs.shape[0] else b""  # Montgomery -> canonical on the device
+        self.append_bytes(int(frs.shape[0]).to_bytes(8, "little") + body)
+
     def append_g1(self, xy: np.ndarray):
         """append_serializable(&G1): ark-serialize uncompressed encoding."""
         self.ctx.check(self.lib.qz_transcript_append_g1(self.ctx.h, _ptr(self.state), _ptr(_u8(xy, (64,)))))
@@ -253,6 +270,23 @@ class MLEvalProof:
     poly_opening_inv: KZGOpeningProof
     s_opening: KZGOpeningProof
     s_opening_inv: KZGOpeningProof
+
+    @staticmethod
+    def from_parts(eval_point, evaluation, s_comm, ops) -> "MLEvalProof":
+        """ops: (4, 128) rows of x ‖ y ‖ proof in the order of mlpcs.rs:109-113"""
+        o = [KZGOpeningProof(ops[i, :32].copy(), ops[i, 32:64].copy(), ops[i, 64:].copy()) for i in range(4)]
+        return MLEvalProof(eval_point, evaluation, s_comm, o[0], o[1], o[2], o[3])
+
+
+@dataclass
+class PendingOpening:
+    """An MLEvalProof between its two halves (KZG.open_multilinear_begin / _finish)."""
+    poly: object
+    eval_point: np.ndarray
+    evaluation: np.ndarray
+    s_comm: np.ndarray
+    s_dev: Optional[int]
+    s_len: int
 
 
 class KZG:
@@ -328,8 +362,34 @@ class KZG:
         if rc == _lib.QZ_ERR_DEGREE:
             raise AssertionError("Polynomial degree exceeds max degree")
         self.ctx.check(rc)
-        o = [KZGOpeningProof(ops[i, :32].copy(), ops[i, 32:64].copy(), ops[i, 64:].copy()) for i in range(4)]
-        return MLEvalProof(pt.copy(), ev, sc, o[0], o[1], o[2], o[3])
+        return MLEvalProof.from_parts(pt.copy(), ev, sc, ops)
+
+    def open_multilinear_begin(self, poly, eval_point: np.ndarray) -> "PendingOpening":
+        """First half of MLEvalProof::prove (mlpcs.rs:86-97): evaluation, S (kept on the device), commit(S)."""
+        ptr, on_dev, n = self._coeffs(poly)
+        pt = _u8(eval_point, (-1, 32))
+        ev = np.zeros(32, dtype=np.uint8)
+        sc = np.zeros(64, dtype=np.uint8)
+        s_dev, s_len = C.c_void_p(), C.c_size_t()
+        rc = self.ctx.lib.qz_mlpcs_open_begin(self.ctx.h, self.srs.h, ptr, n, int(on_dev), _ptr(pt) if pt.shape[0] else None,
+                                              pt.shape[0], _ptr(ev), _ptr(sc), C.byref(s_dev), C.byref(s_len))
+        if rc == _lib.QZ_ERR_DEGREE:
+            raise AssertionError("Polynomial degree exceeds max degree")
+        self.ctx.check(rc)
+        return PendingOpening(poly, pt.copy(), ev, sc, s_dev.value, s_len.value)
+
+    def open_multilinear_finish(self, pending: "PendingOpening", r: np.ndarray) -> "MLEvalProof":
+        """Second half (mlpcs.rs:107-124): the four KZG openings at r and 1/r; releases S."""
+        ptr, on_dev, n = self._coeffs(pending.poly)
+        ops = np.zeros((4, 128), dtype=np.uint8)
+        rc = self.ctx.lib.qz_mlpcs_open_finish(self.ctx.h, self.srs.h, ptr, n, int(on_dev), pending.s_dev, pending.s_len,
+                                               _ptr(_u8(r, (32,))), _ptr(ops))
+        self.ctx.lib.qz_dev_free(self.ctx.h, pending.s_dev)
+        pending.s_dev = None
+        if rc == _lib.QZ_ERR_DEGREE:
+            raise AssertionError("Polynomial degree exceeds max degree")
+        self.ctx.check(rc)
+        return MLEvalProof.from_parts(pending.eval_point, pending.evaluation, pending.s_comm, ops)
 
     def compute_s_polynomial(self, p1: np.ndarray, p2: np.ndarray) -> np.ndarray:
         """InnerProductProof::compute_s_polynomial (pcs/src/ipa.rs:122-157), coefficients not trimmed."""

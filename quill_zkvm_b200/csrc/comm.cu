@@ -143,4 +143,21 @@ int qz_msm_sharded(qz_ctx* ctx, const qz_srs* srs, const void* scalars, size_t n
   return QZ_OK;
 }
 
+int qz_comm_allgather_host(qz_ctx* ctx, const void* send, void* recv, size_t bytes) {
+  if (!ctx || !send || !recv) return QZ_ERR_INVALID_ARG;
+  if (bytes == 0) return QZ_OK;
+  QZ_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->arena_reset();
+  cudaStream_t st = ctx->stream;
+  uint8_t* mine = (uint8_t*)ctx->arena_alloc(bytes);
+  uint8_t* all = (uint8_t*)ctx->arena_alloc(bytes * ctx->nranks);
+  if (!mine || !all) return ctx->fail(QZ_ERR_ALLOC, "all-gather buffers");
+  QZ_CUDA(ctx, cudaMemcpyAsync(mine, send, bytes, cudaMemcpyHostToDevice, st));
+  int rc = comm_allgather(ctx, mine, all, bytes);
+  if (rc) return rc;
+  QZ_CUDA(ctx, cudaMemcpyAsync(recv, all, bytes * ctx->nranks, cudaMemcpyDeviceToHost, st));
+  QZ_CUDA(ctx, cudaStreamSynchronize(st));
+  return QZ_OK;
+}
+
 }  // extern "C"

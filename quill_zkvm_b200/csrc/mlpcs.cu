@@ -296,18 +296,13 @@ int qz_compute_s_polynomial(qz_ctx* ctx, const uint8_t* p1, size_t n1, const uin
   return QZ_OK;
 }
 
-int qz_mlpcs_open(qz_ctx* ctx, const qz_srs* srs, const void* poly, size_t n, int on_device, const uint8_t* point,
-                  size_t n_point, uint8_t state[32], uint8_t out_evaluation[32], uint8_t out_s_comm[64],
-                  uint8_t out_openings[512]) {
-  if (!ctx || !srs || (n && !poly) || (n_point && !point) || !state || !out_evaluation || !out_s_comm || !out_openings)
-    return QZ_ERR_INVALID_ARG;
-  if (n_point >= (size_t)SC_MAX_VARS || n_point > 27) return ctx->fail(QZ_ERR_INVALID_ARG, "too many variables");
-  QZ_CUDA(ctx, cudaSetDevice(ctx->device));
-  ctx->arena_reset();
+// MLEvalProof::prove (mlpcs.rs:83-124) in the two halves its Fiat-Shamir challenge separates.
+// begin: P_r, evaluation, S, commit(S) (:86-97).  Everything is enqueued on the context's stream; `d_s` must hold
+// max(n, 2^n_point) elements, *s_commit_len receives the length commit(S)/open(S) work on.
+static int mlpcs_begin_device(qz_ctx* ctx, const qz_srs* srs, const uint4* pdev, size_t n, const uint8_t* point,
+                              size_t n_point, Fr* d_point, uint4* d_pr, uint4* d_s, uint8_t* d_eval, uint8_t* d_scomm,
+                              uint64_t* s_commit_len) {
   cudaStream_t st = ctx->stream;
-  QZ_CUDA(ctx, cudaEventRecord(ctx->ev_call0, st));
-  QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k0, st));
-  QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k1, st));
   // trimmed length of P_r from the point alone: coefficient j vanishes iff some bit i of j is set with r_i = 0 or clear
   // with r_i = 1, so the last non-zero coefficient is j = sum_{r_i != 0} 2^i (always non-zero)
   uint64_t pr_len = 1;
@@ -319,28 +314,7 @@ int qz_mlpcs_open(qz_ctx* ctx, const qz_srs* srs, const void* poly, size_t n, in
   const uint64_t pr_full = (uint64_t)1 << n_point;
   const uint64_t L = std::max<uint64_t>(n, pr_len);
   const uint64_t s_len = L >= 1 ? L - 1 : 0;  // untrimmed S length
-
-  uint8_t* res = (uint8_t*)ctx->arena_alloc(32 + 64 + 4 * 128 + 32 + 64);  // eval ‖ s_comm ‖ 4 x (x ‖ y ‖ proof) ‖ state ‖ r, r_inv
-  Fr* d_point = (Fr*)ctx->arena_alloc(32 * std::max<size_t>(n_point, 1));
-  uint4* d_pr = (uint4*)ctx->arena_alloc(32 * pr_full);
-  uint4* d_s = (uint4*)ctx->arena_alloc(32 * std::max<uint64_t>(s_len, 1));
-  unsigned long long* d_trim = (unsigned long long*)ctx->arena_alloc(8);
-  if (!res || !d_point || !d_pr || !d_s || !d_trim) return ctx->fail(QZ_ERR_ALLOC, "mlpcs state");
-  uint8_t* d_eval = res;
-  uint8_t* d_scomm = res + 32;
-  uint8_t* d_open = res + 96;
-  uint8_t* d_state = res + 96 + 512;
-  Fr* d_r = (Fr*)(res + 96 + 512 + 32);
-  QZ_CUDA(ctx, cudaMemsetAsync(res, 0, 96 + 512 + 32 + 64, st));
-  QZ_CUDA(ctx, cudaMemcpyAsync(d_state, state, 32, cudaMemcpyHostToDevice, st));
   if (n_point) QZ_CUDA(ctx, cudaMemcpyAsync(d_point, point, 32 * n_point, cudaMemcpyHostToDevice, st));
-  const uint4* pdev = (const uint4*)poly;
-  if (!on_device && n) {
-    void* p = ctx->arena_alloc(32 * n);
-    if (!p) return ctx->fail(QZ_ERR_ALLOC, "poly");
-    QZ_CUDA(ctx, cudaMemcpyAsync(p, poly, 32 * n, cudaMemcpyHostToDevice, st));
-    pdev = (const uint4*)p;
-  }
   int rc = eq_table_device(ctx, (int)n_point, d_point, d_pr, 0, pr_full);  // P_r coefficients (mlpcs.rs:68-78)
   if (rc) return rc;
   const uint64_t ip_n = std::min<uint64_t>(n, pr_full);  // zip stops at the shorter slice (:92)
@@ -353,31 +327,80 @@ int qz_mlpcs_open(qz_ctx* ctx, const qz_srs* srs, const void* poly, size_t n, in
     if (rc) return rc;
   }
   // commit(S) asserts on the TRIMMED length (kzg.rs:62-65); only look it up when the untrimmed one does not fit
-  uint64_t s_commit_len = s_len;
+  *s_commit_len = s_len;
   if (s_len > srs->n) {
+    unsigned long long* d_trim = (unsigned long long*)ctx->arena_alloc(8);
+    if (!d_trim) return ctx->fail(QZ_ERR_ALLOC, "mlpcs state");
     QZ_CUDA(ctx, cudaMemsetAsync(d_trim, 0, 8, st));
     QZ_LAUNCH(ctx, fr_trimmed_len, (unsigned)std::min<uint64_t>((s_len + 255) / 256, 4096), 256, 0, d_s, s_len, d_trim);
     unsigned long long t = 0;
     QZ_CUDA(ctx, cudaMemcpyAsync(&t, d_trim, 8, cudaMemcpyDeviceToHost, st));
     QZ_CUDA(ctx, cudaStreamSynchronize(st));
     if (t > srs->n) return ctx->fail(QZ_ERR_DEGREE, "Polynomial degree exceeds max degree");
-    s_commit_len = t;
+    *s_commit_len = t;
   }
   if (n > srs->n + 1) return ctx->fail(QZ_ERR_DEGREE, "Polynomial degree exceeds max degree");  // open(poly): quotient
-  rc = msm_device(ctx, srs, d_s, s_commit_len, nullptr, d_scomm);  // mlpcs.rs:97
-  if (rc) return rc;
-  QZ_LAUNCH(ctx, mlpcs_transcript, 1, 1, 0, d_state, d_point, (int)n_point, (const Fr*)d_eval, d_scomm, d_r);
-  // poly_opening, poly_opening_inv, s_opening, s_opening_inv (mlpcs.rs:109-113)
+  return msm_device(ctx, srs, d_s, *s_commit_len, nullptr, d_scomm);  // mlpcs.rs:97
+}
+// finish: poly_opening, poly_opening_inv, s_opening, s_opening_inv at d_r[0] = r and d_r[1] = 1/r (mlpcs.rs:109-113)
+static int mlpcs_finish_device(qz_ctx* ctx, const qz_srs* srs, const uint4* pdev, size_t n, const uint4* d_s,
+                               uint64_t s_commit_len, const Fr* d_r, uint8_t* d_open) {
   for (int i = 0; i < 4; i++) {
     uint8_t* o = d_open + 128 * i;
     const Fr* x = d_r + (i & 1);
-    QZ_CUDA(ctx, cudaMemcpyAsync(o, x, 32, cudaMemcpyDeviceToDevice, st));
-    if (i < 2)
-      rc = kzg_open_device(ctx, srs, pdev, n, x, (Fr*)(o + 32), o + 64);
-    else
-      rc = kzg_open_device(ctx, srs, d_s, s_commit_len, x, (Fr*)(o + 32), o + 64);
+    QZ_CUDA(ctx, cudaMemcpyAsync(o, x, 32, cudaMemcpyDeviceToDevice, ctx->stream));
+    const int rc = i < 2 ? kzg_open_device(ctx, srs, pdev, n, x, (Fr*)(o + 32), o + 64)
+                         : kzg_open_device(ctx, srs, d_s, s_commit_len, x, (Fr*)(o + 32), o + 64);
     if (rc) return rc;
   }
+  return QZ_OK;
+}
+static int mlpcs_poly_on_device(qz_ctx* ctx, const void* poly, size_t n, int on_device, const uint4** pdev) {
+  *pdev = (const uint4*)poly;
+  if (!on_device && n) {
+    void* p = ctx->arena_alloc(32 * n);
+    if (!p) return ctx->fail(QZ_ERR_ALLOC, "poly");
+    QZ_CUDA(ctx, cudaMemcpyAsync(p, poly, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
+    *pdev = (const uint4*)p;
+  }
+  return QZ_OK;
+}
+__global__ void fr_with_inverse(Fr* r) { r[1] = fp_inv<FrParams>(r[0]); }
+
+int qz_mlpcs_open(qz_ctx* ctx, const qz_srs* srs, const void* poly, size_t n, int on_device, const uint8_t* point,
+                  size_t n_point, uint8_t state[32], uint8_t out_evaluation[32], uint8_t out_s_comm[64],
+                  uint8_t out_openings[512]) {
+  if (!ctx || !srs || (n && !poly) || (n_point && !point) || !state || !out_evaluation || !out_s_comm || !out_openings)
+    return QZ_ERR_INVALID_ARG;
+  if (n_point >= (size_t)SC_MAX_VARS || n_point > 27) return ctx->fail(QZ_ERR_INVALID_ARG, "too many variables");
+  QZ_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->arena_reset();
+  cudaStream_t st = ctx->stream;
+  QZ_CUDA(ctx, cudaEventRecord(ctx->ev_call0, st));
+  QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k0, st));
+  QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k1, st));
+  const uint64_t pr_full = (uint64_t)1 << n_point;
+  uint8_t* res = (uint8_t*)ctx->arena_alloc(32 + 64 + 4 * 128 + 32 + 64);  // eval ‖ s_comm ‖ 4 x (x ‖ y ‖ proof) ‖ state ‖ r, r_inv
+  Fr* d_point = (Fr*)ctx->arena_alloc(32 * std::max<size_t>(n_point, 1));
+  uint4* d_pr = (uint4*)ctx->arena_alloc(32 * pr_full);
+  uint4* d_s = (uint4*)ctx->arena_alloc(32 * std::max<uint64_t>(std::max<uint64_t>(n, pr_full), 1));
+  if (!res || !d_point || !d_pr || !d_s) return ctx->fail(QZ_ERR_ALLOC, "mlpcs state");
+  uint8_t* d_eval = res;
+  uint8_t* d_scomm = res + 32;
+  uint8_t* d_open = res + 96;
+  uint8_t* d_state = res + 96 + 512;
+  Fr* d_r = (Fr*)(res + 96 + 512 + 32);
+  QZ_CUDA(ctx, cudaMemsetAsync(res, 0, 96 + 512 + 32 + 64, st));
+  QZ_CUDA(ctx, cudaMemcpyAsync(d_state, state, 32, cudaMemcpyHostToDevice, st));
+  const uint4* pdev = nullptr;
+  int rc = mlpcs_poly_on_device(ctx, poly, n, on_device, &pdev);
+  if (rc) return rc;
+  uint64_t s_commit_len = 0;
+  rc = mlpcs_begin_device(ctx, srs, pdev, n, point, n_point, d_point, d_pr, d_s, d_eval, d_scomm, &s_commit_len);
+  if (rc) return rc;
+  QZ_LAUNCH(ctx, mlpcs_transcript, 1, 1, 0, d_state, d_point, (int)n_point, (const Fr*)d_eval, d_scomm, d_r);
+  rc = mlpcs_finish_device(ctx, srs, pdev, n, d_s, s_commit_len, d_r, d_open);
+  if (rc) return rc;
   uint8_t* pin = (uint8_t*)ctx->pinned_buf(96 + 512 + 32);
   if (!pin) return ctx->fail(QZ_ERR_ALLOC, "pinned");
   QZ_CUDA(ctx, cudaMemcpyAsync(pin, res, 96 + 512 + 32, cudaMemcpyDeviceToHost, st));
@@ -389,6 +412,69 @@ int qz_mlpcs_open(qz_ctx* ctx, const qz_srs* srs, const void* poly, size_t n, in
   memcpy(state, pin + 96 + 512, 32);
   cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev_call0, ctx->ev_call1);
   cudaEventElapsedTime(&ctx->last_ms[1], ctx->ev_k0, ctx->ev_k1);
+  return QZ_OK;
+}
+
+int qz_mlpcs_open_begin(qz_ctx* ctx, const qz_srs* srs, const void* poly, size_t n, int on_device, const uint8_t* point,
+                        size_t n_point, uint8_t out_evaluation[32], uint8_t out_s_comm[64], void** out_s_dev,
+                        size_t* out_s_len) {
+  if (!ctx || !srs || (n && !poly) || (n_point && !point) || !out_evaluation || !out_s_comm || !out_s_dev || !out_s_len)
+    return QZ_ERR_INVALID_ARG;
+  if (n_point >= (size_t)SC_MAX_VARS || n_point > 27) return ctx->fail(QZ_ERR_INVALID_ARG, "too many variables");
+  QZ_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->arena_reset();
+  cudaStream_t st = ctx->stream;
+  const uint64_t pr_full = (uint64_t)1 << n_point;
+  uint8_t* res = (uint8_t*)ctx->arena_alloc(96);
+  Fr* d_point = (Fr*)ctx->arena_alloc(32 * std::max<size_t>(n_point, 1));
+  uint4* d_pr = (uint4*)ctx->arena_alloc(32 * pr_full);
+  if (!res || !d_point || !d_pr) return ctx->fail(QZ_ERR_ALLOC, "mlpcs state");
+  void* s_dev = nullptr;  // outlives the call: owned by the caller (qz_dev_free)
+  cudaError_t e = cudaMalloc(&s_dev, 32 * std::max<uint64_t>(std::max<uint64_t>(n, pr_full), 1));
+  if (e != cudaSuccess) return ctx->fail(QZ_ERR_ALLOC, "S polynomial", e);
+  QZ_CUDA(ctx, cudaMemsetAsync(res, 0, 96, st));
+  const uint4* pdev = nullptr;
+  int rc = mlpcs_poly_on_device(ctx, poly, n, on_device, &pdev);
+  uint64_t s_commit_len = 0;
+  if (!rc) rc = mlpcs_begin_device(ctx, srs, pdev, n, point, n_point, d_point, d_pr, (uint4*)s_dev, res, res + 32, &s_commit_len);
+  uint8_t* pin = rc ? nullptr : (uint8_t*)ctx->pinned_buf(96);
+  if (!rc && !pin) rc = ctx->fail(QZ_ERR_ALLOC, "pinned");
+  if (rc) {
+    cudaStreamSynchronize(st);
+    cudaFree(s_dev);
+    return rc;
+  }
+  QZ_CUDA(ctx, cudaMemcpyAsync(pin, res, 96, cudaMemcpyDeviceToHost, st));
+  QZ_CUDA(ctx, cudaStreamSynchronize(st));
+  memcpy(out_evaluation, pin, 32);
+  memcpy(out_s_comm, pin + 32, 64);
+  *out_s_dev = s_dev;
+  *out_s_len = (size_t)s_commit_len;
+  return QZ_OK;
+}
+
+int qz_mlpcs_open_finish(qz_ctx* ctx, const qz_srs* srs, const void* poly, size_t n, int on_device, const void* s_dev,
+                         size_t s_len, const uint8_t r[32], uint8_t out_openings[512]) {
+  if (!ctx || !srs || (n && !poly) || (s_len && !s_dev) || !r || !out_openings) return QZ_ERR_INVALID_ARG;
+  QZ_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->arena_reset();
+  cudaStream_t st = ctx->stream;
+  uint8_t* d_open = (uint8_t*)ctx->arena_alloc(512);
+  Fr* d_r = (Fr*)ctx->arena_alloc(64);
+  if (!d_open || !d_r) return ctx->fail(QZ_ERR_ALLOC, "mlpcs state");
+  QZ_CUDA(ctx, cudaMemsetAsync(d_open, 0, 512, st));
+  QZ_CUDA(ctx, cudaMemcpyAsync(d_r, r, 32, cudaMemcpyHostToDevice, st));
+  QZ_LAUNCH(ctx, fr_with_inverse, 1, 1, 0, d_r);  // mlpcs.rs:107
+  const uint4* pdev = nullptr;
+  int rc = mlpcs_poly_on_device(ctx, poly, n, on_device, &pdev);
+  if (rc) return rc;
+  rc = mlpcs_finish_device(ctx, srs, pdev, n, (const uint4*)s_dev, s_len, d_r, d_open);
+  if (rc) return rc;
+  uint8_t* pin = (uint8_t*)ctx->pinned_buf(512);
+  if (!pin) return ctx->fail(QZ_ERR_ALLOC, "pinned");
+  QZ_CUDA(ctx, cudaMemcpyAsync(pin, d_open, 512, cudaMemcpyDeviceToHost, st));
+  QZ_CUDA(ctx, cudaStreamSynchronize(st));
+  memcpy(out_openings, pin, 512);
   return QZ_OK;
 }
 

@@ -63,6 +63,76 @@ def Sub(a: VirtualPolyExpr, b: VirtualPolyExpr) -> VirtualPolyExpr:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+class OpeningBatch:
+    """A run of consecutive `MultilinearPCS::open` calls with no other transcript traffic between them (the two logup
+    openings of multiset_check.rs:167-170 followed by the num_cols + num_public + 3 openings of proof.rs:202-226).
+
+    One GPU: each opening is the fused qz_mlpcs_open, in order.  Several ranks (last row; every rank holds the
+    same polynomials and runs the same transcript): an opening's evaluation, S polynomial and S commitment do not depend
+    on the transcript, only its four KZG openings need the challenge r -- so the openings are dealt to the ranks, which
+    run the first halves, all-gather (evaluation, S commitment), replay the transcript schedule of mlpcs.rs:100-105 for
+    every opening in order, run the second halves of their own openings and all-gather the results.  Every rank ends
+    with the complete, byte-identical proof."""
+
+    def __init__(self, ctx: Context, pcs: KZG, transcript: Transcript):
+        self.ctx, self.pcs, self.transcript = ctx, pcs, transcript
+        self.items, self.after = [], []
+
+    def add(self, poly, point: np.ndarray, sink) -> None:
+        """queue open(poly, point); `sink(MLEvalProof)` receives the result when the batch runs"""
+        self.items.append((poly, np.ascontiguousarray(point, dtype=np.uint8).reshape(-1, 32), sink))
+
+    def on_done(self, fn) -> None:
+        self.after.append(fn)
+
+    @staticmethod
+    def _length(poly) -> int:
+        return poly.nbytes // 32
+
+    def owners(self, nranks: int) -> List[int]:
+        """longest first onto the least loaded rank (an opening costs about 5 MSMs of its length); ties by index / rank"""
+        load, owner = [0] * nranks, [0] * len(self.items)
+        for i in sorted(range(len(self.items)), key=lambda j: (-self._length(self.items[j][0]), j)):
+            r = min(range(nranks), key=lambda k: (load[k], k))
+            owner[i] = r
+            load[r] += max(self._length(self.items[i][0]), 1)
+        return owner
+
+    def run(self) -> None:
+        ctx, pcs, tr = self.ctx, self.pcs, self.transcript
+        nranks, rank = getattr(ctx, "nranks", 1), getattr(ctx, "rank", 0)
+        if nranks == 1:
+            for poly, point, sink in self.items:
+                sink(pcs.open_multilinear(poly, point, tr))
+        else:
+            B, owner = len(self.items), self.owners(nranks)
+            pending, head = {}, np.zeros((B, 96), dtype=np.uint8)
+            for i, (poly, point, _) in enumerate(self.items):
+                if owner[i] == rank:
+                    pending[i] = pcs.open_multilinear_begin(poly, point)
+                    head[i, :32], head[i, 32:] = pending[i].evaluation, pending[i].s_comm
+            heads = ctx.allgather(head).reshape(nranks, B, 96)
+            tails = np.zeros((B, 512), dtype=np.uint8)
+            for i, (poly, point, _) in enumerate(self.items):  # mlpcs.rs:100-105, every rank, in order
+                ev, sc = heads[owner[i], i, :32], heads[owner[i], i, 32:]
+                tr.append_fr_vec(point)
+                tr.append_fr(ev)
+                tr.append_g1(sc)
+                r = tr.draw_field_element()
+                if owner[i] == rank:
+                    pf = pcs.open_multilinear_finish(pending[i], r)
+                    tails[i] = np.concatenate([np.concatenate([o.x, o.y, o.proof]) for o in
+                                               (pf.poly_opening, pf.poly_opening_inv, pf.s_opening, pf.s_opening_inv)])
+            all_tails = ctx.allgather(tails).reshape(nranks, B, 4, 128)
+            for i, (poly, point, sink) in enumerate(self.items):
+                h = heads[owner[i], i]
+                sink(MLEvalProof.from_parts(point.copy(), h[:32].copy(), h[32:].copy(), all_tails[owner[i], i]))
+        for fn in self.after:
+            fn()
+        self.items, self.after = [], []
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 @dataclass
 class MultisetEqualityProof:
     """multiset_check.rs:17-24"""
@@ -74,8 +144,10 @@ class MultisetEqualityProof:
 
     @staticmethod
     def prove(ctx: Context, store: VirtualPolynomialStore, h_left: int, h_right: int, transcript: Transcript, pcs: KZG,
-              multiplicities: Optional[int] = None) -> Tuple["MultisetEqualityProof", np.ndarray]:
-        """multiset_check.rs:28-182.  multiplicities=None is LookupMode::Equality, else Subset."""
+              multiplicities: Optional[int] = None, batch: Optional[OpeningBatch] = None
+              ) -> Tuple["MultisetEqualityProof", np.ndarray]:
+        """multiset_check.rs:28-182.  multiplicities=None is LookupMode::Equality, else Subset.  With `batch` the two
+        openings are queued on it (the caller runs the batch; nothing else may touch the transcript before that)."""
         num_vars = store.num_vars
         on_dev = bool(store.polynomials) and isinstance(store.polynomials[0], DeviceBuffer)  # keep new tables where the store lives
         gamma = transcript.draw_field_element()  # :40
@@ -104,12 +176,17 @@ class MultisetEqualityProof:
         store.sub_in_place(h_hat, dr, fr_mont(FR - 1))
         sc, claim = SumcheckProof.prove(ctx, num_vars, store, h_hat, fr_mont(0), transcript)  # :162-163
         point = claim.point
-        o_left = pcs.open_multilinear(left, point, transcript)  # :167-170
-        o_right = pcs.open_multilinear(right, point, transcript)
+        proof = MultisetEqualityProof(c_left, c_right, sc, None, None)
+        own_batch = batch is None
+        if own_batch:
+            batch = OpeningBatch(ctx, pcs, transcript)
+        batch.add(left, point, lambda o: setattr(proof, "opening_proof_denom_left", o))  # :167-170
+        batch.add(right, point, lambda o: setattr(proof, "opening_proof_denom_right", o))
         if on_dev:
-            for b in (left, right, eq_tab):
-                b.free()
-        return MultisetEqualityProof(c_left, c_right, sc, o_left, o_right), point
+            batch.on_done(lambda: [b.free() for b in (left, right, eq_tab)])
+        if own_batch:
+            batch.run()
+        return proof, point
 
 
 @dataclass
@@ -119,7 +196,7 @@ class PermutationCheckProof:
 
     @staticmethod
     def prove(ctx: Context, store: VirtualPolynomialStore, h_left: int, h_right: int, id_indices: np.ndarray,
-              permutation_indices: np.ndarray, transcript: Transcript, pcs: KZG):
+              permutation_indices: np.ndarray, transcript: Transcript, pcs: KZG, batch: Optional[OpeningBatch] = None):
         """permutation_check.rs:13-58"""
         assert id_indices.nbytes == 32 << store.num_vars and permutation_indices.nbytes == 32 << store.num_vars
         id_ref = store.allocate_polynomial(id_indices)  # :27-28
@@ -131,7 +208,7 @@ class PermutationCheckProof:
         hr = store.new_virtual_from_virtual(h_right)  # :38-40
         store.mul_const_in_place(hr, alpha)
         store.add_in_place(hr, perm_ref)
-        proof, point = MultisetEqualityProof.prove(ctx, store, hl, hr, transcript, pcs)  # :42-50
+        proof, point = MultisetEqualityProof.prove(ctx, store, hl, hr, transcript, pcs, batch=batch)  # :42-50
         return PermutationCheckProof(proof), point
 
 
@@ -278,21 +355,27 @@ class HyperPlonk:
         store2 = VirtualPolynomialStore(log2_rows + log2_cols)  # :184-196
         w_idx = store2.allocate_polynomial(full_witness)
         w_virtual = store2.new_virtual_from_input(w_idx)
+        # every opening of the trace forms one run in the transcript: queue them, then run the batch (split over the
+        # ranks when there are several)
+        batch = OpeningBatch(ctx, pcs, transcript)
         perm_proof, perm_point = PermutationCheckProof.prove(ctx, store2, w_virtual, w_virtual, pk.id_poly,
-                                                             pk.permutation_poly, transcript, pcs)
-        openings_zc = []  # :202-210: column bits appended as the HIGH variables of the column-major witness
+                                                             pk.permutation_poly, transcript, pcs, batch=batch)
+        openings_zc = [None] * circuit.num_cols()  # :202-210: column bits appended as the HIGH variables of the witness
         for col in range(circuit.num_cols()):
             bits = fr_table([(col >> i) & 1 for i in range(log2_cols)])
             point = np.concatenate([zc_claim.point, bits.reshape(-1, 32)]) if log2_cols else zc_claim.point
-            openings_zc.append(pcs.open_multilinear(full_witness, point, transcript))
-        openings_pub = [pcs.open_multilinear(public[i], zc_claim.point, transcript)  # :214-219 (un-padded columns)
-                        for i in range(circuit.num_public_columns())]
-        o_id = pcs.open_multilinear(pk.id_poly, perm_point, transcript)  # :222-226
-        o_perm = pcs.open_multilinear(pk.permutation_poly, perm_point, transcript)
-        o_trace = pcs.open_multilinear(full_witness, perm_point, transcript)
+            batch.add(full_witness, point, lambda o, col=col: openings_zc.__setitem__(col, o))
+        openings_pub = [None] * circuit.num_public_columns()  # :214-219 (un-padded columns)
+        for i in range(circuit.num_public_columns()):
+            batch.add(public[i], zc_claim.point, lambda o, i=i: openings_pub.__setitem__(i, o))
+        tail = {}
+        batch.add(pk.id_poly, perm_point, lambda o: tail.__setitem__("id", o))  # :222-226
+        batch.add(pk.permutation_poly, perm_point, lambda o: tail.__setitem__("perm", o))
+        batch.add(full_witness, perm_point, lambda o: tail.__setitem__("trace", o))
+        batch.run()
         for p in public:
             p.free()
-        return TraceProof(zero_check_proof, perm_proof, openings_zc, openings_pub, o_id, o_perm, o_trace)
+        return TraceProof(zero_check_proof, perm_proof, openings_zc, openings_pub, tail["id"], tail["perm"], tail["trace"])
 
     def prove(self, pcs: KZG, witness_traces: List[List[np.ndarray]]) -> HyperPlonkProof:
         """proof.rs:239-301.  witness_traces[t][c] is column c of trace t as a (rows, 32) Montgomery array."""

@@ -104,3 +104,25 @@ def test_mlpcs_degree_error(ctx):
     with pytest.raises(AssertionError):
         small.open_multilinear(util.rand_fr(32, 1), util.rand_fr(5, 2), q.Transcript(b"x", ctx))
     small.srs.free()
+
+
+@pytest.mark.parametrize("n,nv", [(5, 5), (12, 12), (5, 3), (3, 5), (0, 0)])
+def test_split_open_equals_fused(ctx, kzg, n, nv):
+    """qz_mlpcs_open_begin + the caller's transcript schedule (mlpcs.rs:100-105) + qz_mlpcs_open_finish is the fused
+    qz_mlpcs_open: the split that lets independent openings be spread over GPUs"""
+    poly = util.rand_fr(1 << n, 300 + n)
+    point = util.rand_fr(nv, 400 + nv)
+    tr1 = q.Transcript(b"split", ctx)
+    fused = kzg.open_multilinear(poly, point, tr1)
+    tr2 = q.Transcript(b"split", ctx)
+    pend = kzg.open_multilinear_begin(poly, point)
+    tr2.append_fr_vec(point)
+    tr2.append_fr(pend.evaluation)
+    tr2.append_g1(pend.s_comm)
+    r = tr2.draw_field_element()
+    split = kzg.open_multilinear_finish(pend, r)
+    assert tr1.state.tobytes() == tr2.state.tobytes()
+    assert np.array_equal(fused.evaluation, split.evaluation) and np.array_equal(fused.s_comm, split.s_comm)
+    for a, b in zip((fused.poly_opening, fused.poly_opening_inv, fused.s_opening, fused.s_opening_inv),
+                    (split.poly_opening, split.poly_opening_inv, split.s_opening, split.s_opening_inv)):
+        assert np.array_equal(a.x, b.x) and np.array_equal(a.y, b.y) and np.array_equal(a.proof, b.proof)

@@ -105,6 +105,42 @@ def _worker(rank, world, port, ret):
                 ev = py.expr_eval_point(h, [g[0] for g in gs])
                 break
         assert (polys, point, ev) == want
+
+        # ---- MLPCS openings dealt to the ranks (hyperplonk.OpeningBatch): the halves before / after the challenge ----
+        from quill_zkvm_b200 import hyperplonk as hp
+        kz = py.KZG(16, gen, 4242)
+        polys_o = [[rnd.randrange(FR) for _ in range(1 << m)] for m in (4, 2, 4, 3, 4)]
+        points_o = [[rnd.randrange(FR) for _ in range(m)] for m in (4, 2, 4, 3, 3)]
+        seq_tr = py.Transcript(b"deal")
+        want_o = [py.mlpcs_open(kz, p, pt, seq_tr) for p, pt in zip(polys_o, points_o)]
+        batch = hp.OpeningBatch(None, None, None)
+        for p, pt in zip(polys_o, points_o):
+            batch.add(np.zeros((len(p), 32), np.uint8), np.zeros((len(pt), 32), np.uint8), None)
+        owner = batch.owners(world)
+        assert sorted(set(owner)) == list(range(world))
+        mine = {}
+        for i, (p, pt) in enumerate(zip(polys_o, points_o)):
+            if owner[i] == rank:  # first half: no transcript involved (mlpcs.rs:86-97)
+                pr = py.compute_pr(pt)
+                s_poly = py.compute_s_polynomial(list(p), pr)
+                mine[i] = (sum(a * b for a, b in zip(p, pr)) % FR, s_poly, kz.commit(s_poly))
+        heads = _gather_obj({i: (v[0], v[2]) for i, v in mine.items()}, world)
+        tr2, got_o = py.Transcript(b"deal"), {}
+        for i, (p, pt) in enumerate(zip(polys_o, points_o)):  # every rank replays the schedule of mlpcs.rs:100-105
+            ev_i, sc_i = heads[owner[i]][i]
+            tr2.append_fr_vec(pt)
+            tr2.append_fr(ev_i)
+            tr2.append_g1(sc_i)
+            r = tr2.draw_field_element()
+            if owner[i] == rank:  # second half: the four KZG openings at r and 1/r
+                r_inv = py.fr_inv(r)
+                got_o[i] = dict(evaluation_point=[x % FR for x in pt], evaluation=ev_i, s_comm=sc_i,
+                                poly_opening=kz.open(p, r), poly_opening_inv=kz.open(p, r_inv),
+                                s_opening=kz.open(mine[i][1], r), s_opening_inv=kz.open(mine[i][1], r_inv))
+        merged = {}
+        for d in _gather_obj(got_o, world):
+            merged.update(d)
+        assert [merged[i] for i in range(len(polys_o))] == want_o and tr2.state == seq_tr.state
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()
@@ -117,6 +153,19 @@ def test_sharding_world2_gloo():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+def test_opening_owners_balanced_and_deterministic():
+    from quill_zkvm_b200 import hyperplonk as hp
+    batch = hp.OpeningBatch(None, None, None)
+    sizes = [1 << 12, 1 << 12, 1 << 14, 1 << 14, 1 << 14, 1 << 14, 1 << 12, 1 << 12, 1 << 14, 1 << 14, 1 << 14]
+    for n in sizes:
+        batch.add(np.zeros((n, 32), np.uint8), np.zeros((3, 32), np.uint8), None)
+    for w in (1, 2, 4, 8):
+        owner = batch.owners(w)
+        assert owner == batch.owners(w) and set(owner) <= set(range(w))
+        load = [sum(s for s, o in zip(sizes, owner) if o == r) for r in range(w)]
+        assert max(load) - min(load) <= max(sizes)
 
 
 def test_shard_ranges_partition():

@@ -55,9 +55,32 @@ def main():
                 assert np.array_equal(sc.r_polys[j], o["coeffs"][j][: o["lens"][j]]), f"rank {rank} nv {nv} round {j}"
             assert np.array_equal(claim.point, o["point"]) and np.array_equal(claim.evaluation, o["evaluation"])
             assert tr.state.tobytes() == st.tobytes()
+    # ---- HyperPlonk: openings dealt to the ranks (hyperplonk.OpeningBatch), every rank ends with the whole proof ----
+    from oracle import fastkzg  # noqa: E402
+    from quill_zkvm_b200 import hyperplonk as hp  # noqa: E402
+    from tests.test_gpu_hyperplonk import to_product_circuit  # noqa: E402
+
+    c1, w1 = py.fibonacci_circuit_and_trace(64)
+    c2, w2 = py.modified_fibonacci_circuit_and_trace()
+    circuits, witnesses = [c1, c2], [w1, w2]
+    max_degree = max(c.num_cols() * c.num_rows for c in circuits)
+    fastkzg.install_fast_s_polynomial()
+    want = py.hyperplonk_prove(circuits, witnesses, fastkzg.FastKZG(max_degree, gen, tau))
+    kzg = q.KZG.trusted_setup(ctx, max_degree, co.g1_to_bytes(gen), co.fr1(tau))
+    prover = hp.HyperPlonk.preprocess(ctx, [to_product_circuit(c) for c in circuits], kzg)
+    got = util.hyperplonk_py(prover.prove(kzg, [[co.to_mont(col) for col in w] for w in witnesses]))
+    kzg.srs.free()
+    assert got["state_end"] == want["state_end"], f"rank {rank}: HyperPlonk transcript differs"
+    assert got["witness_commitment"] == want["witness_commitment"]
+    for g, w in zip(got["trace_proofs"], want["trace_proofs"]):
+        for key in ("openings_zero_check", "openings_public", "opening_id", "opening_permutation", "opening_permutation_trace"):
+            assert g[key] == w[key], f"rank {rank}: {key} differs"
+        for key in ("opening_proof_denom_left", "opening_proof_denom_right", "r_polys"):
+            assert g["permutation"][key] == w["permutation"][key], f"rank {rank}: permutation {key} differs"
     dist.barrier()
     if rank == 0:
-        print(f"multi-GPU parity ok on {world} ranks: sharded MSM and sumcheck match the oracle bit for bit")
+        print(f"multi-GPU parity ok on {world} ranks: sharded MSM, sharded sumcheck and the HyperPlonk proof with its "
+              f"openings dealt to the ranks match the oracle bit for bit")
     ctx.close()
     dist.destroy_process_group()
 
