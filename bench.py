@@ -334,31 +334,6 @@ def run_gpu(args):
     assert np.array_equal(results["dev"], results["host"]), "device-resident and host-input commitments differ"
     msm_c, msm_digits, msm_shared, msm_adds = (ctx.last_stat(i) for i in range(4))
 
-    # ---- config 4: multilinear PCS commit + open (MLEvalProof::prove: 5 MSMs + NTT), N = 1 only ----
-    mlpcs = None
-    if world == 1 and args.mlpcs_log_n > 0:
-        nm = min(args.mlpcs_log_n, args.log_n)
-        poly = ctx.random_fr(1 << nm, 777)
-        point = np.frombuffer(b"".join(((i * 0x9E3779B97F4A7C15 + 12345) % FR).to_bytes(32, "little") for i in range(nm)),
-                              dtype=np.uint8).reshape(nm, 32).copy()
-
-        def commit_open():
-            results["ml_c"] = kzg.commit(poly)
-            results["ml_o"] = kzg.open_multilinear(poly, point, q.Transcript(b"mlpcs_bench", ctx))
-
-        ml_ms, ml_launches = timed_loop(commit_open, max(1, args.steps // 2), 1)
-        mlpcs = {"value": ml_ms * 1e-3, "unit": "s per commit+open", "log_n": nm, "gpu_launches": ml_launches // max(1, args.steps // 2),
-                 "workload": f"MultilinearPCS::commit + ::open of a 2^{nm}-entry MLE (6 MSMs, eq table, NTT 2^{nm + 1}, 4 quotients)"}
-        poly.free()
-
-    # ---- config 5: HyperPlonk prove of two transition-circuit traces (Fibonacci + modified Fibonacci); with N > 1 every
-    # rank holds the traces and the full SRS and the MLPCS openings (5 MSMs each) are dealt to the ranks ----
-    hplonk = None
-    if args.hyperplonk_log_rows > 0:
-        hplonk = bench_hyperplonk(ctx, q, args.hyperplonk_log_rows, np.concatenate([mont(1, FQ), mont(2, FQ)]), mont(TAU),
-                                  timed_loop)
-        hplonk["n_gpus"] = world
-
     # ---- sumcheck: three 2^log_n tables, degree-3 product ----
     nv = args.log_n
     slo, shi = parallel.table_shard_range(nv, rank, world)
@@ -390,6 +365,34 @@ def run_gpu(args):
     sc_e2e_ms, _ = timed_loop(lambda: prove(st_host, "host"), args.steps, args.warmup)
     assert sc_out["dev_state"].tobytes() == sc_out["host_state"].tobytes()
     clocks = sampler.stop() if rank == 0 else None
+
+    # (the nvidia-smi sampler is stopped first: its 200 ms polling contends for the driver and slows these
+    # launch- and allocation-heavy legs several times over; the headline legs above are one call per step)
+    # ---- config 4: multilinear PCS commit + open (MLEvalProof::prove: 5 MSMs + NTT), N = 1 only ----
+    mlpcs = None
+    if world == 1 and args.mlpcs_log_n > 0:
+        nm = min(args.mlpcs_log_n, args.log_n)
+        poly = ctx.random_fr(1 << nm, 777)
+        point = np.frombuffer(b"".join(((i * 0x9E3779B97F4A7C15 + 12345) % FR).to_bytes(32, "little") for i in range(nm)),
+                              dtype=np.uint8).reshape(nm, 32).copy()
+
+        def commit_open():
+            results["ml_c"] = kzg.commit(poly)
+            results["ml_o"] = kzg.open_multilinear(poly, point, q.Transcript(b"mlpcs_bench", ctx))
+
+        ml_ms, ml_launches = timed_loop(commit_open, max(1, args.steps // 2), 1)
+        mlpcs = {"value": ml_ms * 1e-3, "unit": "s per commit+open", "log_n": nm, "gpu_launches": ml_launches // max(1, args.steps // 2),
+                 "workload": f"MultilinearPCS::commit + ::open of a 2^{nm}-entry MLE (6 MSMs, eq table, NTT 2^{nm + 1}, 4 quotients)"}
+        poly.free()
+
+    # ---- config 5: HyperPlonk prove of two transition-circuit traces (Fibonacci + modified Fibonacci); with N > 1 every
+    # rank holds the traces and the full SRS and the MLPCS openings (5 MSMs each) are dealt to the ranks ----
+    hplonk = None
+    if args.hyperplonk_log_rows > 0:
+        hplonk = bench_hyperplonk(ctx, q, args.hyperplonk_log_rows, np.concatenate([mont(1, FQ), mont(2, FQ)]), mont(TAU),
+                                  timed_loop)
+        hplonk["n_gpus"] = world
+
 
     # ---- roofline denominators ----
     imad_peak = ctx.bench_imad(0)  # 32x32->64 multiply-accumulates per second (IMAD.WIDE carry chains), measured now
@@ -463,7 +466,7 @@ def main():
     ap.add_argument("--ref-log-n", type=int, default=18, help="--impl reference: MSM sample size per step")
     ap.add_argument("--ref-sc-log-n", type=int, default=20, help="--impl reference: sumcheck sample size per step")
     ap.add_argument("--mlpcs-log-n", type=int, default=22, help="config 4: MLPCS commit+open size (0 = skip)")
-    ap.add_argument("--hyperplonk-log-rows", type=int, default=14,
+    ap.add_argument("--hyperplonk-log-rows", type=int, default=20,
                     help="config 5: rows per trace of the two-trace HyperPlonk proof (0 = skip; BASELINE names 20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-precompute", action="store_true", help="MSM without the precomputed window multiples")

@@ -32,7 +32,7 @@ KEEP = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dra
         "sm__inst_executed.avg.per_cycle_active", "sm__issue_active.avg.pct_of_peak_sustained_elapsed",
         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
-        "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct", "lts__t_sector_hit_rate.pct", "sm__cycles_elapsed.avg",
         "smsp__cycles_active.avg", "dram__throughput.avg.pct_of_peak_sustained_elapsed"]
 
@@ -51,9 +51,11 @@ def full(rep, out, title):
 
 
 if __name__ == "__main__":
-    launches("gpurun_out/launches2.csv", f"profiles/{TAG}_launches_summary.txt",
+    import shutil
+    shutil.copyfile("gpurun_out/launches.csv", f"profiles/{TAG}_launches_bench_steps2.csv")
+    launches("gpurun_out/launches.csv", f"profiles/{TAG}_launches_summary.txt",
              f"{TAG}: ncu --metrics gpu__time_duration.sum --clock-control none -c 700 python bench.py --steps 2 --warmup 1 "
-             "--no-cpu-baseline --mlpcs-log-n 0   (6 MSMs of 2^24 with precomputed windows + 6 sumcheck proofs of 3 x 2^24 + setup)")
+             "--no-cpu-baseline --mlpcs-log-n 0 --hyperplonk-log-rows 0   (6 MSMs of 2^24 with precomputed windows + 6 sumcheck proofs of 3 x 2^24 + setup)")
     full("gpurun_out/prof_r1_msm.ncu-rep", f"profiles/{TAG}_ncu_msm_accumulate.txt",
          f"{TAG}: ncu --set full --clock-control none -k regex:msm_accumulate -c 1 python tools/profile_one.py msm 24 pre  (2^24 points, c = 22, 12 mixed additions per point)")
     full("gpurun_out/prof_r1_sc.ncu-rep", f"profiles/{TAG}_ncu_sc_round_prod.txt",
