@@ -412,6 +412,8 @@ def run_gpu(args):
             "config": {"workload": f"KZG commit MSM of 2^{args.log_n} random Fr scalars on a tau-power SRS + linear-time "
                                    f"sumcheck over a degree-3 product of three 2^{args.log_n}-entry tables (BN254)",
                        "log_n": args.log_n, "msm_precomputed_windows": not args.no_precompute, "sharding": f"index ranges / top variables over {world} GPU(s)",
+                       "exchange": ("peer mailboxes in HBM over NVLink (CUDA IPC), written by the producing kernel" if ctx.peer_memory
+                                    else "NCCL all-gather") if world > 1 else "none",
                        "l2": "inputs (>= 1.5 GiB) exceed the 126 MB L2; no flush needed"},
             "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "points/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": n_loc * 32 * world, "d2h_bytes_per_step": 64 * world},

@@ -178,6 +178,11 @@ int qz_eq_table(qz_ctx* ctx, size_t n, const uint8_t* point, void* out, int out_
  * broadcast by the caller (torch.distributed, MPI, a file...). */
 int qz_comm_unique_id(uint8_t out_id[128]);
 int qz_comm_init(qz_ctx* ctx, const uint8_t unique_id[128], int rank, int nranks);
+/* 1 when qz_comm_init mapped every peer's mailbox into this process (CUDA IPC over NVLink / NVSwitch): the per-round
+ * sumcheck exchange and the MSM partial-sum exchange are then stores into the peers' HBM issued by the kernel that
+ * produced the value, with no collective launch in between.  0: the exchanges are NCCL all-gathers (peer access
+ * unavailable, or QZ_NO_P2P=1 in the environment at qz_comm_init).  The results are identical either way. */
+int qz_comm_peer_memory(const qz_ctx* ctx);
 /* Sharded MSM: this rank holds SRS points [first, first+len) and the matching scalars; every rank receives the full
  * commitment (partial sums are gathered as raw limbs and added with the group law, never ncclSum). */
 int qz_msm_sharded(qz_ctx* ctx, const qz_srs* srs_shard, const void* scalars_shard, size_t n_scalars,

@@ -114,6 +114,11 @@ class Context:
         self.check(self.lib.qz_comm_init(self.h, _ptr(_u8(unique_id)), rank, nranks))
         self.rank, self.nranks = rank, nranks
 
+    @property
+    def peer_memory(self) -> bool:
+        """True when the ranks exchange through mailboxes in each other's HBM (CUDA IPC) instead of NCCL all-gathers."""
+        return bool(self.lib.qz_comm_peer_memory(self.h))
+
     def allgather(self, mine: np.ndarray) -> np.ndarray:
         """All-gather a small uint8 array over the library's communicator -> (nranks, len)."""
         mine = _u8(mine).reshape(-1)

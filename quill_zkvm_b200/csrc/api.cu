@@ -234,6 +234,7 @@ void qz_ctx_destroy(qz_ctx* c) {
   cudaEventDestroy(c->ev_call1);
   cudaEventDestroy(c->ev_k0);
   cudaEventDestroy(c->ev_k1);
+  c->destroy_prep_stream();
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }

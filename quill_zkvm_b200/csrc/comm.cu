@@ -8,6 +8,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <vector>
+#include "comm.cuh"
 #include "ctx.cuh"
 #include "msm.cuh"
 
@@ -71,7 +73,84 @@ int comm_allgather(qz_ctx* ctx, const void* send, void* recv, size_t bytes) {
   return QZ_OK;
 }
 
+static void peers_close(qz_ctx* ctx) {
+  for (int g = 0; g < QZ_MAX_PEERS; g++) {
+    if (ctx->peer_mbox_host[g] && g != ctx->rank) cudaIpcCloseMemHandle(ctx->peer_mbox_host[g]);
+    ctx->peer_mbox_host[g] = nullptr;
+  }
+  if (ctx->peer_mbox_dev) cudaFree(ctx->peer_mbox_dev);
+  if (ctx->mbox) cudaFree(ctx->mbox);
+  ctx->peer_mbox_dev = nullptr;
+  ctx->mbox = nullptr;
+  cudaGetLastError();
+}
+
+// Map every rank's mailbox into this process (CUDA IPC over the NVLink / NVSwitch peer path).  The 64-byte IPC handles
+// travel through the communicator that was just created.  Every rank takes the same decision: a second all-gather
+// carries each rank's "all peers opened" bit, and the mailboxes are used only if it is set everywhere; otherwise
+// (restricted CUDA_VISIBLE_DEVICES, no peer access, QZ_NO_P2P=1) the exchanges stay on NCCL all-gathers.
+static int peers_setup(qz_ctx* ctx) {
+  const int G = ctx->nranks;
+  if (G > QZ_MAX_PEERS) return QZ_OK;
+  cudaStream_t st = ctx->stream;
+  uint8_t* xchg = nullptr;  // [G] handles, then [G] status bytes
+  QZ_CUDA(ctx, cudaMalloc((void**)&xchg, (size_t)(64 + 64) * G + 128));
+  uint8_t* d_mine = xchg + (size_t)128 * G;
+  int ok = getenv("QZ_NO_P2P") ? 0 : 1;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof mine);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (ok) {
+    if (cudaMalloc(&ctx->mbox, sizeof(PeerMailbox)) != cudaSuccess ||
+        cudaMemset(ctx->mbox, 0, sizeof(PeerMailbox)) != cudaSuccess ||
+        cudaIpcGetMemHandle(&mine, ctx->mbox) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0;
+    }
+  }
+  std::vector<uint8_t> all((size_t)64 * G);
+  QZ_CUDA(ctx, cudaMemcpyAsync(d_mine, &mine, 64, cudaMemcpyHostToDevice, st));
+  int rc = comm_allgather(ctx, d_mine, xchg, 64);
+  if (rc) return rc;
+  QZ_CUDA(ctx, cudaMemcpyAsync(all.data(), xchg, (size_t)64 * G, cudaMemcpyDeviceToHost, st));
+  QZ_CUDA(ctx, cudaStreamSynchronize(st));
+  for (int g = 0; g < G && ok; g++) {
+    if (g == ctx->rank) {
+      ctx->peer_mbox_host[g] = ctx->mbox;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, all.data() + (size_t)64 * g, 64);
+    bool zero = true;
+    for (int i = 0; i < 64; i++) zero = zero && all[(size_t)64 * g + i] == 0;
+    if (zero || cudaIpcOpenMemHandle(&ctx->peer_mbox_host[g], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ctx->peer_mbox_host[g] = nullptr;
+      ok = 0;
+    }
+  }
+  // agree: everyone must have opened everything
+  uint8_t flag = (uint8_t)ok;
+  std::vector<uint8_t> flags(G);
+  QZ_CUDA(ctx, cudaMemcpyAsync(d_mine, &flag, 1, cudaMemcpyHostToDevice, st));
+  rc = comm_allgather(ctx, d_mine, xchg, 1);
+  if (rc) return rc;
+  QZ_CUDA(ctx, cudaMemcpyAsync(flags.data(), xchg, G, cudaMemcpyDeviceToHost, st));
+  QZ_CUDA(ctx, cudaStreamSynchronize(st));
+  for (int g = 0; g < G; g++) ok = ok && flags[g];
+  cudaFree(xchg);
+  if (!ok) {
+    peers_close(ctx);
+    return QZ_OK;
+  }
+  QZ_CUDA(ctx, cudaMalloc((void**)&ctx->peer_mbox_dev, sizeof(void*) * QZ_MAX_PEERS));
+  QZ_CUDA(ctx, cudaMemcpy(ctx->peer_mbox_dev, ctx->peer_mbox_host, sizeof(void*) * QZ_MAX_PEERS, cudaMemcpyHostToDevice));
+  ctx->mbox_seq = 0;
+  return QZ_OK;
+}
+
 void comm_destroy(qz_ctx* ctx) {
+  peers_close(ctx);
   if (ctx->comm && nccl().CommDestroy) nccl().CommDestroy(ctx->comm);
   ctx->comm = nullptr;
 }
@@ -105,8 +184,10 @@ int qz_comm_init(qz_ctx* ctx, const uint8_t unique_id[128], int rank, int nranks
   memcpy(id.internal, unique_id, 128);
   ncclResultT r = api.CommInitRank(&ctx->comm, nranks, id, rank);
   if (r != 0) return ctx->fail(QZ_ERR_NCCL, api.GetErrorString ? api.GetErrorString(r) : "ncclCommInitRank failed");
-  return QZ_OK;
+  return peers_setup(ctx);
 }
+
+int qz_comm_peer_memory(const qz_ctx* ctx) { return ctx && comm_has_peers(ctx) ? 1 : 0; }
 
 int qz_msm_sharded(qz_ctx* ctx, const qz_srs* srs, const void* scalars, size_t n_scalars, int on_device,
                    uint8_t out_xy[64]) {
@@ -118,18 +199,18 @@ int qz_msm_sharded(qz_ctx* ctx, const qz_srs* srs, const void* scalars, size_t n
   QZ_CUDA(ctx, cudaEventRecord(ctx->ev_call0, st));
   QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k0, st));
   QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k1, st));
-  const uint4* sdev = (const uint4*)scalars;
+  uint4* sdev = (uint4*)scalars;
+  const void* shost = nullptr;
   if (!on_device && n) {
-    void* p = ctx->arena_alloc(32 * n);
-    if (!p) return ctx->fail(QZ_ERR_ALLOC, "scalars");
-    QZ_CUDA(ctx, cudaMemcpyAsync(p, scalars, 32 * n, cudaMemcpyHostToDevice, st));
-    sdev = (const uint4*)p;
+    sdev = (uint4*)ctx->arena_alloc(32 * n);
+    if (!sdev) return ctx->fail(QZ_ERR_ALLOC, "scalars");
+    shost = scalars;
   }
   uint8_t* mine = (uint8_t*)ctx->arena_alloc(128);
   uint8_t* all = (uint8_t*)ctx->arena_alloc((size_t)128 * ctx->nranks);
   uint8_t* out_dev = (uint8_t*)ctx->arena_alloc(64);
   if (!mine || !all || !out_dev) return ctx->fail(QZ_ERR_ALLOC, "result");
-  int rc = msm_device(ctx, srs, sdev, n, mine, nullptr);
+  int rc = msm_run(ctx, srs, sdev, shost, n, mine, nullptr);
   if (rc) return rc;
   rc = comm_allgather(ctx, mine, all, 128);
   if (rc) return rc;
@@ -139,7 +220,7 @@ int qz_msm_sharded(qz_ctx* ctx, const qz_srs* srs, const void* scalars, size_t n
   QZ_CUDA(ctx, cudaEventRecord(ctx->ev_call1, st));
   QZ_CUDA(ctx, cudaStreamSynchronize(st));
   cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev_call0, ctx->ev_call1);
-  cudaEventElapsedTime(&ctx->last_ms[1], ctx->ev_k0, ctx->ev_k1);
+  ctx->last_ms[1] = msm_accumulate_ms(ctx);
   return QZ_OK;
 }
 

@@ -29,6 +29,35 @@ struct qz_ctx {
   std::map<int, void*> cache;
 
   cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+
+  // streamed MSM (msm.cu): the scalars' host->device copy, digit extraction and sort of segment s+1 run on `prep_stream`
+  // while `stream` accumulates segment s.  Created on first use, destroyed with the context.
+  static constexpr int MAX_SEGMENTS = 8;
+  cudaStream_t prep_stream = nullptr;
+  cudaEvent_t ev_entry = nullptr, ev_seg_ready[MAX_SEGMENTS] = {}, ev_acc0[MAX_SEGMENTS] = {}, ev_acc1[MAX_SEGMENTS] = {};
+  int acc_launches = 0;  // accumulate launches of the last MSM whose durations ev_acc0/1 bracket (0: ev_k0/ev_k1 do)
+  int ensure_prep_stream() {
+    if (prep_stream) return 0;
+    if (cudaStreamCreateWithFlags(&prep_stream, cudaStreamNonBlocking) != cudaSuccess) return 1;
+    if (cudaEventCreateWithFlags(&ev_entry, cudaEventDisableTiming) != cudaSuccess) return 1;
+    for (int i = 0; i < MAX_SEGMENTS; i++) {
+      if (cudaEventCreateWithFlags(&ev_seg_ready[i], cudaEventDisableTiming) != cudaSuccess) return 1;
+      if (cudaEventCreate(&ev_acc0[i]) != cudaSuccess || cudaEventCreate(&ev_acc1[i]) != cudaSuccess) return 1;
+    }
+    return 0;
+  }
+  void destroy_prep_stream() {
+    if (!prep_stream) return;
+    cudaStreamSynchronize(prep_stream);
+    cudaStreamDestroy(prep_stream);
+    cudaEventDestroy(ev_entry);
+    for (int i = 0; i < MAX_SEGMENTS; i++) {
+      cudaEventDestroy(ev_seg_ready[i]);
+      cudaEventDestroy(ev_acc0[i]);
+      cudaEventDestroy(ev_acc1[i]);
+    }
+    prep_stream = nullptr;
+  }
   float last_ms[2] = {0.f, 0.f};
   double last_stat[4] = {0, 0, 0, 0};  // last MSM: window bits, digits per scalar, shared bucket set (0/1), mixed additions
   float kernel_ms_accum = 0.f;
@@ -39,6 +68,12 @@ struct qz_ctx {
 
   ncclComm* comm = nullptr;
   int rank = 0, nranks = 1;
+  // peer mailboxes (comm.cuh): this rank's mailbox, the device array of all ranks' mailbox pointers (own included),
+  // the peers' mapped pointers (to close them) and the sequence number of the last exchange
+  void* mbox = nullptr;
+  void** peer_mbox_dev = nullptr;
+  void* peer_mbox_host[16] = {};
+  uint32_t mbox_seq = 0;
 
   int fail(int status, const char* what, cudaError_t ce = cudaSuccess) {
     char buf[512];
@@ -113,10 +148,12 @@ struct qz_ctx {
   } while (0)
 
 // kernel launch with launch accounting; errors surface at the next QZ_CUDA / sync
-#define QZ_LAUNCH(ctx, kernel, grid, block, smem, ...)                        \
+#define QZ_LAUNCH_ON(ctx, strm, kernel, grid, block, smem, ...)                \
   do {                                                                        \
-    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);          \
+    kernel<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__);                 \
     (ctx)->launches++;                                                        \
     cudaError_t e_ = cudaPeekAtLastError();                                   \
     if (e_ != cudaSuccess) return (ctx)->fail(QZ_ERR_CUDA, #kernel, e_);      \
   } while (0)
+#define QZ_LAUNCH(ctx, kernel, grid, block, smem, ...) \
+  QZ_LAUNCH_ON(ctx, (ctx)->stream, kernel, grid, block, smem, __VA_ARGS__)

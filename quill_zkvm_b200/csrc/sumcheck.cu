@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cstring>
 #include <vector>
+#include "comm.cuh"
 #include "ctx.cuh"
 #include "sumcheck.cuh"
 
@@ -227,6 +228,34 @@ __global__ void __launch_bounds__(SC_THREADS) sc_finalize(const Fr* partials, in
   for (int b = threadIdx.x; b < n_parts; b += blockDim.x)
     for (int x = 0; x <= d; x++) v[x] = fp_add<FrParams>(v[x], partials[(size_t)b * (d + 1) + x]);
   block_sum_many(v, d + 1, s_part, s_evals);
+  sc_round_close(head, vinv, d, s_evals, s_coef, s_msg, s_prod, out_coeffs_row, out_len, out_point_slot, max_coeffs);
+}
+
+// Sharded mode with peer mailboxes (comm.cuh): ONE launch per round after the round kernel.  The block sums this rank's
+// partials, stores the (d+1)-vector into every rank's mailbox over NVLink, waits for the G vectors addressed to it,
+// adds them (field addition is exact, so the order does not matter) and closes the round -- every rank runs the same
+// transcript on the same sums and draws the same challenge.  Replaces sc_reduce_partials + ncclAllGather + sc_finalize.
+__global__ void __launch_bounds__(SC_THREADS) sc_finalize_peers(const Fr* partials, int n_parts, int d,
+                                                               PeerMailbox* const* peers, int rank, int G, uint32_t seq,
+                                                               ScHead* head, const Fr* vinv, Fr* out_coeffs_row,
+                                                               uint32_t* out_len, Fr* out_point_slot, int max_coeffs) {
+  __shared__ Fr s_part[(SC_THREADS / 32) * SC_MAX_COEFFS];
+  __shared__ Fr s_evals[SC_MAX_COEFFS];
+  __shared__ Fr s_coef[SC_MAX_COEFFS];
+  __shared__ Fr s_prod[SC_PROD_SLOTS];
+  __shared__ __align__(16) uint32_t s_msg[SC_MSG_WORDS];
+  Fr v[SC_MAX_COEFFS];
+  for (int x = 0; x <= d; x++) v[x] = fp_zero<FrParams>();
+  for (int b = threadIdx.x; b < n_parts; b += blockDim.x)
+    for (int x = 0; x <= d; x++) v[x] = fp_add<FrParams>(v[x], partials[(size_t)b * (d + 1) + x]);
+  block_sum_many(v, d + 1, s_part, s_evals);
+  const PeerSlot* got = peer_exchange(peers, rank, G, seq, s_evals, d + 1);
+  if ((int)threadIdx.x <= d) {
+    Fr sum = fp_zero<FrParams>();
+    for (int g = 0; g < G; g++) sum = fp_add<FrParams>(sum, ld_fresh(&got->data[g][threadIdx.x]));
+    s_evals[threadIdx.x] = sum;
+  }
+  __syncthreads();
   sc_round_close(head, vinv, d, s_evals, s_coef, s_msg, s_prod, out_coeffs_row, out_len, out_point_slot, max_coeffs);
 }
 
@@ -565,7 +594,6 @@ int round_grid(qz_ctx* ctx, uint64_t n_pairs, int blocks_per_sm, int threads = S
 
 namespace qz {
 
-int comm_allgather(qz_ctx* ctx, const void* send, void* recv, size_t bytes);  // comm.cu
 
 // elements [base, base + n_elems) of eq(., z) over n variables
 int eq_table_device(qz_ctx* ctx, int n, const Fr* z_dev, uint4* out_dev, uint64_t base, uint64_t n_elems) {
@@ -827,6 +855,10 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
       if (G == 1) {
         QZ_LAUNCH(ctx, sc_finalize, 1, SC_THREADS, 0, partials, grid, d, head, vinv, d_coeffs + (size_t)round * mc,
                   d_lens + round, d_point + round, mc);
+      } else if (comm_has_peers(ctx)) {  // partial sums go straight into the peers' mailboxes (comm.cuh)
+        QZ_LAUNCH(ctx, sc_finalize_peers, 1, SC_THREADS, 0, partials, grid, d, (PeerMailbox* const*)ctx->peer_mbox_dev,
+                  ctx->rank, G, ++ctx->mbox_seq, head, vinv, d_coeffs + (size_t)round * mc, d_lens + round,
+                  d_point + round, mc);
       } else {  // every rank sums all ranks' partial evaluations and runs the same transcript
         QZ_LAUNCH(ctx, sc_reduce_partials, 1, SC_THREADS, 0, partials, grid, d, rank_evals);
         rc = comm_allgather(ctx, rank_evals, all_evals, sizeof(Fr) * (d + 1));
@@ -889,6 +921,11 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
   }
   QZ_CUDA(ctx, cudaEventRecord(ctx->ev_call1, st));
   QZ_CUDA(ctx, cudaStreamSynchronize(st));
+  if (G > 1 && comm_has_peers(ctx)) {
+    uint32_t dead = 0;
+    QZ_CUDA(ctx, cudaMemcpy(&dead, &((PeerMailbox*)ctx->mbox)->timed_out, 4, cudaMemcpyDeviceToHost));
+    if (dead) return ctx->fail(QZ_ERR_NCCL, "a peer did not deliver its partial sums (peer mailbox wait timed out)");
+  }
   const ScHead* h = (const ScHead*)pin;
   memcpy(state, h->tstate, 32);
   memcpy(out_eval, h->evaluation.v, 32);

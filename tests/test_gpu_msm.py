@@ -210,3 +210,45 @@ def test_msm_2_26_closed_form(ctx):
     kzg.srs.free()
     y, _ = co.kzg_open_quotient(sc, co.fr1(TAU))
     assert np.array_equal(got, co.g1_mul(co.g1_to_bytes(GEN), y))
+
+
+@pytest.mark.parametrize("weights", ["1,1", "2,5,12", "1,1,1,1,1,1,1,1", "1,1000"])
+def test_streamed_msm_segments(ctx, kzg_big, weights, monkeypatch):
+    """the streamed MSM (point ranges prepared on a second stream, one bucket-set copy per range, merged before the
+    reduction) must not change a bit: forced at small sizes, host and device scalars, skewed and ragged inputs"""
+    monkeypatch.setenv("QZ_MSM_SEGMENTS", weights)
+    monkeypatch.setenv("QZ_MSM_SEGMENTS_DEV", weights)
+    rnd = random.Random(len(weights))
+    for n in (1, 2, 255, 256, 257, 1000, 5000, 70001):
+        bases = kzg_big.srs.download(0, n)
+        cases = [util.rand_fr(n, 77 + n)]
+        if n == 5000:
+            cases += [co.to_mont([rnd.randrange(3) for _ in range(n)]), co.to_mont([FR - 1] * n), co.to_mont([0] * n)]
+        for sc in cases:
+            want = co.msm(bases, sc, mode=1, threads=os.cpu_count() or 1)
+            assert np.array_equal(kzg_big.commit(sc), want), (n, weights)
+            dev = ctx.upload(sc)
+            assert np.array_equal(kzg_big.commit(dev), want), (n, weights, "device scalars")
+            dev.free()
+    # KZG::open and the precomputed-window layout on top of the segments
+    n = 3000
+    srs = co.srs_generate(co.g1_to_bytes(GEN), co.fr1(TAU), n, threads=4)
+    kz = q.KZG.from_points(ctx, srs).precompute(13)
+    sc = util.rand_fr(n, 5)
+    assert np.array_equal(kz.commit(sc), co.msm(srs, sc, mode=1, threads=4))
+    pr = kz.open(sc, co.fr1(999))
+    y, qpoly = co.kzg_open_quotient(sc, co.fr1(999))
+    assert np.array_equal(pr.y, y) and np.array_equal(pr.proof, co.msm(srs, qpoly, mode=1, threads=4))
+    kz.srs.free()
+
+
+def test_streamed_msm_default_host_path_2_20(ctx, kzg_big):
+    """host scalars at 2^20 take the streamed path by default (>= 2^19): same commitment as device-resident scalars"""
+    n = 1 << 20
+    buf = ctx.random_fr(n, 909)
+    sc = buf.download().reshape(-1, 32)
+    a = kzg_big.commit(buf)
+    b = kzg_big.commit(sc)
+    buf.free()
+    y, _ = co.kzg_open_quotient(sc, co.fr1(TAU))
+    assert np.array_equal(a, b) and np.array_equal(a, co.g1_mul(co.g1_to_bytes(GEN), y))

@@ -80,7 +80,8 @@ def main():
     dist.barrier()
     if rank == 0:
         print(f"multi-GPU parity ok on {world} ranks: sharded MSM, sharded sumcheck and the HyperPlonk proof with its "
-              f"openings dealt to the ranks match the oracle bit for bit")
+              f"openings dealt to the ranks match the oracle bit for bit "
+              f"(exchange: {'peer mailboxes over NVLink' if ctx.peer_memory else 'NCCL all-gather'})")
     ctx.close()
     dist.destroy_process_group()
 
