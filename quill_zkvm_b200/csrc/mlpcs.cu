@@ -48,39 +48,55 @@ __global__ void __launch_bounds__(128) ntt_twiddles(int log_m, uint64_t count, F
   }
 }
 
-// stages [s0, s0 + T) of a size-2^log_m transform on tiles of 2^T elements that are closed under those stages
+// stages [s0, s0 + T) of a size-2^log_m transform.  An element's index reads  hi | t (T bits) | lo (lo_bits bits)  and
+// the 2^T elements that share (hi, lo) are closed under those stages: a sub-tile.  A block works on 2^logC sub-tiles at
+// once -- the ones whose (hi, lo) differ in the lowest logC bits, i.e. adjacent columns -- so that every pass keeps all
+// threads busy whatever T is (a pass of 3 stages used to run 4 threads per block) and a strided pass still moves runs
+// of 2^logC consecutive elements.  Shared memory holds element (t, u) of sub-tile u at [t * C + u].
 template <bool INVERSE>
-__global__ void __launch_bounds__(NTT_THREADS) ntt_pass(uint4* data, int log_m, int s0, int T, const Fr* W) {
+__global__ void __launch_bounds__(NTT_THREADS) ntt_pass(uint4* data, int log_m, int s0, int T, int logC, const Fr* W) {
   __shared__ Fr tile[1 << NTT_TILE_LOG];
-  const uint64_t m = (uint64_t)1 << log_m, tiles = m >> T;
-  const int lo_bits = log_m - s0 - T;
+  const uint64_t m = (uint64_t)1 << log_m, groups = m >> (T + logC);
+  const int lo_bits = log_m - s0 - T, C = 1 << logC;
+  const int lu = logC < lo_bits ? logC : lo_bits;  // bits of u that fall into lo (contiguous in memory)
   const uint64_t stride = (uint64_t)1 << lo_bits, half_m = m >> 1;
-  for (uint64_t tile_id = blockIdx.x; tile_id < tiles; tile_id += gridDim.x) {
-    const uint64_t lo_part = tile_id & (stride - 1), hi_part = tile_id >> lo_bits;
-    const uint64_t base = (hi_part << (log_m - s0)) + lo_part;
-    for (int t = threadIdx.x; t < (1 << T); t += blockDim.x) tile[t] = fp_load<FrParams>(data + 2 * (base + (uint64_t)t * stride));
+  const int n_elems = 1 << (T + logC);
+  for (uint64_t group = blockIdx.x; group < groups; group += gridDim.x) {
+    const uint64_t tile0 = group << logC;  // first of the block's sub-tiles; sub-tile id = hi << lo_bits | lo
+    // global <-> shared in address order: idx = u_hi | t | u_lo
+    for (int idx = threadIdx.x; idx < n_elems; idx += blockDim.x) {
+      const int u = (idx & ((1 << lu) - 1)) | ((idx >> (T + lu)) << lu), t = (idx >> lu) & ((1 << T) - 1);
+      const uint64_t id = tile0 + u, lo = id & (stride - 1), hi = id >> lo_bits;
+      tile[t * C + u] = fp_load<FrParams>(data + 2 * ((hi << (log_m - s0)) + lo + (uint64_t)t * stride));
+    }
     __syncthreads();
     for (int step = 0; step < T; step++) {
       const int ls = INVERSE ? T - 1 - step : step;  // local stage; global stage s = s0 + ls
       const int lhalf = 1 << (T - 1 - ls), s = s0 + ls;
-      for (int b = threadIdx.x; b < (1 << (T - 1)); b += blockDim.x) {
-        const int j_l = b & (lhalf - 1), i0 = ((b - j_l) << 1) + j_l, i1 = i0 + lhalf;
-        const uint64_t e = ((uint64_t)j_l * stride + lo_part) << s;  // twiddle exponent, < m/2
-        const Fr u = tile[i0], v = tile[i1];
+      for (int bb = threadIdx.x; bb < (n_elems >> 1); bb += blockDim.x) {
+        const int u = bb & (C - 1), b = bb >> logC;
+        const int j_l = b & (lhalf - 1), i0 = (((b - j_l) << 1) + j_l) * C + u, i1 = i0 + lhalf * C;
+        const uint64_t lo = (tile0 + u) & (stride - 1);
+        const uint64_t e = ((uint64_t)j_l * stride + lo) << s;  // twiddle exponent, < m/2
+        const Fr a = tile[i0], v = tile[i1];
         if (!INVERSE) {
-          tile[i0] = fp_add<FrParams>(u, v);
-          const Fr d = fp_sub<FrParams>(u, v);
+          tile[i0] = fp_add<FrParams>(a, v);
+          const Fr d = fp_sub<FrParams>(a, v);
           tile[i1] = e ? fp_mul<FrParams>(d, W[e]) : d;
         } else {
           // w^-e = -w^(m/2 - e)
           const Fr vw = e ? fp_neg<FrParams>(fp_mul<FrParams>(v, W[half_m - e])) : v;
-          tile[i0] = fp_add<FrParams>(u, vw);
-          tile[i1] = fp_sub<FrParams>(u, vw);
+          tile[i0] = fp_add<FrParams>(a, vw);
+          tile[i1] = fp_sub<FrParams>(a, vw);
         }
       }
       __syncthreads();
     }
-    for (int t = threadIdx.x; t < (1 << T); t += blockDim.x) fp_store<FrParams>(data + 2 * (base + (uint64_t)t * stride), tile[t]);
+    for (int idx = threadIdx.x; idx < n_elems; idx += blockDim.x) {
+      const int u = (idx & ((1 << lu) - 1)) | ((idx >> (T + lu)) << lu), t = (idx >> lu) & ((1 << T) - 1);
+      const uint64_t id = tile0 + u, lo = id & (stride - 1), hi = id >> lo_bits;
+      fp_store<FrParams>(data + 2 * ((hi << (log_m - s0)) + lo + (uint64_t)t * stride), tile[t * C + u]);
+    }
     __syncthreads();
   }
 }
@@ -207,21 +223,24 @@ int ntt_device(qz_ctx* ctx, uint4* data, int log_m, bool inverse) {
   Fr* W = nullptr;
   int rc = get_twiddles(ctx, log_m, &W);
   if (rc) return rc;
-  // stage groups [s0, s0 + T): forward in increasing order, inverse in decreasing order
-  int starts[32], sizes[32], ng = 0;
-  for (int s0 = 0; s0 < log_m; s0 += NTT_TILE_LOG) {
-    starts[ng] = s0;
-    sizes[ng] = std::min(NTT_TILE_LOG, log_m - s0);
-    ng++;
+  // stage groups [s0, s0 + T), as few as fit the tile and of (almost) equal size: forward in increasing order, inverse
+  // in decreasing order
+  int starts[32], sizes[32];
+  const int ng = (log_m + NTT_TILE_LOG - 1) / NTT_TILE_LOG;
+  for (int g = 0, s0 = 0; g < ng; g++) {
+    starts[g] = s0;
+    sizes[g] = log_m / ng + (g < log_m % ng ? 1 : 0);
+    s0 += sizes[g];
   }
   for (int gi = 0; gi < ng; gi++) {
     const int g = inverse ? ng - 1 - gi : gi;
-    const uint64_t tiles = ((uint64_t)1 << log_m) >> sizes[g];
-    const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * 8);
+    const int logC = std::min(NTT_TILE_LOG, log_m) - sizes[g];
+    const uint64_t groups = ((uint64_t)1 << log_m) >> (sizes[g] + logC);
+    const unsigned grid = (unsigned)std::min<uint64_t>(groups, (uint64_t)ctx->sm_count * 8);
     if (inverse)
-      QZ_LAUNCH(ctx, ntt_pass<true>, grid, NTT_THREADS, 0, data, log_m, starts[g], sizes[g], W);
+      QZ_LAUNCH(ctx, ntt_pass<true>, grid, NTT_THREADS, 0, data, log_m, starts[g], sizes[g], logC, W);
     else
-      QZ_LAUNCH(ctx, ntt_pass<false>, grid, NTT_THREADS, 0, data, log_m, starts[g], sizes[g], W);
+      QZ_LAUNCH(ctx, ntt_pass<false>, grid, NTT_THREADS, 0, data, log_m, starts[g], sizes[g], logC, W);
   }
   return QZ_OK;
 }

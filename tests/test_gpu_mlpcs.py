@@ -34,8 +34,10 @@ def _trim(a):
 
 
 @pytest.mark.parametrize("n1,n2", [(1, 1), (2, 2), (3, 3), (3, 2), (2, 5), (5, 9), (64, 64), (1000, 1000), (4097, 300),
-                                   (1 << 15, 1 << 15)])
+                                   (1 << 15, 1 << 15), (3000, 2049), (1 << 19, 1 << 19), (600000, 1000),
+                                   ((1 << 20) + 5, 300000)])
 def test_s_polynomial_vs_oracle(ctx, kzg, n1, n2):
+    """NTT sizes 2^1 .. 2^22: one pass, two passes and three passes of 10+10, 7+6, 7+7+7 and 8+7+7 fused stages"""
     a, b = util.rand_fr(n1, n1), util.rand_fr(n2, 7 * n2 + 1)
     got = kzg.compute_s_polynomial(a, b)
     want = co.compute_s_polynomial(a, b)

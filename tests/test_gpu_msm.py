@@ -252,3 +252,22 @@ def test_streamed_msm_default_host_path_2_20(ctx, kzg_big):
     buf.free()
     y, _ = co.kzg_open_quotient(sc, co.fr1(TAU))
     assert np.array_equal(a, b) and np.array_equal(a, co.g1_mul(co.g1_to_bytes(GEN), y))
+
+
+def test_kzg_open_large_closed_form(ctx):
+    """KZG::open beyond 2^20 coefficients (the carry scan of the quotient links several level-2 groups per thread, the
+    last run ragged): y = p(x) from the oracle's Horner, proof = commit(q) = ((p(tau) - y) / (tau - x)) * g"""
+    n = (1 << 22) + 4099
+    kzg = q.KZG.trusted_setup(ctx, n - 1, co.g1_to_bytes(GEN), co.fr1(TAU))
+    buf = ctx.random_fr(n, 4242)
+    sc = buf.download().reshape(-1, 32)
+    x = util.rand_fr(1, 99)[0]
+    pr = kzg.open(buf, x)
+    buf.free()
+    kzg.srs.free()
+    y, _ = co.kzg_open_quotient(sc, x)
+    ptau, _ = co.kzg_open_quotient(sc, co.fr1(TAU))
+    yi, pti, xi = (co.from_mont(v.reshape(1, 32))[0] for v in (y, ptau, x))
+    qtau = (pti - yi) * pow((TAU - xi) % FR, -1, FR) % FR
+    assert np.array_equal(pr.y, y)
+    assert np.array_equal(pr.proof, co.g1_mul(co.g1_to_bytes(GEN), co.fr1(qtau)))
