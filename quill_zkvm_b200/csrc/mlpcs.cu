@@ -53,9 +53,24 @@ __global__ void __launch_bounds__(128) ntt_twiddles(int log_m, uint64_t count, F
 // once -- the ones whose (hi, lo) differ in the lowest logC bits, i.e. adjacent columns -- so that every pass keeps all
 // threads busy whatever T is (a pass of 3 stages used to run 4 threads per block) and a strided pass still moves runs
 // of 2^logC consecutive elements.  Shared memory holds element (t, u) of sub-tile u at [t * C + u].
+// A 32-byte element read by consecutive threads as two 128-bit words puts threads i and i+4 of a quarter-warp on the
+// same banks (ncu: half of all shared wavefronts were conflicts), so the tile keeps the two halves in separate planes.
+struct NttTile {
+  uint4 lo[1 << NTT_TILE_LOG], hi[1 << NTT_TILE_LOG];
+  QZ_DEV Fr get(int i) const {
+    const uint4 a = lo[i], b = hi[i];
+    Fr r;
+    r.v[0] = a.x, r.v[1] = a.y, r.v[2] = a.z, r.v[3] = a.w, r.v[4] = b.x, r.v[5] = b.y, r.v[6] = b.z, r.v[7] = b.w;
+    return r;
+  }
+  QZ_DEV void set(int i, const Fr& r) {
+    lo[i] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    hi[i] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+  }
+};
 template <bool INVERSE>
 __global__ void __launch_bounds__(NTT_THREADS) ntt_pass(uint4* data, int log_m, int s0, int T, int logC, const Fr* W) {
-  __shared__ Fr tile[1 << NTT_TILE_LOG];
+  __shared__ NttTile tile;
   const uint64_t m = (uint64_t)1 << log_m, groups = m >> (T + logC);
   const int lo_bits = log_m - s0 - T, C = 1 << logC;
   const int lu = logC < lo_bits ? logC : lo_bits;  // bits of u that fall into lo (contiguous in memory)
@@ -67,7 +82,9 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass(uint4* data, int log_m, 
     for (int idx = threadIdx.x; idx < n_elems; idx += blockDim.x) {
       const int u = (idx & ((1 << lu) - 1)) | ((idx >> (T + lu)) << lu), t = (idx >> lu) & ((1 << T) - 1);
       const uint64_t id = tile0 + u, lo = id & (stride - 1), hi = id >> lo_bits;
-      tile[t * C + u] = fp_load<FrParams>(data + 2 * ((hi << (log_m - s0)) + lo + (uint64_t)t * stride));
+      const uint4* src = data + 2 * ((hi << (log_m - s0)) + lo + (uint64_t)t * stride);
+      tile.lo[t * C + u] = src[0];
+      tile.hi[t * C + u] = src[1];
     }
     __syncthreads();
     for (int step = 0; step < T; step++) {
@@ -78,16 +95,16 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass(uint4* data, int log_m, 
         const int j_l = b & (lhalf - 1), i0 = (((b - j_l) << 1) + j_l) * C + u, i1 = i0 + lhalf * C;
         const uint64_t lo = (tile0 + u) & (stride - 1);
         const uint64_t e = ((uint64_t)j_l * stride + lo) << s;  // twiddle exponent, < m/2
-        const Fr a = tile[i0], v = tile[i1];
+        const Fr a = tile.get(i0), v = tile.get(i1);
         if (!INVERSE) {
-          tile[i0] = fp_add<FrParams>(a, v);
+          tile.set(i0, fp_add<FrParams>(a, v));
           const Fr d = fp_sub<FrParams>(a, v);
-          tile[i1] = e ? fp_mul<FrParams>(d, W[e]) : d;
+          tile.set(i1, e ? fp_mul<FrParams>(d, W[e]) : d);
         } else {
           // w^-e = -w^(m/2 - e)
           const Fr vw = e ? fp_neg<FrParams>(fp_mul<FrParams>(v, W[half_m - e])) : v;
-          tile[i0] = fp_add<FrParams>(a, vw);
-          tile[i1] = fp_sub<FrParams>(a, vw);
+          tile.set(i0, fp_add<FrParams>(a, vw));
+          tile.set(i1, fp_sub<FrParams>(a, vw));
         }
       }
       __syncthreads();
@@ -95,7 +112,9 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass(uint4* data, int log_m, 
     for (int idx = threadIdx.x; idx < n_elems; idx += blockDim.x) {
       const int u = (idx & ((1 << lu) - 1)) | ((idx >> (T + lu)) << lu), t = (idx >> lu) & ((1 << T) - 1);
       const uint64_t id = tile0 + u, lo = id & (stride - 1), hi = id >> lo_bits;
-      fp_store<FrParams>(data + 2 * ((hi << (log_m - s0)) + lo + (uint64_t)t * stride), tile[t * C + u]);
+      uint4* dst = data + 2 * ((hi << (log_m - s0)) + lo + (uint64_t)t * stride);
+      dst[0] = tile.lo[t * C + u];
+      dst[1] = tile.hi[t * C + u];
     }
     __syncthreads();
   }

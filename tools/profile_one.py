@@ -1,4 +1,4 @@
-"""Run ONE call of a hot path (for ncu): python tools/profile_one.py sumcheck|msm|zerocheck LOG_N"""
+"""Run ONE call of a hot path (for ncu): python tools/profile_one.py sumcheck|msm|zerocheck|mlpcs LOG_N"""
 import os
 import sys
 
@@ -30,6 +30,16 @@ if what in ("sumcheck", "zerocheck"):
         else:
             q.ZeroCheckProof.prove(ctx, store, h, tr)
         print(what, n, "ms", ctx.last_elapsed_ms(0), "rounds ms", ctx.last_elapsed_ms(1))
+elif what == "mlpcs":
+    g = np.concatenate([mont(1, FQ), mont(2, FQ)])
+    kzg = q.KZG.trusted_setup(ctx, (1 << n) - 1, g, mont(0x1234567)).precompute()
+    poly = ctx.random_fr(1 << n, 777)
+    point = np.frombuffer(b"".join(((i * 0x9E3779B97F4A7C15 + 12345) % FR).to_bytes(32, "little") for i in range(n)),
+                          dtype=np.uint8).reshape(n, 32).copy()
+    for rep in range(2):
+        kzg.commit(poly)
+        kzg.open_multilinear(poly, point, q.Transcript(b"mlpcs_bench", ctx))
+        print("mlpcs", n, "open ms", ctx.last_elapsed_ms(0))
 else:
     g = np.concatenate([mont(1, FQ), mont(2, FQ)])
     kzg = q.KZG.trusted_setup(ctx, (1 << n) - 1, g, mont(0x1234567))
