@@ -214,7 +214,8 @@ int qz_bench_fp_mul(qz_ctx* ctx, int field, double* out_muls_per_s);
 
 /* test hooks: element-wise field ops on host buffers through the device (op: 0 add, 1 sub, 2 mul, 3 inverse,
  * 4 to_mont, 5 from_mont, 6 a*b + a*a + b*b through the deferred-reduction accumulator, 7 4096 * (a*b) through it,
- * 8 a*b + (a+b)*(a-b) by the fused two-product multiplier, 9 a*a by the dedicated squaring;
+ * 8 a*b + (a+b)*(a-b) by the fused two-product multiplier, 9 a*a by the dedicated squaring,
+ * 10 inverse by the binary extended Euclidean algorithm (the single-thread critical-path inverse);
  * field: 0 Fr, 1 Fq); G1 add / scalar-mul */
 int qz_test_field_op(qz_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
 int qz_test_g1_add(qz_ctx* ctx, const uint8_t* a_xy, const uint8_t* b_xy, uint8_t* out_xy, size_t n);

@@ -71,6 +71,7 @@ __global__ void k_field_op(int op, const uint4* a, const uint4* b, uint4* out, s
       break;
     }
     case 9: r = fp_sqr<P>(x); break;
+    case 10: r = fp_inv_serial<P>(x); break;  // binary extended Euclid (the single-thread critical-path inverse)
     case 8: r = fp_mul2_add<P>(x, y, fp_add<P>(x, y), fp_sub<P>(x, y)); break;  // x*y + (x+y)*(x-y), one reduction
     default: {  // 4096 * (x*y): the accumulator's 17th word in use
       FpWide w;
@@ -395,7 +396,7 @@ int qz_eq_table(qz_ctx* c, size_t n, const uint8_t* point, void* out, int out_on
 
 // ---- test hooks -----------------------------------------------------------------------------------------------------------------------
 int qz_test_field_op(qz_ctx* c, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
-  if (!c || !a || !out || op < 0 || op > 9 || field < 0 || field > 1) return QZ_ERR_INVALID_ARG;
+  if (!c || !a || !out || op < 0 || op > 10 || field < 0 || field > 1) return QZ_ERR_INVALID_ARG;
   if (n == 0) return QZ_OK;
   c->arena_reset();
   uint4* da = (uint4*)c->arena_alloc(32 * n);

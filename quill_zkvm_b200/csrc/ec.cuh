@@ -148,5 +148,18 @@ static __device__ __noinline__ Affine xyzz_to_affine(const Xyzz& p) {
   a.y = fp_mul<FqParams>(p.y, fp_mul<FqParams>(inv, p.zz));
   return a;
 }
+// the same for the single thread that finishes an MSM: latency-optimised inversion (ff.cuh fp_inv_serial)
+static __device__ __noinline__ Affine xyzz_to_affine_serial(const Xyzz& p) {
+  Affine a;
+  if (xyzz_is_identity(p)) {
+    a.x = fp_zero<FqParams>();
+    a.y = fp_zero<FqParams>();
+    return a;
+  }
+  Fq inv = fp_inv_serial<FqParams>(fp_mul<FqParams>(p.zz, p.zzz));
+  a.x = fp_mul<FqParams>(p.x, fp_mul<FqParams>(inv, p.zzz));
+  a.y = fp_mul<FqParams>(p.y, fp_mul<FqParams>(inv, p.zz));
+  return a;
+}
 
 }  // namespace qz

@@ -207,7 +207,7 @@ __global__ void mlpcs_transcript(uint8_t* state, const Fr* point, int n, const F
   tr_absorb(state, buf, 64);
   const Fr r = tr_draw_fr(state);
   r_out[0] = r;
-  r_out[1] = fp_inv<FrParams>(r);  // r = 0 has probability 2^-254; the reference would panic on unwrap (:107)
+  r_out[1] = fp_inv_serial<FrParams>(r);  // r = 0 has probability 2^-254; the reference would panic on unwrap (:107)
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------------------

@@ -264,7 +264,7 @@ __global__ void msm_combine(const uint8_t* window_sums, int c, int W, uint8_t* o
     total = xyzz_add(total, p);
   }
   if (out_xyzz) xyzz_store(out_xyzz, total);
-  if (out_affine) affine_store(out_affine, xyzz_to_affine(total));
+  if (out_affine) affine_store(out_affine, xyzz_to_affine_serial(total));
 }
 // sum of `n` XYZZ points (multi-GPU: the gathered per-rank partial sums) -> affine
 __global__ void msm_sum_points(const uint8_t* pts, int n, uint8_t* out_affine) {
@@ -274,7 +274,7 @@ __global__ void msm_sum_points(const uint8_t* pts, int n, uint8_t* out_affine) {
     xyzz_load(p, pts + (size_t)i * 128);
     total = xyzz_add(total, p);
   }
-  affine_store(out_affine, xyzz_to_affine(total));
+  affine_store(out_affine, xyzz_to_affine_serial(total));
 }
 
 // ---- SRS generation: points[i] = tau^i * g (kzg.rs:44-47), fixed-base 8-bit windows -------------------------------------

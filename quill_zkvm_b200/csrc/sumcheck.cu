@@ -394,7 +394,7 @@ __global__ void zc_finish(ScHead* head, const Fr* z, const Fr* point, int n) {
                                fp_mul<FrParams>(fp_sub<FrParams>(one, x), fp_sub<FrParams>(one, r)));
     e = fp_mul<FrParams>(e, term);
   }
-  head->evaluation = fp_mul<FrParams>(head->evaluation, fp_inv<FrParams>(e));
+  head->evaluation = fp_mul<FrParams>(head->evaluation, fp_inv_serial<FrParams>(e));
 }
 // Inverse Vandermonde on nodes 0..d: vinv[i*(d+1)+j] = coefficient of X^i in the Lagrange basis polynomial L_j
 __global__ void sc_build_vinv(int d, Fr* vinv) {

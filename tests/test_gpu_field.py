@@ -58,6 +58,10 @@ def test_field_inverse(ctx, field, mod):
     A = co.to_mont(a, mod)
     got = co.from_mont(ctx.field_op(field, 3, A), mod)
     assert got == [pow(x, mod - 2, mod) for x in a]
+    # the single-thread critical-path inverse (binary extended Euclid, ff.cuh fp_inv_serial): same values, 0 -> 0
+    a = _edge_and_random(mod, 512, 10) + [2, 3, 4, (mod + 1) // 2, 1 << 128, (1 << 253) % mod, mod - 2]
+    got = co.from_mont(ctx.field_op(field, 10, co.to_mont(a, mod)), mod)
+    assert got == [pow(x, mod - 2, mod) for x in a]
 
 
 def test_random_fr_generator_is_reduced(ctx):
