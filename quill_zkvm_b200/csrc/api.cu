@@ -1,6 +1,7 @@
 // C ABI (include/quill_b200.h): context, transcript, device buffers, test and measurement hooks.
 // The proving entry points forward to sumcheck.cu / msm.cu.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -215,6 +216,7 @@ int qz_ctx_create(int device, void* stream, qz_ctx** out) {
     }
     c->own_stream = true;
   }
+  c->pdl = getenv("QZ_NO_PDL") == nullptr;
   cudaEventCreate(&c->ev_call0);
   cudaEventCreate(&c->ev_call1);
   cudaEventCreate(&c->ev_k0);

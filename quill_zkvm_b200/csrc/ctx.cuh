@@ -15,6 +15,7 @@ struct qz_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int sm_count = 148;
+  bool pdl = true;  // programmatic dependent launches for the sumcheck round chain (QZ_NO_PDL=1 turns them off)
   std::string err;
   uint64_t launches = 0;
 
@@ -157,3 +158,24 @@ struct qz_ctx {
   } while (0)
 #define QZ_LAUNCH(ctx, kernel, grid, block, smem, ...) \
   QZ_LAUNCH_ON(ctx, (ctx)->stream, kernel, grid, block, smem, __VA_ARGS__)
+
+// Programmatic dependent launch for chains of short dependent kernels (the sumcheck rounds): the kernel may become
+// resident while its predecessor in the stream still runs and parks at grid_dep_wait(), so launch processing and block
+// scheduling overlap the predecessor instead of following it.  Kernels launched this way MUST call grid_dep_wait()
+// before touching anything the predecessor writes; the call is a no-op under an ordinary launch.  `pdl` false (or
+// QZ_NO_PDL set when the context was created) degrades to an ordinary launch.
+#define QZ_LAUNCH_PDL(ctx, pdl, kernel, grid, block, ...)                                  \
+  do {                                                                                     \
+    cudaLaunchConfig_t cfg_ = {};                                                          \
+    cfg_.gridDim = dim3(grid);                                                             \
+    cfg_.blockDim = dim3(block);                                                           \
+    cfg_.stream = (ctx)->stream;                                                           \
+    cudaLaunchAttribute at_[1];                                                            \
+    at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                        \
+    at_[0].val.programmaticStreamSerializationAllowed = 1;                                 \
+    cfg_.attrs = at_;                                                                      \
+    cfg_.numAttrs = (pdl) ? 1 : 0;                                                         \
+    cudaError_t e_ = cudaLaunchKernelEx(&cfg_, kernel, __VA_ARGS__);                       \
+    (ctx)->launches++;                                                                     \
+    if (e_ != cudaSuccess) return (ctx)->fail(QZ_ERR_CUDA, #kernel, e_);                   \
+  } while (0)

@@ -17,6 +17,11 @@ namespace qz {
 
 #define QZ_DEV __device__ __forceinline__
 
+// programmatic dependent launch (ctx.cuh QZ_LAUNCH_PDL): let the next kernel of the stream be scheduled / wait until
+// everything the previous kernel wrote is visible.  Both are no-ops under an ordinary launch.
+QZ_DEV void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+QZ_DEV void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <class P>
 struct Fp {
   uint32_t v[8];

@@ -159,6 +159,8 @@ template <int K, bool WIDE, bool FOLD>
 __global__ void __launch_bounds__(WIDE ? SC_WIDE_THREADS : SC_THREADS, (WIDE ? QZ_SC_WIDE_BPS : K <= 3 ? 2 : 1))
     sc_round_prod(ScTables tabs, uint64_t n_pairs, const ScHead* head, Fr* partials) {
   __shared__ Fr s_part[(SC_THREADS / 32) * (K + 1)];
+  grid_dep_launch();
+  grid_dep_wait();
   ProdAcc<K, WIDE> acc;
   acc.init();
   Fr r = fp_zero<FrParams>();
@@ -200,10 +202,12 @@ __global__ void __launch_bounds__(SC_THREADS) sc_round_generic(ScTables tabs, ui
                                                               const Fr* consts, Fr* partials) {
   __shared__ Fr s_part[(SC_THREADS / 32) * SC_MAX_COEFFS];
   __shared__ uint32_t s_ops[SC_MAX_OPS];
-  const uint32_t n_ops = prog->n_ops;
+  grid_dep_launch();
+  const uint32_t n_ops = prog->n_ops;  // the program and the constants are uploaded before the first round
   const int d = (int)prog->degree, k = (int)prog->k;
   for (uint32_t i = threadIdx.x; i < n_ops; i += blockDim.x) s_ops[i] = prog->ops[i];
   __syncthreads();
+  grid_dep_wait();
   Fr acc[SC_MAX_COEFFS];
   for (int x = 0; x <= d; x++) acc[x] = fp_zero<FrParams>();
   Fr r = fp_zero<FrParams>();
@@ -223,6 +227,8 @@ __global__ void __launch_bounds__(SC_THREADS) sc_finalize(const Fr* partials, in
   __shared__ Fr s_coef[SC_MAX_COEFFS];
   __shared__ Fr s_prod[SC_PROD_SLOTS];
   __shared__ __align__(16) uint32_t s_msg[SC_MSG_WORDS];
+  grid_dep_launch();
+  grid_dep_wait();
   Fr v[SC_MAX_COEFFS];
   for (int x = 0; x <= d; x++) v[x] = fp_zero<FrParams>();
   for (int b = threadIdx.x; b < n_parts; b += blockDim.x)
@@ -244,6 +250,8 @@ __global__ void __launch_bounds__(SC_THREADS) sc_finalize_peers(const Fr* partia
   __shared__ Fr s_coef[SC_MAX_COEFFS];
   __shared__ Fr s_prod[SC_PROD_SLOTS];
   __shared__ __align__(16) uint32_t s_msg[SC_MSG_WORDS];
+  grid_dep_launch();
+  grid_dep_wait();
   Fr v[SC_MAX_COEFFS];
   for (int x = 0; x <= d; x++) v[x] = fp_zero<FrParams>();
   for (int b = threadIdx.x; b < n_parts; b += blockDim.x)
@@ -287,6 +295,7 @@ __global__ void __launch_bounds__(SC_THREADS) sc_tail(ScTables tabs, ScTailBufs 
   __shared__ Fr s_prod[SC_PROD_SLOTS];
   __shared__ __align__(16) uint32_t s_msg[SC_MSG_WORDS];
   __shared__ uint32_t s_ops[SC_MAX_OPS];
+  grid_dep_wait();
   const uint32_t n_ops = prog->n_ops;
   const int d = (int)prog->degree, k = (int)prog->k;
   for (uint32_t i = threadIdx.x; i < n_ops; i += blockDim.x) s_ops[i] = prog->ops[i];
@@ -824,18 +833,23 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
 
     uint64_t size = N;  // current (pre-fold) table size
     int pending = 0, round = 0, flip = 0;
+    // the round chain uses programmatic dependent launches, except around NCCL collectives (not written for them)
+    // Measured (tools/sc_pdl_ab.py): -5 us per round while a round is latency-bound, but +10..20 us on the rounds that
+    // stream 2^21 entries or more, so only the short rounds are chained this way.
+    const bool pdl_ok = ctx->pdl && (G == 1 || comm_has_peers(ctx));
     ctx->kernel_ms_accum = 0.f;
     QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k0, st));
     while (size * G > ((uint64_t)1 << SC_TAIL_LOG)) {
       const uint64_t n_pairs = pending ? size / 4 : size / 2;
+      const bool pdl = pdl_ok && n_pairs <= ((uint64_t)1 << 18);
       for (int j = 0; j < ka; j++) tabs.out[j] = flip ? bufB[j] : bufA[j];
       // deferred reduction pays once a thread sums several pairs (its one-off reduction is 3 products per sum)
       const bool wide = bps_wide > 0 && n_pairs >= (uint64_t)8 * SC_WIDE_THREADS * ctx->sm_count * bps_wide;
       const int grid = wide ? round_grid(ctx, n_pairs, bps_wide, SC_WIDE_THREADS) : round_grid(ctx, n_pairs, bps);
 #define QZ_ROUND_PROD(K, W, T)                                                                                  \
   do {                                                                                                          \
-    if (pending) QZ_LAUNCH(ctx, (sc_round_prod<K, W, true>), grid, T, 0, tabs, n_pairs, head, partials);         \
-    else QZ_LAUNCH(ctx, (sc_round_prod<K, W, false>), grid, T, 0, tabs, n_pairs, head, partials);                \
+    if (pending) QZ_LAUNCH_PDL(ctx, pdl, (sc_round_prod<K, W, true>), grid, T, tabs, n_pairs, (const ScHead*)head, partials); \
+    else QZ_LAUNCH_PDL(ctx, pdl, (sc_round_prod<K, W, false>), grid, T, tabs, n_pairs, (const ScHead*)head, partials);        \
   } while (0)
       switch (cp.product_k) {
         case 1: QZ_ROUND_PROD(1, false, SC_THREADS); break;
@@ -849,16 +863,16 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
           else QZ_ROUND_PROD(4, false, SC_THREADS);
           break;
         default:
-          QZ_LAUNCH(ctx, sc_round_generic, grid, SC_THREADS, 0, tabs, n_pairs, pending, head, d_prog, d_consts,
-                    partials);
+          QZ_LAUNCH_PDL(ctx, pdl, sc_round_generic, grid, SC_THREADS, tabs, n_pairs, pending, (const ScHead*)head,
+                        (const ScProgram*)d_prog, (const Fr*)d_consts, partials);
       }
       if (G == 1) {
-        QZ_LAUNCH(ctx, sc_finalize, 1, SC_THREADS, 0, partials, grid, d, head, vinv, d_coeffs + (size_t)round * mc,
-                  d_lens + round, d_point + round, mc);
+        QZ_LAUNCH_PDL(ctx, pdl, sc_finalize, 1, SC_THREADS, (const Fr*)partials, grid, d, head, (const Fr*)vinv,
+                      d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc);
       } else if (comm_has_peers(ctx)) {  // partial sums go straight into the peers' mailboxes (comm.cuh)
-        QZ_LAUNCH(ctx, sc_finalize_peers, 1, SC_THREADS, 0, partials, grid, d, (PeerMailbox* const*)ctx->peer_mbox_dev,
-                  ctx->rank, G, ++ctx->mbox_seq, head, vinv, d_coeffs + (size_t)round * mc, d_lens + round,
-                  d_point + round, mc);
+        QZ_LAUNCH_PDL(ctx, pdl, sc_finalize_peers, 1, SC_THREADS, (const Fr*)partials, grid, d,
+                      (PeerMailbox* const*)ctx->peer_mbox_dev, ctx->rank, G, ++ctx->mbox_seq, head, (const Fr*)vinv,
+                      d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc);
       } else {  // every rank sums all ranks' partial evaluations and runs the same transcript
         QZ_LAUNCH(ctx, sc_reduce_partials, 1, SC_THREADS, 0, partials, grid, d, rank_evals);
         rc = comm_allgather(ctx, rank_evals, all_evals, sizeof(Fr) * (d + 1));
@@ -895,11 +909,11 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
       if (!tb.a[j] || !tb.b[j]) return ctx->fail(QZ_ERR_ALLOC, "tail scratch");
     }
     switch (cp.product_k) {
-      case 1: QZ_LAUNCH(ctx, sc_tail<1>, 1, SC_THREADS, 0, tabs, tb, size, pending, head, d_prog, d_consts, vinv, d_coeffs, d_lens, d_point, round, mc); break;
-      case 2: QZ_LAUNCH(ctx, sc_tail<2>, 1, SC_THREADS, 0, tabs, tb, size, pending, head, d_prog, d_consts, vinv, d_coeffs, d_lens, d_point, round, mc); break;
-      case 3: QZ_LAUNCH(ctx, sc_tail<3>, 1, SC_THREADS, 0, tabs, tb, size, pending, head, d_prog, d_consts, vinv, d_coeffs, d_lens, d_point, round, mc); break;
-      case 4: QZ_LAUNCH(ctx, sc_tail<4>, 1, SC_THREADS, 0, tabs, tb, size, pending, head, d_prog, d_consts, vinv, d_coeffs, d_lens, d_point, round, mc); break;
-      default: QZ_LAUNCH(ctx, sc_tail<0>, 1, SC_THREADS, 0, tabs, tb, size, pending, head, d_prog, d_consts, vinv, d_coeffs, d_lens, d_point, round, mc);
+      case 1: QZ_LAUNCH_PDL(ctx, pdl_ok && G == 1, sc_tail<1>, 1, SC_THREADS, tabs, tb, size, pending, head, d_prog, d_consts, vinv, d_coeffs, d_lens, d_point, round, mc); break;
+      case 2: QZ_LAUNCH_PDL(ctx, pdl_ok && G == 1, sc_tail<2>, 1, SC_THREADS, tabs, tb, size, pending, head, d_prog, d_consts, vinv, d_coeffs, d_lens, d_point, round, mc); break;
+      case 3: QZ_LAUNCH_PDL(ctx, pdl_ok && G == 1, sc_tail<3>, 1, SC_THREADS, tabs, tb, size, pending, head, d_prog, d_consts, vinv, d_coeffs, d_lens, d_point, round, mc); break;
+      case 4: QZ_LAUNCH_PDL(ctx, pdl_ok && G == 1, sc_tail<4>, 1, SC_THREADS, tabs, tb, size, pending, head, d_prog, d_consts, vinv, d_coeffs, d_lens, d_point, round, mc); break;
+      default: QZ_LAUNCH_PDL(ctx, pdl_ok && G == 1, sc_tail<0>, 1, SC_THREADS, tabs, tb, size, pending, head, d_prog, d_consts, vinv, d_coeffs, d_lens, d_point, round, mc);
     }
   }
   if (zerocheck && num_vars > 0) QZ_LAUNCH(ctx, zc_finish, 1, 1, 0, head, d_z, d_point, (int)num_vars);

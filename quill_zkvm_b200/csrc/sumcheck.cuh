@@ -190,6 +190,122 @@ static __device__ __noinline__ Fr tr_draw_fr_words(uint32_t* state) {
   return fp_add<FrParams>(fp_mul<FrParams>(r2, lo), fp_mul<FrParams>(r3, hi));
 }
 
+// ---- the same transcript on FOUR lanes -----------------------------------------------------------------------------------
+// One lane runs a compression in ~2500 cycles: ~1100 instructions from a warp that can issue every other cycle at best.
+// blake3's state is a 4x4 word matrix whose columns (then diagonals) are mixed independently, so lane i of a quad keeps
+// column i (a, b, c, d) = (v[i], v[4+i], v[8+i], v[12+i]): the column step is one G per lane, three shuffles rotate b, c, d
+// into the diagonals, one more G, three shuffles rotate back -- 7 x (2 G + 6 SHFL) ~ 300 instructions per lane.  The
+// chaining value stays spread over the lanes (cva = cv[i], cvb = cv[4+i]) from block to block.
+// Called by lanes 0..3 of a warp (mask 0xF); `m` points to 16 message words all four lanes can read (shared memory).
+// message schedule: nibble j of B3_SCHED[r] = index of the message word used at position j of round r
+__device__ constexpr uint64_t B3_SCHED[7] = {0xfedcba9876543210ull, 0x8fe95cb1d407a362ull, 0x18fb0956e72dca43ull,
+    0x61852b04fd3e9c7aull, 0x461035278eafb9dcull, 0x7462a03d1fc85be9ull,
+    0xd743c2ae689105fbull};
+QZ_DEV uint32_t b3_sched(int r, int j) { return (uint32_t)(B3_SCHED[r] >> (4 * j)) & 15u; }
+constexpr unsigned B3_QUAD = 0xFu;
+#define QZ_G4(mx, my)                       \
+  a = a + b + (mx);                         \
+  d = __funnelshift_r(d ^ a, d ^ a, 16);    \
+  c = c + d;                                \
+  b = __funnelshift_r(b ^ c, b ^ c, 12);    \
+  a = a + b + (my);                         \
+  d = __funnelshift_r(d ^ a, d ^ a, 8);     \
+  c = c + d;                                \
+  b = __funnelshift_r(b ^ c, b ^ c, 7);
+// (cva, cvb) <- words (lane, 4 + lane) of compress(cv, m, counter 0, block_len, flags); returns word 8 + lane of the
+// output block (the extended output the challenge squeeze reads)
+static __device__ __noinline__ uint32_t b3_compress_quad(uint32_t& cva, uint32_t& cvb, const uint32_t* m, uint32_t block_len,
+                                                         uint32_t flags) {
+  const int lane = threadIdx.x & 3, l1 = (lane + 1) & 3, l2 = (lane + 2) & 3, l3 = (lane + 3) & 3;
+  uint32_t w[7][4];
+#pragma unroll
+  for (int r = 0; r < 7; r++) {
+    w[r][0] = m[b3_sched(r, 2 * lane)];
+    w[r][1] = m[b3_sched(r, 2 * lane + 1)];
+    w[r][2] = m[b3_sched(r, 8 + 2 * lane)];
+    w[r][3] = m[b3_sched(r, 9 + 2 * lane)];
+  }
+  uint32_t a = cva, b = cvb, c = Blake3::iv(lane), d = lane == 2 ? block_len : lane == 3 ? flags : 0u;
+#pragma unroll
+  for (int r = 0; r < 7; r++) {
+    QZ_G4(w[r][0], w[r][1])
+    b = __shfl_sync(B3_QUAD, b, l1, 4);
+    c = __shfl_sync(B3_QUAD, c, l2, 4);
+    d = __shfl_sync(B3_QUAD, d, l3, 4);
+    QZ_G4(w[r][2], w[r][3])
+    b = __shfl_sync(B3_QUAD, b, l3, 4);
+    c = __shfl_sync(B3_QUAD, c, l2, 4);
+    d = __shfl_sync(B3_QUAD, d, l1, 4);
+  }
+  const uint32_t x = c ^ cva;
+  cva = a ^ c;
+  cvb = b ^ d;
+  return x;
+}
+#undef QZ_G4
+// single-chunk hash of buf[0 .. total_bytes/4) (zero padded to a multiple of 16 words, <= 1024 bytes) on a quad:
+// lane i ends with digest words (i, 4 + i) in (cva, cvb) and, in *x, word 8 + i of the root output block
+QZ_DEV void b3_single_chunk_quad(const uint32_t* buf, uint32_t total_bytes, uint32_t& cva, uint32_t& cvb, uint32_t* x) {
+  const int lane = threadIdx.x & 3;
+  cva = Blake3::iv(lane);
+  cvb = Blake3::iv(4 + lane);
+  const uint32_t nblocks = total_bytes == 0 ? 1 : (total_bytes + 63) / 64;
+  uint32_t xo = 0;
+#pragma unroll 1
+  for (uint32_t blk = 0; blk < nblocks; blk++) {
+    const bool last = blk + 1 == nblocks;
+    const uint32_t flags = (blk == 0 ? Blake3::F_CHUNK_START : 0u) | (last ? (Blake3::F_CHUNK_END | Blake3::F_ROOT) : 0u);
+    xo = b3_compress_quad(cva, cvb, buf + 16 * blk, last ? total_bytes - 64 * blk : 64u, flags);
+  }
+  if (x) *x = xo;
+}
+// Transcript::append_bytes on a quad: buf (shared) holds the message at [8, 8 + msg_bytes/4), zero padded to a block
+// boundary; state (8 words, any memory the quad can read and write) <- blake3(state ‖ msg).  32 + msg_bytes <= 1024.
+QZ_DEV void tr_absorb_quad(uint32_t* state, uint32_t* buf, uint32_t msg_bytes) {
+  const int lane = threadIdx.x & 3;
+  buf[lane] = state[lane];
+  buf[4 + lane] = state[4 + lane];
+  __syncwarp(B3_QUAD);
+  uint32_t cva, cvb;
+  b3_single_chunk_quad(buf, 32 + msg_bytes, cva, cvb, nullptr);
+  state[lane] = cva;
+  state[4 + lane] = cvb;
+  __syncwarp(B3_QUAD);
+}
+// draw_field_element::<Fr> (transcript.rs:49-75) on a quad; buf: 32 words of shared memory.  Every lane returns r.
+QZ_DEV Fr tr_draw_fr_quad(uint32_t* state, uint32_t* buf) {
+  const int lane = threadIdx.x & 3;
+  for (int i = lane; i < 32; i += 4) buf[i] = i < 8 ? state[i] : 0u;
+  __syncwarp(B3_QUAD);
+  if (lane == 0) {
+    buf[8] = 0x6c616863u;   // "chal"
+    buf[9] = 0x676e656cu;   // "leng"
+    buf[10] = 0x00000065u;  // "e"
+  }
+  __syncwarp(B3_QUAD);
+  uint32_t cva, cvb, x;
+  b3_single_chunk_quad(buf, 41, cva, cvb, &x);  // 48 bytes of extended output: words lane, 4 + lane, 8 + lane
+  __syncwarp(B3_QUAD);
+  buf[8 + lane] = cva;
+  buf[12 + lane] = cvb;
+  buf[16 + lane] = x;
+  __syncwarp(B3_QUAD);
+  uint32_t na, nb;
+  b3_single_chunk_quad(buf, 80, na, nb, nullptr);  // re-absorb the 48 challenge bytes (transcript.rs:60)
+  state[lane] = na;
+  state[4 + lane] = nb;
+  Fr lo, hi, r2, r3;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    lo.v[i] = buf[8 + i];
+    hi.v[i] = i < 4 ? buf[16 + i] : 0u;
+    r2.v[i] = FrParams::R2(i);
+    r3.v[i] = FrParams::R3(i);
+  }
+  __syncwarp(B3_QUAD);
+  return fp_add<FrParams>(fp_mul<FrParams>(r2, lo), fp_mul<FrParams>(r3, hi));
+}
+
 // ---- reductions ------------------------------------------------------------------------------------------------------
 QZ_DEV Fr warp_sum(Fr v) {
 #pragma unroll
@@ -284,18 +400,24 @@ QZ_DEV void sc_round_close(ScHead* head, const Fr* vinv, int d, const Fr* s_eval
     out_coeffs_row[t] = fp_zero<FrParams>();
   }
   __syncthreads();
-  if (t == 0) {
-    int len = d + 1;
-    while (len > 0 && fp_is_zero<FrParams>(s_coef[len - 1])) len--;  // DensePolynomial trims trailing zeros
-    *out_len = (uint32_t)len;
-    s_msg[8] = (uint32_t)len;  // u64 LE length prefix
-    s_msg[9] = 0;
-    for (int i = 10 + 8 * len; i < ((10 + 8 * len + 15) / 16) * 16; i++) s_msg[i] = 0;  // pad the last block
+  if (t < 4) {  // the transcript runs on lanes 0..3 of warp 0 (tr_*_quad)
+    if (t == 0) {
+      int len = d + 1;
+      while (len > 0 && fp_is_zero<FrParams>(s_coef[len - 1])) len--;  // DensePolynomial trims trailing zeros
+      *out_len = (uint32_t)len;
+      s_msg[8] = (uint32_t)len;  // u64 LE length prefix
+      s_msg[9] = 0;
+      for (int i = 10 + 8 * len; i < ((10 + 8 * len + 15) / 16) * 16; i++) s_msg[i] = 0;  // pad the last block
+    }
+    __syncwarp(B3_QUAD);
+    const uint32_t len = s_msg[8];
     uint32_t* state = reinterpret_cast<uint32_t*>(head->tstate);
-    tr_absorb_words(state, s_msg, 8 + 32 * len);  // :73
-    Fr r = tr_draw_fr_words(state);               // :77
-    head->r = r;
-    *out_point_slot = r;
+    tr_absorb_quad(state, s_msg, 8 + 32 * len);  // :73
+    const Fr r = tr_draw_fr_quad(state, s_msg);   // :77
+    if (t == 0) {
+      head->r = r;
+      *out_point_slot = r;
+    }
   }
   __syncthreads();
 }

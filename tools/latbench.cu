@@ -28,6 +28,26 @@ __global__ void klat(uint32_t* state_g, long long* t, Fr* sink) {
   t[0] = t1 - t0; t[1] = t2 - t1; t[2] = t3 - t2; t[3] = t4 - t3; t[4] = t5 - t4;
 }
 
+// the same transcript steps on four lanes (tr_*_quad)
+__global__ void klat4(uint32_t* state_g, long long* t, Fr* sink) {
+  __shared__ uint32_t s_msg[SC_MSG_WORDS];
+  if (threadIdx.x >= 4) return;
+  for (int i = threadIdx.x; i < SC_MSG_WORDS; i += 4) s_msg[i] = i * 2654435761u;
+  __syncwarp(B3_QUAD);
+  for (int i = 10 + 32 + threadIdx.x; i < 48; i += 4) s_msg[i] = 0;
+  __syncwarp(B3_QUAD);
+  long long t0 = clock64();
+  tr_absorb_quad(state_g, s_msg, 8 + 32 * 4);
+  long long t1 = clock64();
+  Fr r = tr_draw_fr_quad(state_g, s_msg);
+  long long t2 = clock64();
+  if (threadIdx.x == 0) {
+    *sink = r;
+    t[0] = t1 - t0;
+    t[1] = t2 - t1;
+  }
+}
+
 int main() {
   uint32_t* st; long long* t; Fr* sink;
   cudaMalloc(&st, 32); cudaMalloc(&t, 64); cudaMalloc(&sink, 32);
@@ -38,6 +58,12 @@ int main() {
     cudaMemcpy(h, t, 40, cudaMemcpyDeviceToHost);
     printf("absorb(3 blocks) %lld cyc | draw_fr %lld cyc | 8 dependent mul %lld cyc | 8 mul+add %lld | 1 compress %lld cyc   %s\n", h[0], h[1], h[2], h[3], h[4],
            cudaGetErrorString(cudaGetLastError()));
+  }
+  for (int rep = 0; rep < 3; rep++) {
+    klat4<<<1, 32>>>(st, t, sink);
+    long long h[2];
+    cudaMemcpy(h, t, 16, cudaMemcpyDeviceToHost);
+    printf("four lanes: absorb(3 blocks) %lld cyc | draw_fr %lld cyc   %s\n", h[0], h[1], cudaGetErrorString(cudaGetLastError()));
   }
   return 0;
 }
