@@ -183,6 +183,88 @@ __global__ void __launch_bounds__(128) msm_partials_reduce(const uint32_t* pkeys
   }
 }
 
+// Last levels in one launch: once the list is short (<= FIN_SLOTS) the level-by-level rule is pure latency (each level
+// a launch plus up to PART_CHUNK dependent additions for a handful of runs: ~33 us x 7 levels at 2^21 points).  One
+// block compacts the non-empty slots and runs a segmented Hillis-Steele scan over them -- keys ascend, so slot i may
+// add slot i-d whenever their keys are equal -- stopping as soon as a step adds nothing (runs at this depth are
+// mostly pairs: two or three steps).  The last slot of every run then holds the bucket.
+constexpr int FIN_SLOTS = 2048, FIN_THREADS = 512;  // 512 threads: the full addition needs ~128 registers
+__global__ void __launch_bounds__(FIN_THREADS) msm_partials_finish(const uint32_t* pkeys_in, const uint8_t* ppts_in,
+                                                                   int n_in, int c, uint8_t* buckets, uint8_t* scratch_a,
+                                                                   uint8_t* scratch_b) {
+  __shared__ uint32_t ck[FIN_SLOTS];
+  __shared__ uint16_t src[FIN_SLOTS];
+  __shared__ int warp_tot[FIN_THREADS / 32];
+  __shared__ int s_m;
+  constexpr int PER = FIN_SLOTS / FIN_THREADS;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  // compact: thread t owns slots [t * PER, t * PER + PER)
+  uint32_t k[PER];
+  int cnt = 0;
+#pragma unroll
+  for (int j = 0; j < PER; j++) {
+    const int i = t * PER + j;
+    k[j] = i < n_in ? pkeys_in[i] : KEY_NONE;
+    cnt += k[j] != KEY_NONE;
+  }
+  int incl = cnt;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += v;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int v = lane < FIN_THREADS / 32 ? warp_tot[lane] : 0;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, v, off);
+      if (lane >= off) v += u;
+    }
+    if (lane < FIN_THREADS / 32) warp_tot[lane] = v;  // inclusive totals per warp
+    if (lane == 31) s_m = v;
+  }
+  __syncthreads();
+  int pos = incl - cnt + (warp ? warp_tot[warp - 1] : 0);
+#pragma unroll
+  for (int j = 0; j < PER; j++)
+    if (k[j] != KEY_NONE) {
+      ck[pos] = k[j];
+      src[pos] = (uint16_t)(t * PER + j);
+      pos++;
+    }
+  __syncthreads();
+  const int m = s_m;
+  // segmented inclusive scan over the m compacted slots; step 0 reads the input list through src[]
+  const uint8_t* in = nullptr;
+  uint8_t* out = scratch_a;
+  for (int d = 1; d < m || d == 1; d <<= 1) {
+    int added = 0;
+    for (int i = t; i < m; i += FIN_THREADS) {
+      Xyzz a;
+      xyzz_load(a, in ? in + (size_t)i * 128 : ppts_in + (size_t)src[i] * 128);
+      if (i >= d && ck[i - d] == ck[i]) {
+        Xyzz b;
+        xyzz_load(b, in ? in + (size_t)(i - d) * 128 : ppts_in + (size_t)src[i - d] * 128);
+        a = xyzz_add(a, b);
+        added = 1;
+      }
+      xyzz_store(out + (size_t)i * 128, a);
+    }
+    const int any = __syncthreads_or(added);  // also orders this step's stores before the next step's loads
+    in = out;
+    out = out == scratch_a ? scratch_b : scratch_a;
+    if (!any) break;
+  }
+  for (int i = t; i < m; i += FIN_THREADS)
+    if (i + 1 == m || ck[i + 1] != ck[i]) {
+      Xyzz a;
+      xyzz_load(a, in + (size_t)i * 128);
+      xyzz_store(buckets + (size_t)bucket_slot(ck[i], c) * 128, a);
+    }
+}
+
 // streamed MSM: every segment of the points filled its own copy of the bucket sets; add copies 1 .. S-1 into copy 0
 __global__ void __launch_bounds__(128) msm_bucket_merge(uint8_t* buckets, uint32_t n_slots, int S) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -574,9 +656,12 @@ int msm_run(qz_ctx* ctx, const qz_srs* srs, uint4* scalars_dev, const void* scal
   uint32_t* pkeys_a = (uint32_t*)ctx->arena_alloc(n_part0 * 4);
   uint8_t* ppts_b = (uint8_t*)ctx->arena_alloc(n_part1 * 128);
   uint32_t* pkeys_b = (uint32_t*)ctx->arena_alloc(n_part1 * 4);
+  uint8_t* fin_a = (uint8_t*)ctx->arena_alloc((size_t)FIN_SLOTS * 128);
+  uint8_t* fin_b = (uint8_t*)ctx->arena_alloc((size_t)FIN_SLOTS * 128);
   // small problems are latency-bound: shorter running-sum segments (more threads, shorter dependent chains)
   // large bucket sets: one wave of threads (2^15 x 64 buckets at c = 22) beats two waves of shorter chains
-  const int seg_want = n_slots <= (1u << 17) ? 8 : n_slots >= (1u << 21) ? 2 * RED_SEG : RED_SEG;
+  // (2^19 buckets, one rank's share of 2^24 points on 8 GPUs: 16K threads walking 32 buckets are latency-bound, 0.63 ms)
+  const int seg_want = n_slots <= (1u << 17) ? 8 : n_slots <= (1u << 19) ? RED_SEG / 2 : n_slots >= (1u << 21) ? 2 * RED_SEG : RED_SEG;
   const int seg = per_w >= (uint32_t)seg_want ? seg_want : (int)per_w;
   const uint32_t red_threads = n_slots / seg, per_window_parts = per_w / seg;
   uint8_t* partial = (uint8_t*)ctx->arena_alloc((size_t)red_threads * 128);
@@ -588,7 +673,7 @@ int msm_run(qz_ctx* ctx, const qz_srs* srs, uint4* scalars_dev, const void* scal
     cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, dk, dv, (int64_t)((uint64_t)Wd * max_seg), 0, key_bits, ps);
   }
   void* sort_tmp = ctx->arena_alloc(sort_bytes);  // shared: the segments' sorts are serialised on the prep stream
-  if (!keys || !vals || !keys2 || !vals2 || !buckets || !ppts_a || !pkeys_a || !ppts_b || !pkeys_b || !partial ||
+  if (!keys || !vals || !keys2 || !vals2 || !buckets || !ppts_a || !pkeys_a || !ppts_b || !pkeys_b || !fin_a || !fin_b || !partial ||
       !partial2 || !window_sums || !sort_tmp)
     return ctx->fail(QZ_ERR_ALLOC, "MSM scratch");
 
@@ -626,6 +711,10 @@ int msm_run(qz_ctx* ctx, const qz_srs* srs, uint4* scalars_dev, const void* scal
     uint8_t* pout = ppts_b;
     uint64_t n_in = n_part0;
     while (true) {
+      if (n_in <= (uint64_t)FIN_SLOTS && n_in > PART_CHUNK) {  // short list: scan it in one launch
+        QZ_LAUNCH(ctx, msm_partials_finish, 1, FIN_THREADS, 0, kin, pin, (int)n_in, c, buckets, fin_a, fin_b);
+        break;
+      }
       const uint64_t chunks = (n_in + PART_CHUNK - 1) / PART_CHUNK;
       const int last_level = chunks == 1;
       QZ_LAUNCH(ctx, msm_partials_reduce, (unsigned)((chunks + 127) / 128), 128, 0, kin, pin, n_in, c, buckets, kout, pout,
