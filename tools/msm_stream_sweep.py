@@ -46,8 +46,8 @@ def main():
         return ev0.elapsed_time(ev1) / steps, sum(acc) / len(acc), r
 
     ref = None
-    for var, arg, settings in (("QZ_MSM_SEGMENTS_DEV", dev, ["1", "1,1", "1,2", "1,1,1,1", "1,3,6"]),
-                               ("QZ_MSM_SEGMENTS", host, ["1", "1,1", "1,2,4", "2,5,12", "1,2.5,6,12", "1,3,9", "1,1,1,1"])):
+    for var, arg, settings in (("QZ_MSM_SEGMENTS_DEV", dev, ["1", "1,1"]),
+                               ("QZ_MSM_SEGMENTS", host, ["1", "1,3,9", "1,4,12", "1,4,16", "1,3.5,10", "2,7,20", "1,5"])):
         for s in settings:
             os.environ[var] = s
             ms, acc, r = timed(lambda: kzg.commit(arg))
