@@ -16,4 +16,15 @@ def timed_loop(fn, steps, warmup):
     ctx.sync(); t=time.perf_counter(); l0=ctx.kernel_launches
     for _ in range(steps): fn()
     ctx.sync(); return (time.perf_counter()-t)*1e3/steps, ctx.kernel_launches-l0
-print(bench.bench_hyperplonk(ctx, q, K, g, mont(bench.TAU), timed_loop))
+REPS = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+def timed_loop_reps(fn, steps, warmup):
+    for _ in range(warmup): fn()
+    out = []
+    for _ in range(REPS):
+        ctx.sync(); t=time.perf_counter(); l0=ctx.kernel_launches
+        fn()
+        ctx.sync(); out.append(round((time.perf_counter()-t)*1e3, 1))
+    print("per-proof ms:", out)
+    return min(out), ctx.kernel_launches-l0
+r = bench.bench_hyperplonk(ctx, q, K, g, mont(bench.TAU), timed_loop_reps if REPS > 1 else timed_loop)
+print({k: r[k] for k in ("value", "rows_per_trace", "gpu_launches")})
