@@ -73,9 +73,13 @@ int qz_ctx_sync(qz_ctx* ctx);                 /* cudaStreamSynchronize on the co
 /* number of kernels this library launched on the context since creation (bench accounting) */
 uint64_t qz_kernel_launches(const qz_ctx* ctx);
 
-/* device buffers for callers that keep inputs resident (the kernel-only bench leg; a shim may ignore these) */
+/* device buffers for callers that keep inputs resident (the kernel-only bench leg; a shim may ignore these).
+ * qz_dev_free parks the block in the context's pool for the next qz_dev_alloc of (about) that size instead of calling
+ * cudaFree -- a device-wide synchronisation a prover would otherwise pay a dozen times per proof; qz_dev_trim returns
+ * the parked blocks to the driver (qz_ctx_destroy does too). */
 int qz_dev_alloc(qz_ctx* ctx, size_t bytes, void** out_dev);
 int qz_dev_free(qz_ctx* ctx, void* dev);
+int qz_dev_trim(qz_ctx* ctx);
 int qz_dev_upload(qz_ctx* ctx, void* dev, const void* host, size_t bytes);   /* H2D, synchronous on return */
 int qz_dev_download(qz_ctx* ctx, void* host, const void* dev, size_t bytes); /* D2H, synchronous on return */
 /* fill dev with n pseudo-random Fr elements (Montgomery form of uniformly-spread values < r), seeded */

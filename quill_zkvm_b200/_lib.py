@@ -17,7 +17,7 @@ QZ_MAX_ROUND_COEFFS = 33
 # every symbol include/quill_b200.h declares (tests check the .so exports each one)
 SYMBOLS = [
     "qz_ctx_create", "qz_ctx_destroy", "qz_status_str", "qz_last_error", "qz_ctx_sync", "qz_kernel_launches",
-    "qz_dev_alloc", "qz_dev_free", "qz_dev_upload", "qz_dev_download", "qz_dev_random_fr",
+    "qz_dev_alloc", "qz_dev_free", "qz_dev_trim", "qz_dev_upload", "qz_dev_download", "qz_dev_random_fr",
     "qz_transcript_new", "qz_transcript_append_bytes", "qz_transcript_draw_challenge", "qz_transcript_draw_fr",
     "qz_transcript_append_fr", "qz_transcript_append_g1", "qz_g1_serialize",
     "qz_srs_upload", "qz_srs_generate", "qz_srs_precompute", "qz_srs_free", "qz_srs_len", "qz_srs_download",
@@ -69,6 +69,7 @@ def load():
     lib.qz_kernel_launches.restype = u64
     lib.qz_dev_alloc.argtypes = [vp, sz, C.POINTER(vp)]
     lib.qz_dev_free.argtypes = [vp, vp]
+    lib.qz_dev_trim.argtypes = [vp]
     lib.qz_dev_upload.argtypes = [vp, vp, vp, sz]
     lib.qz_dev_download.argtypes = [vp, vp, vp, sz]
     lib.qz_dev_random_fr.argtypes = [vp, vp, sz, u64]

@@ -80,6 +80,10 @@ class Context:
         self.check(self.lib.qz_dev_alloc(self.h, nbytes, C.byref(p)))
         return DeviceBuffer(self, p.value, nbytes)
 
+    def trim(self):
+        """Return the device blocks parked by DeviceBuffer.free() to the driver (they are otherwise reused)."""
+        self.check(self.lib.qz_dev_trim(self.h))
+
     def upload(self, host: np.ndarray) -> "DeviceBuffer":
         host = _u8(host)
         buf = self.alloc(host.nbytes)

@@ -232,6 +232,7 @@ void qz_ctx_destroy(qz_ctx* c) {
   comm_destroy(c);
   for (auto& b : c->blocks) cudaFree(b.p);
   for (auto& kv : c->cache) cudaFree(kv.second);
+  c->pool_trim();
   if (c->pinned) cudaFreeHost(c->pinned);
   cudaEventDestroy(c->ev_call0);
   cudaEventDestroy(c->ev_call1);
@@ -256,13 +257,21 @@ int qz_ctx_sync(qz_ctx* c) {
 int qz_dev_alloc(qz_ctx* c, size_t bytes, void** out) {
   if (!c || !out) return QZ_ERR_INVALID_ARG;
   QZ_CUDA(c, cudaSetDevice(c->device));
-  cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
-  if (e != cudaSuccess) return c->fail(QZ_ERR_ALLOC, "cudaMalloc", e);
+  *out = c->pool_alloc(bytes);
+  if (!*out) return c->fail(QZ_ERR_ALLOC, "cudaMalloc");
   return QZ_OK;
 }
 int qz_dev_free(qz_ctx* c, void* p) {
   if (!c) return QZ_ERR_INVALID_ARG;
-  QZ_CUDA(c, cudaFree(p));
+  QZ_CUDA(c, cudaSetDevice(c->device));
+  QZ_CUDA(c, c->pool_release(p));
+  return QZ_OK;
+}
+int qz_dev_trim(qz_ctx* c) {
+  if (!c) return QZ_ERR_INVALID_ARG;
+  QZ_CUDA(c, cudaSetDevice(c->device));
+  QZ_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->pool_trim();
   return QZ_OK;
 }
 int qz_dev_upload(qz_ctx* c, void* dev, const void* host, size_t bytes) {

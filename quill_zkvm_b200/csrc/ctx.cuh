@@ -30,6 +30,47 @@ struct qz_ctx {
   };
   std::vector<Block> blocks;
 
+  // Device buffers handed to the caller (qz_dev_alloc / the S polynomial of qz_mlpcs_open_begin) come from a pool:
+  // qz_dev_free parks a block here instead of calling cudaFree, which is a device-wide synchronisation and, on a
+  // prover that allocates and frees the same few hundred MiB per proof, was measured at 0.2 .. 2.5 s per HyperPlonk
+  // proof (and growing).  A request reuses the smallest parked block that is large enough and at most 1/8 larger.
+  std::multimap<size_t, void*> pool_parked;
+  std::map<void*, size_t> pool_live;
+  void pool_trim() {
+    for (auto& kv : pool_parked) cudaFree(kv.second);
+    pool_parked.clear();
+  }
+  void* pool_alloc(size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes == 0) bytes = 256;
+    auto it = pool_parked.lower_bound(bytes);
+    if (it != pool_parked.end() && it->first <= bytes + bytes / 8 + ((size_t)1 << 16)) {
+      void* p = it->second;
+      pool_live[p] = it->first;
+      pool_parked.erase(it);
+      return p;
+    }
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      pool_trim();  // give the parked blocks back and try once more
+      if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+      }
+    }
+    pool_live[p] = bytes;
+    return p;
+  }
+  cudaError_t pool_release(void* p) {
+    if (!p) return cudaSuccess;
+    auto it = pool_live.find(p);
+    if (it == pool_live.end()) return cudaFree(p);  // not ours (e.g. allocated before the pool existed)
+    pool_parked.emplace(it->second, p);
+    pool_live.erase(it);
+    return cudaSuccess;
+  }
+
   // cached device constants: interpolation matrices keyed by degree (< 1000), NTT twiddle tables keyed by 1000 + log2 size
   std::map<int, void*> cache;
 

@@ -212,19 +212,14 @@ __global__ void mlpcs_transcript(uint8_t* state, const Fr* point, int n, const F
 
 // ---- host side ---------------------------------------------------------------------------------------------------------------
 static int get_twiddles(qz_ctx* ctx, int log_m, Fr** out) {
-  // cached per context (same map as the interpolation matrices, keys offset by 1000) for the last size used
+  // cached per context (same map as the interpolation matrices, keys offset by 1000), one table per size and never
+  // evicted: a prover alternates between a few sizes (HyperPlonk: 2^21, 2^23, 2^24 within one proof) and rebuilding the
+  // table at every switch cost a cudaFree (device-wide synchronisation) + cudaMalloc + the kernel.  All sizes together
+  // are at most twice the largest table (256 MiB at 2^24).
   auto it = ctx->cache.find(1000 + log_m);
   if (it != ctx->cache.end()) {
     *out = (Fr*)it->second;
     return QZ_OK;
-  }
-  for (auto i = ctx->cache.begin(); i != ctx->cache.end();) {  // keep one table at a time (up to 2 GiB at 2^27)
-    if (i->first >= 1000) {
-      cudaFree(i->second);
-      i = ctx->cache.erase(i);
-    } else {
-      ++i;
-    }
   }
   const uint64_t count = log_m ? ((uint64_t)1 << (log_m - 1)) : 1;
   void* p = nullptr;
@@ -467,9 +462,9 @@ int qz_mlpcs_open_begin(qz_ctx* ctx, const qz_srs* srs, const void* poly, size_t
   Fr* d_point = (Fr*)ctx->arena_alloc(32 * std::max<size_t>(n_point, 1));
   uint4* d_pr = (uint4*)ctx->arena_alloc(32 * pr_full);
   if (!res || !d_point || !d_pr) return ctx->fail(QZ_ERR_ALLOC, "mlpcs state");
-  void* s_dev = nullptr;  // outlives the call: owned by the caller (qz_dev_free)
-  cudaError_t e = cudaMalloc(&s_dev, 32 * std::max<uint64_t>(std::max<uint64_t>(n, pr_full), 1));
-  if (e != cudaSuccess) return ctx->fail(QZ_ERR_ALLOC, "S polynomial", e);
+  // outlives the call: owned by the caller (qz_dev_free)
+  void* s_dev = ctx->pool_alloc(32 * std::max<uint64_t>(std::max<uint64_t>(n, pr_full), 1));
+  if (!s_dev) return ctx->fail(QZ_ERR_ALLOC, "S polynomial");
   QZ_CUDA(ctx, cudaMemsetAsync(res, 0, 96, st));
   const uint4* pdev = nullptr;
   int rc = mlpcs_poly_on_device(ctx, poly, n, on_device, &pdev);
@@ -479,7 +474,7 @@ int qz_mlpcs_open_begin(qz_ctx* ctx, const qz_srs* srs, const void* poly, size_t
   if (!rc && !pin) rc = ctx->fail(QZ_ERR_ALLOC, "pinned");
   if (rc) {
     cudaStreamSynchronize(st);
-    cudaFree(s_dev);
+    ctx->pool_release(s_dev);
     return rc;
   }
   QZ_CUDA(ctx, cudaMemcpyAsync(pin, res, 96, cudaMemcpyDeviceToHost, st));
