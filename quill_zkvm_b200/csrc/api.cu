@@ -216,7 +216,7 @@ int qz_ctx_create(int device, void* stream, qz_ctx** out) {
     }
     c->own_stream = true;
   }
-  c->pdl = getenv("QZ_PDL") != nullptr;  // opt-in, see ctx.cuh
+  c->pdl = getenv("QZ_NO_PDL") == nullptr;
   cudaEventCreate(&c->ev_call0);
   cudaEventCreate(&c->ev_call1);
   cudaEventCreate(&c->ev_k0);

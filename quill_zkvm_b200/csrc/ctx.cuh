@@ -15,11 +15,10 @@ struct qz_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int sm_count = 148;
-  // programmatic dependent launches for the sumcheck round chain: OFF unless QZ_PDL=1.  Measured on B200: -5 us per
-  // latency-bound round of a product sumcheck (2^16 proof 463 -> 440 us, 2^24 proof -28 us), but HyperPlonk's chains of
-  // generic-expression rounds then show erratic stalls (2^20-row proof 2.27 +- 0.03 s without, 2.5 .. 5.3 s with), so
-  // the default is the ordinary launch.
-  bool pdl = false;
+  // programmatic dependent launches for the latency-bound rounds of the sumcheck chain (QZ_NO_PDL=1 turns them off).
+  // Measured on B200 (tools/sc_pdl_ab.py): -5 us per such round (2^16 product proof 463 -> 440 us, 2^24 proof -28 us);
+  // HyperPlonk's generic-expression chains are unaffected (2^20-row proof 2.215 s either way).
+  bool pdl = true;
   std::string err;
   uint64_t launches = 0;
 
@@ -207,8 +206,8 @@ struct qz_ctx {
 // Programmatic dependent launch for chains of short dependent kernels (the sumcheck rounds): the kernel may become
 // resident while its predecessor in the stream still runs and parks at grid_dep_wait(), so launch processing and block
 // scheduling overlap the predecessor instead of following it.  Kernels launched this way MUST call grid_dep_wait()
-// before touching anything the predecessor writes; the call is a no-op under an ordinary launch.  `pdl` false (the
-// default: QZ_PDL unset when the context was created) degrades to an ordinary launch.
+// before touching anything the predecessor writes; the call is a no-op under an ordinary launch.  `pdl` false (or
+// QZ_NO_PDL set when the context was created) degrades to an ordinary launch.
 #define QZ_LAUNCH_PDL(ctx, pdl, kernel, grid, block, ...)                                  \
   do {                                                                                     \
     cudaLaunchConfig_t cfg_ = {};                                                          \

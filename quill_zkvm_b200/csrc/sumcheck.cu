@@ -834,7 +834,7 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
     uint64_t size = N;  // current (pre-fold) table size
     int pending = 0, round = 0, flip = 0;
     // the round chain uses programmatic dependent launches, except around NCCL collectives (not written for them)
-    // Opt-in (QZ_PDL=1, see ctx.cuh).  Measured (tools/sc_pdl_ab.py): -5 us per round while a round is latency-bound,
+    // Measured (tools/sc_pdl_ab.py): -5 us per round while a round is latency-bound,
     // but +10..20 us on the rounds that stream 2^21 entries or more, so only the short rounds are chained this way.
     const bool pdl_ok = ctx->pdl && (G == 1 || comm_has_peers(ctx));
     ctx->kernel_ms_accum = 0.f;

@@ -1,4 +1,4 @@
-"""A/B of programmatic dependent launches in the sumcheck round chain: two contexts in one process (QZ_PDL is read
+"""A/B of programmatic dependent launches in the sumcheck round chain: two contexts in one process (QZ_NO_PDL is read
 when a context is created), alternated so that clocks and thermals are shared."""
 import os
 import sys
@@ -13,9 +13,9 @@ from bench import product_expr  # noqa: E402
 
 def main():
     stream = torch.cuda.Stream()
-    os.environ["QZ_PDL"] = "1"
+    os.environ.pop("QZ_NO_PDL", None)
     ctx_a = q.Context(0, stream.cuda_stream)
-    os.environ.pop("QZ_PDL", None)
+    os.environ["QZ_NO_PDL"] = "1"
     ctx_b = q.Context(0, stream.cuda_stream)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     claimed = np.zeros(32, np.uint8)
