@@ -32,7 +32,7 @@ SC_BYTES_PER_ELEM = 128              # 4 * 32 B per input table ele
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the last ncu --set full captures (profiles/r01_ncu_*.txt,
 # 2^24, one GPU): msm_accumulate 27.96 + 1.11 GB (algorithmic 14.5 GB: a 64-byte gather fetches a 128-byte line);
 # sumcheck streaming rounds: round 0 = 1.614 GB, round 1 = 2.392 GB, later rounds halve -> 6.40 GB (algorithmic 6.44 GB)
-MSM_TRAFFIC_BYTES = 29.07e9
+MSM_TRAFFIC_BYTES = 28.90e9
 SC_TRAFFIC_BYTES = 6.40e9
 
 

@@ -138,14 +138,18 @@ __global__ void __launch_bounds__(256) s_pointwise(const uint4* A, const uint4* 
   }
   fp_store<FrParams>(H + 2 * p, t);
 }
-// S[k] = h[L + k] / m, k < L - 1
-__global__ void __launch_bounds__(256) s_extract(const uint4* h, uint64_t L, int log_m, uint4* S) {
-  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k + 1 >= L) return;
+// S[k] = h[L + k] / m, k < L - 1.  1/m = (1/2)^log_m is computed once (s_minv), not by every thread.
+__global__ void s_minv(int log_m, Fr* out) {
   Fr inv2, minv = fp_one<FrParams>();
 #pragma unroll
   for (int i = 0; i < 8; i++) inv2.v[i] = FrParams::INV2(i);
   for (int i = 0; i < log_m; i++) minv = fp_mul<FrParams>(minv, inv2);
+  *out = minv;
+}
+__global__ void __launch_bounds__(256) s_extract(const uint4* h, uint64_t L, const Fr* minv_p, uint4* S) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k + 1 >= L) return;
+  const Fr minv = *minv_p;
   fp_store<FrParams>(S + 2 * k, fp_mul<FrParams>(fp_load<FrParams>(h + 2 * (L + k)), minv));
 }
 // sum_i a[i] * b[i], i < n: one partial per block, then `inner_product_final`
@@ -271,7 +275,8 @@ int s_polynomial_device(qz_ctx* ctx, const uint4* f, size_t n, const uint4* g, s
   uint4* A = (uint4*)ctx->arena_alloc(32 * M);
   uint4* B = (uint4*)ctx->arena_alloc(32 * M);
   uint4* H = (uint4*)ctx->arena_alloc(32 * M);
-  if (!A || !B || !H) return ctx->fail(QZ_ERR_ALLOC, "NTT buffers");
+  Fr* minv = (Fr*)ctx->arena_alloc(32);
+  if (!A || !B || !H || !minv) return ctx->fail(QZ_ERR_ALLOC, "NTT buffers");
   cudaStream_t st = ctx->stream;
   QZ_CUDA(ctx, cudaMemsetAsync(A, 0, 32 * M, st));
   QZ_CUDA(ctx, cudaMemsetAsync(B, 0, 32 * M, st));
@@ -287,7 +292,8 @@ int s_polynomial_device(qz_ctx* ctx, const uint4* f, size_t n, const uint4* g, s
   QZ_LAUNCH(ctx, s_pointwise, (unsigned)((M + 255) / 256), 256, 0, A, B, H, log_m, L - 1, W);
   rc = ntt_device(ctx, H, log_m, true);
   if (rc) return rc;
-  QZ_LAUNCH(ctx, s_extract, (unsigned)((L + 255) / 256), 256, 0, H, L, log_m, S);
+  QZ_LAUNCH(ctx, s_minv, 1, 1, 0, log_m, minv);
+  QZ_LAUNCH(ctx, s_extract, (unsigned)((L + 255) / 256), 256, 0, H, L, (const Fr*)minv, S);
   ctx->arena_release(mark);
   return QZ_OK;
 }
