@@ -364,6 +364,13 @@ def run_gpu(args):
     sc_ms, sc_launches = timed_loop(lambda: prove(st_dev, "dev"), args.steps, args.warmup, rounds_ms)
     sc_e2e_ms, _ = timed_loop(lambda: prove(st_host, "host"), args.steps, args.warmup)
     assert sc_out["dev_state"].tobytes() == sc_out["host_state"].tobytes()
+    # zero-check form of the same workload (config 3): eq table built on the device as a fourth factor, degree 4
+    zc_ms = None
+    if world == 1:
+        def zc_prove():
+            sc_out["zc"] = q.ZeroCheckProof.prove(ctx, st_dev, 0, q.Transcript(b"zerocheck_bench", ctx))
+
+        zc_ms, zc_launches = timed_loop(zc_prove, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
 
     # (the nvidia-smi sampler is stopped first: its 200 ms polling contends for the driver and slows these
@@ -441,6 +448,11 @@ def run_gpu(args):
             "gpu_launches": msm_launches // args.steps,
             "clocks": clocks,
         }
+        if zc_ms is not None:
+            line["zerocheck"] = {"value": 3 * n / (zc_ms * 1e-3), "unit": "field-elems/s", "ms_per_step": zc_ms,
+                                 "gpu_launches": zc_launches // args.steps,
+                                 "workload": f"ZeroCheckProof::prove of f*g*e over three 2^{args.log_n}-entry tables: z drawn and the eq "
+                                             "table built on the device, degree-4 rounds over four tables"}
         if mlpcs:
             line["mlpcs_commit_open"] = mlpcs
         if hplonk:

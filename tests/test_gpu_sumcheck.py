@@ -237,6 +237,37 @@ def test_baseline_sizes_product3(ctx, n):
     assert ok and np.array_equal(ve, claim2.evaluation)
 
 
+@pytest.mark.parametrize("n", [20, 24])
+def test_baseline_sizes_zerocheck_product3(ctx, n):
+    """BASELINE.json config 3, zero-check form: h = f * g * e with the eq table as a fourth factor (degree 4), z drawn on
+    the device, tables resident on the device; every round polynomial, z, the point, the claim (already divided by
+    eq(z, r), zerocheck.rs:34-40) and the transcript state against the oracle on all host cores."""
+    bufs = [ctx.random_fr(1 << n, 2000 + t) for t in range(3)]
+    tabs = [b.download().reshape(-1, 32) for b in bufs]
+    nodes, consts = util.expr_product(3)
+    store = q.VirtualPolynomialStore(n)
+    for b in bufs:
+        store.allocate_polynomial(b)
+    h = store.new_virtual_from_expr(util.to_qexpr(nodes, consts))
+    tr = q.Transcript(b"zerocheck_bench", ctx)
+    proof, claim = q.ZeroCheckProof.prove(ctx, store, h, tr)
+    for b in bufs:
+        b.free()
+    st = co.transcript_new(b"zerocheck_bench")
+    o = co.sumcheck_prove(n, tabs, nodes, consts, None, st, max_coeffs=q._lib.QZ_MAX_ROUND_COEFFS, zerocheck=True,
+                          threads=NCPU)
+    sc = proof.sumcheck_proof
+    assert [p.shape[0] for p in sc.r_polys] == o["lens"].tolist()
+    for j in range(n):
+        assert np.array_equal(sc.r_polys[j], o["coeffs"][j][: o["lens"][j]]), f"round {j}"
+    assert np.array_equal(proof.z, o["z"]) and np.array_equal(claim.point, o["point"])
+    assert np.array_equal(claim.evaluation, o["evaluation"]) and tr.state.tobytes() == st.tobytes()
+    # the claim is h at the point: the product of the three tables' MLE evaluations (zerocheck.rs:142-158)
+    evs = [co.mle_evaluate(t, claim.point) for t in tabs]
+    prod = co.field_op(0, 2, co.field_op(0, 2, evs[0], evs[1]), evs[2])
+    assert np.array_equal(prod.reshape(32), claim.evaluation)
+
+
 def test_2_26_product3_verifier_and_mle(ctx):
     """the upper end of north_star's range (2^16..2^26; 3 x 2 GiB of tables).  The oracle prover would take minutes, so
     this checks the size-independent properties: the reference's verifier (sumcheck.rs:116-150) accepts the transcript
