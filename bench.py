@@ -451,8 +451,9 @@ def run_gpu(args):
         if zc_ms is not None:
             line["zerocheck"] = {"value": 3 * n / (zc_ms * 1e-3), "unit": "field-elems/s", "ms_per_step": zc_ms,
                                  "gpu_launches": zc_launches // args.steps,
-                                 "workload": f"ZeroCheckProof::prove of f*g*e over three 2^{args.log_n}-entry tables: z drawn and the eq "
-                                             "table built on the device, degree-4 rounds over four tables"}
+                                 "workload": f"ZeroCheckProof::prove of f*g*e over three 2^{args.log_n}-entry tables: z drawn on the device, "
+                                             "eq-factored rounds (degree-3 sums weighted by the eq table of the remaining variables, "
+                                             "times the round's linear eq factor)"}
         if mlpcs:
             line["mlpcs_commit_open"] = mlpcs
         if hplonk:

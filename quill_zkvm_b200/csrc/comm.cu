@@ -89,14 +89,10 @@ static void peers_close(qz_ctx* ctx) {
 // travel through the communicator that was just created.  Every rank takes the same decision: a second all-gather
 // carries each rank's "all peers opened" bit, and the mailboxes are used only if it is set everywhere; otherwise
 // (restricted CUDA_VISIBLE_DEVICES, no peer access, QZ_NO_P2P=1) the exchanges stay on NCCL all-gathers.
-static int peers_setup(qz_ctx* ctx) {
+static int peers_exchange_handles(qz_ctx* ctx, uint8_t* xchg, int& ok) {
   const int G = ctx->nranks;
-  if (G > QZ_MAX_PEERS) return QZ_OK;
   cudaStream_t st = ctx->stream;
-  uint8_t* xchg = nullptr;  // [G] handles, then [G] status bytes
-  QZ_CUDA(ctx, cudaMalloc((void**)&xchg, (size_t)(64 + 64) * G + 128));
   uint8_t* d_mine = xchg + (size_t)128 * G;
-  int ok = getenv("QZ_NO_P2P") ? 0 : 1;
   cudaIpcMemHandle_t mine;
   memset(&mine, 0, sizeof mine);
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -121,7 +117,7 @@ static int peers_setup(qz_ctx* ctx) {
     }
     cudaIpcMemHandle_t h;
     memcpy(&h, all.data() + (size_t)64 * g, 64);
-    bool zero = true;
+    bool zero = true;  // a rank that could not allocate its mailbox sends an all-zero handle
     for (int i = 0; i < 64; i++) zero = zero && all[(size_t)64 * g + i] == 0;
     if (zero || cudaIpcOpenMemHandle(&ctx->peer_mbox_host[g], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
       cudaGetLastError();
@@ -138,10 +134,20 @@ static int peers_setup(qz_ctx* ctx) {
   QZ_CUDA(ctx, cudaMemcpyAsync(flags.data(), xchg, G, cudaMemcpyDeviceToHost, st));
   QZ_CUDA(ctx, cudaStreamSynchronize(st));
   for (int g = 0; g < G; g++) ok = ok && flags[g];
+  return QZ_OK;
+}
+
+static int peers_setup(qz_ctx* ctx) {
+  const int G = ctx->nranks;
+  if (G > QZ_MAX_PEERS) return QZ_OK;
+  uint8_t* xchg = nullptr;  // [G] handles / status bytes, then this rank's contribution
+  QZ_CUDA(ctx, cudaMalloc((void**)&xchg, (size_t)128 * G + 128));
+  int ok = getenv("QZ_NO_P2P") ? 0 : 1;
+  const int rc = peers_exchange_handles(ctx, xchg, ok);
   cudaFree(xchg);
-  if (!ok) {
+  if (rc || !ok) {
     peers_close(ctx);
-    return QZ_OK;
+    return rc;
   }
   QZ_CUDA(ctx, cudaMalloc((void**)&ctx->peer_mbox_dev, sizeof(void*) * QZ_MAX_PEERS));
   QZ_CUDA(ctx, cudaMemcpy(ctx->peer_mbox_dev, ctx->peer_mbox_host, sizeof(void*) * QZ_MAX_PEERS, cudaMemcpyHostToDevice));

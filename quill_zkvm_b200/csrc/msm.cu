@@ -711,7 +711,7 @@ int msm_run(qz_ctx* ctx, const qz_srs* srs, uint4* scalars_dev, const void* scal
     uint8_t* pout = ppts_b;
     uint64_t n_in = n_part0;
     while (true) {
-      if (n_in <= (uint64_t)FIN_SLOTS && n_in > PART_CHUNK && !getenv("QZ_NO_FINISH")) {  // short list: scan it in one launch
+      if (n_in <= (uint64_t)FIN_SLOTS && n_in > PART_CHUNK) {  // short list: scan it in one launch
         QZ_LAUNCH(ctx, msm_partials_finish, 1, FIN_THREADS, 0, kin, pin, (int)n_in, c, buckets, fin_a, fin_b);
         break;
       }

@@ -181,6 +181,62 @@ __global__ void __launch_bounds__(WIDE ? SC_WIDE_THREADS : SC_THREADS, (WIDE ? Q
   block_sum_many(sums, K + 1, s_part, &partials[(size_t)blockIdx.x * (K + 1)]);
 }
 
+// ---- round kernel, zero-check fast path: h = g_0 * ... * g_{K-1}, summed against eq(., z) --------------------------------------
+// eq(x, z) = prod_i eq(x_i, z_i) factors over the variables, so the round polynomial of h * eq is
+//     s_j(X) = P_j * eq(X, z_j) * t_j(X),   t_j(X) = sum_{x'} E_{j+1}(x') * prod_t g_t(r_0 .. r_{j-1}, X, x'),
+// with P_j = prod_{i<j} eq(r_i, z_i) and E_{j+1} the eq table of the variables above j.  Instead of streaming and folding
+// eq as one more table of a degree-(K+1) product (zerocheck.rs:25-29 builds exactly that), the pass sums the degree-K
+// polynomial t_j with one weight per pair -- 2 extra products per pair (the weight scales one factor) in place of 2 fold
+// products + the extra evaluation point + the wider product -- and sc_round_close multiplies by the linear factor.
+// The weight tables need no product to shrink: eq(0, z) + eq(1, z) = 1, so E_{j+2}[p] = E_{j+1}[2p] + E_{j+1}[2p+1],
+// done in the same pass that folds the g tables.  s_j is the same polynomial, so every output byte is unchanged.
+template <int K, bool WIDE, bool FOLD>
+__global__ void __launch_bounds__(WIDE ? SC_WIDE_THREADS : SC_THREADS, (WIDE ? QZ_SC_WIDE_BPS : 2))
+    sc_round_zc(ScTables tabs, const uint4* e_in, uint4* e_out, uint64_t n_pairs, const ScHead* head, Fr* partials) {
+  __shared__ Fr s_part[(SC_THREADS / 32) * (K + 1)];
+  grid_dep_launch();
+  grid_dep_wait();
+  ProdAcc<K, WIDE> acc;
+  acc.init();
+  Fr r = fp_zero<FrParams>();
+  if (FOLD) r = head->r;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += stride) {
+    RawPair<FOLD> raw[K];
+#pragma unroll
+    for (int t = 0; t < K; t++) load_raw<FOLD>(tabs.in[t], p, raw[t]);
+    Fr w;
+    if (FOLD) {
+      w = fp_add<FrParams>(ld_elem(e_in, 2 * p), ld_elem(e_in, 2 * p + 1));
+      st_elem(e_out, p, w);
+    } else {
+      w = ld_elem(e_in, p);
+    }
+    Fr lo[K], hi[K];
+#pragma unroll
+    for (int t = 0; t < K; t++) finish_pair<FOLD>(raw[t], tabs.out[t], p, r, lo[t], hi[t]);
+    lo[0] = fp_mul<FrParams>(w, lo[0]);
+    hi[0] = fp_mul<FrParams>(w, hi[0]);
+    prod_core<K, WIDE>(lo, hi, acc);
+  }
+  Fr sums[K + 1];
+#pragma unroll
+  for (int x = 0; x <= K; x++) sums[x] = acc.get(x);
+  block_sum_many(sums, K + 1, s_part, &partials[(size_t)blockIdx.x * (K + 1)]);
+}
+// hand-over to sc_tail: the eq table in the form zerocheck.rs:25 would have left it after the same rounds, i.e. with
+// the last challenge still to be folded in: out[2p + b] = P_{j-1} * eq(b, z_{j-1}) * E_j[p]
+__global__ void __launch_bounds__(256) zc_materialize_eq(const uint4* e_tab, uint64_t half, const ScHead* head, const Fr* z_prev,
+                                                        uint4* out) {
+  const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= half) return;
+  const Fr z = *z_prev, P = head->zc_prefix_prev, e = ld_elem(e_tab, p);
+  const Fr hi = fp_mul<FrParams>(fp_mul<FrParams>(P, z), e);
+  const Fr lo = fp_sub<FrParams>(fp_mul<FrParams>(P, e), hi);  // P (1 - z) E
+  st_elem(out, 2 * p, lo);
+  st_elem(out, 2 * p + 1, hi);
+}
+
 // ---- round kernel, generic expression tree -----------------------------------------------------------------------------------
 QZ_DEV void generic_pair(const ScTables& tabs, uint64_t p, bool fold, const Fr& r, const uint32_t* s_ops,
                          uint32_t n_ops, int k, int d, const Fr* consts, Fr* acc) {
@@ -221,7 +277,7 @@ __global__ void __launch_bounds__(SC_THREADS) sc_round_generic(ScTables tabs, ui
 // ---- finalize: sum `n_parts` partial vectors, close the round (transcript on the device) -----------------------------------
 __global__ void __launch_bounds__(SC_THREADS) sc_finalize(const Fr* partials, int n_parts, int d, ScHead* head,
                                                          const Fr* vinv, Fr* out_coeffs_row, uint32_t* out_len,
-                                                         Fr* out_point_slot, int max_coeffs) {
+                                                         Fr* out_point_slot, int max_coeffs, const Fr* zc_z) {
   __shared__ Fr s_part[(SC_THREADS / 32) * SC_MAX_COEFFS];
   __shared__ Fr s_evals[SC_MAX_COEFFS];
   __shared__ Fr s_coef[SC_MAX_COEFFS];
@@ -234,7 +290,7 @@ __global__ void __launch_bounds__(SC_THREADS) sc_finalize(const Fr* partials, in
   for (int b = threadIdx.x; b < n_parts; b += blockDim.x)
     for (int x = 0; x <= d; x++) v[x] = fp_add<FrParams>(v[x], partials[(size_t)b * (d + 1) + x]);
   block_sum_many(v, d + 1, s_part, s_evals);
-  sc_round_close(head, vinv, d, s_evals, s_coef, s_msg, s_prod, out_coeffs_row, out_len, out_point_slot, max_coeffs);
+  sc_round_close(head, vinv, d, s_evals, s_coef, s_msg, s_prod, out_coeffs_row, out_len, out_point_slot, max_coeffs, zc_z);
 }
 
 // Sharded mode with peer mailboxes (comm.cuh): ONE launch per round after the round kernel.  The block sums this rank's
@@ -434,6 +490,8 @@ __global__ void sc_set_state(ScHead* head, const uint8_t* state) {
   for (int i = 0; i < 32; i++) head->tstate[i] = state[i];
   head->r = fp_zero<FrParams>();
   head->evaluation = fp_zero<FrParams>();
+  head->zc_prefix = fp_one<FrParams>();
+  head->zc_prefix_prev = fp_one<FrParams>();
 }
 
 
@@ -784,9 +842,12 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
       tabs.in[j] = (const uint4*)p;
     }
   }
+  // zero-check fast path (see sc_round_zc): h is a product of up to three tables, one GPU, at least one streaming round
+  const bool zc_fast = zerocheck && G == 1 && eq_slot >= 0 && cp.product_k >= 2 && cp.product_k <= 4 &&
+                       N > ((uint64_t)1 << SC_TAIL_LOG) && !getenv("QZ_ZC_STREAM_EQ");
   if (zerocheck) {
     QZ_LAUNCH(ctx, zc_draw_point, 1, 1, 0, head, (int)num_vars, d_z);  // zerocheck.rs:20-22
-    if (eq_slot >= 0) {
+    if (eq_slot >= 0 && !zc_fast) {
       void* p = ctx->arena_alloc(32 * N);
       if (!p) return ctx->fail(QZ_ERR_ALLOC, "eq table");
       rc = eq_table_device(ctx, (int)num_vars, d_z, (uint4*)p, (uint64_t)ctx->rank * N * (G > 1), N);  // zerocheck.rs:25
@@ -833,13 +894,82 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
 
     uint64_t size = N;  // current (pre-fold) table size
     int pending = 0, round = 0, flip = 0;
+    const uint4* zc_weights = nullptr;  // zero-check fast path: E_j, the weight table of the last round run (size / 2 entries)
     // the round chain uses programmatic dependent launches, except around NCCL collectives (not written for them)
     // Measured (tools/sc_pdl_ab.py): -5 us per round while a round is latency-bound,
     // but +10..20 us on the rounds that stream 2^21 entries or more, so only the short rounds are chained this way.
     const bool pdl_ok = ctx->pdl && (G == 1 || comm_has_peers(ctx));
     ctx->kernel_ms_accum = 0.f;
     QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k0, st));
-    while (size * G > ((uint64_t)1 << SC_TAIL_LOG)) {
+    if (zc_fast) {
+      const int K = cp.product_k - 1;  // factors of h; the eq factor is carried by the weights
+      Fr* vinv_k = nullptr;
+      rc = get_vinv(ctx, K, &vinv_k);
+      if (rc) return rc;
+      int zb = 1, zb_wide = 0;
+      if (K == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&zb, sc_round_zc<1, false, true>, SC_THREADS, 0);
+      else if (K == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&zb, sc_round_zc<2, false, true>, SC_THREADS, 0);
+      else {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&zb, sc_round_zc<3, false, true>, SC_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&zb_wide, sc_round_zc<3, true, true>, SC_WIDE_THREADS, 0);
+      }
+      zb = std::max(1, std::min(zb, std::max(bps, bps_wide)));  // `partials` was sized for max(bps, bps_wide) blocks per SM
+      zb_wide = std::min(zb_wide, std::max(bps, bps_wide));
+      if (getenv("QZ_SC_NARROW")) zb_wide = 0;
+      // the eq slot's fold scratch holds the weight tables: E_1 (N/2 entries) = eq table of z_1 .. z_{n-1}
+      uint4* e_buf[2] = {bufA[eq_slot], bufB[eq_slot]};
+      rc = eq_table_device(ctx, (int)num_vars - 1, d_z + 1, e_buf[0], 0, N / 2);
+      if (rc) return rc;
+      int e_cur = 0;
+      ScTables gt;  // the K tables of h, in dense order without the eq slot
+      memset(&gt, 0, sizeof gt);
+      int g_of[SC_MAX_K];
+      for (int j = 0, i = 0; j < ka; j++)
+        if (j != eq_slot) {
+          gt.in[i] = tabs.in[j];
+          g_of[i++] = j;
+        }
+      while (size > ((uint64_t)1 << SC_TAIL_LOG)) {
+        const uint64_t n_pairs = pending ? size / 4 : size / 2;
+        const bool pdl = pdl_ok && n_pairs <= ((uint64_t)1 << 18);
+        for (int i = 0; i < K; i++) gt.out[i] = flip ? bufB[g_of[i]] : bufA[g_of[i]];
+        const bool wide = zb_wide > 0 && n_pairs >= (uint64_t)8 * SC_WIDE_THREADS * ctx->sm_count * zb_wide;
+        const int grid = wide ? round_grid(ctx, n_pairs, zb_wide, SC_WIDE_THREADS) : round_grid(ctx, n_pairs, zb);
+        const uint4* e_in = e_buf[e_cur];
+        uint4* e_out = e_buf[e_cur ^ 1];
+#define QZ_ROUND_ZC(KK, W, T)                                                                                      \
+  do {                                                                                                             \
+    if (pending) QZ_LAUNCH_PDL(ctx, pdl, (sc_round_zc<KK, W, true>), grid, T, gt, e_in, e_out, n_pairs, (const ScHead*)head, partials); \
+    else QZ_LAUNCH_PDL(ctx, pdl, (sc_round_zc<KK, W, false>), grid, T, gt, e_in, e_out, n_pairs, (const ScHead*)head, partials);        \
+  } while (0)
+        switch (K) {
+          case 1: QZ_ROUND_ZC(1, false, SC_THREADS); break;
+          case 2: QZ_ROUND_ZC(2, false, SC_THREADS); break;
+          default:
+            if (wide) QZ_ROUND_ZC(3, true, SC_WIDE_THREADS);
+            else QZ_ROUND_ZC(3, false, SC_THREADS);
+        }
+        QZ_LAUNCH_PDL(ctx, pdl, sc_finalize, 1, SC_THREADS, (const Fr*)partials, grid, K, head, (const Fr*)vinv_k,
+                      d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc, (const Fr*)(d_z + round));
+        if (pending) {
+          for (int i = 0; i < K; i++) gt.in[i] = gt.out[i];
+          flip ^= 1;
+          size >>= 1;
+          e_cur ^= 1;  // this round wrote E_{round+1} to e_out
+        }
+        zc_weights = e_buf[e_cur];
+        pending = 1;
+        round++;
+      }
+      // hand over to sc_tail: h's tables where they stand, eq materialised in the reference's form (pending fold)
+      uint4* eq_full = (uint4*)ctx->arena_alloc(32 * size);
+      if (!eq_full) return ctx->fail(QZ_ERR_ALLOC, "eq hand-over");
+      QZ_LAUNCH(ctx, zc_materialize_eq, (unsigned)((size / 2 + 255) / 256), 256, 0, zc_weights, size / 2, (const ScHead*)head,
+                (const Fr*)(d_z + (round - 1)), eq_full);
+      for (int i = 0; i < K; i++) tabs.in[g_of[i]] = gt.in[i];
+      tabs.in[eq_slot] = eq_full;
+    }
+    while (!zc_fast && size * G > ((uint64_t)1 << SC_TAIL_LOG)) {
       const uint64_t n_pairs = pending ? size / 4 : size / 2;
       const bool pdl = pdl_ok && n_pairs <= ((uint64_t)1 << 18);
       for (int j = 0; j < ka; j++) tabs.out[j] = flip ? bufB[j] : bufA[j];
@@ -868,7 +998,7 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
       }
       if (G == 1) {
         QZ_LAUNCH_PDL(ctx, pdl, sc_finalize, 1, SC_THREADS, (const Fr*)partials, grid, d, head, (const Fr*)vinv,
-                      d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc);
+                      d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc, (const Fr*)nullptr);
       } else if (comm_has_peers(ctx)) {  // partial sums go straight into the peers' mailboxes (comm.cuh)
         QZ_LAUNCH_PDL(ctx, pdl, sc_finalize_peers, 1, SC_THREADS, (const Fr*)partials, grid, d,
                       (PeerMailbox* const*)ctx->peer_mbox_dev, ctx->rank, G, ++ctx->mbox_seq, head, (const Fr*)vinv,
@@ -878,7 +1008,7 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
         rc = comm_allgather(ctx, rank_evals, all_evals, sizeof(Fr) * (d + 1));
         if (rc) return rc;
         QZ_LAUNCH(ctx, sc_finalize, 1, SC_THREADS, 0, all_evals, G, d, head, vinv, d_coeffs + (size_t)round * mc,
-                  d_lens + round, d_point + round, mc);
+                  d_lens + round, d_point + round, mc, (const Fr*)nullptr);
       }
       if (pending) {
         for (int j = 0; j < ka; j++) tabs.in[j] = tabs.out[j];

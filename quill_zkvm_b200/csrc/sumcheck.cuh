@@ -32,6 +32,9 @@ struct ScHead {
   alignas(16) uint8_t tstate[32];  // Transcript.state
   Fr r;                // challenge of the last closed round (pending fold)
   Fr evaluation;       // EvaluationClaim.evaluation
+  // eq-factored zero-check (sumcheck.cu "zero-check fast path"): P_j = prod_{i<j} eq(r_i, z_i) after round j-1 closed,
+  // and P_{j-1}, the value it had one round earlier (the hand-over to sc_tail needs it)
+  Fr zc_prefix, zc_prefix_prev;
 };
 
 // ---- serialization / transcript (device) -------------------------------------------------------------------------
@@ -372,10 +375,16 @@ static __device__ __noinline__ Fr sc_eval_program(const uint32_t* ops, uint32_t 
 // s_msg: SC_MSG_WORDS words of shared memory: [0..8) state, [8..10) u64 length, then 8 words per coefficient.
 constexpr int SC_MSG_WORDS = ((10 + 8 * SC_MAX_COEFFS + 15) / 16) * 16;
 constexpr int SC_PROD_SLOTS = 256;
+// zc_z (optional, eq-factored zero-check): the evaluations are those of t_j(X) = sum_x' E_{j+1}(x') prod_t g_t(X, x'), of
+// degree d, and the round polynomial is s_j(X) = P_j * eq(X, z_j) * t_j(X), of degree d + 1, with z_j = *zc_z and
+// P_j = head->zc_prefix: the d + 1 coefficients are multiplied by the linear factor a + b X, a = P_j (1 - z_j),
+// b = P_j (2 z_j - 1), before they are trimmed and absorbed, and P_{j+1} = P_j eq(r_j, z_j) once r_j is drawn.
 QZ_DEV void sc_round_close(ScHead* head, const Fr* vinv, int d, const Fr* s_evals, Fr* s_coef, uint32_t* s_msg, Fr* s_prod,
-                           Fr* out_coeffs_row, uint32_t* out_len, Fr* out_point_slot, int max_coeffs) {
+                           Fr* out_coeffs_row, uint32_t* out_len, Fr* out_point_slot, int max_coeffs,
+                           const Fr* zc_z = nullptr) {
   const int t = threadIdx.x;
   const int n1 = d + 1;
+  const int n_out = zc_z ? d + 2 : d + 1;  // coefficients of the round polynomial before trimming
   // coefficient i = sum_j vinv[i][j] * e[j]: the (d+1)^2 products are independent, so when they fit the block each
   // thread does one (s_prod: SC_PROD_SLOTS Fr of shared memory)
   const bool wide = n1 * n1 <= (int)blockDim.x && n1 * n1 <= SC_PROD_SLOTS;
@@ -383,8 +392,8 @@ QZ_DEV void sc_round_close(ScHead* head, const Fr* vinv, int d, const Fr* s_eval
     if (t < n1 * n1) s_prod[t] = fp_mul<FrParams>(vinv[t], s_evals[t % n1]);
     __syncthreads();
   }
+  Fr acc = fp_zero<FrParams>();
   if (t <= d) {
-    Fr acc = fp_zero<FrParams>();
     if (wide) {
       for (int j = 0; j <= d; j++) acc = fp_add<FrParams>(acc, s_prod[t * n1 + j]);
     } else {
@@ -392,6 +401,21 @@ QZ_DEV void sc_round_close(ScHead* head, const Fr* vinv, int d, const Fr* s_eval
       for (int j = 0; j <= d; j++) acc = fp_add<FrParams>(acc, fp_mul<FrParams>(vinv[t * (d + 1) + j], s_evals[j]));
     }
     s_coef[t] = acc;
+  }
+  if (zc_z) {  // (c_0 + c_1 X + ...)(a + b X): c'_t = a c_t + b c_{t-1}
+    __syncthreads();
+    Fr lower = fp_zero<FrParams>();
+    if (t >= 1 && t <= d + 1) lower = s_coef[t - 1];
+    __syncthreads();
+    if (t < n_out) {
+      const Fr z = *zc_z, P = head->zc_prefix, one = fp_one<FrParams>();
+      const Fr a = fp_mul<FrParams>(P, fp_sub<FrParams>(one, z));
+      const Fr b = fp_mul<FrParams>(P, fp_sub<FrParams>(fp_dbl<FrParams>(z), one));
+      acc = fp_add<FrParams>(fp_mul<FrParams>(a, acc), fp_mul<FrParams>(b, lower));  // acc = c_t (zero for t = d + 1)
+      s_coef[t] = acc;
+    }
+  }
+  if (t < n_out) {
     out_coeffs_row[t] = acc;
     const Fr can = fp_from_mont<FrParams>(acc);  // ark-serialize: 32 B little-endian canonical
 #pragma unroll
@@ -402,7 +426,7 @@ QZ_DEV void sc_round_close(ScHead* head, const Fr* vinv, int d, const Fr* s_eval
   __syncthreads();
   if (t < 4) {  // the transcript runs on lanes 0..3 of warp 0 (tr_*_quad)
     if (t == 0) {
-      int len = d + 1;
+      int len = n_out;
       while (len > 0 && fp_is_zero<FrParams>(s_coef[len - 1])) len--;  // DensePolynomial trims trailing zeros
       *out_len = (uint32_t)len;
       s_msg[8] = (uint32_t)len;  // u64 LE length prefix
@@ -417,6 +441,12 @@ QZ_DEV void sc_round_close(ScHead* head, const Fr* vinv, int d, const Fr* s_eval
     if (t == 0) {
       head->r = r;
       *out_point_slot = r;
+      if (zc_z) {  // P_{j+1} = P_j (r z + (1 - r)(1 - z))
+        const Fr z = *zc_z, one = fp_one<FrParams>(), P = head->zc_prefix;
+        const Fr e = fp_add<FrParams>(fp_mul<FrParams>(r, z), fp_mul<FrParams>(fp_sub<FrParams>(one, r), fp_sub<FrParams>(one, z)));
+        head->zc_prefix_prev = P;
+        head->zc_prefix = fp_mul<FrParams>(P, e);
+      }
     }
   }
   __syncthreads();

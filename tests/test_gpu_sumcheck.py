@@ -163,6 +163,26 @@ def test_zerocheck_sizes(ctx, n):
     assert_same(ctx, n, tabs, nodes, consts, None, b"zc", zerocheck=True)
 
 
+@pytest.mark.parametrize("k", [1, 2, 3])
+@pytest.mark.parametrize("n", [12, 13, 16, 18])
+def test_zerocheck_product_fast_path(ctx, n, k, monkeypatch):
+    """h = a product of k tables: the eq-factored rounds (weights instead of a streamed eq table, round polynomial =
+    linear factor x degree-k sum) must give the bytes of the reference's formulation -- against the oracle, with host and
+    device tables, and against the library's own streamed-eq path (QZ_ZC_STREAM_EQ=1)."""
+    tabs = [util.rand_fr(1 << n, 900 + 10 * n + t) for t in range(k)]
+    if n == 13:  # a table that vanishes on half the cube and a constant one: trailing-zero trimming of s_j
+        tabs[0][::2] = 0
+        if k > 1:
+            tabs[1][:] = co.fr1(5)
+    nodes, consts = util.expr_product(k)
+    sc, claim, o = assert_same(ctx, n, tabs, nodes, consts, None, b"zc_fast", zerocheck=True, threads=NCPU)
+    assert_same(ctx, n, tabs, nodes, consts, None, b"zc_fast", zerocheck=True, device_tables=True, threads=NCPU)
+    monkeypatch.setenv("QZ_ZC_STREAM_EQ", "1")
+    sc2, claim2, state2, z2 = gpu_prove(ctx, n, tabs, nodes, consts, None, b"zc_fast", zerocheck=True)
+    assert all(np.array_equal(a, b) for a, b in zip(sc.r_polys, sc2.r_polys)) and len(sc.r_polys) == len(sc2.r_polys)
+    assert np.array_equal(claim.evaluation, claim2.evaluation) and np.array_equal(claim.point, claim2.point)
+
+
 def test_unused_store_tables_and_device_tables(ctx):
     n = 12
     tabs = [util.rand_fr(1 << n, 300 + t) for t in range(5)]
