@@ -296,6 +296,7 @@ class _TracePK:
     id_poly: DeviceBuffer
     permutation_poly: DeviceBuffer
     public_values: List[np.ndarray]
+    public_columns: List[DeviceBuffer] = None  # the un-padded public columns, resident (circuit constants: built once)
 
 
 @dataclass
@@ -329,7 +330,7 @@ class HyperPlonk:
             assert len(ids) == n and len(perm) == n
             id_t, perm_t = ctx.upload(small_int_table(ctx, ids)), ctx.upload(small_int_table(ctx, perm))  # resident for prove()
             vks.append(_TraceVK(c, pub_comms, pcs.commit(id_t), pcs.commit(perm_t)))
-            pks.append(_TracePK(id_t, perm_t, pub))
+            pks.append(_TracePK(id_t, perm_t, pub, [ctx.upload(small_int_table(ctx, col)) for col in c.public_values()]))
         return HyperPlonk(ctx, pks, vks)
 
     def _prove_trace(self, pcs: KZG, full_witness: DeviceBuffer, transcript: Transcript, pk: _TracePK,
@@ -342,7 +343,7 @@ class HyperPlonk:
         store = VirtualPolynomialStore(log2_rows)  # :156-162
         for col in range(circuit.num_cols()):
             store.allocate_polynomial(full_witness.view(col * col_bytes, col_bytes))
-        public = [ctx.upload(small_int_table(ctx, p)) for p in circuit.public_values()]
+        public = pk.public_columns  # proof.rs:159-162 rebuilds them per proof; they are constants of the circuit
         for p in public:
             store.allocate_polynomial(p)
         exprs = circuit.zero_check_expressions()  # :165-175
@@ -373,8 +374,6 @@ class HyperPlonk:
         batch.add(pk.permutation_poly, perm_point, lambda o: tail.__setitem__("perm", o))
         batch.add(full_witness, perm_point, lambda o: tail.__setitem__("trace", o))
         batch.run()
-        for p in public:
-            p.free()
         return TraceProof(zero_check_proof, perm_proof, openings_zc, openings_pub, tail["id"], tail["perm"], tail["trace"])
 
     def prove(self, pcs: KZG, witness_traces: List[List[np.ndarray]]) -> HyperPlonkProof:
