@@ -1,0 +1,261 @@
+"""CPU models of the device-side reformulations, checked against the oracle (no GPU needed).
+
+The CUDA path may compute a value by a different route than the reference as long as every byte is the same.  Each route
+that is not a transcription of the reference is restated here in a few lines of Python -- the same recurrences the
+kernels run -- and compared with `oracle/pyref.py` (the reference's formulation), so the identity each kernel relies on
+is pinned independently of the GPU tests:
+  * eq-factored zero-check rounds (csrc/sumcheck.cu sc_round_zc, sumcheck.cuh sc_round_close with zc_z)
+  * blake3 compression with the state columns spread over four lanes (csrc/sumcheck.cuh b3_compress_quad)
+  * the inverse by the binary extended Euclidean algorithm (csrc/ff.cuh fp_inv_serial)
+  * the merge of partial bucket runs by a segmented scan with early exit (csrc/msm.cu msm_partials_finish)
+  * the streamed MSM's point ranges (csrc/msm.cu msm_run)
+"""
+import os
+import random
+import re
+
+import pytest
+
+from oracle import pyref as py
+
+FR = py.FR
+CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "quill_zkvm_b200", "csrc")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def zerocheck_eq_factored(num_vars, tables, tr):
+    """ZeroCheckProof::prove for h = prod(tables) the way sc_round_zc + sc_round_close do it:
+    s_j(X) = P_j * eq(X, z_j) * t_j(X),  t_j(X) = sum_p E_{j+1}[p] * prod_t g_t(X, p), weights folded by addition."""
+    k = len(tables)
+    z = [tr.draw_field_element() for _ in range(num_vars)]
+    tr.append_usize(num_vars)
+    tr.append_fr(0)
+    gs = [list(t) for t in tables]
+    weights = py.fast_eq_eval_hypercube(num_vars - 1, z[1:]) if num_vars else []  # E_1
+    prefix = 1
+    r_polys, point = [], []
+    for j in range(num_vars):
+        pairs = len(gs[0]) // 2
+        assert len(weights) == pairs
+        # evaluations of t_j at X = 0..k (the weight scales one factor), then Lagrange interpolation on nodes 0..k
+        evals = []
+        for x in range(k + 1):
+            acc = 0
+            for p in range(pairs):
+                term = weights[p]
+                for g in gs:
+                    term = term * (g[2 * p] + x * (g[2 * p + 1] - g[2 * p])) % FR
+                acc = (acc + term) % FR
+            evals.append(acc)
+        coeffs = [0] * (k + 1)
+        for i, yi in enumerate(evals):  # Lagrange basis polynomials
+            num, den = [1], 1
+            for m in range(k + 1):
+                if m != i:
+                    num = py.poly_mul(num, [(-m) % FR, 1])
+                    den = den * (i - m) % FR
+            scale = yi * pow(den, FR - 2, FR) % FR
+            num = num + [0] * (k + 1 - len(num))
+            coeffs = [(c + scale * nc) % FR for c, nc in zip(coeffs, num)]
+        a, b = prefix * (1 - z[j]) % FR, prefix * (2 * z[j] - 1) % FR  # P_j * eq(X, z_j) = a + b X
+        s = [(a * (coeffs[t] if t <= k else 0) + b * (coeffs[t - 1] if t >= 1 else 0)) % FR for t in range(k + 2)]
+        s = py.trim(s)
+        tr.append_fr_vec(s)
+        r_polys.append(s)
+        r = tr.draw_field_element()
+        point.append(r)
+        prefix = prefix * ((r * z[j] + (1 - r) * (1 - z[j])) % FR) % FR
+        gs = [[(g[2 * p] + r * (g[2 * p + 1] - g[2 * p])) % FR for p in range(pairs)] for g in gs]
+        weights = [(weights[2 * p] + weights[2 * p + 1]) % FR for p in range(pairs // 2)]  # eq(0,z) + eq(1,z) = 1
+    ev = 1
+    for g in gs:
+        ev = ev * g[0] % FR
+    # the reference returns h_hat(point) / eq(z, point) = h(point); prefix == eq(z, point) ties the two together
+    assert prefix == py.eq_eval(z, point)
+    return r_polys, point, ev, z
+
+
+@pytest.mark.parametrize("n,k", [(1, 1), (2, 2), (3, 3), (5, 1), (5, 2), (6, 3)])
+def test_eq_factored_zerocheck_equals_reference_formulation(n, k):
+    rnd = random.Random(100 * n + k)
+    tables = [[rnd.randrange(FR) for _ in range(1 << n)] for _ in range(k)]
+    if n == 5:
+        tables[0][::2] = [0] * (1 << (n - 1))  # round polynomials with vanishing leading coefficients get trimmed
+    h = py.e_in(0)
+    for t in range(1, k):
+        h = py.e_mul(h, py.e_in(t))
+    t1, t2 = py.Transcript(b"zc_model"), py.Transcript(b"zc_model")
+    want = py.zerocheck_prove(n, tables, h, t1)
+    got = zerocheck_eq_factored(n, tables, t2)
+    assert got[0] == [py.trim([c % FR for c in p]) for p in want[0]]
+    assert got[1] == want[1] and got[2] == want[2] % FR and got[3] == want[3]
+    assert t1.state == t2.state
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+IV = [0x6A09E667, 0xBB67AE85, 0x3C6EF372, 0xA54FF53A, 0x510E527F, 0x9B05688C, 0x1F83D9AB, 0x5BE0CD19]
+PERM = [2, 6, 3, 10, 7, 0, 4, 13, 1, 11, 12, 5, 9, 14, 15, 8]
+M32 = 0xFFFFFFFF
+
+
+def _ror(x, n):
+    return ((x >> n) | (x << (32 - n))) & M32
+
+
+def _g(a, b, c, d, mx, my):
+    a = (a + b + mx) & M32
+    d = _ror(d ^ a, 16)
+    c = (c + d) & M32
+    b = _ror(b ^ c, 12)
+    a = (a + b + my) & M32
+    d = _ror(d ^ a, 8)
+    c = (c + d) & M32
+    b = _ror(b ^ c, 7)
+    return a, b, c, d
+
+
+def _device_schedule():
+    """the nibble-packed message schedule constants of b3_compress_quad, read from the header"""
+    src = open(os.path.join(CSRC, "sumcheck.cuh")).read()
+    body = re.search(r"B3_SCHED\[7\]\s*=\s*\{([^}]*)\}", src).group(1)
+    words = [int(w.rstrip("ul"), 16) for w in re.findall(r"0x[0-9a-fA-F]+ull", body)]
+    assert len(words) == 7
+    return [[(w >> (4 * j)) & 15 for j in range(16)] for w in words]
+
+
+def compress_quad(cv, m, block_len, flags, sched):
+    """b3_compress_quad: lane i holds column i; shuffles rotate b, c, d into the diagonals and back"""
+    a, b, c = list(cv[:4]), list(cv[4:]), IV[:4]
+    d = [0, 0, block_len, flags]
+    for r in range(7):
+        for i in range(4):  # column step
+            a[i], b[i], c[i], d[i] = _g(a[i], b[i], c[i], d[i], m[sched[r][2 * i]], m[sched[r][2 * i + 1]])
+        b, c, d = [b[(i + 1) & 3] for i in range(4)], [c[(i + 2) & 3] for i in range(4)], [d[(i + 3) & 3] for i in range(4)]
+        for i in range(4):  # diagonal step
+            a[i], b[i], c[i], d[i] = _g(a[i], b[i], c[i], d[i], m[sched[r][8 + 2 * i]], m[sched[r][9 + 2 * i]])
+        b, c, d = [b[(i + 3) & 3] for i in range(4)], [c[(i + 2) & 3] for i in range(4)], [d[(i + 1) & 3] for i in range(4)]
+    out_lo = [a[i] ^ c[i] for i in range(4)] + [b[i] ^ d[i] for i in range(4)]
+    out_hi = [c[i] ^ cv[i] for i in range(4)] + [d[i] ^ cv[4 + i] for i in range(4)]
+    return out_lo, out_hi
+
+
+def blake3_single_chunk_quad(data: bytes, out_len: int, sched) -> bytes:
+    assert len(data) <= 1024 and out_len <= 64
+    nblocks = max(1, (len(data) + 63) // 64)
+    cv = list(IV)
+    for blk in range(nblocks):
+        chunk = data[64 * blk: 64 * blk + 64]
+        m = [int.from_bytes(chunk[4 * i: 4 * i + 4].ljust(4, b"\0"), "little") for i in range(16)]
+        last = blk + 1 == nblocks
+        flags = (1 if blk == 0 else 0) | ((2 | 8) if last else 0)
+        lo, hi = compress_quad(cv, m, len(chunk) if last else 64, flags, sched)
+        cv = lo
+    return b"".join(w.to_bytes(4, "little") for w in lo + hi)[:out_len]
+
+
+def test_quad_lane_blake3_matches_blake3():
+    blake3 = pytest.importorskip("blake3")
+    sched = _device_schedule()
+    ref = [list(range(16))]
+    for _ in range(6):
+        ref.append([ref[-1][PERM[j]] for j in range(16)])
+    assert sched == ref  # the packed constants are the iterated message permutation
+    rnd = random.Random(7)
+    for n in (0, 1, 41, 63, 64, 65, 80, 168, 200, 1024):
+        data = bytes(rnd.randrange(256) for _ in range(n))
+        assert blake3_single_chunk_quad(data, 48, sched) == blake3.blake3(data).digest(length=48), n
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def inv_binary_euclid(a, p):
+    """fp_inv_serial: invariants x1 * a = u and x2 * a = v (mod p)"""
+    if a == 0:
+        return 0
+    u, v, x1, x2 = a, p, 1, 0
+    while u != 1 and v != 1:
+        while u & 1 == 0:
+            u >>= 1
+            x1 = (x1 + p) >> 1 if x1 & 1 else x1 >> 1
+        while v & 1 == 0:
+            v >>= 1
+            x2 = (x2 + p) >> 1 if x2 & 1 else x2 >> 1
+        if u >= v:
+            u, x1 = u - v, (x1 - x2) % p
+        else:
+            v, x2 = v - u, (x2 - x1) % p
+    return x1 if u == 1 else x2
+
+
+@pytest.mark.parametrize("p", [FR, py.FQ])
+def test_binary_euclid_inverse(p):
+    rnd = random.Random(3)
+    R = 1 << 256
+    for a in [1, 2, 3, p - 1, p - 2, (p + 1) // 2, 1 << 128, (1 << 253) % p] + [rnd.randrange(1, p) for _ in range(200)]:
+        assert inv_binary_euclid(a, p) == pow(a, p - 2, p)
+        # Montgomery bookkeeping of the device routine: input aR, raw inverse (aR)^-1, one Montgomery product with R^3
+        raw = inv_binary_euclid(a * R % p, p)
+        assert raw * pow(R, 3, p) % p * pow(R, p - 2, p) % p == pow(a, p - 2, p) * R % p
+    assert inv_binary_euclid(0, p) == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def segmented_scan_finish(keys, vals):
+    """msm_partials_finish with integers standing in for group elements: compact the non-empty slots, Hillis-Steele scan
+    restricted to equal (ascending) keys, stop when a step adds nothing, the last slot of every run is the bucket"""
+    ck = [k for k in keys if k is not None]
+    cur = [v for k, v in zip(keys, vals) if k is not None]
+    m, d, steps = len(ck), 1, 0
+    while d < m or d == 1:
+        nxt, added = list(cur), False
+        for i in range(m):
+            if i >= d and ck[i - d] == ck[i]:
+                nxt[i] = cur[i] + cur[i - d]
+                added = True
+        cur, steps = nxt, steps + 1
+        if not added:
+            break
+        d <<= 1
+    return {ck[i]: cur[i] for i in range(m) if i + 1 == m or ck[i + 1] != ck[i]}, steps
+
+
+def test_segmented_scan_merges_partial_runs():
+    rnd = random.Random(11)
+    for trial in range(200):
+        n = rnd.randrange(0, 80)
+        runs = sorted(rnd.randrange(1, 12) for _ in range(rnd.randrange(1, 10)))
+        keys, vals = [], []
+        while len(keys) < n:
+            if rnd.random() < 0.3:
+                keys.append(None), vals.append(0)
+            else:
+                keys.append(rnd.choice(runs)), vals.append(rnd.randrange(1000))
+        it = iter(sorted(k for k in keys if k is not None))  # non-empty keys ascend; empty slots stay interleaved
+        keys = [None if k is None else next(it) for k in keys]
+        want = {}
+        for k, v in zip(keys, vals):
+            if k is not None:
+                want[k] = want.get(k, 0) + v
+        got, steps = segmented_scan_finish(keys, vals)
+        assert got == want
+        longest = max([sum(1 for k in keys if k == key) for key in want] + [1])
+        assert steps <= max(1, (longest - 1).bit_length()) + 1  # early exit: log2(longest run) + 1 steps
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def segment_bounds(n, weights):
+    """msm_run: cumulative weights -> range ends rounded up to 256 points, empty ranges dropped, last end = n"""
+    total, run, lo = sum(weights), 0.0, [0]
+    for s, w in enumerate(weights):
+        run += w
+        hi = n if s == len(weights) - 1 else min(n, (int(n * run / total) + 255) & ~255)
+        if hi > lo[-1]:
+            lo.append(hi)
+    return lo
+
+
+def test_streamed_msm_ranges_partition_the_points():
+    for n in (1, 2, 255, 256, 257, 1000, 70001, 1 << 19, (1 << 24) + 5):
+        for weights in ([1], [1, 1], [1, 3, 9], [1] * 8, [1, 1000], [5, 0.001]):
+            lo = segment_bounds(n, weights)
+            assert lo[0] == 0 and lo[-1] == n and all(a < b for a, b in zip(lo, lo[1:])) and len(lo) - 1 <= len(weights)
+            assert all(x % 256 == 0 for x in lo[1:-1])
