@@ -314,6 +314,7 @@ __global__ void __launch_bounds__(SC_THREADS) sc_finalize_peers(const Fr* partia
     for (int x = 0; x <= d; x++) v[x] = fp_add<FrParams>(v[x], partials[(size_t)b * (d + 1) + x]);
   block_sum_many(v, d + 1, s_part, s_evals);
   const PeerSlot* got = peer_exchange(peers, rank, G, seq, s_evals, d + 1);
+  if (threadIdx.x == 0 && *reinterpret_cast<volatile uint32_t*>(&peers[rank]->timed_out)) head->peer_fault = 1;
   if ((int)threadIdx.x <= d) {
     Fr sum = fp_zero<FrParams>();
     for (int g = 0; g < G; g++) sum = fp_add<FrParams>(sum, ld_fresh(&got->data[g][threadIdx.x]));
@@ -406,9 +407,17 @@ __global__ void __launch_bounds__(SC_THREADS) sc_tail(ScTables tabs, ScTailBufs 
 }
 
 // ---- small helper kernels ---------------------------------------------------------------------------------------------------------
-// absorb num_vars (u64 LE) and claimed_sum (sumcheck.rs:35-36)
-__global__ void sc_header(ScHead* head, uint64_t num_vars, Fr claimed_sum) {
+// Opens a proof in one launch: the caller's transcript state; for a zero-check the n challenges drawn before the header
+// (zerocheck.rs:20-22); then num_vars (u64 LE) and claimed_sum are absorbed (sumcheck.rs:35-36).
+__global__ void sc_begin(ScHead* head, const uint8_t* state_in, uint64_t num_vars, Fr claimed_sum, int zc_n, Fr* z) {
+  for (int i = 0; i < 32; i++) head->tstate[i] = state_in[i];
+  head->r = fp_zero<FrParams>();
+  head->evaluation = fp_zero<FrParams>();
+  head->zc_prefix = fp_one<FrParams>();
+  head->zc_prefix_prev = fp_one<FrParams>();
+  head->peer_fault = 0;
   uint32_t* state = reinterpret_cast<uint32_t*>(head->tstate);
+  for (int i = 0; i < zc_n; i++) z[i] = tr_draw_fr_words(state);
   uint32_t buf[16];
   for (int i = 0; i < 16; i++) buf[i] = 0;
   buf[8] = (uint32_t)num_vars;
@@ -417,10 +426,6 @@ __global__ void sc_header(ScHead* head, uint64_t num_vars, Fr claimed_sum) {
   const Fr can = fp_from_mont<FrParams>(claimed_sum);
   for (int i = 0; i < 8; i++) buf[8 + i] = can.v[i];
   tr_absorb_words(state, buf, 32);
-}
-// zerocheck.rs:20-22: n challenges drawn before the sumcheck header
-__global__ void zc_draw_point(ScHead* head, int n, Fr* z) {
-  for (int i = 0; i < n; i++) z[i] = tr_draw_fr_words(reinterpret_cast<uint32_t*>(head->tstate));
 }
 // eq(x, z) tables over the low `a` variables and the remaining high variables
 __global__ void eq_half_tables(const Fr* z, int n, int a, Fr* lo_tab, Fr* hi_tab) {
@@ -485,13 +490,6 @@ __global__ void sc_build_vinv(int d, Fr* vinv) {
   }
   Fr inv = fp_inv<FrParams>(denom);
   for (int i = 0; i <= d; i++) vinv[i * (d + 1) + j] = fp_mul<FrParams>(c[i], inv);
-}
-__global__ void sc_set_state(ScHead* head, const uint8_t* state) {
-  for (int i = 0; i < 32; i++) head->tstate[i] = state[i];
-  head->r = fp_zero<FrParams>();
-  head->evaluation = fp_zero<FrParams>();
-  head->zc_prefix = fp_one<FrParams>();
-  head->zc_prefix_prev = fp_one<FrParams>();
 }
 
 
@@ -806,21 +804,37 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
   cudaStream_t st = ctx->stream;
   QZ_CUDA(ctx, cudaEventRecord(ctx->ev_call0, st));
 
-  // device-resident proof state and outputs
-  ScHead* head = (ScHead*)ctx->arena_alloc(sizeof(ScHead));
-  uint8_t* d_state_in = (uint8_t*)ctx->arena_alloc(32);
-  Fr* d_coeffs = (Fr*)ctx->arena_alloc(sizeof(Fr) * std::max<size_t>(1, num_vars * max_coeffs));
-  uint32_t* d_lens = (uint32_t*)ctx->arena_alloc(4 * std::max<size_t>(1, num_vars));
-  Fr* d_point = (Fr*)ctx->arena_alloc(sizeof(Fr) * std::max<size_t>(1, num_vars));
-  Fr* d_z = (Fr*)ctx->arena_alloc(sizeof(Fr) * std::max<size_t>(1, num_vars));
-  ScProgram* d_prog = (ScProgram*)ctx->arena_alloc(sizeof(ScProgram));
-  Fr* d_consts = (Fr*)ctx->arena_alloc(sizeof(Fr) * std::max<size_t>(1, n_consts));
-  if (!head || !d_state_in || !d_coeffs || !d_lens || !d_point || !d_z || !d_prog || !d_consts)
-    return ctx->fail(QZ_ERR_ALLOC, "sumcheck state");
-  QZ_CUDA(ctx, cudaMemcpyAsync(d_state_in, state, 32, cudaMemcpyHostToDevice, st));
-  QZ_CUDA(ctx, cudaMemcpyAsync(d_prog, &cp.prog, sizeof(ScProgram), cudaMemcpyHostToDevice, st));
-  if (n_consts) QZ_CUDA(ctx, cudaMemcpyAsync(d_consts, consts, 32 * n_consts, cudaMemcpyHostToDevice, st));
-  QZ_LAUNCH(ctx, sc_set_state, 1, 1, 0, head, d_state_in);
+  // Device-resident proof state.  The small inputs (transcript state, program, constants) travel in ONE copy from the
+  // pinned staging buffer and the outputs (head, coefficients, lengths, point, z) come back in ONE copy: every extra
+  // cudaMemcpyAsync is ~5-10 us on a call whose fixed cost is otherwise ~100 us.
+  auto up32 = [](size_t v) { return (v + 31) & ~(size_t)31; };
+  const size_t in_state = 0, in_prog = 32, in_consts = in_prog + up32(sizeof(ScProgram)), in_bytes = in_consts + 32 * n_consts;
+  const size_t coeff_bytes = 32 * num_vars * max_coeffs, lens_bytes = 4 * num_vars, pt_bytes = 32 * num_vars;
+  const size_t o_head = 0, o_coeffs = up32(sizeof(ScHead)), o_lens = o_coeffs + coeff_bytes, o_point = o_lens + up32(lens_bytes),
+               o_z = o_point + pt_bytes, out_bytes = o_z + pt_bytes;
+  uint8_t* d_in = (uint8_t*)ctx->arena_alloc(in_bytes);
+  uint8_t* d_out = (uint8_t*)ctx->arena_alloc(out_bytes);
+  uint8_t* pin = (uint8_t*)ctx->pinned_buf(up32(in_bytes) + out_bytes);
+  if (!d_in || !d_out || !pin) return ctx->fail(QZ_ERR_ALLOC, "sumcheck state");
+  uint8_t* pin_out = pin + up32(in_bytes);
+  ScHead* head = (ScHead*)(d_out + o_head);
+  Fr* d_coeffs = (Fr*)(d_out + o_coeffs);
+  uint32_t* d_lens = (uint32_t*)(d_out + o_lens);
+  Fr* d_point = (Fr*)(d_out + o_point);
+  Fr* d_z = (Fr*)(d_out + o_z);
+  ScProgram* d_prog = (ScProgram*)(d_in + in_prog);
+  Fr* d_consts = (Fr*)(d_in + in_consts);
+  memcpy(pin + in_state, state, 32);
+  memcpy(pin + in_prog, &cp.prog, sizeof(ScProgram));
+  if (n_consts) memcpy(pin + in_consts, consts, 32 * n_consts);
+  QZ_CUDA(ctx, cudaMemcpyAsync(d_in, pin, in_bytes, cudaMemcpyHostToDevice, st));
+  {
+    Fr cs;
+    memset(&cs, 0, sizeof cs);
+    if (!zerocheck) memcpy(cs.v, claimed_sum, 32);
+    QZ_LAUNCH(ctx, sc_begin, 1, 1, 0, head, (const uint8_t*)(d_in + in_state), (uint64_t)num_vars, cs,
+              zerocheck ? (int)num_vars : 0, d_z);  // zerocheck.rs:20-22, sumcheck.rs:35-36
+  }
 
   // tables referenced by h: device copies (host input) or the caller's device buffers
   ScTables tabs;
@@ -845,21 +859,12 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
   // zero-check fast path (see sc_round_zc): h is a product of up to three tables, one GPU, at least one streaming round
   const bool zc_fast = zerocheck && G == 1 && eq_slot >= 0 && cp.product_k >= 2 && cp.product_k <= 4 &&
                        N > ((uint64_t)1 << SC_TAIL_LOG) && !getenv("QZ_ZC_STREAM_EQ");
-  if (zerocheck) {
-    QZ_LAUNCH(ctx, zc_draw_point, 1, 1, 0, head, (int)num_vars, d_z);  // zerocheck.rs:20-22
-    if (eq_slot >= 0 && !zc_fast) {
-      void* p = ctx->arena_alloc(32 * N);
-      if (!p) return ctx->fail(QZ_ERR_ALLOC, "eq table");
-      rc = eq_table_device(ctx, (int)num_vars, d_z, (uint4*)p, (uint64_t)ctx->rank * N * (G > 1), N);  // zerocheck.rs:25
-      if (rc) return rc;
-      tabs.in[eq_slot] = (const uint4*)p;
-    }
-  }
-  {
-    Fr cs;
-    memset(&cs, 0, sizeof cs);
-    if (!zerocheck) memcpy(cs.v, claimed_sum, 32);
-    QZ_LAUNCH(ctx, sc_header, 1, 1, 0, head, (uint64_t)num_vars, cs);  // sumcheck.rs:35-36
+  if (zerocheck && eq_slot >= 0 && !zc_fast) {
+    void* p = ctx->arena_alloc(32 * N);
+    if (!p) return ctx->fail(QZ_ERR_ALLOC, "eq table");
+    rc = eq_table_device(ctx, (int)num_vars, d_z, (uint4*)p, (uint64_t)ctx->rank * N * (G > 1), N);  // zerocheck.rs:25
+    if (rc) return rc;
+    tabs.in[eq_slot] = (const uint4*)p;
   }
 
   if (num_vars > 0) {
@@ -1049,35 +1054,18 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
   if (zerocheck && num_vars > 0) QZ_LAUNCH(ctx, zc_finish, 1, 1, 0, head, d_z, d_point, (int)num_vars);
 
   // results -> pinned staging -> caller
-  const size_t coeff_bytes = 32 * num_vars * max_coeffs, lens_bytes = 4 * num_vars, pt_bytes = 32 * num_vars;
-  uint8_t* pin = (uint8_t*)ctx->pinned_buf(sizeof(ScHead) + coeff_bytes + lens_bytes + 2 * pt_bytes);
-  if (!pin) return ctx->fail(QZ_ERR_ALLOC, "pinned staging");
-  size_t off = 0;
-  QZ_CUDA(ctx, cudaMemcpyAsync(pin, head, sizeof(ScHead), cudaMemcpyDeviceToHost, st));
-  off += sizeof(ScHead);
-  if (num_vars) {
-    QZ_CUDA(ctx, cudaMemcpyAsync(pin + off, d_coeffs, coeff_bytes, cudaMemcpyDeviceToHost, st));
-    QZ_CUDA(ctx, cudaMemcpyAsync(pin + off + coeff_bytes, d_lens, lens_bytes, cudaMemcpyDeviceToHost, st));
-    QZ_CUDA(ctx, cudaMemcpyAsync(pin + off + coeff_bytes + lens_bytes, d_point, pt_bytes, cudaMemcpyDeviceToHost, st));
-    if (zerocheck)
-      QZ_CUDA(ctx, cudaMemcpyAsync(pin + off + coeff_bytes + lens_bytes + pt_bytes, d_z, pt_bytes,
-                                   cudaMemcpyDeviceToHost, st));
-  }
+  QZ_CUDA(ctx, cudaMemcpyAsync(pin_out, d_out, zerocheck ? out_bytes : o_z, cudaMemcpyDeviceToHost, st));
   QZ_CUDA(ctx, cudaEventRecord(ctx->ev_call1, st));
   QZ_CUDA(ctx, cudaStreamSynchronize(st));
-  if (G > 1 && comm_has_peers(ctx)) {
-    uint32_t dead = 0;
-    QZ_CUDA(ctx, cudaMemcpy(&dead, &((PeerMailbox*)ctx->mbox)->timed_out, 4, cudaMemcpyDeviceToHost));
-    if (dead) return ctx->fail(QZ_ERR_NCCL, "a peer did not deliver its partial sums (peer mailbox wait timed out)");
-  }
-  const ScHead* h = (const ScHead*)pin;
+  const ScHead* h = (const ScHead*)(pin_out + o_head);
+  if (h->peer_fault) return ctx->fail(QZ_ERR_NCCL, "a peer did not deliver its partial sums (peer mailbox wait timed out)");
   memcpy(state, h->tstate, 32);
   memcpy(out_eval, h->evaluation.v, 32);
   if (num_vars) {
-    memcpy(out_coeffs, pin + off, coeff_bytes);
-    memcpy(out_lens, pin + off + coeff_bytes, lens_bytes);
-    memcpy(out_point, pin + off + coeff_bytes + lens_bytes, pt_bytes);
-    if (zerocheck) memcpy(out_z, pin + off + coeff_bytes + lens_bytes + pt_bytes, pt_bytes);
+    memcpy(out_coeffs, pin_out + o_coeffs, coeff_bytes);
+    memcpy(out_lens, pin_out + o_lens, lens_bytes);
+    memcpy(out_point, pin_out + o_point, pt_bytes);
+    if (zerocheck) memcpy(out_z, pin_out + o_z, pt_bytes);
   }
   cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev_call0, ctx->ev_call1);
   if (num_vars > 0) cudaEventElapsedTime(&ctx->last_ms[1], ctx->ev_k0, ctx->ev_k1);

@@ -35,6 +35,7 @@ struct ScHead {
   // eq-factored zero-check (sumcheck.cu "zero-check fast path"): P_j = prod_{i<j} eq(r_i, z_i) after round j-1 closed,
   // and P_{j-1}, the value it had one round earlier (the hand-over to sc_tail needs it)
   Fr zc_prefix, zc_prefix_prev;
+  uint32_t peer_fault;  // a peer-mailbox wait timed out during this proof (comm.cuh): the results are void
 };
 
 // ---- serialization / transcript (device) -------------------------------------------------------------------------
