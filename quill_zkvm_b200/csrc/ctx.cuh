@@ -139,7 +139,15 @@ struct qz_ctx {
       }
       blocks.clear();
       void* p = nullptr;
-      if (cudaMalloc(&p, total) == cudaSuccess) blocks.push_back(Block{p, total, 0});
+      if (cudaMalloc(&p, total) != cudaSuccess) {
+        cudaGetLastError();
+        pool_trim();
+        if (cudaMalloc(&p, total) != cudaSuccess) {
+          cudaGetLastError();
+          p = nullptr;  // start over from an empty arena: arena_alloc grows it block by block
+        }
+      }
+      if (p) blocks.push_back(Block{p, total, 0});
     }
     for (auto& b : blocks) b.off = 0;
   }
@@ -156,7 +164,12 @@ struct qz_ctx {
     void* p = nullptr;
     if (cudaMalloc(&p, cap) != cudaSuccess) {
       cudaGetLastError();
-      return nullptr;
+      if (pool_parked.empty()) return nullptr;
+      pool_trim();  // the parked caller buffers are the only memory this library can give back
+      if (cudaMalloc(&p, cap) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+      }
     }
     blocks.push_back(Block{p, cap, bytes});
     return p;
