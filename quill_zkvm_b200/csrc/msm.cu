@@ -380,6 +380,32 @@ __global__ void srs_table_fill(const uint8_t* pow_bases, uint8_t* table) {
   }
   affine_store(table + (size_t)idx * 64, xyzz_to_affine(acc));
 }
+// Affine conversion of a thread's batch of points with ONE inversion (Montgomery's trick on the denominators zz * zzz):
+// 8 products per point instead of the 380 of a Fermat inversion.  pts[0 .. cnt) stay in local memory; `store(j, a)`
+// receives the affine point.  Identity points (zz = 0) are skipped in the product and come out as (0, 0).
+template <int MAXN, class Store>
+QZ_DEV void xyzz_batch_to_affine(const Xyzz* pts, int cnt, Store store) {
+  Fq pref[MAXN];
+  Fq run = fp_one<FqParams>();
+  for (int j = 0; j < cnt; j++) {
+    pref[j] = run;
+    if (!xyzz_is_identity(pts[j])) run = fp_mul<FqParams>(run, fp_mul<FqParams>(pts[j].zz, pts[j].zzz));
+  }
+  Fq inv = fp_inv<FqParams>(run);
+  for (int j = cnt - 1; j >= 0; j--) {
+    Affine a;
+    a.x = fp_zero<FqParams>();
+    a.y = fp_zero<FqParams>();
+    if (!xyzz_is_identity(pts[j])) {
+      const Fq dinv = fp_mul<FqParams>(inv, pref[j]);  // 1 / (zz_j zzz_j)
+      inv = fp_mul<FqParams>(inv, fp_mul<FqParams>(pts[j].zz, pts[j].zzz));
+      a.x = fp_mul<FqParams>(pts[j].x, fp_mul<FqParams>(dinv, pts[j].zzz));
+      a.y = fp_mul<FqParams>(pts[j].y, fp_mul<FqParams>(dinv, pts[j].zz));
+    }
+    store(j, a);
+  }
+}
+
 constexpr int SRS_CHUNK = 8;
 __global__ void __launch_bounds__(128) srs_generate(const uint8_t* table, Fr tau, uint64_t n, uint8_t* out) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -392,6 +418,7 @@ __global__ void __launch_bounds__(128) srs_generate(const uint8_t* table, Fr tau
     if ((begin >> bit) & 1) ti = fp_mul<FrParams>(ti, tau);
   }
   const uint64_t end = begin + SRS_CHUNK < n ? begin + SRS_CHUNK : n;
+  Xyzz pts[SRS_CHUNK];
   for (uint64_t i = begin; i < end; i++) {
     const Fr k = fp_from_mont<FrParams>(ti);
     Xyzz acc = xyzz_identity();
@@ -399,26 +426,32 @@ __global__ void __launch_bounds__(128) srs_generate(const uint8_t* table, Fr tau
       const uint32_t d = (k.v[w >> 2] >> (8 * (w & 3))) & 0xffu;
       if (d) acc = xyzz_add_affine(acc, affine_load(table + (size_t)(w * 255 + d - 1) * 64));
     }
-    affine_store(out + i * 64, xyzz_to_affine(acc));
+    pts[i - begin] = acc;
     ti = fp_mul<FrParams>(ti, tau);
   }
+  xyzz_batch_to_affine<SRS_CHUNK>(pts, (int)(end - begin), [&](int j, const Affine& a) { affine_store(out + (begin + j) * 64, a); });
 }
 
 // pre[w * n + i] = 2^(c w) * P_i (affine), w < W: with these multiples every window of a scalar lands in ONE shared set
 // of buckets, so an MSM needs ceil(256 / c) * n mixed additions with a c far larger than a per-window bucket array
 // would allow (c = 22, 12 additions per point at n = 2^24 instead of 16), one bucket reduction and no window-combine
 // doublings.  It costs W x the SRS in HBM (12 GiB at 2^24): a trade a 180 GB part can make.
+// A thread walks its point through the windows in XYZZ and converts PRE_BATCH multiples to affine with one inversion.
+constexpr int PRE_BATCH = 16;
 __global__ void __launch_bounds__(128) srs_precompute(const uint8_t* bases, uint64_t n, int c, int W, uint8_t* pre) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const Affine p = affine_load(bases + i * 64);
   affine_store(pre + i * 64, p);
   Xyzz acc = xyzz_from_affine(p);
-  for (int w = 1; w < W; w++) {
-    for (int j = 0; j < c; j++) acc = xyzz_dbl(acc);
-    const Affine a = xyzz_to_affine(acc);
-    affine_store(pre + ((uint64_t)w * n + i) * 64, a);
-    acc = xyzz_from_affine(a);
+  Xyzz pts[PRE_BATCH];
+  for (int w0 = 1; w0 < W; w0 += PRE_BATCH) {
+    const int cnt = W - w0 < PRE_BATCH ? W - w0 : PRE_BATCH;
+    for (int j = 0; j < cnt; j++) {
+      for (int b = 0; b < c; b++) acc = xyzz_dbl(acc);
+      pts[j] = acc;
+    }
+    xyzz_batch_to_affine<PRE_BATCH>(pts, cnt, [&](int j, const Affine& a) { affine_store(pre + ((uint64_t)(w0 + j) * n + i) * 64, a); });
   }
 }
 
