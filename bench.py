@@ -365,12 +365,10 @@ def run_gpu(args):
     sc_e2e_ms, _ = timed_loop(lambda: prove(st_host, "host"), args.steps, args.warmup)
     assert sc_out["dev_state"].tobytes() == sc_out["host_state"].tobytes()
     # zero-check form of the same workload (config 3): eq table built on the device as a fourth factor, degree 4
-    zc_ms = None
-    if world == 1:
-        def zc_prove():
-            sc_out["zc"] = q.ZeroCheckProof.prove(ctx, st_dev, 0, q.Transcript(b"zerocheck_bench", ctx))
+    def zc_prove():
+        sc_out["zc"] = q.ZeroCheckProof.prove(ctx, st_dev, 0, q.Transcript(b"zerocheck_bench", ctx), sharded=world > 1)
 
-        zc_ms, zc_launches = timed_loop(zc_prove, args.steps, args.warmup)
+    zc_ms, zc_launches = timed_loop(zc_prove, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
 
     # (the nvidia-smi sampler is stopped first: its 200 ms polling contends for the driver and slows these

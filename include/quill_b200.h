@@ -199,6 +199,13 @@ int qz_sumcheck_prove_sharded(qz_ctx* ctx, size_t num_vars, size_t k, const void
                               size_t n_consts, const uint8_t claimed_sum[32], uint8_t state[32], size_t max_coeffs,
                               uint8_t* out_coeffs, uint32_t* out_lens, uint8_t* out_point, uint8_t out_eval[32]);
 
+/* Sharded zero-check: qz_zerocheck_prove over the same table shards; z is drawn identically on every rank, rank g
+ * builds elements [g*2^m, (g+1)*2^m) of the eq table (or of its weight tables), all ranks return the same proof. */
+int qz_zerocheck_prove_sharded(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* table_shards,
+                               int tables_on_device, const qz_expr_node* nodes, size_t n_nodes, const uint8_t* consts,
+                               size_t n_consts, uint8_t state[32], size_t max_coeffs, uint8_t* out_coeffs,
+                               uint32_t* out_lens, uint8_t* out_point, uint8_t out_eval[32], uint8_t* out_z);
+
 /* All-gather of `bytes` host bytes per rank into `recv` (nranks * bytes, rank-major) over the library's communicator:
  * the exchange of (evaluation, S commitment) and of finished openings between the halves above. */
 int qz_comm_allgather_host(qz_ctx* ctx, const void* send, void* recv, size_t bytes);

@@ -24,7 +24,7 @@ SYMBOLS = [
     "qz_msm", "qz_kzg_commit", "qz_kzg_open", "qz_mlpcs_open", "qz_mlpcs_open_begin", "qz_mlpcs_open_finish",
     "qz_compute_s_polynomial",
     "qz_sumcheck_prove", "qz_zerocheck_prove", "qz_eq_table", "qz_logup_denominators",
-    "qz_comm_unique_id", "qz_comm_init", "qz_comm_peer_memory", "qz_msm_sharded", "qz_sumcheck_prove_sharded", "qz_comm_allgather_host",
+    "qz_comm_unique_id", "qz_comm_init", "qz_comm_peer_memory", "qz_msm_sharded", "qz_sumcheck_prove_sharded", "qz_zerocheck_prove_sharded", "qz_comm_allgather_host",
     "qz_last_elapsed_ms", "qz_last_stat", "qz_bench_imad", "qz_bench_fp_mul",
     "qz_test_field_op", "qz_test_g1_add", "qz_test_g1_mul",
 ]
@@ -102,6 +102,7 @@ def load():
     lib.qz_sumcheck_prove.argtypes = sc
     lib.qz_sumcheck_prove_sharded.argtypes = sc
     lib.qz_zerocheck_prove.argtypes = [vp, sz, sz, vp, i32, vp, sz, vp, sz, vp, sz, vp, vp, vp, vp, vp]
+    lib.qz_zerocheck_prove_sharded.argtypes = lib.qz_zerocheck_prove.argtypes
     lib.qz_eq_table.argtypes = [vp, sz, vp, vp, i32]
     lib.qz_logup_denominators.argtypes = [vp, sz, sz, vp, i32, vp, sz, vp, sz, vp, sz, vp, vp, i32]
     lib.qz_comm_unique_id.argtypes = [vp]

@@ -551,8 +551,9 @@ class ZeroCheckProof:
     z: np.ndarray  # the eq challenges (not part of the reference struct; exposed for checking)
 
     @staticmethod
-    def prove(ctx: Context, store: VirtualPolynomialStore, h: int, transcript: Transcript):
-        """zerocheck.rs:14-49 -> (ZeroCheckProof, EvaluationClaim).  The eq table is built on the device."""
+    def prove(ctx: Context, store: VirtualPolynomialStore, h: int, transcript: Transcript, sharded: bool = False):
+        """zerocheck.rs:14-49 -> (ZeroCheckProof, EvaluationClaim).  The eq table is built on the device.
+        sharded: the store holds this rank's shard of every table (see SumcheckProof.prove)."""
         num_vars = store.num_vars
         nd, cs = store.virtual_polys[h].flatten()
         tabs, k, on_dev = store._tables()
@@ -562,9 +563,10 @@ class ZeroCheckProof:
         point = np.zeros((max(num_vars, 1), 32), dtype=np.uint8)
         z = np.zeros((max(num_vars, 1), 32), dtype=np.uint8)
         ev = np.zeros(32, dtype=np.uint8)
-        ctx.check(ctx.lib.qz_zerocheck_prove(ctx.h, num_vars, k, tabs, on_dev, _ptr(nd), nd.shape[0],
-                                             _ptr(cs) if cs.shape[0] else None, cs.shape[0], _ptr(transcript.state),
-                                             mc, _ptr(coeffs), _ptr(lens), _ptr(point), _ptr(ev), _ptr(z)))
+        fn = ctx.lib.qz_zerocheck_prove_sharded if sharded else ctx.lib.qz_zerocheck_prove
+        ctx.check(fn(ctx.h, num_vars, k, tabs, on_dev, _ptr(nd), nd.shape[0],
+                     _ptr(cs) if cs.shape[0] else None, cs.shape[0], _ptr(transcript.state),
+                     mc, _ptr(coeffs), _ptr(lens), _ptr(point), _ptr(ev), _ptr(z)))
         polys = [coeffs[j, : lens[j]].copy() for j in range(num_vars)]
         sc = SumcheckProof(num_vars, np.zeros(32, dtype=np.uint8), polys)
         return ZeroCheckProof(num_vars, sc, z[:num_vars].copy()), EvaluationClaim(point[:num_vars].copy(), ev)

@@ -382,6 +382,14 @@ int qz_zerocheck_prove(qz_ctx* ctx, size_t num_vars, size_t k, const void* const
   return sumcheck_run(ctx, num_vars, k, tables, tables_on_device, nodes, n_nodes, consts, n_consts, nullptr, state,
                       max_coeffs, out_coeffs, out_lens, out_point, out_eval, true, out_z, false);
 }
+int qz_zerocheck_prove_sharded(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* table_shards,
+                               int tables_on_device, const qz_expr_node* nodes, size_t n_nodes, const uint8_t* consts,
+                               size_t n_consts, uint8_t state[32], size_t max_coeffs, uint8_t* out_coeffs,
+                               uint32_t* out_lens, uint8_t* out_point, uint8_t out_eval[32], uint8_t* out_z) {
+  if (!ctx) return QZ_ERR_INVALID_ARG;
+  return sumcheck_run(ctx, num_vars, k, table_shards, tables_on_device, nodes, n_nodes, consts, n_consts, nullptr, state,
+                      max_coeffs, out_coeffs, out_lens, out_point, out_eval, true, out_z, true);
+}
 int qz_logup_denominators(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tables, int tables_on_device,
                           const qz_expr_node* nodes_h, size_t n_nodes_h, const qz_expr_node* nodes_m, size_t n_nodes_m,
                           const uint8_t* consts, size_t n_consts, const uint8_t gamma[32], void* out, int out_on_device) {

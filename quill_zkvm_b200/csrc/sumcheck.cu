@@ -300,7 +300,8 @@ __global__ void __launch_bounds__(SC_THREADS) sc_finalize(const Fr* partials, in
 __global__ void __launch_bounds__(SC_THREADS) sc_finalize_peers(const Fr* partials, int n_parts, int d,
                                                                PeerMailbox* const* peers, int rank, int G, uint32_t seq,
                                                                ScHead* head, const Fr* vinv, Fr* out_coeffs_row,
-                                                               uint32_t* out_len, Fr* out_point_slot, int max_coeffs) {
+                                                               uint32_t* out_len, Fr* out_point_slot, int max_coeffs,
+                                                               const Fr* zc_z) {
   __shared__ Fr s_part[(SC_THREADS / 32) * SC_MAX_COEFFS];
   __shared__ Fr s_evals[SC_MAX_COEFFS];
   __shared__ Fr s_coef[SC_MAX_COEFFS];
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(SC_THREADS) sc_finalize_peers(const Fr* partia
     s_evals[threadIdx.x] = sum;
   }
   __syncthreads();
-  sc_round_close(head, vinv, d, s_evals, s_coef, s_msg, s_prod, out_coeffs_row, out_len, out_point_slot, max_coeffs);
+  sc_round_close(head, vinv, d, s_evals, s_coef, s_msg, s_prod, out_coeffs_row, out_len, out_point_slot, max_coeffs, zc_z);
 }
 
 // reduce block partials to one vector per rank (sharded mode: the vectors are all-gathered, then sc_finalize)
@@ -856,9 +857,9 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
       tabs.in[j] = (const uint4*)p;
     }
   }
-  // zero-check fast path (see sc_round_zc): h is a product of up to three tables, one GPU, at least one streaming round
-  const bool zc_fast = zerocheck && G == 1 && eq_slot >= 0 && cp.product_k >= 2 && cp.product_k <= 4 &&
-                       N > ((uint64_t)1 << SC_TAIL_LOG) && !getenv("QZ_ZC_STREAM_EQ");
+  // zero-check fast path (see sc_round_zc): h is a product of up to three tables and at least one streaming round runs
+  const bool zc_fast = zerocheck && eq_slot >= 0 && cp.product_k >= 2 && cp.product_k <= 4 &&
+                       N * G > ((uint64_t)1 << SC_TAIL_LOG) && !getenv("QZ_ZC_STREAM_EQ");
   if (zerocheck && eq_slot >= 0 && !zc_fast) {
     void* p = ctx->arena_alloc(32 * N);
     if (!p) return ctx->fail(QZ_ERR_ALLOC, "eq table");
@@ -921,9 +922,9 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
       zb = std::max(1, std::min(zb, std::max(bps, bps_wide)));  // `partials` was sized for max(bps, bps_wide) blocks per SM
       zb_wide = std::min(zb_wide, std::max(bps, bps_wide));
       if (getenv("QZ_SC_NARROW")) zb_wide = 0;
-      // the eq slot's fold scratch holds the weight tables: E_1 (N/2 entries) = eq table of z_1 .. z_{n-1}
+      // the eq slot's fold scratch holds the weight tables: E_1 = eq table of z_1 .. z_{n-1}, this rank's N/2 entries
       uint4* e_buf[2] = {bufA[eq_slot], bufB[eq_slot]};
-      rc = eq_table_device(ctx, (int)num_vars - 1, d_z + 1, e_buf[0], 0, N / 2);
+      rc = eq_table_device(ctx, (int)num_vars - 1, d_z + 1, e_buf[0], (uint64_t)ctx->rank * (N / 2) * (G > 1), N / 2);
       if (rc) return rc;
       int e_cur = 0;
       ScTables gt;  // the K tables of h, in dense order without the eq slot
@@ -934,7 +935,7 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
           gt.in[i] = tabs.in[j];
           g_of[i++] = j;
         }
-      while (size > ((uint64_t)1 << SC_TAIL_LOG)) {
+      while (size * G > ((uint64_t)1 << SC_TAIL_LOG)) {
         const uint64_t n_pairs = pending ? size / 4 : size / 2;
         const bool pdl = pdl_ok && n_pairs <= ((uint64_t)1 << 18);
         for (int i = 0; i < K; i++) gt.out[i] = flip ? bufB[g_of[i]] : bufA[g_of[i]];
@@ -954,8 +955,20 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
             if (wide) QZ_ROUND_ZC(3, true, SC_WIDE_THREADS);
             else QZ_ROUND_ZC(3, false, SC_THREADS);
         }
-        QZ_LAUNCH_PDL(ctx, pdl, sc_finalize, 1, SC_THREADS, (const Fr*)partials, grid, K, head, (const Fr*)vinv_k,
-                      d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc, (const Fr*)(d_z + round));
+        if (G == 1) {
+          QZ_LAUNCH_PDL(ctx, pdl, sc_finalize, 1, SC_THREADS, (const Fr*)partials, grid, K, head, (const Fr*)vinv_k,
+                        d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc, (const Fr*)(d_z + round));
+        } else if (comm_has_peers(ctx)) {
+          QZ_LAUNCH_PDL(ctx, pdl, sc_finalize_peers, 1, SC_THREADS, (const Fr*)partials, grid, K,
+                        (PeerMailbox* const*)ctx->peer_mbox_dev, ctx->rank, G, ++ctx->mbox_seq, head, (const Fr*)vinv_k,
+                        d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc, (const Fr*)(d_z + round));
+        } else {
+          QZ_LAUNCH(ctx, sc_reduce_partials, 1, SC_THREADS, 0, partials, grid, K, rank_evals);
+          rc = comm_allgather(ctx, rank_evals, all_evals, sizeof(Fr) * (K + 1));
+          if (rc) return rc;
+          QZ_LAUNCH(ctx, sc_finalize, 1, SC_THREADS, 0, all_evals, G, K, head, vinv_k, d_coeffs + (size_t)round * mc,
+                    d_lens + round, d_point + round, mc, (const Fr*)(d_z + round));
+        }
         if (pending) {
           for (int i = 0; i < K; i++) gt.in[i] = gt.out[i];
           flip ^= 1;
@@ -1007,7 +1020,7 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
       } else if (comm_has_peers(ctx)) {  // partial sums go straight into the peers' mailboxes (comm.cuh)
         QZ_LAUNCH_PDL(ctx, pdl, sc_finalize_peers, 1, SC_THREADS, (const Fr*)partials, grid, d,
                       (PeerMailbox* const*)ctx->peer_mbox_dev, ctx->rank, G, ++ctx->mbox_seq, head, (const Fr*)vinv,
-                      d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc);
+                      d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc, (const Fr*)nullptr);
       } else {  // every rank sums all ranks' partial evaluations and runs the same transcript
         QZ_LAUNCH(ctx, sc_reduce_partials, 1, SC_THREADS, 0, partials, grid, d, rank_evals);
         rc = comm_allgather(ctx, rank_evals, all_evals, sizeof(Fr) * (d + 1));

@@ -55,6 +55,24 @@ def main():
                 assert np.array_equal(sc.r_polys[j], o["coeffs"][j][: o["lens"][j]]), f"rank {rank} nv {nv} round {j}"
             assert np.array_equal(claim.point, o["point"]) and np.array_equal(claim.evaluation, o["evaluation"])
             assert tr.state.tobytes() == st.tobytes()
+    # ---- zero-check: eq-factored rounds (product) and the streamed eq shard (generic expression) ----
+    for nv in (8, 12, 13, 16, 20):
+        if (1 << nv) < world:
+            continue
+        tabs = [util.rand_fr(1 << nv, 55 * nv + t) for t in range(3)]
+        lo, hi = parallel.table_shard_range(nv, rank, world)
+        for nodes, consts in exprs:
+            store = q.VirtualPolynomialStore(nv)
+            store.polynomials = [np.ascontiguousarray(t[lo:hi]) for t in tabs]
+            h = store.new_virtual_from_expr(util.to_qexpr(nodes, consts))
+            tr = q.Transcript(b"multi_zc", ctx)
+            proof, claim = q.ZeroCheckProof.prove(ctx, store, h, tr, sharded=True)
+            st = co.transcript_new(b"multi_zc")
+            o = co.sumcheck_prove(nv, tabs, nodes, consts, None, st, max_coeffs=q._lib.QZ_MAX_ROUND_COEFFS, zerocheck=True, threads=4)
+            for j in range(nv):
+                assert np.array_equal(proof.sumcheck_proof.r_polys[j], o["coeffs"][j][: o["lens"][j]]), f"rank {rank} zc nv {nv} round {j}"
+            assert np.array_equal(proof.z, o["z"]) and np.array_equal(claim.point, o["point"])
+            assert np.array_equal(claim.evaluation, o["evaluation"]) and tr.state.tobytes() == st.tobytes()
     # ---- HyperPlonk: openings dealt to the ranks (hyperplonk.OpeningBatch), every rank ends with the whole proof ----
     from oracle import fastkzg  # noqa: E402
     from quill_zkvm_b200 import hyperplonk as hp  # noqa: E402
@@ -79,7 +97,7 @@ def main():
             assert g["permutation"][key] == w["permutation"][key], f"rank {rank}: permutation {key} differs"
     dist.barrier()
     if rank == 0:
-        print(f"multi-GPU parity ok on {world} ranks: sharded MSM, sharded sumcheck and the HyperPlonk proof with its "
+        print(f"multi-GPU parity ok on {world} ranks: sharded MSM, sharded sumcheck, sharded zero-check and the HyperPlonk proof with its "
               f"openings dealt to the ranks match the oracle bit for bit "
               f"(exchange: {'peer mailboxes over NVLink' if ctx.peer_memory else 'NCCL all-gather'})")
     ctx.close()
