@@ -1,7 +1,8 @@
 """CPU, world_size 2 over gloo: the sharding the multi-GPU path uses, with the oracle standing in for the
 device.  MSM: per-rank partial sums over contiguous index ranges, gathered and added with the group law.  Sumcheck:
 tables split by the top variable; per round the ranks exchange partial round polynomials and run the same transcript;
-when one entry per rank is left the shards are gathered and the last rounds are replayed by every rank."""
+when one entry per rank is left the shards are gathered and the last rounds are replayed by every rank.  Zero-check:
+the eq-factored rounds with the weight table sharded like the pairs, then the hand-over in the reference's form."""
 import os
 import socket
 import sys
@@ -105,6 +106,85 @@ def _worker(rank, world, port, ret):
                 ev = py.expr_eval_point(h, [g[0] for g in gs])
                 break
         assert (polys, point, ev) == want
+
+        # ---- zero-check sharding, eq-factored rounds (csrc/sumcheck.cu sc_round_zc with G > 1) ----
+        # rank g holds pairs [g * N/2G, ...) of the weight table E_1 = eq(., z_1..z_{n-1}); weights fold by addition, which
+        # is as local as the pairs; per round the ranks exchange the k+1 evaluations of t_j; with two entries per rank left
+        # the eq shard is materialised in the reference's form (last challenge still to fold) and everything is gathered.
+        nv, k = 5, 2
+        tabs = [[rnd.randrange(FR) for _ in range(1 << nv)] for _ in range(k)]
+        hz = py.e_mul(py.e_in(0), py.e_in(1))
+        want_z = py.zerocheck_prove(nv, tabs, hz, py.Transcript(b"shard_zc"))
+        tr = py.Transcript(b"shard_zc")
+        z = [tr.draw_field_element() for _ in range(nv)]
+        tr.append_usize(nv)
+        tr.append_fr(0)
+        lo, hi = parallel.table_shard_range(nv, rank, world)
+        gs = [t[lo:hi] for t in tabs]
+        e1 = py.fast_eq_eval_hypercube(nv - 1, z[1:])
+        weights = e1[lo // 2: hi // 2]
+        prefix, prefix_prev, polys, point = 1, 1, [], []
+
+        def lagrange(evals):  # coefficients from evaluations at 0..len-1
+            n_pts, coeffs = len(evals), [0] * len(evals)
+            for i, yi in enumerate(evals):
+                num, den = [1], 1
+                for m in range(n_pts):
+                    if m != i:
+                        num = py.poly_mul(num, [(-m) % FR, 1])
+                        den = den * (i - m) % FR
+                scale = yi * pow(den, FR - 2, FR) % FR
+                num = num + [0] * (n_pts - len(num))
+                coeffs = [(c + scale * nc) % FR for c, nc in zip(coeffs, num)]
+            return coeffs
+
+        j = 0
+        while True:
+            pairs = len(gs[0]) // 2
+            assert len(weights) == pairs
+            part = []
+            for x in range(k + 1):
+                acc = 0
+                for p in range(pairs):
+                    term = weights[p]
+                    for g in gs:
+                        term = term * (g[2 * p] + x * (g[2 * p + 1] - g[2 * p])) % FR
+                    acc = (acc + term) % FR
+                part.append(acc)
+            evals = [sum(col) % FR for col in zip(*_gather_obj(part, world))]  # the per-round exchange
+            c = lagrange(evals)
+            a, b = prefix * (1 - z[j]) % FR, prefix * (2 * z[j] - 1) % FR
+            s_j = py.trim([(a * (c[t] if t <= k else 0) + b * (c[t - 1] if t >= 1 else 0)) % FR for t in range(k + 2)])
+            tr.append_fr_vec(s_j)
+            polys.append(s_j)
+            r = tr.draw_field_element()
+            point.append(r)
+            prefix_prev, prefix = prefix, prefix * ((r * z[j] + (1 - r) * (1 - z[j])) % FR) % FR
+            j += 1
+            if len(gs[0]) == 2:
+                break  # hand over with the fold by r pending, as the device does at 2^11 entries
+            gs = [[(g[2 * p] + r * (g[2 * p + 1] - g[2 * p])) % FR for p in range(pairs)] for g in gs]
+            weights = [(weights[2 * p] + weights[2 * p + 1]) % FR for p in range(pairs // 2)]
+        eq_local = [prefix_prev * (1 - z[j - 1]) % FR * weights[0] % FR, prefix_prev * z[j - 1] % FR * weights[0] % FR]
+        rest = _gather_obj((gs, eq_local), world)  # rank order = index order
+        full = [[v for rk in range(world) for v in rest[rk][0][t]] for t in range(k)] + [[v for rk in range(world) for v in rest[rk][1]]]
+        h_hat = py.e_mul(hz, py.e_in(k))
+        r_pending, ev = point[-1], 0
+        while True:  # the reference's rounds on h * eq from here on (sc_tail)
+            full = [[(g[2 * p] + r_pending * (g[2 * p + 1] - g[2 * p])) % FR for p in range(len(g) // 2)] for g in full]
+            if len(full[0]) == 1:
+                ev = py.expr_eval_point(h_hat, [g[0] for g in full])
+                break
+            msg = []
+            for p in range(len(full[0]) // 2):
+                lin = [py.trim([g[2 * p], g[2 * p + 1] - g[2 * p]]) for g in full]
+                msg = py.poly_add(msg, py.expr_eval_poly(h_hat, lin))
+            tr.append_fr_vec(msg)
+            polys.append(msg)
+            r_pending = tr.draw_field_element()
+            point.append(r_pending)
+        ev = ev * py.fr_inv(py.eq_eval(z, point)) % FR
+        assert (polys, point, ev, z) == (want_z[0], want_z[1], want_z[2] % FR, want_z[3])
 
         # ---- MLPCS openings dealt to the ranks (hyperplonk.OpeningBatch): the halves before / after the challenge ----
         from quill_zkvm_b200 import hyperplonk as hp
