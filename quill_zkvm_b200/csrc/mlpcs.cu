@@ -68,6 +68,15 @@ struct NttTile {
     hi[i] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
   }
 };
+// Twiddles.  Stage s pairs index i with i + m / 2^(s+1) and multiplies the difference by w^((i mod m / 2^(s+1)) 2^s); with
+// i = hi | t | lo that exponent is (j_l * stride + lo) << s, one distinct twiddle per butterfly of a strided pass -- a
+// 32-byte gather each, which bound those passes (ncu: l1tex 90 % of peak, 0.90 / 0.98 ms against 0.59 ms for the pass
+// whose twiddles do not depend on lo).  The exponent splits: w^((j_l * stride) << s) is the same for every sub-tile (a
+// table of 2^(T-1) values that lives in L1), and the lo part, w^(lo 2^s), multiplies the odd output of stage s and then
+// rides through the later (linear) stages unchanged -- both inputs of a later butterfly went through the same branches
+// -- so an element that ends at local index t has collected w^(lo 2^s0 brev_T(t)).  A strided pass is therefore a plain
+// local transform plus ONE correction product per element, applied while the tile is stored (forward) or, inverted,
+// while it is loaded (inverse): the four-step decomposition, done per pass.
 template <bool INVERSE>
 __global__ void __launch_bounds__(NTT_THREADS) ntt_pass(uint4* data, int log_m, int s0, int T, int logC, const Fr* W) {
   __shared__ NttTile tile;
@@ -83,8 +92,15 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass(uint4* data, int log_m, 
       const int u = (idx & ((1 << lu) - 1)) | ((idx >> (T + lu)) << lu), t = (idx >> lu) & ((1 << T) - 1);
       const uint64_t id = tile0 + u, lo = id & (stride - 1), hi = id >> lo_bits;
       const uint4* src = data + 2 * ((hi << (log_m - s0)) + lo + (uint64_t)t * stride);
-      tile.lo[t * C + u] = src[0];
-      tile.hi[t * C + u] = src[1];
+      if (INVERSE && lo) {  // undo the correction first: w^-E, E = lo * brev_T(t) << s0 (< m)
+        const uint64_t E = (lo * (uint64_t)(__brev((unsigned)t) >> (32 - T))) << s0;
+        Fr v = fp_load<FrParams>(src);
+        if (E) v = E > half_m ? fp_mul<FrParams>(v, W[m - E]) : fp_neg<FrParams>(fp_mul<FrParams>(v, W[half_m - E]));
+        tile.set(t * C + u, v);
+      } else {
+        tile.lo[t * C + u] = src[0];
+        tile.hi[t * C + u] = src[1];
+      }
     }
     __syncthreads();
     for (int step = 0; step < T; step++) {
@@ -93,8 +109,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass(uint4* data, int log_m, 
       for (int bb = threadIdx.x; bb < (n_elems >> 1); bb += blockDim.x) {
         const int u = bb & (C - 1), b = bb >> logC;
         const int j_l = b & (lhalf - 1), i0 = (((b - j_l) << 1) + j_l) * C + u, i1 = i0 + lhalf * C;
-        const uint64_t lo = (tile0 + u) & (stride - 1);
-        const uint64_t e = ((uint64_t)j_l * stride + lo) << s;  // twiddle exponent, < m/2
+        const uint64_t e = ((uint64_t)j_l << lo_bits) << s;  // the part of the twiddle exponent all sub-tiles share, < m/2
         const Fr a = tile.get(i0), v = tile.get(i1);
         if (!INVERSE) {
           tile.set(i0, fp_add<FrParams>(a, v));
@@ -113,8 +128,15 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass(uint4* data, int log_m, 
       const int u = (idx & ((1 << lu) - 1)) | ((idx >> (T + lu)) << lu), t = (idx >> lu) & ((1 << T) - 1);
       const uint64_t id = tile0 + u, lo = id & (stride - 1), hi = id >> lo_bits;
       uint4* dst = data + 2 * ((hi << (log_m - s0)) + lo + (uint64_t)t * stride);
-      dst[0] = tile.lo[t * C + u];
-      dst[1] = tile.hi[t * C + u];
+      if (!INVERSE && lo) {  // the correction: w^E, E = lo * brev_T(t) << s0 (< m)
+        const uint64_t E = (lo * (uint64_t)(__brev((unsigned)t) >> (32 - T))) << s0;
+        Fr v = tile.get(t * C + u);
+        if (E) v = E < half_m ? fp_mul<FrParams>(v, W[E]) : fp_neg<FrParams>(fp_mul<FrParams>(v, W[E - half_m]));
+        fp_store<FrParams>(dst, v);
+      } else {
+        dst[0] = tile.lo[t * C + u];
+        dst[1] = tile.hi[t * C + u];
+      }
     }
     __syncthreads();
   }

@@ -9,6 +9,7 @@ is pinned independently of the GPU tests:
   * the inverse by the binary extended Euclidean algorithm (csrc/ff.cuh fp_inv_serial)
   * the merge of partial bucket runs by a segmented scan with early exit (csrc/msm.cu msm_partials_finish)
   * the streamed MSM's point ranges (csrc/msm.cu msm_run)
+  * NTT passes as plain local transforms + one correction product per element (csrc/mlpcs.cu ntt_pass)
 """
 import os
 import random
@@ -259,3 +260,74 @@ def test_streamed_msm_ranges_partition_the_points():
             lo = segment_bounds(n, weights)
             assert lo[0] == 0 and lo[-1] == n and all(a < b for a, b in zip(lo, lo[1:])) and len(lo) - 1 <= len(weights)
             assert all(x % 256 == 0 for x in lo[1:-1])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+NTT_P = 12289  # 3 * 2^12 + 1: a small NTT-friendly prime stands in for Fr (the identity is about exponents of w)
+
+
+def _ntt_root(order):
+    w = pow(11, (NTT_P - 1) // order, NTT_P)
+    assert pow(w, order, NTT_P) == 1 and pow(w, order // 2, NTT_P) != 1
+    return w
+
+
+def _brev(x, bits):
+    return int(format(x, f"0{bits}b")[::-1], 2) if bits else 0
+
+
+def ntt_dif_reference(a, log_m):
+    """radix-2 decimation in frequency, natural -> bit-reversed, full twiddle w^((i mod half) << s) at stage s"""
+    m, w, a = 1 << log_m, _ntt_root(1 << log_m), list(a)
+    for s in range(log_m):
+        half = m >> (s + 1)
+        for i in range(m):
+            if (i // half) % 2 == 0:
+                u, v = a[i], a[i + half]
+                a[i], a[i + half] = (u + v) % NTT_P, (u - v) * pow(w, (i % half) << s, NTT_P) % NTT_P
+    return a
+
+
+def ntt_pass_model(a, log_m, s0, T, inverse):
+    """ntt_pass: stages [s0, s0 + T) on the sub-tiles (hi, lo); butterflies use only the twiddle part shared by all
+    sub-tiles, and element t is corrected by w^(+-(lo * brev_T(t) << s0)) on the way out (forward) / in (inverse)"""
+    m, w, a = 1 << log_m, _ntt_root(1 << log_m), list(a)
+    lo_bits = log_m - s0 - T
+    for hi in range(1 << s0):
+        for lo in range(1 << lo_bits):
+            idx = [(hi << (log_m - s0)) + lo + (t << lo_bits) for t in range(1 << T)]
+            tile = [a[i] for i in idx]
+            if inverse and lo:
+                tile = [v * pow(w, (m - ((lo * _brev(t, T)) << s0)) % m, NTT_P) % NTT_P for t, v in enumerate(tile)]
+            for ls in (range(T - 1, -1, -1) if inverse else range(T)):
+                lhalf, s = 1 << (T - 1 - ls), s0 + ls
+                for b in range(1 << (T - 1)):
+                    j_l = b & (lhalf - 1)
+                    i0 = ((b - j_l) << 1) + j_l
+                    i1, e = i0 + lhalf, (j_l << lo_bits) << s
+                    u, v = tile[i0], tile[i1]
+                    if not inverse:
+                        tile[i0], tile[i1] = (u + v) % NTT_P, (u - v) * pow(w, e, NTT_P) % NTT_P
+                    else:
+                        vw = v * pow(w, (m - e) % m, NTT_P) % NTT_P
+                        tile[i0], tile[i1] = (u + vw) % NTT_P, (u - vw) % NTT_P
+            if not inverse and lo:
+                tile = [v * pow(w, (lo * _brev(t, T)) << s0, NTT_P) % NTT_P for t, v in enumerate(tile)]
+            for t, i in enumerate(idx):
+                a[i] = tile[t]
+    return a
+
+
+@pytest.mark.parametrize("log_m,groups", [(5, (5,)), (6, (3, 3)), (6, (2, 2, 2)), (7, (3, 2, 2)), (8, (3, 3, 2)), (10, (4, 3, 3))])
+def test_ntt_passes_with_per_pass_correction(log_m, groups):
+    rnd = random.Random(log_m)
+    a = [rnd.randrange(NTT_P) for _ in range(1 << log_m)]
+    got, s0 = list(a), 0
+    for T in groups:
+        got = ntt_pass_model(got, log_m, s0, T, False)
+        s0 += T
+    assert got == ntt_dif_reference(a, log_m)
+    for T in reversed(groups):  # the inverse passes, last group first, undo it up to the factor m
+        s0 -= T
+        got = ntt_pass_model(got, log_m, s0, T, True)
+    assert got == [x * (1 << log_m) % NTT_P for x in a]
