@@ -837,6 +837,14 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
               zerocheck ? (int)num_vars : 0, d_z);  // zerocheck.rs:20-22, sumcheck.rs:35-36
   }
 
+  // Host tables of a large proof are copied in UP_CHUNKS slices on the second stream and round 0 (evaluate only: every
+  // pair is independent) runs slice by slice behind the copies, so only the last slice's round-0 work is exposed after
+  // the PCIe transfer; from round 1 on the challenge depends on all of the data.
+  constexpr int UP_CHUNKS = 8;
+  const int up_chunks = (!tables_on_device && G == 1 && !zerocheck && N >= ((uint64_t)1 << 21)) ? UP_CHUNKS : 1;
+  uint8_t* up_dst[SC_MAX_K];
+  const uint8_t* up_src[SC_MAX_K];
+  int n_up = 0;
   // tables referenced by h: device copies (host input) or the caller's device buffers
   ScTables tabs;
   memset(&tabs, 0, sizeof tabs);
@@ -853,7 +861,12 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
     } else {
       void* p = ctx->arena_alloc(32 * N);
       if (!p) return ctx->fail(QZ_ERR_ALLOC, "table copy");
-      QZ_CUDA(ctx, cudaMemcpyAsync(p, tables[orig], 32 * N, cudaMemcpyHostToDevice, st));
+      if (up_chunks > 1) {  // copied chunk by chunk under round 0 (below)
+        up_dst[n_up] = (uint8_t*)p;
+        up_src[n_up++] = (const uint8_t*)tables[orig];
+      } else {
+        QZ_CUDA(ctx, cudaMemcpyAsync(p, tables[orig], 32 * N, cudaMemcpyHostToDevice, st));
+      }
       tabs.in[j] = (const uint4*)p;
     }
   }
@@ -893,7 +906,7 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
     } else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sc_round_generic, SC_THREADS, 0);
     if (bps < 1) bps = 1;
     if (getenv("QZ_SC_NARROW")) bps_wide = 0;  // measurement switch: force the fully reduced sums
-    Fr* partials = (Fr*)ctx->arena_alloc(sizeof(Fr) * (size_t)ctx->sm_count * std::max(bps, bps_wide) * (d + 1));
+    Fr* partials = (Fr*)ctx->arena_alloc(sizeof(Fr) * (size_t)ctx->sm_count * std::max(bps, bps_wide) * (d + 1) * up_chunks);
     Fr* rank_evals = (Fr*)ctx->arena_alloc(sizeof(Fr) * (d + 1));
     Fr* all_evals = (Fr*)ctx->arena_alloc(sizeof(Fr) * (size_t)(d + 1) * G);
     if (!partials || !rank_evals || !all_evals) return ctx->fail(QZ_ERR_ALLOC, "partials");
@@ -987,17 +1000,12 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
       for (int i = 0; i < K; i++) tabs.in[g_of[i]] = gt.in[i];
       tabs.in[eq_slot] = eq_full;
     }
-    while (!zc_fast && size * G > ((uint64_t)1 << SC_TAIL_LOG)) {
-      const uint64_t n_pairs = pending ? size / 4 : size / 2;
-      const bool pdl = pdl_ok && n_pairs <= ((uint64_t)1 << 18);
-      for (int j = 0; j < ka; j++) tabs.out[j] = flip ? bufB[j] : bufA[j];
-      // deferred reduction pays once a thread sums several pairs (its one-off reduction is 3 products per sum)
-      const bool wide = bps_wide > 0 && n_pairs >= (uint64_t)8 * SC_WIDE_THREADS * ctx->sm_count * bps_wide;
-      const int grid = wide ? round_grid(ctx, n_pairs, bps_wide, SC_WIDE_THREADS) : round_grid(ctx, n_pairs, bps);
+    // one round kernel over `n_pairs` pairs of `tb` (fold of the pending challenge fused when `pend`)
+    auto launch_round = [&](const ScTables& tb, uint64_t n_pairs, int pend, int grid, bool wide, bool pdl, Fr* parts) -> int {
 #define QZ_ROUND_PROD(K, W, T)                                                                                  \
   do {                                                                                                          \
-    if (pending) QZ_LAUNCH_PDL(ctx, pdl, (sc_round_prod<K, W, true>), grid, T, tabs, n_pairs, (const ScHead*)head, partials); \
-    else QZ_LAUNCH_PDL(ctx, pdl, (sc_round_prod<K, W, false>), grid, T, tabs, n_pairs, (const ScHead*)head, partials);        \
+    if (pend) QZ_LAUNCH_PDL(ctx, pdl, (sc_round_prod<K, W, true>), grid, T, tb, n_pairs, (const ScHead*)head, parts); \
+    else QZ_LAUNCH_PDL(ctx, pdl, (sc_round_prod<K, W, false>), grid, T, tb, n_pairs, (const ScHead*)head, parts);     \
   } while (0)
       switch (cp.product_k) {
         case 1: QZ_ROUND_PROD(1, false, SC_THREADS); break;
@@ -1011,9 +1019,43 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
           else QZ_ROUND_PROD(4, false, SC_THREADS);
           break;
         default:
-          QZ_LAUNCH_PDL(ctx, pdl, sc_round_generic, grid, SC_THREADS, tabs, n_pairs, pending, (const ScHead*)head,
-                        (const ScProgram*)d_prog, (const Fr*)d_consts, partials);
+          QZ_LAUNCH_PDL(ctx, pdl, sc_round_generic, grid, SC_THREADS, tb, n_pairs, pend, (const ScHead*)head,
+                        (const ScProgram*)d_prog, (const Fr*)d_consts, parts);
       }
+      return QZ_OK;
+    };
+    if (up_chunks > 1) {  // round 0 behind the host -> device copies, slice by slice
+      if (ctx->ensure_prep_stream()) return ctx->fail(QZ_ERR_CUDA, "prep stream");
+      cudaStream_t ps = ctx->prep_stream;
+      QZ_CUDA(ctx, cudaEventRecord(ctx->ev_entry, st));  // earlier users of the arena are done before the copies land
+      QZ_CUDA(ctx, cudaStreamWaitEvent(ps, ctx->ev_entry, 0));
+      const uint64_t per = N / up_chunks, pairs_c = per / 2;
+      const bool wide = bps_wide > 0 && pairs_c >= (uint64_t)8 * SC_WIDE_THREADS * ctx->sm_count * bps_wide;
+      const int grid_c = wide ? round_grid(ctx, pairs_c, bps_wide, SC_WIDE_THREADS) : round_grid(ctx, pairs_c, bps);
+      for (int c = 0; c < up_chunks; c++) {
+        for (int u = 0; u < n_up; u++)
+          QZ_CUDA(ctx, cudaMemcpyAsync(up_dst[u] + 32 * per * c, up_src[u] + 32 * per * c, 32 * per, cudaMemcpyHostToDevice, ps));
+        QZ_CUDA(ctx, cudaEventRecord(ctx->ev_seg_ready[c], ps));
+        QZ_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_seg_ready[c], 0));
+        ScTables slice = tabs;
+        for (int j = 0; j < ka; j++) slice.in[j] = tabs.in[j] + 2 * per * c;
+        rc = launch_round(slice, pairs_c, 0, grid_c, wide, false, partials + (size_t)c * grid_c * (d + 1));
+        if (rc) return rc;
+      }
+      QZ_LAUNCH(ctx, sc_finalize, 1, SC_THREADS, 0, (const Fr*)partials, grid_c * up_chunks, d, head, (const Fr*)vinv, d_coeffs,
+                d_lens, d_point, mc, (const Fr*)nullptr);
+      pending = 1;
+      round = 1;
+    }
+    while (!zc_fast && size * G > ((uint64_t)1 << SC_TAIL_LOG)) {
+      const uint64_t n_pairs = pending ? size / 4 : size / 2;
+      const bool pdl = pdl_ok && n_pairs <= ((uint64_t)1 << 18);
+      for (int j = 0; j < ka; j++) tabs.out[j] = flip ? bufB[j] : bufA[j];
+      // deferred reduction pays once a thread sums several pairs (its one-off reduction is 3 products per sum)
+      const bool wide = bps_wide > 0 && n_pairs >= (uint64_t)8 * SC_WIDE_THREADS * ctx->sm_count * bps_wide;
+      const int grid = wide ? round_grid(ctx, n_pairs, bps_wide, SC_WIDE_THREADS) : round_grid(ctx, n_pairs, bps);
+      rc = launch_round(tabs, n_pairs, pending, grid, wide, pdl, partials);
+      if (rc) return rc;
       if (G == 1) {
         QZ_LAUNCH_PDL(ctx, pdl, sc_finalize, 1, SC_THREADS, (const Fr*)partials, grid, d, head, (const Fr*)vinv,
                       d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc, (const Fr*)nullptr);
