@@ -841,6 +841,7 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
   // pair is independent) runs slice by slice behind the copies, so only the last slice's round-0 work is exposed after
   // the PCIe transfer; from round 1 on the challenge depends on all of the data.
   constexpr int UP_CHUNKS = 8;
+  static_assert(UP_CHUNKS <= qz_ctx::MAX_SEGMENTS, "one ready-event per slice");
   const int up_chunks = (!tables_on_device && G == 1 && !zerocheck && N >= ((uint64_t)1 << 21)) ? UP_CHUNKS : 1;
   uint8_t* up_dst[SC_MAX_K];
   const uint8_t* up_src[SC_MAX_K];
