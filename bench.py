@@ -368,7 +368,13 @@ def run_gpu(args):
     def zc_prove():
         sc_out["zc"] = q.ZeroCheckProof.prove(ctx, st_dev, 0, q.Transcript(b"zerocheck_bench", ctx), sharded=world > 1)
 
-    zc_ms, zc_launches = timed_loop(zc_prove, args.steps, args.warmup)
+    zc_err = None
+    try:
+        zc_ms, zc_launches = timed_loop(zc_prove, args.steps, args.warmup)
+    except q.QuillError as e:  # an auxiliary leg: report it in the line instead of losing the headline legs above
+        if world == 1:
+            raise
+        zc_ms, zc_launches, zc_err = None, 0, str(e)
     clocks = sampler.stop() if rank == 0 else None
 
     # (the nvidia-smi sampler is stopped first: its 200 ms polling contends for the driver and slows these
@@ -446,6 +452,8 @@ def run_gpu(args):
             "gpu_launches": msm_launches // args.steps,
             "clocks": clocks,
         }
+        if zc_err is not None:
+            line["zerocheck"] = {"error": zc_err}
         if zc_ms is not None:
             line["zerocheck"] = {"value": 3 * n / (zc_ms * 1e-3), "unit": "field-elems/s", "ms_per_step": zc_ms,
                                  "gpu_launches": zc_launches // args.steps,
