@@ -11,6 +11,7 @@
  *   compute_s_polynomial               pcs/src/ipa.rs:122-157        -> qz_compute_s_polynomial
  *   SumcheckProof::prove               hyperplonk/src/piops/sumcheck.rs:28-114   -> qz_sumcheck_prove
  *   ZeroCheckProof::prove              hyperplonk/src/piops/zerocheck.rs:14-49   -> qz_zerocheck_prove
+ *   (sharded over the GPUs of one box: qz_msm_sharded, qz_sumcheck_prove_sharded, qz_zerocheck_prove_sharded)
  *   fast_eq_eval_hypercube             hyperplonk/src/utils/eq_eval.rs:6-31      -> qz_eq_table
  *   logup denominators                 hyperplonk/src/piops/multiset_check.rs:43-95 -> qz_logup_denominators
  *   Transcript                         transcript/src/transcript.rs:14-75        -> qz_transcript_*

@@ -32,6 +32,33 @@ def test_header_symbols_exported():
         assert hasattr(lib, name), f"{name} not exported by libquill_b200.so"
 
 
+def test_header_compiles_as_c_and_links(tmp_path):
+    """include/quill_b200.h is plain C (what bindgen / cgo / a C caller would consume): a C99 translation unit that
+    includes nothing else compiles without warnings, links against the shared library and gets the documented refusal
+    when there is no device."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    src = tmp_path / "abi_link.c"
+    src.write_text(
+        '#include "quill_b200.h"\n#include <stdio.h>\n'
+        "int main(void) {\n"
+        "  qz_ctx* ctx = 0;\n"
+        "  int rc = qz_ctx_create(0, 0, &ctx);\n"
+        '  printf("%d %s\\n", rc, qz_status_str(rc));\n'
+        "  if (ctx) qz_ctx_destroy(ctx);\n"
+        "  return 0;\n}\n")
+    exe = tmp_path / "abi_link"
+    libdir = os.path.join(ROOT, "quill_zkvm_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), "-L", libdir, "-lquill_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    rc = int(out.stdout.split()[0])
+    assert rc == (_lib.QZ_OK if _has_gpu() else _lib.QZ_ERR_NO_DEVICE), out.stdout
+
+
 def test_no_cpu_fallback():
     if _has_gpu():
         pytest.skip("a GPU is present")
