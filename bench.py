@@ -88,6 +88,16 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+GOLDEN64 = 0x9E3779B97F4A7C15
+
+
+def shard_seed(seed: int, first_index: int) -> int:
+    """qz_dev_random_fr derives element i from seed + GOLDEN64 * (4 i + 1) (mod 2^64), so a shard that starts at global
+    index `first_index` continues the SAME sequence when seeded with seed + 4 * first_index * GOLDEN64: every GPU count
+    proves the same problem and the digests printed in the line must be equal for N = 1, 2, 4, 8."""
+    return (seed + 4 * first_index * GOLDEN64) & 0xFFFFFFFFFFFFFFFF
+
+
 def product_expr(q, k):
     e = q.VirtualPolyExpr.Input(0)
     for i in range(1, k):
@@ -186,7 +196,7 @@ def cpu_baseline(args):
     }
 
 
-def bench_hyperplonk(ctx, q, log_rows, g_bytes, tau_mont, timed_loop):
+def bench_hyperplonk(ctx, q, log_rows, g_bytes, tau_mont, timed_loop, verify=False):
     """BASELINE.json config 5 shape: two traces (Fibonacci, 4 columns; modified Fibonacci, 5 columns padded to 8) of
     2^log_rows rows each, proved with HyperPlonk::prove (zero-check + logup permutation check + MLPCS openings)."""
     import numpy as np
@@ -244,7 +254,29 @@ def bench_hyperplonk(ctx, q, log_rows, g_bytes, tau_mont, timed_loop):
     out = {}
     ms, launches = timed_loop(lambda: out.__setitem__("p", prover.prove(kzg, witnesses)), 1, 1)
     kzg.srs.free()
+    verified = None
+    if verify:  # the reference's acceptance criterion (HyperPlonkProof::verify, proof.rs:493-523) restated in oracle/: a
+        # CHECK of the timed proof, run after and outside the timed region; nothing on the proving path touches it
+        from oracle import pyref as py
+        from oracle import verifier as vf
+        from tests import util
+        t0 = time.perf_counter()
+        circuits_py = [py.fibonacci_circuit_and_trace(2)[0], py.modified_fibonacci_circuit_and_trace(2)[0]]
+        for c in circuits_py:
+            c.num_rows = rows  # the verifier reads only the circuit's shape and constraint expressions
+        gx = int.from_bytes(bytes(g_bytes[:32]), "little") * pow(1 << 256, -1, py.FQ) % py.FQ
+        gy = int.from_bytes(bytes(g_bytes[32:]), "little") * pow(1 << 256, -1, py.FQ) % py.FQ
+        vk = vf.VerifierKey((gx, gy), TAU, g2_scalar=11)
+        proof = util.hyperplonk_py(out["p"])
+        try:
+            verified = vf.hyperplonk_verify(proof, util.hyperplonk_vk_py(prover.trace_vks, circuits_py), vk) == proof["state_end"]
+        except ValueError as e:
+            verified = False
+            print("hyperplonk verifier rejected:", e, file=sys.stderr)
+        verify_s = time.perf_counter() - t0
     return {"value": ms * 1e-3, "unit": "s per proof", "rows_per_trace": rows, "traces": 2, "columns": [4, 8],
+            "verified": verified, "verified_by": "oracle/verifier.py hyperplonk_verify (restated reference verifier incl. BN254 pairings), "
+            f"{verify_s:.1f} s on the host after the timed region" if verify else None,
             "gpu_launches": launches, "workload": "HyperPlonk::prove of Fibonacci + modified-Fibonacci transition circuits "
             "(2 witness commits, 2 zero-checks, 2 logup permutation checks, 2 x (cols + public + 5) MLPCS openings)",
             "final_transcript_state": out["p"].transcript_state.hex()}
@@ -300,7 +332,7 @@ def run_gpu(args):
     kzg = q.KZG.trusted_setup(ctx, n_loc - 1, g_bytes, mont(TAU))  # SRS shard: g * tau^(lo + i)
     if not args.no_precompute:
         kzg.precompute(args.precompute_bits)  # one-time, like the SRS upload: window multiples 2^(c w) P_i in HBM
-    scal_dev = ctx.random_fr(n_loc, 0x5155494C4C + rank)
+    scal_dev = ctx.random_fr(n_loc, shard_seed(0x5155494C4C, lo))  # seeded by GLOBAL index: the same scalars at every N
     pin_scal = torch.empty(n_loc * 32, dtype=torch.uint8, pin_memory=True)
     scal_host = pin_scal.numpy()
     scal_host[:] = scal_dev.download()
@@ -338,12 +370,12 @@ def run_gpu(args):
     nv = args.log_n
     slo, shi = parallel.table_shard_range(nv, rank, world)
     t_loc = shi - slo
-    tabs_dev = [ctx.random_fr(t_loc, 1000 * (t + 1) + rank) for t in range(3)]
+    tabs_dev = [ctx.random_fr(t_loc, shard_seed(1000 * (t + 1), slo)) for t in range(3)]  # global-index seeds
     pins = [torch.empty(t_loc * 32, dtype=torch.uint8, pin_memory=True) for _ in range(3)]
     tabs_host = [p.numpy().reshape(-1, 32) for p in pins]
     for th, td in zip(tabs_host, tabs_dev):
         th[:] = td.download().reshape(-1, 32)
-    claimed = mont(12345)
+    claimed = mont(0)  # replaced below by the true sum, read off an untimed proof's round-0 polynomial
 
     def make_store(tabs):
         st = q.VirtualPolynomialStore(nv if world == 1 else nv)
@@ -360,13 +392,21 @@ def run_gpu(args):
         sc_out[key] = q.SumcheckProof.prove(ctx, nv, store, 0, claimed, tr, sharded=world > 1)
         sc_out[key + "_state"] = tr.state.copy()
 
+    # claimed_sum = the true sum: s_0(0) + s_0(1) = 2 c_0 + c_1 + c_2 + c_3 of the round-0 polynomial, which does not
+    # depend on the claim (only the transcript does)
+    prove(st_dev, "dev")
+    c0 = [int.from_bytes(bytes(c), "little") * pow(1 << 256, -1, FR) % FR for c in sc_out["dev"][0].r_polys[0]]
+    true_sum = (2 * c0[0] + sum(c0[1:])) % FR
+    claimed[:] = mont(true_sum)
     rounds_ms: list = []
     sc_ms, sc_launches = timed_loop(lambda: prove(st_dev, "dev"), args.steps, args.warmup, rounds_ms)
     sc_e2e_ms, _ = timed_loop(lambda: prove(st_host, "host"), args.steps, args.warmup)
     assert sc_out["dev_state"].tobytes() == sc_out["host_state"].tobytes()
     # zero-check form of the same workload (config 3): eq table built on the device as a fourth factor, degree 4
     def zc_prove():
-        sc_out["zc"] = q.ZeroCheckProof.prove(ctx, st_dev, 0, q.Transcript(b"zerocheck_bench", ctx), sharded=world > 1)
+        tr = q.Transcript(b"zerocheck_bench", ctx)
+        sc_out["zc"] = q.ZeroCheckProof.prove(ctx, st_dev, 0, tr, sharded=world > 1)
+        sc_out["zc_state"] = tr.state.copy()
 
     zc_err = None
     try:
@@ -401,7 +441,7 @@ def run_gpu(args):
     hplonk = None
     if args.hyperplonk_log_rows > 0:
         hplonk = bench_hyperplonk(ctx, q, args.hyperplonk_log_rows, np.concatenate([mont(1, FQ), mont(2, FQ)]), mont(TAU),
-                                  timed_loop)
+                                  timed_loop, verify=rank == 0 and not args.no_verify)
         hplonk["n_gpus"] = world
 
 
@@ -451,6 +491,13 @@ def run_gpu(args):
             },
             "gpu_launches": msm_launches // args.steps,
             "clocks": clocks,
+            # N-invariance evidence: inputs are seeded by global index, so these must be identical at N = 1, 2, 4, 8
+            "digests": {"commitment_xy": bytes(results["dev"]).hex(),
+                        "commitment_serialized": ctx.g1_serialize(results["dev"]).hex(),
+                        "sumcheck_claimed_sum": "%064x" % true_sum,
+                        "sumcheck_final_transcript_state": sc_out["dev_state"].tobytes().hex(),
+                        "sumcheck_evaluation": bytes(sc_out["dev"][1].evaluation).hex(),
+                        "zerocheck_final_transcript_state": sc_out["zc_state"].tobytes().hex() if "zc_state" in sc_out else None},
         }
         if zc_err is not None:
             line["zerocheck"] = {"error": zc_err}
@@ -490,6 +537,7 @@ def main():
     ap.add_argument("--hyperplonk-log-rows", type=int, default=20,
                     help="config 5: rows per trace of the two-trace HyperPlonk proof (0 = skip; BASELINE names 20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the verifier check of the HyperPlonk proof")
     ap.add_argument("--no-precompute", action="store_true", help="MSM without the precomputed window multiples")
     ap.add_argument("--precompute-bits", type=int, default=0, help="window bits of the precomputed table (0 = auto)")
     args = ap.parse_args()

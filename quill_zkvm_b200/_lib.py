@@ -43,8 +43,9 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise OSError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+    path = os.environ.get("QZ_LIB_PATH", LIB_PATH)  # A/B measurements of alternative builds (tools/_libs/); default: in-tree
+    if not os.path.exists(path):
+        raise OSError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                       "(make -C quill_zkvm_b200/csrc).  There is no CPU fallback.")
     # NCCL is bound lazily with dlopen inside the library; point it at torch's bundled copy when present
     if "QZ_NCCL_LIB" not in os.environ:
@@ -55,7 +56,7 @@ def load():
                 os.environ["QZ_NCCL_LIB"] = cand
         except Exception:
             pass
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, sz, i32, u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64
     lib.qz_ctx_create.argtypes = [i32, vp, C.POINTER(vp)]
     lib.qz_ctx_destroy.argtypes = [vp]

@@ -24,7 +24,7 @@ constexpr int SC_TAIL_LOG = 11;
 constexpr int SC_THREADS = 256;
 constexpr int SC_WIDE_THREADS = 128;  // deferred-reduction round kernel: 168 registers, 3 blocks per SM
 #ifndef QZ_SC_WIDE_BPS
-#define QZ_SC_WIDE_BPS 3
+#define QZ_SC_WIDE_BPS 4
 #endif
 
 // ---- loads ---------------------------------------------------------------------------------------------------------------
@@ -80,33 +80,44 @@ QZ_DEV void finish_pair(const RawPair<FOLD>& raw, uint4* out, uint64_t p, const 
 // sum, so its Montgomery reduction is deferred: the 512-bit products accumulate in 17-word sums that are reduced once
 // per thread (ff.cuh "deferred reduction") -- 64 instead of 128 multiply-adds for 4 of the 13 products of a K = 3 pair.
 // The reduction costs 3 products per sum, so passes with only a few pairs per thread use the narrow sums.
-template <int K, bool WIDE>
+// SKIP1: the value at X = 1 is not summed.  From round 1 on it follows from the previous round's TRUE polynomial,
+// s_j(0) + s_j(1) = s_{j-1}(r_{j-1}) (an identity of the tables, whatever the prover's claim was: round 0 still sums
+// every point, so a false claimed_sum is proved exactly as the reference proves it, zerocheck.rs:161-211), and the
+// finalize step restores it (sc_expand_evals).  One product and one running sum less per pair.  The NS = K or K + 1
+// sums are stored compactly: slot 0 = X 0, then X = 2.. (SKIP1) or X = 1.. .
+template <int K, bool WIDE, bool SKIP1>
 struct ProdAcc {
   static_assert(!WIDE || K >= 3, "nothing to defer below three factors");
-  FpWide wide[WIDE ? K + 1 : 1];
-  Fr narrow[WIDE ? 1 : K + 1];
+  static constexpr int NS = SKIP1 ? K : K + 1;
+  FpWide wide[WIDE ? NS : 1];
+  Fr narrow[WIDE ? 1 : NS];
+  static QZ_DEV constexpr int slot(int x) { return SKIP1 && x > 0 ? x - 1 : x; }
   QZ_DEV void init() {
     if (WIDE) {
 #pragma unroll
-      for (int x = 0; x <= K; x++) wide_zero(wide[x]);
+      for (int x = 0; x < NS; x++) wide_zero(wide[x]);
     } else {
 #pragma unroll
-      for (int x = 0; x <= K; x++) narrow[x] = fp_zero<FrParams>();
+      for (int x = 0; x < NS; x++) narrow[x] = fp_zero<FrParams>();
     }
   }
   QZ_DEV void add_product(int x, const Fr& a, const Fr& b) {
+    if (SKIP1 && x == 1) return;
     if (WIDE)
-      wide_mul_acc<FrParams>(wide[WIDE ? x : 0], a, b);
+      wide_mul_acc<FrParams>(wide[WIDE ? slot(x) : 0], a, b);
     else
       add_value(x, fp_mul<FrParams>(a, b));
   }
-  QZ_DEV void add_value(int x, const Fr& v) { narrow[WIDE ? 0 : x] = fp_add<FrParams>(narrow[WIDE ? 0 : x], v); }
-  QZ_DEV Fr get(int x) const { return WIDE ? wide_reduce<FrParams>(wide[WIDE ? x : 0]) : narrow[WIDE ? 0 : x]; }
+  QZ_DEV void add_value(int x, const Fr& v) {
+    if (SKIP1 && x == 1) return;
+    narrow[WIDE ? 0 : slot(x)] = fp_add<FrParams>(narrow[WIDE ? 0 : slot(x)], v);
+  }
+  QZ_DEV Fr get_slot(int i) const { return WIDE ? wide_reduce<FrParams>(wide[WIDE ? i : 0]) : narrow[WIDE ? 0 : i]; }
 };
 
 // core of a pair once the K (lo, hi) values are in registers
-template <int K, bool WIDE>
-QZ_DEV void prod_core(const Fr* lo, const Fr* hi, ProdAcc<K, WIDE>& acc) {
+template <int K, bool WIDE, bool SKIP1>
+QZ_DEV void prod_core(const Fr* lo, const Fr* hi, ProdAcc<K, WIDE, SKIP1>& acc) {
   constexpr int NP = K / 2;
   Fr val[NP > 0 ? NP : 1], dl[NP > 0 ? NP : 1], q22[NP > 0 ? NP : 1], lin, lin_df;
 #pragma unroll
@@ -147,21 +158,23 @@ QZ_DEV void prod_core(const Fr* lo, const Fr* hi, ProdAcc<K, WIDE>& acc) {
 
 // tail kernel: `fold` is a run-time flag, tables fetched one after the other
 template <int K, bool WIDE>
-QZ_DEV void prod_pair(const ScTables& tabs, uint64_t p, bool fold, const Fr& r, ProdAcc<K, WIDE>& acc) {
+QZ_DEV void prod_pair(const ScTables& tabs, uint64_t p, bool fold, const Fr& r, ProdAcc<K, WIDE, false>& acc) {
   Fr lo[K], hi[K];
 #pragma unroll
   for (int t = 0; t < K; t++) fetch_pair(tabs.in[t], tabs.out[t], p, fold, r, lo[t], hi[t]);
-  prod_core<K, WIDE>(lo, hi, acc);
+  prod_core<K, WIDE, false>(lo, hi, acc);
 }
 
 // ---- round kernel, fast path ---------------------------------------------------------------------------------------------
+// FOLD rounds (every round but the first) skip X = 1: NS = K sums per block instead of K + 1
 template <int K, bool WIDE, bool FOLD>
 __global__ void __launch_bounds__(WIDE ? SC_WIDE_THREADS : SC_THREADS, (WIDE ? QZ_SC_WIDE_BPS : K <= 3 ? 2 : 1))
     sc_round_prod(ScTables tabs, uint64_t n_pairs, const ScHead* head, Fr* partials) {
-  __shared__ Fr s_part[(SC_THREADS / 32) * (K + 1)];
+  constexpr int NS = ProdAcc<K, WIDE, FOLD>::NS;
+  __shared__ Fr s_part[(SC_THREADS / 32) * NS];
   grid_dep_launch();
   grid_dep_wait();
-  ProdAcc<K, WIDE> acc;
+  ProdAcc<K, WIDE, FOLD> acc;
   acc.init();
   Fr r = fp_zero<FrParams>();
   if (FOLD) r = head->r;
@@ -173,12 +186,12 @@ __global__ void __launch_bounds__(WIDE ? SC_WIDE_THREADS : SC_THREADS, (WIDE ? Q
     Fr lo[K], hi[K];
 #pragma unroll
     for (int t = 0; t < K; t++) finish_pair<FOLD>(raw[t], tabs.out[t], p, r, lo[t], hi[t]);
-    prod_core<K, WIDE>(lo, hi, acc);
+    prod_core<K, WIDE, FOLD>(lo, hi, acc);
   }
-  Fr sums[K + 1];
+  Fr sums[NS];
 #pragma unroll
-  for (int x = 0; x <= K; x++) sums[x] = acc.get(x);
-  block_sum_many(sums, K + 1, s_part, &partials[(size_t)blockIdx.x * (K + 1)]);
+  for (int x = 0; x < NS; x++) sums[x] = acc.get_slot(x);
+  block_sum_many(sums, NS, s_part, &partials[(size_t)blockIdx.x * NS]);
 }
 
 // ---- round kernel, zero-check fast path: h = g_0 * ... * g_{K-1}, summed against eq(., z) --------------------------------------
@@ -190,13 +203,17 @@ __global__ void __launch_bounds__(WIDE ? SC_WIDE_THREADS : SC_THREADS, (WIDE ? Q
 // products + the extra evaluation point + the wider product -- and sc_round_close multiplies by the linear factor.
 // The weight tables need no product to shrink: eq(0, z) + eq(1, z) = 1, so E_{j+2}[p] = E_{j+1}[2p] + E_{j+1}[2p+1],
 // done in the same pass that folds the g tables.  s_j is the same polynomial, so every output byte is unchanged.
-template <int K, bool WIDE, bool FOLD>
+// SKIP1 (FOLD rounds of large proofs only): t_j(1) is restored from t_{j-1}(r_{j-1}) = (1 - z_j) t_j(0) + z_j t_j(1),
+// which needs 1 / z_j (sc_begin inverts the z in one batch when asked to)
+template <int K, bool WIDE, bool FOLD, bool SKIP1>
 __global__ void __launch_bounds__(WIDE ? SC_WIDE_THREADS : SC_THREADS, (WIDE ? QZ_SC_WIDE_BPS : 2))
     sc_round_zc(ScTables tabs, const uint4* e_in, uint4* e_out, uint64_t n_pairs, const ScHead* head, Fr* partials) {
-  __shared__ Fr s_part[(SC_THREADS / 32) * (K + 1)];
+  static_assert(FOLD || !SKIP1, "round 0 sums every point");
+  constexpr int NS = ProdAcc<K, WIDE, SKIP1>::NS;
+  __shared__ Fr s_part[(SC_THREADS / 32) * NS];
   grid_dep_launch();
   grid_dep_wait();
-  ProdAcc<K, WIDE> acc;
+  ProdAcc<K, WIDE, SKIP1> acc;
   acc.init();
   Fr r = fp_zero<FrParams>();
   if (FOLD) r = head->r;
@@ -217,12 +234,12 @@ __global__ void __launch_bounds__(WIDE ? SC_WIDE_THREADS : SC_THREADS, (WIDE ? Q
     for (int t = 0; t < K; t++) finish_pair<FOLD>(raw[t], tabs.out[t], p, r, lo[t], hi[t]);
     lo[0] = fp_mul<FrParams>(w, lo[0]);
     hi[0] = fp_mul<FrParams>(w, hi[0]);
-    prod_core<K, WIDE>(lo, hi, acc);
+    prod_core<K, WIDE, SKIP1>(lo, hi, acc);
   }
-  Fr sums[K + 1];
+  Fr sums[NS];
 #pragma unroll
-  for (int x = 0; x <= K; x++) sums[x] = acc.get(x);
-  block_sum_many(sums, K + 1, s_part, &partials[(size_t)blockIdx.x * (K + 1)]);
+  for (int x = 0; x < NS; x++) sums[x] = acc.get_slot(x);
+  block_sum_many(sums, NS, s_part, &partials[(size_t)blockIdx.x * NS]);
 }
 // hand-over to sc_tail: the eq table in the form zerocheck.rs:25 would have left it after the same rounds, i.e. with
 // the last challenge still to be folded in: out[2p + b] = P_{j-1} * eq(b, z_{j-1}) * E_j[p]
@@ -238,8 +255,9 @@ __global__ void __launch_bounds__(256) zc_materialize_eq(const uint4* e_tab, uin
 }
 
 // ---- round kernel, generic expression tree -----------------------------------------------------------------------------------
+// skip1: X = 1 is not evaluated (see ProdAcc); the sums are stored compactly, acc[0] = X 0, acc[x - 1] = X x >= 2
 QZ_DEV void generic_pair(const ScTables& tabs, uint64_t p, bool fold, const Fr& r, const uint32_t* s_ops,
-                         uint32_t n_ops, int k, int d, const Fr* consts, Fr* acc) {
+                         uint32_t n_ops, int k, int d, const Fr* consts, Fr* acc, bool skip1 = false) {
   Fr cur[SC_MAX_K], df[SC_MAX_K];
   for (int t = 0; t < k; t++) {
     Fr hi;
@@ -247,7 +265,10 @@ QZ_DEV void generic_pair(const ScTables& tabs, uint64_t p, bool fold, const Fr& 
     df[t] = fp_sub<FrParams>(hi, cur[t]);
   }
   for (int x = 0; x <= d; x++) {
-    acc[x] = fp_add<FrParams>(acc[x], sc_eval_program(s_ops, n_ops, consts, cur));
+    if (!(skip1 && x == 1)) {
+      const int sl = skip1 && x > 0 ? x - 1 : x;
+      acc[sl] = fp_add<FrParams>(acc[sl], sc_eval_program(s_ops, n_ops, consts, cur));
+    }
     if (x < d)
       for (int t = 0; t < k; t++) cur[t] = fp_add<FrParams>(cur[t], df[t]);
   }
@@ -268,16 +289,21 @@ __global__ void __launch_bounds__(SC_THREADS) sc_round_generic(ScTables tabs, ui
   for (int x = 0; x <= d; x++) acc[x] = fp_zero<FrParams>();
   Fr r = fp_zero<FrParams>();
   if (fold) r = head->r;
+  const bool skip1 = fold != 0 && d >= 1;  // every round but the first (see ProdAcc)
+  const int ns = skip1 ? d : d + 1;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += stride)
-    generic_pair(tabs, p, fold != 0, r, s_ops, n_ops, k, d, consts, acc);
-  block_sum_many(acc, d + 1, s_part, &partials[(size_t)blockIdx.x * (d + 1)]);
+    generic_pair(tabs, p, fold != 0, r, s_ops, n_ops, k, d, consts, acc, skip1);
+  block_sum_many(acc, ns, s_part, &partials[(size_t)blockIdx.x * ns]);
 }
 
 // ---- finalize: sum `n_parts` partial vectors, close the round (transcript on the device) -----------------------------------
+// derive1: the partial vectors hold ns = d sums (X = 0, 2, .., d); X = 1 is restored from the running claim
+// (sc_expand_evals).  zc_zinv: 1 / z_j for that step on the eq-factored zero-check path.
 __global__ void __launch_bounds__(SC_THREADS) sc_finalize(const Fr* partials, int n_parts, int d, ScHead* head,
                                                          const Fr* vinv, Fr* out_coeffs_row, uint32_t* out_len,
-                                                         Fr* out_point_slot, int max_coeffs, const Fr* zc_z) {
+                                                         Fr* out_point_slot, int max_coeffs, const Fr* zc_z, int derive1,
+                                                         const Fr* zc_zinv) {
   __shared__ Fr s_part[(SC_THREADS / 32) * SC_MAX_COEFFS];
   __shared__ Fr s_evals[SC_MAX_COEFFS];
   __shared__ Fr s_coef[SC_MAX_COEFFS];
@@ -285,12 +311,15 @@ __global__ void __launch_bounds__(SC_THREADS) sc_finalize(const Fr* partials, in
   __shared__ __align__(16) uint32_t s_msg[SC_MSG_WORDS];
   grid_dep_launch();
   grid_dep_wait();
+  const int ns = derive1 ? d : d + 1;
   Fr v[SC_MAX_COEFFS];
-  for (int x = 0; x <= d; x++) v[x] = fp_zero<FrParams>();
+  for (int x = 0; x < ns; x++) v[x] = fp_zero<FrParams>();
   for (int b = threadIdx.x; b < n_parts; b += blockDim.x)
-    for (int x = 0; x <= d; x++) v[x] = fp_add<FrParams>(v[x], partials[(size_t)b * (d + 1) + x]);
-  block_sum_many(v, d + 1, s_part, s_evals);
-  sc_round_close(head, vinv, d, s_evals, s_coef, s_msg, s_prod, out_coeffs_row, out_len, out_point_slot, max_coeffs, zc_z);
+    for (int x = 0; x < ns; x++) v[x] = fp_add<FrParams>(v[x], partials[(size_t)b * ns + x]);
+  block_sum_many(v, ns, s_part, s_evals);
+  if (derive1) sc_expand_evals(head, d, s_evals, zc_z, zc_zinv);
+  sc_round_close(head, vinv, d, s_evals, s_coef, s_msg, s_prod, out_coeffs_row, out_len, out_point_slot, max_coeffs, zc_z,
+                 true);
 }
 
 // Sharded mode with peer mailboxes (comm.cuh): ONE launch per round after the round kernel.  The block sums this rank's
@@ -301,7 +330,7 @@ __global__ void __launch_bounds__(SC_THREADS) sc_finalize_peers(const Fr* partia
                                                                PeerMailbox* const* peers, int rank, int G, uint32_t seq,
                                                                ScHead* head, const Fr* vinv, Fr* out_coeffs_row,
                                                                uint32_t* out_len, Fr* out_point_slot, int max_coeffs,
-                                                               const Fr* zc_z) {
+                                                               const Fr* zc_z, int derive1, const Fr* zc_zinv) {
   __shared__ Fr s_part[(SC_THREADS / 32) * SC_MAX_COEFFS];
   __shared__ Fr s_evals[SC_MAX_COEFFS];
   __shared__ Fr s_coef[SC_MAX_COEFFS];
@@ -309,20 +338,23 @@ __global__ void __launch_bounds__(SC_THREADS) sc_finalize_peers(const Fr* partia
   __shared__ __align__(16) uint32_t s_msg[SC_MSG_WORDS];
   grid_dep_launch();
   grid_dep_wait();
+  const int ns = derive1 ? d : d + 1;
   Fr v[SC_MAX_COEFFS];
-  for (int x = 0; x <= d; x++) v[x] = fp_zero<FrParams>();
+  for (int x = 0; x < ns; x++) v[x] = fp_zero<FrParams>();
   for (int b = threadIdx.x; b < n_parts; b += blockDim.x)
-    for (int x = 0; x <= d; x++) v[x] = fp_add<FrParams>(v[x], partials[(size_t)b * (d + 1) + x]);
-  block_sum_many(v, d + 1, s_part, s_evals);
-  const PeerSlot* got = peer_exchange(peers, rank, G, seq, s_evals, d + 1);
+    for (int x = 0; x < ns; x++) v[x] = fp_add<FrParams>(v[x], partials[(size_t)b * ns + x]);
+  block_sum_many(v, ns, s_part, s_evals);
+  const PeerSlot* got = peer_exchange(peers, rank, G, seq, s_evals, ns);
   if (threadIdx.x == 0 && *reinterpret_cast<volatile uint32_t*>(&peers[rank]->timed_out)) head->peer_fault = 1;
-  if ((int)threadIdx.x <= d) {
+  if ((int)threadIdx.x < ns) {
     Fr sum = fp_zero<FrParams>();
     for (int g = 0; g < G; g++) sum = fp_add<FrParams>(sum, ld_fresh(&got->data[g][threadIdx.x]));
     s_evals[threadIdx.x] = sum;
   }
   __syncthreads();
-  sc_round_close(head, vinv, d, s_evals, s_coef, s_msg, s_prod, out_coeffs_row, out_len, out_point_slot, max_coeffs, zc_z);
+  if (derive1) sc_expand_evals(head, d, s_evals, zc_z, zc_zinv);
+  sc_round_close(head, vinv, d, s_evals, s_coef, s_msg, s_prod, out_coeffs_row, out_len, out_point_slot, max_coeffs, zc_z,
+                 true);
 }
 
 // reduce block partials to one vector per rank (sharded mode: the vectors are all-gathered, then sc_finalize)
@@ -371,11 +403,11 @@ __global__ void __launch_bounds__(SC_THREADS) sc_tail(ScTables tabs, ScTailBufs 
     Fr acc[SC_MAX_COEFFS];
     if (KP > 0) {
       constexpr int KX = KP > 0 ? KP : 1;
-      ProdAcc<KX, false> pa;
+      ProdAcc<KX, false, false> pa;
       pa.init();
       for (uint64_t p = threadIdx.x; p < n_pairs; p += blockDim.x) prod_pair<KX, false>(view, p, pending_fold != 0, r, pa);
 #pragma unroll
-      for (int x = 0; x <= KX; x++) acc[x] = pa.get(x);
+      for (int x = 0; x <= KX; x++) acc[x] = pa.get_slot(x);
     } else {
       for (int x = 0; x <= d; x++) acc[x] = fp_zero<FrParams>();
       for (uint64_t p = threadIdx.x; p < n_pairs; p += blockDim.x)
@@ -408,25 +440,61 @@ __global__ void __launch_bounds__(SC_THREADS) sc_tail(ScTables tabs, ScTailBufs 
 }
 
 // ---- small helper kernels ---------------------------------------------------------------------------------------------------------
-// Opens a proof in one launch: the caller's transcript state; for a zero-check the n challenges drawn before the header
-// (zerocheck.rs:20-22); then num_vars (u64 LE) and claimed_sum are absorbed (sumcheck.rs:35-36).
-__global__ void sc_begin(ScHead* head, const uint8_t* state_in, uint64_t num_vars, Fr claimed_sum, int zc_n, Fr* z) {
-  for (int i = 0; i < 32; i++) head->tstate[i] = state_in[i];
-  head->r = fp_zero<FrParams>();
-  head->evaluation = fp_zero<FrParams>();
-  head->zc_prefix = fp_one<FrParams>();
-  head->zc_prefix_prev = fp_one<FrParams>();
-  head->peer_fault = 0;
-  uint32_t* state = reinterpret_cast<uint32_t*>(head->tstate);
-  for (int i = 0; i < zc_n; i++) z[i] = tr_draw_fr_words(state);
-  uint32_t buf[16];
-  for (int i = 0; i < 16; i++) buf[i] = 0;
-  buf[8] = (uint32_t)num_vars;
-  buf[9] = (uint32_t)(num_vars >> 32);
-  tr_absorb_words(state, buf, 8);
-  const Fr can = fp_from_mont<FrParams>(claimed_sum);
-  for (int i = 0; i < 8; i++) buf[8 + i] = can.v[i];
-  tr_absorb_words(state, buf, 32);
+// Opens a proof in one launch (one warp; the transcript runs on lanes 0..3, tr_*_quad): the caller's transcript state;
+// for a zero-check the n challenges drawn before the header (zerocheck.rs:20-22); then num_vars (u64 LE) and
+// claimed_sum are absorbed (sumcheck.rs:35-36).  zinv (optional): 1 / z_j for the SKIP1 rounds of the eq-factored
+// zero-check, by one batched inversion (Montgomery's trick: 3 products per element + one binary-Euclid inverse).
+__global__ void __launch_bounds__(32) sc_begin(ScHead* head, const uint8_t* state_in, uint64_t num_vars, Fr claimed_sum,
+                                               int zc_n, Fr* z, Fr* zinv) {
+  __shared__ __align__(16) uint32_t buf[32];
+  const int t = threadIdx.x;
+  if (t == 0) {
+    for (int i = 0; i < 32; i++) head->tstate[i] = state_in[i];
+    head->r = fp_zero<FrParams>();
+    head->evaluation = fp_zero<FrParams>();
+    head->zc_prefix = fp_one<FrParams>();
+    head->zc_prefix_prev = fp_one<FrParams>();
+    head->claim = fp_zero<FrParams>();
+    head->peer_fault = 0;
+    head->zc_degenerate = 0;
+  }
+  __syncwarp();
+  if (t < 4) {
+    uint32_t* state = reinterpret_cast<uint32_t*>(head->tstate);
+    for (int i = 0; i < zc_n; i++) {
+      const Fr zi = tr_draw_fr_quad(state, buf);
+      if (t == 0) z[i] = zi;
+    }
+    for (int i = t; i < 32; i += 4) buf[i] = 0;
+    __syncwarp(B3_QUAD);
+    if (t == 0) {
+      buf[8] = (uint32_t)num_vars;
+      buf[9] = (uint32_t)(num_vars >> 32);
+    }
+    __syncwarp(B3_QUAD);
+    tr_absorb_quad(state, buf, 8);
+    if (t == 0) {
+      const Fr can = fp_from_mont<FrParams>(claimed_sum);
+      for (int i = 0; i < 8; i++) buf[8 + i] = can.v[i];
+    }
+    __syncwarp(B3_QUAD);
+    tr_absorb_quad(state, buf, 32);
+  }
+  if (t == 0 && zinv && zc_n > 0) {
+    Fr run = fp_one<FrParams>();
+    for (int i = 0; i < zc_n; i++) {
+      const Fr zi = z[i];
+      if (fp_is_zero<FrParams>(zi)) head->zc_degenerate = 1;
+      zinv[i] = run;
+      run = fp_mul<FrParams>(run, zi);
+    }
+    Fr inv = fp_inv_serial<FrParams>(run);
+    for (int i = zc_n - 1; i >= 0; i--) {
+      const Fr zi = z[i];
+      zinv[i] = fp_mul<FrParams>(inv, zinv[i]);
+      inv = fp_mul<FrParams>(inv, zi);
+    }
+  }
 }
 // eq(x, z) tables over the low `a` variables and the remaining high variables
 __global__ void eq_half_tables(const Fr* z, int n, int a, Fr* lo_tab, Fr* hi_tab) {
@@ -660,6 +728,7 @@ int round_grid(qz_ctx* ctx, uint64_t n_pairs, int blocks_per_sm, int threads = S
 
 namespace qz {
 
+static thread_local bool tl_zc_no_skip = false;  // set while a zero-check is redone without the SKIP1 rounds
 
 // elements [base, base + n_elems) of eq(., z) over n variables
 int eq_table_device(qz_ctx* ctx, int n, const Fr* z_dev, uint4* out_dev, uint64_t base, uint64_t n_elems) {
@@ -829,12 +898,23 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
   memcpy(pin + in_prog, &cp.prog, sizeof(ScProgram));
   if (n_consts) memcpy(pin + in_consts, consts, 32 * n_consts);
   QZ_CUDA(ctx, cudaMemcpyAsync(d_in, pin, in_bytes, cudaMemcpyHostToDevice, st));
+  bool zc_skip1 = false;
+  Fr* d_zinv = nullptr;
   {
     Fr cs;
     memset(&cs, 0, sizeof cs);
     if (!zerocheck) memcpy(cs.v, claimed_sum, 32);
-    QZ_LAUNCH(ctx, sc_begin, 1, 1, 0, head, (const uint8_t*)(d_in + in_state), (uint64_t)num_vars, cs,
-              zerocheck ? (int)num_vars : 0, d_z);  // zerocheck.rs:20-22, sumcheck.rs:35-36
+    // the eq-factored zero-check skips X = 1 from round 1 on when the proof is large enough to repay the batched
+    // inversion of the z (~30 us on one thread); decided here because sc_begin computes the inverses
+    const bool zc_maybe_fast = zerocheck && cp.product_k >= 2 && cp.product_k <= 4 &&
+                               ((uint64_t)1 << num_vars) > ((uint64_t)1 << SC_TAIL_LOG) && !getenv("QZ_ZC_STREAM_EQ");
+    zc_skip1 = zc_maybe_fast && num_vars >= 21 && !tl_zc_no_skip && !getenv("QZ_ZC_NO_SKIP1");
+    if (zc_skip1) {
+      d_zinv = (Fr*)ctx->arena_alloc(32 * num_vars);
+      if (!d_zinv) return ctx->fail(QZ_ERR_ALLOC, "zero-check inverses");
+    }
+    QZ_LAUNCH(ctx, sc_begin, 1, 32, 0, head, (const uint8_t*)(d_in + in_state), (uint64_t)num_vars, cs,
+              zerocheck ? (int)num_vars : 0, d_z, d_zinv);  // zerocheck.rs:20-22, sumcheck.rs:35-36
   }
 
   // Host tables of a large proof are copied in UP_CHUNKS slices on the second stream and round 0 (evaluate only: every
@@ -927,11 +1007,11 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
       rc = get_vinv(ctx, K, &vinv_k);
       if (rc) return rc;
       int zb = 1, zb_wide = 0;
-      if (K == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&zb, sc_round_zc<1, false, true>, SC_THREADS, 0);
-      else if (K == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&zb, sc_round_zc<2, false, true>, SC_THREADS, 0);
+      if (K == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&zb, sc_round_zc<1, false, true, false>, SC_THREADS, 0);
+      else if (K == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&zb, sc_round_zc<2, false, true, false>, SC_THREADS, 0);
       else {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&zb, sc_round_zc<3, false, true>, SC_THREADS, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&zb_wide, sc_round_zc<3, true, true>, SC_WIDE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&zb, sc_round_zc<3, false, true, false>, SC_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&zb_wide, sc_round_zc<3, true, true, false>, SC_WIDE_THREADS, 0);
       }
       zb = std::max(1, std::min(zb, std::max(bps, bps_wide)));  // `partials` was sized for max(bps, bps_wide) blocks per SM
       zb_wide = std::min(zb_wide, std::max(bps, bps_wide));
@@ -957,10 +1037,12 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
         const int grid = wide ? round_grid(ctx, n_pairs, zb_wide, SC_WIDE_THREADS) : round_grid(ctx, n_pairs, zb);
         const uint4* e_in = e_buf[e_cur];
         uint4* e_out = e_buf[e_cur ^ 1];
+        const int derive1 = pending && zc_skip1 ? 1 : 0;
 #define QZ_ROUND_ZC(KK, W, T)                                                                                      \
   do {                                                                                                             \
-    if (pending) QZ_LAUNCH_PDL(ctx, pdl, (sc_round_zc<KK, W, true>), grid, T, gt, e_in, e_out, n_pairs, (const ScHead*)head, partials); \
-    else QZ_LAUNCH_PDL(ctx, pdl, (sc_round_zc<KK, W, false>), grid, T, gt, e_in, e_out, n_pairs, (const ScHead*)head, partials);        \
+    if (derive1) QZ_LAUNCH_PDL(ctx, pdl, (sc_round_zc<KK, W, true, true>), grid, T, gt, e_in, e_out, n_pairs, (const ScHead*)head, partials); \
+    else if (pending) QZ_LAUNCH_PDL(ctx, pdl, (sc_round_zc<KK, W, true, false>), grid, T, gt, e_in, e_out, n_pairs, (const ScHead*)head, partials); \
+    else QZ_LAUNCH_PDL(ctx, pdl, (sc_round_zc<KK, W, false, false>), grid, T, gt, e_in, e_out, n_pairs, (const ScHead*)head, partials);        \
   } while (0)
         switch (K) {
           case 1: QZ_ROUND_ZC(1, false, SC_THREADS); break;
@@ -969,19 +1051,24 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
             if (wide) QZ_ROUND_ZC(3, true, SC_WIDE_THREADS);
             else QZ_ROUND_ZC(3, false, SC_THREADS);
         }
+#undef QZ_ROUND_ZC
+        const Fr* zinv_j = zc_skip1 ? d_zinv + round : nullptr;
+        const int ns = derive1 ? K : K + 1;
         if (G == 1) {
           QZ_LAUNCH_PDL(ctx, pdl, sc_finalize, 1, SC_THREADS, (const Fr*)partials, grid, K, head, (const Fr*)vinv_k,
-                        d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc, (const Fr*)(d_z + round));
+                        d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc, (const Fr*)(d_z + round), derive1,
+                        zinv_j);
         } else if (comm_has_peers(ctx)) {
           QZ_LAUNCH_PDL(ctx, pdl, sc_finalize_peers, 1, SC_THREADS, (const Fr*)partials, grid, K,
                         (PeerMailbox* const*)ctx->peer_mbox_dev, ctx->rank, G, ++ctx->mbox_seq, head, (const Fr*)vinv_k,
-                        d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc, (const Fr*)(d_z + round));
+                        d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc, (const Fr*)(d_z + round), derive1,
+                        zinv_j);
         } else {
-          QZ_LAUNCH(ctx, sc_reduce_partials, 1, SC_THREADS, 0, partials, grid, K, rank_evals);
-          rc = comm_allgather(ctx, rank_evals, all_evals, sizeof(Fr) * (K + 1));
+          QZ_LAUNCH(ctx, sc_reduce_partials, 1, SC_THREADS, 0, partials, grid, ns - 1, rank_evals);
+          rc = comm_allgather(ctx, rank_evals, all_evals, sizeof(Fr) * ns);
           if (rc) return rc;
           QZ_LAUNCH(ctx, sc_finalize, 1, SC_THREADS, 0, all_evals, G, K, head, vinv_k, d_coeffs + (size_t)round * mc,
-                    d_lens + round, d_point + round, mc, (const Fr*)(d_z + round));
+                    d_lens + round, d_point + round, mc, (const Fr*)(d_z + round), derive1, zinv_j);
         }
         if (pending) {
           for (int i = 0; i < K; i++) gt.in[i] = gt.out[i];
@@ -1044,7 +1131,7 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
         if (rc) return rc;
       }
       QZ_LAUNCH(ctx, sc_finalize, 1, SC_THREADS, 0, (const Fr*)partials, grid_c * up_chunks, d, head, (const Fr*)vinv, d_coeffs,
-                d_lens, d_point, mc, (const Fr*)nullptr);
+                d_lens, d_point, mc, (const Fr*)nullptr, 0, (const Fr*)nullptr);
       pending = 1;
       round = 1;
     }
@@ -1057,19 +1144,23 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
       const int grid = wide ? round_grid(ctx, n_pairs, bps_wide, SC_WIDE_THREADS) : round_grid(ctx, n_pairs, bps);
       rc = launch_round(tabs, n_pairs, pending, grid, wide, pdl, partials);
       if (rc) return rc;
+      // every round but the first leaves X = 1 to the running claim (ProdAcc / generic_pair)
+      const int derive1 = pending && d >= 1 ? 1 : 0, ns = derive1 ? d : d + 1;
       if (G == 1) {
         QZ_LAUNCH_PDL(ctx, pdl, sc_finalize, 1, SC_THREADS, (const Fr*)partials, grid, d, head, (const Fr*)vinv,
-                      d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc, (const Fr*)nullptr);
+                      d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc, (const Fr*)nullptr, derive1,
+                      (const Fr*)nullptr);
       } else if (comm_has_peers(ctx)) {  // partial sums go straight into the peers' mailboxes (comm.cuh)
         QZ_LAUNCH_PDL(ctx, pdl, sc_finalize_peers, 1, SC_THREADS, (const Fr*)partials, grid, d,
                       (PeerMailbox* const*)ctx->peer_mbox_dev, ctx->rank, G, ++ctx->mbox_seq, head, (const Fr*)vinv,
-                      d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc, (const Fr*)nullptr);
+                      d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc, (const Fr*)nullptr, derive1,
+                      (const Fr*)nullptr);
       } else {  // every rank sums all ranks' partial evaluations and runs the same transcript
-        QZ_LAUNCH(ctx, sc_reduce_partials, 1, SC_THREADS, 0, partials, grid, d, rank_evals);
-        rc = comm_allgather(ctx, rank_evals, all_evals, sizeof(Fr) * (d + 1));
+        QZ_LAUNCH(ctx, sc_reduce_partials, 1, SC_THREADS, 0, partials, grid, ns - 1, rank_evals);
+        rc = comm_allgather(ctx, rank_evals, all_evals, sizeof(Fr) * ns);
         if (rc) return rc;
         QZ_LAUNCH(ctx, sc_finalize, 1, SC_THREADS, 0, all_evals, G, d, head, vinv, d_coeffs + (size_t)round * mc,
-                  d_lens + round, d_point + round, mc, (const Fr*)nullptr);
+                  d_lens + round, d_point + round, mc, (const Fr*)nullptr, derive1, (const Fr*)nullptr);
       }
       if (pending) {
         for (int j = 0; j < ka; j++) tabs.in[j] = tabs.out[j];
@@ -1115,6 +1206,13 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
   QZ_CUDA(ctx, cudaStreamSynchronize(st));
   const ScHead* h = (const ScHead*)(pin_out + o_head);
   if (h->peer_fault) return ctx->fail(QZ_ERR_NCCL, "a peer did not deliver its partial sums (peer mailbox wait timed out)");
+  if (zc_skip1 && h->zc_degenerate) {  // some z_j = 0 (probability 2^-254 per challenge): redo without the 1 / z_j shortcut
+    tl_zc_no_skip = true;              // every rank draws the same z, so every rank takes this branch
+    rc = sumcheck_run(ctx, num_vars, k, tables, tables_on_device, nodes, n_nodes, consts, n_consts, claimed_sum, state,
+                      max_coeffs, out_coeffs, out_lens, out_point, out_eval, zerocheck, out_z, sharded);
+    tl_zc_no_skip = false;
+    return rc;
+  }
   memcpy(state, h->tstate, 32);
   memcpy(out_eval, h->evaluation.v, 32);
   if (num_vars) {

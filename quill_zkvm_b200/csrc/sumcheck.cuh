@@ -35,7 +35,11 @@ struct ScHead {
   // eq-factored zero-check (sumcheck.cu "zero-check fast path"): P_j = prod_{i<j} eq(r_i, z_i) after round j-1 closed,
   // and P_{j-1}, the value it had one round earlier (the hand-over to sc_tail needs it)
   Fr zc_prefix, zc_prefix_prev;
-  uint32_t peer_fault;  // a peer-mailbox wait timed out during this proof (comm.cuh): the results are void
+  // running claim for the rounds that do not sum X = 1 (sumcheck.cu ProdAcc): s_j(r_j) of the last closed round -- on
+  // the eq-factored zero-check path t_j(r_j), the factor of s_j that the weighted sums are taken of
+  Fr claim;
+  uint32_t peer_fault;     // a peer-mailbox wait timed out during this proof (comm.cuh): the results are void
+  uint32_t zc_degenerate;  // a zero-check challenge z_j was 0: no 1 / z_j, the proof is redone without that shortcut
 };
 
 // ---- serialization / transcript (device) -------------------------------------------------------------------------
@@ -380,9 +384,32 @@ constexpr int SC_PROD_SLOTS = 256;
 // degree d, and the round polynomial is s_j(X) = P_j * eq(X, z_j) * t_j(X), of degree d + 1, with z_j = *zc_z and
 // P_j = head->zc_prefix: the d + 1 coefficients are multiplied by the linear factor a + b X, a = P_j (1 - z_j),
 // b = P_j (2 z_j - 1), before they are trimmed and absorbed, and P_{j+1} = P_j eq(r_j, z_j) once r_j is drawn.
+// Restore the value at X = 1 that a SKIP1 round did not sum.  s_evals holds d sums compactly (X = 0, 2, .., d) and is
+// expanded in place to X = 0..d.  Plain rounds: s_j(1) = s_{j-1}(r_{j-1}) - s_j(0).  Eq-factored zero-check rounds:
+// t_{j-1}(r_{j-1}) = sum_x E_j(x) prod_t g_t = (1 - z_j) t_j(0) + z_j t_j(1), so t_j(1) = (claim - (1 - z_j) t_j(0)) / z_j.
+// Called by every thread of the block; ends with a barrier.
+QZ_DEV void sc_expand_evals(const ScHead* head, int d, Fr* s_evals, const Fr* zc_z, const Fr* zc_zinv) {
+  Fr mine = fp_zero<FrParams>();
+  const int t = threadIdx.x;
+  if (t >= 2 && t <= d) mine = s_evals[t - 1];
+  if (t == 1) {
+    const Fr e0 = s_evals[0], claim = head->claim;
+    if (zc_z) {
+      const Fr z = *zc_z, one = fp_one<FrParams>();
+      mine = fp_mul<FrParams>(fp_sub<FrParams>(claim, fp_mul<FrParams>(fp_sub<FrParams>(one, z), e0)), *zc_zinv);
+    } else {
+      mine = fp_sub<FrParams>(claim, e0);
+    }
+  }
+  __syncthreads();
+  if (t >= 1 && t <= d) s_evals[t] = mine;
+  __syncthreads();
+}
+
+// want_claim: leave s_j(r_j) (t_j(r_j) on the eq-factored path) in head->claim for a following SKIP1 round
 QZ_DEV void sc_round_close(ScHead* head, const Fr* vinv, int d, const Fr* s_evals, Fr* s_coef, uint32_t* s_msg, Fr* s_prod,
                            Fr* out_coeffs_row, uint32_t* out_len, Fr* out_point_slot, int max_coeffs,
-                           const Fr* zc_z = nullptr) {
+                           const Fr* zc_z = nullptr, bool want_claim = false) {
   const int t = threadIdx.x;
   const int n1 = d + 1;
   const int n_out = zc_z ? d + 2 : d + 1;  // coefficients of the round polynomial before trimming
@@ -407,6 +434,7 @@ QZ_DEV void sc_round_close(ScHead* head, const Fr* vinv, int d, const Fr* s_eval
     __syncthreads();
     Fr lower = fp_zero<FrParams>();
     if (t >= 1 && t <= d + 1) lower = s_coef[t - 1];
+    if (want_claim && t <= d) s_prod[t] = acc;  // t_j's coefficients, for the running claim (s_prod is free again)
     __syncthreads();
     if (t < n_out) {
       const Fr z = *zc_z, P = head->zc_prefix, one = fp_one<FrParams>();
@@ -442,6 +470,12 @@ QZ_DEV void sc_round_close(ScHead* head, const Fr* vinv, int d, const Fr* s_eval
     if (t == 0) {
       head->r = r;
       *out_point_slot = r;
+      if (want_claim) {  // Horner at the challenge
+        const Fr* c = zc_z ? s_prod : s_coef;
+        Fr v = c[d];
+        for (int i = d - 1; i >= 0; i--) v = fp_add<FrParams>(fp_mul<FrParams>(v, r), c[i]);
+        head->claim = v;
+      }
       if (zc_z) {  // P_{j+1} = P_j (r z + (1 - r)(1 - z))
         const Fr z = *zc_z, one = fp_one<FrParams>(), P = head->zc_prefix;
         const Fr e = fp_add<FrParams>(fp_mul<FrParams>(r, z), fp_mul<FrParams>(fp_sub<FrParams>(one, r), fp_sub<FrParams>(one, z)));

@@ -108,6 +108,18 @@ out["hyperplonk"] = dict(
                    perm_point=[H(x) for x in hp1["trace_proofs"][0]["perm_point"]]),
     multitrace=dict(state_end=hp2["state_end"]))
 
+# ---- MLEvalProof::prove (pcs/src/mlpcs.rs:83-124): 5 variables, seeded (drawn last so earlier vectors keep their values) ----------
+poly5 = [rnd.randrange(FR) for _ in range(32)]
+point5 = [rnd.randrange(FR) for _ in range(5)]
+t = py.Transcript(b"mlpcs_golden")
+com5 = okzg.commit(poly5)
+pf5 = py.mlpcs_open(okzg, poly5, point5, t)
+op = lambda o: dict(x=H(o[0]), y=H(o[1]), proof_bytes=py.ser_g1(o[2]).hex())  # noqa: E731
+out["mlpcs_n5"] = dict(poly=[H(x) for x in poly5], point=[H(x) for x in point5], commitment_bytes=py.ser_g1(com5).hex(),
+                       evaluation=H(pf5["evaluation"]), s_comm_bytes=py.ser_g1(pf5["s_comm"]).hex(),
+                       poly_opening=op(pf5["poly_opening"]), poly_opening_inv=op(pf5["poly_opening_inv"]),
+                       s_opening=op(pf5["s_opening"]), s_opening_inv=op(pf5["s_opening_inv"]), state_end=t.state.hex())
+
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden.json")
 json.dump(out, open(path, "w"), indent=1)
 print("wrote", path, os.path.getsize(path), "bytes")

@@ -1,0 +1,16 @@
+#!/bin/bash
+# round-2 development check on ONE GPU: gpu tests, then sumcheck / zero-check timings of the default build and of the
+# A/B builds under tools/_libs/ (scratch output in gpurun_out/)
+mkdir -p gpurun_out
+if [ "$1" == "test" ]; then
+  timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2_tests.log 2>&1; echo "tests rc=$?"; tail -5 gpurun_out/r2_tests.log
+fi
+for what in sumcheck zerocheck; do
+  echo "== default $what"; python tools/profile_one.py $what 24 2>&1 | tail -1
+  for l in tools/_libs/*.so; do
+    [ -f "$l" ] || continue
+    echo "== $l $what"; QZ_LIB_PATH=$l python tools/profile_one.py $what 24 2>&1 | tail -1
+  done
+done
+python tools/profile_one.py sumcheck 16 2>&1 | tail -1
+python tools/profile_one.py sumcheck 20 2>&1 | tail -1
