@@ -168,7 +168,7 @@ QZ_DEV void prod_pair(const ScTables& tabs, uint64_t p, bool fold, const Fr& r, 
 // ---- round kernel, fast path ---------------------------------------------------------------------------------------------
 // FOLD rounds (every round but the first) skip X = 1: NS = K sums per block instead of K + 1
 template <int K, bool WIDE, bool FOLD>
-__global__ void __launch_bounds__(WIDE ? SC_WIDE_THREADS : SC_THREADS, (WIDE ? QZ_SC_WIDE_BPS : K <= 3 ? 2 : 1))
+__global__ void __launch_bounds__(WIDE ? SC_WIDE_THREADS : SC_THREADS, (WIDE ? (K <= 3 ? QZ_SC_WIDE_BPS : 3) : K <= 3 ? 2 : 1))
     sc_round_prod(ScTables tabs, uint64_t n_pairs, const ScHead* head, Fr* partials) {
   constexpr int NS = ProdAcc<K, WIDE, FOLD>::NS;
   __shared__ Fr s_part[(SC_THREADS / 32) * NS];
@@ -241,6 +241,120 @@ __global__ void __launch_bounds__(WIDE ? SC_WIDE_THREADS : SC_THREADS, (WIDE ? Q
   for (int x = 0; x < NS; x++) sums[x] = acc.get_slot(x);
   block_sum_many(sums, NS, s_part, &partials[(size_t)blockIdx.x * NS]);
 }
+// ---- the same rounds with shared-memory staging (large passes) ------------------------------------------------------------------
+// The kernels above front-load a pair's 12 global loads (96 registers for three tables in a fold round) and then wait:
+// ncu r01 showed the integer pipe at 71 % with the memory round trip exposed once per pair and the register file capping
+// the SM at 12 warps.  Here every warp owns a small ring in shared memory, one slot per table, filled with cp.async
+// (global -> shared, no registers, L1 bypassed): while the warp folds and multiplies pair i, the tiles of pair i + 1 are
+// already in flight -- a slot is refilled for the next pair as soon as its rows have been read.  A row is one thread's
+// 128 contiguous bytes (four elements; two in round 0), stored with a 16-byte pad so that the eight lanes of a quarter
+// warp read their rows from different banks; the copies themselves are issued chunk-major, 512 contiguous bytes per
+// instruction.  No block-level barrier, no mbarrier: a thread waits for its own copy groups, __syncwarp publishes them.
+QZ_DEV void cp_async16(uint32_t smem_addr, const void* gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+QZ_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+QZ_DEV void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+template <bool FOLD>
+struct StageGeom {
+  static constexpr int ROW = FOLD ? 128 : 64;        // bytes of one pair of one table
+  static constexpr int STRIDE = ROW + 16;            // padded row
+  static constexpr int SLOT = 32 * STRIDE;           // one warp-tile of one table
+  static constexpr int CHUNKS = ROW / 16;            // 16-byte chunks per row = copy instructions per tile
+};
+// copy rows [base, base + 32) of `in` (row = ROW bytes) into the slot; rows at or beyond n_pairs are skipped
+template <bool FOLD>
+QZ_DEV void stage_issue(uint32_t slot_addr, const uint4* in, uint64_t base, uint64_t n_pairs, int lane) {
+  using G = StageGeom<FOLD>;
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(in) + base * G::ROW;
+  const uint64_t valid = n_pairs - base < 32 ? n_pairs - base : 32;  // rows of this tile that exist
+#pragma unroll
+  for (int j = 0; j < G::CHUNKS; j++) {
+    const int g = j * 32 + lane, row = g / G::CHUNKS, chunk = g % G::CHUNKS;
+    if ((uint64_t)row < valid) cp_async16(slot_addr + row * G::STRIDE + chunk * 16, src + (size_t)g * 16);
+  }
+}
+template <bool FOLD>
+QZ_DEV void stage_read(const uint8_t* slot, int lane, RawPair<FOLD>& raw) {
+  using G = StageGeom<FOLD>;
+  const uint4* row = reinterpret_cast<const uint4*>(slot + lane * G::STRIDE);
+#pragma unroll
+  for (int e = 0; e < (FOLD ? 4 : 2); e++) {
+    const uint4 a = row[2 * e], b = row[2 * e + 1];
+    raw.e[e].v[0] = a.x; raw.e[e].v[1] = a.y; raw.e[e].v[2] = a.z; raw.e[e].v[3] = a.w;
+    raw.e[e].v[4] = b.x; raw.e[e].v[5] = b.y; raw.e[e].v[6] = b.z; raw.e[e].v[7] = b.w;
+  }
+}
+// ZC: the eq-factored zero-check form (see sc_round_zc); SKIP1 as above (plain rounds: SKIP1 == FOLD)
+template <int K, bool FOLD, bool ZC, bool SKIP1>
+__global__ void __launch_bounds__(SC_WIDE_THREADS, K <= 3 ? QZ_SC_WIDE_BPS : 3)
+    sc_round_staged(ScTables tabs, const uint4* e_in, uint4* e_out, uint64_t n_pairs, const ScHead* head, Fr* partials) {
+  using G = StageGeom<FOLD>;
+  constexpr int NS = ProdAcc<K, true, SKIP1>::NS;
+  extern __shared__ __align__(16) uint8_t s_stage[];  // [warp][table][SLOT]
+  __shared__ Fr s_part[(SC_WIDE_THREADS / 32) * NS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* my = s_stage + (size_t)warp * K * G::SLOT;
+  const uint32_t my_addr = (uint32_t)__cvta_generic_to_shared(my);
+  ProdAcc<K, true, SKIP1> acc;
+  acc.init();
+  Fr r = fp_zero<FrParams>();
+  if (FOLD) r = head->r;
+  const uint64_t stride = (uint64_t)gridDim.x * (SC_WIDE_THREADS / 32) * 32;
+  uint64_t base = ((uint64_t)blockIdx.x * (SC_WIDE_THREADS / 32) + warp) * 32;
+  if (base < n_pairs) {
+#pragma unroll
+    for (int t = 0; t < K; t++) {
+      stage_issue<FOLD>(my_addr + t * G::SLOT, tabs.in[t], base, n_pairs, lane);
+      cp_async_commit();
+    }
+  }
+  for (; base < n_pairs; base += stride) {
+    const uint64_t next = base + stride, p = base + lane;
+    const bool active = p < n_pairs;
+    Fr w;
+    if (ZC && active) {
+      if (FOLD) {
+        w = fp_add<FrParams>(ld_elem(e_in, 2 * p), ld_elem(e_in, 2 * p + 1));
+        st_elem(e_out, p, w);
+      } else {
+        w = ld_elem(e_in, p);
+      }
+    }
+    Fr lo[K], hi[K];
+#pragma unroll
+    for (int t = 0; t < K; t++) {
+      cp_async_wait<K - 1>();  // the oldest of the K groups in flight is (this pair, table t)
+      __syncwarp();
+      RawPair<FOLD> raw;
+      stage_read<FOLD>(my + t * G::SLOT, lane, raw);
+      __syncwarp();  // every lane has its row: the slot can be refilled
+      if (next < n_pairs) stage_issue<FOLD>(my_addr + t * G::SLOT, tabs.in[t], next, n_pairs, lane);
+      cp_async_commit();  // (an empty group after the last tile keeps the count uniform)
+      if (active) finish_pair<FOLD>(raw, tabs.out[t], p, r, lo[t], hi[t]);
+    }
+    if (active) {
+      if (ZC) {
+        lo[0] = fp_mul<FrParams>(w, lo[0]);
+        hi[0] = fp_mul<FrParams>(w, hi[0]);
+      }
+      prod_core<K, true, SKIP1>(lo, hi, acc);
+    }
+  }
+  cp_async_wait<0>();
+  Fr sums[NS];
+#pragma unroll
+  for (int x = 0; x < NS; x++) sums[x] = acc.get_slot(x);
+  block_sum_many(sums, NS, s_part, &partials[(size_t)blockIdx.x * NS]);
+}
+template <int K, bool FOLD>
+constexpr size_t staged_smem() {
+  return (size_t)(SC_WIDE_THREADS / 32) * K * StageGeom<FOLD>::SLOT;
+}
+
 // hand-over to sc_tail: the eq table in the form zerocheck.rs:25 would have left it after the same rounds, i.e. with
 // the last challenge still to be folded in: out[2p + b] = P_{j-1} * eq(b, z_{j-1}) * E_j[p]
 __global__ void __launch_bounds__(256) zc_materialize_eq(const uint4* e_tab, uint64_t half, const ScHead* head, const Fr* z_prev,
@@ -718,6 +832,27 @@ int get_vinv(qz_ctx* ctx, int d, Fr** out) {
   return QZ_OK;
 }
 
+// launch of a staged round (sc_round_staged): opt in to the dynamic shared memory once per instantiation, size the grid by
+// the occupancy the ring allows.  Returns the grid (= number of partial vectors) through *grid_out.
+template <int K, bool FOLD, bool ZC, bool SKIP1>
+int launch_staged(qz_ctx* ctx, const ScTables& tb, const uint4* e_in, uint4* e_out, uint64_t n_pairs, const ScHead* head,
+                  Fr* parts, int max_bps, int* grid_out) {
+  static int bps_cached[16] = {0};  // per device
+  constexpr size_t smem = staged_smem<K, FOLD>();
+  auto kern = sc_round_staged<K, FOLD, ZC, SKIP1>;
+  int& bps = bps_cached[ctx->device & 15];
+  if (bps == 0) {
+    QZ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QZ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, SC_WIDE_THREADS, smem));
+    if (bps < 1) bps = 1;
+  }
+  const uint64_t want = (n_pairs + SC_WIDE_THREADS - 1) / SC_WIDE_THREADS;
+  const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)ctx->sm_count * std::min(bps, max_bps)));
+  QZ_LAUNCH(ctx, kern, grid, SC_WIDE_THREADS, smem, tb, e_in, e_out, n_pairs, head, parts);
+  *grid_out = grid;
+  return QZ_OK;
+}
+
 int round_grid(qz_ctx* ctx, uint64_t n_pairs, int blocks_per_sm, int threads = SC_THREADS) {
   uint64_t want = (n_pairs + threads - 1) / threads;
   uint64_t cap = (uint64_t)ctx->sm_count * blocks_per_sm;
@@ -1034,9 +1169,10 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
         const bool pdl = pdl_ok && n_pairs <= ((uint64_t)1 << 18);
         for (int i = 0; i < K; i++) gt.out[i] = flip ? bufB[g_of[i]] : bufA[g_of[i]];
         const bool wide = zb_wide > 0 && n_pairs >= (uint64_t)8 * SC_WIDE_THREADS * ctx->sm_count * zb_wide;
-        const int grid = wide ? round_grid(ctx, n_pairs, zb_wide, SC_WIDE_THREADS) : round_grid(ctx, n_pairs, zb);
+        int grid = wide ? round_grid(ctx, n_pairs, zb_wide, SC_WIDE_THREADS) : round_grid(ctx, n_pairs, zb);
         const uint4* e_in = e_buf[e_cur];
         uint4* e_out = e_buf[e_cur ^ 1];
+        const bool zc_staged = wide && K == 3 && !getenv("QZ_SC_NO_STAGE");
         const int derive1 = pending && zc_skip1 ? 1 : 0;
 #define QZ_ROUND_ZC(KK, W, T)                                                                                      \
   do {                                                                                                             \
@@ -1048,7 +1184,14 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
           case 1: QZ_ROUND_ZC(1, false, SC_THREADS); break;
           case 2: QZ_ROUND_ZC(2, false, SC_THREADS); break;
           default:
-            if (wide) QZ_ROUND_ZC(3, true, SC_WIDE_THREADS);
+            if (zc_staged) {
+              const int mb = std::max(bps, bps_wide);
+              const ScHead* hd = head;
+              rc = derive1   ? launch_staged<3, true, true, true>(ctx, gt, e_in, e_out, n_pairs, hd, partials, mb, &grid)
+                   : pending ? launch_staged<3, true, true, false>(ctx, gt, e_in, e_out, n_pairs, hd, partials, mb, &grid)
+                             : launch_staged<3, false, true, false>(ctx, gt, e_in, e_out, n_pairs, hd, partials, mb, &grid);
+              if (rc) return rc;
+            } else if (wide) QZ_ROUND_ZC(3, true, SC_WIDE_THREADS);
             else QZ_ROUND_ZC(3, false, SC_THREADS);
         }
 #undef QZ_ROUND_ZC
@@ -1089,7 +1232,16 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
       tabs.in[eq_slot] = eq_full;
     }
     // one round kernel over `n_pairs` pairs of `tb` (fold of the pending challenge fused when `pend`)
-    auto launch_round = [&](const ScTables& tb, uint64_t n_pairs, int pend, int grid, bool wide, bool pdl, Fr* parts) -> int {
+    const bool staged_ok = !getenv("QZ_SC_NO_STAGE");  // A/B switch: large passes without the shared-memory ring
+    const int parts_bps = std::max(bps, bps_wide);    // `partials` holds this many vectors per SM
+    auto launch_round = [&](const ScTables& tb, uint64_t n_pairs, int pend, int& grid, bool wide, bool pdl, Fr* parts) -> int {
+      if (wide && staged_ok && (cp.product_k == 3 || cp.product_k == 4)) {
+        const ScHead* hd = head;
+        if (cp.product_k == 3) return pend ? launch_staged<3, true, false, true>(ctx, tb, nullptr, nullptr, n_pairs, hd, parts, parts_bps, &grid)
+                                           : launch_staged<3, false, false, false>(ctx, tb, nullptr, nullptr, n_pairs, hd, parts, parts_bps, &grid);
+        return pend ? launch_staged<4, true, false, true>(ctx, tb, nullptr, nullptr, n_pairs, hd, parts, parts_bps, &grid)
+                    : launch_staged<4, false, false, false>(ctx, tb, nullptr, nullptr, n_pairs, hd, parts, parts_bps, &grid);
+      }
 #define QZ_ROUND_PROD(K, W, T)                                                                                  \
   do {                                                                                                          \
     if (pend) QZ_LAUNCH_PDL(ctx, pdl, (sc_round_prod<K, W, true>), grid, T, tb, n_pairs, (const ScHead*)head, parts); \
@@ -1119,7 +1271,7 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
       QZ_CUDA(ctx, cudaStreamWaitEvent(ps, ctx->ev_entry, 0));
       const uint64_t per = N / up_chunks, pairs_c = per / 2;
       const bool wide = bps_wide > 0 && pairs_c >= (uint64_t)8 * SC_WIDE_THREADS * ctx->sm_count * bps_wide;
-      const int grid_c = wide ? round_grid(ctx, pairs_c, bps_wide, SC_WIDE_THREADS) : round_grid(ctx, pairs_c, bps);
+      int grid_c = wide ? round_grid(ctx, pairs_c, bps_wide, SC_WIDE_THREADS) : round_grid(ctx, pairs_c, bps);
       for (int c = 0; c < up_chunks; c++) {
         for (int u = 0; u < n_up; u++)
           QZ_CUDA(ctx, cudaMemcpyAsync(up_dst[u] + 32 * per * c, up_src[u] + 32 * per * c, 32 * per, cudaMemcpyHostToDevice, ps));
@@ -1141,7 +1293,7 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
       for (int j = 0; j < ka; j++) tabs.out[j] = flip ? bufB[j] : bufA[j];
       // deferred reduction pays once a thread sums several pairs (its one-off reduction is 3 products per sum)
       const bool wide = bps_wide > 0 && n_pairs >= (uint64_t)8 * SC_WIDE_THREADS * ctx->sm_count * bps_wide;
-      const int grid = wide ? round_grid(ctx, n_pairs, bps_wide, SC_WIDE_THREADS) : round_grid(ctx, n_pairs, bps);
+      int grid = wide ? round_grid(ctx, n_pairs, bps_wide, SC_WIDE_THREADS) : round_grid(ctx, n_pairs, bps);
       rc = launch_round(tabs, n_pairs, pending, grid, wide, pdl, partials);
       if (rc) return rc;
       // every round but the first leaves X = 1 to the running claim (ProdAcc / generic_pair)

@@ -98,3 +98,24 @@ def test_expr_flatten_roundtrip():
     assert consts.shape == (1, 32)
     g = co.to_mont([6, 10])
     assert co.from_mont(co.expr_eval_point([tuple(r) for r in nodes.tolist()], consts, g))[0] == 26
+
+
+def test_rust_sys_crate_declares_every_symbol():
+    """rust/quill-b200-sys/src/lib.rs (uncompiled: no Rust toolchain here) must at least name every function the header
+    declares, with the same number of parameters"""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "quill_b200.h")).read()
+    rust = open(os.path.join(root, "rust", "quill-b200-sys", "src", "lib.rs")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    c_fns = {m.group(1): m.group(2) for m in re.finditer(r"\b(qz_\w+)\s*\(([^;{]*?)\)\s*;", header)}
+    r_fns = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (qz_\w+)\s*\(([^;]*?)\)\s*(?:->[^;]*)?;", rust, flags=re.S)}
+    assert len(c_fns) >= 50
+    missing = sorted(set(c_fns) - set(r_fns))
+    assert not missing, missing
+
+    def arity(params: str) -> int:
+        params = params.strip()
+        return 0 if params in ("", "void") else params.count(",") + 1
+    wrong = [f for f in c_fns if arity(c_fns[f]) != arity(r_fns[f])]
+    assert not wrong, wrong
