@@ -230,6 +230,10 @@ int qz_bench_fp_mul(qz_ctx* ctx, int field, double* out_muls_per_s);
  * 10 inverse by the binary extended Euclidean algorithm (the single-thread critical-path inverse);
  * field: 0 Fr, 1 Fq); G1 add / scalar-mul */
 int qz_test_field_op(qz_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
+/* out[i] = a0[i] + r (a1[i] - a0[i]) by the fixed-challenge fold of the large sumcheck passes (table of shifted multiples
+ * of r in constant memory, 88 instead of 136 multiply-adds per product); a1 - a0 is taken without reduction, so any
+ * 256-bit a0 < p, a1 < p are valid */
+int qz_test_fold(qz_ctx* ctx, const uint8_t r[32], const uint8_t* a0, const uint8_t* a1, uint8_t* out, size_t n);
 int qz_test_g1_add(qz_ctx* ctx, const uint8_t* a_xy, const uint8_t* b_xy, uint8_t* out_xy, size_t n);
 int qz_test_g1_mul(qz_ctx* ctx, const uint8_t* a_xy, const uint8_t* scalars, uint8_t* out_xy, size_t n);
 

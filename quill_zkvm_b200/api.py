@@ -142,6 +142,13 @@ class Context:
         self.check(self.lib.qz_test_field_op(self.h, field, op, _ptr(a), bp, _ptr(out), a.shape[0]))
         return out
 
+    def fold(self, r: np.ndarray, a0: np.ndarray, a1: np.ndarray) -> np.ndarray:
+        """test hook: a0 + r (a1 - a0) element-wise through the fixed-challenge fold of the large sumcheck passes"""
+        a0, a1 = _u8(a0).reshape(-1, 32), _u8(a1).reshape(-1, 32)
+        out = np.zeros_like(a0)
+        self.check(self.lib.qz_test_fold(self.h, _ptr(_u8(r, (32,))), _ptr(a0), _ptr(a1), _ptr(out), a0.shape[0]))
+        return out
+
     def g1_add(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
         a, b = _u8(a, (-1, 64)), _u8(b, (-1, 64))
         out = np.zeros_like(a)

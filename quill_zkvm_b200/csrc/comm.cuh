@@ -20,6 +20,11 @@ struct PeerSlot {
 struct PeerMailbox {
   PeerSlot slot[MBOX_SLOTS];
   uint32_t timed_out;  // set by a consumer that gave up waiting (a peer died): the host turns it into QZ_ERR_NCCL
+  uint32_t pad_[7];
+  // hand-over of a sharded sumcheck to its last rounds (sumcheck.cu sc_mid): every rank stores its shard of every table
+  // here, in every rank's mailbox, rank order = index order.  Two copies, picked by the parity of the exchange number: a
+  // rank can be at most one proof ahead of the slowest one (it cannot finish proof n + 1 without that rank's shards).
+  Fr gather[2][SC_MAX_K][1 << SC_TAIL_LOG];
 };
 
 // ---- device side -------------------------------------------------------------------------------------------------------

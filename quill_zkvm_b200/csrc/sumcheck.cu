@@ -13,6 +13,7 @@
 //   * once a table is down to 2^SC_TAIL_LOG elements a single block finishes all remaining rounds in one launch.
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 #include <vector>
 #include "comm.cuh"
 #include "ctx.cuh"
@@ -20,7 +21,7 @@
 
 namespace qz {
 
-constexpr int SC_TAIL_LOG = 11;
+constexpr int SC_MID_LOG = 18;  // tables of at most 2^18 elements (per rank): sc_mid runs every remaining round in one launch
 constexpr int SC_THREADS = 256;
 constexpr int SC_WIDE_THREADS = 128;  // deferred-reduction round kernel: 168 registers, 3 blocks per SM
 #ifndef QZ_SC_WIDE_BPS
@@ -30,19 +31,46 @@ constexpr int SC_WIDE_THREADS = 128;  // deferred-reduction round kernel: 168 re
 // ---- loads ---------------------------------------------------------------------------------------------------------------
 QZ_DEV Fr ld_elem(const uint4* base, uint64_t e) { return fp_load<FrParams>(base + 2 * e); }
 QZ_DEV void st_elem(uint4* base, uint64_t e, const Fr& v) { fp_store<FrParams>(base + 2 * e, v); }
+// the same load past L1 (ld.global.cv): for data another block -- or another GPU -- wrote during this kernel (sc_mid)
+QZ_DEV Fr ld_elem_cv(const uint4* base, uint64_t e) {
+  const uint4 a = __ldcv(base + 2 * e), b = __ldcv(base + 2 * e + 1);
+  Fr r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+template <bool CV>
+QZ_DEV Fr ld_elem_t(const uint4* base, uint64_t e) {
+  return CV ? ld_elem_cv(base, e) : ld_elem(base, e);
+}
+
+// multiples of the pending challenge for fp_mul_fixed (ff.cuh), refreshed by the host with a device-to-device copy of the
+// table sc_round_close left in device memory, before every pass that folds with it (the large passes).  Constant memory:
+// the 64 words are instruction operands, not registers.  One table per device and process: sumcheck_run serialises the
+// contexts of a device while it uses it.
+__constant__ uint32_t c_fold[64];
+// lo + r (hi - lo) with r given by the table
+QZ_DEV Fr fold_fixed(const Fr& lo, const Fr& hi) {
+  return fp_add<FrParams>(lo, fp_mul_fixed<FrParams>(fp_sub_lazy<FrParams>(hi, lo), c_fold));
+}
 
 // fetch pair p of table t, folding the pending challenge first when `fold` (sumcheck.rs:81-92 fused into the next
 // round's pass): lo' = a0 + r (a1 - a0), hi' = a2 + r (a3 - a2), both written to the half-size table.
+template <bool CV = false, bool CF = false>
 QZ_DEV void fetch_pair(const uint4* in, uint4* out, uint64_t p, bool fold, const Fr& r, Fr& lo, Fr& hi) {
   if (fold) {
-    Fr a0 = ld_elem(in, 4 * p), a1 = ld_elem(in, 4 * p + 1), a2 = ld_elem(in, 4 * p + 2), a3 = ld_elem(in, 4 * p + 3);
-    lo = fp_add<FrParams>(a0, fp_mul<FrParams>(r, fp_sub<FrParams>(a1, a0)));
-    hi = fp_add<FrParams>(a2, fp_mul<FrParams>(r, fp_sub<FrParams>(a3, a2)));
+    Fr a0 = ld_elem_t<CV>(in, 4 * p), a1 = ld_elem_t<CV>(in, 4 * p + 1), a2 = ld_elem_t<CV>(in, 4 * p + 2), a3 = ld_elem_t<CV>(in, 4 * p + 3);
+    if (CF) {
+      lo = fold_fixed(a0, a1);
+      hi = fold_fixed(a2, a3);
+    } else {
+      lo = fp_add<FrParams>(a0, fp_mul<FrParams>(r, fp_sub<FrParams>(a1, a0)));
+      hi = fp_add<FrParams>(a2, fp_mul<FrParams>(r, fp_sub<FrParams>(a3, a2)));
+    }
     st_elem(out, 2 * p, lo);
     st_elem(out, 2 * p + 1, hi);
   } else {
-    lo = ld_elem(in, 2 * p);
-    hi = ld_elem(in, 2 * p + 1);
+    lo = ld_elem_t<CV>(in, 2 * p);
+    hi = ld_elem_t<CV>(in, 2 * p + 1);
   }
 }
 
@@ -58,11 +86,16 @@ QZ_DEV void load_raw(const uint4* in, uint64_t p, RawPair<FOLD>& raw) {
 #pragma unroll
   for (int j = 0; j < (FOLD ? 4 : 2); j++) raw.e[j] = ld_elem(in, (FOLD ? 4 : 2) * p + j);
 }
-template <bool FOLD>
+template <bool FOLD, bool CF = false>
 QZ_DEV void finish_pair(const RawPair<FOLD>& raw, uint4* out, uint64_t p, const Fr& r, Fr& lo, Fr& hi) {
   if (FOLD) {
-    lo = fp_add<FrParams>(raw.e[0], fp_mul<FrParams>(r, fp_sub<FrParams>(raw.e[1], raw.e[0])));
-    hi = fp_add<FrParams>(raw.e[FOLD ? 2 : 0], fp_mul<FrParams>(r, fp_sub<FrParams>(raw.e[FOLD ? 3 : 1], raw.e[FOLD ? 2 : 0])));
+    if (CF) {
+      lo = fold_fixed(raw.e[0], raw.e[1]);
+      hi = fold_fixed(raw.e[FOLD ? 2 : 0], raw.e[FOLD ? 3 : 1]);
+    } else {
+      lo = fp_add<FrParams>(raw.e[0], fp_mul<FrParams>(r, fp_sub<FrParams>(raw.e[1], raw.e[0])));
+      hi = fp_add<FrParams>(raw.e[FOLD ? 2 : 0], fp_mul<FrParams>(r, fp_sub<FrParams>(raw.e[FOLD ? 3 : 1], raw.e[FOLD ? 2 : 0])));
+    }
     st_elem(out, 2 * p, lo);
     st_elem(out, 2 * p + 1, hi);
   } else {
@@ -157,12 +190,12 @@ QZ_DEV void prod_core(const Fr* lo, const Fr* hi, ProdAcc<K, WIDE, SKIP1>& acc) 
 }
 
 // tail kernel: `fold` is a run-time flag, tables fetched one after the other
-template <int K, bool WIDE>
-QZ_DEV void prod_pair(const ScTables& tabs, uint64_t p, bool fold, const Fr& r, ProdAcc<K, WIDE, false>& acc) {
+template <int K, bool WIDE, bool SKIP1 = false, bool CV = false>
+QZ_DEV void prod_pair(const ScTables& tabs, uint64_t p, bool fold, const Fr& r, ProdAcc<K, WIDE, SKIP1>& acc) {
   Fr lo[K], hi[K];
 #pragma unroll
-  for (int t = 0; t < K; t++) fetch_pair(tabs.in[t], tabs.out[t], p, fold, r, lo[t], hi[t]);
-  prod_core<K, WIDE, false>(lo, hi, acc);
+  for (int t = 0; t < K; t++) fetch_pair<CV>(tabs.in[t], tabs.out[t], p, fold, r, lo[t], hi[t]);
+  prod_core<K, WIDE, SKIP1>(lo, hi, acc);
 }
 
 // ---- round kernel, fast path ---------------------------------------------------------------------------------------------
@@ -185,7 +218,7 @@ __global__ void __launch_bounds__(WIDE ? SC_WIDE_THREADS : SC_THREADS, (WIDE ? (
     for (int t = 0; t < K; t++) load_raw<FOLD>(tabs.in[t], p, raw[t]);
     Fr lo[K], hi[K];
 #pragma unroll
-    for (int t = 0; t < K; t++) finish_pair<FOLD>(raw[t], tabs.out[t], p, r, lo[t], hi[t]);
+    for (int t = 0; t < K; t++) finish_pair<FOLD, WIDE>(raw[t], tabs.out[t], p, r, lo[t], hi[t]);  // WIDE passes fold by c_fold
     prod_core<K, WIDE, FOLD>(lo, hi, acc);
   }
   Fr sums[NS];
@@ -231,7 +264,7 @@ __global__ void __launch_bounds__(WIDE ? SC_WIDE_THREADS : SC_THREADS, (WIDE ? Q
     }
     Fr lo[K], hi[K];
 #pragma unroll
-    for (int t = 0; t < K; t++) finish_pair<FOLD>(raw[t], tabs.out[t], p, r, lo[t], hi[t]);
+    for (int t = 0; t < K; t++) finish_pair<FOLD, WIDE>(raw[t], tabs.out[t], p, r, lo[t], hi[t]);
     lo[0] = fp_mul<FrParams>(w, lo[0]);
     hi[0] = fp_mul<FrParams>(w, hi[0]);
     prod_core<K, WIDE, SKIP1>(lo, hi, acc);
@@ -241,125 +274,19 @@ __global__ void __launch_bounds__(WIDE ? SC_WIDE_THREADS : SC_THREADS, (WIDE ? Q
   for (int x = 0; x < NS; x++) sums[x] = acc.get_slot(x);
   block_sum_many(sums, NS, s_part, &partials[(size_t)blockIdx.x * NS]);
 }
-// ---- the same rounds with shared-memory staging (large passes) ------------------------------------------------------------------
-// The kernels above front-load a pair's 12 global loads (96 registers for three tables in a fold round) and then wait:
-// ncu r01 showed the integer pipe at 71 % with the memory round trip exposed once per pair and the register file capping
-// the SM at 12 warps.  Here every warp owns a small ring in shared memory, one slot per table, filled with cp.async
-// (global -> shared, no registers, L1 bypassed): while the warp folds and multiplies pair i, the tiles of pair i + 1 are
-// already in flight -- a slot is refilled for the next pair as soon as its rows have been read.  A row is one thread's
-// 128 contiguous bytes (four elements; two in round 0), stored with a 16-byte pad so that the eight lanes of a quarter
-// warp read their rows from different banks; the copies themselves are issued chunk-major, 512 contiguous bytes per
-// instruction.  No block-level barrier, no mbarrier: a thread waits for its own copy groups, __syncwarp publishes them.
-QZ_DEV void cp_async16(uint32_t smem_addr, const void* gptr) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
-}
-QZ_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-QZ_DEV void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-template <bool FOLD>
-struct StageGeom {
-  static constexpr int ROW = FOLD ? 128 : 64;        // bytes of one pair of one table
-  static constexpr int STRIDE = ROW + 16;            // padded row
-  static constexpr int SLOT = 32 * STRIDE;           // one warp-tile of one table
-  static constexpr int CHUNKS = ROW / 16;            // 16-byte chunks per row = copy instructions per tile
-};
-// copy rows [base, base + 32) of `in` (row = ROW bytes) into the slot; rows at or beyond n_pairs are skipped
-template <bool FOLD>
-QZ_DEV void stage_issue(uint32_t slot_addr, const uint4* in, uint64_t base, uint64_t n_pairs, int lane) {
-  using G = StageGeom<FOLD>;
-  const uint8_t* src = reinterpret_cast<const uint8_t*>(in) + base * G::ROW;
-  const uint64_t valid = n_pairs - base < 32 ? n_pairs - base : 32;  // rows of this tile that exist
-#pragma unroll
-  for (int j = 0; j < G::CHUNKS; j++) {
-    const int g = j * 32 + lane, row = g / G::CHUNKS, chunk = g % G::CHUNKS;
-    if ((uint64_t)row < valid) cp_async16(slot_addr + row * G::STRIDE + chunk * 16, src + (size_t)g * 16);
-  }
-}
-template <bool FOLD>
-QZ_DEV void stage_read(const uint8_t* slot, int lane, RawPair<FOLD>& raw) {
-  using G = StageGeom<FOLD>;
-  const uint4* row = reinterpret_cast<const uint4*>(slot + lane * G::STRIDE);
-#pragma unroll
-  for (int e = 0; e < (FOLD ? 4 : 2); e++) {
-    const uint4 a = row[2 * e], b = row[2 * e + 1];
-    raw.e[e].v[0] = a.x; raw.e[e].v[1] = a.y; raw.e[e].v[2] = a.z; raw.e[e].v[3] = a.w;
-    raw.e[e].v[4] = b.x; raw.e[e].v[5] = b.y; raw.e[e].v[6] = b.z; raw.e[e].v[7] = b.w;
-  }
-}
-// ZC: the eq-factored zero-check form (see sc_round_zc); SKIP1 as above (plain rounds: SKIP1 == FOLD)
-template <int K, bool FOLD, bool ZC, bool SKIP1>
-__global__ void __launch_bounds__(SC_WIDE_THREADS, K <= 3 ? QZ_SC_WIDE_BPS : 3)
-    sc_round_staged(ScTables tabs, const uint4* e_in, uint4* e_out, uint64_t n_pairs, const ScHead* head, Fr* partials) {
-  using G = StageGeom<FOLD>;
-  constexpr int NS = ProdAcc<K, true, SKIP1>::NS;
-  extern __shared__ __align__(16) uint8_t s_stage[];  // [warp][table][SLOT]
-  __shared__ Fr s_part[(SC_WIDE_THREADS / 32) * NS];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint8_t* my = s_stage + (size_t)warp * K * G::SLOT;
-  const uint32_t my_addr = (uint32_t)__cvta_generic_to_shared(my);
-  ProdAcc<K, true, SKIP1> acc;
-  acc.init();
-  Fr r = fp_zero<FrParams>();
-  if (FOLD) r = head->r;
-  const uint64_t stride = (uint64_t)gridDim.x * (SC_WIDE_THREADS / 32) * 32;
-  uint64_t base = ((uint64_t)blockIdx.x * (SC_WIDE_THREADS / 32) + warp) * 32;
-  if (base < n_pairs) {
-#pragma unroll
-    for (int t = 0; t < K; t++) {
-      stage_issue<FOLD>(my_addr + t * G::SLOT, tabs.in[t], base, n_pairs, lane);
-      cp_async_commit();
-    }
-  }
-  for (; base < n_pairs; base += stride) {
-    const uint64_t next = base + stride, p = base + lane;
-    const bool active = p < n_pairs;
-    Fr w;
-    if (ZC && active) {
-      if (FOLD) {
-        w = fp_add<FrParams>(ld_elem(e_in, 2 * p), ld_elem(e_in, 2 * p + 1));
-        st_elem(e_out, p, w);
-      } else {
-        w = ld_elem(e_in, p);
-      }
-    }
-    Fr lo[K], hi[K];
-#pragma unroll
-    for (int t = 0; t < K; t++) {
-      cp_async_wait<K - 1>();  // the oldest of the K groups in flight is (this pair, table t)
-      __syncwarp();
-      RawPair<FOLD> raw;
-      stage_read<FOLD>(my + t * G::SLOT, lane, raw);
-      __syncwarp();  // every lane has its row: the slot can be refilled
-      if (next < n_pairs) stage_issue<FOLD>(my_addr + t * G::SLOT, tabs.in[t], next, n_pairs, lane);
-      cp_async_commit();  // (an empty group after the last tile keeps the count uniform)
-      if (active) finish_pair<FOLD>(raw, tabs.out[t], p, r, lo[t], hi[t]);
-    }
-    if (active) {
-      if (ZC) {
-        lo[0] = fp_mul<FrParams>(w, lo[0]);
-        hi[0] = fp_mul<FrParams>(w, hi[0]);
-      }
-      prod_core<K, true, SKIP1>(lo, hi, acc);
-    }
-  }
-  cp_async_wait<0>();
-  Fr sums[NS];
-#pragma unroll
-  for (int x = 0; x < NS; x++) sums[x] = acc.get_slot(x);
-  block_sum_many(sums, NS, s_part, &partials[(size_t)blockIdx.x * NS]);
-}
-template <int K, bool FOLD>
-constexpr size_t staged_smem() {
-  return (size_t)(SC_WIDE_THREADS / 32) * K * StageGeom<FOLD>::SLOT;
-}
+// (A variant of these kernels that staged each warp's tiles in shared memory with cp.async, one slot per table refilled a
+// pair ahead, was built and measured in round 2: 3.59 ms against 3.19 ms for the streaming rounds of a 2^24 proof.  The
+// passes are bound by the integer multiply pipe, not by the exposed load latency; the ring's copy / read / __syncwarp
+// instructions and its spills only took issue slots from the multiplier.  Removed.)
 
 // hand-over to sc_tail: the eq table in the form zerocheck.rs:25 would have left it after the same rounds, i.e. with
 // the last challenge still to be folded in: out[2p + b] = P_{j-1} * eq(b, z_{j-1}) * E_j[p]
-__global__ void __launch_bounds__(256) zc_materialize_eq(const uint4* e_tab, uint64_t half, const ScHead* head, const Fr* z_prev,
+// The running claim changes meaning with it: the eq-factored rounds kept t_j(r_j), the rounds that follow sum h * eq as
+// the reference does and expect s_j(r_j) = P_{j+1} t_j(r_j).
+__global__ void __launch_bounds__(256) zc_materialize_eq(const uint4* e_tab, uint64_t half, ScHead* head, const Fr* z_prev,
                                                         uint4* out) {
   const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p == 0) head->claim = fp_mul<FrParams>(head->zc_prefix, head->claim);
   if (p >= half) return;
   const Fr z = *z_prev, P = head->zc_prefix_prev, e = ld_elem(e_tab, p);
   const Fr hi = fp_mul<FrParams>(fp_mul<FrParams>(P, z), e);
@@ -370,12 +297,13 @@ __global__ void __launch_bounds__(256) zc_materialize_eq(const uint4* e_tab, uin
 
 // ---- round kernel, generic expression tree -----------------------------------------------------------------------------------
 // skip1: X = 1 is not evaluated (see ProdAcc); the sums are stored compactly, acc[0] = X 0, acc[x - 1] = X x >= 2
+template <bool CV = false, bool CF = false>
 QZ_DEV void generic_pair(const ScTables& tabs, uint64_t p, bool fold, const Fr& r, const uint32_t* s_ops,
                          uint32_t n_ops, int k, int d, const Fr* consts, Fr* acc, bool skip1 = false) {
   Fr cur[SC_MAX_K], df[SC_MAX_K];
   for (int t = 0; t < k; t++) {
     Fr hi;
-    fetch_pair(tabs.in[t], tabs.out[t], p, fold, r, cur[t], hi);
+    fetch_pair<CV, CF>(tabs.in[t], tabs.out[t], p, fold, r, cur[t], hi);
     df[t] = fp_sub<FrParams>(hi, cur[t]);
   }
   for (int x = 0; x <= d; x++) {
@@ -388,6 +316,8 @@ QZ_DEV void generic_pair(const ScTables& tabs, uint64_t p, bool fold, const Fr& 
   }
 }
 
+// CF: fold by the challenge table in constant memory (large passes; the host refreshes c_fold first)
+template <bool CF>
 __global__ void __launch_bounds__(SC_THREADS) sc_round_generic(ScTables tabs, uint64_t n_pairs, int fold,
                                                               const ScHead* head, const ScProgram* prog,
                                                               const Fr* consts, Fr* partials) {
@@ -407,7 +337,7 @@ __global__ void __launch_bounds__(SC_THREADS) sc_round_generic(ScTables tabs, ui
   const int ns = skip1 ? d : d + 1;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += stride)
-    generic_pair(tabs, p, fold != 0, r, s_ops, n_ops, k, d, consts, acc, skip1);
+    generic_pair<false, CF>(tabs, p, fold != 0, r, s_ops, n_ops, k, d, consts, acc, skip1);
   block_sum_many(acc, ns, s_part, &partials[(size_t)blockIdx.x * ns]);
 }
 
@@ -417,7 +347,7 @@ __global__ void __launch_bounds__(SC_THREADS) sc_round_generic(ScTables tabs, ui
 __global__ void __launch_bounds__(SC_THREADS) sc_finalize(const Fr* partials, int n_parts, int d, ScHead* head,
                                                          const Fr* vinv, Fr* out_coeffs_row, uint32_t* out_len,
                                                          Fr* out_point_slot, int max_coeffs, const Fr* zc_z, int derive1,
-                                                         const Fr* zc_zinv) {
+                                                         const Fr* zc_zinv, uint32_t* foldc) {
   __shared__ Fr s_part[(SC_THREADS / 32) * SC_MAX_COEFFS];
   __shared__ Fr s_evals[SC_MAX_COEFFS];
   __shared__ Fr s_coef[SC_MAX_COEFFS];
@@ -433,7 +363,7 @@ __global__ void __launch_bounds__(SC_THREADS) sc_finalize(const Fr* partials, in
   block_sum_many(v, ns, s_part, s_evals);
   if (derive1) sc_expand_evals(head, d, s_evals, zc_z, zc_zinv);
   sc_round_close(head, vinv, d, s_evals, s_coef, s_msg, s_prod, out_coeffs_row, out_len, out_point_slot, max_coeffs, zc_z,
-                 true);
+                 true, foldc);
 }
 
 // Sharded mode with peer mailboxes (comm.cuh): ONE launch per round after the round kernel.  The block sums this rank's
@@ -444,7 +374,8 @@ __global__ void __launch_bounds__(SC_THREADS) sc_finalize_peers(const Fr* partia
                                                                PeerMailbox* const* peers, int rank, int G, uint32_t seq,
                                                                ScHead* head, const Fr* vinv, Fr* out_coeffs_row,
                                                                uint32_t* out_len, Fr* out_point_slot, int max_coeffs,
-                                                               const Fr* zc_z, int derive1, const Fr* zc_zinv) {
+                                                               const Fr* zc_z, int derive1, const Fr* zc_zinv,
+                                                               uint32_t* foldc) {
   __shared__ Fr s_part[(SC_THREADS / 32) * SC_MAX_COEFFS];
   __shared__ Fr s_evals[SC_MAX_COEFFS];
   __shared__ Fr s_coef[SC_MAX_COEFFS];
@@ -468,7 +399,7 @@ __global__ void __launch_bounds__(SC_THREADS) sc_finalize_peers(const Fr* partia
   __syncthreads();
   if (derive1) sc_expand_evals(head, d, s_evals, zc_z, zc_zinv);
   sc_round_close(head, vinv, d, s_evals, s_coef, s_msg, s_prod, out_coeffs_row, out_len, out_point_slot, max_coeffs, zc_z,
-                 true);
+                 true, foldc);
 }
 
 // reduce block partials to one vector per rank (sharded mode: the vectors are all-gathered, then sc_finalize)
@@ -481,24 +412,65 @@ __global__ void __launch_bounds__(SC_THREADS) sc_reduce_partials(const Fr* parti
   block_sum_many(v, d + 1, s_part, out);
 }
 
-// ---- tail: one block runs every remaining round -------------------------------------------------------------------------------
-// in[t]: current tables of `size` elements; bufa/bufb: scratch of >= size/2 elements per table.
+// ---- the short rounds: one persistent kernel runs every remaining round ----------------------------------------------------------
+// Once a table is down to 2^SC_MID_LOG elements a round is pure latency (two launches, ~30 us, whatever its size: r01).
+// sc_mid takes the proof from there to the end in ONE launch.  While a round still has more pairs than one block has
+// threads it is spread over the (co-resident, cooperatively launched) grid: every block folds and evaluates its pairs
+// and parks one partial vector, the block that arrives LAST at the round's counter sums the vectors, closes the round
+// (interpolation, blake3 transcript, challenge -- sc_round_close) and releases a flag the other blocks spin on.  Blocks
+// whose index is beyond a round's pairs exit (rounds only shrink); from 2^SC_TAIL_LOG elements on block 0 is alone and no
+// counter is touched.  Data written by other blocks during the kernel is read past L1 (ld.cv).
+// Sharded proofs (G > 1): the closing block also exchanges the partial vector with the peers' mailboxes, exactly as
+// sc_finalize_peers does, and when G x the local size is down to 2^SC_TAIL_LOG every rank stores its shard into every
+// peer's gather area (rank order = index order) and finishes the remaining rounds alone -- no collective launch.
+// in[t]: current tables of `size` elements; bufs.a / bufs.b: scratch of >= max(size, 2^SC_TAIL_LOG) / 2 elements per table.
 struct ScTailBufs {
   uint4* a[SC_MAX_K];
   uint4* b[SC_MAX_K];
 };
+struct ScMidSync {
+  unsigned int arrive;  // blocks that finished their share of a round, cumulative over the rounds
+  unsigned int flag;    // number of rounds closed so far (release / acquire)
+};
+QZ_DEV unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+QZ_DEV void st_release_gpu(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// one block's share of a round: pairs first, first + step, ... ; the ns sums land in acc[0 .. ns)
+template <int KP, bool SKIP1>
+QZ_DEV void mid_block_pass(const ScTables& view, uint64_t first, uint64_t step, uint64_t n_pairs, bool fold, const Fr& r,
+                           const uint32_t* s_ops, uint32_t n_ops, int k, int d, const Fr* consts, Fr* acc) {
+  if (KP > 0) {
+    constexpr int KX = KP > 0 ? KP : 1;
+    ProdAcc<KX, false, SKIP1> pa;
+    pa.init();
+    for (uint64_t p = first; p < n_pairs; p += step) prod_pair<KX, false, SKIP1, true>(view, p, fold, r, pa);
+#pragma unroll
+    for (int x = 0; x < ProdAcc<KX, false, SKIP1>::NS; x++) acc[x] = pa.get_slot(x);
+  } else {
+    for (int x = 0; x <= d; x++) acc[x] = fp_zero<FrParams>();
+    for (uint64_t p = first; p < n_pairs; p += step) generic_pair<true>(view, p, fold, r, s_ops, n_ops, k, d, consts, acc, SKIP1);
+  }
+}
 // KP > 0: h is a product of KP distinct tables (same fast path as sc_round_prod); KP == 0: interpret the program
 template <int KP>
-__global__ void __launch_bounds__(SC_THREADS) sc_tail(ScTables tabs, ScTailBufs bufs, uint64_t size, int pending_fold,
-                                                     ScHead* head, const ScProgram* prog, const Fr* consts,
-                                                     const Fr* vinv, Fr* out_coeffs, uint32_t* out_lens,
-                                                     Fr* out_point, int round, int max_coeffs) {
+__global__ void __launch_bounds__(SC_THREADS) sc_mid(ScTables tabs, ScTailBufs bufs, uint64_t size, int pending_fold,
+                                                    ScHead* head, const ScProgram* prog, const Fr* consts, const Fr* vinv,
+                                                    Fr* out_coeffs, uint32_t* out_lens, Fr* out_point, int round,
+                                                    int max_coeffs, Fr* partials, ScMidSync* sync,
+                                                    PeerMailbox* const* peers, int rank, int G, uint32_t seq,
+                                                    int gather_par, const Fr* zc_z, int zc_n) {
   __shared__ Fr s_part[(SC_THREADS / 32) * SC_MAX_COEFFS];
   __shared__ Fr s_evals[SC_MAX_COEFFS];
   __shared__ Fr s_coef[SC_MAX_COEFFS];
   __shared__ Fr s_prod[SC_PROD_SLOTS];
   __shared__ __align__(16) uint32_t s_msg[SC_MSG_WORDS];
   __shared__ uint32_t s_ops[SC_MAX_OPS];
+  __shared__ int s_last;
   grid_dep_wait();
   const uint32_t n_ops = prog->n_ops;
   const int d = (int)prog->degree, k = (int)prog->k;
@@ -507,29 +479,99 @@ __global__ void __launch_bounds__(SC_THREADS) sc_tail(ScTables tabs, ScTailBufs 
   ScTables view;
   for (int t = 0; t < k; t++) view.in[t] = tabs.in[t];
   int flip = 0;
+  bool gathered = G == 1;
+  unsigned int arrive_target = 0, rounds_closed = 0;
   // `size` elements per table with (pending_fold) the last challenge still to be folded in.  Each round is ONE pass:
   // fold (reads 4, writes 2) fused with the evaluation of the new pairs, exactly like the streaming kernel.
-  while (!(pending_fold && size == 2) && size > 1) {
+  for (;;) {
+    if (!gathered && size * (uint64_t)G <= ((uint64_t)1 << SC_TAIL_LOG)) {
+      // hand-over of a sharded proof: every rank's shard into every rank's gather area, then everyone runs alone
+      if (blockIdx.x != 0) return;
+      PeerMailbox* mine = peers[rank];
+      const int par = gather_par;
+      for (int t = 0; t < k; t++)
+        for (uint64_t i = threadIdx.x; i < size; i += blockDim.x) {
+          const Fr v = ld_elem_cv(view.in[t], i);
+          for (int g = 0; g < G; g++) fp_store<FrParams>(&peers[g]->gather[par][t][(uint64_t)rank * size + i], v);
+        }
+      __syncthreads();
+      if (threadIdx.x == 0) s_evals[0] = fp_zero<FrParams>();
+      __syncthreads();
+      peer_exchange(peers, rank, G, seq++, s_evals, 1);  // fence + flags: every rank's stores above are visible after it
+      if (threadIdx.x == 0 && *reinterpret_cast<volatile uint32_t*>(&mine->timed_out)) head->peer_fault = 1;
+      for (int t = 0; t < k; t++) view.in[t] = reinterpret_cast<const uint4*>(&mine->gather[par][t][0]);
+      size *= (uint64_t)G;
+      gathered = true;
+    }
+    if (size <= 1 || (pending_fold && size == 2)) break;
     const uint64_t n_pairs = pending_fold ? size / 4 : size / 2;
+    const bool alone = G > 1 && gathered;  // after the gather a rank never spreads a round again (the data is tiny)
+    const uint64_t want = (n_pairs + SC_THREADS - 1) / SC_THREADS;
+    const unsigned int nblk = alone ? 1u : (unsigned int)(want < gridDim.x ? (want ? want : 1) : gridDim.x);
+    if (blockIdx.x >= nblk) return;  // rounds only shrink: idle now means idle until the end
     for (int t = 0; t < k; t++) view.out[t] = flip ? bufs.b[t] : bufs.a[t];
     Fr r = fp_zero<FrParams>();
-    if (pending_fold) r = head->r;
+    if (pending_fold) r = ld_elem_cv(reinterpret_cast<const uint4*>(&head->r), 0);
+    const bool skip1 = pending_fold && d >= 1;  // X = 1 from the running claim (ProdAcc)
+    const int ns = skip1 ? d : d + 1;
     Fr acc[SC_MAX_COEFFS];
-    if (KP > 0) {
-      constexpr int KX = KP > 0 ? KP : 1;
-      ProdAcc<KX, false, false> pa;
-      pa.init();
-      for (uint64_t p = threadIdx.x; p < n_pairs; p += blockDim.x) prod_pair<KX, false>(view, p, pending_fold != 0, r, pa);
-#pragma unroll
-      for (int x = 0; x <= KX; x++) acc[x] = pa.get_slot(x);
+    const uint64_t first = (uint64_t)blockIdx.x * SC_THREADS + threadIdx.x, step = (uint64_t)nblk * SC_THREADS;
+    if (skip1) mid_block_pass<KP, true>(view, first, step, n_pairs, true, r, s_ops, n_ops, k, d, consts, acc);
+    else mid_block_pass<KP, false>(view, first, step, n_pairs, pending_fold != 0, r, s_ops, n_ops, k, d, consts, acc);
+    bool closer = true;
+    if (nblk > 1) {  // park this block's vector; the last block to arrive closes the round
+      block_sum_many(acc, ns, s_part, &partials[(size_t)blockIdx.x * ns]);
+      arrive_target += nblk;
+      if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(&sync->arrive, 1u) + 1u == arrive_target;
+      }
+      __syncthreads();
+      closer = s_last != 0;
+      if (closer) {  // one parked vector per thread (at most gridDim.x <= blockDim.x of them), then a block sum
+        __threadfence();
+        for (int x = 0; x < ns; x++)
+          acc[x] = threadIdx.x < nblk ? ld_elem_cv(reinterpret_cast<const uint4*>(partials), (uint64_t)threadIdx.x * ns + x)
+                                      : fp_zero<FrParams>();
+        block_sum_many(acc, ns, s_part, s_evals);
+      }
     } else {
-      for (int x = 0; x <= d; x++) acc[x] = fp_zero<FrParams>();
-      for (uint64_t p = threadIdx.x; p < n_pairs; p += blockDim.x)
-        generic_pair(view, p, pending_fold != 0, r, s_ops, n_ops, k, d, consts, acc);
+      block_sum_many(acc, ns, s_part, s_evals);
     }
-    block_sum_many(acc, d + 1, s_part, s_evals);
-    sc_round_close(head, vinv, d, s_evals, s_coef, s_msg, s_prod, out_coeffs + (size_t)round * max_coeffs,
-                   out_lens + round, out_point + round, max_coeffs);
+    if (closer) {
+      if (!gathered) {  // sharded: all ranks' vectors (comm.cuh), exact field addition in any order
+        const PeerSlot* got = peer_exchange(peers, rank, G, seq, s_evals, ns);
+        if (threadIdx.x == 0 && *reinterpret_cast<volatile uint32_t*>(&peers[rank]->timed_out)) head->peer_fault = 1;
+        if ((int)threadIdx.x < ns) {
+          Fr sum = fp_zero<FrParams>();
+          for (int g = 0; g < G; g++) sum = fp_add<FrParams>(sum, ld_fresh(&got->data[g][threadIdx.x]));
+          s_evals[threadIdx.x] = sum;
+        }
+        __syncthreads();
+      }
+      if (skip1) sc_expand_evals(head, d, s_evals, nullptr, nullptr);
+      sc_round_close(head, vinv, d, s_evals, s_coef, s_msg, s_prod, out_coeffs + (size_t)round * max_coeffs,
+                     out_lens + round, out_point + round, max_coeffs, nullptr, true);
+      if (nblk > 1 && threadIdx.x == 0) {
+        __threadfence();
+        st_release_gpu(&sync->flag, rounds_closed + 1);
+      }
+    }
+    rounds_closed++;
+    if (!gathered) seq++;
+    if (nblk > 1) {
+      if (threadIdx.x == 0 && ld_acquire_gpu(&sync->flag) < rounds_closed) {
+        // the closing block may itself be waiting for a peer GPU (20 s at most, comm.cuh); give up a little later than that
+        // rather than hang the device: the proof is void (peer_fault) and every block runs on to the end on stale data
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_gpu(&sync->flag) < rounds_closed)
+          if (global_timer_ns() - t0 > PEER_WAIT_NS + PEER_WAIT_NS / 2) {
+            head->peer_fault = 2;
+            break;
+          }
+      }
+      __syncthreads();
+    }
     round++;
     if (pending_fold) {
       for (int t = 0; t < k; t++) view.in[t] = view.out[t];
@@ -538,19 +580,38 @@ __global__ void __launch_bounds__(SC_THREADS) sc_tail(ScTables tabs, ScTailBufs 
     }
     pending_fold = 1;
   }
-  if (threadIdx.x == 0) {  // sumcheck.rs:81-100: last fold, then h(g_1(r), ..., g_k(r))
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // sumcheck.rs:81-100: last fold, then h(g_1(r), ..., g_k(r))
     Fr fin[SC_MAX_K];
     const Fr r = head->r;
     for (int t = 0; t < k; t++) {
-      Fr lo = ld_elem(view.in[t], 0);
+      Fr lo = ld_elem_cv(view.in[t], 0);
       if (pending_fold && size == 2) {
-        const Fr hi = ld_elem(view.in[t], 1);
+        const Fr hi = ld_elem_cv(view.in[t], 1);
         lo = fp_add<FrParams>(lo, fp_mul<FrParams>(r, fp_sub<FrParams>(hi, lo)));
       }
       fin[t] = lo;
     }
-    head->evaluation = sc_eval_program(s_ops, n_ops, consts, fin);
+    Fr ev = sc_eval_program(s_ops, n_ops, consts, fin);
+    if (zc_n > 0) {  // zerocheck.rs:34-40: the claim of h = the claim of h * eq divided by eq_eval(z, point) (eq_eval.rs:33-43)
+      const Fr one = fp_one<FrParams>();
+      Fr e = one;
+      for (int i = 0; i < zc_n; i++) {
+        const Fr x = zc_z[i], ri = out_point[i];
+        e = fp_mul<FrParams>(e, fp_add<FrParams>(fp_mul<FrParams>(x, ri), fp_mul<FrParams>(fp_sub<FrParams>(one, x), fp_sub<FrParams>(one, ri))));
+      }
+      ev = fp_mul<FrParams>(ev, fp_inv_serial<FrParams>(e));
+    }
+    head->evaluation = ev;
   }
+}
+
+// test hook (qz_test_fold): out[i] = a0[i] + r (a1[i] - a0[i]) through the challenge table and fp_mul_fixed
+__global__ void k_fold_table(Fr r, uint32_t* foldc) {
+  if (threadIdx.x < 8) fold_table_row(r, threadIdx.x, foldc);
+}
+__global__ void k_fold_fixed(const uint4* a0, const uint4* a1, uint4* out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) st_elem(out, i, fold_fixed(ld_elem(a0, i), ld_elem(a1, i)));
 }
 
 // ---- small helper kernels ---------------------------------------------------------------------------------------------------------
@@ -559,10 +620,13 @@ __global__ void __launch_bounds__(SC_THREADS) sc_tail(ScTables tabs, ScTailBufs 
 // claimed_sum are absorbed (sumcheck.rs:35-36).  zinv (optional): 1 / z_j for the SKIP1 rounds of the eq-factored
 // zero-check, by one batched inversion (Montgomery's trick: 3 products per element + one binary-Euclid inverse).
 __global__ void __launch_bounds__(32) sc_begin(ScHead* head, const uint8_t* state_in, uint64_t num_vars, Fr claimed_sum,
-                                               int zc_n, Fr* z, Fr* zinv) {
+                                               int zc_n, Fr* z, Fr* zinv, ScMidSync* sync, PeerMailbox* mbox) {
   __shared__ __align__(16) uint32_t buf[32];
   const int t = threadIdx.x;
   if (t == 0) {
+    sync->arrive = 0;
+    sync->flag = 0;
+    if (mbox) mbox->timed_out = 0;  // a wait that timed out in an earlier proof must not void this one
     for (int i = 0; i < 32; i++) head->tstate[i] = state_in[i];
     head->r = fp_zero<FrParams>();
     head->evaluation = fp_zero<FrParams>();
@@ -832,27 +896,6 @@ int get_vinv(qz_ctx* ctx, int d, Fr** out) {
   return QZ_OK;
 }
 
-// launch of a staged round (sc_round_staged): opt in to the dynamic shared memory once per instantiation, size the grid by
-// the occupancy the ring allows.  Returns the grid (= number of partial vectors) through *grid_out.
-template <int K, bool FOLD, bool ZC, bool SKIP1>
-int launch_staged(qz_ctx* ctx, const ScTables& tb, const uint4* e_in, uint4* e_out, uint64_t n_pairs, const ScHead* head,
-                  Fr* parts, int max_bps, int* grid_out) {
-  static int bps_cached[16] = {0};  // per device
-  constexpr size_t smem = staged_smem<K, FOLD>();
-  auto kern = sc_round_staged<K, FOLD, ZC, SKIP1>;
-  int& bps = bps_cached[ctx->device & 15];
-  if (bps == 0) {
-    QZ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    QZ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, SC_WIDE_THREADS, smem));
-    if (bps < 1) bps = 1;
-  }
-  const uint64_t want = (n_pairs + SC_WIDE_THREADS - 1) / SC_WIDE_THREADS;
-  const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)ctx->sm_count * std::min(bps, max_bps)));
-  QZ_LAUNCH(ctx, kern, grid, SC_WIDE_THREADS, smem, tb, e_in, e_out, n_pairs, head, parts);
-  *grid_out = grid;
-  return QZ_OK;
-}
-
 int round_grid(qz_ctx* ctx, uint64_t n_pairs, int blocks_per_sm, int threads = SC_THREADS) {
   uint64_t want = (n_pairs + threads - 1) / threads;
   uint64_t cap = (uint64_t)ctx->sm_count * blocks_per_sm;
@@ -864,6 +907,8 @@ int round_grid(qz_ctx* ctx, uint64_t n_pairs, int blocks_per_sm, int threads = S
 namespace qz {
 
 static thread_local bool tl_zc_no_skip = false;  // set while a zero-check is redone without the SKIP1 rounds
+// c_fold is one table per device: proofs of different contexts on the same device take turns
+static std::recursive_mutex g_fold_table_lock[16];
 
 // elements [base, base + n_elems) of eq(., z) over n variables
 int eq_table_device(qz_ctx* ctx, int n, const Fr* z_dev, uint4* out_dev, uint64_t base, uint64_t n_elems) {
@@ -984,6 +1029,7 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
   if (!zerocheck && !claimed_sum) return ctx->fail(QZ_ERR_INVALID_ARG, "claimed_sum is null");
   if (zerocheck && num_vars && !out_z) return ctx->fail(QZ_ERR_INVALID_ARG, "out_z is null");
   QZ_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::lock_guard<std::recursive_mutex> fold_table_guard(g_fold_table_lock[ctx->device & 15]);
   ctx->arena_reset();
 
   // h, or h_hat = Mul(h, Input(eq)) with eq appended as the last store polynomial (zerocheck.rs:27-29)
@@ -1035,21 +1081,26 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
   QZ_CUDA(ctx, cudaMemcpyAsync(d_in, pin, in_bytes, cudaMemcpyHostToDevice, st));
   bool zc_skip1 = false;
   Fr* d_zinv = nullptr;
+  ScMidSync* d_sync = nullptr;
+  uint32_t* d_foldc = nullptr;  // multiples of the last challenge (sc_round_close), copied into c_fold before a large fold pass
   {
     Fr cs;
     memset(&cs, 0, sizeof cs);
     if (!zerocheck) memcpy(cs.v, claimed_sum, 32);
     // the eq-factored zero-check skips X = 1 from round 1 on when the proof is large enough to repay the batched
     // inversion of the z (~30 us on one thread); decided here because sc_begin computes the inverses
-    const bool zc_maybe_fast = zerocheck && cp.product_k >= 2 && cp.product_k <= 4 &&
-                               ((uint64_t)1 << num_vars) > ((uint64_t)1 << SC_TAIL_LOG) && !getenv("QZ_ZC_STREAM_EQ");
+    const bool zc_maybe_fast = zerocheck && cp.product_k >= 2 && cp.product_k <= 4 && !getenv("QZ_ZC_STREAM_EQ");
     zc_skip1 = zc_maybe_fast && num_vars >= 21 && !tl_zc_no_skip && !getenv("QZ_ZC_NO_SKIP1");
     if (zc_skip1) {
       d_zinv = (Fr*)ctx->arena_alloc(32 * num_vars);
       if (!d_zinv) return ctx->fail(QZ_ERR_ALLOC, "zero-check inverses");
     }
+    d_sync = (ScMidSync*)ctx->arena_alloc(sizeof(ScMidSync));
+    d_foldc = (uint32_t*)ctx->arena_alloc(64 * sizeof(uint32_t));
+    if (!d_sync || !d_foldc) return ctx->fail(QZ_ERR_ALLOC, "round counters");
     QZ_LAUNCH(ctx, sc_begin, 1, 32, 0, head, (const uint8_t*)(d_in + in_state), (uint64_t)num_vars, cs,
-              zerocheck ? (int)num_vars : 0, d_z, d_zinv);  // zerocheck.rs:20-22, sumcheck.rs:35-36
+              zerocheck ? (int)num_vars : 0, d_z, d_zinv, d_sync,
+              (PeerMailbox*)(sharded && comm_has_peers(ctx) ? ctx->mbox : nullptr));  // zerocheck.rs:20-22, sumcheck.rs:35-36
   }
 
   // Host tables of a large proof are copied in UP_CHUNKS slices on the second stream and round 0 (evaluate only: every
@@ -1087,8 +1138,14 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
     }
   }
   // zero-check fast path (see sc_round_zc): h is a product of up to three tables and at least one streaming round runs
-  const bool zc_fast = zerocheck && eq_slot >= 0 && cp.product_k >= 2 && cp.product_k <= 4 &&
-                       N * G > ((uint64_t)1 << SC_TAIL_LOG) && !getenv("QZ_ZC_STREAM_EQ");
+  // streaming rounds run while a rank's table has more than 2^SC_MID_LOG entries (with peer mailboxes or one GPU; the
+  // NCCL fallback streams down to the gather size), then sc_mid takes every remaining round
+  const bool mid_sharded = G == 1 || comm_has_peers(ctx);
+  auto streaming = [&](uint64_t sz) {
+    return mid_sharded ? sz > ((uint64_t)1 << SC_MID_LOG) : sz * G > ((uint64_t)1 << SC_TAIL_LOG);
+  };
+  const bool zc_fast = zerocheck && eq_slot >= 0 && cp.product_k >= 2 && cp.product_k <= 4 && streaming(N) &&
+                       !getenv("QZ_ZC_STREAM_EQ");
   if (zerocheck && eq_slot >= 0 && !zc_fast) {
     void* p = ctx->arena_alloc(32 * N);
     if (!p) return ctx->fail(QZ_ERR_ALLOC, "eq table");
@@ -1119,7 +1176,7 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
     } else if (cp.product_k == 4) {
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sc_round_prod<4, false, true>, SC_THREADS, 0);
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_wide, sc_round_prod<4, true, true>, SC_WIDE_THREADS, 0);
-    } else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sc_round_generic, SC_THREADS, 0);
+    } else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sc_round_generic<true>, SC_THREADS, 0);
     if (bps < 1) bps = 1;
     if (getenv("QZ_SC_NARROW")) bps_wide = 0;  // measurement switch: force the fully reduced sums
     Fr* partials = (Fr*)ctx->arena_alloc(sizeof(Fr) * (size_t)ctx->sm_count * std::max(bps, bps_wide) * (d + 1) * up_chunks);
@@ -1164,7 +1221,7 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
           gt.in[i] = tabs.in[j];
           g_of[i++] = j;
         }
-      while (size * G > ((uint64_t)1 << SC_TAIL_LOG)) {
+      while (streaming(size)) {
         const uint64_t n_pairs = pending ? size / 4 : size / 2;
         const bool pdl = pdl_ok && n_pairs <= ((uint64_t)1 << 18);
         for (int i = 0; i < K; i++) gt.out[i] = flip ? bufB[g_of[i]] : bufA[g_of[i]];
@@ -1172,8 +1229,10 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
         int grid = wide ? round_grid(ctx, n_pairs, zb_wide, SC_WIDE_THREADS) : round_grid(ctx, n_pairs, zb);
         const uint4* e_in = e_buf[e_cur];
         uint4* e_out = e_buf[e_cur ^ 1];
-        const bool zc_staged = wide && K == 3 && !getenv("QZ_SC_NO_STAGE");
+
         const int derive1 = pending && zc_skip1 ? 1 : 0;
+        if (pending && wide && K == 3)  // the deferred-reduction pass folds through c_fold
+          QZ_CUDA(ctx, cudaMemcpyToSymbolAsync(c_fold, d_foldc, 64 * sizeof(uint32_t), 0, cudaMemcpyDeviceToDevice, st));
 #define QZ_ROUND_ZC(KK, W, T)                                                                                      \
   do {                                                                                                             \
     if (derive1) QZ_LAUNCH_PDL(ctx, pdl, (sc_round_zc<KK, W, true, true>), grid, T, gt, e_in, e_out, n_pairs, (const ScHead*)head, partials); \
@@ -1184,14 +1243,7 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
           case 1: QZ_ROUND_ZC(1, false, SC_THREADS); break;
           case 2: QZ_ROUND_ZC(2, false, SC_THREADS); break;
           default:
-            if (zc_staged) {
-              const int mb = std::max(bps, bps_wide);
-              const ScHead* hd = head;
-              rc = derive1   ? launch_staged<3, true, true, true>(ctx, gt, e_in, e_out, n_pairs, hd, partials, mb, &grid)
-                   : pending ? launch_staged<3, true, true, false>(ctx, gt, e_in, e_out, n_pairs, hd, partials, mb, &grid)
-                             : launch_staged<3, false, true, false>(ctx, gt, e_in, e_out, n_pairs, hd, partials, mb, &grid);
-              if (rc) return rc;
-            } else if (wide) QZ_ROUND_ZC(3, true, SC_WIDE_THREADS);
+            if (wide) QZ_ROUND_ZC(3, true, SC_WIDE_THREADS);
             else QZ_ROUND_ZC(3, false, SC_THREADS);
         }
 #undef QZ_ROUND_ZC
@@ -1200,18 +1252,18 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
         if (G == 1) {
           QZ_LAUNCH_PDL(ctx, pdl, sc_finalize, 1, SC_THREADS, (const Fr*)partials, grid, K, head, (const Fr*)vinv_k,
                         d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc, (const Fr*)(d_z + round), derive1,
-                        zinv_j);
+                        zinv_j, d_foldc);
         } else if (comm_has_peers(ctx)) {
           QZ_LAUNCH_PDL(ctx, pdl, sc_finalize_peers, 1, SC_THREADS, (const Fr*)partials, grid, K,
                         (PeerMailbox* const*)ctx->peer_mbox_dev, ctx->rank, G, ++ctx->mbox_seq, head, (const Fr*)vinv_k,
                         d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc, (const Fr*)(d_z + round), derive1,
-                        zinv_j);
+                        zinv_j, d_foldc);
         } else {
           QZ_LAUNCH(ctx, sc_reduce_partials, 1, SC_THREADS, 0, partials, grid, ns - 1, rank_evals);
           rc = comm_allgather(ctx, rank_evals, all_evals, sizeof(Fr) * ns);
           if (rc) return rc;
           QZ_LAUNCH(ctx, sc_finalize, 1, SC_THREADS, 0, all_evals, G, K, head, vinv_k, d_coeffs + (size_t)round * mc,
-                    d_lens + round, d_point + round, mc, (const Fr*)(d_z + round), derive1, zinv_j);
+                    d_lens + round, d_point + round, mc, (const Fr*)(d_z + round), derive1, zinv_j, d_foldc);
         }
         if (pending) {
           for (int i = 0; i < K; i++) gt.in[i] = gt.out[i];
@@ -1226,21 +1278,24 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
       // hand over to sc_tail: h's tables where they stand, eq materialised in the reference's form (pending fold)
       uint4* eq_full = (uint4*)ctx->arena_alloc(32 * size);
       if (!eq_full) return ctx->fail(QZ_ERR_ALLOC, "eq hand-over");
-      QZ_LAUNCH(ctx, zc_materialize_eq, (unsigned)((size / 2 + 255) / 256), 256, 0, zc_weights, size / 2, (const ScHead*)head,
+      QZ_LAUNCH(ctx, zc_materialize_eq, (unsigned)((size / 2 + 255) / 256), 256, 0, zc_weights, size / 2, head,
                 (const Fr*)(d_z + (round - 1)), eq_full);
       for (int i = 0; i < K; i++) tabs.in[g_of[i]] = gt.in[i];
       tabs.in[eq_slot] = eq_full;
     }
     // one round kernel over `n_pairs` pairs of `tb` (fold of the pending challenge fused when `pend`)
-    const bool staged_ok = !getenv("QZ_SC_NO_STAGE");  // A/B switch: large passes without the shared-memory ring
-    const int parts_bps = std::max(bps, bps_wide);    // `partials` holds this many vectors per SM
+    // a pass folds through the challenge table in constant memory when it is a deferred-reduction (large) product pass
+    // or a large interpreted pass
+    const uint64_t generic_cf_pairs = (uint64_t)1 << 16;
+    auto refresh_fold_table = [&]() -> int {
+      QZ_CUDA(ctx, cudaMemcpyToSymbolAsync(c_fold, d_foldc, 64 * sizeof(uint32_t), 0, cudaMemcpyDeviceToDevice, st));
+      return QZ_OK;
+    };
     auto launch_round = [&](const ScTables& tb, uint64_t n_pairs, int pend, int& grid, bool wide, bool pdl, Fr* parts) -> int {
-      if (wide && staged_ok && (cp.product_k == 3 || cp.product_k == 4)) {
-        const ScHead* hd = head;
-        if (cp.product_k == 3) return pend ? launch_staged<3, true, false, true>(ctx, tb, nullptr, nullptr, n_pairs, hd, parts, parts_bps, &grid)
-                                           : launch_staged<3, false, false, false>(ctx, tb, nullptr, nullptr, n_pairs, hd, parts, parts_bps, &grid);
-        return pend ? launch_staged<4, true, false, true>(ctx, tb, nullptr, nullptr, n_pairs, hd, parts, parts_bps, &grid)
-                    : launch_staged<4, false, false, false>(ctx, tb, nullptr, nullptr, n_pairs, hd, parts, parts_bps, &grid);
+      const bool generic_cf = cp.product_k == 0 && pend && n_pairs >= generic_cf_pairs;
+      if (pend && (wide || generic_cf)) {
+        int rcf = refresh_fold_table();
+        if (rcf) return rcf;
       }
 #define QZ_ROUND_PROD(K, W, T)                                                                                  \
   do {                                                                                                          \
@@ -1259,8 +1314,12 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
           else QZ_ROUND_PROD(4, false, SC_THREADS);
           break;
         default:
-          QZ_LAUNCH_PDL(ctx, pdl, sc_round_generic, grid, SC_THREADS, tb, n_pairs, pend, (const ScHead*)head,
-                        (const ScProgram*)d_prog, (const Fr*)d_consts, parts);
+          if (generic_cf)
+            QZ_LAUNCH_PDL(ctx, pdl, sc_round_generic<true>, grid, SC_THREADS, tb, n_pairs, pend, (const ScHead*)head,
+                          (const ScProgram*)d_prog, (const Fr*)d_consts, parts);
+          else
+            QZ_LAUNCH_PDL(ctx, pdl, sc_round_generic<false>, grid, SC_THREADS, tb, n_pairs, pend, (const ScHead*)head,
+                          (const ScProgram*)d_prog, (const Fr*)d_consts, parts);
       }
       return QZ_OK;
     };
@@ -1283,11 +1342,11 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
         if (rc) return rc;
       }
       QZ_LAUNCH(ctx, sc_finalize, 1, SC_THREADS, 0, (const Fr*)partials, grid_c * up_chunks, d, head, (const Fr*)vinv, d_coeffs,
-                d_lens, d_point, mc, (const Fr*)nullptr, 0, (const Fr*)nullptr);
+                d_lens, d_point, mc, (const Fr*)nullptr, 0, (const Fr*)nullptr, d_foldc);
       pending = 1;
       round = 1;
     }
-    while (!zc_fast && size * G > ((uint64_t)1 << SC_TAIL_LOG)) {
+    while (!zc_fast && streaming(size)) {
       const uint64_t n_pairs = pending ? size / 4 : size / 2;
       const bool pdl = pdl_ok && n_pairs <= ((uint64_t)1 << 18);
       for (int j = 0; j < ka; j++) tabs.out[j] = flip ? bufB[j] : bufA[j];
@@ -1301,18 +1360,18 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
       if (G == 1) {
         QZ_LAUNCH_PDL(ctx, pdl, sc_finalize, 1, SC_THREADS, (const Fr*)partials, grid, d, head, (const Fr*)vinv,
                       d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc, (const Fr*)nullptr, derive1,
-                      (const Fr*)nullptr);
+                      (const Fr*)nullptr, d_foldc);
       } else if (comm_has_peers(ctx)) {  // partial sums go straight into the peers' mailboxes (comm.cuh)
         QZ_LAUNCH_PDL(ctx, pdl, sc_finalize_peers, 1, SC_THREADS, (const Fr*)partials, grid, d,
                       (PeerMailbox* const*)ctx->peer_mbox_dev, ctx->rank, G, ++ctx->mbox_seq, head, (const Fr*)vinv,
                       d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc, (const Fr*)nullptr, derive1,
-                      (const Fr*)nullptr);
+                      (const Fr*)nullptr, d_foldc);
       } else {  // every rank sums all ranks' partial evaluations and runs the same transcript
         QZ_LAUNCH(ctx, sc_reduce_partials, 1, SC_THREADS, 0, partials, grid, ns - 1, rank_evals);
         rc = comm_allgather(ctx, rank_evals, all_evals, sizeof(Fr) * ns);
         if (rc) return rc;
         QZ_LAUNCH(ctx, sc_finalize, 1, SC_THREADS, 0, all_evals, G, d, head, vinv, d_coeffs + (size_t)round * mc,
-                  d_lens + round, d_point + round, mc, (const Fr*)nullptr, derive1, (const Fr*)nullptr);
+                  d_lens + round, d_point + round, mc, (const Fr*)nullptr, derive1, (const Fr*)nullptr, d_foldc);
       }
       if (pending) {
         for (int j = 0; j < ka; j++) tabs.in[j] = tabs.out[j];
@@ -1325,8 +1384,9 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
     QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k1, st));
     ScTailBufs tb;
     memset(&tb, 0, sizeof tb);
-    if (G > 1) {
-      // gather the ranks' shards (rank order = index order): every rank finishes the remaining rounds redundantly
+    int mid_G = G;
+    if (G > 1 && !mid_sharded) {
+      // NCCL fallback: gather the ranks' shards (rank order = index order); every rank finishes the remaining rounds alone
       for (int j = 0; j < ka; j++) {
         uint4* full = (uint4*)ctx->arena_alloc(32 * size * G);
         if (!full) return ctx->fail(QZ_ERR_ALLOC, "gathered tables");
@@ -1335,28 +1395,86 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
         tabs.in[j] = full;
       }
       size *= G;
+      mid_G = 1;
     }
-    // the tail's scratch must not alias its input: input is bufA/bufB[flip^1], the gathered copy, or the caller's tables
+    // sc_mid's fold scratch (never aliases its input): the first fold writes size / 2 elements, the second size / 4, ...;
+    // after a gather the tables have 2^SC_TAIL_LOG elements again
+    const uint64_t tail_half = ((uint64_t)1 << SC_TAIL_LOG) / 2;
     for (int j = 0; j < ka; j++) {
-      tb.a[j] = G > 1 ? (uint4*)ctx->arena_alloc(32 * (((uint64_t)1 << SC_TAIL_LOG) / 2)) : (flip ? bufB[j] : bufA[j]);
-      tb.b[j] = (uint4*)ctx->arena_alloc(32 * (((uint64_t)1 << SC_TAIL_LOG) / 2));
-      if (!tb.a[j] || !tb.b[j]) return ctx->fail(QZ_ERR_ALLOC, "tail scratch");
+      tb.a[j] = (uint4*)ctx->arena_alloc(32 * std::max<uint64_t>(size / 2, tail_half));
+      tb.b[j] = (uint4*)ctx->arena_alloc(32 * std::max<uint64_t>(size / 4, tail_half));
+      if (!tb.a[j] || !tb.b[j]) return ctx->fail(QZ_ERR_ALLOC, "fold scratch of the short rounds");
     }
-    switch (cp.product_k) {
-      case 1: QZ_LAUNCH_PDL(ctx, pdl_ok && G == 1, sc_tail<1>, 1, SC_THREADS, tabs, tb, size, pending, head, d_prog, d_consts, vinv, d_coeffs, d_lens, d_point, round, mc); break;
-      case 2: QZ_LAUNCH_PDL(ctx, pdl_ok && G == 1, sc_tail<2>, 1, SC_THREADS, tabs, tb, size, pending, head, d_prog, d_consts, vinv, d_coeffs, d_lens, d_point, round, mc); break;
-      case 3: QZ_LAUNCH_PDL(ctx, pdl_ok && G == 1, sc_tail<3>, 1, SC_THREADS, tabs, tb, size, pending, head, d_prog, d_consts, vinv, d_coeffs, d_lens, d_point, round, mc); break;
-      case 4: QZ_LAUNCH_PDL(ctx, pdl_ok && G == 1, sc_tail<4>, 1, SC_THREADS, tabs, tb, size, pending, head, d_prog, d_consts, vinv, d_coeffs, d_lens, d_point, round, mc); break;
-      default: QZ_LAUNCH_PDL(ctx, pdl_ok && G == 1, sc_tail<0>, 1, SC_THREADS, tabs, tb, size, pending, head, d_prog, d_consts, vinv, d_coeffs, d_lens, d_point, round, mc);
+    // exchanges sc_mid will make with the peers: one per round before the gather, one for the gather itself
+    uint32_t seq0 = 0;
+    int gather_par = 0;
+    if (mid_G > 1) {
+      uint32_t n_ex = 0;
+      uint64_t sz = size;
+      for (int pend = pending; sz * G > ((uint64_t)1 << SC_TAIL_LOG); pend = 1) {
+        n_ex++;
+        if (pend) sz >>= 1;
+      }
+      n_ex++;
+      seq0 = ctx->mbox_seq + 1;
+      ctx->mbox_seq += n_ex;
+      gather_par = (int)(ctx->gather_seq++ & 1);
+    }
+    {
+      const uint64_t n_pairs0 = pending ? size / 4 : size / 2;
+      uint64_t want = std::max<uint64_t>(1, (n_pairs0 + SC_THREADS - 1) / SC_THREADS);
+      if (mid_G > 1 && size * G <= ((uint64_t)1 << SC_TAIL_LOG)) want = 1;
+      const void* kern = nullptr;
+      switch (cp.product_k) {
+        case 1: kern = (const void*)sc_mid<1>; break;
+        case 2: kern = (const void*)sc_mid<2>; break;
+        case 3: kern = (const void*)sc_mid<3>; break;
+        case 4: kern = (const void*)sc_mid<4>; break;
+        default: kern = (const void*)sc_mid<0>;
+      }
+      int occ = 1;
+      if (want > 1) {
+        QZ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SC_THREADS, 0));
+        if (occ < 1) occ = 1;
+      }
+      // (the closing block sums one parked vector per thread: never more blocks than a block has threads)
+      const int grid = (int)std::min<uint64_t>(std::min<uint64_t>(want, SC_THREADS), (uint64_t)ctx->sm_count * occ);
+      ScTables k_tabs = tabs;
+      uint64_t k_size = size;
+      int k_pending = pending, k_round = round, k_mc = mc, k_rank = ctx->rank, k_G = mid_G, k_zc_n = zerocheck ? (int)num_vars : 0;
+      ScHead* k_head = head;
+      const ScProgram* k_prog = d_prog;
+      const Fr *k_consts = d_consts, *k_vinv = vinv, *k_z = d_z;
+      Fr *k_coeffs = d_coeffs, *k_point = d_point, *k_parts = partials;
+      uint32_t* k_lens = d_lens;
+      PeerMailbox* const* k_peers = (PeerMailbox* const*)ctx->peer_mbox_dev;
+      void* args[] = {&k_tabs, &tb, &k_size, &k_pending, &k_head, &k_prog, &k_consts, &k_vinv, &k_coeffs, &k_lens, &k_point,
+                      &k_round, &k_mc, &k_parts, &d_sync, &k_peers, &k_rank, &k_G, &seq0, &gather_par, &k_z, &k_zc_n};
+      if (grid > 1) {  // the blocks wait for one another: they must all be resident
+        QZ_CUDA(ctx, cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(SC_THREADS), args, 0, st));
+        ctx->launches++;
+      } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(1);
+        cfg.blockDim = dim3(SC_THREADS);
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = (pdl_ok && G == 1) ? 1 : 0;
+        QZ_CUDA(ctx, cudaLaunchKernelExC(&cfg, kern, args));
+        ctx->launches++;
+      }
     }
   }
-  if (zerocheck && num_vars > 0) QZ_LAUNCH(ctx, zc_finish, 1, 1, 0, head, d_z, d_point, (int)num_vars);
 
   // results -> pinned staging -> caller
   QZ_CUDA(ctx, cudaMemcpyAsync(pin_out, d_out, zerocheck ? out_bytes : o_z, cudaMemcpyDeviceToHost, st));
   QZ_CUDA(ctx, cudaEventRecord(ctx->ev_call1, st));
   QZ_CUDA(ctx, cudaStreamSynchronize(st));
   const ScHead* h = (const ScHead*)(pin_out + o_head);
+  if (h->peer_fault == 2) return ctx->fail(QZ_ERR_CUDA, "a block of the persistent round kernel never saw its round closed");
   if (h->peer_fault) return ctx->fail(QZ_ERR_NCCL, "a peer did not deliver its partial sums (peer mailbox wait timed out)");
   if (zc_skip1 && h->zc_degenerate) {  // some z_j = 0 (probability 2^-254 per challenge): redo without the 1 / z_j shortcut
     tl_zc_no_skip = true;              // every rank draws the same z, so every rank takes this branch
@@ -1380,3 +1498,25 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
 }
 
 }  // namespace qz
+
+extern "C" int qz_test_fold(qz_ctx* ctx, const uint8_t r[32], const uint8_t* a0, const uint8_t* a1, uint8_t* out, size_t n) {
+  if (!ctx || !r || !a0 || !a1 || !out) return QZ_ERR_INVALID_ARG;
+  if (n == 0) return QZ_OK;
+  QZ_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::lock_guard<std::recursive_mutex> guard(qz::g_fold_table_lock[ctx->device & 15]);
+  ctx->arena_reset();
+  cudaStream_t st = ctx->stream;
+  uint4 *d0 = (uint4*)ctx->arena_alloc(32 * n), *d1 = (uint4*)ctx->arena_alloc(32 * n), *dd = (uint4*)ctx->arena_alloc(32 * n);
+  uint32_t* tab = (uint32_t*)ctx->arena_alloc(256);
+  if (!d0 || !d1 || !dd || !tab) return ctx->fail(QZ_ERR_ALLOC, "scratch");
+  Fr rr;
+  memcpy(rr.v, r, 32);
+  QZ_CUDA(ctx, cudaMemcpyAsync(d0, a0, 32 * n, cudaMemcpyHostToDevice, st));
+  QZ_CUDA(ctx, cudaMemcpyAsync(d1, a1, 32 * n, cudaMemcpyHostToDevice, st));
+  QZ_LAUNCH(ctx, k_fold_table, 1, 32, 0, rr, tab);
+  QZ_CUDA(ctx, cudaMemcpyToSymbolAsync(qz::c_fold, tab, 256, 0, cudaMemcpyDeviceToDevice, st));
+  QZ_LAUNCH(ctx, k_fold_fixed, (unsigned)((n + 127) / 128), 128, 0, (const uint4*)d0, (const uint4*)d1, dd, n);
+  QZ_CUDA(ctx, cudaMemcpyAsync(out, dd, 32 * n, cudaMemcpyDeviceToHost, st));
+  QZ_CUDA(ctx, cudaStreamSynchronize(st));
+  return QZ_OK;
+}

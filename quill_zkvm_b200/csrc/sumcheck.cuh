@@ -13,6 +13,7 @@ constexpr int SC_MAX_K = 16;      // tables referenced by one expression
 constexpr int SC_MAX_OPS = 512;   // postfix program length
 constexpr int SC_MAX_STACK = 16;  // interpreter stack depth
 constexpr int SC_MAX_VARS = 40;
+constexpr int SC_TAIL_LOG = 11;  // from 2^11 elements on one block runs a round alone (sumcheck.cu sc_mid)
 
 enum : uint32_t { SC_OP_IN = 0, SC_OP_CONST = 1, SC_OP_ADD = 2, SC_OP_MUL = 3 };
 
@@ -384,6 +385,27 @@ constexpr int SC_PROD_SLOTS = 256;
 // degree d, and the round polynomial is s_j(X) = P_j * eq(X, z_j) * t_j(X), of degree d + 1, with z_j = *zc_z and
 // P_j = head->zc_prefix: the d + 1 coefficients are multiplied by the linear factor a + b X, a = P_j (1 - z_j),
 // b = P_j (2 z_j - 1), before they are trimmed and absorbed, and P_{j+1} = P_j eq(r_j, z_j) once r_j is drawn.
+// Row t of the table of shifted multiples of a challenge for the next pass's folds (ff.cuh fp_mul_fixed):
+// C_t = r * 2^e_t mod p, e_t = fold_consts_exponent(t), canonical.  With rM = r R: fp_mul(rM, x) = r x for a raw x.
+QZ_DEV void fold_table_row(const Fr& rM, int t, uint32_t* foldc) {
+  const int e = fold_consts_exponent(t);
+  Fr x = fp_zero<FrParams>(), c;
+  if (e < 256) {
+    x.v[e >> 5] = 1u << (e & 31);
+    c = fp_mul<FrParams>(rM, x);
+  } else if (e == 256) {
+    c = rM;  // r * 2^256 mod p is the Montgomery form itself
+  } else {   // e == 288: (r * 2^32) * 2^256
+    Fr r2;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r2.v[i] = FrParams::R2(i);
+    x.v[1] = 1u;
+    c = fp_mul<FrParams>(fp_mul<FrParams>(rM, x), r2);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) foldc[8 * t + i] = c.v[i];
+}
+
 // Restore the value at X = 1 that a SKIP1 round did not sum.  s_evals holds d sums compactly (X = 0, 2, .., d) and is
 // expanded in place to X = 0..d.  Plain rounds: s_j(1) = s_{j-1}(r_{j-1}) - s_j(0).  Eq-factored zero-check rounds:
 // t_{j-1}(r_{j-1}) = sum_x E_j(x) prod_t g_t = (1 - z_j) t_j(0) + z_j t_j(1), so t_j(1) = (claim - (1 - z_j) t_j(0)) / z_j.
@@ -409,7 +431,7 @@ QZ_DEV void sc_expand_evals(const ScHead* head, int d, Fr* s_evals, const Fr* zc
 // want_claim: leave s_j(r_j) (t_j(r_j) on the eq-factored path) in head->claim for a following SKIP1 round
 QZ_DEV void sc_round_close(ScHead* head, const Fr* vinv, int d, const Fr* s_evals, Fr* s_coef, uint32_t* s_msg, Fr* s_prod,
                            Fr* out_coeffs_row, uint32_t* out_len, Fr* out_point_slot, int max_coeffs,
-                           const Fr* zc_z = nullptr, bool want_claim = false) {
+                           const Fr* zc_z = nullptr, bool want_claim = false, uint32_t* foldc = nullptr) {
   const int t = threadIdx.x;
   const int n1 = d + 1;
   const int n_out = zc_z ? d + 2 : d + 1;  // coefficients of the round polynomial before trimming
@@ -465,7 +487,12 @@ QZ_DEV void sc_round_close(ScHead* head, const Fr* vinv, int d, const Fr* s_eval
     __syncwarp(B3_QUAD);
     const uint32_t len = s_msg[8];
     uint32_t* state = reinterpret_cast<uint32_t*>(head->tstate);
-    tr_absorb_quad(state, s_msg, 8 + 32 * len);  // :73
+    if (32 + 8 + 32 * len <= 1024) {
+      tr_absorb_quad(state, s_msg, 8 + 32 * len);  // :73
+    } else {  // 31 coefficients or more: state ‖ message spans two blake3 chunks, which the quad routine does not hash
+      if (t == 0) tr_absorb_words(state, s_msg, 8 + 32 * len);
+      __syncwarp(B3_QUAD);
+    }
     const Fr r = tr_draw_fr_quad(state, s_msg);   // :77
     if (t == 0) {
       head->r = r;
@@ -485,6 +512,7 @@ QZ_DEV void sc_round_close(ScHead* head, const Fr* vinv, int d, const Fr* s_eval
     }
   }
   __syncthreads();
+  if (foldc && t < 8) fold_table_row(head->r, t, foldc);
 }
 
 }  // namespace qz

@@ -331,3 +331,37 @@ def test_ntt_passes_with_per_pass_correction(log_m, groups):
         s0 -= T
         got = ntt_pass_model(got, log_m, s0, T, True)
     assert got == [x * (1 << log_m) % NTT_P for x in a]
+
+
+def test_fixed_multiplier_bounds_and_value():
+    """ff.cuh fp_mul_fixed: r * d = sum_i d_i * C_i with C_i = r * 2^(32 i + 32 q_i) mod p, rows 0..3, one Montgomery
+    reduction row, rows 4..7, two more reduction rows.  The running value must stay below 2^288 (nine 32-bit columns)
+    and end below 2p, for ANY 256-bit d (the kernels pass a1 - a0 + p unreduced) -- checked on the extremes."""
+    import random
+    p = FR
+    inv = (-pow(p, -1, 1 << 32)) % (1 << 32)
+    exps = [32 * i + (96 if i < 4 else 64) for i in range(8)]
+
+    def mont_row(v):
+        m = (v & 0xFFFFFFFF) * inv & 0xFFFFFFFF
+        v += m * p
+        assert v < 1 << 288 and v & 0xFFFFFFFF == 0
+        return v >> 32
+
+    def model(d, r):
+        C = [r * pow(2, e, p) % p for e in exps]
+        w = [(d >> (32 * i)) & 0xFFFFFFFF for i in range(8)]
+        v = sum(w[i] * C[i] for i in range(4))
+        v = mont_row(v)
+        v += sum(w[i] * C[i] for i in range(4, 8))
+        assert v < 1 << 288
+        v = mont_row(mont_row(v))
+        assert v < 2 * p
+        return v - p if v >= p else v
+
+    rnd = random.Random(5)
+    ds = [0, 1, p - 1, 2 * p - 1, (1 << 256) - 1, (1 << 256) - (1 << 32), 0xFFFFFFFF] + [rnd.randrange(1 << 256) for _ in range(200)]
+    rs = [0, 1, p - 1, p - 2, (1 << 253) % p] + [rnd.randrange(p) for _ in range(20)]
+    for r in rs:
+        for d in ds:
+            assert model(d, r) == r * d % p

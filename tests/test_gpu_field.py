@@ -64,6 +64,17 @@ def test_field_inverse(ctx, field, mod):
     assert got == [pow(x, mod - 2, mod) for x in a]
 
 
+def test_fixed_challenge_fold(ctx):
+    """a0 + r (a1 - a0) through the table of shifted multiples of r in constant memory (ff.cuh fp_mul_fixed, the fold of the
+    large sumcheck passes: sumcheck.rs:81-92) against plain modular arithmetic, edge values included"""
+    rnd = random.Random(77)
+    for r in (0, 1, FR - 1, (1 << 253) % FR, rnd.randrange(FR), rnd.randrange(FR)):
+        a0 = _edge_and_random(FR, 2048, 5)
+        a1 = list(reversed(_edge_and_random(FR, 2048, 9)))
+        got = co.from_mont(ctx.fold(co.fr1(r), co.to_mont(a0), co.to_mont(a1)))
+        assert got == [(x + r * (y - x)) % FR for x, y in zip(a0, a1)], hex(r)
+
+
 def test_random_fr_generator_is_reduced(ctx):
     buf = ctx.random_fr(1000, 42)
     v = buf.download().reshape(-1, 32)

@@ -142,6 +142,46 @@ def test_generic_expressions(ctx, n):
             assert all(p.shape[0] == 0 for p in sc.r_polys)
 
 
+def _power(e, m):
+    """e^m as a balanced tree of products"""
+    if m == 1:
+        return e
+    return py.e_mul(_power(e, m // 2), _power(e, m - m // 2))
+
+
+@pytest.mark.parametrize("deg", [29, 30, 31, 32])
+@pytest.mark.parametrize("n", [3, 13])
+def test_high_degree_round_polynomials(ctx, deg, n):
+    """round polynomials of 30..33 coefficients: from 31 on `state ‖ len ‖ coeffs` no longer fits one blake3 chunk
+    (32 + 8 + 32 * 31 > 1024), which the device transcript must hash as a two-chunk tree like the reference's blake3"""
+    tabs = [util.rand_fr(1 << n, 31 * n + t) for t in range(2)]
+    e = py.e_add(_power(py.e_in(0), deg), py.e_mul(py.e_in(1), py.e_const(3)))
+    nodes, consts = util.expr_from_py(e)
+    sc, claim, o = assert_same(ctx, n, tabs, nodes, consts, co.fr1(deg), b"deg%d" % deg, threads=NCPU)
+    assert sc.r_polys[0].shape[0] == deg + 1
+    if deg < 32:  # the zero-check multiplies by eq: one more degree
+        assert_same(ctx, n, tabs, nodes, consts, None, b"zdeg%d" % deg, zerocheck=True, threads=NCPU)
+
+
+@pytest.mark.parametrize("n,k", [(17, 3), (18, 3), (19, 3), (20, 3), (19, 1), (19, 2), (20, 4)])
+def test_product_sizes_across_the_persistent_rounds(ctx, n, k):
+    """2^17 .. 2^20: the proof starts inside sc_mid (<= 2^18 entries), or streams one or two rounds and hands over to it"""
+    tabs = [util.rand_fr(1 << n, 300 * n + t) for t in range(k)]
+    nodes, consts = util.expr_product(k)
+    assert_same(ctx, n, tabs, nodes, consts, co.fr1(7), b"mid", threads=NCPU, device_tables=True)
+    if k <= 3:
+        assert_same(ctx, n, tabs, nodes, consts, None, b"midzc", zerocheck=True, threads=NCPU, device_tables=True)
+
+
+@pytest.mark.parametrize("n", [18, 19])
+def test_generic_expression_across_the_persistent_rounds(ctx, n):
+    tabs = [util.rand_fr(1 << n, 17 * n + t) for t in range(4)]
+    e = py.e_add(py.e_sub(py.e_mul(py.e_in(0), py.e_in(1)), py.e_in(3)), py.e_mul(py.e_const(7), py.e_mul(py.e_in(2), py.e_in(2))))
+    nodes, consts = util.expr_from_py(e)
+    assert_same(ctx, n, tabs, nodes, consts, co.fr1(1), b"midgen", threads=NCPU)
+    assert_same(ctx, n, tabs, nodes, consts, None, b"midgenzc", zerocheck=True, threads=NCPU)
+
+
 def test_logup_shaped_expression(ctx):
     """the batched expression of multiset_check.rs:132-157: (d_l (gamma + f) - 1) + alpha (d_r (gamma + g) - 1) ... times eq via zerocheck"""
     n = 13

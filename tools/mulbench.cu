@@ -1,8 +1,8 @@
 // Micro-benchmark of Montgomery multiplier variants (development tool; build: nvcc -O3 -std=c++17 -gencode
-// arch=compute_100a,code=sm_100a -Iquill_zkvm_b200/csrc -o /tmp/mulbench tools/mulbench.cu).
+// arch=compute_100a,code=sm_100a -Itools -o /tmp/mulbench tools/mulbench.cu).
 #include <cstdio>
 #include <cuda_runtime.h>
-#include "ff.cuh"
+#include "ff_variants.cuh"  // fp_mul_inline, fp_sqr_sos (+ the product header ff.cuh)
 using namespace qz;
 
 template <class P, int VAR>

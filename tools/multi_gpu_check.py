@@ -38,7 +38,7 @@ def main():
         kz.srs.free()
     # ---- sumcheck ----
     exprs = [util.expr_product(3), util.expr_from_py(py.e_sub(py.e_mul(py.e_in(0), py.e_in(1)), py.e_mul(py.e_const(9), py.e_in(2))))]
-    for nv in (3, 8, 11, 12, 13, 16, 18, 22):  # 22: the deferred-reduction round kernel runs on every shard
+    for nv in (3, 8, 11, 12, 13, 16, 18, 19, 20, 22):  # 19, 20: sc_mid's multi-block rounds exchange with the peers; 22: streaming rounds first
         if (1 << nv) < world:
             continue
         tabs = [util.rand_fr(1 << nv, 77 * nv + t) for t in range(3)]
