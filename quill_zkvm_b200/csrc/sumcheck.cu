@@ -15,6 +15,29 @@
 #include <cstring>
 #include <mutex>
 #include <vector>
+#ifdef QZ_SC_TRACE
+// measurement build (tools/sc_trace.py): thread 32 of a block stamps (id, block, clock64, globaltimer) at the marked points
+namespace qz {
+__device__ unsigned long long g_trace[3 * 8192];
+__device__ unsigned int g_trace_n;
+static __device__ __forceinline__ void sc_trace(int id) {
+  if (threadIdx.x == 32) {  // a lane of warp 1: a divergent lane 0 in warp 0 slows the four-lane transcript several-fold
+    const unsigned int i = atomicAdd(&g_trace_n, 1u);
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    if (i < 8192) {
+      g_trace[3 * i] = (unsigned long long)id | ((unsigned long long)blockIdx.x << 16);
+      g_trace[3 * i + 1] = (unsigned long long)clock64();
+      g_trace[3 * i + 2] = gt;
+    }
+  }
+}
+}  // namespace qz
+#define SC_TRACE(id)                                  \
+  do {                                                \
+    if (((QZ_SC_TRACE) >> (id)) & 1) sc_trace(id);    \
+  } while (0)  // QZ_SC_TRACE = bit mask of the stamps to take
+#endif
 #include "comm.cuh"
 #include "ctx.cuh"
 #include "sumcheck.cuh"
@@ -456,6 +479,185 @@ QZ_DEV void mid_block_pass(const ScTables& view, uint64_t first, uint64_t step, 
     for (uint64_t p = first; p < n_pairs; p += step) generic_pair<true>(view, p, fold, r, s_ops, n_ops, k, d, consts, acc, SKIP1);
   }
 }
+
+// ---- the split pass: a short round as two levels of products spread over the whole block ------------------------------------------
+// A thread that owns a whole pair runs its 12 products (K = 3: 6 folds, 3 + 3 for the sums) one after the other -- a
+// lone product is ~810 cycles of dependent carry chains (tools/latbench.cu) and nothing overlaps them, so a round costs
+// ~7 us however few pairs it has (tools/sc_trace.py).  Here a tile of pairs is worked on by the whole block:
+//   level 1: one work item per ELEMENT of the folded tables (2 k per pair): load 2, fold, store to the half-size table
+//            and to shared memory;
+//   level 2: one work item per (pair, evaluation point): the k values at X by additions, then the k - 1 products of
+//            the fast path (or the interpreter) -- the same count as the quadratic trick of prod_core for K = 3.  The
+//            threads form one row per evaluation point (32 * (8 / ns) threads, whole warps), so a thread only ever
+//            sums one point and a row is reduced by one shuffle sum per thread.
+// Two product latencies and a memory round trip for a tile of <= 32 pairs instead of twelve; larger tiles loop over
+// the items and approach the multiplier's throughput.  The plan (blocks per round, pairs per block) is made by the
+// host, which also sizes the grid with it, and travels as a kernel argument.
+constexpr int SC_TILE_ELEMS = 512;  // shared-memory tile of the split pass, in field elements (16 KiB)
+struct ScMidPlan {
+  uint16_t nblk[SC_MAX_VARS];    // blocks that work on round j of this launch
+  uint16_t future[SC_MAX_VARS];  // max of nblk over rounds >= j: blocks beyond it leave the kernel
+  uint32_t chunk[SC_MAX_VARS];   // pairs per block (split rounds)
+  uint32_t split;                // 1: rounds run the split pass (the shape fits), 0: whole pairs per thread
+  uint32_t tile;                 // pairs per tile of the split pass
+};
+// does the shape fit the split pass, and with which tile?  k tables, at most d + 1 evaluation points
+inline int mid_tile_pairs(int k, int d) {
+  if (k > 8 || d + 1 > 8) return 0;
+  int tile = 256;
+  while (2 * k * tile > SC_TILE_ELEMS) tile >>= 1;
+  return tile;
+}
+// rounds of an sc_mid launch from (size, pending) on; returns the grid it needs (<= cap)
+inline unsigned int mid_make_plan(ScMidPlan& plan, uint64_t size, int pending, int k, int d, unsigned int cap, int G) {
+  memset(&plan, 0, sizeof plan);
+  const int tile = mid_tile_pairs(k, d);
+  plan.split = tile > 0;
+  plan.tile = (uint32_t)tile;
+  bool gathered = G == 1;
+  int j = 0;
+  while (j < SC_MAX_VARS) {
+    if (!gathered && size * (uint64_t)G <= ((uint64_t)1 << SC_TAIL_LOG)) {
+      size *= (uint64_t)G;
+      gathered = true;
+    }
+    if (size <= 1 || (pending && size == 2)) break;
+    const uint64_t n_pairs = pending ? size / 4 : size / 2;
+    // split: at least 32 pairs per block (below that the round is two product latencies whatever the count);
+    // whole pairs: one pair per thread
+    const uint64_t unit = plan.split ? 32 : SC_THREADS;
+    uint64_t nb = std::max<uint64_t>(1, std::min<uint64_t>((n_pairs + unit - 1) / unit, cap));
+    const uint64_t ch = (n_pairs + nb - 1) / nb;
+    nb = (n_pairs + ch - 1) / ch;
+    plan.nblk[j] = (uint16_t)nb;
+    plan.chunk[j] = (uint32_t)ch;
+    if (pending) size >>= 1;
+    pending = 1;
+    j++;
+  }
+  uint16_t best = 1;
+  for (int i = j - 1; i >= 0; i--) {
+    best = std::max(best, plan.nblk[i]);
+    plan.future[i] = best;
+  }
+  for (int i = j; i < SC_MAX_VARS; i++) plan.nblk[i] = plan.future[i] = 1;
+  return best;
+}
+
+// this block's pairs [p_begin, p_end) of a round, tile by tile; dst[x] (x < ns <= 8) <- the block's sums.  Ends with a
+// barrier.  s_tile: SC_TILE_ELEMS Fr of shared memory, s_rows: SC_THREADS / 32 Fr.
+template <int KP>
+QZ_DEV void mid_split_pass(const ScTables& view, uint64_t p_begin, uint64_t p_end, bool fold, bool skip1, const Fr& r,
+                           const uint32_t* s_ops, uint32_t n_ops, int k, int ns, const Fr* consts, int tile_pairs,
+                           Fr* s_tile, Fr* s_rows, Fr* dst) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wpr = 8 / ns, rw = 32 * wpr;             // warps / threads per row
+  const int xi = tid / rw, ri = tid % rw;            // level 2: evaluation point index, position in its row
+  const int x = skip1 && xi > 0 ? xi + 1 : xi;       // SKIP1 rounds: X = 0, 2, 3, ..
+  Fr acc = fp_zero<FrParams>();
+  for (uint64_t tile = p_begin; tile < p_end; tile += (uint64_t)tile_pairs) {
+    const int np = (int)(p_end - tile < (uint64_t)tile_pairs ? p_end - tile : (uint64_t)tile_pairs);
+    for (int item = tid; item < 2 * k * np; item += SC_THREADS) {
+      const int ft = item / (2 * np), fe = item - ft * 2 * np;  // table, element of the tile
+      const uint64_t idx = 2 * tile + (uint64_t)fe;             // element of the tables this round sums over
+      Fr v;
+      if (fold) {
+        const Fr a0 = ld_elem_cv(view.in[ft], 2 * idx), a1 = ld_elem_cv(view.in[ft], 2 * idx + 1);
+        v = fp_add<FrParams>(a0, fp_mul<FrParams>(r, fp_sub<FrParams>(a1, a0)));
+        st_elem(view.out[ft], idx, v);
+      } else {
+        v = ld_elem_cv(view.in[ft], idx);
+      }
+      s_tile[item] = v;
+    }
+    __syncthreads();
+    if (xi < ns) {
+      for (int pr = ri; pr < np; pr += rw) {
+        constexpr int KC = KP > 0 ? KP : 8;
+        Fr cur[KC];
+#pragma unroll
+        for (int t = 0; t < KC; t++) {
+          if (t < k) {
+            const Fr lo = s_tile[t * 2 * np + 2 * pr], hi = s_tile[t * 2 * np + 2 * pr + 1];
+            if (x == 0) {
+              cur[t] = lo;
+            } else {
+              const Fr df = fp_sub<FrParams>(hi, lo);
+              Fr v = hi;
+              for (int i = 1; i < x; i++) v = fp_add<FrParams>(v, df);
+              cur[t] = v;
+            }
+          }
+        }
+        Fr val;
+        if (KP > 0) {
+          val = cur[0];
+#pragma unroll
+          for (int t = 1; t < KC; t++) val = fp_mul<FrParams>(val, cur[t]);
+        } else {
+          val = sc_eval_program(s_ops, n_ops, consts, cur);
+        }
+        acc = fp_add<FrParams>(acc, val);
+      }
+    }
+    __syncthreads();
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) s_rows[warp] = acc;
+  __syncthreads();
+  if (tid < ns) {
+    Fr sum = s_rows[tid * wpr];
+    for (int w = 1; w < wpr; w++) sum = fp_add<FrParams>(sum, s_rows[tid * wpr + w]);
+    dst[tid] = sum;
+  }
+  __syncthreads();
+}
+
+// the closing block's sum of the nblk parked vectors.  ns <= 8: a row of 32 * (8 / ns) threads per evaluation point, one
+// shuffle sum per thread (block_sum_many runs ns of them back to back).  dst[x] written by thread x.  Ends with a barrier.
+QZ_DEV void mid_sum_parked(const Fr* partials, unsigned int nblk, int ns, Fr* s_part, Fr* dst) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (ns <= 8) {
+    const int wpr = 8 / ns, rw = 32 * wpr;  // warps / threads per row
+    const int x = tid / rw, i = tid % rw;
+    Fr v = fp_zero<FrParams>();
+    if (x < ns)
+      for (unsigned int b = (unsigned int)i; b < nblk; b += (unsigned int)rw)
+        v = fp_add<FrParams>(v, ld_elem_cv(reinterpret_cast<const uint4*>(partials), (uint64_t)b * ns + x));
+    v = warp_sum(v);
+    if (lane == 0) s_part[warp] = v;
+    __syncthreads();
+    if (tid < ns) {
+      Fr s = s_part[tid * wpr];
+      for (int w = 1; w < wpr; w++) s = fp_add<FrParams>(s, s_part[tid * wpr + w]);
+      dst[tid] = s;
+    }
+    __syncthreads();
+  } else {
+    Fr acc[SC_MAX_COEFFS];
+    for (int x = 0; x < ns; x++)
+      acc[x] = (unsigned int)tid < nblk ? ld_elem_cv(reinterpret_cast<const uint4*>(partials), (uint64_t)tid * ns + x)
+                                        : fp_zero<FrParams>();
+    block_sum_many(acc, ns, s_part, dst);
+  }
+}
+
+// blocks other than the closing one wait here until `target` rounds are closed
+QZ_DEV void mid_wait_closed(ScMidSync* sync, unsigned int target, ScHead* head) {
+  if (threadIdx.x == 0 && ld_acquire_gpu(&sync->flag) < target) {
+    // the closing block may itself be waiting for a peer GPU (20 s at most, comm.cuh); give up a little later than that
+    // rather than hang the device: the proof is void (peer_fault) and every block runs on to the end on stale data.
+    // The clock is read once per 256 polls: reading it costs more than the poll.
+    const unsigned long long t0 = global_timer_ns();
+    for (unsigned int polls = 1; ld_acquire_gpu(&sync->flag) < target; polls++)
+      if ((polls & 255u) == 0 && global_timer_ns() - t0 > PEER_WAIT_NS + PEER_WAIT_NS / 2) {
+        head->peer_fault = 2;
+        break;
+      }
+  }
+  __syncthreads();
+}
+
 // KP > 0: h is a product of KP distinct tables (same fast path as sc_round_prod); KP == 0: interpret the program
 template <int KP>
 __global__ void __launch_bounds__(SC_THREADS) sc_mid(ScTables tabs, ScTailBufs bufs, uint64_t size, int pending_fold,
@@ -463,11 +665,13 @@ __global__ void __launch_bounds__(SC_THREADS) sc_mid(ScTables tabs, ScTailBufs b
                                                     Fr* out_coeffs, uint32_t* out_lens, Fr* out_point, int round,
                                                     int max_coeffs, Fr* partials, ScMidSync* sync,
                                                     PeerMailbox* const* peers, int rank, int G, uint32_t seq,
-                                                    int gather_par, const Fr* zc_z, int zc_n) {
+                                                    int gather_par, const Fr* zc_z, int zc_n,
+                                                    const __grid_constant__ ScMidPlan plan) {
   __shared__ Fr s_part[(SC_THREADS / 32) * SC_MAX_COEFFS];
   __shared__ Fr s_evals[SC_MAX_COEFFS];
   __shared__ Fr s_coef[SC_MAX_COEFFS];
   __shared__ Fr s_prod[SC_PROD_SLOTS];
+  __shared__ Fr s_tile[SC_TILE_ELEMS];
   __shared__ __align__(16) uint32_t s_msg[SC_MSG_WORDS];
   __shared__ uint32_t s_ops[SC_MAX_OPS];
   __shared__ int s_last;
@@ -481,63 +685,87 @@ __global__ void __launch_bounds__(SC_THREADS) sc_mid(ScTables tabs, ScTailBufs b
   int flip = 0;
   bool gathered = G == 1;
   unsigned int arrive_target = 0, rounds_closed = 0;
+  int pj = 0;  // round of this launch (index into the plan)
   // `size` elements per table with (pending_fold) the last challenge still to be folded in.  Each round is ONE pass:
   // fold (reads 4, writes 2) fused with the evaluation of the new pairs, exactly like the streaming kernel.
   for (;;) {
+    // blocks no later round will use leave (the count is not monotone: a split round spreads thinner than the
+    // whole-pair round before it, and the rounds after a gather have more pairs than the ones just before it)
+    if (blockIdx.x >= plan.future[pj]) return;
     if (!gathered && size * (uint64_t)G <= ((uint64_t)1 << SC_TAIL_LOG)) {
-      // hand-over of a sharded proof: every rank's shard into every rank's gather area, then everyone runs alone
-      if (blockIdx.x != 0) return;
+      // hand-over of a sharded proof: block 0 stores this rank's shard into every rank's gather area (rank order =
+      // index order) and exchanges flags with the peers; the step is closed like a round for the other blocks
       PeerMailbox* mine = peers[rank];
       const int par = gather_par;
-      for (int t = 0; t < k; t++)
-        for (uint64_t i = threadIdx.x; i < size; i += blockDim.x) {
-          const Fr v = ld_elem_cv(view.in[t], i);
-          for (int g = 0; g < G; g++) fp_store<FrParams>(&peers[g]->gather[par][t][(uint64_t)rank * size + i], v);
+      if (blockIdx.x == 0) {
+        for (int t = 0; t < k; t++)
+          for (uint64_t i = threadIdx.x; i < size; i += blockDim.x) {
+            const Fr v = ld_elem_cv(view.in[t], i);
+            for (int g = 0; g < G; g++) fp_store<FrParams>(&peers[g]->gather[par][t][(uint64_t)rank * size + i], v);
+          }
+        __syncthreads();
+        if (threadIdx.x == 0) s_evals[0] = fp_zero<FrParams>();
+        __syncthreads();
+        peer_exchange(peers, rank, G, seq, s_evals, 1);  // fence + flags: every rank's stores above are visible after it
+        if (threadIdx.x == 0) {
+          if (*reinterpret_cast<volatile uint32_t*>(&mine->timed_out)) head->peer_fault = 1;
+          __threadfence();
+          st_release_gpu(&sync->flag, rounds_closed + 1);
         }
-      __syncthreads();
-      if (threadIdx.x == 0) s_evals[0] = fp_zero<FrParams>();
-      __syncthreads();
-      peer_exchange(peers, rank, G, seq++, s_evals, 1);  // fence + flags: every rank's stores above are visible after it
-      if (threadIdx.x == 0 && *reinterpret_cast<volatile uint32_t*>(&mine->timed_out)) head->peer_fault = 1;
+        __syncthreads();
+      } else {
+        mid_wait_closed(sync, rounds_closed + 1, head);
+      }
+      rounds_closed++;
+      seq++;
       for (int t = 0; t < k; t++) view.in[t] = reinterpret_cast<const uint4*>(&mine->gather[par][t][0]);
       size *= (uint64_t)G;
       gathered = true;
     }
     if (size <= 1 || (pending_fold && size == 2)) break;
     const uint64_t n_pairs = pending_fold ? size / 4 : size / 2;
-    const bool alone = G > 1 && gathered;  // after the gather a rank never spreads a round again (the data is tiny)
-    const uint64_t want = (n_pairs + SC_THREADS - 1) / SC_THREADS;
-    const unsigned int nblk = alone ? 1u : (unsigned int)(want < gridDim.x ? (want ? want : 1) : gridDim.x);
-    if (blockIdx.x >= nblk) return;  // rounds only shrink: idle now means idle until the end
-    for (int t = 0; t < k; t++) view.out[t] = flip ? bufs.b[t] : bufs.a[t];
-    Fr r = fp_zero<FrParams>();
-    if (pending_fold) r = ld_elem_cv(reinterpret_cast<const uint4*>(&head->r), 0);
+    const bool split = plan.split != 0;
+    const uint64_t chunk = plan.chunk[pj];
+    const unsigned int nblk = plan.nblk[pj];
     const bool skip1 = pending_fold && d >= 1;  // X = 1 from the running claim (ProdAcc)
     const int ns = skip1 ? d : d + 1;
-    Fr acc[SC_MAX_COEFFS];
-    const uint64_t first = (uint64_t)blockIdx.x * SC_THREADS + threadIdx.x, step = (uint64_t)nblk * SC_THREADS;
-    if (skip1) mid_block_pass<KP, true>(view, first, step, n_pairs, true, r, s_ops, n_ops, k, d, consts, acc);
-    else mid_block_pass<KP, false>(view, first, step, n_pairs, pending_fold != 0, r, s_ops, n_ops, k, d, consts, acc);
-    bool closer = true;
-    if (nblk > 1) {  // park this block's vector; the last block to arrive closes the round
-      block_sum_many(acc, ns, s_part, &partials[(size_t)blockIdx.x * ns]);
-      arrive_target += nblk;
-      if (threadIdx.x == 0) {
-        __threadfence();
-        s_last = atomicAdd(&sync->arrive, 1u) + 1u == arrive_target;
+    bool closer = false;
+    SC_TRACE(1);
+    if (blockIdx.x < nblk) {
+      for (int t = 0; t < k; t++) view.out[t] = flip ? bufs.b[t] : bufs.a[t];
+      Fr r = fp_zero<FrParams>();
+      if (pending_fold) r = ld_elem_cv(reinterpret_cast<const uint4*>(&head->r), 0);
+      Fr* dst = nblk > 1 ? &partials[(size_t)blockIdx.x * ns] : s_evals;
+      if (split) {
+        const uint64_t p0 = (uint64_t)blockIdx.x * chunk, p1 = p0 + chunk < n_pairs ? p0 + chunk : n_pairs;
+        mid_split_pass<KP>(view, p0, p1, pending_fold != 0, skip1, r, s_ops, n_ops, k, ns, consts, (int)plan.tile, s_tile, s_part,
+                           dst);
+      } else {
+        Fr acc[SC_MAX_COEFFS];
+        const uint64_t first = (uint64_t)blockIdx.x * SC_THREADS + threadIdx.x, step = (uint64_t)nblk * SC_THREADS;
+        if (skip1) mid_block_pass<KP, true>(view, first, step, n_pairs, true, r, s_ops, n_ops, k, d, consts, acc);
+        else mid_block_pass<KP, false>(view, first, step, n_pairs, pending_fold != 0, r, s_ops, n_ops, k, d, consts, acc);
+        block_sum_many(acc, ns, s_part, dst);
       }
-      __syncthreads();
-      closer = s_last != 0;
-      if (closer) {  // one parked vector per thread (at most gridDim.x <= blockDim.x of them), then a block sum
-        __threadfence();
-        for (int x = 0; x < ns; x++)
-          acc[x] = threadIdx.x < nblk ? ld_elem_cv(reinterpret_cast<const uint4*>(partials), (uint64_t)threadIdx.x * ns + x)
-                                      : fp_zero<FrParams>();
-        block_sum_many(acc, ns, s_part, s_evals);
+      SC_TRACE(2);
+      closer = true;
+      if (nblk > 1) {  // this block's vector is parked; the last block to arrive closes the round
+        arrive_target += nblk;
+        if (threadIdx.x == 0) {
+          __threadfence();
+          s_last = atomicAdd(&sync->arrive, 1u) + 1u == arrive_target;
+        }
+        __syncthreads();
+        closer = s_last != 0;
+        if (closer) {
+          __threadfence();
+          mid_sum_parked(partials, nblk, ns, s_part, s_evals);
+        }
       }
-    } else {
-      block_sum_many(acc, ns, s_part, s_evals);
+    } else if (nblk > 1) {
+      arrive_target += nblk;  // idle this round, needed by a later one
     }
+    SC_TRACE(3);
     if (closer) {
       if (!gathered) {  // sharded: all ranks' vectors (comm.cuh), exact field addition in any order
         const PeerSlot* got = peer_exchange(peers, rank, G, seq, s_evals, ns);
@@ -549,32 +777,32 @@ __global__ void __launch_bounds__(SC_THREADS) sc_mid(ScTables tabs, ScTailBufs b
         }
         __syncthreads();
       }
+      SC_TRACE(4);
       if (skip1) sc_expand_evals(head, d, s_evals, nullptr, nullptr);
+      // The other blocks are released as soon as the challenge is out, provided this block works on the next round too:
+      // its arrival there orders the claim it is still computing before the next closing block reads it.
+      const bool multi = gridDim.x > 1;
+      const bool early = multi && pj + 1 < SC_MAX_VARS && blockIdx.x < plan.nblk[pj + 1];
       sc_round_close(head, vinv, d, s_evals, s_coef, s_msg, s_prod, out_coeffs + (size_t)round * max_coeffs,
-                     out_lens + round, out_point + round, max_coeffs, nullptr, true);
-      if (nblk > 1 && threadIdx.x == 0) {
-        __threadfence();
-        st_release_gpu(&sync->flag, rounds_closed + 1);
+                     out_lens + round, out_point + round, max_coeffs, nullptr, true, nullptr,
+                     early ? &sync->flag : nullptr, rounds_closed + 1);
+      SC_TRACE(6);
+      if (multi && !early) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          __threadfence();
+          st_release_gpu(&sync->flag, rounds_closed + 1);
+        }
       }
     }
     rounds_closed++;
     if (!gathered) seq++;
-    if (nblk > 1) {
-      if (threadIdx.x == 0 && ld_acquire_gpu(&sync->flag) < rounds_closed) {
-        // the closing block may itself be waiting for a peer GPU (20 s at most, comm.cuh); give up a little later than that
-        // rather than hang the device: the proof is void (peer_fault) and every block runs on to the end on stale data
-        const unsigned long long t0 = global_timer_ns();
-        while (ld_acquire_gpu(&sync->flag) < rounds_closed)
-          if (global_timer_ns() - t0 > PEER_WAIT_NS + PEER_WAIT_NS / 2) {
-            head->peer_fault = 2;
-            break;
-          }
-      }
-      __syncthreads();
-    }
+    if (!closer) mid_wait_closed(sync, rounds_closed, head);
+    SC_TRACE(7);
     round++;
+    pj++;
     if (pending_fold) {
-      for (int t = 0; t < k; t++) view.in[t] = view.out[t];
+      for (int t = 0; t < k; t++) view.in[t] = flip ? bufs.b[t] : bufs.a[t];
       flip ^= 1;
       size >>= 1;
     }
@@ -582,7 +810,7 @@ __global__ void __launch_bounds__(SC_THREADS) sc_mid(ScTables tabs, ScTailBufs b
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // sumcheck.rs:81-100: last fold, then h(g_1(r), ..., g_k(r))
     Fr fin[SC_MAX_K];
-    const Fr r = head->r;
+    const Fr r = fr_ld_cv(&head->r);
     for (int t = 0; t < k; t++) {
       Fr lo = ld_elem_cv(view.in[t], 0);
       if (pending_fold && size == 2) {
@@ -1179,7 +1407,7 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
     } else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sc_round_generic<true>, SC_THREADS, 0);
     if (bps < 1) bps = 1;
     if (getenv("QZ_SC_NARROW")) bps_wide = 0;  // measurement switch: force the fully reduced sums
-    Fr* partials = (Fr*)ctx->arena_alloc(sizeof(Fr) * (size_t)ctx->sm_count * std::max(bps, bps_wide) * (d + 1) * up_chunks);
+    Fr* partials = (Fr*)ctx->arena_alloc(sizeof(Fr) * std::max<size_t>((size_t)ctx->sm_count * std::max(bps, bps_wide), SC_THREADS) * (d + 1) * up_chunks);
     Fr* rank_evals = (Fr*)ctx->arena_alloc(sizeof(Fr) * (d + 1));
     Fr* all_evals = (Fr*)ctx->arena_alloc(sizeof(Fr) * (size_t)(d + 1) * G);
     if (!partials || !rank_evals || !all_evals) return ctx->fail(QZ_ERR_ALLOC, "partials");
@@ -1421,9 +1649,6 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
       gather_par = (int)(ctx->gather_seq++ & 1);
     }
     {
-      const uint64_t n_pairs0 = pending ? size / 4 : size / 2;
-      uint64_t want = std::max<uint64_t>(1, (n_pairs0 + SC_THREADS - 1) / SC_THREADS);
-      if (mid_G > 1 && size * G <= ((uint64_t)1 << SC_TAIL_LOG)) want = 1;
       const void* kern = nullptr;
       switch (cp.product_k) {
         case 1: kern = (const void*)sc_mid<1>; break;
@@ -1432,13 +1657,15 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
         case 4: kern = (const void*)sc_mid<4>; break;
         default: kern = (const void*)sc_mid<0>;
       }
+      // the grid: as many blocks as the widest remaining round uses (the kernel derives every round's share from
+      // gridDim.x with the same plan), all co-resident, and never more than a block has threads (the closing block
+      // reads the parked vectors one per thread)
       int occ = 1;
-      if (want > 1) {
-        QZ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SC_THREADS, 0));
-        if (occ < 1) occ = 1;
-      }
-      // (the closing block sums one parked vector per thread: never more blocks than a block has threads)
-      const int grid = (int)std::min<uint64_t>(std::min<uint64_t>(want, SC_THREADS), (uint64_t)ctx->sm_count * occ);
+      QZ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SC_THREADS, 0));
+      if (occ < 1) occ = 1;
+      const unsigned int cap = (unsigned int)std::min<uint64_t>(SC_THREADS, (uint64_t)ctx->sm_count * occ);
+      ScMidPlan plan;
+      const int grid = (int)mid_make_plan(plan, size, pending, ka, d, cap, mid_G);
       ScTables k_tabs = tabs;
       uint64_t k_size = size;
       int k_pending = pending, k_round = round, k_mc = mc, k_rank = ctx->rank, k_G = mid_G, k_zc_n = zerocheck ? (int)num_vars : 0;
@@ -1449,7 +1676,7 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
       uint32_t* k_lens = d_lens;
       PeerMailbox* const* k_peers = (PeerMailbox* const*)ctx->peer_mbox_dev;
       void* args[] = {&k_tabs, &tb, &k_size, &k_pending, &k_head, &k_prog, &k_consts, &k_vinv, &k_coeffs, &k_lens, &k_point,
-                      &k_round, &k_mc, &k_parts, &d_sync, &k_peers, &k_rank, &k_G, &seq0, &gather_par, &k_z, &k_zc_n};
+                      &k_round, &k_mc, &k_parts, &d_sync, &k_peers, &k_rank, &k_G, &seq0, &gather_par, &k_z, &k_zc_n, &plan};
       if (grid > 1) {  // the blocks wait for one another: they must all be resident
         QZ_CUDA(ctx, cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(SC_THREADS), args, 0, st));
         ctx->launches++;
@@ -1498,6 +1725,20 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
 }
 
 }  // namespace qz
+
+#ifdef QZ_SC_TRACE
+extern "C" int qz_debug_trace(unsigned long long* out, int max_records) {
+  unsigned int n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, qz::g_trace_n, 4);
+  if (n > 8192) n = 8192;
+  if ((int)n > max_records) n = max_records;
+  cudaMemcpyFromSymbol(out, qz::g_trace, (size_t)n * 24);
+  unsigned int zero = 0;
+  cudaMemcpyToSymbol(qz::g_trace_n, &zero, 4);
+  return (int)n;
+}
+#endif
 
 extern "C" int qz_test_fold(qz_ctx* ctx, const uint8_t r[32], const uint8_t* a0, const uint8_t* a1, uint8_t* out, size_t n) {
   if (!ctx || !r || !a0 || !a1 || !out) return QZ_ERR_INVALID_ARG;

@@ -5,6 +5,10 @@
 #include "blake3.cuh"
 #include "ff.cuh"
 
+#ifndef SC_TRACE
+#define SC_TRACE(id)  // measurement hook, active only in the -DQZ_SC_TRACE build of sumcheck.cu
+#endif
+
 namespace qz {
 
 constexpr int SC_MAX_DEG = QZ_MAX_ROUND_COEFFS - 1;
@@ -42,6 +46,14 @@ struct ScHead {
   uint32_t peer_fault;     // a peer-mailbox wait timed out during this proof (comm.cuh): the results are void
   uint32_t zc_degenerate;  // a zero-check challenge z_j was 0: no 1 / z_j, the proof is redone without that shortcut
 };
+
+// a field element of the proof head read past L1: the previous round may have been closed by another block or kernel
+QZ_DEV Fr fr_ld_cv(const Fr* p) {
+  const uint4 a = __ldcv(reinterpret_cast<const uint4*>(p)), b = __ldcv(reinterpret_cast<const uint4*>(p) + 1);
+  Fr r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
 
 // ---- serialization / transcript (device) -------------------------------------------------------------------------
 QZ_DEV void fr_to_le_bytes(const Fr& mont, uint8_t* out) {  // ark-serialize: 32 B little-endian canonical
@@ -272,8 +284,8 @@ QZ_DEV void b3_single_chunk_quad(const uint32_t* buf, uint32_t total_bytes, uint
 // boundary; state (8 words, any memory the quad can read and write) <- blake3(state ‖ msg).  32 + msg_bytes <= 1024.
 QZ_DEV void tr_absorb_quad(uint32_t* state, uint32_t* buf, uint32_t msg_bytes) {
   const int lane = threadIdx.x & 3;
-  buf[lane] = state[lane];
-  buf[4 + lane] = state[4 + lane];
+  buf[lane] = __ldcv(state + lane);  // past L1: another block (sc_mid) or kernel may have written the state
+  buf[4 + lane] = __ldcv(state + 4 + lane);
   __syncwarp(B3_QUAD);
   uint32_t cva, cvb;
   b3_single_chunk_quad(buf, 32 + msg_bytes, cva, cvb, nullptr);
@@ -284,7 +296,7 @@ QZ_DEV void tr_absorb_quad(uint32_t* state, uint32_t* buf, uint32_t msg_bytes) {
 // draw_field_element::<Fr> (transcript.rs:49-75) on a quad; buf: 32 words of shared memory.  Every lane returns r.
 QZ_DEV Fr tr_draw_fr_quad(uint32_t* state, uint32_t* buf) {
   const int lane = threadIdx.x & 3;
-  for (int i = lane; i < 32; i += 4) buf[i] = i < 8 ? state[i] : 0u;
+  for (int i = lane; i < 32; i += 4) buf[i] = i < 8 ? __ldcv(state + i) : 0u;
   __syncwarp(B3_QUAD);
   if (lane == 0) {
     buf[8] = 0x6c616863u;   // "chal"
@@ -303,16 +315,18 @@ QZ_DEV Fr tr_draw_fr_quad(uint32_t* state, uint32_t* buf) {
   b3_single_chunk_quad(buf, 80, na, nb, nullptr);  // re-absorb the 48 challenge bytes (transcript.rs:60)
   state[lane] = na;
   state[4 + lane] = nb;
-  Fr lo, hi, r2, r3;
+  // x = lo + hi 2^256 -> x R = lo R^2 / R + hi R^3 / R: lane 0 takes the first product, lane 1 the second
+  Fr op, cst;
 #pragma unroll
   for (int i = 0; i < 8; i++) {
-    lo.v[i] = buf[8 + i];
-    hi.v[i] = i < 4 ? buf[16 + i] : 0u;
-    r2.v[i] = FrParams::R2(i);
-    r3.v[i] = FrParams::R3(i);
+    op.v[i] = (lane & 1) ? (i < 4 ? buf[16 + i] : 0u) : buf[8 + i];
+    cst.v[i] = (lane & 1) ? FrParams::R3(i) : FrParams::R2(i);
   }
   __syncwarp(B3_QUAD);
-  return fp_add<FrParams>(fp_mul<FrParams>(r2, lo), fp_mul<FrParams>(r3, hi));
+  Fr part = fp_mul<FrParams>(cst, op), other;
+#pragma unroll
+  for (int i = 0; i < 8; i++) other.v[i] = __shfl_xor_sync(B3_QUAD, part.v[i], 1, 4);
+  return fp_add<FrParams>(part, other);
 }
 
 // ---- reductions ------------------------------------------------------------------------------------------------------
@@ -415,7 +429,7 @@ QZ_DEV void sc_expand_evals(const ScHead* head, int d, Fr* s_evals, const Fr* zc
   const int t = threadIdx.x;
   if (t >= 2 && t <= d) mine = s_evals[t - 1];
   if (t == 1) {
-    const Fr e0 = s_evals[0], claim = head->claim;
+    const Fr e0 = s_evals[0], claim = fr_ld_cv(&head->claim);
     if (zc_z) {
       const Fr z = *zc_z, one = fp_one<FrParams>();
       mine = fp_mul<FrParams>(fp_sub<FrParams>(claim, fp_mul<FrParams>(fp_sub<FrParams>(one, z), e0)), *zc_zinv);
@@ -429,9 +443,15 @@ QZ_DEV void sc_expand_evals(const ScHead* head, int d, Fr* s_evals, const Fr* zc
 }
 
 // want_claim: leave s_j(r_j) (t_j(r_j) on the eq-factored path) in head->claim for a following SKIP1 round
+// release_flag (sc_mid): set to release_value as soon as the challenge is in head->r -- the other blocks of the grid
+// start folding with it while this block finishes the bookkeeping.  That bookkeeping (the running claim: d dependent
+// products; the zero-check prefix) is done by lane 0 of the LAST warp, which a short round leaves without work, so
+// the first warps of this block are not held up either.
 QZ_DEV void sc_round_close(ScHead* head, const Fr* vinv, int d, const Fr* s_evals, Fr* s_coef, uint32_t* s_msg, Fr* s_prod,
                            Fr* out_coeffs_row, uint32_t* out_len, Fr* out_point_slot, int max_coeffs,
-                           const Fr* zc_z = nullptr, bool want_claim = false, uint32_t* foldc = nullptr) {
+                           const Fr* zc_z = nullptr, bool want_claim = false, uint32_t* foldc = nullptr,
+                           unsigned int* release_flag = nullptr, unsigned int release_value = 0) {
+  __shared__ Fr s_chal;
   const int t = threadIdx.x;
   const int n1 = d + 1;
   const int n_out = zc_z ? d + 2 : d + 1;  // coefficients of the round polynomial before trimming
@@ -452,16 +472,19 @@ QZ_DEV void sc_round_close(ScHead* head, const Fr* vinv, int d, const Fr* s_eval
     }
     s_coef[t] = acc;
   }
+  SC_TRACE(10);
+  Fr zc_P = fp_zero<FrParams>();
   if (zc_z) {  // (c_0 + c_1 X + ...)(a + b X): c'_t = a c_t + b c_{t-1}
     __syncthreads();
     Fr lower = fp_zero<FrParams>();
     if (t >= 1 && t <= d + 1) lower = s_coef[t - 1];
     if (want_claim && t <= d) s_prod[t] = acc;  // t_j's coefficients, for the running claim (s_prod is free again)
     __syncthreads();
+    zc_P = fr_ld_cv(&head->zc_prefix);
     if (t < n_out) {
-      const Fr z = *zc_z, P = head->zc_prefix, one = fp_one<FrParams>();
-      const Fr a = fp_mul<FrParams>(P, fp_sub<FrParams>(one, z));
-      const Fr b = fp_mul<FrParams>(P, fp_sub<FrParams>(fp_dbl<FrParams>(z), one));
+      const Fr z = *zc_z, one = fp_one<FrParams>();
+      const Fr a = fp_mul<FrParams>(zc_P, fp_sub<FrParams>(one, z));
+      const Fr b = fp_mul<FrParams>(zc_P, fp_sub<FrParams>(fp_dbl<FrParams>(z), one));
       acc = fp_add<FrParams>(fp_mul<FrParams>(a, acc), fp_mul<FrParams>(b, lower));  // acc = c_t (zero for t = d + 1)
       s_coef[t] = acc;
     }
@@ -475,6 +498,7 @@ QZ_DEV void sc_round_close(ScHead* head, const Fr* vinv, int d, const Fr* s_eval
     out_coeffs_row[t] = fp_zero<FrParams>();
   }
   __syncthreads();
+  SC_TRACE(11);
   if (t < 4) {  // the transcript runs on lanes 0..3 of warp 0 (tr_*_quad)
     if (t == 0) {
       int len = n_out;
@@ -493,26 +517,36 @@ QZ_DEV void sc_round_close(ScHead* head, const Fr* vinv, int d, const Fr* s_eval
       if (t == 0) tr_absorb_words(state, s_msg, 8 + 32 * len);
       __syncwarp(B3_QUAD);
     }
+    SC_TRACE(12);
     const Fr r = tr_draw_fr_quad(state, s_msg);   // :77
+    SC_TRACE(13);
     if (t == 0) {
       head->r = r;
       *out_point_slot = r;
-      if (want_claim) {  // Horner at the challenge
-        const Fr* c = zc_z ? s_prod : s_coef;
-        Fr v = c[d];
-        for (int i = d - 1; i >= 0; i--) v = fp_add<FrParams>(fp_mul<FrParams>(v, r), c[i]);
-        head->claim = v;
-      }
-      if (zc_z) {  // P_{j+1} = P_j (r z + (1 - r)(1 - z))
-        const Fr z = *zc_z, one = fp_one<FrParams>(), P = head->zc_prefix;
-        const Fr e = fp_add<FrParams>(fp_mul<FrParams>(r, z), fp_mul<FrParams>(fp_sub<FrParams>(one, r), fp_sub<FrParams>(one, z)));
-        head->zc_prefix_prev = P;
-        head->zc_prefix = fp_mul<FrParams>(P, e);
-      }
+      s_chal = r;
     }
   }
   __syncthreads();
-  if (foldc && t < 8) fold_table_row(head->r, t, foldc);
+  if (t == 0 && release_flag) {  // every write of this round (tables, state, challenge) before the flag
+    __threadfence();
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(release_flag), "r"(release_value) : "memory");
+  }
+  if (t == (int)blockDim.x - 32) {
+    const Fr r = s_chal;
+    if (want_claim) {  // Horner at the challenge
+      const Fr* c = zc_z ? s_prod : s_coef;
+      Fr v = c[d];
+      for (int i = d - 1; i >= 0; i--) v = fp_add<FrParams>(fp_mul<FrParams>(v, r), c[i]);
+      head->claim = v;
+    }
+    if (zc_z) {  // P_{j+1} = P_j (r z + (1 - r)(1 - z))
+      const Fr z = *zc_z, one = fp_one<FrParams>();
+      const Fr e = fp_add<FrParams>(fp_mul<FrParams>(r, z), fp_mul<FrParams>(fp_sub<FrParams>(one, r), fp_sub<FrParams>(one, z)));
+      head->zc_prefix_prev = zc_P;
+      head->zc_prefix = fp_mul<FrParams>(zc_P, e);
+    }
+  }
+  if (foldc && t < 8) fold_table_row(s_chal, t, foldc);
 }
 
 }  // namespace qz

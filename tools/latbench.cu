@@ -48,6 +48,21 @@ __global__ void klat4(uint32_t* state_g, long long* t, Fr* sink) {
   }
 }
 
+// dependent-load latency of the three global load flavours the short rounds could use (pointer chase over 4 KiB)
+__global__ void kload(const uint32_t* chain, long long* t, uint32_t* sink) {
+  if (threadIdx.x != 0) return;
+  uint32_t i = 0;
+  long long t0 = clock64();
+  for (int k = 0; k < 64; k++) i = __ldcv(chain + i);
+  long long t1 = clock64();
+  for (int k = 0; k < 64; k++) i = __ldcg(chain + i);
+  long long t2 = clock64();
+  for (int k = 0; k < 64; k++) i = __ldca(chain + i);
+  long long t3 = clock64();
+  *sink = i;
+  t[0] = (t1 - t0) / 64; t[1] = (t2 - t1) / 64; t[2] = (t3 - t2) / 64;
+}
+
 int main() {
   uint32_t* st; long long* t; Fr* sink;
   cudaMalloc(&st, 32); cudaMalloc(&t, 64); cudaMalloc(&sink, 32);
@@ -64,6 +79,18 @@ int main() {
     long long h[2];
     cudaMemcpy(h, t, 16, cudaMemcpyDeviceToHost);
     printf("four lanes: absorb(3 blocks) %lld cyc | draw_fr %lld cyc   %s\n", h[0], h[1], cudaGetErrorString(cudaGetLastError()));
+  }
+  {
+    uint32_t h[1024], *d, *sk;
+    for (int i = 0; i < 1024; i++) h[i] = (i * 37 + 11) & 1023;  // a permutation of the 1024 words
+    cudaMalloc(&d, 4096); cudaMalloc(&sk, 4);
+    cudaMemcpy(d, h, 4096, cudaMemcpyHostToDevice);
+    for (int rep = 0; rep < 2; rep++) {
+      kload<<<1, 32>>>(d, t, sk);
+      long long r[3];
+      cudaMemcpy(r, t, 24, cudaMemcpyDeviceToHost);
+      printf("dependent load: ld.cv %lld cyc | ld.cg %lld cyc | ld.ca %lld cyc\n", r[0], r[1], r[2]);
+    }
   }
   return 0;
 }
