@@ -29,11 +29,39 @@ FR = 218882428718392752222464057452572750885483644004160343436982041865758084956
 TAU = 0x1234567890ABCDEF1234567890ABCDEF
 MSM_LIMB_PRODUCTS_PER_POINT = 20480  # 16 windows x (8M + 2S) x 128 32x32->64 products per Montgomery mult
 SC_BYTES_PER_ELEM = 128              # 4 * 32 B per input table element over the whole proof
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the last ncu --set full captures (profiles/r01_ncu_*.txt,
-# 2^24, one GPU): msm_accumulate 27.96 + 1.11 GB (algorithmic 14.5 GB: a 64-byte gather fetches a 128-byte line);
-# sumcheck streaming rounds: round 0 = 1.614 GB, round 1 = 2.392 GB, later rounds halve -> 6.40 GB (algorithmic 6.44 GB)
-MSM_TRAFFIC_BYTES = 28.90e9
-SC_TRAFFIC_BYTES = 6.40e9
+SC_ZC_WEIGHT_BYTES_PER_ENTRY = 64    # eq-factored zero-check: the weight tables E_1, E_2, .. (N/2, N/4, .. entries) are
+                                     # written once and read once each: 2 * 32 B * N = 64 B per entry of ONE table
+
+
+def profile_traffic(kind: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, read from the newest committed
+    `ncu --set full` summary under profiles/ (tools/summarise_profiles.py writes them), 2^24 on one GPU.
+    msm: the single msm_accumulate launch.  sumcheck: the captured launches are round 0 (evaluate only) and round 1
+    (fold fused); the later streaming rounds halve, so the proof's traffic is round0 + 2 * round1 (geometric series,
+    the 2^-k tail below the streamed sizes neglected).  Returns (bytes, source file) or (None, None)."""
+    import glob
+    import re
+    pat = {"msm": "*_ncu_msm_accumulate.txt", "sumcheck": "*_ncu_sc_round_prod.txt"}[kind]
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", pat)))
+    if not files:
+        return None, None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    per_launch, cur = [], None
+    for line in open(files[-1]):
+        if line.startswith("## captured launch"):
+            cur = 0.0
+            per_launch.append(cur)
+        m = re.match(r"dram__bytes_(read|write)\.sum \[(\w+)\] = ([0-9.,]+)", line)
+        if m and per_launch:
+            per_launch[-1] += float(m.group(3).replace(",", "")) * unit.get(m.group(2), 1.0)
+    if not per_launch:
+        return None, None
+    src = os.path.relpath(files[-1], ROOT)
+    if kind == "msm":
+        return per_launch[0], src
+    if len(per_launch) < 2:
+        return None, None
+    return per_launch[0] + 2.0 * per_launch[1], src
 
 
 def peaks():
@@ -98,6 +126,18 @@ def shard_seed(seed: int, first_index: int) -> int:
     return (seed + 4 * first_index * GOLDEN64) & 0xFFFFFFFFFFFFFFFF
 
 
+def workload_config(args, world: int, peer_memory: bool = True) -> dict:
+    """The `config` object of the line: the workload both arms are quoted on (the reference arm times a bounded sample
+    of it and says so in `cpu_baseline.sample`)."""
+    return {"workload": f"KZG commit MSM of 2^{args.log_n} random Fr scalars on a tau-power SRS + linear-time "
+                        f"sumcheck over a degree-3 product of three 2^{args.log_n}-entry tables (BN254)",
+            "log_n": args.log_n, "msm_precomputed_windows": not args.no_precompute,
+            "sharding": f"index ranges / top variables over {world} GPU(s)",
+            "exchange": ("peer mailboxes in HBM over NVLink (CUDA IPC), written by the producing kernel" if peer_memory
+                         else "NCCL all-gather") if world > 1 else "none",
+            "l2": "inputs (>= 1.5 GiB) exceed the 126 MB L2; no flush needed"}
+
+
 def product_expr(q, k):
     e = q.VirtualPolyExpr.Input(0)
     for i in range(1, k):
@@ -150,9 +190,9 @@ def run_reference(args):
         "impl": "reference", "metric": f"KZG MSM points/s (sumcheck field-elems/s in `sumcheck`)", "value": v,
         "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (254-bit modular integer)",
-        "data": "synthetic", "config": {"workload": f"KZG commit MSM + degree-3 sumcheck, CPU sample of the 2^{args.log_n} workload",
-                                         "msm_log_n": args.ref_log_n, "sumcheck_log_n": args.ref_sc_log_n},
-        "cpu_baseline": {"value": v, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
+        "data": "synthetic", "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": v, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample,
+                         "msm_log_n": args.ref_log_n, "sumcheck_log_n": args.ref_sc_log_n},
         "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "sumcheck": {"value": sc_v, "unit": "field-elems/s", "ms_per_step": sc_ms,
                      "e2e": {"value": sc_v, "unit": "field-elems/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
@@ -185,7 +225,21 @@ def cpu_baseline(args):
     co.sumcheck_prove(args.cpu_sc_log_n, tabs, nodes, consts, co.fr1(1), co.transcript_new(b"sumcheck_bench"),
                       max_coeffs=8, threads=1)
     t_sc = time.perf_counter() - t0
+    # BASELINE.json configs[0], literally: KZG commit of a random degree-2^16 polynomial + sumcheck prove over a
+    # 2^16-entry degree-3 product, 1 thread
+    n1 = 1 << 16
+    srs1 = srs[:n1] if srs.shape[0] >= n1 else co.srs_generate(g, co.fr1(TAU), n1, threads=cores)  # kzg.rs:65: <= max degree
+    sc1 = util.rand_fr(n1, 2)
+    t0 = time.perf_counter()
+    co.kzg_commit_reference_shape(srs1, sc1, threads=1)
+    t_c1 = time.perf_counter() - t0
+    tabs1 = [util.rand_fr(n1, 20 + t) for t in range(3)]
+    t0 = time.perf_counter()
+    co.sumcheck_prove(16, tabs1, nodes, consts, co.fr1(1), co.transcript_new(b"sumcheck_bench"), max_coeffs=8, threads=1)
+    t_s1 = time.perf_counter() - t0
     return {
+        "config_1": {"kzg_commit_2_16_s": t_c1, "kzg_commit_points_per_s": n1 / t_c1, "sumcheck_2_16_s": t_s1,
+                     "sumcheck_field_elems_per_s": 3 * n1 / t_s1, "cores": 1},
         "value": n / t_commit, "unit": "points/s", "cores": 1, "kind": "port",
         "sample": (f"KZG::commit (kzg.rs:61-73) of 2^{args.cpu_log_n} coefficients, 1 thread: {t_commit:.2f} s "
                    f"({s_norm:.2f} s per-call SRS normalisation + {s_msm:.2f} s Pippenger); sumcheck prove over three "
@@ -194,6 +248,30 @@ def cpu_baseline(args):
         "sumcheck": {"value": 3 * nsc / t_sc, "unit": "field-elems/s", "cores": 1},
         "host_cores_available": cores,
     }
+
+
+def zc_roofline(rounds_ms, t_loc, hbm_peak, hbm_src, step_ms):
+    """Streaming rounds of the eq-factored zero-check (sc_round_zc): the three tables move 128 B per entry over the proof
+    as in the sumcheck, the weight tables E_1, E_2, .. (built on the device, then halved by additions in the pass that
+    folds the tables) another 64 B per entry of one table."""
+    ms = sum(rounds_ms) / len(rounds_ms)
+    alg = (SC_BYTES_PER_ELEM * 3 + SC_ZC_WEIGHT_BYTES_PER_ENTRY) * t_loc
+    return {"kernel": "sc_round_zc<3> (streaming rounds incl. the weight-table build)", "bound": "hbm",
+            "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak,
+            "kernel_ms": ms, "kernel_share_of_step": ms / step_ms, "traffic": None, "peak_source": hbm_src,
+            "note": "integer-bound like the sumcheck rounds (DESIGN.md section 4): 2 more products per pair for the weight"}
+
+
+def imad_roofline(stats, imad_peak, step_ms, steps):
+    """msm_accumulate over all the MSMs of a multi-MSM step (stats = qz_msm_accumulate_stats over the timed steps):
+    executed limb products against the IMAD.WIDE rate measured in this run, and the kernel's share of the step."""
+    ms, adds, launches = stats
+    if launches == 0 or ms <= 0:
+        return None
+    return {"kernel": f"msm_accumulate ({launches // steps} launches per step)", "bound": "int32-imad", "unit": "T limb-MAC/s",
+            "achieved": adds * 1280 / (ms * 1e-3) / 1e12, "peak": imad_peak / 1e12, "frac": adds * 1280 / (ms * 1e-3) / imad_peak,
+            "kernel_ms": ms / steps, "kernel_share_of_step": ms / steps / step_ms, "mixed_additions_per_step": adds / steps,
+            "traffic": None, "peak_source": "qz_bench_imad measured in this run"}
 
 
 def bench_hyperplonk(ctx, q, log_rows, g_bytes, tau_mont, timed_loop, verify=False):
@@ -252,7 +330,10 @@ def bench_hyperplonk(ctx, q, log_rows, g_bytes, tau_mont, timed_loop, verify=Fal
     kzg = q.KZG.trusted_setup(ctx, max_degree, g_bytes, tau_mont).precompute()
     prover = hp.HyperPlonk.preprocess(ctx, circuits, kzg)
     out = {}
-    ms, launches = timed_loop(lambda: out.__setitem__("p", prover.prove(kzg, witnesses)), 1, 1)
+    out["p"] = prover.prove(kzg, witnesses)  # warm-up proof (untimed)
+    ctx.msm_accumulate_stats(1)
+    ms, launches = timed_loop(lambda: out.__setitem__("p", prover.prove(kzg, witnesses)), 1, 0)
+    acc_stats = ctx.msm_accumulate_stats(-1)
     kzg.srs.free()
     verified = None
     if verify:  # the reference's acceptance criterion (HyperPlonkProof::verify, proof.rs:493-523) restated in oracle/: a
@@ -279,7 +360,7 @@ def bench_hyperplonk(ctx, q, log_rows, g_bytes, tau_mont, timed_loop, verify=Fal
             f"{verify_s:.1f} s on the host after the timed region" if verify else None,
             "gpu_launches": launches, "workload": "HyperPlonk::prove of Fibonacci + modified-Fibonacci transition circuits "
             "(2 witness commits, 2 zero-checks, 2 logup permutation checks, 2 x (cols + public + 5) MLPCS openings)",
-            "final_transcript_state": out["p"].transcript_state.hex()}
+            "final_transcript_state": out["p"].transcript_state.hex(), "_acc_stats": acc_stats, "_ms": ms}
 
 
 def run_gpu(args):
@@ -410,7 +491,8 @@ def run_gpu(args):
 
     zc_err = None
     try:
-        zc_ms, zc_launches = timed_loop(zc_prove, args.steps, args.warmup)
+        zc_rounds_ms: list = []
+        zc_ms, zc_launches = timed_loop(zc_prove, args.steps, args.warmup, zc_rounds_ms)
     except q.QuillError as e:  # an auxiliary leg: report it in the line instead of losing the headline legs above
         if world == 1:
             raise
@@ -431,8 +513,11 @@ def run_gpu(args):
             results["ml_c"] = kzg.commit(poly)
             results["ml_o"] = kzg.open_multilinear(poly, point, q.Transcript(b"mlpcs_bench", ctx))
 
-        ml_ms, ml_launches = timed_loop(commit_open, max(1, args.steps // 2), 1)
-        mlpcs = {"value": ml_ms * 1e-3, "unit": "s per commit+open", "log_n": nm, "gpu_launches": ml_launches // max(1, args.steps // 2),
+        commit_open()  # warm-up (untimed)
+        ctx.msm_accumulate_stats(1)
+        ml_ms, ml_launches = timed_loop(commit_open, max(1, args.steps // 2), 0)
+        ml_stats = ctx.msm_accumulate_stats(-1)
+        mlpcs = {"_acc_stats": ml_stats, "_ms": ml_ms, "_steps": max(1, args.steps // 2), "value": ml_ms * 1e-3, "unit": "s per commit+open", "log_n": nm, "gpu_launches": ml_launches // max(1, args.steps // 2),
                  "workload": f"MultilinearPCS::commit + ::open of a 2^{nm}-entry MLE (6 MSMs, eq table, NTT 2^{nm + 1}, 4 quotients)"}
         poly.free()
 
@@ -451,6 +536,8 @@ def run_gpu(args):
     out_bytes = nv * (33 * 32 + 4 + 32) + 32 + 32 + 64
 
     if rank == 0:
+        msm_traffic, msm_traffic_src = profile_traffic("msm")
+        sc_traffic, sc_traffic_src = profile_traffic("sumcheck")
         acc_avg = sum(acc_ms) / len(acc_ms)
         rounds_avg = sum(rounds_ms) / len(rounds_ms)
         msm_v = n / (msm_ms * 1e-3)
@@ -460,24 +547,25 @@ def run_gpu(args):
             "value": msm_v, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": msm_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32x8 (254-bit modular integer)", "data": "synthetic",
-            "config": {"workload": f"KZG commit MSM of 2^{args.log_n} random Fr scalars on a tau-power SRS + linear-time "
-                                   f"sumcheck over a degree-3 product of three 2^{args.log_n}-entry tables (BN254)",
-                       "log_n": args.log_n, "msm_precomputed_windows": not args.no_precompute, "sharding": f"index ranges / top variables over {world} GPU(s)",
-                       "exchange": ("peer mailboxes in HBM over NVLink (CUDA IPC), written by the producing kernel" if ctx.peer_memory
-                                    else "NCCL all-gather") if world > 1 else "none",
-                       "l2": "inputs (>= 1.5 GiB) exceed the 126 MB L2; no flush needed"},
+            "config": workload_config(args, world, bool(ctx.peer_memory)),
             "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "points/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": n_loc * 32 * world, "d2h_bytes_per_step": 64 * world},
             "roofline": {
+                # frac = the work the kernel EXECUTES (mixed additions x 1280 limb products) against the measured
+                # IMAD.WIDE rate; `canonical` restates SURVEY 8(d)'s 16-window model, which the precomputed-window table
+                # beats by doing fewer additions per point (its fraction can exceed 1 and is not a utilisation)
                 "kernel": "msm_accumulate", "bound": "int32-imad (integer multiply pipe; not hbm / tensor, see DESIGN.md)",
-                "achieved": n_loc * MSM_LIMB_PRODUCTS_PER_POINT / (acc_avg * 1e-3) / 1e12, "peak": imad_peak / 1e12,
-                "unit": "T limb-MAC/s", "frac": n_loc * MSM_LIMB_PRODUCTS_PER_POINT / (acc_avg * 1e-3) / imad_peak,
-                "model": "SURVEY 8(d) canonical model: 16 windows x (8M+2S) x 128 limb products = 20480 per point",
-                "executed": {"window_bits": msm_c, "mixed_adds_per_point": msm_digits, "shared_bucket_set": bool(msm_shared),
-                             "limb_macs_per_point": msm_digits * 1280,
-                             "frac_of_peak": msm_adds * 1280 / (acc_avg * 1e-3) / imad_peak},
+                "achieved": msm_adds * 1280 / (acc_avg * 1e-3) / 1e12, "peak": imad_peak / 1e12,
+                "unit": "T limb-MAC/s", "frac": msm_adds * 1280 / (acc_avg * 1e-3) / imad_peak,
+                "model": f"executed work: {msm_digits:.0f} mixed additions per point (c = {msm_c:.0f}"
+                         f"{', one shared bucket set over precomputed window multiples' if msm_shared else ''}) x (8M + 2S) x 128 "
+                         "limb products = 1280 per addition",
+                "canonical": {"model": "SURVEY 8(d): 16 windows x (8M+2S) x 128 limb products = 20480 per point",
+                              "achieved": n_loc * MSM_LIMB_PRODUCTS_PER_POINT / (acc_avg * 1e-3) / 1e12,
+                              "frac": n_loc * MSM_LIMB_PRODUCTS_PER_POINT / (acc_avg * 1e-3) / imad_peak},
                 "kernel_ms": acc_avg, "kernel_share_of_step": acc_avg / msm_ms,
-                "traffic": MSM_TRAFFIC_BYTES if (world == 1 and args.log_n == 24 and not args.no_precompute) else None,
+                "traffic": msm_traffic if (world == 1 and args.log_n == 24 and not args.no_precompute) else None,
+                "traffic_source": msm_traffic_src if (world == 1 and args.log_n == 24 and not args.no_precompute) else None,
                 "peak_source": "qz_bench_imad (IMAD.WIDE.U32 carry chains) measured in this run"},
             "sumcheck": {
                 "value": sc_v, "unit": "field-elems/s", "ms_per_step": sc_ms, "gpu_launches": sc_launches // args.steps,
@@ -486,7 +574,9 @@ def run_gpu(args):
                 "roofline": {"kernel": "sc_round_prod<3> (streaming rounds, fold fused)", "bound": "hbm",
                              "achieved": SC_BYTES_PER_ELEM * 3 * t_loc / (rounds_avg * 1e-3) / 1e9, "peak": hbm_peak,
                              "unit": "GB/s", "frac": SC_BYTES_PER_ELEM * 3 * t_loc / (rounds_avg * 1e-3) / 1e9 / hbm_peak,
-                             "kernel_ms": rounds_avg, "kernel_share_of_step": rounds_avg / sc_ms, "traffic": SC_TRAFFIC_BYTES if (world == 1 and args.log_n == 24) else None,
+                             "kernel_ms": rounds_avg, "kernel_share_of_step": rounds_avg / sc_ms,
+                             "traffic": sc_traffic if (world == 1 and args.log_n == 24) else None,
+                             "traffic_source": sc_traffic_src if (world == 1 and args.log_n == 24) else None,
                              "peak_source": hbm_src},
             },
             "gpu_launches": msm_launches // args.steps,
@@ -504,12 +594,15 @@ def run_gpu(args):
         if zc_ms is not None:
             line["zerocheck"] = {"value": 3 * n / (zc_ms * 1e-3), "unit": "field-elems/s", "ms_per_step": zc_ms,
                                  "gpu_launches": zc_launches // args.steps,
+                                 "roofline": zc_roofline(zc_rounds_ms, t_loc, hbm_peak, hbm_src, zc_ms),
                                  "workload": f"ZeroCheckProof::prove of f*g*e over three 2^{args.log_n}-entry tables: z drawn on the device, "
                                              "eq-factored rounds (degree-3 sums weighted by the eq table of the remaining variables, "
                                              "times the round's linear eq factor)"}
         if mlpcs:
+            mlpcs["roofline"] = imad_roofline(mlpcs.pop("_acc_stats"), imad_peak, mlpcs.pop("_ms"), mlpcs.pop("_steps"))
             line["mlpcs_commit_open"] = mlpcs
         if hplonk:
+            hplonk["roofline"] = imad_roofline(hplonk.pop("_acc_stats"), imad_peak, hplonk.pop("_ms"), 1)
             line["hyperplonk_prove"] = hplonk
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)

@@ -218,6 +218,12 @@ float qz_last_elapsed_ms(qz_ctx* ctx, int which);
 /* shape of the most recent MSM on this context: which = 0 window bits c, 1 digits (mixed additions) per scalar,
  * 2 whether the precomputed shared bucket set was used (0/1), 3 total mixed additions */
 double qz_last_stat(const qz_ctx* ctx, int which);
+/* msm_accumulate (the MSM's dominant kernel) over MANY calls: reset = 1 starts collecting -- every accumulate launch is
+ * then bracketed by its own CUDA event pair on the context's stream --, reset = 0 reads the totals so far (summed
+ * kernel time in milliseconds, mixed additions executed, launches; synchronises the stream first), reset = -1 reads
+ * and stops.  Lets a caller that runs several MSMs per step (MultilinearPCS::open: 5, HyperPlonk::prove: ~140) report
+ * the kernel's share of the step and its integer-pipe fraction.  Not collecting is the default and costs nothing. */
+int qz_msm_accumulate_stats(qz_ctx* ctx, int reset, double* out_ms, double* out_mixed_additions, uint64_t* out_launches);
 /* integer-pipe micro-benchmark: returns 32x32->64 multiply-accumulates per second sustained by all SMs (the MSM
  * roofline denominator).  variant 0 = IMAD.WIDE.U32 carry chains as used by the field multiplier, 1 = 32-bit IMAD. */
 int qz_bench_imad(qz_ctx* ctx, int variant, double* out_ops_per_s);

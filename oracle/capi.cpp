@@ -60,7 +60,8 @@ void orc_transcript_draw_fr(uint8_t state[32], uint8_t out_mont[32]) {
   memcpy(state, t.state, 32);
 }
 
-// ---- field helpers (field: 0 = Fr, 1 = Fq); op: 0 add, 1 sub, 2 mul, 3 inverse(a), 4 to_mont(a canonical), 5 from_mont
+// ---- field helpers (field: 0 = Fr, 1 = Fq); op: 0 add, 1 sub, 2 mul, 3 inverse(a), 4 to_mont(a canonical), 5 from_mont,
+// 6 inverse by Fermat (the cross-check of 3)
 void orc_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
   for (size_t i = 0; i < n; i++) {
     if (field == 0) {
@@ -71,6 +72,7 @@ void orc_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t
         case 2: r = x * y; break;
         case 3: r = x.inverse(); break;
         case 4: r = Fr::from_canonical(x.l); break;
+        case 6: r = x.inverse_fermat(); break;
         default: x.to_canonical(r.l); break;
       }
       memcpy(out + 32 * i, r.l, 32);
@@ -84,6 +86,7 @@ void orc_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t
         case 2: r = x * y; break;
         case 3: r = x.inverse(); break;
         case 4: r = Fq::from_canonical(x.l); break;
+        case 6: r = x.inverse_fermat(); break;
         default: x.to_canonical(r.l); break;
       }
       memcpy(out + 32 * i, r.l, 32);

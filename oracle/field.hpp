@@ -180,11 +180,74 @@ struct Fp {
     }
     return acc;
   }
-  Fp inverse() const {  // Fermat; 0 -> 0
+  Fp inverse_fermat() const {  // a^(p-2); 0 -> 0.  Kept as the cross-check of inverse() (tests/test_oracle.py, field op 5)
     u64 e[4];
     memcpy(e, P::MOD, 32);
     e[0] -= 2;
     return pow(e);
+  }
+  // Field::inverse.  ark-ff 0.5.0 inverts with a binary extended Euclid on the Montgomery limbs (Guajardo, Kumar, Paar,
+  // Pelzl, alg. 16) -- a few microseconds, not the 380 products of a Fermat power.  The restatement uses the same
+  // family in Kaliski's form ("The Montgomery inverse and its applications", 1995), whose loop needs no modular
+  // halving: phase 1 on plain integers (u, v, r, s) = (p, x, 0, 1) ends with r = -x^-1 2^k mod p, 254 <= k <= 508;
+  // phase 2 removes 2^k and restores Montgomery form with two products.  The value is unique, so any algorithm gives
+  // the reference's bytes; the choice only matters for the CPU baseline's per-commit normalisation leg
+  // (kzg.rs:67-71), which a Fermat inverse made 4-6x slower than arkworks'.  0 -> 0.
+  Fp inverse() const {
+    if (is_zero()) return zero();
+    u64 u[4], v[4], r[4] = {0, 0, 0, 0}, t[4] = {1, 0, 0, 0};
+    memcpy(u, P::MOD, 32);
+    memcpy(v, l, 32);  // x = aR as an integer < p
+    auto shr1 = [](u64 x[4]) {
+      x[0] = (x[0] >> 1) | (x[1] << 63);
+      x[1] = (x[1] >> 1) | (x[2] << 63);
+      x[2] = (x[2] >> 1) | (x[3] << 63);
+      x[3] >>= 1;
+    };
+    auto shl1 = [](u64 x[4]) {
+      x[3] = (x[3] << 1) | (x[2] >> 63);
+      x[2] = (x[2] << 1) | (x[1] >> 63);
+      x[1] = (x[1] << 1) | (x[0] >> 63);
+      x[0] <<= 1;
+    };
+    int k = 0;
+    while (v[0] | v[1] | v[2] | v[3]) {
+      if (!(u[0] & 1)) {
+        shr1(u);
+        shl1(t);
+      } else if (!(v[0] & 1)) {
+        shr1(v);
+        shl1(r);
+      } else if (!geq(v, u)) {  // u > v
+        sub_raw(u, v);
+        shr1(u);
+        add_raw(r, t);
+        shl1(t);
+      } else {
+        sub_raw(v, u);
+        shr1(v);
+        add_raw(t, r);
+        shl1(r);
+      }
+      k++;
+    }
+    if (geq(r, P::MOD)) sub_raw(r, P::MOD);
+    u64 neg[4];
+    memcpy(neg, P::MOD, 32);
+    sub_raw(neg, r);  // x^-1 2^k mod p
+    // (aR)^-1 2^k -> a^-1 R = (aR)^-1 R^2: multiply by 2^(512 - k) = R2 * 2^e / R^2 with e = 512 - k in [4, 258]
+    int e = 512 - k, extra = 0;
+    if (e > 255) {
+      extra = e - 255;
+      e = 255;
+    }
+    u64 pw[4] = {0, 0, 0, 0};
+    pw[e / 64] = (u64)1 << (e % 64);  // any 256-bit value may be the second operand of the CIOS product
+    Fp out;
+    mont_mul(out.l, neg, C().r2);
+    mont_mul(out.l, out.l, pw);
+    for (int i = 0; i < extra; i++) out = out.dbl();
+    return out;
   }
 };
 

@@ -25,7 +25,7 @@ SYMBOLS = [
     "qz_compute_s_polynomial",
     "qz_sumcheck_prove", "qz_zerocheck_prove", "qz_eq_table", "qz_logup_denominators",
     "qz_comm_unique_id", "qz_comm_init", "qz_comm_peer_memory", "qz_msm_sharded", "qz_sumcheck_prove_sharded", "qz_zerocheck_prove_sharded", "qz_comm_allgather_host",
-    "qz_last_elapsed_ms", "qz_last_stat", "qz_bench_imad", "qz_bench_fp_mul",
+    "qz_last_elapsed_ms", "qz_last_stat", "qz_msm_accumulate_stats", "qz_bench_imad", "qz_bench_fp_mul",
     "qz_test_field_op", "qz_test_fold", "qz_test_g1_add", "qz_test_g1_mul",
 ]
 
@@ -115,6 +115,7 @@ def load():
     lib.qz_last_elapsed_ms.restype = C.c_float
     lib.qz_last_stat.argtypes = [vp, i32]
     lib.qz_last_stat.restype = C.c_double
+    lib.qz_msm_accumulate_stats.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     lib.qz_bench_imad.argtypes = [vp, i32, C.POINTER(C.c_double)]
     lib.qz_bench_fp_mul.argtypes = [vp, i32, C.POINTER(C.c_double)]
     lib.qz_test_field_op.argtypes = [vp, i32, i32, vp, vp, vp, sz]

@@ -74,6 +74,13 @@ class Context:
     def last_stat(self, which: int) -> float:
         return float(self.lib.qz_last_stat(self.h, which))
 
+    def msm_accumulate_stats(self, reset: int = 0):
+        """(summed msm_accumulate kernel ms, mixed additions, launches) since collection was started with reset=1;
+        reset=-1 reads and stops (qz_msm_accumulate_stats)."""
+        ms, adds, n = C.c_double(), C.c_double(), C.c_uint64()
+        self.check(self.lib.qz_msm_accumulate_stats(self.h, reset, C.byref(ms), C.byref(adds), C.byref(n)))
+        return ms.value, adds.value, int(n.value)
+
     # -- device buffers ------------------------------------------------------------------------------------------
     def alloc(self, nbytes: int) -> "DeviceBuffer":
         p = C.c_void_p()

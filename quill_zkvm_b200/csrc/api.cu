@@ -238,6 +238,11 @@ void qz_ctx_destroy(qz_ctx* c) {
   cudaEventDestroy(c->ev_call1);
   cudaEventDestroy(c->ev_k0);
   cudaEventDestroy(c->ev_k1);
+  if (c->acc_nonzero_dev) cudaFree(c->acc_nonzero_dev);
+  for (auto& pr : c->acc_ring) {
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
   c->destroy_prep_stream();
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -247,6 +252,31 @@ const char* qz_last_error(const qz_ctx* c) { return c ? c->err.c_str() : "null c
 uint64_t qz_kernel_launches(const qz_ctx* c) { return c ? c->launches : 0; }
 double qz_last_stat(const qz_ctx* c, int which) { return c && which >= 0 && which < 4 ? c->last_stat[which] : -1.0; }
 float qz_last_elapsed_ms(qz_ctx* c, int which) { return c && which >= 0 && which < 2 ? c->last_ms[which] : -1.f; }
+
+int qz_msm_accumulate_stats(qz_ctx* c, int reset, double* out_ms, double* out_mixed_additions, uint64_t* out_launches) {
+  if (!c) return QZ_ERR_INVALID_ARG;
+  QZ_CUDA(c, cudaSetDevice(c->device));
+  QZ_CUDA(c, cudaStreamSynchronize(c->stream));
+  double total = 0;
+  for (size_t i = 0; i < c->acc_ring_used; i++) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->acc_ring[i].first, c->acc_ring[i].second) == cudaSuccess) total += ms;
+    else cudaGetLastError();
+  }
+  if (out_ms) *out_ms = total;
+  unsigned long long nz = 0;
+  if (c->acc_nonzero_dev) QZ_CUDA(c, cudaMemcpy(&nz, c->acc_nonzero_dev, 8, cudaMemcpyDeviceToHost));
+  if (out_mixed_additions) *out_mixed_additions = (double)nz;
+  if (out_launches) *out_launches = c->acc_ring_used;
+  if (reset) {
+    c->acc_ring_used = 0;
+    c->acc_ring_adds = 0;
+    c->acc_ring_on = reset > 0;  // reset = 1: start (or restart) collecting; reset = -1: stop
+    if (c->acc_ring_on && !c->acc_nonzero_dev) QZ_CUDA(c, cudaMalloc(&c->acc_nonzero_dev, 8));
+    if (c->acc_nonzero_dev) QZ_CUDA(c, cudaMemset(c->acc_nonzero_dev, 0, 8));
+  }
+  return QZ_OK;
+}
 
 int qz_ctx_sync(qz_ctx* c) {
   if (!c) return QZ_ERR_INVALID_ARG;

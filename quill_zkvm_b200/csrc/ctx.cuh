@@ -1,6 +1,7 @@
 // Context shared by the C-ABI entry points: one device, one stream, a scratch arena, cached constants.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only; ranges are no-ops unless a profiler injects itself
 #include <cstdint>
 #include <cstdio>
 #include <map>
@@ -9,6 +10,14 @@
 #include "../../include/quill_b200.h"
 
 struct ncclComm;
+
+// NVTX range per phase of a call: the enqueue of the phase's kernels, visible in nsys / ncu --nvtx
+struct QzRange {
+  explicit QzRange(const char* name) { nvtxRangePushA(name); }
+  ~QzRange() { nvtxRangePop(); }
+  QzRange(const QzRange&) = delete;
+  QzRange& operator=(const QzRange&) = delete;
+};
 
 struct qz_ctx {
   int device = 0;
@@ -103,6 +112,26 @@ struct qz_ctx {
     }
     prep_stream = nullptr;
   }
+  // every msm_accumulate launch since the last qz_msm_accumulate_stats(reset) is bracketed by an event pair of this ring
+  // (grown on demand, reused after a reset), so that a caller that runs many MSMs per step (MLPCS open: 5, HyperPlonk:
+  // ~140) can report the dominant kernel's share and its integer-pipe fraction for the whole step
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> acc_ring;
+  size_t acc_ring_used = 0;
+  double acc_ring_adds = 0;  // sorted entries of those launches (upper bound of the additions: zero digits are skipped)
+  unsigned long long* acc_nonzero_dev = nullptr;  // non-zero digits = additions executed, counted by msm_digits
+  bool acc_ring_on = false;
+  int acc_ring_next(cudaEvent_t* e0, cudaEvent_t* e1) {
+    if (!acc_ring_on) return 1;
+    if (acc_ring_used == acc_ring.size()) {
+      cudaEvent_t a = nullptr, b = nullptr;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return 1;
+      acc_ring.emplace_back(a, b);
+    }
+    *e0 = acc_ring[acc_ring_used].first;
+    *e1 = acc_ring[acc_ring_used].second;
+    acc_ring_used++;
+    return 0;
+  }
   float last_ms[2] = {0.f, 0.f};
   double last_stat[4] = {0, 0, 0, 0};  // last MSM: window bits, digits per scalar, shared bucket set (0/1), mixed additions
   float kernel_ms_accum = 0.f;
@@ -128,8 +157,17 @@ struct qz_ctx {
     else
       snprintf(buf, sizeof buf, "%s", what);
     err = buf;
+    // An entry point may fail after it enqueued copies from the caller's buffers or kernels on the prep stream: drain
+    // both before the caller sees the error, so that it may free or reuse its buffers and the next call's arena reset
+    // cannot hand out scratch that is still being written.
+    if (stream_busy_possible) {
+      if (stream) cudaStreamSynchronize(stream);
+      if (prep_stream) cudaStreamSynchronize(prep_stream);
+      cudaGetLastError();
+    }
     return status;
   }
+  bool stream_busy_possible = true;
 
   void arena_reset() {
     if (blocks.size() > 1) {  // coalesce into one block for the next call

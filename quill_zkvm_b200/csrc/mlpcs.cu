@@ -259,6 +259,7 @@ static int get_twiddles(qz_ctx* ctx, int log_m, Fr** out) {
 
 int ntt_device(qz_ctx* ctx, uint4* data, int log_m, bool inverse) {
   if (log_m == 0) return QZ_OK;
+  QzRange nvtx_call(inverse ? "qz:ntt:inverse" : "qz:ntt:forward");
   if (log_m > 28) return ctx->fail(QZ_ERR_INVALID_ARG, "NTT size exceeds the two-adicity of Fr (2^28)");
   Fr* W = nullptr;
   int rc = get_twiddles(ctx, log_m, &W);
@@ -287,6 +288,7 @@ int ntt_device(qz_ctx* ctx, uint4* data, int log_m, bool inverse) {
 
 // S polynomial of (f, n) and (g, m) on the device: writes max(n, m) - 1 coefficients (not trimmed) to S
 int s_polynomial_device(qz_ctx* ctx, const uint4* f, size_t n, const uint4* g, size_t m_len, uint4* S) {
+  QzRange nvtx_call("qz:mlpcs:s-polynomial");
   const uint64_t L = std::max(n, m_len);
   if (L < 2) return QZ_OK;
   int log_m = 1;
@@ -364,6 +366,7 @@ static int mlpcs_begin_device(qz_ctx* ctx, const qz_srs* srs, const uint4* pdev,
                               size_t n_point, Fr* d_point, uint4* d_pr, uint4* d_s, uint8_t* d_eval, uint8_t* d_scomm,
                               uint64_t* s_commit_len) {
   cudaStream_t st = ctx->stream;
+  QzRange nvtx_call("qz:mlpcs:begin (P_r, evaluation, S, commit S)");
   // trimmed length of P_r from the point alone: coefficient j vanishes iff some bit i of j is set with r_i = 0 or clear
   // with r_i = 1, so the last non-zero coefficient is j = sum_{r_i != 0} 2^i (always non-zero)
   uint64_t pr_len = 1;
@@ -406,6 +409,7 @@ static int mlpcs_begin_device(qz_ctx* ctx, const qz_srs* srs, const uint4* pdev,
 // finish: poly_opening, poly_opening_inv, s_opening, s_opening_inv at d_r[0] = r and d_r[1] = 1/r (mlpcs.rs:109-113)
 static int mlpcs_finish_device(qz_ctx* ctx, const qz_srs* srs, const uint4* pdev, size_t n, const uint4* d_s,
                                uint64_t s_commit_len, const Fr* d_r, uint8_t* d_open) {
+  QzRange nvtx_call("qz:mlpcs:finish (4 KZG openings)");
   for (int i = 0; i < 4; i++) {
     uint8_t* o = d_open + 128 * i;
     const Fr* x = d_r + (i & 1);

@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <new>
 #include "ctx.cuh"
 #include "ec.cuh"
@@ -40,27 +41,39 @@ constexpr uint32_t KEY_NONE = 0xffffffffu;
 // index of its first bucket set: segments are told apart by the key's high bits exactly as windows are.
 __global__ void __launch_bounds__(256) msm_digits(const uint4* scalars, uint32_t n, uint32_t index_base, int c, int W,
                                                   uint32_t collapse_stride, uint32_t set_base, uint32_t* keys,
-                                                  uint32_t* vals) {
+                                                  uint32_t* vals, unsigned long long* nonzero_digits) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const Fr k = fp_from_mont<FrParams>(fp_load<FrParams>(scalars + 2 * (size_t)i));
-  const uint32_t mask = (1u << c) - 1, half = 1u << (c - 1);
-  uint32_t carry = 0;
-  for (int w = 0; w < W; w++) {
-    const int bit = w * c, limb = bit >> 5, off = bit & 31;
-    uint64_t two = 0;
-    if (limb < 8) two = k.v[limb];
-    if (limb + 1 < 8) two |= (uint64_t)k.v[limb + 1] << 32;
-    uint32_t d = ((uint32_t)(two >> off) & mask) + carry;
-    uint32_t neg = 0;
-    carry = 0;
-    if (d > half) {  // d in (2^(c-1), 2^c]  ->  -(2^c - d), carry one into the next window
-      d = (1u << c) - d;
-      neg = 1;
-      carry = 1;
+  uint32_t nz = 0;
+  if (i < n) {
+    const Fr k = fp_from_mont<FrParams>(fp_load<FrParams>(scalars + 2 * (size_t)i));
+    const uint32_t mask = (1u << c) - 1, half = 1u << (c - 1);
+    uint32_t carry = 0;
+    for (int w = 0; w < W; w++) {
+      const int bit = w * c, limb = bit >> 5, off = bit & 31;
+      uint64_t two = 0;
+      if (limb < 8) two = k.v[limb];
+      if (limb + 1 < 8) two |= (uint64_t)k.v[limb + 1] << 32;
+      uint32_t d = ((uint32_t)(two >> off) & mask) + carry;
+      uint32_t neg = 0;
+      carry = 0;
+      if (d > half) {  // d in (2^(c-1), 2^c]  ->  -(2^c - d), carry one into the next window
+        d = (1u << c) - d;
+        neg = 1;
+        carry = 1;
+      }
+      keys[(size_t)w * n + i] = ((set_base + (collapse_stride ? 0u : (uint32_t)w)) << c) | d;
+      vals[(size_t)w * n + i] = ((uint32_t)w * collapse_stride + index_base + i) | (neg << 31);
+      nz += d != 0;
     }
-    keys[(size_t)w * n + i] = ((set_base + (collapse_stride ? 0u : (uint32_t)w)) << c) | d;
-    vals[(size_t)w * n + i] = ((uint32_t)w * collapse_stride + index_base + i) | (neg << 31);
+  }
+  if (nonzero_digits) {  // measurement (qz_msm_accumulate_stats): the additions msm_accumulate will execute
+    __shared__ uint32_t s_nz;
+    if (threadIdx.x == 0) s_nz = 0;
+    __syncthreads();
+    nz = __reduce_add_sync(0xffffffffu, nz);
+    if ((threadIdx.x & 31) == 0 && nz) atomicAdd(&s_nz, nz);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_nz) atomicAdd(nonzero_digits, (unsigned long long)s_nz);
   }
 }
 
@@ -619,6 +632,7 @@ static int segment_weights(bool host_scalars, size_t n, double* w) {
 int msm_run(qz_ctx* ctx, const qz_srs* srs, uint4* scalars_dev, const void* scalars_host, size_t n,
             uint8_t* out_xyzz_dev, uint8_t* out_affine_dev) {
   cudaStream_t st = ctx->stream;
+  QzRange nvtx_call("qz:msm");
   ctx->acc_launches = 0;
   if (n == 0) {  // empty sum = identity (reachable: commit(&[]) for the quotient of a constant, mlpcs.rs:321-393)
     if (out_xyzz_dev) QZ_CUDA(ctx, cudaMemsetAsync(out_xyzz_dev, 0, 128, st));
@@ -718,11 +732,13 @@ int msm_run(qz_ctx* ctx, const qz_srs* srs, uint4* scalars_dev, const void* scal
   for (int s = 0; s < S; s++) {
     const size_t lo = seg_lo[s], ns = seg_lo[s + 1] - lo;
     const uint64_t off = (uint64_t)Wd * lo, ms = (uint64_t)Wd * ns;
+    std::unique_ptr<QzRange> nvtx_prep(new QzRange("qz:msm:digits+sort"));
     if (scalars_host)
       QZ_CUDA(ctx, cudaMemcpyAsync(scalars_dev + 2 * lo, (const uint8_t*)scalars_host + 32 * lo, 32 * ns,
                                    cudaMemcpyHostToDevice, ps));
     QZ_LAUNCH_ON(ctx, ps, msm_digits, (unsigned)((ns + 255) / 256), 256, 0, scalars_dev + 2 * lo, (uint32_t)ns,
-                 (uint32_t)lo, c, Wd, collapsed ? (uint32_t)srs->n : 0u, (uint32_t)(s * W), keys + off, vals + off);
+                 (uint32_t)lo, c, Wd, collapsed ? (uint32_t)srs->n : 0u, (uint32_t)(s * W), keys + off, vals + off,
+                 ctx->acc_ring_on ? ctx->acc_nonzero_dev : nullptr);
     cub::DoubleBuffer<uint32_t> dk(keys + off, keys2 + off), dv(vals + off, vals2 + off);
     QZ_CUDA(ctx, cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, dk, dv, (int64_t)ms, 0, key_bits, ps));
     ctx->launches += 2 + (key_bits + 7) / 8;  // CUB: histogram + one onesweep pass per 8 key bits (approximate)
@@ -730,14 +746,24 @@ int msm_run(qz_ctx* ctx, const qz_srs* srs, uint4* scalars_dev, const void* scal
       QZ_CUDA(ctx, cudaEventRecord(ctx->ev_seg_ready[s], ps));
       QZ_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_seg_ready[s], 0));
     }
+    nvtx_prep.reset();
+    QzRange nvtx_acc("qz:msm:accumulate");
+    cudaEvent_t ring0 = nullptr, ring1 = nullptr;
+    const bool ring = ctx->acc_ring_next(&ring0, &ring1) == 0;
+    if (ring) QZ_CUDA(ctx, cudaEventRecord(ring0, st));
     QZ_CUDA(ctx, cudaEventRecord(S > 1 ? ctx->ev_acc0[s] : ctx->ev_k0, st));
     QZ_LAUNCH(ctx, msm_accumulate, (unsigned)((chunk_base[s + 1] - chunk_base[s] + ACC_THREADS - 1) / ACC_THREADS),
               ACC_THREADS, 0, dk.Current(), dv.Current(), ms, chunk_len, bases, c, buckets,
               ppts_a + chunk_base[s] * 256, pkeys_a + 2 * chunk_base[s]);
     QZ_CUDA(ctx, cudaEventRecord(S > 1 ? ctx->ev_acc1[s] : ctx->ev_k1, st));
+    if (ring) {
+      QZ_CUDA(ctx, cudaEventRecord(ring1, st));
+      ctx->acc_ring_adds += (double)ms;  // sorted entries; the additions executed are counted by msm_digits
+    }
   }
   ctx->acc_launches = S > 1 ? S : 0;
   {  // merge partial runs level by level until one chunk holds them all (one list: the segments' keys ascend)
+    QzRange nvtx_parts("qz:msm:partial-runs");
     const uint32_t* kin = pkeys_a;
     const uint8_t* pin = ppts_a;
     uint32_t* kout = pkeys_b;
@@ -763,6 +789,7 @@ int msm_run(qz_ctx* ctx, const qz_srs* srs, uint4* scalars_dev, const void* scal
       pout = const_cast<uint8_t*>(tp);
     }
   }
+  QzRange nvtx_red("qz:msm:bucket-reduce+combine");
   if (S > 1) QZ_LAUNCH(ctx, msm_bucket_merge, (n_slots + 127) / 128, 128, 0, buckets, n_slots, S);
   QZ_LAUNCH(ctx, msm_bucket_reduce, (red_threads + 127) / 128, 128, 0, buckets, c, W, seg, partial);
   {  // per window: per_window_parts partial sums -> 1
@@ -815,6 +842,7 @@ int kzg_open_device(qz_ctx* ctx, const qz_srs* srs, const uint4* pdev, size_t n_
     QZ_CUDA(ctx, cudaMemsetAsync(proof_affine_dev, 0, 64, st));
     return QZ_OK;
   }
+  QzRange nvtx_call("qz:kzg_open");
   auto mark = ctx->arena_mark();
   const uint64_t n = n_coeffs, nchunks = (n + OPEN_CHUNK - 1) / OPEN_CHUNK;
   const int group = 64;

@@ -13,6 +13,7 @@
 //   * once a table is down to 2^SC_TAIL_LOG elements a single block finishes all remaining rounds in one launch.
 #include <algorithm>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <vector>
 #ifdef QZ_SC_TRACE
@@ -494,11 +495,11 @@ QZ_DEV void mid_block_pass(const ScTables& view, uint64_t first, uint64_t step, 
 // the items and approach the multiplier's throughput.  The plan (blocks per round, pairs per block) is made by the
 // host, which also sizes the grid with it, and travels as a kernel argument.
 constexpr int SC_TILE_ELEMS = 512;  // shared-memory tile of the split pass, in field elements (16 KiB)
+constexpr int SC_SPLIT_MAX_CHUNK = 128;  // pairs per block up to which a round runs the split pass
 struct ScMidPlan {
   uint16_t nblk[SC_MAX_VARS];    // blocks that work on round j of this launch
   uint16_t future[SC_MAX_VARS];  // max of nblk over rounds >= j: blocks beyond it leave the kernel
-  uint32_t chunk[SC_MAX_VARS];   // pairs per block (split rounds)
-  uint32_t split;                // 1: rounds run the split pass (the shape fits), 0: whole pairs per thread
+  uint32_t chunk[SC_MAX_VARS];   // split rounds: pairs per block; 0: the round keeps whole pairs per thread
   uint32_t tile;                 // pairs per tile of the split pass
 };
 // does the shape fit the split pass, and with which tile?  k tables, at most d + 1 evaluation points
@@ -512,7 +513,6 @@ inline int mid_tile_pairs(int k, int d) {
 inline unsigned int mid_make_plan(ScMidPlan& plan, uint64_t size, int pending, int k, int d, unsigned int cap, int G) {
   memset(&plan, 0, sizeof plan);
   const int tile = mid_tile_pairs(k, d);
-  plan.split = tile > 0;
   plan.tile = (uint32_t)tile;
   bool gathered = G == 1;
   int j = 0;
@@ -523,12 +523,17 @@ inline unsigned int mid_make_plan(ScMidPlan& plan, uint64_t size, int pending, i
     }
     if (size <= 1 || (pending && size == 2)) break;
     const uint64_t n_pairs = pending ? size / 4 : size / 2;
-    // split: at least 32 pairs per block (below that the round is two product latencies whatever the count);
-    // whole pairs: one pair per thread
-    const uint64_t unit = plan.split ? 32 : SC_THREADS;
-    uint64_t nb = std::max<uint64_t>(1, std::min<uint64_t>((n_pairs + unit - 1) / unit, cap));
-    const uint64_t ch = (n_pairs + nb - 1) / nb;
-    nb = (n_pairs + ch - 1) / ch;
+    // split: at least 32 pairs per block (below that the round is two product latencies whatever the count).  Once a
+    // block would get more than SC_SPLIT_MAX_CHUNK pairs its multiplier is busy either way and whole pairs per thread
+    // (one pair per thread and more) need no tiles, no barriers and one product less per pair in round 0.
+    uint64_t nb = std::max<uint64_t>(1, std::min<uint64_t>((n_pairs + 31) / 32, cap));
+    uint64_t ch = (n_pairs + nb - 1) / nb;
+    if (tile > 0 && ch <= (uint64_t)SC_SPLIT_MAX_CHUNK) {
+      nb = (n_pairs + ch - 1) / ch;
+    } else {
+      nb = std::max<uint64_t>(1, std::min<uint64_t>((n_pairs + SC_THREADS - 1) / SC_THREADS, cap));
+      ch = 0;
+    }
     plan.nblk[j] = (uint16_t)nb;
     plan.chunk[j] = (uint32_t)ch;
     if (pending) size >>= 1;
@@ -724,8 +729,8 @@ __global__ void __launch_bounds__(SC_THREADS) sc_mid(ScTables tabs, ScTailBufs b
     }
     if (size <= 1 || (pending_fold && size == 2)) break;
     const uint64_t n_pairs = pending_fold ? size / 4 : size / 2;
-    const bool split = plan.split != 0;
     const uint64_t chunk = plan.chunk[pj];
+    const bool split = chunk != 0;
     const unsigned int nblk = plan.nblk[pj];
     const bool skip1 = pending_fold && d >= 1;  // X = 1 from the running claim (ProdAcc)
     const int ns = skip1 ? d : d + 1;
@@ -1258,6 +1263,7 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
   if (zerocheck && num_vars && !out_z) return ctx->fail(QZ_ERR_INVALID_ARG, "out_z is null");
   QZ_CUDA(ctx, cudaSetDevice(ctx->device));
   std::lock_guard<std::recursive_mutex> fold_table_guard(g_fold_table_lock[ctx->device & 15]);
+  QzRange nvtx_call(zerocheck ? "qz:zerocheck_prove" : "qz:sumcheck_prove");
   ctx->arena_reset();
 
   // h, or h_hat = Mul(h, Input(eq)) with eq appended as the last store polynomial (zerocheck.rs:27-29)
@@ -1369,8 +1375,13 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
   // streaming rounds run while a rank's table has more than 2^SC_MID_LOG entries (with peer mailboxes or one GPU; the
   // NCCL fallback streams down to the gather size), then sc_mid takes every remaining round
   const bool mid_sharded = G == 1 || comm_has_peers(ctx);
+  static const int mid_log = [] {  // QZ_SC_MID_LOG: measurement switch for the hand-over size
+    const char* e = getenv("QZ_SC_MID_LOG");
+    const int v = e ? atoi(e) : SC_MID_LOG;
+    return v >= SC_TAIL_LOG && v <= 24 ? v : SC_MID_LOG;
+  }();
   auto streaming = [&](uint64_t sz) {
-    return mid_sharded ? sz > ((uint64_t)1 << SC_MID_LOG) : sz * G > ((uint64_t)1 << SC_TAIL_LOG);
+    return mid_sharded ? sz > ((uint64_t)1 << mid_log) : sz * G > ((uint64_t)1 << SC_TAIL_LOG);
   };
   const bool zc_fast = zerocheck && eq_slot >= 0 && cp.product_k >= 2 && cp.product_k <= 4 && streaming(N) &&
                        !getenv("QZ_ZC_STREAM_EQ");
@@ -1420,6 +1431,7 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
     // but +10..20 us on the rounds that stream 2^21 entries or more, so only the short rounds are chained this way.
     const bool pdl_ok = ctx->pdl && (G == 1 || comm_has_peers(ctx));
     ctx->kernel_ms_accum = 0.f;
+    std::unique_ptr<QzRange> nvtx_stream(new QzRange("qz:sumcheck:streaming-rounds"));
     QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k0, st));
     if (zc_fast) {
       const int K = cp.product_k - 1;  // factors of h; the eq factor is carried by the weights
@@ -1610,6 +1622,8 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
       round++;
     }
     QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k1, st));
+    nvtx_stream.reset();
+    QzRange nvtx_mid("qz:sumcheck:short-rounds");
     ScTailBufs tb;
     memset(&tb, 0, sizeof tb);
     int mid_G = G;

@@ -115,6 +115,7 @@ extern "C" {
     // ---- measurement and test hooks
     pub fn qz_last_elapsed_ms(ctx: *mut qz_ctx, which: i32) -> f32;
     pub fn qz_last_stat(ctx: *const qz_ctx, which: i32) -> f64;
+    pub fn qz_msm_accumulate_stats(ctx: *mut qz_ctx, reset: i32, out_ms: *mut f64, out_mixed_additions: *mut f64, out_launches: *mut u64) -> i32;
     pub fn qz_bench_imad(ctx: *mut qz_ctx, variant: i32, out_ops_per_s: *mut f64) -> i32;
     pub fn qz_bench_fp_mul(ctx: *mut qz_ctx, field: i32, out_muls_per_s: *mut f64) -> i32;
     pub fn qz_test_field_op(ctx: *mut qz_ctx, field: i32, op: i32, a: *const u8, b: *const u8, out: *mut u8, n: usize) -> i32;

@@ -27,6 +27,22 @@ def test_constants_match_survey():
     assert int.from_bytes(one.tobytes(), "little") == (1 << 256) % FR
 
 
+@pytest.mark.parametrize("field,mod", [(0, FR), (1, FQ)])
+def test_inverse_binary_euclid_matches_fermat_and_python(field, mod):
+    """Field::inverse of the oracle is the binary extended Euclid of ark-ff (oracle/field.hpp); it must agree with the
+    Fermat power it replaced and with Python's modular inverse, on random values and on the edge values."""
+    rnd = random.Random(1234 + field)
+    vals = [0, 1, 2, mod - 1, mod - 2, (mod + 1) // 2, 1 << 255 % mod] + [rnd.randrange(mod) for _ in range(200)]
+    R = 1 << 256
+    mont = np.frombuffer(b"".join((v * R % mod).to_bytes(32, "little") for v in vals), dtype=np.uint8).reshape(-1, 32)
+    inv = co.field_op(field, 3, mont)
+    fermat = co.field_op(field, 6, mont)
+    assert np.array_equal(inv, fermat)
+    for v, row in zip(vals, inv):
+        got = int.from_bytes(row.tobytes(), "little") * pow(R, -1, mod) % mod
+        assert got == (pow(v, -1, mod) if v else 0)
+
+
 @pytest.mark.parametrize("n", [0, 1, 63, 64, 65, 1023, 1024, 1025, 2048, 3073, 9000])
 def test_blake3_matches_wheel(n):
     rnd = random.Random(n)
