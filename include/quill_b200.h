@@ -192,6 +192,12 @@ int qz_comm_peer_memory(const qz_ctx* ctx);
  * commitment (partial sums are gathered as raw limbs and added with the group law, never ncclSum). */
 int qz_msm_sharded(qz_ctx* ctx, const qz_srs* srs_shard, const void* scalars_shard, size_t n_scalars,
                    int scalars_on_device, uint8_t out_xy[64]);
+/* The same product when every rank holds the WHOLE SRS and the WHOLE scalar vector (the witness and logup-denominator
+ * commits of HyperPlonk::prove, proof.rs:270-276 / multiset_check.rs:98-99, at N > 1): rank g multiplies the index
+ * range [n g / G, n (g + 1) / G) and every rank receives KZG::commit(scalars).  Without a communicator it is
+ * qz_kzg_commit.  QZ_ERR_DEGREE when n_scalars exceeds the SRS (kzg.rs:65). */
+int qz_msm_split(qz_ctx* ctx, const qz_srs* srs, const void* scalars, size_t n_scalars, int scalars_on_device,
+                 uint8_t out_xy[64]);
 /* Sharded sumcheck: rank g holds elements [g*2^m, (g+1)*2^m) of every table, m = num_vars - log2(nranks), i.e. the
  * tables are split by the top variables so every (2p, 2p+1) pair is local (sumcheck.rs:56-57).  Per round the ranks
  * exchange (deg+1) partial sums; all ranks run the same transcript and return the same proof. */

@@ -361,6 +361,17 @@ class KZG:
         self.ctx.check(self.ctx.lib.qz_msm_sharded(self.ctx.h, self.srs.h, ptr, n, int(on_dev), _ptr(out)))
         return out
 
+    def commit_split(self, coeffs) -> np.ndarray:
+        """KZG::commit when every rank holds the whole SRS and the whole polynomial: each multiplies its index range and
+        all receive the commitment (qz_msm_split); on one rank it is `commit`."""
+        ptr, on_dev, n = self._coeffs(coeffs)
+        out = np.zeros(64, dtype=np.uint8)
+        rc = self.ctx.lib.qz_msm_split(self.ctx.h, self.srs.h, ptr, n, int(on_dev), _ptr(out))
+        if rc == _lib.QZ_ERR_DEGREE:
+            raise AssertionError("Polynomial degree exceeds max degree")
+        self.ctx.check(rc)
+        return out
+
     def open(self, polynomial, x: np.ndarray) -> KZGOpeningProof:
         """kzg.rs:75-96."""
         ptr, on_dev, n = self._coeffs(polynomial)

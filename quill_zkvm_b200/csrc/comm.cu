@@ -230,6 +230,49 @@ int qz_msm_sharded(qz_ctx* ctx, const qz_srs* srs, const void* scalars, size_t n
   return QZ_OK;
 }
 
+// The same product when every rank holds the WHOLE SRS and the WHOLE scalar vector (HyperPlonk's witness and logup
+// commits at N > 1): rank g takes the index range [n g / G, n (g + 1) / G), the 128-byte partial sums are gathered
+// and added on every rank.  Without a communicator it is qz_kzg_commit.
+int qz_msm_split(qz_ctx* ctx, const qz_srs* srs, const void* scalars, size_t n_scalars, int on_device, uint8_t out_xy[64]) {
+  if (!ctx || !srs || !out_xy || (n_scalars && !scalars)) return QZ_ERR_INVALID_ARG;
+  if (n_scalars > srs->n) return ctx->fail(QZ_ERR_DEGREE, "Polynomial degree exceeds max degree");
+  QZ_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->arena_reset();
+  const int G = ctx->nranks > 0 ? ctx->nranks : 1;
+  const size_t lo = n_scalars * (size_t)ctx->rank / G, hi = n_scalars * ((size_t)ctx->rank + 1) / G, n = hi - lo;
+  cudaStream_t st = ctx->stream;
+  QZ_CUDA(ctx, cudaEventRecord(ctx->ev_call0, st));
+  QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k0, st));
+  QZ_CUDA(ctx, cudaEventRecord(ctx->ev_k1, st));
+  uint4* sdev = on_device ? (uint4*)scalars + 2 * lo : nullptr;
+  const void* shost = nullptr;
+  if (!on_device && n) {
+    sdev = (uint4*)ctx->arena_alloc(32 * n);
+    if (!sdev) return ctx->fail(QZ_ERR_ALLOC, "scalars");
+    shost = (const uint8_t*)scalars + 32 * lo;
+  }
+  uint8_t* mine = (uint8_t*)ctx->arena_alloc(128);
+  uint8_t* all = (uint8_t*)ctx->arena_alloc((size_t)128 * G);
+  uint8_t* out_dev = (uint8_t*)ctx->arena_alloc(64);
+  if (!mine || !all || !out_dev) return ctx->fail(QZ_ERR_ALLOC, "result");
+  int rc = msm_run(ctx, srs, sdev, shost, n, mine, nullptr, lo);
+  if (rc) return rc;
+  if (G > 1) {
+    rc = comm_allgather(ctx, mine, all, 128);
+    if (rc) return rc;
+  } else {
+    all = mine;
+  }
+  rc = msm_sum_points_launch(ctx, all, G, out_dev);
+  if (rc) return rc;
+  QZ_CUDA(ctx, cudaMemcpyAsync(out_xy, out_dev, 64, cudaMemcpyDeviceToHost, st));
+  QZ_CUDA(ctx, cudaEventRecord(ctx->ev_call1, st));
+  QZ_CUDA(ctx, cudaStreamSynchronize(st));
+  cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev_call0, ctx->ev_call1);
+  ctx->last_ms[1] = msm_accumulate_ms(ctx);
+  return QZ_OK;
+}
+
 int qz_comm_allgather_host(qz_ctx* ctx, const void* send, void* recv, size_t bytes) {
   if (!ctx || !send || !recv) return QZ_ERR_INVALID_ARG;
   if (bytes == 0) return QZ_OK;

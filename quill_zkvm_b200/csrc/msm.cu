@@ -630,7 +630,7 @@ static int segment_weights(bool host_scalars, size_t n, double* w) {
 // and cheaper by the cost model, the precomputed window multiples.  Asynchronous: everything is ordered on ctx->stream
 // when the call returns (the prep stream is joined before the last accumulation).
 int msm_run(qz_ctx* ctx, const qz_srs* srs, uint4* scalars_dev, const void* scalars_host, size_t n,
-            uint8_t* out_xyzz_dev, uint8_t* out_affine_dev) {
+            uint8_t* out_xyzz_dev, uint8_t* out_affine_dev, size_t first) {
   cudaStream_t st = ctx->stream;
   QzRange nvtx_call("qz:msm");
   ctx->acc_launches = 0;
@@ -737,7 +737,7 @@ int msm_run(qz_ctx* ctx, const qz_srs* srs, uint4* scalars_dev, const void* scal
       QZ_CUDA(ctx, cudaMemcpyAsync(scalars_dev + 2 * lo, (const uint8_t*)scalars_host + 32 * lo, 32 * ns,
                                    cudaMemcpyHostToDevice, ps));
     QZ_LAUNCH_ON(ctx, ps, msm_digits, (unsigned)((ns + 255) / 256), 256, 0, scalars_dev + 2 * lo, (uint32_t)ns,
-                 (uint32_t)lo, c, Wd, collapsed ? (uint32_t)srs->n : 0u, (uint32_t)(s * W), keys + off, vals + off,
+                 (uint32_t)(first + lo), c, Wd, collapsed ? (uint32_t)srs->n : 0u, (uint32_t)(s * W), keys + off, vals + off,
                  ctx->acc_ring_on ? ctx->acc_nonzero_dev : nullptr);
     cub::DoubleBuffer<uint32_t> dk(keys + off, keys2 + off), dv(vals + off, vals2 + off);
     QZ_CUDA(ctx, cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, dk, dv, (int64_t)ms, 0, key_bits, ps));

@@ -19,9 +19,10 @@ namespace qz {
 int msm_device(qz_ctx* ctx, const qz_srs* srs, const uint4* scalars_dev, size_t n, uint8_t* out_xyzz_dev,
                uint8_t* out_affine_dev);
 // the same with the scalars in host memory (scalars_host non-null): they are copied into scalars_dev range by range
-// on a second stream, overlapped with the accumulation of the previous range
+// on a second stream, overlapped with the accumulation of the previous range.  `first`: the scalars belong to the bases
+// first, first + 1, .. (a rank's index range of an MSM over an SRS every rank holds: qz_msm_split)
 int msm_run(qz_ctx* ctx, const qz_srs* srs, uint4* scalars_dev, const void* scalars_host, size_t n,
-            uint8_t* out_xyzz_dev, uint8_t* out_affine_dev);
+            uint8_t* out_xyzz_dev, uint8_t* out_affine_dev, size_t first = 0);
 // duration of the last MSM's msm_accumulate launches, summed (valid once ctx->stream is synchronised)
 float msm_accumulate_ms(qz_ctx* ctx);
 // KZG::open on the device: x read from device memory, y (32 B) and the affine proof (64 B) written to device memory

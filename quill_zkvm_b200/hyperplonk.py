@@ -63,6 +63,83 @@ def Sub(a: VirtualPolyExpr, b: VirtualPolyExpr) -> VirtualPolyExpr:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+class OpeningPool:
+    """Several ranks: the second halves of ALL the MLEvalProofs of one proof, run at the end as one balanced pool.
+
+    An MLEvalProof's four KZG openings (mlpcs.rs:109-113) are never absorbed by the transcript -- only its evaluation
+    and S commitment are (mlpcs.rs:100-102) -- so nothing that follows depends on them.  A batch therefore only runs
+    the first halves (dealt to the ranks), exchanges (evaluation, S commitment), replays the transcript and leaves
+    (opening, r) here; `finish` deals the 4 x (number of openings) KZG openings of the whole proof to the ranks at
+    once: the two openings of S stay with the rank that holds S, the two of the polynomial (resident on every rank) go
+    to whichever rank is least loaded.  With 13 openings per trace and 8 ranks, per-batch dealing left most ranks idle
+    half of the time (two openings on some ranks, one on the others, traces of different sizes back to back)."""
+
+    def __init__(self, ctx: Context, pcs: KZG, nranks: Optional[int] = None, rank: Optional[int] = None):
+        self.ctx, self.pcs = ctx, pcs
+        self.nranks = getattr(ctx, "nranks", 1) if nranks is None else nranks
+        self.rank = getattr(ctx, "rank", 0) if rank is None else rank
+        self.load = [0.0] * self.nranks  # cost dealt so far, in polynomial entries x MSMs
+        self.entries, self.after = [], []
+
+    BEGIN_COST = 1.6  # first half of an opening in units of one MSM of its length: commit(S) + three transforms
+
+    def deal_begin(self, length: int) -> int:
+        """owner of an opening's first half (and with it of its two S openings): the least loaded rank"""
+        r = min(range(self.nranks), key=lambda k: (self.load[k], k))
+        self.load[r] += (self.BEGIN_COST + 2.0) * max(length, 1)
+        return r
+
+    def add(self, poly, point, evaluation, s_comm, r, owner: int, pending, sink) -> None:
+        self.entries.append(dict(poly=poly, point=point, ev=evaluation, sc=s_comm, r=r, owner=owner, pending=pending, sink=sink))
+
+    def on_done(self, fn) -> None:
+        self.after.append(fn)
+
+    def place_poly_openings(self, lengths: List[int]) -> dict:
+        """(opening, slot) -> rank for the two openings of every polynomial, longest first onto the least loaded rank
+        (pure bookkeeping: every rank takes the same decisions)"""
+        place = {}
+        for i in sorted(range(len(lengths)), key=lambda j: (-lengths[j], j)):
+            for slot in (0, 1):
+                k = min(range(self.nranks), key=lambda q: (self.load[q], q))
+                self.load[k] += max(lengths[i], 1)
+                place[(i, slot)] = k
+        return place
+
+    def finish(self) -> None:
+        ctx, pcs, rank = self.ctx, self.pcs, self.rank
+        B = len(self.entries)
+        place = self.place_poly_openings([e["poly"].nbytes // 32 for e in self.entries])
+        tails = np.zeros((B, 4, 128), dtype=np.uint8)
+        for i, e in enumerate(self.entries):
+            r = np.ascontiguousarray(e["r"], dtype=np.uint8).reshape(32)
+            xs = None
+            for slot in range(4):
+                who = place[(i, slot)] if slot < 2 else e["owner"]
+                if who != rank:
+                    continue
+                if xs is None:
+                    xs = (r, ctx.field_op(0, 3, r.reshape(1, 32)).reshape(32))  # r, 1 / r (mlpcs.rs:107)
+                if slot < 2:
+                    target = e["poly"]
+                else:
+                    pend = e["pending"]
+                    target = (DeviceBuffer(ctx, pend.s_dev, 32 * pend.s_len, owner=False) if pend.s_len
+                              else np.zeros((0, 32), dtype=np.uint8))
+                o = pcs.open(target, xs[slot & 1])
+                tails[i, slot] = np.concatenate([o.x, o.y, o.proof])
+            if e["pending"] is not None and e["pending"].s_dev:
+                ctx.lib.qz_dev_free(ctx.h, e["pending"].s_dev)
+                e["pending"].s_dev = None
+        all_tails = ctx.allgather(tails).reshape(self.nranks, B, 4, 128)
+        for i, e in enumerate(self.entries):
+            ops = np.stack([all_tails[place[(i, slot)] if slot < 2 else e["owner"], i, slot] for slot in range(4)])
+            e["sink"](MLEvalProof.from_parts(e["point"].copy(), e["ev"].copy(), e["sc"].copy(), ops))
+        for fn in self.after:
+            fn()
+        self.entries, self.after = [], []
+
+
 class OpeningBatch:
     """A run of consecutive `MultilinearPCS::open` calls with no other transcript traffic between them (the two logup
     openings of multiset_check.rs:167-170 followed by the num_cols + num_public + 3 openings of proof.rs:202-226).
@@ -70,16 +147,16 @@ class OpeningBatch:
     One GPU: each opening is the fused qz_mlpcs_open, in order.  Several ranks (last row; every rank holds the
     same polynomials and runs the same transcript): an opening's evaluation, S polynomial and S commitment do not depend
     on the transcript, only its four KZG openings need the challenge r -- so the openings are dealt to the ranks, which
-    run the first halves, all-gather (evaluation, S commitment), replay the transcript schedule of mlpcs.rs:100-105 for
-    every opening in order, run the second halves of their own openings and all-gather the results.  Every rank ends
-    with the complete, byte-identical proof."""
+    run the first halves, all-gather (evaluation, S commitment) and replay the transcript schedule of mlpcs.rs:100-105
+    for every opening in order; the second halves wait in the proof's OpeningPool.  Every rank ends with the complete,
+    byte-identical proof."""
 
-    def __init__(self, ctx: Context, pcs: KZG, transcript: Transcript):
-        self.ctx, self.pcs, self.transcript = ctx, pcs, transcript
+    def __init__(self, ctx: Context, pcs: KZG, transcript: Transcript, pool: Optional[OpeningPool] = None):
+        self.ctx, self.pcs, self.transcript, self.pool = ctx, pcs, transcript, pool
         self.items, self.after = [], []
 
     def add(self, poly, point: np.ndarray, sink) -> None:
-        """queue open(poly, point); `sink(MLEvalProof)` receives the result when the batch runs"""
+        """queue open(poly, point); `sink(MLEvalProof)` receives the result when the batch (or its pool) has run"""
         self.items.append((poly, np.ascontiguousarray(point, dtype=np.uint8).reshape(-1, 32), sink))
 
     def on_done(self, fn) -> None:
@@ -89,13 +166,13 @@ class OpeningBatch:
     def _length(poly) -> int:
         return poly.nbytes // 32
 
-    def owners(self, nranks: int) -> List[int]:
-        """longest first onto the least loaded rank (an opening costs about 5 MSMs of its length); ties by index / rank"""
-        load, owner = [0] * nranks, [0] * len(self.items)
+    def owners(self, nranks: int, pool: Optional[OpeningPool] = None) -> List[int]:
+        """rank that runs each opening's first half: longest first onto the least loaded rank of the whole proof so far
+        (`pool` carries the load of the earlier batches); ties by index / rank"""
+        pool = pool if pool is not None else OpeningPool(None, None, nranks=nranks, rank=0)
+        owner = [0] * len(self.items)
         for i in sorted(range(len(self.items)), key=lambda j: (-self._length(self.items[j][0]), j)):
-            r = min(range(nranks), key=lambda k: (load[k], k))
-            owner[i] = r
-            load[r] += max(self._length(self.items[i][0]), 1)
+            owner[i] = pool.deal_begin(self._length(self.items[i][0]))
         return owner
 
     def run(self) -> None:
@@ -104,31 +181,28 @@ class OpeningBatch:
         if nranks == 1:
             for poly, point, sink in self.items:
                 sink(pcs.open_multilinear(poly, point, tr))
+            for fn in self.after:
+                fn()
         else:
-            B, owner = len(self.items), self.owners(nranks)
+            pool = self.pool if self.pool is not None else OpeningPool(ctx, pcs)
+            B, owner = len(self.items), self.owners(nranks, pool)
             pending, head = {}, np.zeros((B, 96), dtype=np.uint8)
             for i, (poly, point, _) in enumerate(self.items):
                 if owner[i] == rank:
                     pending[i] = pcs.open_multilinear_begin(poly, point)
                     head[i, :32], head[i, 32:] = pending[i].evaluation, pending[i].s_comm
             heads = ctx.allgather(head).reshape(nranks, B, 96)
-            tails = np.zeros((B, 512), dtype=np.uint8)
-            for i, (poly, point, _) in enumerate(self.items):  # mlpcs.rs:100-105, every rank, in order
+            for i, (poly, point, sink) in enumerate(self.items):  # mlpcs.rs:100-105, every rank, in order
                 ev, sc = heads[owner[i], i, :32], heads[owner[i], i, 32:]
                 tr.append_fr_vec(point)
                 tr.append_fr(ev)
                 tr.append_g1(sc)
                 r = tr.draw_field_element()
-                if owner[i] == rank:
-                    pf = pcs.open_multilinear_finish(pending[i], r)
-                    tails[i] = np.concatenate([np.concatenate([o.x, o.y, o.proof]) for o in
-                                               (pf.poly_opening, pf.poly_opening_inv, pf.s_opening, pf.s_opening_inv)])
-            all_tails = ctx.allgather(tails).reshape(nranks, B, 4, 128)
-            for i, (poly, point, sink) in enumerate(self.items):
-                h = heads[owner[i], i]
-                sink(MLEvalProof.from_parts(point.copy(), h[:32].copy(), h[32:].copy(), all_tails[owner[i], i]))
-        for fn in self.after:
-            fn()
+                pool.add(poly, point, ev.copy(), sc.copy(), r.copy(), owner[i], pending.get(i), sink)
+            for fn in self.after:
+                pool.on_done(fn)
+            if self.pool is None:
+                pool.finish()
         self.items, self.after = [], []
 
 
@@ -153,8 +227,9 @@ class MultisetEqualityProof:
         gamma = transcript.draw_field_element()  # :40
         left = logup_denominators(ctx, store, h_left, gamma, device=on_dev)  # :43-53
         right = logup_denominators(ctx, store, h_right, gamma, multiplicities, device=on_dev)  # :55-95
-        c_left = pcs.commit(left)  # :98-99
-        c_right = pcs.commit(right)
+        split = getattr(ctx, "nranks", 1) > 1 and on_dev  # every rank holds the tables: each multiplies its index range
+        c_left = pcs.commit_split(left) if split else pcs.commit(left)  # :98-99
+        c_right = pcs.commit_split(right) if split else pcs.commit(right)
         transcript.append_g1(c_left)  # :100-101
         transcript.append_g1(c_right)
         lam = transcript.draw_field_element()  # :104-105
@@ -334,7 +409,7 @@ class HyperPlonk:
         return HyperPlonk(ctx, pks, vks)
 
     def _prove_trace(self, pcs: KZG, full_witness: DeviceBuffer, transcript: Transcript, pk: _TracePK,
-                     circuit: TransitionCircuit) -> TraceProof:
+                     circuit: TransitionCircuit, pool: Optional[OpeningPool] = None) -> TraceProof:
         """prove_trace (:145-237).  The trace stays in HBM: `full_witness` is the column-major witness on the device and
         every column handed to the zero-check is a window of it."""
         ctx = self.ctx
@@ -358,7 +433,7 @@ class HyperPlonk:
         w_virtual = store2.new_virtual_from_input(w_idx)
         # every opening of the trace forms one run in the transcript: queue them, then run the batch (split over the
         # ranks when there are several)
-        batch = OpeningBatch(ctx, pcs, transcript)
+        batch = OpeningBatch(ctx, pcs, transcript, pool)
         perm_proof, perm_point = PermutationCheckProof.prove(ctx, store2, w_virtual, w_virtual, pk.id_poly,
                                                              pk.permutation_poly, transcript, pcs, batch=batch)
         openings_zc = [None] * circuit.num_cols()  # :202-210: column bits appended as the HIGH variables of the witness
@@ -374,12 +449,19 @@ class HyperPlonk:
         batch.add(pk.permutation_poly, perm_point, lambda o: tail.__setitem__("perm", o))
         batch.add(full_witness, perm_point, lambda o: tail.__setitem__("trace", o))
         batch.run()
-        return TraceProof(zero_check_proof, perm_proof, openings_zc, openings_pub, tail["id"], tail["perm"], tail["trace"])
+        proof = TraceProof(zero_check_proof, perm_proof, openings_zc, openings_pub, tail.get("id"), tail.get("perm"), tail.get("trace"))
+        if pool is not None and getattr(ctx, "nranks", 1) > 1:  # the openings arrive when the pool has run
+            def fill():
+                proof.opening_id, proof.opening_permutation, proof.opening_permutation_trace = tail["id"], tail["perm"], tail["trace"]
+            pool.on_done(fill)
+        return proof
 
     def prove(self, pcs: KZG, witness_traces: List[List[np.ndarray]]) -> HyperPlonkProof:
         """proof.rs:239-301.  witness_traces[t][c] is column c of trace t as a (rows, 32) Montgomery array."""
         ctx = self.ctx
         transcript = Transcript(b"hyperplonk_proof", ctx)  # :245
+        multi = getattr(ctx, "nranks", 1) > 1
+        pool = OpeningPool(ctx, pcs) if multi else None
         comms, fulls = [], []
         for witness, vk in zip(witness_traces, self.trace_vks):  # :250-284
             c = vk.circuit
@@ -389,12 +471,14 @@ class HyperPlonk:
             full = ctx.alloc(32 * c.num_cols() * c.num_rows())  # column-major (:270), uploaded once and kept resident
             for j, col in enumerate(witness):
                 ctx.check(ctx.lib.qz_dev_upload(ctx.h, full.ptr + j * 32 * c.num_rows(), _host_ptr(col), 32 * c.num_rows()))
-            com = pcs.commit(full)
+            com = pcs.commit_split(full) if multi else pcs.commit(full)
             transcript.append_g1(com)
             comms.append(com)
             fulls.append(full)
-        proofs = [self._prove_trace(pcs, fulls[i], transcript, self.trace_pks[i], self.trace_vks[i].circuit)
+        proofs = [self._prove_trace(pcs, fulls[i], transcript, self.trace_pks[i], self.trace_vks[i].circuit, pool)
                   for i in range(len(witness_traces))]
+        if pool is not None:
+            pool.finish()
         for f in fulls:
             f.free()
         return HyperPlonkProof(comms, proofs, transcript.state.tobytes())

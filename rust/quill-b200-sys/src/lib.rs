@@ -101,6 +101,7 @@ extern "C" {
     pub fn qz_comm_peer_memory(ctx: *const qz_ctx) -> i32;
     pub fn qz_msm_sharded(ctx: *mut qz_ctx, srs_shard: *const qz_srs, scalars_shard: *const c_void, n_scalars: usize,
                           scalars_on_device: i32, out_xy: *mut u8) -> i32;
+    pub fn qz_msm_split(ctx: *mut qz_ctx, srs: *const qz_srs, scalars: *const c_void, n_scalars: usize, scalars_on_device: i32, out_xy: *mut u8) -> i32;
     pub fn qz_sumcheck_prove_sharded(ctx: *mut qz_ctx, num_vars: usize, k: usize, table_shards: *const *const c_void,
                                      tables_on_device: i32, nodes: *const qz_expr_node, n_nodes: usize,
                                      consts: *const u8, n_consts: usize, claimed_sum: *const u8, state: *mut u8,

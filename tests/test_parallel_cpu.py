@@ -196,7 +196,8 @@ def _worker(rank, world, port, ret):
         batch = hp.OpeningBatch(None, None, None)
         for p, pt in zip(polys_o, points_o):
             batch.add(np.zeros((len(p), 32), np.uint8), np.zeros((len(pt), 32), np.uint8), None)
-        owner = batch.owners(world)
+        pool = hp.OpeningPool(None, None, nranks=world, rank=rank)
+        owner = batch.owners(world, pool)
         assert sorted(set(owner)) == list(range(world))
         mine = {}
         for i, (p, pt) in enumerate(zip(polys_o, points_o)):
@@ -205,22 +206,32 @@ def _worker(rank, world, port, ret):
                 s_poly = py.compute_s_polynomial(list(p), pr)
                 mine[i] = (sum(a * b for a, b in zip(p, pr)) % FR, s_poly, kz.commit(s_poly))
         heads = _gather_obj({i: (v[0], v[2]) for i, v in mine.items()}, world)
-        tr2, got_o = py.Transcript(b"deal"), {}
+        tr2, chal = py.Transcript(b"deal"), {}
         for i, (p, pt) in enumerate(zip(polys_o, points_o)):  # every rank replays the schedule of mlpcs.rs:100-105
             ev_i, sc_i = heads[owner[i]][i]
             tr2.append_fr_vec(pt)
             tr2.append_fr(ev_i)
             tr2.append_g1(sc_i)
-            r = tr2.draw_field_element()
-            if owner[i] == rank:  # second half: the four KZG openings at r and 1/r
-                r_inv = py.fr_inv(r)
-                got_o[i] = dict(evaluation_point=[x % FR for x in pt], evaluation=ev_i, s_comm=sc_i,
-                                poly_opening=kz.open(p, r), poly_opening_inv=kz.open(p, r_inv),
-                                s_opening=kz.open(mine[i][1], r), s_opening_inv=kz.open(mine[i][1], r_inv))
+            chal[i] = tr2.draw_field_element()
+        # second halves (hyperplonk.OpeningPool.finish): the four KZG openings at r and 1/r are not absorbed by the
+        # transcript, so they run after every batch's replay; S's two stay with the owner of S, the polynomial's two go
+        # to the least loaded rank
+        place = pool.place_poly_openings([len(p) for p in polys_o])
+        assert set(place.values()) <= set(range(world)) and len(place) == 2 * len(polys_o)
+        names = ("poly_opening", "poly_opening_inv", "s_opening", "s_opening_inv")
+        got_o = {}
+        for i, p in enumerate(polys_o):
+            r, r_inv = chal[i], py.fr_inv(chal[i])
+            for slot in range(4):
+                who = place[(i, slot)] if slot < 2 else owner[i]
+                if who == rank:
+                    got_o[(i, slot)] = kz.open(p if slot < 2 else mine[i][1], r_inv if slot & 1 else r)
         merged = {}
         for d in _gather_obj(got_o, world):
             merged.update(d)
-        assert [merged[i] for i in range(len(polys_o))] == want_o and tr2.state == seq_tr.state
+        got = [dict(evaluation_point=[x % FR for x in pt], evaluation=heads[owner[i]][i][0], s_comm=heads[owner[i]][i][1],
+                    **{names[slot]: merged[(i, slot)] for slot in range(4)}) for i, pt in enumerate(points_o)]
+        assert got == want_o and tr2.state == seq_tr.state
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()
@@ -246,6 +257,12 @@ def test_opening_owners_balanced_and_deterministic():
         assert owner == batch.owners(w) and set(owner) <= set(range(w))
         load = [sum(s for s, o in zip(sizes, owner) if o == r) for r in range(w)]
         assert max(load) - min(load) <= max(sizes)
+        # the whole proof: first halves (+ the two S openings) with their owner, the polynomials' openings pooled
+        pool = hp.OpeningPool(None, None, nranks=w, rank=0)
+        batch.owners(w, pool)
+        place = pool.place_poly_openings(sizes)
+        assert sorted(place) == [(i, s) for i in range(len(sizes)) for s in (0, 1)]
+        assert max(pool.load) - min(pool.load) <= (hp.OpeningPool.BEGIN_COST + 2.0) * max(sizes)
 
 
 def test_shard_ranges_partition():
