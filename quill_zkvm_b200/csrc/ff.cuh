@@ -521,6 +521,44 @@ QZ_DEV Fp<P> fp_sub_lazy(const Fp<P>& a, const Fp<P>& b) {
   return r;
 }
 
+// plain 256-bit integer addition / subtraction (no reduction; the caller guarantees 0 <= result < 2^256): for operands
+// whose magnitude does not matter -- wide_mul_acc takes any 256-bit values, fp_mul any 256-bit second operand
+template <class P>
+QZ_DEV Fp<P> u256_add(const Fp<P>& a, const Fp<P>& b) {
+  Fp<P> r;
+  asm volatile(
+      "add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;\n\t"
+      : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+        "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+  return r;
+}
+template <class P>
+QZ_DEV Fp<P> u256_p_minus(const Fp<P>& a) {  // p - a for a <= p
+  Fp<P> r;
+  asm volatile(
+      "sub.cc.u32 %0, %8, %16;\n\t"
+      "subc.cc.u32 %1, %9, %17;\n\t"
+      "subc.cc.u32 %2, %10, %18;\n\t"
+      "subc.cc.u32 %3, %11, %19;\n\t"
+      "subc.cc.u32 %4, %12, %20;\n\t"
+      "subc.cc.u32 %5, %13, %21;\n\t"
+      "subc.cc.u32 %6, %14, %22;\n\t"
+      "subc.u32 %7, %15, %23;\n\t"
+      : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+      : "r"(P::MOD(0)), "r"(P::MOD(1)), "r"(P::MOD(2)), "r"(P::MOD(3)), "r"(P::MOD(4)), "r"(P::MOD(5)), "r"(P::MOD(6)),
+        "r"(P::MOD(7)), "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]),
+        "r"(a.v[7]));
+  return r;
+}
+
 // Montgomery -> canonical limbs (multiply by 1)
 template <class P>
 QZ_DEV Fp<P> fp_from_mont(const Fp<P>& a) {

@@ -53,6 +53,20 @@ constexpr int SC_WIDE_THREADS = 128;  // deferred-reduction round kernel: 168 re
 #endif
 
 // ---- loads ---------------------------------------------------------------------------------------------------------------
+// The streaming passes ask L2 for the next pair's lines while the current pair is being multiplied: 2.615 -> 2.59 ms over
+// the streaming rounds of a 2^24 proof (L1 as the target measured the same).  0 turns it off (tools/build_variant.sh).
+#ifndef QZ_SC_PREFETCH
+#define QZ_SC_PREFETCH 1
+#endif
+QZ_DEV void prefetch_line(const void* p) {
+#if QZ_SC_PREFETCH == 1
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#elif QZ_SC_PREFETCH == 2
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
 QZ_DEV Fr ld_elem(const uint4* base, uint64_t e) { return fp_load<FrParams>(base + 2 * e); }
 QZ_DEV void st_elem(uint4* base, uint64_t e, const Fr& v) { fp_store<FrParams>(base + 2 * e, v); }
 // the same load past L1 (ld.global.cv): for data another block -- or another GPU -- wrote during this kernel (sc_mid)
@@ -172,9 +186,40 @@ struct ProdAcc {
   QZ_DEV Fr get_slot(int i) const { return WIDE ? wide_reduce<FrParams>(wide[WIDE ? i : 0]) : narrow[WIDE ? 0 : i]; }
 };
 
+// K = 3 with deferred reduction: the cubic is sampled at X = 0, 1, -1 and "infinity" (its leading coefficient) instead of
+// X = 0 .. 3.  The quadratic g_0 g_1 = q0 + (q1 - q0 - q2) X + q2 X^2 already has its three samples q0 = q(0), q1 = q(1),
+// q2 = q(inf) from the three products, q(-1) = 2 q0 + 2 q2 - q1 and g_2(-1) = 2 lo_2 - hi_2 are the only derived
+// values, and every operand of a deferred-reduction product may be ANY 256-bit integer, so they are formed by plain
+// additions: 4 modular differences' worth of carry-chain instructions per pair instead of 14 (forward differences of
+// the quadratic and the linear factor up to X = 3).  The passes are bound by dependent-issue latency at four warps per
+// scheduler, not by the multiplier alone (ncu: stall "wait" 2.7 per issue), so the ~250 fewer serial instructions per
+// pair show up directly.  The slots are, in order, X = 0, 1, -1, inf (X = 1 absent under SKIP1); the finalize step
+// turns them into coefficients (sc_toom3_to_coeffs).
+template <bool SKIP1>
+QZ_DEV void prod_core_toom3(const Fr* lo, const Fr* hi, ProdAcc<3, true, SKIP1>& acc) {
+  const Fr q0 = fp_mul<FrParams>(lo[0], lo[1]);
+  const Fr q1 = fp_mul<FrParams>(hi[0], hi[1]);
+  const Fr d0 = fp_sub<FrParams>(hi[0], lo[0]);       // < p: the first operand of a reducing product
+  const Fr d1 = fp_sub_lazy<FrParams>(hi[1], lo[1]);  // in (0, 2p)
+  const Fr q2 = fp_mul<FrParams>(d0, d1);
+  const Fr d2 = fp_sub_lazy<FrParams>(hi[2], lo[2]);  // leading coefficient of g_2, in (0, 2p)
+  acc.add_product(0, q0, lo[2]);
+  acc.add_product(1, q1, hi[2]);
+  acc.add_product(3, q2, d2);
+  // q(-1) = 2 (q0 + q2) + (p - q1) in (0, 5p), below 2^256 = 5.29 p;  g_2(-1) = lo_2 + (lo_2 - hi_2 + p) in (0, 3p)
+  const Fr s02 = u256_add<FrParams>(q0, q2);
+  const Fr qm = u256_add<FrParams>(u256_add<FrParams>(s02, s02), u256_p_minus<FrParams>(q1));
+  const Fr gm = u256_add<FrParams>(lo[2], fp_sub_lazy<FrParams>(lo[2], hi[2]));
+  acc.add_product(2, qm, gm);
+}
+
 // core of a pair once the K (lo, hi) values are in registers
 template <int K, bool WIDE, bool SKIP1>
 QZ_DEV void prod_core(const Fr* lo, const Fr* hi, ProdAcc<K, WIDE, SKIP1>& acc) {
+  if constexpr (K == 3 && WIDE) {
+    prod_core_toom3<SKIP1>(lo, hi, acc);
+    return;
+  }
   constexpr int NP = K / 2;
   Fr val[NP > 0 ? NP : 1], dl[NP > 0 ? NP : 1], q22[NP > 0 ? NP : 1], lin, lin_df;
 #pragma unroll
@@ -240,6 +285,10 @@ __global__ void __launch_bounds__(WIDE ? SC_WIDE_THREADS : SC_THREADS, (WIDE ? (
     RawPair<FOLD> raw[K];
 #pragma unroll
     for (int t = 0; t < K; t++) load_raw<FOLD>(tabs.in[t], p, raw[t]);
+    if (QZ_SC_PREFETCH && p + stride < n_pairs) {
+#pragma unroll
+      for (int t = 0; t < K; t++) prefetch_line(tabs.in[t] + (FOLD ? 8 : 4) * (p + stride));
+    }
     Fr lo[K], hi[K];
 #pragma unroll
     for (int t = 0; t < K; t++) finish_pair<FOLD, WIDE>(raw[t], tabs.out[t], p, r, lo[t], hi[t]);  // WIDE passes fold by c_fold
@@ -279,6 +328,11 @@ __global__ void __launch_bounds__(WIDE ? SC_WIDE_THREADS : SC_THREADS, (WIDE ? Q
     RawPair<FOLD> raw[K];
 #pragma unroll
     for (int t = 0; t < K; t++) load_raw<FOLD>(tabs.in[t], p, raw[t]);
+    if (QZ_SC_PREFETCH && p + stride < n_pairs) {
+#pragma unroll
+      for (int t = 0; t < K; t++) prefetch_line(tabs.in[t] + (FOLD ? 8 : 4) * (p + stride));
+      prefetch_line(e_in + (FOLD ? 4 : 2) * (p + stride));
+    }
     Fr w;
     if (FOLD) {
       w = fp_add<FrParams>(ld_elem(e_in, 2 * p), ld_elem(e_in, 2 * p + 1));
@@ -371,7 +425,7 @@ __global__ void __launch_bounds__(SC_THREADS) sc_round_generic(ScTables tabs, ui
 __global__ void __launch_bounds__(SC_THREADS) sc_finalize(const Fr* partials, int n_parts, int d, ScHead* head,
                                                          const Fr* vinv, Fr* out_coeffs_row, uint32_t* out_len,
                                                          Fr* out_point_slot, int max_coeffs, const Fr* zc_z, int derive1,
-                                                         const Fr* zc_zinv, uint32_t* foldc) {
+                                                         const Fr* zc_zinv, uint32_t* foldc, int toom) {
   __shared__ Fr s_part[(SC_THREADS / 32) * SC_MAX_COEFFS];
   __shared__ Fr s_evals[SC_MAX_COEFFS];
   __shared__ Fr s_coef[SC_MAX_COEFFS];
@@ -386,8 +440,9 @@ __global__ void __launch_bounds__(SC_THREADS) sc_finalize(const Fr* partials, in
     for (int x = 0; x < ns; x++) v[x] = fp_add<FrParams>(v[x], partials[(size_t)b * ns + x]);
   block_sum_many(v, ns, s_part, s_evals);
   if (derive1) sc_expand_evals(head, d, s_evals, zc_z, zc_zinv);
-  sc_round_close(head, vinv, d, s_evals, s_coef, s_msg, s_prod, out_coeffs_row, out_len, out_point_slot, max_coeffs, zc_z,
-                 true, foldc);
+  if (toom) sc_toom3_to_coeffs(s_evals);  // the sums are samples at X = 0, 1, -1, inf (prod_core_toom3)
+  sc_round_close(head, toom ? nullptr : vinv, d, s_evals, s_coef, s_msg, s_prod, out_coeffs_row, out_len, out_point_slot,
+                 max_coeffs, zc_z, true, foldc);
 }
 
 // Sharded mode with peer mailboxes (comm.cuh): ONE launch per round after the round kernel.  The block sums this rank's
@@ -399,7 +454,7 @@ __global__ void __launch_bounds__(SC_THREADS) sc_finalize_peers(const Fr* partia
                                                                ScHead* head, const Fr* vinv, Fr* out_coeffs_row,
                                                                uint32_t* out_len, Fr* out_point_slot, int max_coeffs,
                                                                const Fr* zc_z, int derive1, const Fr* zc_zinv,
-                                                               uint32_t* foldc) {
+                                                               uint32_t* foldc, int toom) {
   __shared__ Fr s_part[(SC_THREADS / 32) * SC_MAX_COEFFS];
   __shared__ Fr s_evals[SC_MAX_COEFFS];
   __shared__ Fr s_coef[SC_MAX_COEFFS];
@@ -422,8 +477,9 @@ __global__ void __launch_bounds__(SC_THREADS) sc_finalize_peers(const Fr* partia
   }
   __syncthreads();
   if (derive1) sc_expand_evals(head, d, s_evals, zc_z, zc_zinv);
-  sc_round_close(head, vinv, d, s_evals, s_coef, s_msg, s_prod, out_coeffs_row, out_len, out_point_slot, max_coeffs, zc_z,
-                 true, foldc);
+  if (toom) sc_toom3_to_coeffs(s_evals);
+  sc_round_close(head, toom ? nullptr : vinv, d, s_evals, s_coef, s_msg, s_prod, out_coeffs_row, out_len, out_point_slot,
+                 max_coeffs, zc_z, true, foldc);
 }
 
 // reduce block partials to one vector per rank (sharded mode: the vectors are all-gathered, then sc_finalize)
@@ -1489,21 +1545,22 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
 #undef QZ_ROUND_ZC
         const Fr* zinv_j = zc_skip1 ? d_zinv + round : nullptr;
         const int ns = derive1 ? K : K + 1;
+        const int toom = wide && K == 3 ? 1 : 0;  // the sums are samples at X = 0, 1, -1, inf (prod_core_toom3)
         if (G == 1) {
           QZ_LAUNCH_PDL(ctx, pdl, sc_finalize, 1, SC_THREADS, (const Fr*)partials, grid, K, head, (const Fr*)vinv_k,
                         d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc, (const Fr*)(d_z + round), derive1,
-                        zinv_j, d_foldc);
+                        zinv_j, d_foldc, toom);
         } else if (comm_has_peers(ctx)) {
           QZ_LAUNCH_PDL(ctx, pdl, sc_finalize_peers, 1, SC_THREADS, (const Fr*)partials, grid, K,
                         (PeerMailbox* const*)ctx->peer_mbox_dev, ctx->rank, G, ++ctx->mbox_seq, head, (const Fr*)vinv_k,
                         d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc, (const Fr*)(d_z + round), derive1,
-                        zinv_j, d_foldc);
+                        zinv_j, d_foldc, toom);
         } else {
           QZ_LAUNCH(ctx, sc_reduce_partials, 1, SC_THREADS, 0, partials, grid, ns - 1, rank_evals);
           rc = comm_allgather(ctx, rank_evals, all_evals, sizeof(Fr) * ns);
           if (rc) return rc;
           QZ_LAUNCH(ctx, sc_finalize, 1, SC_THREADS, 0, all_evals, G, K, head, vinv_k, d_coeffs + (size_t)round * mc,
-                    d_lens + round, d_point + round, mc, (const Fr*)(d_z + round), derive1, zinv_j, d_foldc);
+                    d_lens + round, d_point + round, mc, (const Fr*)(d_z + round), derive1, zinv_j, d_foldc, toom);
         }
         if (pending) {
           for (int i = 0; i < K; i++) gt.in[i] = gt.out[i];
@@ -1582,7 +1639,7 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
         if (rc) return rc;
       }
       QZ_LAUNCH(ctx, sc_finalize, 1, SC_THREADS, 0, (const Fr*)partials, grid_c * up_chunks, d, head, (const Fr*)vinv, d_coeffs,
-                d_lens, d_point, mc, (const Fr*)nullptr, 0, (const Fr*)nullptr, d_foldc);
+                d_lens, d_point, mc, (const Fr*)nullptr, 0, (const Fr*)nullptr, d_foldc, wide && cp.product_k == 3 ? 1 : 0);
       pending = 1;
       round = 1;
     }
@@ -1597,21 +1654,22 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
       if (rc) return rc;
       // every round but the first leaves X = 1 to the running claim (ProdAcc / generic_pair)
       const int derive1 = pending && d >= 1 ? 1 : 0, ns = derive1 ? d : d + 1;
+      const int toom = wide && cp.product_k == 3 ? 1 : 0;  // the sums are samples at X = 0, 1, -1, inf (prod_core_toom3)
       if (G == 1) {
         QZ_LAUNCH_PDL(ctx, pdl, sc_finalize, 1, SC_THREADS, (const Fr*)partials, grid, d, head, (const Fr*)vinv,
                       d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc, (const Fr*)nullptr, derive1,
-                      (const Fr*)nullptr, d_foldc);
+                      (const Fr*)nullptr, d_foldc, toom);
       } else if (comm_has_peers(ctx)) {  // partial sums go straight into the peers' mailboxes (comm.cuh)
         QZ_LAUNCH_PDL(ctx, pdl, sc_finalize_peers, 1, SC_THREADS, (const Fr*)partials, grid, d,
                       (PeerMailbox* const*)ctx->peer_mbox_dev, ctx->rank, G, ++ctx->mbox_seq, head, (const Fr*)vinv,
                       d_coeffs + (size_t)round * mc, d_lens + round, d_point + round, mc, (const Fr*)nullptr, derive1,
-                      (const Fr*)nullptr, d_foldc);
+                      (const Fr*)nullptr, d_foldc, toom);
       } else {  // every rank sums all ranks' partial evaluations and runs the same transcript
         QZ_LAUNCH(ctx, sc_reduce_partials, 1, SC_THREADS, 0, partials, grid, ns - 1, rank_evals);
         rc = comm_allgather(ctx, rank_evals, all_evals, sizeof(Fr) * ns);
         if (rc) return rc;
         QZ_LAUNCH(ctx, sc_finalize, 1, SC_THREADS, 0, all_evals, G, d, head, vinv, d_coeffs + (size_t)round * mc,
-                  d_lens + round, d_point + round, mc, (const Fr*)nullptr, derive1, (const Fr*)nullptr, d_foldc);
+                  d_lens + round, d_point + round, mc, (const Fr*)nullptr, derive1, (const Fr*)nullptr, d_foldc, toom);
       }
       if (pending) {
         for (int j = 0; j < ka; j++) tabs.in[j] = tabs.out[j];

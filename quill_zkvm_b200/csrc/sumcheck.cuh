@@ -442,6 +442,25 @@ QZ_DEV void sc_expand_evals(const ScHead* head, int d, Fr* s_evals, const Fr* zc
   __syncthreads();
 }
 
+// Samples of a cubic at X = 0, 1, -1 and infinity (its leading coefficient), in that order in s_evals[0..4), to its
+// coefficients, in place: c0 = s(0), c3 = s(inf), c2 = (s(1) + s(-1)) / 2 - c0, c1 = (s(1) - s(-1)) / 2 - c3.
+// Called by every thread of the block; ends with a barrier.
+QZ_DEV void sc_toom3_to_coeffs(Fr* s_evals) {
+  const int t = threadIdx.x;
+  Fr mine = fp_zero<FrParams>();
+  if (t == 1 || t == 2) {
+    const Fr s0 = s_evals[0], s1 = s_evals[1], sm = s_evals[2], sinf = s_evals[3];
+    Fr inv2;
+#pragma unroll
+    for (int i = 0; i < 8; i++) inv2.v[i] = FrParams::INV2(i);
+    mine = t == 2 ? fp_sub<FrParams>(fp_mul<FrParams>(inv2, fp_add<FrParams>(s1, sm)), s0)
+                  : fp_sub<FrParams>(fp_mul<FrParams>(inv2, fp_sub<FrParams>(s1, sm)), sinf);
+  }
+  __syncthreads();
+  if (t == 1 || t == 2) s_evals[t] = mine;
+  __syncthreads();
+}
+
 // want_claim: leave s_j(r_j) (t_j(r_j) on the eq-factored path) in head->claim for a following SKIP1 round
 // release_flag (sc_mid): set to release_value as soon as the challenge is in head->r -- the other blocks of the grid
 // start folding with it while this block finishes the bookkeeping.  That bookkeeping (the running claim: d dependent
@@ -457,14 +476,17 @@ QZ_DEV void sc_round_close(ScHead* head, const Fr* vinv, int d, const Fr* s_eval
   const int n_out = zc_z ? d + 2 : d + 1;  // coefficients of the round polynomial before trimming
   // coefficient i = sum_j vinv[i][j] * e[j]: the (d+1)^2 products are independent, so when they fit the block each
   // thread does one (s_prod: SC_PROD_SLOTS Fr of shared memory)
-  const bool wide = n1 * n1 <= (int)blockDim.x && n1 * n1 <= SC_PROD_SLOTS;
+  // (vinv null: s_evals already holds the coefficients, see sc_toom3_to_coeffs)
+  const bool wide = vinv && n1 * n1 <= (int)blockDim.x && n1 * n1 <= SC_PROD_SLOTS;
   if (wide) {
     if (t < n1 * n1) s_prod[t] = fp_mul<FrParams>(vinv[t], s_evals[t % n1]);
     __syncthreads();
   }
   Fr acc = fp_zero<FrParams>();
   if (t <= d) {
-    if (wide) {
+    if (!vinv) {
+      acc = s_evals[t];
+    } else if (wide) {
       for (int j = 0; j <= d; j++) acc = fp_add<FrParams>(acc, s_prod[t * n1 + j]);
     } else {
 #pragma unroll 1

@@ -52,21 +52,24 @@ def full(rep, out, title):
 
 
 if __name__ == "__main__":
-    import shutil
-    shutil.copyfile("gpurun_out/launches.csv", f"profiles/{TAG}_launches_bench_steps2.csv")
-    launches("gpurun_out/launches.csv", f"profiles/{TAG}_launches_summary.txt",
-             f"{TAG}: ncu --metrics gpu__time_duration.sum --clock-control none -c 900 python bench.py --steps 2 --warmup 1 "
-             "--no-cpu-baseline --mlpcs-log-n 0 --hyperplonk-log-rows 0   (3 MSMs of 2^24 with device-resident scalars and 3 with host scalars -- streamed in 3 ranges --, precomputed windows; 6 sumcheck proofs of 3 x 2^24; setup)")
-    full("gpurun_out/prof_r1_msm.ncu-rep", f"profiles/{TAG}_ncu_msm_accumulate.txt",
-         f"{TAG}: ncu --set full --clock-control none -k regex:msm_accumulate -c 1 python tools/profile_one.py msm 24 pre  (2^24 points, c = 22, 12 mixed additions per point)")
     import os
-    if os.path.exists("gpurun_out/lhp20.csv"):
-        launches("gpurun_out/lhp20.csv", f"profiles/{TAG}_launches_hyperplonk_2_20.txt",
-                 f"{TAG}: ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 python tools/profile_hp.py 20   "
+    import shutil
+    G = "gpurun_out/"
+    shutil.copyfile(G + "launches.csv", f"profiles/{TAG}_launches_bench_steps2.csv")
+    launches(G + "launches.csv", f"profiles/{TAG}_launches_summary.txt",
+             f"{TAG}: ncu --metrics gpu__time_duration.sum --clock-control none -c 900 python bench.py --steps 2 --warmup 1 "
+             "--no-cpu-baseline --mlpcs-log-n 0 --hyperplonk-log-rows 0   (MSMs of 2^24 with device-resident and with host scalars -- streamed in 3 ranges --, precomputed windows; sumcheck and zero-check proofs of 3 x 2^24; setup)")
+    if os.path.exists(G + "lhp20.csv"):
+        launches(G + "lhp20.csv", f"profiles/{TAG}_launches_hyperplonk_2_20.txt",
+                 f"{TAG}: ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 python tools/profile_hp.py 20   "
                  "(setup + 2 HyperPlonk proofs of two 2^20-row traces: BASELINE config 5 on one GPU)")
-    if os.path.exists("gpurun_out/prof_r1_ntt.ncu-rep"):
-        full("gpurun_out/prof_r1_ntt.ncu-rep", f"profiles/{TAG}_ncu_ntt_pass.txt",
-             f"{TAG}: ncu --set full --clock-control none -k regex:ntt_pass -c 3 python tools/profile_one.py mlpcs 22  "
-             "(forward 2^23 transform: passes of 8 + 8 + 7 stages; the first two gather one twiddle per butterfly)")
-    full("gpurun_out/prof_r1_sc.ncu-rep", f"profiles/{TAG}_ncu_sc_round_prod.txt",
-         f"{TAG}: ncu --set full --clock-control none -k regex:sc_round_prod -c 2 python tools/profile_one.py sumcheck 24  (launch 0 = round 0, evaluate only; launch 1 = round 1, fold fused)")
+    CAP = [("prof_msm", "msm_accumulate", "-k regex:msm_accumulate -c 1 python tools/profile_one.py msm 24 pre  (2^24 points, c = 22, 12 mixed additions per point)"),
+           ("prof_bucket_reduce", "msm_bucket_reduce", "-k regex:msm_bucket_reduce -c 1 python tools/profile_one.py msm 24 pre  (2^21 buckets, 64 per thread)"),
+           ("prof_sort", "msm_sort_onesweep", "-k regex:Onesweep -c 3 python tools/profile_one.py msm 24 pre  (cub::DeviceRadixSort over 12 x 2^24 (key, value) pairs, 22-bit keys: three onesweep passes)"),
+           ("prof_sc", "sc_round_prod", "-k regex:sc_round_prod -c 3 python tools/profile_one.py sumcheck 24  (launch 0 = round 0, evaluate only; launches 1, 2 = rounds 1, 2, fold fused, X = 1 derived)"),
+           ("prof_sc_mid", "sc_mid", "-k regex:sc_mid -c 1 python tools/profile_one.py sumcheck 24  (the 18 rounds from 2^18 entries down, one cooperative launch)"),
+           ("prof_zc", "sc_round_zc", "-k regex:sc_round_zc -c 2 python tools/profile_one.py zerocheck 24  (eq-factored zero-check: round 0 and round 1)"),
+           ("prof_ntt", "ntt_pass", "-k regex:ntt_pass -c 3 python tools/profile_one.py mlpcs 22  (forward 2^23 transform: passes of 8 + 8 + 7 stages)")]
+    for rep, name, what in CAP:
+        if os.path.exists(G + rep + ".ncu-rep"):
+            full(G + rep + ".ncu-rep", f"profiles/{TAG}_ncu_{name}.txt", f"{TAG}: ncu --set full --clock-control none {what}")
