@@ -11,6 +11,7 @@
 #include <vector>
 #include "comm.cuh"
 #include "ctx.cuh"
+#include "ec.cuh"
 #include "msm.cuh"
 
 namespace {
@@ -195,6 +196,58 @@ int qz_comm_init(qz_ctx* ctx, const uint8_t unique_id[128], int rank, int nranks
 
 int qz_comm_peer_memory(const qz_ctx* ctx) { return ctx && comm_has_peers(ctx) ? 1 : 0; }
 
+// The MSM's one exchange through the peer mailboxes: this rank's XYZZ partial sum (4 x 32 B) goes into every rank's
+// mailbox, the G partial sums are added with the group law (never ncclSum) and converted to affine -- one launch in
+// place of ncclAllGather + msm_sum_points.
+__global__ void __launch_bounds__(32) msm_sum_points_peers(const uint8_t* mine_xyzz, qz::PeerMailbox* const* peers, int rank,
+                                                          int G, uint32_t seq, uint8_t* out_affine, uint32_t* fault) {
+  using namespace qz;
+  __shared__ Fr s_vals[4];
+  if (threadIdx.x < 4) s_vals[threadIdx.x] = fp_load<FrParams>(mine_xyzz + 32 * threadIdx.x);  // raw limbs of x, y, zz, zzz
+  __syncthreads();
+  const PeerSlot* got = peer_exchange(peers, rank, G, seq, s_vals, 4);
+  if (threadIdx.x == 0) {
+    if (*reinterpret_cast<volatile uint32_t*>(&peers[rank]->timed_out)) *fault = 1;
+    Xyzz total = xyzz_identity();
+    for (int g = 0; g < G; g++) {
+      Xyzz p;
+      Fr w[4];
+      for (int i = 0; i < 4; i++) w[i] = ld_fresh(&got->data[g][i]);
+      for (int i = 0; i < 8; i++) {
+        p.x.v[i] = w[0].v[i];
+        p.y.v[i] = w[1].v[i];
+        p.zz.v[i] = w[2].v[i];
+        p.zzz.v[i] = w[3].v[i];
+      }
+      total = xyzz_add(total, p);
+    }
+    affine_store(out_affine, xyzz_to_affine_serial(total));
+  }
+}
+// all ranks' partial sums (`mine`: 128 B XYZZ on the device) -> affine sum on every rank
+static int msm_exchange_sum(qz_ctx* ctx, uint8_t* mine, uint8_t* all, uint8_t* out_dev) {
+  const int G = ctx->nranks > 0 ? ctx->nranks : 1;
+  if (G > 1 && qz::comm_has_peers(ctx)) {
+    uint32_t* fault = (uint32_t*)ctx->arena_alloc(4);
+    if (!fault) return ctx->fail(QZ_ERR_ALLOC, "fault flag");
+    QZ_CUDA(ctx, cudaMemsetAsync(fault, 0, 4, ctx->stream));
+    QZ_LAUNCH(ctx, msm_sum_points_peers, 1, 32, 0, (const uint8_t*)mine, (qz::PeerMailbox* const*)ctx->peer_mbox_dev, ctx->rank, G,
+              ++ctx->mbox_seq, out_dev, fault);
+    uint32_t* pin = (uint32_t*)ctx->pinned_buf(64);
+    if (!pin) return ctx->fail(QZ_ERR_ALLOC, "pinned");
+    QZ_CUDA(ctx, cudaMemcpyAsync(pin, fault, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->pending_fault = pin;
+    return QZ_OK;
+  }
+  if (G > 1) {
+    int rc = qz::comm_allgather(ctx, mine, all, 128);
+    if (rc) return rc;
+  } else {
+    all = mine;
+  }
+  return qz::msm_sum_points_launch(ctx, all, G, out_dev);
+}
+
 int qz_msm_sharded(qz_ctx* ctx, const qz_srs* srs, const void* scalars, size_t n_scalars, int on_device,
                    uint8_t out_xy[64]) {
   if (!ctx || !srs || !out_xy || (n_scalars && !scalars)) return QZ_ERR_INVALID_ARG;
@@ -218,13 +271,16 @@ int qz_msm_sharded(qz_ctx* ctx, const qz_srs* srs, const void* scalars, size_t n
   if (!mine || !all || !out_dev) return ctx->fail(QZ_ERR_ALLOC, "result");
   int rc = msm_run(ctx, srs, sdev, shost, n, mine, nullptr);
   if (rc) return rc;
-  rc = comm_allgather(ctx, mine, all, 128);
-  if (rc) return rc;
-  rc = msm_sum_points_launch(ctx, all, ctx->nranks, out_dev);
+  rc = msm_exchange_sum(ctx, mine, all, out_dev);
   if (rc) return rc;
   QZ_CUDA(ctx, cudaMemcpyAsync(out_xy, out_dev, 64, cudaMemcpyDeviceToHost, st));
   QZ_CUDA(ctx, cudaEventRecord(ctx->ev_call1, st));
   QZ_CUDA(ctx, cudaStreamSynchronize(st));
+  if (ctx->pending_fault && *ctx->pending_fault) {
+    ctx->pending_fault = nullptr;
+    return ctx->fail(QZ_ERR_NCCL, "a peer did not deliver its partial sum (peer mailbox wait timed out)");
+  }
+  ctx->pending_fault = nullptr;
   cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev_call0, ctx->ev_call1);
   ctx->last_ms[1] = msm_accumulate_ms(ctx);
   return QZ_OK;
@@ -257,17 +313,16 @@ int qz_msm_split(qz_ctx* ctx, const qz_srs* srs, const void* scalars, size_t n_s
   if (!mine || !all || !out_dev) return ctx->fail(QZ_ERR_ALLOC, "result");
   int rc = msm_run(ctx, srs, sdev, shost, n, mine, nullptr, lo);
   if (rc) return rc;
-  if (G > 1) {
-    rc = comm_allgather(ctx, mine, all, 128);
-    if (rc) return rc;
-  } else {
-    all = mine;
-  }
-  rc = msm_sum_points_launch(ctx, all, G, out_dev);
+  rc = msm_exchange_sum(ctx, mine, all, out_dev);
   if (rc) return rc;
   QZ_CUDA(ctx, cudaMemcpyAsync(out_xy, out_dev, 64, cudaMemcpyDeviceToHost, st));
   QZ_CUDA(ctx, cudaEventRecord(ctx->ev_call1, st));
   QZ_CUDA(ctx, cudaStreamSynchronize(st));
+  if (ctx->pending_fault && *ctx->pending_fault) {
+    ctx->pending_fault = nullptr;
+    return ctx->fail(QZ_ERR_NCCL, "a peer did not deliver its partial sum (peer mailbox wait timed out)");
+  }
+  ctx->pending_fault = nullptr;
   cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev_call0, ctx->ev_call1);
   ctx->last_ms[1] = msm_accumulate_ms(ctx);
   return QZ_OK;

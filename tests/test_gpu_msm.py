@@ -271,3 +271,28 @@ def test_kzg_open_large_closed_form(ctx):
     qtau = (pti - yi) * pow((TAU - xi) % FR, -1, FR) % FR
     assert np.array_equal(pr.y, y)
     assert np.array_equal(pr.proof, co.g1_mul(co.g1_to_bytes(GEN), co.fr1(qtau)))
+
+
+def test_commit_split_and_accumulate_stats(ctx, kzg_big):
+    """qz_msm_split without a communicator is KZG::commit (one rank takes the whole index range; the N > 1 case runs in
+    tools/multi_gpu_check.py and the bench's HyperPlonk leg); qz_msm_accumulate_stats counts the additions the bucket
+    accumulation executes (non-zero digits) and times its launches."""
+    n = 1 << 14
+    sc = util.rand_fr(n, 4242)
+    sc[5] = 0  # a zero scalar: every digit zero, no addition
+    want = kzg_big.commit(sc)
+    assert np.array_equal(kzg_big.commit_split(sc), want)
+    d = ctx.upload(sc)
+    assert np.array_equal(kzg_big.commit_split(d), want)
+    with pytest.raises(AssertionError):
+        kzg_big.commit_split(util.rand_fr((1 << 20) + 1, 1))
+    ctx.msm_accumulate_stats(1)
+    kzg_big.commit(d)
+    kzg_big.commit(d)
+    ms, adds, launches = ctx.msm_accumulate_stats(-1)
+    digits = ctx.last_stat(1)
+    assert launches == 2 and ms > 0
+    assert (n - 2) * digits * 2 * 0.9 < adds <= (n - 1) * digits * 2  # one scalar is zero; a digit is zero with probability 2^-c
+    kzg_big.commit(d)
+    assert ctx.msm_accumulate_stats(0)[2] == 0  # collection stopped
+    d.free()

@@ -182,6 +182,26 @@ def test_generic_expression_across_the_persistent_rounds(ctx, n):
     assert_same(ctx, n, tabs, nodes, consts, None, b"midgenzc", zerocheck=True, threads=NCPU)
 
 
+@pytest.mark.parametrize("k,deg", [(6, 2), (8, 3), (3, 7), (2, 6), (9, 2), (4, 8)])
+@pytest.mark.parametrize("n", [6, 13, 15])
+def test_shapes_around_the_split_pass(ctx, k, deg, n):
+    """The short rounds run the split pass (one work item per folded element, then per (pair, evaluation point)) when at
+    most 8 tables and 8 evaluation points are involved, and whole pairs per thread otherwise: both sides of each limit,
+    with row widths of 1, 2 and 4 warps per evaluation point."""
+    tabs = [util.rand_fr(1 << n, 41 * n + 7 * k + t) for t in range(k)]
+    # sum over the tables of g_t * g_{t+1} ... (deg factors, wrapping around) + a constant: degree `deg`, all k tables used
+    e = py.e_const(11)
+    for t in range(k):
+        term = py.e_in(t)
+        for j in range(1, deg if t == 0 else min(deg, 2)):
+            term = py.e_mul(term, py.e_in((t + j) % k))
+        e = py.e_add(e, term)
+    nodes, consts = util.expr_from_py(e)
+    assert_same(ctx, n, tabs, nodes, consts, co.fr1(k * deg), b"split%d" % k, threads=NCPU)
+    if deg < 8:
+        assert_same(ctx, n, tabs, nodes, consts, None, b"splitzc%d" % k, zerocheck=True, threads=NCPU, device_tables=True)
+
+
 def test_logup_shaped_expression(ctx):
     """the batched expression of multiset_check.rs:132-157: (d_l (gamma + f) - 1) + alpha (d_r (gamma + g) - 1) ... times eq via zerocheck"""
     n = 13

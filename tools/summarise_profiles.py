@@ -5,6 +5,8 @@ import subprocess
 import sys
 
 TAG = sys.argv[1] if len(sys.argv) > 1 else "r01"
+REPS = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/"   # where the .ncu-rep files are
+OUT = sys.argv[3] if len(sys.argv) > 3 else "profiles/"      # where the text summaries go
 
 
 def launches(path, out, title):
@@ -51,16 +53,53 @@ def full(rep, out, title):
     open(out, "w").write("\n".join(o) + "\n")
 
 
+def hot_spots(rep, out):
+    """append, per captured launch, where the warps' stall samples fall by opcode (ncu source page, SASS view)"""
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    kern, hdr, data = None, None, collections.OrderedDict()
+    for r in rows:
+        if len(r) >= 2 and r[0] == "Kernel Name":
+            kern = f"{len(data)}: {r[1][:90]}"
+            data[kern] = []
+            hdr = None
+        elif r and r[0] == "Address":
+            hdr = r
+        elif hdr and kern and len(r) == len(hdr):
+            data[kern].append(dict(zip(hdr, r)))
+    o, seen = [], set()
+    for k, v in data.items():
+        tot = sum(int(x.get("# Samples") or 0) for x in v) or 1
+        sig = (k.split(": ", 1)[1], len(v), tot)  # the page lists a launch once per view: keep the first
+        if sig in seen:
+            continue
+        seen.add(sig)
+        by, cnt = collections.Counter(), collections.Counter()
+        for x in v:
+            parts = x["Source"].split()
+            if not parts:
+                continue
+            op = parts[1] if parts[0].startswith("@") and len(parts) > 1 else parts[0]
+            key = op.split(".")[0] + (".WIDE" if "WIDE" in op else "")
+            by[key] += int(x.get("# Samples") or 0)
+            cnt[key] += 1
+        o.append(f"## stall samples by opcode, launch {k}  ({len(v)} SASS instructions, {tot} samples)")
+        for op, smp in by.most_common(8):
+            o.append(f"   {op:12s} {cnt[op]:6d} instructions  {100 * smp / tot:5.1f} % of the samples")
+    open(out, "a").write("\n".join(o) + "\n")
+
+
 if __name__ == "__main__":
     import os
     import shutil
     G = "gpurun_out/"
-    shutil.copyfile(G + "launches.csv", f"profiles/{TAG}_launches_bench_steps2.csv")
-    launches(G + "launches.csv", f"profiles/{TAG}_launches_summary.txt",
+    os.makedirs(OUT, exist_ok=True)
+    shutil.copyfile(G + "launches.csv", f"{OUT}{TAG}_launches_bench_steps2.csv")
+    launches(G + "launches.csv", f"{OUT}{TAG}_launches_summary.txt",
              f"{TAG}: ncu --metrics gpu__time_duration.sum --clock-control none -c 900 python bench.py --steps 2 --warmup 1 "
              "--no-cpu-baseline --mlpcs-log-n 0 --hyperplonk-log-rows 0   (MSMs of 2^24 with device-resident and with host scalars -- streamed in 3 ranges --, precomputed windows; sumcheck and zero-check proofs of 3 x 2^24; setup)")
     if os.path.exists(G + "lhp20.csv"):
-        launches(G + "lhp20.csv", f"profiles/{TAG}_launches_hyperplonk_2_20.txt",
+        launches(G + "lhp20.csv", f"{OUT}{TAG}_launches_hyperplonk_2_20.txt",
                  f"{TAG}: ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 python tools/profile_hp.py 20   "
                  "(setup + 2 HyperPlonk proofs of two 2^20-row traces: BASELINE config 5 on one GPU)")
     CAP = [("prof_msm", "msm_accumulate", "-k regex:msm_accumulate -c 1 python tools/profile_one.py msm 24 pre  (2^24 points, c = 22, 12 mixed additions per point)"),
@@ -71,5 +110,6 @@ if __name__ == "__main__":
            ("prof_zc", "sc_round_zc", "-k regex:sc_round_zc -c 2 python tools/profile_one.py zerocheck 24  (eq-factored zero-check: round 0 and round 1)"),
            ("prof_ntt", "ntt_pass", "-k regex:ntt_pass -c 3 python tools/profile_one.py mlpcs 22  (forward 2^23 transform: passes of 8 + 8 + 7 stages)")]
     for rep, name, what in CAP:
-        if os.path.exists(G + rep + ".ncu-rep"):
-            full(G + rep + ".ncu-rep", f"profiles/{TAG}_ncu_{name}.txt", f"{TAG}: ncu --set full --clock-control none {what}")
+        if os.path.exists(REPS + rep + ".ncu-rep"):
+            full(REPS + rep + ".ncu-rep", f"{OUT}{TAG}_ncu_{name}.txt", f"{TAG}: ncu --set full --clock-control none {what}")
+            hot_spots(REPS + rep + ".ncu-rep", f"{OUT}{TAG}_ncu_{name}.txt")
