@@ -213,6 +213,10 @@ int qz_zerocheck_prove_sharded(qz_ctx* ctx, size_t num_vars, size_t k, const voi
                                size_t n_consts, uint8_t state[32], size_t max_coeffs, uint8_t* out_coeffs,
                                uint32_t* out_lens, uint8_t* out_point, uint8_t out_eval[32], uint8_t* out_z);
 
+/* Collective (every rank calls it): re-agree on the peer-mailbox sequence numbers after a sharded call returned an error
+ * on some rank -- a rank that left a call early has consumed fewer exchange numbers than the others and every later
+ * wait would time out (QZ_ERR_NCCL after 20 s).  Also clears the timed-out mark.  A no-op without a communicator. */
+int qz_comm_resync(qz_ctx* ctx);
 /* All-gather of `bytes` host bytes per rank into `recv` (nranks * bytes, rank-major) over the library's communicator:
  * the exchange of (evaluation, S commitment) and of finished openings between the halves above. */
 int qz_comm_allgather_host(qz_ctx* ctx, const void* send, void* recv, size_t bytes);

@@ -24,7 +24,7 @@ SYMBOLS = [
     "qz_msm", "qz_kzg_commit", "qz_kzg_open", "qz_mlpcs_open", "qz_mlpcs_open_begin", "qz_mlpcs_open_finish",
     "qz_compute_s_polynomial",
     "qz_sumcheck_prove", "qz_zerocheck_prove", "qz_eq_table", "qz_logup_denominators",
-    "qz_comm_unique_id", "qz_comm_init", "qz_comm_peer_memory", "qz_msm_sharded", "qz_msm_split", "qz_sumcheck_prove_sharded", "qz_zerocheck_prove_sharded", "qz_comm_allgather_host",
+    "qz_comm_unique_id", "qz_comm_init", "qz_comm_peer_memory", "qz_msm_sharded", "qz_msm_split", "qz_sumcheck_prove_sharded", "qz_zerocheck_prove_sharded", "qz_comm_allgather_host", "qz_comm_resync",
     "qz_last_elapsed_ms", "qz_last_stat", "qz_msm_accumulate_stats", "qz_bench_imad", "qz_bench_fp_mul",
     "qz_test_field_op", "qz_test_fold", "qz_test_g1_add", "qz_test_g1_mul",
 ]
@@ -112,6 +112,7 @@ def load():
     lib.qz_msm_sharded.argtypes = [vp, vp, vp, sz, i32, vp]
     lib.qz_msm_split.argtypes = [vp, vp, vp, sz, i32, vp]
     lib.qz_comm_allgather_host.argtypes = [vp, vp, vp, sz]
+    lib.qz_comm_resync.argtypes = [vp]
     lib.qz_last_elapsed_ms.argtypes = [vp, i32]
     lib.qz_last_elapsed_ms.restype = C.c_float
     lib.qz_last_stat.argtypes = [vp, i32]

@@ -130,6 +130,10 @@ class Context:
         """True when the ranks exchange through mailboxes in each other's HBM (CUDA IPC) instead of NCCL all-gathers."""
         return bool(self.lib.qz_comm_peer_memory(self.h))
 
+    def comm_resync(self) -> None:
+        """Collective: re-agree on the mailbox sequence numbers after a sharded call failed on some rank (qz_comm_resync)."""
+        self.check(self.lib.qz_comm_resync(self.h))
+
     def allgather(self, mine: np.ndarray) -> np.ndarray:
         """All-gather a small uint8 array over the library's communicator -> (nranks, len)."""
         mine = _u8(mine).reshape(-1)

@@ -328,6 +328,43 @@ int qz_msm_split(qz_ctx* ctx, const qz_srs* srs, const void* scalars, size_t n_s
   return QZ_OK;
 }
 
+// Re-agree on the mailbox sequence numbers after a sharded call failed somewhere (a rank that left a call early -- an
+// allocation failure, a bad argument -- has consumed fewer exchange numbers than the others, and from then on every
+// wait would time out).  Collective: every rank of the communicator calls it; all continue from the largest number
+// any rank reached, a full ring of slots further, with the timed-out mark of their own mailbox cleared.
+int qz_comm_resync(qz_ctx* ctx) {
+  if (!ctx) return QZ_ERR_INVALID_ARG;
+  if (ctx->nranks <= 1) return QZ_OK;
+  QZ_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->arena_reset();
+  cudaStream_t st = ctx->stream;
+  QZ_CUDA(ctx, cudaStreamSynchronize(st));
+  uint32_t mine[2] = {ctx->mbox_seq, ctx->gather_seq};
+  uint32_t* d_mine = (uint32_t*)ctx->arena_alloc(8);
+  uint32_t* d_all = (uint32_t*)ctx->arena_alloc((size_t)8 * ctx->nranks);
+  if (!d_mine || !d_all) return ctx->fail(QZ_ERR_ALLOC, "resync scratch");
+  QZ_CUDA(ctx, cudaMemcpyAsync(d_mine, mine, 8, cudaMemcpyHostToDevice, st));
+  int rc = comm_allgather(ctx, d_mine, d_all, 8);
+  if (rc) return rc;
+  std::vector<uint32_t> all(2 * (size_t)ctx->nranks);
+  QZ_CUDA(ctx, cudaMemcpyAsync(all.data(), d_all, 8 * (size_t)ctx->nranks, cudaMemcpyDeviceToHost, st));
+  QZ_CUDA(ctx, cudaStreamSynchronize(st));
+  uint32_t seq = 0, gseq = 0;
+  for (int g = 0; g < ctx->nranks; g++) {
+    seq = std::max(seq, all[2 * g]);
+    gseq = std::max(gseq, all[2 * g + 1]);
+  }
+  ctx->mbox_seq = seq + 2 * MBOX_SLOTS;  // past every slot a straggler may still be writing
+  ctx->gather_seq = gseq + 2;
+  if (ctx->mbox)
+    QZ_CUDA(ctx, cudaMemsetAsync(&((PeerMailbox*)ctx->mbox)->timed_out, 0, sizeof(uint32_t), st));
+  // nobody may start the next exchange before everyone has cleared its mark and taken the new numbers
+  rc = comm_allgather(ctx, d_mine, d_all, 8);
+  if (rc) return rc;
+  QZ_CUDA(ctx, cudaStreamSynchronize(st));
+  return QZ_OK;
+}
+
 int qz_comm_allgather_host(qz_ctx* ctx, const void* send, void* recv, size_t bytes) {
   if (!ctx || !send || !recv) return QZ_ERR_INVALID_ARG;
   if (bytes == 0) return QZ_OK;

@@ -112,6 +112,7 @@ extern "C" {
                                       consts: *const u8, n_consts: usize, state: *mut u8, max_coeffs: usize,
                                       out_coeffs: *mut u8, out_lens: *mut u32, out_point: *mut u8, out_eval: *mut u8,
                                       out_z: *mut u8) -> i32;
+    pub fn qz_comm_resync(ctx: *mut qz_ctx) -> i32;
     pub fn qz_comm_allgather_host(ctx: *mut qz_ctx, send: *const c_void, recv: *mut c_void, bytes: usize) -> i32;
     // ---- measurement and test hooks
     pub fn qz_last_elapsed_ms(ctx: *mut qz_ctx, which: i32) -> f32;

@@ -36,6 +36,14 @@ def main():
         want = co.msm(srs, sc, mode=1, threads=4)
         assert np.array_equal(got, want), f"rank {rank}: sharded MSM n={n} differs"
         kz.srs.free()
+        # the same product with the whole SRS and scalar vector on every rank (qz_msm_split), host and device scalars
+        kz = q.KZG.from_points(ctx, srs)
+        assert np.array_equal(kz.commit_split(sc), want), f"rank {rank}: split MSM n={n} differs"
+        d = ctx.upload(sc)
+        assert np.array_equal(kz.commit_split(d), want), f"rank {rank}: split MSM (device scalars) n={n} differs"
+        d.free()
+        kz.srs.free()
+    ctx.comm_resync()  # collective re-agreement on the mailbox sequence numbers: the exchanges below must still line up
     # ---- sumcheck ----
     exprs = [util.expr_product(3), util.expr_from_py(py.e_sub(py.e_mul(py.e_in(0), py.e_in(1)), py.e_mul(py.e_const(9), py.e_in(2))))]
     for nv in (3, 8, 11, 12, 13, 16, 18, 19, 20, 22):  # 19, 20: sc_mid's multi-block rounds exchange with the peers; 22: streaming rounds first
