@@ -589,6 +589,13 @@ def run_gpu(args):
                         "sumcheck_evaluation": bytes(sc_out["dev"][1].evaluation).hex(),
                         "zerocheck_final_transcript_state": sc_out["zc_state"].tobytes().hex() if "zc_state" in sc_out else None},
         }
+        # parity carried into every run: the digests of the default workload are pinned against the oracle by
+        # tests/test_gpu_config_sizes.py::test_bench_digests_pinned_by_the_oracle; any N must reproduce them
+        gpath = os.path.join(ROOT, "tests", "golden", f"bench_digests_2_{args.log_n}.json")
+        if os.path.exists(gpath):
+            gold = json.load(open(gpath))["digests"]
+            line["digests_match_golden"] = all(line["digests"].get(k) == v for k, v in gold.items() if line["digests"].get(k) is not None)
+            line["digests_golden"] = os.path.relpath(gpath, ROOT)
         if zc_err is not None:
             line["zerocheck"] = {"error": zc_err}
         if zc_ms is not None:

@@ -62,6 +62,24 @@ def Sub(a: VirtualPolyExpr, b: VirtualPolyExpr) -> VirtualPolyExpr:
     return a + (Const(FR - 1) * b)
 
 
+def sharded_view(ctx: Context, store: VirtualPolynomialStore) -> Optional[VirtualPolynomialStore]:
+    """Several ranks, every table resident on every rank: a store over this rank's contiguous 1/G of every table (the
+    top log2 G variables, so every (2p, 2p+1) pair stays local: sumcheck.rs:56-57) as non-owning windows, for the
+    sharded sumcheck / zero-check entry points -- instead of every rank proving the whole table.  None when the store
+    does not qualify (one rank, host tables, fewer than 2^12 entries per rank)."""
+    G, rank = getattr(ctx, "nranks", 1), getattr(ctx, "rank", 0)
+    n = 1 << store.num_vars
+    if G <= 1 or n % G or n // G < (1 << 12):
+        return None
+    if not store.polynomials or not all(isinstance(p, DeviceBuffer) and p.nbytes == 32 * n for p in store.polynomials):
+        return None
+    part = VirtualPolynomialStore(store.num_vars)
+    shard = 32 * (n // G)
+    part.polynomials = [p.view(rank * shard, shard) for p in store.polynomials]
+    part.virtual_polys = store.virtual_polys
+    return part
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 class OpeningPool:
     """Several ranks: the second halves of ALL the MLEvalProofs of one proof, run at the end as one balanced pool.
@@ -249,7 +267,11 @@ class MultisetEqualityProof:
         store.mul_const_in_place(h_hat, alpha)  # :156-158
         store.add_in_place(h_hat, dl)
         store.sub_in_place(h_hat, dr, fr_mont(FR - 1))
-        sc, claim = SumcheckProof.prove(ctx, num_vars, store, h_hat, fr_mont(0), transcript)  # :162-163
+        part = sharded_view(ctx, store)
+        if part is not None:  # :162-163, each rank on its shard of the tables (same bytes: tools/multi_gpu_check.py)
+            sc, claim = SumcheckProof.prove(ctx, num_vars, part, h_hat, fr_mont(0), transcript, sharded=True)
+        else:
+            sc, claim = SumcheckProof.prove(ctx, num_vars, store, h_hat, fr_mont(0), transcript)
         point = claim.point
         proof = MultisetEqualityProof(c_left, c_right, sc, None, None)
         own_batch = batch is None
@@ -427,7 +449,11 @@ class HyperPlonk:
         for i, e in enumerate(exprs):
             zc_expr = zc_expr + (Const(pow(alpha, i, FR)) * e)
         zc_virtual = store.new_virtual_from_expr(zc_expr)
-        zero_check_proof, zc_claim = ZeroCheckProof.prove(ctx, store, zc_virtual, transcript)  # :178-180
+        part = sharded_view(ctx, store)
+        if part is not None:  # :178-180, each rank on its shard of the columns
+            zero_check_proof, zc_claim = ZeroCheckProof.prove(ctx, part, zc_virtual, transcript, sharded=True)
+        else:
+            zero_check_proof, zc_claim = ZeroCheckProof.prove(ctx, store, zc_virtual, transcript)
         store2 = VirtualPolynomialStore(log2_rows + log2_cols)  # :184-196
         w_idx = store2.allocate_polynomial(full_witness)
         w_virtual = store2.new_virtual_from_input(w_idx)

@@ -152,3 +152,42 @@ def test_hyperplonk_config5_2_20_rows(ctx):
     state = _prove_and_verify(ctx, 20, py.G1_GEN)  # bench.py's SRS: the standard generator (1, 2), same tau
     golden = os.path.join(os.path.dirname(__file__), "golden", "hyperplonk_2_20_state.txt")
     assert state == open(golden).read().strip()
+
+
+def test_bench_digests_pinned_by_the_oracle(ctx):
+    """tests/golden/bench_digests_2_24.json holds the commitment and the final transcript states of bench.py's default
+    2^24 workload; bench.py compares every run with it at every GPU count (inputs are seeded by global index), so the
+    file is what carries parity into the driver's multi-GPU runs.  Here the file itself is held to the oracle: the
+    commitment through the closed form p(tau) * g, the sumcheck and zero-check transcripts through the multi-threaded
+    C++ restatement on the very same tables."""
+    import json
+
+    import bench
+
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bench_digests_2_24.json")))
+    d, n = g["digests"], g["log_n"]
+    ncpu = os.cpu_count() or 1
+    # commitment of the bench's scalars on srs[i] = tau^i * (1, 2)
+    sc = ctx.random_fr(1 << n, bench.shard_seed(0x5155494C4C, 0))
+    y, _ = co.kzg_open_quotient(sc.download().reshape(-1, 32), co.fr1(bench.TAU))
+    sc.free()
+    want = co.g1_mul(co.g1_to_bytes((1, 2)), y)  # the generator bench.py uses
+    assert bytes(want).hex() == d["commitment_xy"]
+    assert ctx.g1_serialize(want).hex() == d["commitment_serialized"]
+    # the three tables, the true sum, both transcripts
+    tabs = []
+    for t in range(3):
+        b = ctx.random_fr(1 << n, bench.shard_seed(1000 * (t + 1), 0))
+        tabs.append(b.download().reshape(-1, 32))
+        b.free()
+    nodes, consts = util.expr_product(3)
+    claimed = co.fr1(int(d["sumcheck_claimed_sum"], 16))
+    st = co.transcript_new(b"sumcheck_bench")
+    o = co.sumcheck_prove(n, tabs, nodes, consts, claimed, st, max_coeffs=8, threads=ncpu)
+    c0 = co.from_mont(o["coeffs"][0][: o["lens"][0]])
+    assert (2 * c0[0] + sum(c0[1:])) % FR == int(d["sumcheck_claimed_sum"], 16)  # the claim is the true sum (SURVEY 8d)
+    assert st.tobytes().hex() == d["sumcheck_final_transcript_state"]
+    assert bytes(o["evaluation"]).hex() == d["sumcheck_evaluation"]
+    st = co.transcript_new(b"zerocheck_bench")
+    co.sumcheck_prove(n, tabs, nodes, consts, None, st, max_coeffs=8, zerocheck=True, threads=ncpu)
+    assert st.tobytes().hex() == d["zerocheck_final_transcript_state"]

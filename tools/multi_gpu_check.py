@@ -103,6 +103,37 @@ def main():
             assert g[key] == w[key], f"rank {rank}: {key} differs"
         for key in ("opening_proof_denom_left", "opening_proof_denom_right", "r_polys"):
             assert g["permutation"][key] == w["permutation"][key], f"rank {rank}: permutation {key} differs"
+    # ---- the same at a size where the sharded commits, the sharded zero-check / logup sumchecks and the pooled openings all
+    # engage (2^14 rows; the Python oracle would need minutes): against the single-GPU prover on a context without a
+    # communicator, which tests/test_gpu_hyperplonk.py holds to the oracle ----
+    rows = 1 << 14
+    In, C = q.VirtualPolyExpr.Input, hp.Const
+
+    def fib_circuit():
+        c = hp.TransitionCircuit(rows)
+        s1, s2 = c.allocate_state_cell(), c.allocate_state_cell()
+        c.enforce_boundary_constraint(0, In(s1[0]))
+        c.enforce_boundary_constraint(0, hp.Sub(In(s2[0]), C(1)))
+        c.enforce_constraint(hp.Sub(In(s2[1]), In(s1[0]) + In(s2[0])))
+        c.enforce_constraint(hp.Sub(In(s1[1]), In(s2[0])))
+        w = [[0] * rows for _ in range(c.num_cols())]
+        a, b = 0, 1
+        for r in range(rows):
+            w[s1[0]][r], w[s2[0]][r] = a, b
+            a, b = b, (a + b) % FR
+            w[s1[1]][r], w[s2[1]][r] = a, b
+        return c, [co.to_mont(col) for col in w]
+
+    circ, wit = fib_circuit()
+    proofs = []
+    for c in (ctx, q.Context(local)):  # with the communicator, then alone
+        kz = q.KZG.trusted_setup(c, circ.num_cols() * rows, co.g1_to_bytes(gen), co.fr1(tau)).precompute()
+        pr = hp.HyperPlonk.preprocess(c, [circ], kz)
+        proofs.append(util.hyperplonk_py(pr.prove(kz, [wit])))
+        kz.srs.free()
+        if c is not ctx:
+            c.close()
+    assert proofs[0] == proofs[1], f"rank {rank}: the 2^14-row HyperPlonk proof differs from the single-GPU prover's"
     dist.barrier()
     if rank == 0:
         print(f"multi-GPU parity ok on {world} ranks: sharded MSM, sharded sumcheck, sharded zero-check and the HyperPlonk proof with its "
