@@ -501,6 +501,19 @@ def run_gpu(args):
 
     # (the nvidia-smi sampler is stopped first: its 200 ms polling contends for the driver and slows these
     # launch- and allocation-heavy legs several times over; the headline legs above are one call per step)
+    # ---- config 2: KZG commit MSM of 2^20 scalars on one B200 (its own SRS and window table), N = 1 only ----
+    msm20 = None
+    if world == 1 and args.log_n >= 20 and not args.no_precompute:
+        k20 = q.KZG.trusted_setup(ctx, (1 << 20) - 1, g_bytes, mont(TAU)).precompute()
+        s20 = ctx.random_fr(1 << 20, shard_seed(0x5155494C4C, 0))
+        ms20, l20 = timed_loop(lambda: results.__setitem__("c20", k20.commit(s20)), args.steps, args.warmup)
+        msm20 = {"value": (1 << 20) / (ms20 * 1e-3), "unit": "points/s", "ms_per_step": ms20, "gpu_launches": l20 // args.steps,
+                 "window_bits": ctx.last_stat(0), "mixed_adds_per_point": ctx.last_stat(1),
+                 "commitment_xy": bytes(results["c20"]).hex(),
+                 "workload": "KZG::commit of 2^20 random Fr scalars, device-resident, precomputed windows (BASELINE config 2)"}
+        s20.free()
+        k20.srs.free()
+
     # ---- config 4: multilinear PCS commit + open (MLEvalProof::prove: 5 MSMs + NTT), N = 1 only ----
     mlpcs = None
     if world == 1 and args.mlpcs_log_n > 0:
@@ -605,6 +618,8 @@ def run_gpu(args):
                                  "workload": f"ZeroCheckProof::prove of f*g*e over three 2^{args.log_n}-entry tables: z drawn on the device, "
                                              "eq-factored rounds (degree-3 sums weighted by the eq table of the remaining variables, "
                                              "times the round's linear eq factor)"}
+        if msm20:
+            line["msm_2_20"] = msm20
         if mlpcs:
             mlpcs["roofline"] = imad_roofline(mlpcs.pop("_acc_stats"), imad_peak, mlpcs.pop("_ms"), mlpcs.pop("_steps"))
             line["mlpcs_commit_open"] = mlpcs
