@@ -77,6 +77,17 @@ struct NttTile {
 // -- so an element that ends at local index t has collected w^(lo 2^s0 brev_T(t)).  A strided pass is therefore a plain
 // local transform plus ONE correction product per element, applied while the tile is stored (forward) or, inverted,
 // while it is loaded (inverse): the four-step decomposition, done per pass.
+// Where element (t, u) of the tile lives.  The transfer loops walk t with u fixed, i.e. in steps of C 16-byte units per
+// plane: with C >= 8 every lane of a quarter-warp lands on the same four banks (ncu r01: 30 M conflicts in 64 M
+// wavefronts for the 7-stage pass, C = 8), with C = 4 or 2 every second or fourth.  XOR-ing the column with bits of t
+// spreads eight consecutive t over the eight 16-byte bank groups, and the butterflies, which walk u with t fixed, still
+// touch one contiguous row (a permutation of it).
+QZ_DEV int ntt_slot(int t, int u, int logC) {
+  const int C = 1 << logC;
+  const int sw = logC >= 3 ? (t & 7) : (t >> (3 - logC)) & (C - 1);
+  return t * C + (u ^ sw);
+}
+
 template <bool INVERSE>
 __global__ void __launch_bounds__(NTT_THREADS) ntt_pass(uint4* data, int log_m, int s0, int T, int logC, const Fr* W) {
   __shared__ NttTile tile;
@@ -96,10 +107,11 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass(uint4* data, int log_m, 
         const uint64_t E = (lo * (uint64_t)(__brev((unsigned)t) >> (32 - T))) << s0;
         Fr v = fp_load<FrParams>(src);
         if (E) v = E > half_m ? fp_mul<FrParams>(v, W[m - E]) : fp_neg<FrParams>(fp_mul<FrParams>(v, W[half_m - E]));
-        tile.set(t * C + u, v);
+        tile.set(ntt_slot(t, u, logC), v);
       } else {
-        tile.lo[t * C + u] = src[0];
-        tile.hi[t * C + u] = src[1];
+        const int slot = ntt_slot(t, u, logC);
+        tile.lo[slot] = src[0];
+        tile.hi[slot] = src[1];
       }
     }
     __syncthreads();
@@ -108,7 +120,8 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass(uint4* data, int log_m, 
       const int lhalf = 1 << (T - 1 - ls), s = s0 + ls;
       for (int bb = threadIdx.x; bb < (n_elems >> 1); bb += blockDim.x) {
         const int u = bb & (C - 1), b = bb >> logC;
-        const int j_l = b & (lhalf - 1), i0 = (((b - j_l) << 1) + j_l) * C + u, i1 = i0 + lhalf * C;
+        const int j_l = b & (lhalf - 1), t0 = ((b - j_l) << 1) + j_l;
+        const int i0 = ntt_slot(t0, u, logC), i1 = ntt_slot(t0 + lhalf, u, logC);
         const uint64_t e = ((uint64_t)j_l << lo_bits) << s;  // the part of the twiddle exponent all sub-tiles share, < m/2
         const Fr a = tile.get(i0), v = tile.get(i1);
         if (!INVERSE) {
@@ -130,12 +143,13 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass(uint4* data, int log_m, 
       uint4* dst = data + 2 * ((hi << (log_m - s0)) + lo + (uint64_t)t * stride);
       if (!INVERSE && lo) {  // the correction: w^E, E = lo * brev_T(t) << s0 (< m)
         const uint64_t E = (lo * (uint64_t)(__brev((unsigned)t) >> (32 - T))) << s0;
-        Fr v = tile.get(t * C + u);
+        Fr v = tile.get(ntt_slot(t, u, logC));
         if (E) v = E < half_m ? fp_mul<FrParams>(v, W[E]) : fp_neg<FrParams>(fp_mul<FrParams>(v, W[E - half_m]));
         fp_store<FrParams>(dst, v);
       } else {
-        dst[0] = tile.lo[t * C + u];
-        dst[1] = tile.hi[t * C + u];
+        const int slot = ntt_slot(t, u, logC);
+        dst[0] = tile.lo[slot];
+        dst[1] = tile.hi[slot];
       }
     }
     __syncthreads();
