@@ -47,7 +47,7 @@ def main():
 
     ref = None
     for var, arg, settings in (("QZ_MSM_SEGMENTS_DEV", dev, ["1", "1,1"]),
-                               ("QZ_MSM_SEGMENTS", host, ["1", "1,3,9", "1,4,12", "1,4,16", "1,3.5,10", "2,7,20", "1,5"])):
+                               ("QZ_MSM_SEGMENTS", host, ["1", "1,3,9", "1,4,12", "1,2", "1,3", "1,7", "1,2,5", "1,5"])):
         for s in settings:
             os.environ[var] = s
             ms, acc, r = timed(lambda: kzg.commit(arg))
