@@ -81,6 +81,8 @@ struct qz_ctx {
 
   // cached device constants: interpolation matrices keyed by degree (< 1000), NTT twiddle tables keyed by 1000 + log2 size
   std::map<int, void*> cache;
+  // resident blocks per SM by (kernel, block size): the runtime is asked once per context (sumcheck.cu blocks_per_sm)
+  std::map<std::pair<const void*, int>, int> occupancy;
 
   cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
 

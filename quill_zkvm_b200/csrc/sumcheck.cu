@@ -904,15 +904,28 @@ __global__ void k_fold_fixed(const uint4* a0, const uint4* a1, uint4* out, size_
 // for a zero-check the n challenges drawn before the header (zerocheck.rs:20-22); then num_vars (u64 LE) and
 // claimed_sum are absorbed (sumcheck.rs:35-36).  zinv (optional): 1 / z_j for the SKIP1 rounds of the eq-factored
 // zero-check, by one batched inversion (Montgomery's trick: 3 products per element + one binary-Euclid inverse).
-__global__ void __launch_bounds__(32) sc_begin(ScHead* head, const uint8_t* state_in, uint64_t num_vars, Fr claimed_sum,
-                                               int zc_n, Fr* z, Fr* zinv, ScMidSync* sync, PeerMailbox* mbox) {
+// The caller's transcript state and the compiled program travel as kernel ARGUMENTS (32 B + 2 KiB of the 4 KiB parameter
+// space) and are written to device memory here: a proof without constants needs no host-to-device copy at all (the
+// copy's DMA round trip was ~8 us of a small proof's ~85 us of fixed cost).
+struct ScStateArg {
+  uint8_t b[32];
+};
+__global__ void __launch_bounds__(32) sc_begin(ScHead* head, const __grid_constant__ ScStateArg state_in, uint64_t num_vars,
+                                               Fr claimed_sum, int zc_n, Fr* z, Fr* zinv, ScMidSync* sync, PeerMailbox* mbox,
+                                               const __grid_constant__ ScProgram prog_in, ScProgram* prog_out) {
   __shared__ __align__(16) uint32_t buf[32];
   const int t = threadIdx.x;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&prog_in);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(prog_out);
+    const int words = 4 + (int)prog_in.n_ops;  // header + the ops in use
+    for (int i = t; i < words; i += 32) dst[i] = src[i];
+  }
   if (t == 0) {
     sync->arrive = 0;
     sync->flag = 0;
     if (mbox) mbox->timed_out = 0;  // a wait that timed out in an earlier proof must not void this one
-    for (int i = 0; i < 32; i++) head->tstate[i] = state_in[i];
+    for (int i = 0; i < 32; i++) head->tstate[i] = state_in.b[i];
     head->r = fp_zero<FrParams>();
     head->evaluation = fp_zero<FrParams>();
     head->zc_prefix = fp_one<FrParams>();
@@ -1181,6 +1194,22 @@ int get_vinv(qz_ctx* ctx, int d, Fr** out) {
   return QZ_OK;
 }
 
+// resident blocks per SM of a kernel, asked of the runtime once per context (the query costs microseconds and a proof
+// asked three or four of them: a tenth of a small proof's fixed cost)
+template <class Kernel>
+int blocks_per_sm(qz_ctx* ctx, Kernel kern, int threads) {
+  const std::pair<const void*, int> key((const void*)kern, threads);
+  auto it = ctx->occupancy.find(key);
+  if (it != ctx->occupancy.end()) return it->second;
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0) != cudaSuccess) {
+    cudaGetLastError();
+    occ = 0;
+  }
+  ctx->occupancy[key] = occ;
+  return occ;
+}
+
 int round_grid(qz_ctx* ctx, uint64_t n_pairs, int blocks_per_sm, int threads = SC_THREADS) {
   uint64_t want = (n_pairs + threads - 1) / threads;
   uint64_t cap = (uint64_t)ctx->sm_count * blocks_per_sm;
@@ -1345,7 +1374,7 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
   // pinned staging buffer and the outputs (head, coefficients, lengths, point, z) come back in ONE copy: every extra
   // cudaMemcpyAsync is ~5-10 us on a call whose fixed cost is otherwise ~100 us.
   auto up32 = [](size_t v) { return (v + 31) & ~(size_t)31; };
-  const size_t in_state = 0, in_prog = 32, in_consts = in_prog + up32(sizeof(ScProgram)), in_bytes = in_consts + 32 * n_consts;
+  const size_t in_prog = 32, in_consts = in_prog + up32(sizeof(ScProgram)), in_bytes = in_consts + 32 * n_consts;
   const size_t coeff_bytes = 32 * num_vars * max_coeffs, lens_bytes = 4 * num_vars, pt_bytes = 32 * num_vars;
   const size_t o_head = 0, o_coeffs = up32(sizeof(ScHead)), o_lens = o_coeffs + coeff_bytes, o_point = o_lens + up32(lens_bytes),
                o_z = o_point + pt_bytes, out_bytes = o_z + pt_bytes;
@@ -1361,10 +1390,10 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
   Fr* d_z = (Fr*)(d_out + o_z);
   ScProgram* d_prog = (ScProgram*)(d_in + in_prog);
   Fr* d_consts = (Fr*)(d_in + in_consts);
-  memcpy(pin + in_state, state, 32);
-  memcpy(pin + in_prog, &cp.prog, sizeof(ScProgram));
-  if (n_consts) memcpy(pin + in_consts, consts, 32 * n_consts);
-  QZ_CUDA(ctx, cudaMemcpyAsync(d_in, pin, in_bytes, cudaMemcpyHostToDevice, st));
+  if (n_consts) {  // the constants are the only small input that still needs a copy
+    memcpy(pin + in_consts, consts, 32 * n_consts);
+    QZ_CUDA(ctx, cudaMemcpyAsync(d_in + in_consts, pin + in_consts, 32 * n_consts, cudaMemcpyHostToDevice, st));
+  }
   bool zc_skip1 = false;
   Fr* d_zinv = nullptr;
   ScMidSync* d_sync = nullptr;
@@ -1384,9 +1413,11 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
     d_sync = (ScMidSync*)ctx->arena_alloc(sizeof(ScMidSync));
     d_foldc = (uint32_t*)ctx->arena_alloc(64 * sizeof(uint32_t));
     if (!d_sync || !d_foldc) return ctx->fail(QZ_ERR_ALLOC, "round counters");
-    QZ_LAUNCH(ctx, sc_begin, 1, 32, 0, head, (const uint8_t*)(d_in + in_state), (uint64_t)num_vars, cs,
-              zerocheck ? (int)num_vars : 0, d_z, d_zinv, d_sync,
-              (PeerMailbox*)(sharded && comm_has_peers(ctx) ? ctx->mbox : nullptr));  // zerocheck.rs:20-22, sumcheck.rs:35-36
+    ScStateArg state_arg;
+    memcpy(state_arg.b, state, 32);
+    QZ_LAUNCH(ctx, sc_begin, 1, 32, 0, head, state_arg, (uint64_t)num_vars, cs, zerocheck ? (int)num_vars : 0, d_z, d_zinv,
+              d_sync, (PeerMailbox*)(sharded && comm_has_peers(ctx) ? ctx->mbox : nullptr), cp.prog,
+              d_prog);  // zerocheck.rs:20-22, sumcheck.rs:35-36
   }
 
   // Host tables of a large proof are copied in UP_CHUNKS slices on the second stream and round 0 (evaluate only: every
@@ -1459,15 +1490,15 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
     // occupancy-sized grids for the streaming rounds
     int bps = 1;
     int bps_wide = 0;  // > 0: a deferred-reduction variant of the round kernel exists for this product
-    if (cp.product_k == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sc_round_prod<1, false, true>, SC_THREADS, 0);
-    else if (cp.product_k == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sc_round_prod<2, false, true>, SC_THREADS, 0);
+    if (cp.product_k == 1) bps = blocks_per_sm(ctx, sc_round_prod<1, false, true>, SC_THREADS);
+    else if (cp.product_k == 2) bps = blocks_per_sm(ctx, sc_round_prod<2, false, true>, SC_THREADS);
     else if (cp.product_k == 3) {
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sc_round_prod<3, false, true>, SC_THREADS, 0);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_wide, sc_round_prod<3, true, true>, SC_WIDE_THREADS, 0);
+      bps = blocks_per_sm(ctx, sc_round_prod<3, false, true>, SC_THREADS);
+      bps_wide = blocks_per_sm(ctx, sc_round_prod<3, true, true>, SC_WIDE_THREADS);
     } else if (cp.product_k == 4) {
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sc_round_prod<4, false, true>, SC_THREADS, 0);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_wide, sc_round_prod<4, true, true>, SC_WIDE_THREADS, 0);
-    } else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sc_round_generic<true>, SC_THREADS, 0);
+      bps = blocks_per_sm(ctx, sc_round_prod<4, false, true>, SC_THREADS);
+      bps_wide = blocks_per_sm(ctx, sc_round_prod<4, true, true>, SC_WIDE_THREADS);
+    } else bps = blocks_per_sm(ctx, sc_round_generic<true>, SC_THREADS);
     if (bps < 1) bps = 1;
     if (getenv("QZ_SC_NARROW")) bps_wide = 0;  // measurement switch: force the fully reduced sums
     Fr* partials = (Fr*)ctx->arena_alloc(sizeof(Fr) * std::max<size_t>((size_t)ctx->sm_count * std::max(bps, bps_wide), SC_THREADS) * (d + 1) * up_chunks);
@@ -1491,11 +1522,11 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
       rc = get_vinv(ctx, K, &vinv_k);
       if (rc) return rc;
       int zb = 1, zb_wide = 0;
-      if (K == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&zb, sc_round_zc<1, false, true, false>, SC_THREADS, 0);
-      else if (K == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&zb, sc_round_zc<2, false, true, false>, SC_THREADS, 0);
+      if (K == 1) zb = blocks_per_sm(ctx, sc_round_zc<1, false, true, false>, SC_THREADS);
+      else if (K == 2) zb = blocks_per_sm(ctx, sc_round_zc<2, false, true, false>, SC_THREADS);
       else {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&zb, sc_round_zc<3, false, true, false>, SC_THREADS, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&zb_wide, sc_round_zc<3, true, true, false>, SC_WIDE_THREADS, 0);
+        zb = blocks_per_sm(ctx, sc_round_zc<3, false, true, false>, SC_THREADS);
+        zb_wide = blocks_per_sm(ctx, sc_round_zc<3, true, true, false>, SC_WIDE_THREADS);
       }
       zb = std::max(1, std::min(zb, std::max(bps, bps_wide)));  // `partials` was sized for max(bps, bps_wide) blocks per SM
       zb_wide = std::min(zb_wide, std::max(bps, bps_wide));
@@ -1728,8 +1759,7 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
       // the grid: as many blocks as the widest remaining round uses (the kernel derives every round's share from
       // gridDim.x with the same plan), all co-resident, and never more than a block has threads (the closing block
       // reads the parked vectors one per thread)
-      int occ = 1;
-      QZ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SC_THREADS, 0));
+      int occ = blocks_per_sm(ctx, kern, SC_THREADS);
       if (occ < 1) occ = 1;
       const unsigned int cap = (unsigned int)std::min<uint64_t>(SC_THREADS, (uint64_t)ctx->sm_count * occ);
       ScMidPlan plan;
