@@ -578,7 +578,9 @@ inline unsigned int mid_make_plan(ScMidPlan& plan, uint64_t size, int pending, i
     // split: at least 32 pairs per block (below that the round is two product latencies whatever the count).  Once a
     // block would get more than SC_SPLIT_MAX_CHUNK pairs its multiplier is busy either way and whole pairs per thread
     // (one pair per thread and more) need no tiles, no barriers and one product less per pair in round 0.
-    uint64_t nb = std::max<uint64_t>(1, std::min<uint64_t>((n_pairs + 31) / 32, cap));
+    // A round of up to 128 pairs stays on one block: two tiles cost ~3 us more than one, gathering the vectors of
+    // several blocks ~5 us (tools/sc_trace.py).
+    uint64_t nb = n_pairs <= 128 ? 1 : std::max<uint64_t>(1, std::min<uint64_t>((n_pairs + 31) / 32, cap));
     uint64_t ch = (n_pairs + nb - 1) / nb;
     if (tile > 0 && ch <= (uint64_t)SC_SPLIT_MAX_CHUNK) {
       nb = (n_pairs + ch - 1) / ch;
@@ -628,6 +630,7 @@ QZ_DEV void mid_split_pass(const ScTables& view, uint64_t p_begin, uint64_t p_en
       s_tile[item] = v;
     }
     __syncthreads();
+    SC_TRACE(8);
     if (xi < ns) {
       for (int pr = ri; pr < np; pr += rw) {
         constexpr int KC = KP > 0 ? KP : 8;
@@ -658,6 +661,7 @@ QZ_DEV void mid_split_pass(const ScTables& view, uint64_t p_begin, uint64_t p_en
       }
     }
     __syncthreads();
+    SC_TRACE(9);
   }
   acc = warp_sum(acc);
   if (lane == 0) s_rows[warp] = acc;

@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import quill_zkvm_b200 as q  # noqa: E402
 from quill_zkvm_b200 import _lib  # noqa: E402
 
-NAMES = {1: "round start", 2: "pairs done", 3: "block sums / arrive", 4: "closer has sums", 10: "interpolated", 11: "message ready",
+NAMES = {1: "round start", 8: "tile folded", 9: "tile evaluated", 2: "pairs done", 3: "block sums / arrive", 4: "closer has sums", 10: "interpolated", 11: "message ready",
          12: "absorbed", 13: "challenge drawn", 6: "closed", 7: "released"}
 
 
@@ -42,7 +42,7 @@ def main():
     for ident, blk, clk, gt in sorted(recs, key=lambda r: r[3]):
         if ident == 1 and blk == 0:
             rnd += 1
-        if blk == 0 or ident in (4, 10, 11, 12, 13, 6):
+        if (blk == 0 and ident not in (8, 9)) or ident in (4, 10, 11, 12, 13, 6) or (blk == 0 and ident in (8, 9)):
             d = "" if last is None else f"+{(gt - last) / 1e3:7.2f} us"
             print(f"round {rnd:2d} blk {blk:3d} {NAMES.get(ident, ident):22s} t={(gt - t0) / 1e3:9.2f} us {d}  clk {clk}")
             last = gt
