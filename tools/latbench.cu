@@ -48,6 +48,22 @@ __global__ void klat4(uint32_t* state_g, long long* t, Fr* sink) {
   }
 }
 
+// ILP probe: do two (four) independent dependent-product chains overlap in one thread?  Cycles per step of 1, 2, 4 chains.
+__global__ void kilp(long long* t, Fr* sink, Fr seed) {
+  if (threadIdx.x != 0) return;
+  Fr a = seed, b = seed, c = seed, d = seed, m = seed;
+  a.v[0] ^= 1; b.v[0] ^= 2; c.v[0] ^= 3; d.v[0] ^= 4;
+  long long t0 = clock64();
+  for (int i = 0; i < 16; i++) a = fp_mul<FrParams>(a, m);
+  long long t1 = clock64();
+  for (int i = 0; i < 16; i++) { a = fp_mul<FrParams>(a, m); b = fp_mul<FrParams>(b, m); }
+  long long t2 = clock64();
+  for (int i = 0; i < 16; i++) { a = fp_mul<FrParams>(a, m); b = fp_mul<FrParams>(b, m); c = fp_mul<FrParams>(c, m); d = fp_mul<FrParams>(d, m); }
+  long long t3 = clock64();
+  *sink = fp_add<FrParams>(fp_add<FrParams>(a, b), fp_add<FrParams>(c, d));
+  t[0] = (t1 - t0) / 16; t[1] = (t2 - t1) / 16; t[2] = (t3 - t2) / 16;
+}
+
 // dependent-load latency of the three global load flavours the short rounds could use (pointer chase over 4 KiB)
 __global__ void kload(const uint32_t* chain, long long* t, uint32_t* sink) {
   if (threadIdx.x != 0) return;
@@ -79,6 +95,15 @@ int main() {
     long long h[2];
     cudaMemcpy(h, t, 16, cudaMemcpyDeviceToHost);
     printf("four lanes: absorb(3 blocks) %lld cyc | draw_fr %lld cyc   %s\n", h[0], h[1], cudaGetErrorString(cudaGetLastError()));
+  }
+  for (int rep = 0; rep < 2; rep++) {
+    Fr seed;
+    for (int i = 0; i < 8; i++) seed.v[i] = 0x01234567u * (i + 1);
+    seed.v[7] &= 0x0fffffffu;
+    kilp<<<1, 32>>>(t, sink, seed);
+    long long r[3];
+    cudaMemcpy(r, t, 24, cudaMemcpyDeviceToHost);
+    printf("ILP probe: 1 chain %lld cyc/step | 2 chains %lld | 4 chains %lld   %s\n", r[0], r[1], r[2], cudaGetErrorString(cudaGetLastError()));
   }
   {
     uint32_t h[1024], *d, *sk;
