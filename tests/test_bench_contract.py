@@ -33,3 +33,26 @@ def test_reference_arm_other_ranks_exit_quietly():
                          timeout=600, cwd=ROOT, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     assert not [l for l in out.stdout.splitlines() if l.startswith("{")]
+
+
+def test_traffic_comes_from_the_committed_profiles_and_config_is_shared():
+    """roofline.traffic is read from the newest ncu summary under profiles/ (not a constant in bench.py); both arms of
+    the bench print the same `config` object; the digest file the GPU arm compares itself with is complete."""
+    import argparse
+    import json
+
+    import bench
+
+    msm, msm_src = bench.profile_traffic("msm")
+    sc, sc_src = bench.profile_traffic("sumcheck")
+    assert msm_src.startswith("profiles/") and sc_src.startswith("profiles/")
+    assert 14.5e9 < msm < 40e9      # algorithmic 14.5 GB; the 64-byte gathers pull 128-byte lines
+    assert 6.0e9 < sc < 7.5e9       # algorithmic 6.44 GB: no re-reads
+    args = argparse.Namespace(log_n=24, no_precompute=False)
+    assert bench.workload_config(args, 1) == bench.workload_config(args, 1, peer_memory=False)  # one GPU: no exchange
+    assert bench.workload_config(args, 8)["exchange"] != bench.workload_config(args, 8, peer_memory=False)["exchange"]
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_digests_2_24.json")))
+    assert g["log_n"] == 24 and set(g["digests"]) >= {"commitment_xy", "commitment_serialized", "sumcheck_claimed_sum",
+                                                      "sumcheck_final_transcript_state", "sumcheck_evaluation",
+                                                      "zerocheck_final_transcript_state"}
+    assert bench.shard_seed(5, 0) == 5 and bench.shard_seed(5, 1) == (5 + 4 * bench.GOLDEN64) % (1 << 64)
