@@ -87,9 +87,10 @@ class OpeningPool:
     An MLEvalProof's four KZG openings (mlpcs.rs:109-113) are never absorbed by the transcript -- only its evaluation
     and S commitment are (mlpcs.rs:100-102) -- so nothing that follows depends on them.  A batch therefore only runs
     the first halves (dealt to the ranks), exchanges (evaluation, S commitment), replays the transcript and leaves
-    (opening, r) here; `finish` deals the 4 x (number of openings) KZG openings of the whole proof to the ranks at
-    once: the two openings of S stay with the rank that holds S, the two of the polynomial (resident on every rank) go
-    to whichever rank is least loaded.  With 13 openings per trace and 8 ranks, per-batch dealing left most ranks idle
+    (opening, r) here, where the 4 x (number of openings) KZG openings of the whole proof form one pool: the two openings
+    of S stay with the rank that holds S, the two of the polynomial (resident on every rank) go to whichever rank is
+    least loaded; they run when a rank would otherwise wait for a later batch's slowest first half, and the rest in
+    `finish`.  With 13 openings per trace and 8 ranks, per-batch dealing left most ranks idle
     half of the time (two openings on some ranks, one on the others, traces of different sizes back to back)."""
 
     def __init__(self, ctx: Context, pcs: KZG, nranks: Optional[int] = None, rank: Optional[int] = None):
@@ -98,6 +99,9 @@ class OpeningPool:
         self.rank = getattr(ctx, "rank", 0) if rank is None else rank
         self.load = [0.0] * self.nranks  # cost dealt so far, in polynomial entries x MSMs
         self.entries, self.after = [], []
+        self.place = {}    # (opening, slot) -> rank that runs that KZG opening
+        self.done = {}     # (opening, slot) -> x ‖ y ‖ proof, for the openings this rank has run
+        self.placed = 0    # openings whose four KZG openings have a rank
 
     BEGIN_COST = 1.6  # first half of an opening in units of one MSM of its length: commit(S) + three transforms
 
@@ -113,49 +117,68 @@ class OpeningPool:
     def on_done(self, fn) -> None:
         self.after.append(fn)
 
-    def place_poly_openings(self, lengths: List[int]) -> dict:
-        """(opening, slot) -> rank for the two openings of every polynomial, longest first onto the least loaded rank
-        (pure bookkeeping: every rank takes the same decisions)"""
+    def place_poly_openings(self, lengths: List[int], first: int = 0) -> dict:
+        """(opening, slot) -> rank for the two openings of the polynomials first, first + 1, ..: longest first onto the
+        least loaded rank (pure bookkeeping: every rank takes the same decisions)"""
         place = {}
         for i in sorted(range(len(lengths)), key=lambda j: (-lengths[j], j)):
             for slot in (0, 1):
                 k = min(range(self.nranks), key=lambda q: (self.load[q], q))
                 self.load[k] += max(lengths[i], 1)
-                place[(i, slot)] = k
+                place[(first + i, slot)] = k
         return place
 
-    def finish(self) -> None:
-        ctx, pcs, rank = self.ctx, self.pcs, self.rank
-        B = len(self.entries)
-        place = self.place_poly_openings([e["poly"].nbytes // 32 for e in self.entries])
-        tails = np.zeros((B, 4, 128), dtype=np.uint8)
-        for i, e in enumerate(self.entries):
-            r = np.ascontiguousarray(e["r"], dtype=np.uint8).reshape(32)
-            xs = None
+    def place_new(self) -> None:
+        """give the KZG openings of the entries added since the last call their ranks (called when a batch has replayed
+        its transcript: from then on the openings can run whenever their rank has nothing better to do)"""
+        new = self.entries[self.placed:]
+        self.place.update(self.place_poly_openings([e["poly"].nbytes // 32 for e in new], self.placed))
+        for j, e in enumerate(new):
+            self.place[(self.placed + j, 2)] = self.place[(self.placed + j, 3)] = e["owner"]
+        self.placed = len(self.entries)
+
+    def run_units(self, budget: Optional[float] = None) -> None:
+        """run this rank's pending KZG openings, oldest first, until `budget` (in polynomial entries; None = all) is spent"""
+        ctx, pcs, spent = self.ctx, self.pcs, 0.0
+        for i in range(self.placed):
+            e = self.entries[i]
             for slot in range(4):
-                who = place[(i, slot)] if slot < 2 else e["owner"]
-                if who != rank:
+                if self.place[(i, slot)] != self.rank or (i, slot) in self.done:
                     continue
-                if xs is None:
-                    xs = (r, ctx.field_op(0, 3, r.reshape(1, 32)).reshape(32))  # r, 1 / r (mlpcs.rs:107)
+                if budget is not None and spent >= budget:
+                    return
+                if "xs" not in e:
+                    r = np.ascontiguousarray(e["r"], dtype=np.uint8).reshape(32)
+                    e["xs"] = (r, ctx.field_op(0, 3, r.reshape(1, 32)).reshape(32))  # r, 1 / r (mlpcs.rs:107)
                 if slot < 2:
                     target = e["poly"]
                 else:
                     pend = e["pending"]
                     target = (DeviceBuffer(ctx, pend.s_dev, 32 * pend.s_len, owner=False) if pend.s_len
                               else np.zeros((0, 32), dtype=np.uint8))
-                o = pcs.open(target, xs[slot & 1])
-                tails[i, slot] = np.concatenate([o.x, o.y, o.proof])
-            if e["pending"] is not None and e["pending"].s_dev:
-                ctx.lib.qz_dev_free(ctx.h, e["pending"].s_dev)
-                e["pending"].s_dev = None
+                o = pcs.open(target, e["xs"][slot & 1])
+                self.done[(i, slot)] = np.concatenate([o.x, o.y, o.proof])
+                spent += max(e["poly"].nbytes // 32, 1)
+            pend = e["pending"]
+            if pend is not None and pend.s_dev and (i, 2) in self.done and (i, 3) in self.done:
+                ctx.lib.qz_dev_free(ctx.h, pend.s_dev)  # both openings of S are out: release it
+                pend.s_dev = None
+
+    def finish(self) -> None:
+        ctx = self.ctx
+        self.place_new()
+        self.run_units()
+        B = len(self.entries)
+        tails = np.zeros((B, 4, 128), dtype=np.uint8)
+        for (i, slot), v in self.done.items():
+            tails[i, slot] = v
         all_tails = ctx.allgather(tails).reshape(self.nranks, B, 4, 128)
         for i, e in enumerate(self.entries):
-            ops = np.stack([all_tails[place[(i, slot)] if slot < 2 else e["owner"], i, slot] for slot in range(4)])
+            ops = np.stack([all_tails[self.place[(i, slot)], i, slot] for slot in range(4)])
             e["sink"](MLEvalProof.from_parts(e["point"].copy(), e["ev"].copy(), e["sc"].copy(), ops))
         for fn in self.after:
             fn()
-        self.entries, self.after = [], []
+        self.entries, self.after, self.place, self.done, self.placed = [], [], {}, {}, 0
 
 
 class OpeningBatch:
@@ -209,6 +232,14 @@ class OpeningBatch:
                 if owner[i] == rank:
                     pending[i] = pcs.open_multilinear_begin(poly, point)
                     head[i, :32], head[i, 32:] = pending[i].evaluation, pending[i].s_comm
+            # 13 first halves over 8 ranks is two on some and one on the others, and all wait for the slowest before the
+            # transcript can go on: a rank with fewer first halves spends the difference on KZG openings of EARLIER
+            # batches, whose challenges are known (they would otherwise run at the end of the proof)
+            begun = [0.0] * nranks
+            for i, (poly, _, _) in enumerate(self.items):
+                begun[owner[i]] += OpeningPool.BEGIN_COST * max(self._length(poly), 1)
+            if max(begun) > begun[rank]:
+                pool.run_units(max(begun) - begun[rank])
             heads = ctx.allgather(head).reshape(nranks, B, 96)
             for i, (poly, point, sink) in enumerate(self.items):  # mlpcs.rs:100-105, every rank, in order
                 ev, sc = heads[owner[i], i, :32], heads[owner[i], i, 32:]
@@ -217,6 +248,7 @@ class OpeningBatch:
                 tr.append_g1(sc)
                 r = tr.draw_field_element()
                 pool.add(poly, point, ev.copy(), sc.copy(), r.copy(), owner[i], pending.get(i), sink)
+            pool.place_new()
             for fn in self.after:
                 pool.on_done(fn)
             if self.pool is None:
