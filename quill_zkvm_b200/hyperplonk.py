@@ -103,7 +103,9 @@ class OpeningPool:
         self.done = {}     # (opening, slot) -> x ‖ y ‖ proof, for the openings this rank has run
         self.placed = 0    # openings whose four KZG openings have a rank
 
-    BEGIN_COST = 1.6  # first half of an opening in units of one MSM of its length: commit(S) + three transforms
+    # first half of an opening in units of one KZG opening of its length: commit(S), three transforms of twice the length,
+    # the eq table and the inner product (fitted on the per-call profile of an 8-GPU proof, tools/profile_hp_multi.py)
+    BEGIN_COST = 2.0
 
     def deal_begin(self, length: int) -> int:
         """owner of an opening's first half (and with it of its two S openings): the least loaded rank"""

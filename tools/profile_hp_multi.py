@@ -62,7 +62,11 @@ def timed_loop(fn, steps, warmup):
         fn()
         ctx.sync()
         out.append((time.perf_counter() - t) * 1e3)
-        print(f"rank {rank}: {out[-1]:.1f} ms:", {k: (round(v[0] * 1e3, 1), v[1]) for k, v in sorted(ACC.items(), key=lambda kv: -kv[1][0])}, flush=True)
+        sys.stdout.write(f"rank {rank}: {out[-1]:.1f} ms: " + str({k: (round(v[0] * 1e3, 1), v[1]) for k, v in sorted(ACC.items(), key=lambda kv: -kv[1][0])}) + "\n")
+        sys.stdout.flush()
+        if world > 1:
+            dist.barrier()
+            time.sleep(0.05 * rank)
     return min(out), 0
 
 
