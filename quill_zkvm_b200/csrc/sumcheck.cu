@@ -10,7 +10,10 @@
 //   * per-thread partial sums -> warp shuffles -> one partial per block -> a one-block "finalize" kernel that sums the
 //     partials, interpolates to monomial coefficients, serialises them and runs the blake3 transcript ON THE DEVICE,
 //     leaving the next challenge in device memory: no host round trip between rounds;
-//   * once a table is down to 2^SC_TAIL_LOG elements a single block finishes all remaining rounds in one launch.
+//   * once a rank's table is down to 2^SC_MID_LOG elements ONE persistent cooperative kernel (sc_mid) runs every remaining
+//     round: a round's pairs are spread over the grid (split pass: one work item per folded element, then per (pair,
+//     evaluation point)), the last block to arrive closes the round and releases the challenge to the others, peer GPUs
+//     exchange through mailboxes from inside the kernel.
 #include <algorithm>
 #include <cstring>
 #include <memory>
@@ -353,7 +356,7 @@ __global__ void __launch_bounds__(WIDE ? SC_WIDE_THREADS : SC_THREADS, (WIDE ? Q
 // passes are bound by the integer multiply pipe, not by the exposed load latency; the ring's copy / read / __syncwarp
 // instructions and its spills only took issue slots from the multiplier.  Removed.)
 
-// hand-over to sc_tail: the eq table in the form zerocheck.rs:25 would have left it after the same rounds, i.e. with
+// hand-over to sc_mid: the eq table in the form zerocheck.rs:25 would have left it after the same rounds, i.e. with
 // the last challenge still to be folded in: out[2p + b] = P_{j-1} * eq(b, z_{j-1}) * E_j[p]
 // The running claim changes meaning with it: the eq-factored rounds kept t_j(r_j), the rounds that follow sum h * eq as
 // the reference does and expect s_j(r_j) = P_{j+1} t_j(r_j).
@@ -1603,7 +1606,7 @@ int sumcheck_run(qz_ctx* ctx, size_t num_vars, size_t k, const void* const* tabl
         pending = 1;
         round++;
       }
-      // hand over to sc_tail: h's tables where they stand, eq materialised in the reference's form (pending fold)
+      // hand over to sc_mid: h's tables where they stand, eq materialised in the reference's form (pending fold)
       uint4* eq_full = (uint4*)ctx->arena_alloc(32 * size);
       if (!eq_full) return ctx->fail(QZ_ERR_ALLOC, "eq hand-over");
       QZ_LAUNCH(ctx, zc_materialize_eq, (unsigned)((size / 2 + 255) / 256), 256, 0, zc_weights, size / 2, head,

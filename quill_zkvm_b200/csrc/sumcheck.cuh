@@ -38,7 +38,7 @@ struct ScHead {
   Fr r;                // challenge of the last closed round (pending fold)
   Fr evaluation;       // EvaluationClaim.evaluation
   // eq-factored zero-check (sumcheck.cu "zero-check fast path"): P_j = prod_{i<j} eq(r_i, z_i) after round j-1 closed,
-  // and P_{j-1}, the value it had one round earlier (the hand-over to sc_tail needs it)
+  // and P_{j-1}, the value it had one round earlier (the hand-over to sc_mid needs it)
   Fr zc_prefix, zc_prefix_prev;
   // running claim for the rounds that do not sum X = 1 (sumcheck.cu ProdAcc): s_j(r_j) of the last closed round -- on
   // the eq-factored zero-check path t_j(r_j), the factor of s_j that the weighted sums are taken of
