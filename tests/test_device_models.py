@@ -10,6 +10,8 @@ is pinned independently of the GPU tests:
   * the merge of partial bucket runs by a segmented scan with early exit (csrc/msm.cu msm_partials_finish)
   * the streamed MSM's point ranges (csrc/msm.cu msm_run)
   * NTT passes as plain local transforms + one correction product per element (csrc/mlpcs.cu ntt_pass)
+  * the K = 3 round polynomial from samples at X = 0, 1, -1, infinity with lazily added operands, X = 1 restored from the
+    running claim (csrc/sumcheck.cu prod_core_toom3, csrc/sumcheck.cuh sc_expand_evals / sc_toom3_to_coeffs)
 """
 import os
 import random
@@ -365,3 +367,64 @@ def test_fixed_multiplier_bounds_and_value():
     for r in rs:
         for d in ds:
             assert model(d, r) == r * d % p
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def sumcheck_toom3_skip1(num_vars, tables, claimed, tr):
+    """SumcheckProof::prove for h = g0 g1 g2 the way sc_round_prod<3, WIDE> + sc_finalize do it (csrc/sumcheck.cu
+    prod_core_toom3, sumcheck.cuh sc_expand_evals / sc_toom3_to_coeffs): the cubic is sampled at X = 0, 1, -1 and
+    infinity, with q(-1) = 2 q(0) + 2 q(inf) - q(1) of the quadratic g0 g1 and g2(-1) = 2 lo - hi formed as plain
+    (unreduced) integers below 2^256; from round 1 on s(1) is not summed but restored from the running claim."""
+    gs = [list(t) for t in tables]
+    tr.append_usize(num_vars)
+    tr.append_fr(claimed)
+    r_polys, point, claim = [], [], None
+    inv2 = pow(2, -1, FR)
+    for j in range(num_vars):
+        pairs = len(gs[0]) // 2
+        s0 = s1 = sm = sinf = 0
+        for p in range(pairs):
+            lo = [g[2 * p] for g in gs]
+            hi = [g[2 * p + 1] for g in gs]
+            q0, q1 = lo[0] * lo[1] % FR, hi[0] * hi[1] % FR
+            d0 = (hi[0] - lo[0]) % FR               # reduced: first operand of a reducing product
+            d1 = hi[1] - lo[1] + FR                 # lazy, in (0, 2p)
+            q2 = d0 * d1 % FR
+            d2 = hi[2] - lo[2] + FR                 # lazy
+            qm = 2 * (q0 + q2) + (FR - q1)          # plain integers: must stay below 2^256
+            gm = lo[2] + (lo[2] - hi[2] + FR)
+            assert 0 < d1 < 2 * FR and 0 < d2 < 2 * FR and 0 < qm < 5 * FR < (1 << 256) and 0 < gm < 3 * FR
+            s0 += q0 * lo[2]                        # deferred reduction: the products are summed as integers
+            s1 += q1 * hi[2]
+            sinf += q2 * d2
+            sm += qm * gm
+        s0, s1, sm, sinf = s0 % FR, s1 % FR, sm % FR, sinf % FR
+        if j > 0:                                    # SKIP1: s_j(1) = s_{j-1}(r_{j-1}) - s_j(0)
+            assert s1 == (claim - s0) % FR
+            s1 = (claim - s0) % FR
+        c0, c3 = s0, sinf
+        c2 = ((s1 + sm) * inv2 - c0) % FR
+        c1 = ((s1 - sm) * inv2 - c3) % FR
+        poly = py.trim([c0, c1, c2, c3])
+        tr.append_fr_vec(poly)
+        r = tr.draw_field_element()
+        claim = sum(c * pow(r, i, FR) for i, c in enumerate([c0, c1, c2, c3])) % FR
+        gs = [[(g[2 * p] + r * (g[2 * p + 1] - g[2 * p])) % FR for p in range(pairs)] for g in gs]
+        r_polys.append(poly)
+        point.append(r)
+    return r_polys, point, gs[0][0] * gs[1][0] * gs[2][0] % FR
+
+
+@pytest.mark.parametrize("n", [1, 4, 7])
+def test_toom3_sampling_with_derived_s1_equals_reference_formulation(n):
+    rnd = random.Random(300 + n)
+    tables = [[rnd.randrange(FR) for _ in range(1 << n)] for _ in range(3)]
+    tables[0][0] = tables[1][1] = 0
+    tables[2][2 % (1 << n)] = FR - 1
+    h = py.e_mul(py.e_mul(py.e_in(0), py.e_in(1)), py.e_in(2))
+    for claimed in (sum(a * b * c for a, b, c in zip(*tables)) % FR, 12345):  # the true sum and a false claim
+        tr_ref = py.Transcript(b"toom")
+        want = py.sumcheck_prove(n, [list(t) for t in tables], h, claimed, tr_ref)
+        tr = py.Transcript(b"toom")
+        got = sumcheck_toom3_skip1(n, tables, claimed, tr)
+        assert got == want and tr.state == tr_ref.state
