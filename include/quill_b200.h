@@ -250,6 +250,13 @@ int qz_test_field_op(qz_ctx* ctx, int field, int op, const uint8_t* a, const uin
  * of r in constant memory, 88 instead of 136 multiply-adds per product); a1 - a0 is taken without reduction, so any
  * 256-bit a0 < p, a1 < p are valid */
 int qz_test_fold(qz_ctx* ctx, const uint8_t r[32], const uint8_t* a0, const uint8_t* a1, uint8_t* out, size_t n);
+/* test hook, host logic only (no device needed): the round plan of the persistent short-round kernel for tables of
+ * `size` entries per rank (pending != 0: a challenge still to be folded in), k tables, degree d, at most `cap`
+ * co-resident blocks, G ranks.  Arrays of QZ_TEST_PLAN_ROUNDS entries: blocks working on round j, the largest block
+ * count any round >= j needs, pairs per block (0: whole pairs per thread).  Returns the grid size, < 0 on bad input. */
+#define QZ_TEST_PLAN_ROUNDS 40
+int qz_test_mid_plan(uint64_t size, int pending, int k, int d, unsigned int cap, int G, uint32_t* out_nblk,
+                     uint32_t* out_future, uint32_t* out_chunk, uint32_t* out_tile);
 int qz_test_g1_add(qz_ctx* ctx, const uint8_t* a_xy, const uint8_t* b_xy, uint8_t* out_xy, size_t n);
 int qz_test_g1_mul(qz_ctx* ctx, const uint8_t* a_xy, const uint8_t* scalars, uint8_t* out_xy, size_t n);
 

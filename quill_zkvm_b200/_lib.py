@@ -26,7 +26,7 @@ SYMBOLS = [
     "qz_sumcheck_prove", "qz_zerocheck_prove", "qz_eq_table", "qz_logup_denominators",
     "qz_comm_unique_id", "qz_comm_init", "qz_comm_peer_memory", "qz_msm_sharded", "qz_msm_split", "qz_sumcheck_prove_sharded", "qz_zerocheck_prove_sharded", "qz_comm_allgather_host", "qz_comm_resync",
     "qz_last_elapsed_ms", "qz_last_stat", "qz_msm_accumulate_stats", "qz_bench_imad", "qz_bench_fp_mul",
-    "qz_test_field_op", "qz_test_fold", "qz_test_g1_add", "qz_test_g1_mul",
+    "qz_test_field_op", "qz_test_fold", "qz_test_mid_plan", "qz_test_g1_add", "qz_test_g1_mul",
 ]
 
 _lib = None
@@ -122,6 +122,7 @@ def load():
     lib.qz_bench_fp_mul.argtypes = [vp, i32, C.POINTER(C.c_double)]
     lib.qz_test_field_op.argtypes = [vp, i32, i32, vp, vp, vp, sz]
     lib.qz_test_fold.argtypes = [vp, vp, vp, vp, vp, sz]
+    lib.qz_test_mid_plan.argtypes = [C.c_uint64, i32, i32, i32, C.c_uint32, i32, vp, vp, vp, vp]
     lib.qz_test_g1_add.argtypes = [vp, vp, vp, vp, sz]
     lib.qz_test_g1_mul.argtypes = [vp, vp, vp, vp, sz]
     _lib = lib

@@ -1845,6 +1845,23 @@ extern "C" int qz_debug_trace(unsigned long long* out, int max_records) {
 }
 #endif
 
+// test hook (host logic only, no device needed): the plan sumcheck_run hands to sc_mid for tables of `size` entries per rank
+// (pending != 0: a challenge is still to be folded in), k tables, degree d, at most `cap` co-resident blocks, G ranks.
+// out_nblk / out_future / out_chunk: QZ_TEST_PLAN_ROUNDS entries each; returns the grid the launch would use.
+extern "C" int qz_test_mid_plan(uint64_t size, int pending, int k, int d, unsigned int cap, int G, uint32_t* out_nblk,
+                                uint32_t* out_future, uint32_t* out_chunk, uint32_t* out_tile) {
+  if (!out_nblk || !out_future || !out_chunk || !out_tile || cap == 0 || G < 1) return -1;
+  qz::ScMidPlan plan;
+  const unsigned int grid = qz::mid_make_plan(plan, size, pending, k, d, cap, G);
+  for (int j = 0; j < qz::SC_MAX_VARS; j++) {
+    out_nblk[j] = plan.nblk[j];
+    out_future[j] = plan.future[j];
+    out_chunk[j] = plan.chunk[j];
+  }
+  *out_tile = plan.tile;
+  return (int)grid;
+}
+
 extern "C" int qz_test_fold(qz_ctx* ctx, const uint8_t r[32], const uint8_t* a0, const uint8_t* a1, uint8_t* out, size_t n) {
   if (!ctx || !r || !a0 || !a1 || !out) return QZ_ERR_INVALID_ARG;
   if (n == 0) return QZ_OK;

@@ -121,6 +121,7 @@ extern "C" {
     pub fn qz_bench_imad(ctx: *mut qz_ctx, variant: i32, out_ops_per_s: *mut f64) -> i32;
     pub fn qz_bench_fp_mul(ctx: *mut qz_ctx, field: i32, out_muls_per_s: *mut f64) -> i32;
     pub fn qz_test_field_op(ctx: *mut qz_ctx, field: i32, op: i32, a: *const u8, b: *const u8, out: *mut u8, n: usize) -> i32;
+    pub fn qz_test_mid_plan(size: u64, pending: i32, k: i32, d: i32, cap: u32, g: i32, out_nblk: *mut u32, out_future: *mut u32, out_chunk: *mut u32, out_tile: *mut u32) -> i32;
     pub fn qz_test_fold(ctx: *mut qz_ctx, r: *const u8, a0: *const u8, a1: *const u8, out: *mut u8, n: usize) -> i32;
     pub fn qz_test_g1_add(ctx: *mut qz_ctx, a_xy: *const u8, b_xy: *const u8, out_xy: *mut u8, n: usize) -> i32;
     pub fn qz_test_g1_mul(ctx: *mut qz_ctx, a_xy: *const u8, scalars: *const u8, out_xy: *mut u8, n: usize) -> i32;
