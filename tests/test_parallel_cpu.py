@@ -274,3 +274,31 @@ def test_shard_ranges_partition():
     assert parallel.table_shard_range(5, 1, 2) == (16, 32)
     with pytest.raises(AssertionError):
         parallel.table_shard_range(1, 0, 4)
+
+
+def test_sharded_view_windows():
+    """hyperplonk.sharded_view: rank g's store holds the g-th contiguous 1/G of every resident table (the top variables),
+    or nothing when the store does not qualify"""
+    from types import SimpleNamespace
+
+    import quill_zkvm_b200 as q
+    from quill_zkvm_b200 import hyperplonk as hp
+
+    n = 14
+    store = q.VirtualPolynomialStore(n)
+    store.polynomials = [q.DeviceBuffer(None, 0x1000_0000 * (t + 1), 32 << n, owner=False) for t in range(3)]
+    store.virtual_polys = ["h"]
+    for G in (2, 4):
+        spans = []
+        for rank in range(G):
+            part = hp.sharded_view(SimpleNamespace(nranks=G, rank=rank), store)
+            assert part is not None and part.num_vars == n and part.virtual_polys is store.virtual_polys
+            for t, (p, full) in enumerate(zip(part.polynomials, store.polynomials)):
+                assert not p.owner and p.nbytes == (32 << n) // G and p.ptr == full.ptr + rank * p.nbytes
+            spans.append(parallel.table_shard_range(n, rank, G))
+        assert spans[0][0] == 0 and spans[-1][1] == 1 << n  # the same partition the sharded entry points document
+    assert hp.sharded_view(SimpleNamespace(nranks=1, rank=0), store) is None          # one rank
+    assert hp.sharded_view(SimpleNamespace(nranks=8, rank=0), store) is None          # 2^11 entries per rank: too few
+    host = q.VirtualPolynomialStore(n)
+    host.polynomials = [np.zeros((1 << n, 32), np.uint8)]
+    assert hp.sharded_view(SimpleNamespace(nranks=2, rank=0), host) is None           # host tables
