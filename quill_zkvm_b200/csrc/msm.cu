@@ -78,8 +78,19 @@ __global__ void __launch_bounds__(256) msm_digits(const uint4* scalars, uint32_t
 }
 
 // ---- 4. accumulate ----------------------------------------------------------------------------------------------------------
+// A value with VAL_PAIR set addresses the array of pair sums (pair levels, below) instead of the bases.
+constexpr uint32_t VAL_PAIR = 1u << 30;
+constexpr uint32_t VAL_INDEX = VAL_PAIR - 1;
+QZ_DEV const uint8_t* entry_point(const uint8_t* bases, const uint8_t* sums, uint32_t val) {
+  return ((val & VAL_PAIR) ? sums : bases) + (size_t)(val & VAL_INDEX) * 64;
+}
 QZ_DEV Affine load_base(const uint8_t* bases, uint32_t val) {
   Affine a = affine_load(bases + (size_t)(val & 0x7fffffffu) * 64);
+  if (val >> 31) a.y = fp_neg<FqParams>(a.y);
+  return a;
+}
+QZ_DEV Affine load_entry(const uint8_t* bases, const uint8_t* sums, uint32_t val) {
+  Affine a = affine_load(entry_point(bases, sums, val));
   if (val >> 31) a.y = fp_neg<FqParams>(a.y);
   return a;
 }
@@ -90,12 +101,29 @@ QZ_DEV uint32_t bucket_slot(uint32_t key, int c) {  // dense slot of a non-zero 
 
 // Partial runs go to a list of (key, XYZZ) slots, two per chunk: slot 2*chunk = the run touching the chunk's start,
 // slot 2*chunk + 1 = the run touching its end (KEY_NONE = empty).  Keys of non-empty slots are non-decreasing.
-__global__ void __launch_bounds__(ACC_THREADS, 4) msm_accumulate(const uint32_t* keys, const uint32_t* vals, uint64_t m,
-                                                              int chunk_len, const uint8_t* bases, int c,
+// PAIRED: the list went through the pair levels first -- its length is read from device memory (the launch covers the
+// `n_chunks` chunks of the longest list possible; chunks past the end leave empty slots) and values may address `sums`.
+template <bool PAIRED>
+__global__ void __launch_bounds__(ACC_THREADS, 4) msm_accumulate(const uint32_t* keys, const uint32_t* vals, uint64_t m_host,
+                                                              const uint64_t* m_dev, uint64_t n_chunks, int chunk_len,
+                                                              const uint8_t* bases, const uint8_t* sums, int c,
                                                               uint8_t* buckets, uint8_t* ppts, uint32_t* pkeys) {
   const uint64_t chunk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t begin = chunk * chunk_len;
-  if (begin >= m) return;
+  uint64_t m = m_host;
+  if constexpr (PAIRED) {
+    m = *m_dev;
+    if (begin >= m) {
+      if (chunk < n_chunks) {
+        pkeys[2 * chunk] = KEY_NONE;
+        pkeys[2 * chunk + 1] = KEY_NONE;
+      }
+      return;
+    }
+  } else {
+    if (begin >= m) return;
+  }
+  auto load = [&](uint32_t val) { return PAIRED ? load_entry(bases, sums, val) : load_base(bases, val); };
   uint8_t* heads = ppts;             // slot 2*chunk
   uint8_t* tails = ppts + 128;       // slot 2*chunk + 1
   const uint64_t end = begin + chunk_len < m ? begin + chunk_len : m;
@@ -105,14 +133,14 @@ __global__ void __launch_bounds__(ACC_THREADS, 4) msm_accumulate(const uint32_t*
   bool first = true;
   uint32_t hk = KEY_NONE, tk = KEY_NONE;
   uint32_t nk = cur_key, nv = vals[begin];
-  Affine npt = (nk & dmask) ? load_base(bases, nv) : Affine{fp_zero<FqParams>(), fp_zero<FqParams>()};
+  Affine npt = (nk & dmask) ? load(nv) : Affine{fp_zero<FqParams>(), fp_zero<FqParams>()};
   for (uint64_t j = begin; j < end; j++) {
     const uint32_t k = nk;
     const Affine pt = npt;
     if (j + 1 < end) {  // prefetch the next entry's base while this one is added
       nk = keys[j + 1];
       nv = vals[j + 1];
-      if (nk & dmask) npt = load_base(bases, nv);
+      if (nk & dmask) npt = load(nv);
     }
     if (k != cur_key) {  // the run of cur_key ended inside the chunk
       if (cur_key & dmask) {
@@ -140,6 +168,181 @@ __global__ void __launch_bounds__(ACC_THREADS, 4) msm_accumulate(const uint32_t*
   }
   pkeys[2 * chunk] = hk;
   pkeys[2 * chunk + 1] = tk;
+}
+
+// ---- 4b. pair levels: affine additions with a shared inversion, ahead of the accumulation --------------------------
+// A mixed addition into an XYZZ accumulator is 10 products.  Two AFFINE points add in 1 inversion + 3 products, and
+// Montgomery's trick turns n inversions into one inversion + 3 (n - 1) products, i.e. ~6 products per addition when
+// the batch is large.  A level pairs the entries at positions (2i, 2i + 1) of the sorted list: when both carry the same
+// non-zero key, their sum is written to the array of pair sums and ONE entry (key, VAL_PAIR | index of the sum) takes
+// their place; any other pair passes through unchanged (zero digits are dropped), so the output is again a list sorted
+// by key whose entries sum to the same buckets, about half as long.  L levels leave runs of ~r / 2^L entries for the
+// XYZZ accumulation, where r = entries per bucket.  Pairs that cannot be added by the affine chord rule -- equal x
+// (P + P, P - P) or an infinite point -- pass through as well: the complete XYZZ law downstream handles them, which
+// keeps this stage free of special cases.
+// One level = three passes over chunks of PAIR_B pairs per thread, with no thread ever waiting on an inversion:
+//   scan   d = x_b - x_a per pair; running product of the thread's d's (prefix[pair] = the product BEFORE the pair),
+//          the thread's total and its output / sum counts
+//   invert the totals, by a product tree of fan-in PAIR_G: up, up, one Fermat inversion per root, down, down
+//   apply  walks the thread's pairs backwards: 1/d = inv * prefix, inv *= d; lambda = (y_b - y_a) / d,
+//          x3 = lambda^2 - x_a - x_b, y3 = lambda (x_a - x3) - y_a; outputs land at the positions an exclusive scan of
+//          the counts assigns (order preserved)
+// The list lengths live on the device (PairCtl): launches cover the longest list possible and threads past the end
+// return, so the host never synchronises.  The sums written by all levels number at most m - 1 (every sum shortens
+// the list by one): the array of m slots cannot overflow whatever the input.
+constexpr int PAIR_B = 16;            // pairs per thread
+constexpr int PAIR_G = 64;            // fan-in of the inversion's product tree
+constexpr int PAIR_MAX_LEVELS = 8;
+struct PairCtl {
+  uint64_t m[PAIR_MAX_LEVELS + 1];     // m[l]: entries entering level l; m[L]: entries left for msm_accumulate
+  uint64_t sums[PAIR_MAX_LEVELS + 1];  // sums[l]: pair sums written by the levels before l
+};
+__global__ void msm_pair_init(PairCtl* ctl, uint64_t m, unsigned long long* counts_last) {
+  for (int l = 0; l <= PAIR_MAX_LEVELS; l++) {
+    ctl->m[l] = l == 0 ? m : 0;
+    ctl->sums[l] = 0;
+  }
+  *counts_last = 0;  // the scan's extra item: offs[n_threads] = the totals
+}
+__global__ void __launch_bounds__(128, 8) msm_pair_scan(const uint32_t* keys, const uint32_t* vals, const PairCtl* ctl, int level,
+                                                      uint32_t dmask, const uint8_t* bases, const uint8_t* sums,
+                                                      uint8_t* prefix, uint8_t* totals, unsigned long long* counts,
+                                                      uint64_t n_threads) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_threads) return;
+  const uint64_t m = ctl->m[level], e0 = t * (2 * PAIR_B);
+  if (e0 >= m) {
+    counts[t] = 0;
+    return;
+  }
+  Fq run = fp_one<FqParams>();
+  uint32_t n_out = 0, n_sum = 0;
+  for (int j = 0; j < PAIR_B; j++) {
+    const uint64_t a = e0 + 2 * j;
+    if (a >= m) break;
+    const bool has_b = a + 1 < m;
+    const uint32_t ka = keys[a], kb = has_b ? keys[a + 1] : 0u;
+    bool paired = false;
+    if (has_b && ka == kb && (ka & dmask)) {
+      const Fq xa = fp_load<FqParams>(entry_point(bases, sums, vals[a]));
+      const Fq xb = fp_load<FqParams>(entry_point(bases, sums, vals[a + 1]));
+      const Fq d = fp_sub<FqParams>(xb, xa);
+      if (!fp_is_zero<FqParams>(xa) && !fp_is_zero<FqParams>(xb) && !fp_is_zero<FqParams>(d)) {
+        paired = true;
+        fp_store<FqParams>(prefix + (t * PAIR_B + j) * 32, run);
+        run = fp_mul<FqParams>(run, d);
+      }
+    }
+    if (paired) {
+      n_out++;
+      n_sum++;
+    } else {
+      n_out += ((ka & dmask) != 0) + (has_b && (kb & dmask) != 0);
+    }
+  }
+  fp_store<FqParams>(totals + t * 32, run);
+  counts[t] = (unsigned long long)n_out | ((unsigned long long)n_sum << 32);
+}
+// elements of the inversion tree at `depth` above the threads' totals (depth 0) for the list entering `level`
+QZ_DEV uint64_t pair_tree_count(const PairCtl* ctl, int level, int depth) {
+  uint64_t n = (ctl->m[level] + 2 * PAIR_B - 1) / (2 * PAIR_B);
+  for (int k = 0; k < depth; k++) n = (n + PAIR_G - 1) / PAIR_G;
+  return n;
+}
+__global__ void __launch_bounds__(128) msm_pair_tree_up(const PairCtl* ctl, int level, int depth, const uint8_t* v, uint8_t* pre,
+                                                        uint8_t* v_up) {
+  const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t n = pair_tree_count(ctl, level, depth);
+  if (u * PAIR_G >= n) return;
+  const uint64_t end = u * PAIR_G + PAIR_G < n ? u * PAIR_G + PAIR_G : n;
+  Fq run = fp_one<FqParams>();
+  for (uint64_t i = u * PAIR_G; i < end; i++) {
+    fp_store<FqParams>(pre + i * 32, run);
+    run = fp_mul<FqParams>(run, fp_load<FqParams>(v + i * 32));
+  }
+  fp_store<FqParams>(v_up + u * 32, run);
+}
+__global__ void __launch_bounds__(128) msm_pair_tree_root(const PairCtl* ctl, int level, int depth, uint8_t* v) {
+  const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= pair_tree_count(ctl, level, depth)) return;
+  fp_store<FqParams>(v + u * 32, fp_inv<FqParams>(fp_load<FqParams>(v + u * 32)));  // products of non-zero d's: never 0
+}
+__global__ void __launch_bounds__(128) msm_pair_tree_down(const PairCtl* ctl, int level, int depth, uint8_t* v, const uint8_t* pre,
+                                                          const uint8_t* v_up) {
+  const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t n = pair_tree_count(ctl, level, depth);
+  if (u * PAIR_G >= n) return;
+  const uint64_t end = u * PAIR_G + PAIR_G < n ? u * PAIR_G + PAIR_G : n;
+  Fq inv = fp_load<FqParams>(v_up + u * 32);  // 1 / (product of this thread's elements)
+  for (uint64_t i = end; i-- > u * PAIR_G;) {
+    const Fq x = fp_load<FqParams>(v + i * 32);
+    fp_store<FqParams>(v + i * 32, fp_mul<FqParams>(inv, fp_load<FqParams>(pre + i * 32)));
+    inv = fp_mul<FqParams>(inv, x);
+  }
+}
+__global__ void __launch_bounds__(128, 4) msm_pair_apply(const uint32_t* keys, const uint32_t* vals, PairCtl* ctl, int level,
+                                                       uint32_t dmask, const uint8_t* bases, uint8_t* sums,
+                                                       const uint8_t* prefix, const uint8_t* totals_inv,
+                                                       const unsigned long long* offs, uint64_t n_threads,
+                                                       uint32_t* keys_out, uint32_t* vals_out) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_threads) return;
+  const uint64_t m = ctl->m[level], sum_base = ctl->sums[level], e0 = t * (2 * PAIR_B);
+  if (t == 0) {  // the next level's list length and first free sum slot
+    const unsigned long long total = offs[n_threads];
+    ctl->m[level + 1] = total & 0xffffffffull;
+    ctl->sums[level + 1] = sum_base + (total >> 32);
+  }
+  if (e0 >= m) return;
+  const unsigned long long end = offs[t + 1];  // exclusive scan: this thread's outputs END here
+  uint64_t pos = end & 0xffffffffull, sidx = sum_base + (end >> 32);
+  Fq inv = fp_load<FqParams>(totals_inv + t * 32);
+  const uint64_t left = m - e0;
+  const int n_pairs = left >= 2 * PAIR_B ? PAIR_B : (int)((left + 1) / 2);
+  for (int j = n_pairs - 1; j >= 0; j--) {
+    const uint64_t a = e0 + 2 * j;
+    const bool has_b = a + 1 < m;
+    const uint32_t ka = keys[a], kb = has_b ? keys[a + 1] : 0u;
+    const uint32_t va = vals[a], vb = has_b ? vals[a + 1] : 0u;
+    bool paired = false;
+    if (has_b && ka == kb && (ka & dmask)) {
+      // both points and the prefix are requested together: one memory round trip per pair, not three
+      const uint8_t* pa = entry_point(bases, sums, va);
+      const uint8_t* pb = entry_point(bases, sums, vb);
+      const Fq xa = fp_load<FqParams>(pa), xb = fp_load<FqParams>(pb);
+      Fq ya = fp_load<FqParams>(pa + 32), yb = fp_load<FqParams>(pb + 32);
+      const Fq pre = fp_load<FqParams>(prefix + (t * PAIR_B + j) * 32);  // unwritten (and unused) when the pair passes through
+      const Fq d = fp_sub<FqParams>(xb, xa);
+      if (!fp_is_zero<FqParams>(xa) && !fp_is_zero<FqParams>(xb) && !fp_is_zero<FqParams>(d)) {
+        paired = true;
+        if (va >> 31) ya = fp_neg<FqParams>(ya);
+        if (vb >> 31) yb = fp_neg<FqParams>(yb);
+        const Fq dinv = fp_mul<FqParams>(inv, pre);
+        inv = fp_mul<FqParams>(inv, d);
+        const Fq lam = fp_mul<FqParams>(fp_sub<FqParams>(yb, ya), dinv);
+        Affine s;
+        s.x = fp_sub<FqParams>(fp_sub<FqParams>(fp_sqr<FqParams>(lam), xa), xb);
+        s.y = fp_sub<FqParams>(fp_mul<FqParams>(lam, fp_sub<FqParams>(xa, s.x)), ya);
+        --sidx;
+        affine_store(sums + sidx * 64, s);
+        --pos;
+        keys_out[pos] = ka;
+        vals_out[pos] = VAL_PAIR | (uint32_t)sidx;
+      }
+    }
+    if (!paired) {
+      if (has_b && (kb & dmask)) {
+        --pos;
+        keys_out[pos] = kb;
+        vals_out[pos] = vb;
+      }
+      if (ka & dmask) {
+        --pos;
+        keys_out[pos] = ka;
+        vals_out[pos] = va;
+      }
+    }
+  }
 }
 
 // ---- 5. merge the partial runs, level by level ---------------------------------------------------------------------
@@ -659,6 +862,18 @@ int msm_run(qz_ctx* ctx, const qz_srs* srs, uint4* scalars_dev, const void* scal
   chunk_len = std::max(ACC_CHUNK_MIN, chunk_len / 32 * 32);
   int key_bits = c;
   while ((1u << (key_bits - c)) < (uint32_t)W) key_bits++;
+  // pair levels ahead of the accumulation (QZ_MSM_PAIR_LEVELS = count; unset: none): values need bit 30 as the flag
+  int pair_levels = 0;
+  {
+    const char* env = getenv("QZ_MSM_PAIR_LEVELS");
+    if (env && *env) pair_levels = std::max(0, std::min(PAIR_MAX_LEVELS, atoi(env)));
+    const uint64_t max_index = (collapsed ? (uint64_t)Wd * srs->n : (uint64_t)srs->n);
+    if (m >= VAL_PAIR || max_index >= VAL_PAIR || m < 4 * PAIR_B) pair_levels = 0;
+  }
+  if (pair_levels) {  // the list the accumulation sees is ~2^levels shorter: keep enough chunks to fill the machine
+    chunk_len = (int)std::min<uint64_t>(ACC_CHUNK_MAX, (m >> pair_levels) / ((uint64_t)ctx->sm_count * 4 * ACC_THREADS * 16));
+    chunk_len = std::max(ACC_CHUNK_MIN, chunk_len / 32 * 32);
+  }
 
   // point ranges [seg_lo[s], seg_lo[s+1])
   double weights[qz_ctx::MAX_SEGMENTS];
@@ -723,6 +938,31 @@ int msm_run(qz_ctx* ctx, const qz_srs* srs, uint4* scalars_dev, const void* scal
   if (!keys || !vals || !keys2 || !vals2 || !buckets || !ppts_a || !pkeys_a || !ppts_b || !pkeys_b || !fin_a || !fin_b || !partial ||
       !partial2 || !window_sums || !sort_tmp)
     return ctx->fail(QZ_ERR_ALLOC, "MSM scratch");
+  // pair levels (msm_pair_*): scratch for the longest segment, shared by the segments (they run in turn on `st`)
+  PairCtl* pair_ctl = nullptr;
+  uint8_t *pair_sums = nullptr, *pair_prefix = nullptr, *pair_v[3] = {nullptr, nullptr, nullptr}, *pair_pre[2] = {nullptr, nullptr};
+  unsigned long long *pair_counts = nullptr, *pair_offs = nullptr;
+  void* pair_scan_tmp = nullptr;
+  size_t pair_scan_bytes = 0;
+  uint64_t pair_n[3] = {0, 0, 0};
+  if (pair_levels) {
+    const uint64_t mmax = (uint64_t)Wd * max_seg;
+    pair_n[0] = (mmax + 2 * PAIR_B - 1) / (2 * PAIR_B);
+    pair_n[1] = (pair_n[0] + PAIR_G - 1) / PAIR_G;
+    pair_n[2] = (pair_n[1] + PAIR_G - 1) / PAIR_G;
+    pair_ctl = (PairCtl*)ctx->arena_alloc(sizeof(PairCtl));
+    pair_sums = (uint8_t*)ctx->arena_alloc(mmax * 64);
+    pair_prefix = (uint8_t*)ctx->arena_alloc(pair_n[0] * PAIR_B * 32);
+    for (int k = 0; k < 3; k++) pair_v[k] = (uint8_t*)ctx->arena_alloc(pair_n[k] * 32);
+    for (int k = 0; k < 2; k++) pair_pre[k] = (uint8_t*)ctx->arena_alloc(pair_n[k] * 32);
+    pair_counts = (unsigned long long*)ctx->arena_alloc((pair_n[0] + 1) * 8);
+    pair_offs = (unsigned long long*)ctx->arena_alloc((pair_n[0] + 1) * 8);
+    cub::DeviceScan::ExclusiveSum(nullptr, pair_scan_bytes, pair_counts, pair_offs, (int64_t)(pair_n[0] + 1), st);
+    pair_scan_tmp = ctx->arena_alloc(pair_scan_bytes);
+    if (!pair_ctl || !pair_sums || !pair_prefix || !pair_v[0] || !pair_v[1] || !pair_v[2] || !pair_pre[0] || !pair_pre[1] ||
+        !pair_counts || !pair_offs || !pair_scan_tmp)
+      return ctx->fail(QZ_ERR_ALLOC, "MSM pair-level scratch");
+  }
 
   if (S > 1) {  // the prep stream starts where the main stream stands (earlier users of the scratch, the scalars)
     QZ_CUDA(ctx, cudaEventRecord(ctx->ev_entry, st));
@@ -752,9 +992,39 @@ int msm_run(qz_ctx* ctx, const qz_srs* srs, uint4* scalars_dev, const void* scal
     const bool ring = ctx->acc_ring_next(&ring0, &ring1) == 0;
     if (ring) QZ_CUDA(ctx, cudaEventRecord(ring0, st));
     QZ_CUDA(ctx, cudaEventRecord(S > 1 ? ctx->ev_acc0[s] : ctx->ev_k0, st));
-    QZ_LAUNCH(ctx, msm_accumulate, (unsigned)((chunk_base[s + 1] - chunk_base[s] + ACC_THREADS - 1) / ACC_THREADS),
-              ACC_THREADS, 0, dk.Current(), dv.Current(), ms, chunk_len, bases, c, buckets,
-              ppts_a + chunk_base[s] * 256, pkeys_a + 2 * chunk_base[s]);
+    const uint64_t seg_chunks = chunk_base[s + 1] - chunk_base[s];
+    if (pair_levels) {
+      uint32_t* kbuf[2] = {dk.Current(), dk.Alternate()};  // a level reads one buffer of the sort's pair and writes the other
+      uint32_t* vbuf[2] = {dv.Current(), dv.Alternate()};
+      int cur = 0;
+      const uint64_t T = (ms + 2 * PAIR_B - 1) / (2 * PAIR_B);  // threads of a level over the longest list possible
+      const uint64_t T1 = (T + PAIR_G - 1) / PAIR_G, T2 = (T1 + PAIR_G - 1) / PAIR_G;
+      const uint32_t dmask = (1u << c) - 1;
+      QZ_LAUNCH(ctx, msm_pair_init, 1, 1, 0, pair_ctl, ms, pair_counts + T);
+      for (int l = 0; l < pair_levels; l++) {
+        const uint32_t* kc = kbuf[cur];
+        const uint32_t* vc = vbuf[cur];
+        QZ_LAUNCH(ctx, msm_pair_scan, (unsigned)((T + 127) / 128), 128, 0, kc, vc, pair_ctl, l, dmask, bases, pair_sums,
+                  pair_prefix, pair_v[0], pair_counts, T);
+        QZ_CUDA(ctx, cub::DeviceScan::ExclusiveSum(pair_scan_tmp, pair_scan_bytes, pair_counts, pair_offs, (int64_t)(T + 1), st));
+        ctx->launches += 2;
+        QZ_LAUNCH(ctx, msm_pair_tree_up, (unsigned)((T1 + 127) / 128), 128, 0, pair_ctl, l, 0, pair_v[0], pair_pre[0], pair_v[1]);
+        QZ_LAUNCH(ctx, msm_pair_tree_up, (unsigned)((T2 + 127) / 128), 128, 0, pair_ctl, l, 1, pair_v[1], pair_pre[1], pair_v[2]);
+        QZ_LAUNCH(ctx, msm_pair_tree_root, (unsigned)((T2 + 127) / 128), 128, 0, pair_ctl, l, 2, pair_v[2]);
+        QZ_LAUNCH(ctx, msm_pair_tree_down, (unsigned)((T2 + 127) / 128), 128, 0, pair_ctl, l, 1, pair_v[1], pair_pre[1], pair_v[2]);
+        QZ_LAUNCH(ctx, msm_pair_tree_down, (unsigned)((T1 + 127) / 128), 128, 0, pair_ctl, l, 0, pair_v[0], pair_pre[0], pair_v[1]);
+        QZ_LAUNCH(ctx, msm_pair_apply, (unsigned)((T + 127) / 128), 128, 0, kc, vc, pair_ctl, l, dmask, bases, pair_sums,
+                  pair_prefix, pair_v[0], pair_offs, T, kbuf[cur ^ 1], vbuf[cur ^ 1]);
+        cur ^= 1;
+      }
+      QZ_LAUNCH(ctx, msm_accumulate<true>, (unsigned)((seg_chunks + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0,
+                (const uint32_t*)kbuf[cur], (const uint32_t*)vbuf[cur], (uint64_t)0, &pair_ctl->m[pair_levels], seg_chunks, chunk_len, bases, pair_sums, c, buckets,
+                ppts_a + chunk_base[s] * 256, pkeys_a + 2 * chunk_base[s]);
+    } else {
+      QZ_LAUNCH(ctx, msm_accumulate<false>, (unsigned)((seg_chunks + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0,
+                dk.Current(), dv.Current(), ms, (const uint64_t*)nullptr, seg_chunks, chunk_len, bases,
+                (const uint8_t*)nullptr, c, buckets, ppts_a + chunk_base[s] * 256, pkeys_a + 2 * chunk_base[s]);
+    }
     QZ_CUDA(ctx, cudaEventRecord(S > 1 ? ctx->ev_acc1[s] : ctx->ev_k1, st));
     if (ring) {
       QZ_CUDA(ctx, cudaEventRecord(ring1, st));

@@ -428,3 +428,147 @@ def test_toom3_sampling_with_derived_s1_equals_reference_formulation(n):
         tr = py.Transcript(b"toom")
         got = sumcheck_toom3_skip1(n, tables, claimed, tr)
         assert got == want and tr.state == tr_ref.state
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+PAIR_B, PAIR_G, VAL_PAIR = 16, 64, 1 << 30
+
+
+def _batch_inverse_tree(v, p):
+    """msm_pair_tree_up / _root / _down: invert every element through a product tree of fan-in PAIR_G (two levels up,
+    one modular inversion per root, two levels down); `pre` holds the running product before each element"""
+    levels, pres = [list(v)], []
+    for _ in range(2):
+        cur, pre, up = levels[-1], [0] * len(levels[-1]), []
+        for u in range(0, len(cur), PAIR_G):
+            run = 1
+            for i in range(u, min(u + PAIR_G, len(cur))):
+                pre[i] = run
+                run = run * cur[i] % p
+            up.append(run)
+        pres.append(pre)
+        levels.append(up)
+    levels[2] = [pow(x, p - 2, p) for x in levels[2]]
+    for depth in (1, 0):
+        cur, pre, up = levels[depth], pres[depth], levels[depth + 1]
+        for u in range(len(up)):
+            inv = up[u]
+            for i in reversed(range(u * PAIR_G, min(u * PAIR_G + PAIR_G, len(cur)))):
+                x = cur[i]
+                cur[i] = inv * pre[i] % p
+                inv = inv * x % p
+    return levels[0]
+
+
+def pair_level(keys, vals, dmask, bases, sums):
+    """One pair level of csrc/msm.cu (msm_pair_scan, the inversion tree, msm_pair_apply) over Python ints: returns the
+    output list; appends this level's pair sums to `sums`.  Points are (x, y) with (0, 0) = infinity, values carry the
+    sign in bit 31 and VAL_PAIR when they address `sums`."""
+    q = py.FQ
+    m = len(keys)
+
+    def point(val):
+        x, y = (sums if val & VAL_PAIR else bases)[val & (VAL_PAIR - 1)]
+        return (x, (-y) % q if val >> 31 else y)
+
+    def candidate(a):  # the scan and the apply pass take the same decision from the same inputs
+        if a + 1 >= m or keys[a] != keys[a + 1] or not keys[a] & dmask:
+            return None
+        xa, xb = point(vals[a])[0], point(vals[a + 1])[0]
+        d = (xb - xa) % q
+        return d if xa and xb and d else None
+
+    n_threads = (m + 2 * PAIR_B - 1) // (2 * PAIR_B)
+    prefix, totals, counts = {}, [], []
+    for t in range(n_threads):  # scan
+        run, n_out, n_sum = 1, 0, 0
+        for j in range(PAIR_B):
+            a = 32 * t + 2 * j
+            if a >= m:
+                break
+            d = candidate(a)
+            if d is not None:
+                prefix[t * PAIR_B + j] = run
+                run = run * d % q
+                n_out, n_sum = n_out + 1, n_sum + 1
+            else:
+                n_out += (keys[a] & dmask != 0) + (a + 1 < m and keys[a + 1] & dmask != 0)
+        totals.append(run)
+        counts.append((n_out, n_sum))
+    offs = [(0, 0)]
+    for c in counts:  # exclusive scan of the packed counts, with the extra item that receives the totals
+        offs.append((offs[-1][0] + c[0], offs[-1][1] + c[1]))
+    inv_totals = _batch_inverse_tree(totals, q)
+    sum_base = len(sums)
+    m_out, n_sums = offs[n_threads]
+    keys_out, vals_out = [None] * m_out, [None] * m_out
+    sums.extend([None] * n_sums)
+    for t in range(n_threads):  # apply, backwards
+        pos, sidx = offs[t + 1][0], sum_base + offs[t + 1][1]
+        inv = inv_totals[t]
+        left = m - 32 * t
+        n_pairs = PAIR_B if left >= 2 * PAIR_B else (left + 1) // 2
+        for j in reversed(range(n_pairs)):
+            a = 32 * t + 2 * j
+            d = candidate(a)
+            if d is not None:
+                (xa, ya), (xb, yb) = point(vals[a]), point(vals[a + 1])
+                dinv = inv * prefix[t * PAIR_B + j] % q
+                inv = inv * d % q
+                lam = (yb - ya) * dinv % q
+                x3 = (lam * lam - xa - xb) % q
+                sidx -= 1
+                sums[sidx] = (x3, (lam * (xa - x3) - ya) % q)
+                pos -= 1
+                keys_out[pos], vals_out[pos] = keys[a], VAL_PAIR | sidx
+            else:
+                if a + 1 < m and keys[a + 1] & dmask:
+                    pos -= 1
+                    keys_out[pos], vals_out[pos] = keys[a + 1], vals[a + 1]
+                if keys[a] & dmask:
+                    pos -= 1
+                    keys_out[pos], vals_out[pos] = keys[a], vals[a]
+        assert pos == offs[t][0] and sidx == sum_base + offs[t][1]
+    return keys_out, vals_out
+
+
+def test_pair_levels_keep_every_bucket_sum():
+    rnd = random.Random(5)
+    c = 6
+    dmask = (1 << c) - 1
+    base_pts = [py.g1_mul(py.G1_GEN, k) for k in range(1, 40)]
+    bases = [(0, 0)] + base_pts  # index 0: infinity in the SRS
+
+    def as_opt(pt):
+        return None if pt == (0, 0) else pt
+
+    for trial in range(12):
+        m = rnd.choice([1, 2, 31, 32, 33, 64, 65, 200, 333])
+        n_keys = rnd.choice([1, 3, 20])
+        entries = []
+        for _ in range(m):
+            key = (rnd.randrange(2) << c) | rnd.choice([0] + list(range(1, n_keys + 1)))
+            if trial % 3 == 0:  # few distinct points: equal x (P + P and P - P) inside buckets
+                idx = rnd.randrange(0, 3)
+            else:
+                idx = rnd.randrange(0, len(bases))
+            entries.append((key, idx | (rnd.randrange(2) << 31)))
+        entries.sort(key=lambda e: e[0])
+        keys, vals = [e[0] for e in entries], [e[1] for e in entries]
+        want = {}
+        for k, v in zip(keys, vals):
+            if k & dmask:
+                pt = as_opt(bases[v & (VAL_PAIR - 1)])
+                want[k] = py.g1_add(want.get(k), py.g1_neg(pt) if v >> 31 else pt)
+        sums = []
+        for level in range(4):
+            keys, vals = pair_level(keys, vals, dmask, bases, sums)
+            assert keys == sorted(keys) and all(k & dmask for k in keys)
+            assert len(sums) <= max(0, m - 1)
+            got = {}
+            for k, v in zip(keys, vals):
+                x, y = (sums if v & VAL_PAIR else bases)[v & (VAL_PAIR - 1)]
+                pt = as_opt((x, (-y) % py.FQ if v >> 31 else y))
+                got[k] = py.g1_add(got.get(k), pt)
+            assert {k: v for k, v in got.items() if v is not None} == {k: v for k, v in want.items() if v is not None}
+        assert all(py.g1_is_on_curve(s) for s in sums)

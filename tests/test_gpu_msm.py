@@ -296,3 +296,61 @@ def test_commit_split_and_accumulate_stats(ctx, kzg_big):
     kzg_big.commit(d)
     assert ctx.msm_accumulate_stats(0)[2] == 0  # collection stopped
     d.free()
+
+
+@pytest.mark.parametrize("levels", [1, 3, 8])
+def test_pair_levels(ctx, kzg_big, levels, monkeypatch):
+    """QZ_MSM_PAIR_LEVELS: equal-key neighbours of the sorted list are added in affine coordinates with a shared
+    inversion before the XYZZ accumulation (csrc/msm.cu msm_pair_*; CPU model: tests/test_device_models.py).  Not a bit
+    may change: ragged sizes, skewed scalars, P + P / P - P / infinity inside buckets, precomputed windows, streamed
+    ranges, KZG::open, the 2^20 closed form."""
+    monkeypatch.setenv("QZ_MSM_PAIR_LEVELS", str(levels))
+    threads = os.cpu_count() or 1
+    rnd = random.Random(levels)
+    for n in (63, 64, 65, 100, 1000, 4097, 1 << 14):
+        bases = kzg_big.srs.download(0, n)
+        cases = [util.rand_fr(n, 500 + n)]
+        if n == 4097:
+            cases += [co.to_mont([rnd.randrange(2) for _ in range(n)]), co.to_mont([rnd.randrange(256) for _ in range(n)]),
+                      co.to_mont([FR - 1] * n), co.to_mont([rnd.choice([0, 1, FR - 1, 1 << 128]) for _ in range(n)])]
+        for sc in cases:
+            want = co.msm(bases, sc, mode=1, threads=threads)
+            assert np.array_equal(kzg_big.commit(sc), want), n
+            dev = ctx.upload(sc)
+            assert np.array_equal(kzg_big.commit(dev), want), (n, "device scalars")
+            dev.free()
+    # repeated and opposite points, infinity in the SRS
+    srs = co.srs_generate(co.g1_to_bytes(GEN), co.fr1(TAU), 40, threads=2)
+    p = srs[3]
+    neg = co.g1_to_bytes(py.g1_neg(co.g1_from_bytes(p)))
+    pts = np.stack([p] * 50 + [neg] * 50 + [srs[4]] * 33 + [np.zeros(64, np.uint8)] * 7)
+    kz = q.KZG.from_points(ctx, pts)
+    for s in (np.concatenate([co.to_mont([3] * 100), util.rand_fr(40, 1)]), co.to_mont([5] * 140), util.rand_fr(140, 2)):
+        assert np.array_equal(kz.commit(s), co.msm(pts, s))
+    kz.srs.free()
+    # precomputed windows (one shared bucket set: long runs), with streamed ranges on top, and KZG::open
+    n = 3000
+    srs = co.srs_generate(co.g1_to_bytes(GEN), co.fr1(TAU), n, threads=4)
+    srs[7] = 0
+    for c in (5, 13, 0):
+        kz = q.KZG.from_points(ctx, srs).precompute(c)
+        for s in (util.rand_fr(n, 3 + c), co.to_mont([rnd.randrange(4) for _ in range(n)]), co.to_mont([FR - 1] * n)):
+            assert np.array_equal(kz.commit(s), co.msm(srs, s, mode=1, threads=threads)), c
+        monkeypatch.setenv("QZ_MSM_SEGMENTS", "2,5,12")
+        s = util.rand_fr(n, 77)
+        assert np.array_equal(kz.commit(s), co.msm(srs, s, mode=1, threads=threads)), (c, "segments")
+        monkeypatch.delenv("QZ_MSM_SEGMENTS")
+        pr = kz.open(s, co.fr1(12345))
+        y, qpoly = co.kzg_open_quotient(s, co.fr1(12345))
+        assert np.array_equal(pr.y, y) and np.array_equal(pr.proof, co.msm(srs, qpoly, mode=1, threads=threads))
+        kz.srs.free()
+    # BASELINE config 2 through the closed form, device and host (streamed) scalars
+    n = 1 << 20
+    buf = ctx.random_fr(n, 2020 + levels)
+    sc = buf.download().reshape(-1, 32)
+    got_dev = kzg_big.commit(buf)
+    got_host = kzg_big.commit(sc)
+    buf.free()
+    y, _ = co.kzg_open_quotient(sc, co.fr1(TAU))
+    want = co.g1_mul(co.g1_to_bytes(GEN), y)
+    assert np.array_equal(got_dev, want) and np.array_equal(got_host, want)
