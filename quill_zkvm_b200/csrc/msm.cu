@@ -173,24 +173,28 @@ __global__ void __launch_bounds__(ACC_THREADS, 4) msm_accumulate(const uint32_t*
 // ---- 4b. pair levels: affine additions with a shared inversion, ahead of the accumulation --------------------------
 // A mixed addition into an XYZZ accumulator is 10 products.  Two AFFINE points add in 1 inversion + 3 products, and
 // Montgomery's trick turns n inversions into one inversion + 3 (n - 1) products, i.e. ~6 products per addition when
-// the batch is large.  A level pairs the entries at positions (2i, 2i + 1) of the sorted list: when both carry the same
+// the batch is large.  A level pairs the entries at positions (2p, 2p + 1) of the sorted list: when both carry the same
 // non-zero key, their sum is written to the array of pair sums and ONE entry (key, VAL_PAIR | index of the sum) takes
 // their place; any other pair passes through unchanged (zero digits are dropped), so the output is again a list sorted
 // by key whose entries sum to the same buckets, about half as long.  L levels leave runs of ~r / 2^L entries for the
 // XYZZ accumulation, where r = entries per bucket.  Pairs that cannot be added by the affine chord rule -- equal x
 // (P + P, P - P) or an infinite point -- pass through as well: the complete XYZZ law downstream handles them, which
 // keeps this stage free of special cases.
-// One level = three passes over chunks of PAIR_B pairs per thread, with no thread ever waiting on an inversion:
+// A block owns a tile of PAIR_TILE consecutive pairs; thread i takes pairs i, i + 128, i + 256, .. of the tile, so that
+// a warp's accesses to the keys, values, prefixes, outputs and (from level 2 on) the points are to neighbouring
+// addresses.  One level = three passes, with no thread ever waiting on an inversion:
 //   scan   d = x_b - x_a per pair; running product of the thread's d's (prefix[pair] = the product BEFORE the pair),
-//          the thread's total and its output / sum counts
-//   invert the totals, by a product tree of fan-in PAIR_G: up, up, one Fermat inversion per root, down, down
+//          the thread's total, a code per pair (outputs 0..2, summed or not) and the tile's output / sum counts
+//   invert the threads' totals, by a product tree of fan-in PAIR_G: up, up, one Fermat inversion per root, down, down
 //   apply  walks the thread's pairs backwards: 1/d = inv * prefix, inv *= d; lambda = (y_b - y_a) / d,
-//          x3 = lambda^2 - x_a - x_b, y3 = lambda (x_a - x3) - y_a; outputs land at the positions an exclusive scan of
-//          the counts assigns (order preserved)
-// The list lengths live on the device (PairCtl): launches cover the longest list possible and threads past the end
+//          x3 = lambda^2 - x_a - x_b, y3 = lambda (x_a - x3) - y_a.  Outputs land, in list order, at the tile's base
+//          (exclusive scan of the tiles' counts) + the pair's offset inside the tile (block scan of the codes).
+// The list lengths live on the device (PairCtl): launches cover the longest list possible and tiles past the end
 // return, so the host never synchronises.  The sums written by all levels number at most m - 1 (every sum shortens
 // the list by one): the array of m slots cannot overflow whatever the input.
 constexpr int PAIR_B = 16;            // pairs per thread
+constexpr int PAIR_THREADS = 128;
+constexpr int PAIR_TILE = PAIR_B * PAIR_THREADS;  // pairs per block
 constexpr int PAIR_G = 64;            // fan-in of the inversion's product tree
 constexpr int PAIR_MAX_LEVELS = 8;
 struct PairCtl {
@@ -202,50 +206,68 @@ __global__ void msm_pair_init(PairCtl* ctl, uint64_t m, unsigned long long* coun
     ctl->m[l] = l == 0 ? m : 0;
     ctl->sums[l] = 0;
   }
-  *counts_last = 0;  // the scan's extra item: offs[n_threads] = the totals
+  *counts_last = 0;  // the scan's extra item: offs[n_tiles] = the totals
 }
-__global__ void __launch_bounds__(128, 8) msm_pair_scan(const uint32_t* keys, const uint32_t* vals, const PairCtl* ctl, int level,
-                                                      uint32_t dmask, const uint8_t* bases, const uint8_t* sums,
-                                                      uint8_t* prefix, uint8_t* totals, unsigned long long* counts,
-                                                      uint64_t n_threads) {
-  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_threads) return;
-  const uint64_t m = ctl->m[level], e0 = t * (2 * PAIR_B);
-  if (e0 >= m) {
-    counts[t] = 0;
+// entries a = 2p, a + 1 of pair p: keys and values (0 past the end of the list: a zero digit)
+QZ_DEV void pair_entries(const uint32_t* keys, const uint32_t* vals, uint64_t a, uint64_t m, uint32_t& ka, uint32_t& kb,
+                         uint32_t& va, uint32_t& vb) {
+  ka = kb = va = vb = 0;
+  if (a + 1 < m) {  // a is even and the lists are 8-byte aligned
+    const uint2 k2 = *reinterpret_cast<const uint2*>(keys + a), v2 = *reinterpret_cast<const uint2*>(vals + a);
+    ka = k2.x, kb = k2.y, va = v2.x, vb = v2.y;
+  } else if (a < m) {
+    ka = keys[a], va = vals[a];
+  }
+}
+// codes: bits 0-1 = outputs of the pair (0..2), bit 2 = the pair is summed (then one output)
+__global__ void __launch_bounds__(PAIR_THREADS, 8) msm_pair_scan(const uint32_t* keys, const uint32_t* vals, const PairCtl* ctl,
+                                                               int level, uint32_t dmask, const uint8_t* bases,
+                                                               const uint8_t* sums, uint8_t* prefix, uint8_t* totals,
+                                                               uint8_t* codes, unsigned long long* counts) {
+  __shared__ unsigned long long s_cnt[PAIR_THREADS / 32];
+  const uint64_t m = ctl->m[level], tile0 = (uint64_t)blockIdx.x * PAIR_TILE;
+  const int i = threadIdx.x;
+  if (2 * tile0 >= m) {
+    if (i == 0) counts[blockIdx.x] = 0;
     return;
   }
   Fq run = fp_one<FqParams>();
   uint32_t n_out = 0, n_sum = 0;
+#pragma unroll 1
   for (int j = 0; j < PAIR_B; j++) {
-    const uint64_t a = e0 + 2 * j;
-    if (a >= m) break;
-    const bool has_b = a + 1 < m;
-    const uint32_t ka = keys[a], kb = has_b ? keys[a + 1] : 0u;
-    bool paired = false;
-    if (has_b && ka == kb && (ka & dmask)) {
-      const Fq xa = fp_load<FqParams>(entry_point(bases, sums, vals[a]));
-      const Fq xb = fp_load<FqParams>(entry_point(bases, sums, vals[a + 1]));
+    const uint64_t p = tile0 + (uint64_t)j * PAIR_THREADS + i, a = 2 * p;
+    uint32_t ka, kb, va, vb;
+    pair_entries(keys, vals, a, m, ka, kb, va, vb);
+    uint32_t code = ((ka & dmask) != 0) + ((kb & dmask) != 0);
+    if (ka == kb && (ka & dmask)) {
+      const Fq xa = fp_load<FqParams>(entry_point(bases, sums, va));
+      const Fq xb = fp_load<FqParams>(entry_point(bases, sums, vb));
       const Fq d = fp_sub<FqParams>(xb, xa);
       if (!fp_is_zero<FqParams>(xa) && !fp_is_zero<FqParams>(xb) && !fp_is_zero<FqParams>(d)) {
-        paired = true;
-        fp_store<FqParams>(prefix + (t * PAIR_B + j) * 32, run);
+        code = 4 | 1;
+        fp_store<FqParams>(prefix + p * 32, run);
         run = fp_mul<FqParams>(run, d);
       }
     }
-    if (paired) {
-      n_out++;
-      n_sum++;
-    } else {
-      n_out += ((ka & dmask) != 0) + (has_b && (kb & dmask) != 0);
-    }
+    codes[p] = (uint8_t)code;
+    n_out += code & 3;
+    n_sum += code >> 2;
   }
-  fp_store<FqParams>(totals + t * 32, run);
-  counts[t] = (unsigned long long)n_out | ((unsigned long long)n_sum << 32);
+  fp_store<FqParams>(totals + ((uint64_t)blockIdx.x * PAIR_THREADS + i) * 32, run);
+  unsigned long long cnt = (unsigned long long)n_out | ((unsigned long long)n_sum << 32);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, off);
+  if ((i & 31) == 0) s_cnt[i >> 5] = cnt;
+  __syncthreads();
+  if (i == 0) {
+    unsigned long long total = 0;
+    for (int w = 0; w < PAIR_THREADS / 32; w++) total += s_cnt[w];
+    counts[blockIdx.x] = total;
+  }
 }
 // elements of the inversion tree at `depth` above the threads' totals (depth 0) for the list entering `level`
 QZ_DEV uint64_t pair_tree_count(const PairCtl* ctl, int level, int depth) {
-  uint64_t n = (ctl->m[level] + 2 * PAIR_B - 1) / (2 * PAIR_B);
+  uint64_t n = (ctl->m[level] + 2 * PAIR_TILE - 1) / (2 * PAIR_TILE) * PAIR_THREADS;
   for (int k = 0; k < depth; k++) n = (n + PAIR_G - 1) / PAIR_G;
   return n;
 }
@@ -280,66 +302,87 @@ __global__ void __launch_bounds__(128) msm_pair_tree_down(const PairCtl* ctl, in
     inv = fp_mul<FqParams>(inv, x);
   }
 }
-__global__ void __launch_bounds__(128, 4) msm_pair_apply(const uint32_t* keys, const uint32_t* vals, PairCtl* ctl, int level,
-                                                       uint32_t dmask, const uint8_t* bases, uint8_t* sums,
-                                                       const uint8_t* prefix, const uint8_t* totals_inv,
-                                                       const unsigned long long* offs, uint64_t n_threads,
-                                                       uint32_t* keys_out, uint32_t* vals_out) {
-  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_threads) return;
-  const uint64_t m = ctl->m[level], sum_base = ctl->sums[level], e0 = t * (2 * PAIR_B);
-  if (t == 0) {  // the next level's list length and first free sum slot
-    const unsigned long long total = offs[n_threads];
+__global__ void __launch_bounds__(PAIR_THREADS, 4) msm_pair_apply(const uint32_t* keys, const uint32_t* vals, PairCtl* ctl, int level,
+                                                                uint32_t dmask, const uint8_t* bases, uint8_t* sums,
+                                                                const uint8_t* prefix, const uint8_t* totals_inv,
+                                                                const uint8_t* codes, const unsigned long long* offs,
+                                                                uint32_t n_tiles, uint32_t* keys_out, uint32_t* vals_out) {
+  // per pair: offset of its outputs inside the tile (bits 0-15) and of its sum (bits 16-28), its code (bits 29-31)
+  __shared__ uint32_t s_off[PAIR_B][PAIR_THREADS];
+  __shared__ uint32_t s_warp[PAIR_B][PAIR_THREADS / 32];
+  const uint64_t m = ctl->m[level], sum_base = ctl->sums[level], tile0 = (uint64_t)blockIdx.x * PAIR_TILE;
+  const int i = threadIdx.x, lane = i & 31, warp = i >> 5;
+  if (blockIdx.x == 0 && i == 0) {  // the next level's list length and first free sum slot
+    const unsigned long long total = offs[n_tiles];
     ctl->m[level + 1] = total & 0xffffffffull;
     ctl->sums[level + 1] = sum_base + (total >> 32);
   }
-  if (e0 >= m) return;
-  const unsigned long long end = offs[t + 1];  // exclusive scan: this thread's outputs END here
-  uint64_t pos = end & 0xffffffffull, sidx = sum_base + (end >> 32);
-  Fq inv = fp_load<FqParams>(totals_inv + t * 32);
-  const uint64_t left = m - e0;
-  const int n_pairs = left >= 2 * PAIR_B ? PAIR_B : (int)((left + 1) / 2);
-  for (int j = n_pairs - 1; j >= 0; j--) {
-    const uint64_t a = e0 + 2 * j;
-    const bool has_b = a + 1 < m;
-    const uint32_t ka = keys[a], kb = has_b ? keys[a + 1] : 0u;
-    const uint32_t va = vals[a], vb = has_b ? vals[a + 1] : 0u;
-    bool paired = false;
-    if (has_b && ka == kb && (ka & dmask)) {
-      // both points and the prefix are requested together: one memory round trip per pair, not three
+  if (2 * tile0 >= m) return;
+#pragma unroll
+  for (int j = 0; j < PAIR_B; j++) {  // offsets in list order: row j of the tile = pairs j * 128 .. j * 128 + 127
+    const uint32_t code = codes[tile0 + (uint64_t)j * PAIR_THREADS + i];
+    const uint32_t v = (code & 3) | ((code >> 2) << 16);
+    uint32_t incl = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += up;
+    }
+    s_off[j][i] = (incl - v) | (code << 29);
+    if (lane == 31) s_warp[j][warp] = incl;
+  }
+  __syncthreads();
+  if (i == 0) {
+    uint32_t running = 0;
+    for (int j = 0; j < PAIR_B; j++)
+      for (int w = 0; w < PAIR_THREADS / 32; w++) {
+        const uint32_t t = s_warp[j][w];
+        s_warp[j][w] = running;
+        running += t;
+      }
+  }
+  __syncthreads();
+  const unsigned long long tile_off = offs[blockIdx.x];
+  const uint64_t pos_base = tile_off & 0xffffffffull, sidx_base = sum_base + (tile_off >> 32);
+  Fq inv = fp_load<FqParams>(totals_inv + ((uint64_t)blockIdx.x * PAIR_THREADS + i) * 32);
+#pragma unroll 1
+  for (int j = PAIR_B - 1; j >= 0; j--) {
+    const uint32_t packed = s_off[j][i], code = packed >> 29;
+    if ((code & 3) == 0) continue;  // nothing to write (both digits zero, or past the end of the list)
+    const uint32_t off = (packed & 0x1fffffffu) + s_warp[j][warp];
+    const uint64_t p = tile0 + (uint64_t)j * PAIR_THREADS + i, a = 2 * p;
+    uint64_t pos = pos_base + (off & 0xffffu);
+    uint32_t ka, kb, va, vb;
+    pair_entries(keys, vals, a, m, ka, kb, va, vb);
+    if (code & 4) {
+      // both points and the prefix are requested together: one memory round trip per pair
       const uint8_t* pa = entry_point(bases, sums, va);
       const uint8_t* pb = entry_point(bases, sums, vb);
       const Fq xa = fp_load<FqParams>(pa), xb = fp_load<FqParams>(pb);
       Fq ya = fp_load<FqParams>(pa + 32), yb = fp_load<FqParams>(pb + 32);
-      const Fq pre = fp_load<FqParams>(prefix + (t * PAIR_B + j) * 32);  // unwritten (and unused) when the pair passes through
+      const Fq pre = fp_load<FqParams>(prefix + p * 32);
       const Fq d = fp_sub<FqParams>(xb, xa);
-      if (!fp_is_zero<FqParams>(xa) && !fp_is_zero<FqParams>(xb) && !fp_is_zero<FqParams>(d)) {
-        paired = true;
-        if (va >> 31) ya = fp_neg<FqParams>(ya);
-        if (vb >> 31) yb = fp_neg<FqParams>(yb);
-        const Fq dinv = fp_mul<FqParams>(inv, pre);
-        inv = fp_mul<FqParams>(inv, d);
-        const Fq lam = fp_mul<FqParams>(fp_sub<FqParams>(yb, ya), dinv);
-        Affine s;
-        s.x = fp_sub<FqParams>(fp_sub<FqParams>(fp_sqr<FqParams>(lam), xa), xb);
-        s.y = fp_sub<FqParams>(fp_mul<FqParams>(lam, fp_sub<FqParams>(xa, s.x)), ya);
-        --sidx;
-        affine_store(sums + sidx * 64, s);
-        --pos;
-        keys_out[pos] = ka;
-        vals_out[pos] = VAL_PAIR | (uint32_t)sidx;
-      }
-    }
-    if (!paired) {
-      if (has_b && (kb & dmask)) {
-        --pos;
-        keys_out[pos] = kb;
-        vals_out[pos] = vb;
-      }
+      if (va >> 31) ya = fp_neg<FqParams>(ya);
+      if (vb >> 31) yb = fp_neg<FqParams>(yb);
+      const Fq dinv = fp_mul<FqParams>(inv, pre);
+      inv = fp_mul<FqParams>(inv, d);
+      const Fq lam = fp_mul<FqParams>(fp_sub<FqParams>(yb, ya), dinv);
+      Affine r;
+      r.x = fp_sub<FqParams>(fp_sub<FqParams>(fp_sqr<FqParams>(lam), xa), xb);
+      r.y = fp_sub<FqParams>(fp_mul<FqParams>(lam, fp_sub<FqParams>(xa, r.x)), ya);
+      const uint64_t sidx = sidx_base + (off >> 16);
+      affine_store(sums + sidx * 64, r);
+      keys_out[pos] = ka;
+      vals_out[pos] = VAL_PAIR | (uint32_t)sidx;
+    } else {
       if (ka & dmask) {
-        --pos;
         keys_out[pos] = ka;
         vals_out[pos] = va;
+        pos++;
+      }
+      if (kb & dmask) {
+        keys_out[pos] = kb;
+        vals_out[pos] = vb;
       }
     }
   }
@@ -868,7 +911,7 @@ int msm_run(qz_ctx* ctx, const qz_srs* srs, uint4* scalars_dev, const void* scal
     const char* env = getenv("QZ_MSM_PAIR_LEVELS");
     if (env && *env) pair_levels = std::max(0, std::min(PAIR_MAX_LEVELS, atoi(env)));
     const uint64_t max_index = (collapsed ? (uint64_t)Wd * srs->n : (uint64_t)srs->n);
-    if (m >= VAL_PAIR || max_index >= VAL_PAIR || m < 4 * PAIR_B) pair_levels = 0;
+    if (m >= VAL_PAIR || max_index >= VAL_PAIR || m < 64) pair_levels = 0;
   }
   if (pair_levels) {  // the list the accumulation sees is ~2^levels shorter: keep enough chunks to fill the machine
     chunk_len = (int)std::min<uint64_t>(ACC_CHUNK_MAX, (m >> pair_levels) / ((uint64_t)ctx->sm_count * 4 * ACC_THREADS * 16));
@@ -940,26 +983,28 @@ int msm_run(qz_ctx* ctx, const qz_srs* srs, uint4* scalars_dev, const void* scal
     return ctx->fail(QZ_ERR_ALLOC, "MSM scratch");
   // pair levels (msm_pair_*): scratch for the longest segment, shared by the segments (they run in turn on `st`)
   PairCtl* pair_ctl = nullptr;
-  uint8_t *pair_sums = nullptr, *pair_prefix = nullptr, *pair_v[3] = {nullptr, nullptr, nullptr}, *pair_pre[2] = {nullptr, nullptr};
+  uint8_t *pair_sums = nullptr, *pair_prefix = nullptr, *pair_codes = nullptr, *pair_v[3] = {nullptr, nullptr, nullptr}, *pair_pre[2] = {nullptr, nullptr};
   unsigned long long *pair_counts = nullptr, *pair_offs = nullptr;
   void* pair_scan_tmp = nullptr;
   size_t pair_scan_bytes = 0;
   uint64_t pair_n[3] = {0, 0, 0};
   if (pair_levels) {
     const uint64_t mmax = (uint64_t)Wd * max_seg;
-    pair_n[0] = (mmax + 2 * PAIR_B - 1) / (2 * PAIR_B);
+    const uint64_t tiles = (mmax + 2 * PAIR_TILE - 1) / (2 * PAIR_TILE);
+    pair_n[0] = tiles * PAIR_THREADS;
     pair_n[1] = (pair_n[0] + PAIR_G - 1) / PAIR_G;
     pair_n[2] = (pair_n[1] + PAIR_G - 1) / PAIR_G;
     pair_ctl = (PairCtl*)ctx->arena_alloc(sizeof(PairCtl));
     pair_sums = (uint8_t*)ctx->arena_alloc(mmax * 64);
-    pair_prefix = (uint8_t*)ctx->arena_alloc(pair_n[0] * PAIR_B * 32);
+    pair_prefix = (uint8_t*)ctx->arena_alloc(tiles * PAIR_TILE * 32);
+    pair_codes = (uint8_t*)ctx->arena_alloc(tiles * PAIR_TILE);
     for (int k = 0; k < 3; k++) pair_v[k] = (uint8_t*)ctx->arena_alloc(pair_n[k] * 32);
     for (int k = 0; k < 2; k++) pair_pre[k] = (uint8_t*)ctx->arena_alloc(pair_n[k] * 32);
-    pair_counts = (unsigned long long*)ctx->arena_alloc((pair_n[0] + 1) * 8);
-    pair_offs = (unsigned long long*)ctx->arena_alloc((pair_n[0] + 1) * 8);
-    cub::DeviceScan::ExclusiveSum(nullptr, pair_scan_bytes, pair_counts, pair_offs, (int64_t)(pair_n[0] + 1), st);
+    pair_counts = (unsigned long long*)ctx->arena_alloc((tiles + 1) * 8);
+    pair_offs = (unsigned long long*)ctx->arena_alloc((tiles + 1) * 8);
+    cub::DeviceScan::ExclusiveSum(nullptr, pair_scan_bytes, pair_counts, pair_offs, (int64_t)(tiles + 1), st);
     pair_scan_tmp = ctx->arena_alloc(pair_scan_bytes);
-    if (!pair_ctl || !pair_sums || !pair_prefix || !pair_v[0] || !pair_v[1] || !pair_v[2] || !pair_pre[0] || !pair_pre[1] ||
+    if (!pair_ctl || !pair_sums || !pair_prefix || !pair_codes || !pair_v[0] || !pair_v[1] || !pair_v[2] || !pair_pre[0] || !pair_pre[1] ||
         !pair_counts || !pair_offs || !pair_scan_tmp)
       return ctx->fail(QZ_ERR_ALLOC, "MSM pair-level scratch");
   }
@@ -997,24 +1042,24 @@ int msm_run(qz_ctx* ctx, const qz_srs* srs, uint4* scalars_dev, const void* scal
       uint32_t* kbuf[2] = {dk.Current(), dk.Alternate()};  // a level reads one buffer of the sort's pair and writes the other
       uint32_t* vbuf[2] = {dv.Current(), dv.Alternate()};
       int cur = 0;
-      const uint64_t T = (ms + 2 * PAIR_B - 1) / (2 * PAIR_B);  // threads of a level over the longest list possible
-      const uint64_t T1 = (T + PAIR_G - 1) / PAIR_G, T2 = (T1 + PAIR_G - 1) / PAIR_G;
+      const uint64_t tiles = (ms + 2 * PAIR_TILE - 1) / (2 * PAIR_TILE);  // of a level over the longest list possible
+      const uint64_t T = tiles * PAIR_THREADS, T1 = (T + PAIR_G - 1) / PAIR_G, T2 = (T1 + PAIR_G - 1) / PAIR_G;
       const uint32_t dmask = (1u << c) - 1;
-      QZ_LAUNCH(ctx, msm_pair_init, 1, 1, 0, pair_ctl, ms, pair_counts + T);
+      QZ_LAUNCH(ctx, msm_pair_init, 1, 1, 0, pair_ctl, ms, pair_counts + tiles);
       for (int l = 0; l < pair_levels; l++) {
         const uint32_t* kc = kbuf[cur];
         const uint32_t* vc = vbuf[cur];
-        QZ_LAUNCH(ctx, msm_pair_scan, (unsigned)((T + 127) / 128), 128, 0, kc, vc, pair_ctl, l, dmask, bases, pair_sums,
-                  pair_prefix, pair_v[0], pair_counts, T);
-        QZ_CUDA(ctx, cub::DeviceScan::ExclusiveSum(pair_scan_tmp, pair_scan_bytes, pair_counts, pair_offs, (int64_t)(T + 1), st));
+        QZ_LAUNCH(ctx, msm_pair_scan, (unsigned)tiles, PAIR_THREADS, 0, kc, vc, pair_ctl, l, dmask, bases, pair_sums, pair_prefix,
+                  pair_v[0], pair_codes, pair_counts);
+        QZ_CUDA(ctx, cub::DeviceScan::ExclusiveSum(pair_scan_tmp, pair_scan_bytes, pair_counts, pair_offs, (int64_t)(tiles + 1), st));
         ctx->launches += 2;
         QZ_LAUNCH(ctx, msm_pair_tree_up, (unsigned)((T1 + 127) / 128), 128, 0, pair_ctl, l, 0, pair_v[0], pair_pre[0], pair_v[1]);
         QZ_LAUNCH(ctx, msm_pair_tree_up, (unsigned)((T2 + 127) / 128), 128, 0, pair_ctl, l, 1, pair_v[1], pair_pre[1], pair_v[2]);
         QZ_LAUNCH(ctx, msm_pair_tree_root, (unsigned)((T2 + 127) / 128), 128, 0, pair_ctl, l, 2, pair_v[2]);
         QZ_LAUNCH(ctx, msm_pair_tree_down, (unsigned)((T2 + 127) / 128), 128, 0, pair_ctl, l, 1, pair_v[1], pair_pre[1], pair_v[2]);
         QZ_LAUNCH(ctx, msm_pair_tree_down, (unsigned)((T1 + 127) / 128), 128, 0, pair_ctl, l, 0, pair_v[0], pair_pre[0], pair_v[1]);
-        QZ_LAUNCH(ctx, msm_pair_apply, (unsigned)((T + 127) / 128), 128, 0, kc, vc, pair_ctl, l, dmask, bases, pair_sums,
-                  pair_prefix, pair_v[0], pair_offs, T, kbuf[cur ^ 1], vbuf[cur ^ 1]);
+        QZ_LAUNCH(ctx, msm_pair_apply, (unsigned)tiles, PAIR_THREADS, 0, kc, vc, pair_ctl, l, dmask, bases, pair_sums, pair_prefix,
+                  pair_v[0], pair_codes, pair_offs, (uint32_t)tiles, kbuf[cur ^ 1], vbuf[cur ^ 1]);
         cur ^= 1;
       }
       QZ_LAUNCH(ctx, msm_accumulate<true>, (unsigned)((seg_chunks + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0,
