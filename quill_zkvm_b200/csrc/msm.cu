@@ -172,29 +172,32 @@ __global__ void __launch_bounds__(ACC_THREADS, 4) msm_accumulate(const uint32_t*
 
 // ---- 4b. pair levels: affine additions with a shared inversion, ahead of the accumulation --------------------------
 // A mixed addition into an XYZZ accumulator is 10 products.  Two AFFINE points add in 1 inversion + 3 products, and
-// Montgomery's trick turns n inversions into one inversion + 3 (n - 1) products, i.e. ~6.5 products per addition when
+// Montgomery's trick turns n inversions into one inversion + 3 (n - 1) products, i.e. ~6 products per addition when
 // the batch is large.  A level pairs the entries at positions (2p, 2p + 1) of the sorted list: when both carry the same
 // non-zero key, their sum is written to the array of pair sums and ONE entry (key, VAL_PAIR | index of the sum) takes
 // their place; any other pair passes through unchanged (zero digits are dropped), so the output is again a list sorted
 // by key whose entries sum to the same buckets, about half as long.  L levels leave runs of ~r / 2^L entries for the
-// XYZZ accumulation, where r = entries per bucket.  The affine law used here is COMPLETE -- chord, tangent (P + P, the
-// denominator 2y joins the batch), P - P and infinite operands ((0, 0), also the encoding of an infinite sum) -- so
-// whether a pair is summed depends on its keys alone, and the positions of a level's outputs follow from the keys.
-// A level = a count of each tile's outputs (keys only), an exclusive scan over the tiles, and ONE kernel in which a
-// block owns a tile of PAIR_TILE consecutive pairs, thread i taking pairs i, i + 128, .. (a warp touches neighbouring
-// keys, values, outputs and, from level 2 on, points):
-//   forward   denominator d per pair, running product of the thread's d's (kept in shared memory per pair)
-//   invert    product tree over the 128 thread totals in shared memory, ONE inversion per tile (binary Euclid on one
-//             thread; the other blocks of the SM keep the multiplier busy meanwhile), and back down the tree
-//   backward  1/d = inv * prefix, inv *= d; lambda = (y_b - y_a) / d or 3 x^2 / 2y; x3 = lambda^2 - x_a - x_b,
-//             y3 = lambda (x_a - x3) - y_a; outputs land, in list order, at the tile's base + the pair's offset inside
-//             the tile (block scan).  The points are read a second time here, out of L2.
+// XYZZ accumulation, where r = entries per bucket.  Pairs that cannot be added by the affine chord rule -- equal x
+// (P + P, P - P) or an infinite point -- pass through as well: the complete XYZZ law downstream handles them, which
+// keeps this stage free of special cases.
+// A block owns a tile of PAIR_TILE consecutive pairs; thread i takes pairs i, i + 128, i + 256, .. of the tile, so that
+// a warp's accesses to the keys, values, prefixes, outputs and (from level 2 on) the points are to neighbouring
+// addresses.  One level = three passes, with no thread ever waiting on an inversion:
+//   scan   d = x_b - x_a per pair; running product of the thread's d's (prefix[pair] = the product BEFORE the pair),
+//          the thread's total, a code per pair (outputs 0..2, summed or not) and the tile's output / sum counts
+//   invert the threads' totals, by a product tree of fan-in PAIR_G: up to ONE root, inverted by one thread (binary
+//          Euclid), and down again; every step is a short launch of chains of PAIR_G products
+//   apply  walks the thread's pairs backwards: 1/d = inv * prefix, inv *= d; lambda = (y_b - y_a) / d,
+//          x3 = lambda^2 - x_a - x_b, y3 = lambda (x_a - x3) - y_a.  Outputs land, in list order, at the tile's base
+//          (exclusive scan of the tiles' counts) + the pair's offset inside the tile (block scan of the codes).
 // The list lengths live on the device (PairCtl): launches cover the longest list possible and tiles past the end
 // return, so the host never synchronises.  The sums written by all levels number at most m - 1 (every sum shortens
 // the list by one): the array of m slots cannot overflow whatever the input.
-constexpr int PAIR_B = 8;             // pairs per thread
+constexpr int PAIR_B = 16;            // pairs per thread
 constexpr int PAIR_THREADS = 128;
 constexpr int PAIR_TILE = PAIR_B * PAIR_THREADS;  // pairs per block
+constexpr int PAIR_G = 16;            // fan-in of the inversion's product tree (short chains: the tree is pure latency)
+constexpr int PAIR_TREE_MAX = 10;     // depths: 16^8 threads' totals and more
 constexpr int PAIR_MAX_LEVELS = 8;
 struct PairCtl {
   uint64_t m[PAIR_MAX_LEVELS + 1];     // m[l]: entries entering level l; m[L]: entries left for msm_accumulate
@@ -218,81 +221,110 @@ QZ_DEV void pair_entries(const uint32_t* keys, const uint32_t* vals, uint64_t a,
     ka = keys[a], va = vals[a];
   }
 }
-// bits 0-1 = outputs of the pair (0..2), bit 2 = the pair is summed (one output)
-QZ_DEV uint32_t pair_code(uint32_t ka, uint32_t kb, uint32_t dmask) {
-  if (ka == kb && (ka & dmask)) return 4 | 1;
-  return ((ka & dmask) != 0) + ((kb & dmask) != 0);
-}
-__global__ void __launch_bounds__(256) msm_pair_count(const uint32_t* keys, const PairCtl* ctl, int level, uint32_t dmask,
-                                                      unsigned long long* counts) {
-  __shared__ unsigned long long s_cnt[8];
+QZ_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// codes: bits 0-1 = outputs of the pair (0..2), bit 2 = the pair is summed (then one output)
+__global__ void __launch_bounds__(PAIR_THREADS, 8) msm_pair_scan(const uint32_t* keys, const uint32_t* vals, const PairCtl* ctl,
+                                                               int level, uint32_t dmask, const uint8_t* bases,
+                                                               const uint8_t* sums, uint8_t* prefix, uint8_t* totals,
+                                                               uint8_t* codes, unsigned long long* counts) {
+  __shared__ unsigned long long s_cnt[PAIR_THREADS / 32];
   const uint64_t m = ctl->m[level], tile0 = (uint64_t)blockIdx.x * PAIR_TILE;
   const int i = threadIdx.x;
   if (2 * tile0 >= m) {
     if (i == 0) counts[blockIdx.x] = 0;
     return;
   }
-  unsigned long long cnt = 0;
-  for (int k = 0; k < PAIR_TILE / 256; k++) {
-    const uint64_t a = 2 * (tile0 + (uint64_t)k * 256 + i);
-    uint32_t ka = 0, kb = 0;
-    if (a + 1 < m) {
-      const uint2 k2 = *reinterpret_cast<const uint2*>(keys + a);
-      ka = k2.x, kb = k2.y;
-    } else if (a < m) {
-      ka = keys[a];
+  // all of the thread's candidate points are requested before the first is used (level 1 gathers them from all over
+  // the bases: the pass is bound by the memory's rate of random accesses, so every request should be in flight early)
+#pragma unroll 4
+  for (int j = 0; j < PAIR_B; j++) {
+    const uint64_t a = 2 * (tile0 + (uint64_t)j * PAIR_THREADS + i);
+    uint32_t ka, kb, va, vb;
+    pair_entries(keys, vals, a, m, ka, kb, va, vb);
+    if (ka == kb && (ka & dmask)) {
+      prefetch_l2(entry_point(bases, sums, va));
+      prefetch_l2(entry_point(bases, sums, vb));
     }
-    const uint32_t code = pair_code(ka, kb, dmask);
-    cnt += (unsigned long long)(code & 3) | ((unsigned long long)(code >> 2) << 32);
   }
+  Fq run = fp_one<FqParams>();
+  uint32_t n_out = 0, n_sum = 0;
+#pragma unroll 1
+  for (int j = 0; j < PAIR_B; j++) {
+    const uint64_t p = tile0 + (uint64_t)j * PAIR_THREADS + i, a = 2 * p;
+    uint32_t ka, kb, va, vb;
+    pair_entries(keys, vals, a, m, ka, kb, va, vb);
+    uint32_t code = ((ka & dmask) != 0) + ((kb & dmask) != 0);
+    if (ka == kb && (ka & dmask)) {
+      const Fq xa = fp_load<FqParams>(entry_point(bases, sums, va));
+      const Fq xb = fp_load<FqParams>(entry_point(bases, sums, vb));
+      const Fq d = fp_sub<FqParams>(xb, xa);
+      if (!fp_is_zero<FqParams>(xa) && !fp_is_zero<FqParams>(xb) && !fp_is_zero<FqParams>(d)) {
+        code = 4 | 1;
+        fp_store<FqParams>(prefix + p * 32, run);
+        run = fp_mul<FqParams>(run, d);
+      }
+    }
+    codes[p] = (uint8_t)code;
+    n_out += code & 3;
+    n_sum += code >> 2;
+  }
+  fp_store<FqParams>(totals + ((uint64_t)blockIdx.x * PAIR_THREADS + i) * 32, run);
+  unsigned long long cnt = (unsigned long long)n_out | ((unsigned long long)n_sum << 32);
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, off);
   if ((i & 31) == 0) s_cnt[i >> 5] = cnt;
   __syncthreads();
   if (i == 0) {
     unsigned long long total = 0;
-    for (int w = 0; w < 8; w++) total += s_cnt[w];
+    for (int w = 0; w < PAIR_THREADS / 32; w++) total += s_cnt[w];
     counts[blockIdx.x] = total;
   }
 }
-
-struct PairOperands {
-  Fq xa, ya, xb, yb;
-};
-QZ_DEV void pair_load(const uint8_t* bases, const uint8_t* sums, uint32_t va, uint32_t vb, PairOperands& o) {
-  const uint8_t* pa = entry_point(bases, sums, va);
-  const uint8_t* pb = entry_point(bases, sums, vb);
-  o.xa = fp_load<FqParams>(pa), o.xb = fp_load<FqParams>(pb);
-  o.ya = fp_load<FqParams>(pa + 32), o.yb = fp_load<FqParams>(pb + 32);
-  if (va >> 31) o.ya = fp_neg<FqParams>(o.ya);  // -0 = 0: the infinity encoding survives
-  if (vb >> 31) o.yb = fp_neg<FqParams>(o.yb);
+// elements of the inversion tree at `depth` above the threads' totals (depth 0) for the list entering `level`
+QZ_DEV uint64_t pair_tree_count(const PairCtl* ctl, int level, int depth) {
+  uint64_t n = (ctl->m[level] + 2 * PAIR_TILE - 1) / (2 * PAIR_TILE) * PAIR_THREADS;
+  for (int k = 0; k < depth; k++) n = (n + PAIR_G - 1) / PAIR_G;
+  return n;
 }
-enum { PAIR_COPY = 0, PAIR_INF = 1, PAIR_CHORD = 2, PAIR_TANGENT = 3 };  // >= PAIR_CHORD: a denominator joins the batch
-QZ_DEV int pair_classify(const PairOperands& o, Fq& d) {
-  const bool infa = fp_is_zero<FqParams>(o.xa) && fp_is_zero<FqParams>(o.ya);
-  const bool infb = fp_is_zero<FqParams>(o.xb) && fp_is_zero<FqParams>(o.yb);
-  if (infa || infb) return PAIR_COPY;
-  if (fp_eq<FqParams>(o.xa, o.xb)) {
-    if (fp_eq<FqParams>(o.ya, o.yb) && !fp_is_zero<FqParams>(o.ya)) {
-      d = fp_dbl<FqParams>(o.ya);
-      return PAIR_TANGENT;
-    }
-    return PAIR_INF;
+__global__ void __launch_bounds__(128) msm_pair_tree_up(const PairCtl* ctl, int level, int depth, const uint8_t* v, uint8_t* pre,
+                                                        uint8_t* v_up) {
+  const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t n = pair_tree_count(ctl, level, depth);
+  if (u * PAIR_G >= n) return;
+  const uint64_t end = u * PAIR_G + PAIR_G < n ? u * PAIR_G + PAIR_G : n;
+  Fq run = fp_one<FqParams>();
+  for (uint64_t i = u * PAIR_G; i < end; i++) {
+    fp_store<FqParams>(pre + i * 32, run);
+    run = fp_mul<FqParams>(run, fp_load<FqParams>(v + i * 32));
   }
-  d = fp_sub<FqParams>(o.xb, o.xa);
-  return PAIR_CHORD;
+  fp_store<FqParams>(v_up + u * 32, run);
 }
-QZ_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
+// the root: ONE element (the host climbs until the longest list possible is down to one), inverted by one thread
+__global__ void msm_pair_tree_root(const PairCtl* ctl, int level, uint8_t* v) {
+  if (pair_tree_count(ctl, level, 0) == 0) return;  // empty list: nothing was written below, nothing to invert
+  fp_store<FqParams>(v, fp_inv_serial<FqParams>(fp_load<FqParams>(v)));  // a product of non-zero d's: never 0
+}
+__global__ void __launch_bounds__(128) msm_pair_tree_down(const PairCtl* ctl, int level, int depth, uint8_t* v, const uint8_t* pre,
+                                                          const uint8_t* v_up) {
+  const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t n = pair_tree_count(ctl, level, depth);
+  if (u * PAIR_G >= n) return;
+  const uint64_t end = u * PAIR_G + PAIR_G < n ? u * PAIR_G + PAIR_G : n;
+  Fq inv = fp_load<FqParams>(v_up + u * 32);  // 1 / (product of this thread's elements)
+  for (uint64_t i = end; i-- > u * PAIR_G;) {
+    const Fq x = fp_load<FqParams>(v + i * 32);
+    fp_store<FqParams>(v + i * 32, fp_mul<FqParams>(inv, fp_load<FqParams>(pre + i * 32)));
+    inv = fp_mul<FqParams>(inv, x);
+  }
+}
 __global__ void __launch_bounds__(PAIR_THREADS, 4) msm_pair_apply(const uint32_t* keys, const uint32_t* vals, PairCtl* ctl, int level,
                                                                 uint32_t dmask, const uint8_t* bases, uint8_t* sums,
-                                                                const unsigned long long* offs, uint32_t n_tiles,
-                                                                uint32_t* keys_out, uint32_t* vals_out) {
+                                                                const uint8_t* prefix, const uint8_t* totals_inv,
+                                                                const uint8_t* codes, const unsigned long long* offs,
+                                                                uint32_t n_tiles, uint32_t* keys_out, uint32_t* vals_out) {
   // per pair: offset of its outputs inside the tile (bits 0-15) and of its sum (bits 16-28), its code (bits 29-31)
   __shared__ uint32_t s_off[PAIR_B][PAIR_THREADS];
   __shared__ uint32_t s_warp[PAIR_B][PAIR_THREADS / 32];
-  __shared__ uint32_t s_prefix[PAIR_B * 8][PAIR_THREADS];  // word w of pair row j at [j * 8 + w][thread]
-  __shared__ uint32_t s_tree[2 * PAIR_THREADS][8];         // node n = product of nodes 2n, 2n + 1; leaves 128 + thread
   const uint64_t m = ctl->m[level], sum_base = ctl->sums[level], tile0 = (uint64_t)blockIdx.x * PAIR_TILE;
   const int i = threadIdx.x, lane = i & 31, warp = i >> 5;
   if (blockIdx.x == 0 && i == 0) {  // the next level's list length and first free sum slot
@@ -301,16 +333,13 @@ __global__ void __launch_bounds__(PAIR_THREADS, 4) msm_pair_apply(const uint32_t
     ctl->sums[level + 1] = sum_base + (total >> 32);
   }
   if (2 * tile0 >= m) return;
-  // offsets in list order (row j of the tile = pairs j * 128 .. j * 128 + 127); the points go on their way to L2
 #pragma unroll
-  for (int j = 0; j < PAIR_B; j++) {
-    const uint64_t a = 2 * (tile0 + (uint64_t)j * PAIR_THREADS + i);
-    uint32_t ka, kb, va, vb;
-    pair_entries(keys, vals, a, m, ka, kb, va, vb);
-    const uint32_t code = pair_code(ka, kb, dmask);
-    if (code & 4) {
-      prefetch_l2(entry_point(bases, sums, va));
-      prefetch_l2(entry_point(bases, sums, vb));
+  for (int j = 0; j < PAIR_B; j++) {  // offsets in list order: row j of the tile = pairs j * 128 .. j * 128 + 127
+    const uint32_t code = codes[tile0 + (uint64_t)j * PAIR_THREADS + i];
+    if (code & 4) {  // both entries exist: request the points (first half; the y's share the 64-byte block)
+      const uint2 v2 = *reinterpret_cast<const uint2*>(vals + 2 * (tile0 + (uint64_t)j * PAIR_THREADS + i));
+      prefetch_l2(entry_point(bases, sums, v2.x));
+      prefetch_l2(entry_point(bases, sums, v2.y));
     }
     const uint32_t v = (code & 3) | ((code >> 2) << 16);
     uint32_t incl = v;
@@ -322,26 +351,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, 4) msm_pair_apply(const uint32_t
     s_off[j][i] = (incl - v) | (code << 29);
     if (lane == 31) s_warp[j][warp] = incl;
   }
-  // forward: the thread's running product of denominators
-  Fq run = fp_one<FqParams>();
-#pragma unroll 1
-  for (int j = 0; j < PAIR_B; j++) {
-    if (!(s_off[j][i] >> 31)) continue;  // bit 31 = bit 2 of the code: summed
-    const uint64_t a = 2 * (tile0 + (uint64_t)j * PAIR_THREADS + i);
-    const uint2 v2 = *reinterpret_cast<const uint2*>(vals + a);
-    PairOperands o;
-    pair_load(bases, sums, v2.x, v2.y, o);
-    Fq d;
-    if (pair_classify(o, d) >= PAIR_CHORD) {
-#pragma unroll
-      for (int w = 0; w < 8; w++) s_prefix[j * 8 + w][i] = run.v[w];
-      run = fp_mul<FqParams>(run, d);
-    }
-  }
-#pragma unroll
-  for (int w = 0; w < 8; w++) s_tree[PAIR_THREADS + i][w] = run.v[w];
   __syncthreads();
-  if (i == 0) {  // warp bases of the offsets, in (row, warp) order
+  if (i == 0) {
     uint32_t running = 0;
     for (int j = 0; j < PAIR_B; j++)
       for (int w = 0; w < PAIR_THREADS / 32; w++) {
@@ -350,74 +361,35 @@ __global__ void __launch_bounds__(PAIR_THREADS, 4) msm_pair_apply(const uint32_t
         running += t;
       }
   }
-  auto tree_load = [&](int node) {
-    Fq x;
-#pragma unroll
-    for (int w = 0; w < 8; w++) x.v[w] = s_tree[node][w];
-    return x;
-  };
-  auto tree_store = [&](int node, const Fq& x) {
-#pragma unroll
-    for (int w = 0; w < 8; w++) s_tree[node][w] = x.v[w];
-  };
-#pragma unroll 1
-  for (int s = PAIR_THREADS / 2; s >= 1; s >>= 1) {  // up: products
-    if (i < s) tree_store(s + i, fp_mul<FqParams>(tree_load(2 * (s + i)), tree_load(2 * (s + i) + 1)));
-    __syncthreads();
-  }
-  if (i == 0) tree_store(1, fp_inv_serial<FqParams>(tree_load(1)));  // denominators are never zero
   __syncthreads();
-#pragma unroll 1
-  for (int s = 1; s < PAIR_THREADS; s <<= 1) {  // down: inverse of a child = inverse of the parent x its sibling
-    if (i < s) {
-      const Fq invp = tree_load(s + i), l = tree_load(2 * (s + i)), r = tree_load(2 * (s + i) + 1);
-      tree_store(2 * (s + i), fp_mul<FqParams>(invp, r));
-      tree_store(2 * (s + i) + 1, fp_mul<FqParams>(invp, l));
-    }
-    __syncthreads();
-  }
-  Fq inv = tree_load(PAIR_THREADS + i);  // 1 / (product of this thread's denominators)
   const unsigned long long tile_off = offs[blockIdx.x];
   const uint64_t pos_base = tile_off & 0xffffffffull, sidx_base = sum_base + (tile_off >> 32);
+  Fq inv = fp_load<FqParams>(totals_inv + ((uint64_t)blockIdx.x * PAIR_THREADS + i) * 32);
 #pragma unroll 1
   for (int j = PAIR_B - 1; j >= 0; j--) {
     const uint32_t packed = s_off[j][i], code = packed >> 29;
     if ((code & 3) == 0) continue;  // nothing to write (both digits zero, or past the end of the list)
     const uint32_t off = (packed & 0x1fffffffu) + s_warp[j][warp];
-    const uint64_t a = 2 * (tile0 + (uint64_t)j * PAIR_THREADS + i);
+    const uint64_t p = tile0 + (uint64_t)j * PAIR_THREADS + i, a = 2 * p;
     uint64_t pos = pos_base + (off & 0xffffu);
     uint32_t ka, kb, va, vb;
     pair_entries(keys, vals, a, m, ka, kb, va, vb);
     if (code & 4) {
-      PairOperands o;
-      pair_load(bases, sums, va, vb, o);
-      Fq d;
-      const int kind = pair_classify(o, d);
+      // both points and the prefix are requested together: one memory round trip per pair
+      const uint8_t* pa = entry_point(bases, sums, va);
+      const uint8_t* pb = entry_point(bases, sums, vb);
+      const Fq xa = fp_load<FqParams>(pa), xb = fp_load<FqParams>(pb);
+      Fq ya = fp_load<FqParams>(pa + 32), yb = fp_load<FqParams>(pb + 32);
+      const Fq pre = fp_load<FqParams>(prefix + p * 32);
+      const Fq d = fp_sub<FqParams>(xb, xa);
+      if (va >> 31) ya = fp_neg<FqParams>(ya);
+      if (vb >> 31) yb = fp_neg<FqParams>(yb);
+      const Fq dinv = fp_mul<FqParams>(inv, pre);
+      inv = fp_mul<FqParams>(inv, d);
+      const Fq lam = fp_mul<FqParams>(fp_sub<FqParams>(yb, ya), dinv);
       Affine r;
-      if (kind >= PAIR_CHORD) {
-        Fq pre;
-#pragma unroll
-        for (int w = 0; w < 8; w++) pre.v[w] = s_prefix[j * 8 + w][i];
-        const Fq dinv = fp_mul<FqParams>(inv, pre);
-        inv = fp_mul<FqParams>(inv, d);
-        Fq num;
-        if (kind == PAIR_CHORD) {
-          num = fp_sub<FqParams>(o.yb, o.ya);
-        } else {
-          const Fq xx = fp_sqr<FqParams>(o.xa);
-          num = fp_add<FqParams>(fp_dbl<FqParams>(xx), xx);
-        }
-        const Fq lam = fp_mul<FqParams>(num, dinv);
-        r.x = fp_sub<FqParams>(fp_sub<FqParams>(fp_sqr<FqParams>(lam), o.xa), o.xb);
-        r.y = fp_sub<FqParams>(fp_mul<FqParams>(lam, fp_sub<FqParams>(o.xa, r.x)), o.ya);
-      } else if (kind == PAIR_COPY) {  // an infinite operand: the other one (infinite as well if both are)
-        const bool infa = fp_is_zero<FqParams>(o.xa) && fp_is_zero<FqParams>(o.ya);
-        r.x = infa ? o.xb : o.xa;
-        r.y = infa ? o.yb : o.ya;
-      } else {
-        r.x = fp_zero<FqParams>();
-        r.y = fp_zero<FqParams>();
-      }
+      r.x = fp_sub<FqParams>(fp_sub<FqParams>(fp_sqr<FqParams>(lam), xa), xb);
+      r.y = fp_sub<FqParams>(fp_mul<FqParams>(lam, fp_sub<FqParams>(xa, r.x)), ya);
       const uint64_t sidx = sidx_base + (off >> 16);
       affine_store(sums + sidx * 64, r);
       keys_out[pos] = ka;
@@ -1031,7 +1003,8 @@ int msm_run(qz_ctx* ctx, const qz_srs* srs, uint4* scalars_dev, const void* scal
     return ctx->fail(QZ_ERR_ALLOC, "MSM scratch");
   // pair levels (msm_pair_*): scratch for the longest segment, shared by the segments (they run in turn on `st`)
   PairCtl* pair_ctl = nullptr;
-  uint8_t* pair_sums = nullptr;
+  uint8_t *pair_sums = nullptr, *pair_prefix = nullptr, *pair_codes = nullptr;
+  uint8_t *pair_v[PAIR_TREE_MAX + 1] = {}, *pair_pre[PAIR_TREE_MAX] = {};  // inversion tree: elements / running products per depth
   unsigned long long *pair_counts = nullptr, *pair_offs = nullptr;
   void* pair_scan_tmp = nullptr;
   size_t pair_scan_bytes = 0;
@@ -1040,11 +1013,29 @@ int msm_run(qz_ctx* ctx, const qz_srs* srs, uint4* scalars_dev, const void* scal
     const uint64_t tiles = (mmax + 2 * PAIR_TILE - 1) / (2 * PAIR_TILE);
     pair_ctl = (PairCtl*)ctx->arena_alloc(sizeof(PairCtl));
     pair_sums = (uint8_t*)ctx->arena_alloc(mmax * 64);
+    pair_prefix = (uint8_t*)ctx->arena_alloc(tiles * PAIR_TILE * 32);
+    pair_codes = (uint8_t*)ctx->arena_alloc(tiles * PAIR_TILE);
+    bool tree_ok = true;
+    {
+      uint64_t n = tiles * PAIR_THREADS;
+      for (int k = 0; k <= PAIR_TREE_MAX; k++) {
+        pair_v[k] = (uint8_t*)ctx->arena_alloc(n * 32);
+        tree_ok = tree_ok && pair_v[k];
+        if (n == 1) break;
+        if (k == PAIR_TREE_MAX) {
+          tree_ok = false;
+          break;
+        }
+        pair_pre[k] = (uint8_t*)ctx->arena_alloc(n * 32);
+        tree_ok = tree_ok && pair_pre[k];
+        n = (n + PAIR_G - 1) / PAIR_G;
+      }
+    }
     pair_counts = (unsigned long long*)ctx->arena_alloc((tiles + 1) * 8);
     pair_offs = (unsigned long long*)ctx->arena_alloc((tiles + 1) * 8);
     cub::DeviceScan::ExclusiveSum(nullptr, pair_scan_bytes, pair_counts, pair_offs, (int64_t)(tiles + 1), st);
     pair_scan_tmp = ctx->arena_alloc(pair_scan_bytes);
-    if (!pair_ctl || !pair_sums || !pair_counts || !pair_offs || !pair_scan_tmp)
+    if (!pair_ctl || !pair_sums || !pair_prefix || !pair_codes || !tree_ok || !pair_counts || !pair_offs || !pair_scan_tmp)
       return ctx->fail(QZ_ERR_ALLOC, "MSM pair-level scratch");
   }
 
@@ -1082,14 +1073,31 @@ int msm_run(qz_ctx* ctx, const qz_srs* srs, uint4* scalars_dev, const void* scal
       uint32_t* vbuf[2] = {dv.Current(), dv.Alternate()};
       int cur = 0;
       const uint64_t tiles = (ms + 2 * PAIR_TILE - 1) / (2 * PAIR_TILE);  // of a level over the longest list possible
+      uint64_t tree_n[PAIR_TREE_MAX + 1];  // elements per depth over the longest list possible, down to ONE root
+      int tree_depth = 0;
+      tree_n[0] = tiles * PAIR_THREADS;
+      while (tree_n[tree_depth] > 1) {
+        tree_n[tree_depth + 1] = (tree_n[tree_depth] + PAIR_G - 1) / PAIR_G;
+        tree_depth++;
+      }
       const uint32_t dmask = (1u << c) - 1;
       QZ_LAUNCH(ctx, msm_pair_init, 1, 1, 0, pair_ctl, ms, pair_counts + tiles);
       for (int l = 0; l < pair_levels; l++) {
-        QZ_LAUNCH(ctx, msm_pair_count, (unsigned)tiles, 256, 0, (const uint32_t*)kbuf[cur], pair_ctl, l, dmask, pair_counts);
+        const uint32_t* kc = kbuf[cur];
+        const uint32_t* vc = vbuf[cur];
+        QZ_LAUNCH(ctx, msm_pair_scan, (unsigned)tiles, PAIR_THREADS, 0, kc, vc, pair_ctl, l, dmask, bases, pair_sums, pair_prefix,
+                  pair_v[0], pair_codes, pair_counts);
         QZ_CUDA(ctx, cub::DeviceScan::ExclusiveSum(pair_scan_tmp, pair_scan_bytes, pair_counts, pair_offs, (int64_t)(tiles + 1), st));
         ctx->launches += 2;
-        QZ_LAUNCH(ctx, msm_pair_apply, (unsigned)tiles, PAIR_THREADS, 0, (const uint32_t*)kbuf[cur], (const uint32_t*)vbuf[cur],
-                  pair_ctl, l, dmask, bases, pair_sums, pair_offs, (uint32_t)tiles, kbuf[cur ^ 1], vbuf[cur ^ 1]);
+        for (int k = 0; k < tree_depth; k++)
+          QZ_LAUNCH(ctx, msm_pair_tree_up, (unsigned)((tree_n[k + 1] + 127) / 128), 128, 0, pair_ctl, l, k, pair_v[k], pair_pre[k],
+                    pair_v[k + 1]);
+        QZ_LAUNCH(ctx, msm_pair_tree_root, 1, 1, 0, pair_ctl, l, pair_v[tree_depth]);
+        for (int k = tree_depth - 1; k >= 0; k--)
+          QZ_LAUNCH(ctx, msm_pair_tree_down, (unsigned)((tree_n[k + 1] + 127) / 128), 128, 0, pair_ctl, l, k, pair_v[k], pair_pre[k],
+                    pair_v[k + 1]);
+        QZ_LAUNCH(ctx, msm_pair_apply, (unsigned)tiles, PAIR_THREADS, 0, kc, vc, pair_ctl, l, dmask, bases, pair_sums, pair_prefix,
+                  pair_v[0], pair_codes, pair_offs, (uint32_t)tiles, kbuf[cur ^ 1], vbuf[cur ^ 1]);
         cur ^= 1;
       }
       QZ_LAUNCH(ctx, msm_accumulate<true>, (unsigned)((seg_chunks + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0,

@@ -431,34 +431,41 @@ def test_toom3_sampling_with_derived_s1_equals_reference_formulation(n):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-PAIR_B, PAIR_THREADS, VAL_PAIR = 8, 128, 1 << 30
+PAIR_B, PAIR_THREADS, PAIR_G, VAL_PAIR = 16, 128, 16, 1 << 30
 PAIR_TILE = PAIR_B * PAIR_THREADS
 
 
-def _tile_inverses(totals, p):
-    """msm_pair_apply's product tree in shared memory: node n = product of nodes 2n and 2n + 1 (leaves 128 + thread),
-    ONE inversion at the root, inverse of a child = inverse of the parent x its sibling"""
-    n = len(totals)
-    tree = [1] * n + list(totals)
-    s = n // 2
-    while s >= 1:
-        for i in range(s):
-            tree[s + i] = tree[2 * (s + i)] * tree[2 * (s + i) + 1] % p
-        s //= 2
-    tree[1] = pow(tree[1], p - 2, p)
-    s = 1
-    while s < n:
-        for i in range(s):
-            invp, left, right = tree[s + i], tree[2 * (s + i)], tree[2 * (s + i) + 1]
-            tree[2 * (s + i)], tree[2 * (s + i) + 1] = invp * right % p, invp * left % p
-        s *= 2
-    return tree[n:]
+def _batch_inverse_tree(v, p):
+    """msm_pair_tree_up / _root / _down: invert every element through a product tree of fan-in PAIR_G climbed to ONE
+    root (one modular inversion); `pre` holds the running product before each element"""
+    levels, pres = [list(v)], []
+    while len(levels[-1]) > 1:
+        cur, pre, up = levels[-1], [0] * len(levels[-1]), []
+        for u in range(0, len(cur), PAIR_G):
+            run = 1
+            for i in range(u, min(u + PAIR_G, len(cur))):
+                pre[i] = run
+                run = run * cur[i] % p
+            up.append(run)
+        pres.append(pre)
+        levels.append(up)
+    levels[-1] = [pow(levels[-1][0], p - 2, p)]
+    for depth in reversed(range(len(pres))):
+        cur, pre, up = levels[depth], pres[depth], levels[depth + 1]
+        for u in range(len(up)):
+            inv = up[u]
+            for i in reversed(range(u * PAIR_G, min(u * PAIR_G + PAIR_G, len(cur)))):
+                x = cur[i]
+                cur[i] = inv * pre[i] % p
+                inv = inv * x % p
+    return levels[0]
 
 
 def pair_level(keys, vals, dmask, bases, sums):
-    """One pair level of csrc/msm.cu (msm_pair_count, the scan over tiles, msm_pair_apply) over Python ints: returns the
+    """One pair level of csrc/msm.cu (msm_pair_scan, the inversion tree, msm_pair_apply) over Python ints: returns the
     output list; appends this level's pair sums to `sums`.  Points are (x, y) with (0, 0) = infinity, values carry the
-    sign in bit 31 and VAL_PAIR when they address `sums`."""
+    sign in bit 31 and VAL_PAIR when they address `sums`.  A block owns a tile of PAIR_TILE pairs, thread i the pairs
+    i, i + 128, .. of it."""
     q = py.FQ
     m = len(keys)
 
@@ -472,76 +479,60 @@ def pair_level(keys, vals, dmask, bases, sums):
         kb, vb = (keys[a + 1], vals[a + 1]) if a + 1 < m else (0, 0)
         return ka, kb, va, vb
 
-    def code(ka, kb):
-        if ka == kb and ka & dmask:
-            return 4 | 1
-        return (ka & dmask != 0) + (kb & dmask != 0)
-
-    def classify(va, vb):  # (kind, denominator): the complete affine law, decided from the operands alone
-        (xa, ya), (xb, yb) = point(va), point(vb)
-        if (xa, ya) == (0, 0) or (xb, yb) == (0, 0):
-            return "copy", None
-        if xa == xb:
-            return ("tangent", 2 * ya % q) if ya == yb and ya else ("inf", None)
-        return "chord", (xb - xa) % q
-
     n_tiles = (m + 2 * PAIR_TILE - 1) // (2 * PAIR_TILE)
-    counts = []
-    for tile in range(n_tiles):  # msm_pair_count: keys only
-        cs = [code(*entries(tile * PAIR_TILE + k)[:2]) for k in range(PAIR_TILE)]
-        counts.append((sum(c & 3 for c in cs), sum(c >> 2 for c in cs)))
+    pair_of = lambda tile, j, i: tile * PAIR_TILE + j * PAIR_THREADS + i  # noqa: E731
+    codes, prefix, totals, counts = {}, {}, [], []
+    for tile in range(n_tiles):  # scan
+        n_out = n_sum = 0
+        for i in range(PAIR_THREADS):
+            run = 1
+            for j in range(PAIR_B):
+                pr = pair_of(tile, j, i)
+                ka, kb, va, vb = entries(pr)
+                code = (ka & dmask != 0) + (kb & dmask != 0)
+                if ka == kb and ka & dmask:
+                    xa, xb = point(va)[0], point(vb)[0]
+                    d = (xb - xa) % q
+                    if xa and xb and d:  # the chord rule applies; anything else passes through to the XYZZ law
+                        code = 4 | 1
+                        prefix[pr] = run
+                        run = run * d % q
+                codes[pr] = code
+                n_out, n_sum = n_out + (code & 3), n_sum + (code >> 2)
+            totals.append(run)
+        counts.append((n_out, n_sum))
     offs = [(0, 0)]
-    for c in counts:
+    for c in counts:  # exclusive scan over the tiles, with the extra item that receives the totals
         offs.append((offs[-1][0] + c[0], offs[-1][1] + c[1]))
+    inv_totals = _batch_inverse_tree(totals, q) if totals else []
     sum_base = len(sums)
     m_out, n_sums = offs[n_tiles]
     keys_out, vals_out = [None] * m_out, [None] * m_out
     sums.extend([None] * n_sums)
-    for tile in range(n_tiles):
-        tile0 = tile * PAIR_TILE
-        pair_of = lambda j, i: tile0 + j * PAIR_THREADS + i  # noqa: E731  (row j of the tile, thread i)
-        # offsets in list order = (row, thread) order
+    for tile in range(n_tiles):  # apply
         off, run_out, run_sum = {}, 0, 0
-        for j in range(PAIR_B):
+        for j in range(PAIR_B):  # offsets inside the tile, in list order = (row, thread) order
             for i in range(PAIR_THREADS):
-                c = code(*entries(pair_of(j, i))[:2])
-                off[(j, i)] = (run_out, run_sum, c)
+                off[(j, i)] = (run_out, run_sum)
+                c = codes[pair_of(tile, j, i)]
                 run_out, run_sum = run_out + (c & 3), run_sum + (c >> 2)
-        prefix, totals = {}, []
-        for i in range(PAIR_THREADS):  # forward
-            run = 1
-            for j in range(PAIR_B):
-                if off[(j, i)][2] & 4:
-                    _, _, va, vb = entries(pair_of(j, i))
-                    kind, d = classify(va, vb)
-                    if d is not None:
-                        prefix[(j, i)] = run
-                        run = run * d % q
-            totals.append(run)
-        invs = _tile_inverses(totals, q)
-        for i in range(PAIR_THREADS):  # backward
-            inv = invs[i]
+        for i in range(PAIR_THREADS):
+            inv = inv_totals[tile * PAIR_THREADS + i]
             for j in reversed(range(PAIR_B)):
-                o_out, o_sum, c = off[(j, i)]
-                if not c & 3:
+                pr = pair_of(tile, j, i)
+                code = codes[pr]
+                if not code & 3:
                     continue
-                ka, kb, va, vb = entries(pair_of(j, i))
-                pos = offs[tile][0] + o_out
-                if c & 4:
-                    kind, d = classify(va, vb)
+                ka, kb, va, vb = entries(pr)
+                pos = offs[tile][0] + off[(j, i)][0]
+                if code & 4:
                     (xa, ya), (xb, yb) = point(va), point(vb)
-                    if d is not None:
-                        dinv = inv * prefix[(j, i)] % q
-                        inv = inv * d % q
-                        lam = ((yb - ya) if kind == "chord" else 3 * xa * xa) * dinv % q
-                        x3 = (lam * lam - xa - xb) % q
-                        r = (x3, (lam * (xa - x3) - ya) % q)
-                    elif kind == "copy":
-                        r = (xb, yb) if (xa, ya) == (0, 0) else (xa, ya)
-                    else:
-                        r = (0, 0)
-                    sidx = sum_base + offs[tile][1] + o_sum
-                    sums[sidx] = r
+                    dinv = inv * prefix[pr] % q
+                    inv = inv * ((xb - xa) % q) % q
+                    lam = (yb - ya) * dinv % q
+                    x3 = (lam * lam - xa - xb) % q
+                    sidx = sum_base + offs[tile][1] + off[(j, i)][1]
+                    sums[sidx] = (x3, (lam * (xa - x3) - ya) % q)
                     keys_out[pos], vals_out[pos] = ka, VAL_PAIR | sidx
                 else:
                     if ka & dmask:
@@ -565,12 +556,12 @@ def test_pair_levels_keep_every_bucket_sum():
         return None if pt == (0, 0) else pt
 
     for trial in range(12):
-        m = rnd.choice([1, 2, 31, 32, 33, 64, 65, 200, 333, 2047, 2049, 2500])
+        m = rnd.choice([1, 2, 31, 32, 33, 64, 65, 200, 333, 4095, 4097, 5000])
         n_keys = rnd.choice([1, 3, 20])
         entries = []
         for _ in range(m):
             key = (rnd.randrange(2) << c) | rnd.choice([0] + list(range(1, n_keys + 1)))
-            if trial % 3 == 0:  # few distinct points: P + P, P - P and infinite operands inside buckets
+            if trial % 3 == 0:  # few distinct points: equal x (P + P and P - P) and infinite operands inside buckets
                 idx = rnd.randrange(0, 3)
             else:
                 idx = rnd.randrange(0, len(bases))
@@ -594,4 +585,4 @@ def test_pair_levels_keep_every_bucket_sum():
                 pt = as_opt((x, (-y) % py.FQ if v >> 31 else y))
                 got[k] = py.g1_add(got.get(k), pt)
             assert {k: v for k, v in got.items() if v is not None} == {k: v for k, v in want.items() if v is not None}
-        assert all(s == (0, 0) or py.g1_is_on_curve(s) for s in sums)
+        assert all(py.g1_is_on_curve(s) for s in sums)
