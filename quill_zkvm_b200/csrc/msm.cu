@@ -221,7 +221,6 @@ QZ_DEV void pair_entries(const uint32_t* keys, const uint32_t* vals, uint64_t a,
     ka = keys[a], va = vals[a];
   }
 }
-QZ_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // codes: bits 0-1 = outputs of the pair (0..2), bit 2 = the pair is summed (then one output)
 __global__ void __launch_bounds__(PAIR_THREADS, 8) msm_pair_scan(const uint32_t* keys, const uint32_t* vals, const PairCtl* ctl,
                                                                int level, uint32_t dmask, const uint8_t* bases,
@@ -233,18 +232,6 @@ __global__ void __launch_bounds__(PAIR_THREADS, 8) msm_pair_scan(const uint32_t*
   if (2 * tile0 >= m) {
     if (i == 0) counts[blockIdx.x] = 0;
     return;
-  }
-  // all of the thread's candidate points are requested before the first is used (level 1 gathers them from all over
-  // the bases: the pass is bound by the memory's rate of random accesses, so every request should be in flight early)
-#pragma unroll 4
-  for (int j = 0; j < PAIR_B; j++) {
-    const uint64_t a = 2 * (tile0 + (uint64_t)j * PAIR_THREADS + i);
-    uint32_t ka, kb, va, vb;
-    pair_entries(keys, vals, a, m, ka, kb, va, vb);
-    if (ka == kb && (ka & dmask)) {
-      prefetch_l2(entry_point(bases, sums, va));
-      prefetch_l2(entry_point(bases, sums, vb));
-    }
   }
   Fq run = fp_one<FqParams>();
   uint32_t n_out = 0, n_sum = 0;
@@ -336,11 +323,6 @@ __global__ void __launch_bounds__(PAIR_THREADS, 4) msm_pair_apply(const uint32_t
 #pragma unroll
   for (int j = 0; j < PAIR_B; j++) {  // offsets in list order: row j of the tile = pairs j * 128 .. j * 128 + 127
     const uint32_t code = codes[tile0 + (uint64_t)j * PAIR_THREADS + i];
-    if (code & 4) {  // both entries exist: request the points (first half; the y's share the 64-byte block)
-      const uint2 v2 = *reinterpret_cast<const uint2*>(vals + 2 * (tile0 + (uint64_t)j * PAIR_THREADS + i));
-      prefetch_l2(entry_point(bases, sums, v2.x));
-      prefetch_l2(entry_point(bases, sums, v2.y));
-    }
     const uint32_t v = (code & 3) | ((code >> 2) << 16);
     uint32_t incl = v;
 #pragma unroll
