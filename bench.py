@@ -458,6 +458,24 @@ def run_gpu(args):
     e2e_ms, _ = timed_loop(lambda: results.__setitem__("host", commit(scal_host.reshape(-1, 32))), args.steps, args.warmup)
     assert np.array_equal(results["dev"], results["host"]), "device-resident and host-input commitments differ"
     msm_c, msm_digits, msm_shared, msm_adds = (ctx.last_stat(i) for i in range(4))
+    # side leg (N = 1): the same commitment with the opt-in pair levels (QZ_MSM_PAIR_LEVELS, csrc/msm.cu msm_pair_*:
+    # batched affine additions ahead of the XYZZ accumulation) -- reported beside the default path
+    pair_leg = None
+    if world == 1 and not args.no_pair_leg:
+        os.environ["QZ_MSM_PAIR_LEVELS"] = str(args.pair_levels)
+        try:
+            pair_acc: list = []
+            pair_ms, pair_launches = timed_loop(lambda: results.__setitem__("pair", commit(scal_dev)), args.steps, args.warmup, pair_acc)
+            pair_leg = {"ms_per_step": pair_ms, "value": n / (pair_ms * 1e-3), "unit": "points/s", "levels": args.pair_levels,
+                        "pair_levels_plus_accumulate_ms": sum(pair_acc) / len(pair_acc),
+                        "gpu_launches": pair_launches // args.steps,
+                        "same_commitment": bool(np.array_equal(results["pair"], results["dev"])),
+                        "default": "off (loses with host scalars: the streamed ranges' sort and the level-1 gathers share the "
+                                   "memory system; neutral below 2^23 points)"}
+        except Exception as e:  # noqa: BLE001  (a side leg never takes the line down)
+            pair_leg = {"error": str(e)[:200]}
+        finally:
+            os.environ.pop("QZ_MSM_PAIR_LEVELS", None)
 
     # ---- sumcheck: three 2^log_n tables, degree-3 product ----
     nv = args.log_n
@@ -632,6 +650,8 @@ def run_gpu(args):
                                              "times the round's linear eq factor)"}
         if msm20:
             line["msm_2_20"] = msm20
+        if pair_leg:
+            line["msm_pair_levels"] = pair_leg
         if mlpcs:
             mlpcs["roofline"] = imad_roofline(mlpcs.pop("_acc_stats"), imad_peak, mlpcs.pop("_ms"), mlpcs.pop("_steps"))
             line["mlpcs_commit_open"] = mlpcs
@@ -664,6 +684,8 @@ def main():
     ap.add_argument("--hyperplonk-log-rows", type=int, default=20,
                     help="config 5: rows per trace of the two-trace HyperPlonk proof (0 = skip; BASELINE names 20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pair-leg", action="store_true", help="skip the side leg with the MSM pair levels switched on")
+    ap.add_argument("--pair-levels", type=int, default=3, help="QZ_MSM_PAIR_LEVELS of the side leg")
     ap.add_argument("--no-verify", action="store_true", help="skip the verifier check of the HyperPlonk proof")
     ap.add_argument("--no-precompute", action="store_true", help="MSM without the precomputed window multiples")
     ap.add_argument("--precompute-bits", type=int, default=0, help="window bits of the precomputed table (0 = auto)")

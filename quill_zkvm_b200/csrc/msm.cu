@@ -11,6 +11,8 @@
 //                        chunk, XYZZ += affine (8M + 2S) per entry with the next base prefetched; load is balanced
 //                        whatever the scalar distribution.  A chunk's first / last runs may be partial buckets and go
 //                        to a list of partial runs, interior runs are complete buckets and are written in place.
+//  3b. msm_pair_*        optional (QZ_MSM_PAIR_LEVELS = k, off by default): k halvings of the sorted list by affine
+//                        additions with a shared inversion before step 3 (section 4b below)
 //   4. msm_partials_reduce  the list of partial runs is reduced by the same chunked rule, level by level, until it
 //                        fits one chunk: no thread ever walks a whole bucket, however skewed the scalars are
 //   5. msm_bucket_reduce per window: sum_b b * B_b by segmented running sums + a tree reduction
