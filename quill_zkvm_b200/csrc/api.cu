@@ -244,7 +244,6 @@ void qz_ctx_destroy(qz_ctx* c) {
     cudaEventDestroy(pr.second);
   }
   c->destroy_prep_stream();
-  c->destroy_pair_stream();
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }

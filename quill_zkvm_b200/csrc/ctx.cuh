@@ -114,34 +114,6 @@ struct qz_ctx {
     }
     prep_stream = nullptr;
   }
-  // pair levels of the MSM in slices (msm.cu, QZ_MSM_PAIR_SPLIT): the memory-bound passes of one slice run on this
-  // high-priority stream, in small grids, beside the multiplier-bound pass of another slice on `stream`
-  cudaStream_t pair_stream = nullptr;
-  std::vector<cudaEvent_t> pair_events;  // untimed, handed out in order per call (pair_event), reused by the next call
-  size_t pair_events_used = 0;
-  int ensure_pair_stream() {
-    if (pair_stream) return 0;
-    int lo = 0, hi = 0;
-    if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return 1;
-    return cudaStreamCreateWithPriority(&pair_stream, cudaStreamNonBlocking, hi) != cudaSuccess;
-  }
-  cudaEvent_t pair_event() {
-    if (pair_events_used == pair_events.size()) {
-      cudaEvent_t e = nullptr;
-      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-      pair_events.push_back(e);
-    }
-    return pair_events[pair_events_used++];
-  }
-  void destroy_pair_stream() {
-    if (pair_stream) {
-      cudaStreamSynchronize(pair_stream);
-      cudaStreamDestroy(pair_stream);
-      pair_stream = nullptr;
-    }
-    for (cudaEvent_t e : pair_events) cudaEventDestroy(e);
-    pair_events.clear();
-  }
   // every msm_accumulate launch since the last qz_msm_accumulate_stats(reset) is bracketed by an event pair of this ring
   // (grown on demand, reused after a reset), so that a caller that runs many MSMs per step (MLPCS open: 5, HyperPlonk:
   // ~140) can report the dominant kernel's share and its integer-pipe fraction for the whole step
@@ -194,7 +166,6 @@ struct qz_ctx {
     if (stream_busy_possible) {
       if (stream) cudaStreamSynchronize(stream);
       if (prep_stream) cudaStreamSynchronize(prep_stream);
-      if (pair_stream) cudaStreamSynchronize(pair_stream);
       cudaGetLastError();
     }
     return status;

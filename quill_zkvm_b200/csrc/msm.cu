@@ -205,10 +205,10 @@ struct PairCtl {
   uint64_t m[PAIR_MAX_LEVELS + 1];     // m[l]: entries entering level l; m[L]: entries left for msm_accumulate
   uint64_t sums[PAIR_MAX_LEVELS + 1];  // sums[l]: pair sums written by the levels before l
 };
-__global__ void msm_pair_init(PairCtl* ctl, uint64_t m, uint64_t first_sum, unsigned long long* counts_last) {
+__global__ void msm_pair_init(PairCtl* ctl, uint64_t m, unsigned long long* counts_last) {
   for (int l = 0; l <= PAIR_MAX_LEVELS; l++) {
     ctl->m[l] = l == 0 ? m : 0;
-    ctl->sums[l] = first_sum;  // a slice of the list owns the slots [its offset, its offset + its length) of the sums
+    ctl->sums[l] = 0;
   }
   *counts_last = 0;  // the scan's extra item: offs[n_tiles] = the totals
 }
@@ -224,55 +224,49 @@ QZ_DEV void pair_entries(const uint32_t* keys, const uint32_t* vals, uint64_t a,
   }
 }
 // codes: bits 0-1 = outputs of the pair (0..2), bit 2 = the pair is summed (then one output)
-// The grid may be smaller than the number of tiles (blocks stride over them): a slice's scan then runs as a few blocks
-// per SM beside another slice's multiplier-bound apply pass instead of after it.
 __global__ void __launch_bounds__(PAIR_THREADS, 8) msm_pair_scan(const uint32_t* keys, const uint32_t* vals, const PairCtl* ctl,
                                                                int level, uint32_t dmask, const uint8_t* bases,
                                                                const uint8_t* sums, uint8_t* prefix, uint8_t* totals,
-                                                               uint8_t* codes, unsigned long long* counts, uint32_t n_tiles) {
+                                                               uint8_t* codes, unsigned long long* counts) {
   __shared__ unsigned long long s_cnt[PAIR_THREADS / 32];
-  const uint64_t m = ctl->m[level];
+  const uint64_t m = ctl->m[level], tile0 = (uint64_t)blockIdx.x * PAIR_TILE;
   const int i = threadIdx.x;
-  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const uint64_t tile0 = (uint64_t)tile * PAIR_TILE;
-    if (2 * tile0 >= m) {
-      if (i == 0) counts[tile] = 0;
-      continue;
-    }
-    Fq run = fp_one<FqParams>();
-    uint32_t n_out = 0, n_sum = 0;
+  if (2 * tile0 >= m) {
+    if (i == 0) counts[blockIdx.x] = 0;
+    return;
+  }
+  Fq run = fp_one<FqParams>();
+  uint32_t n_out = 0, n_sum = 0;
 #pragma unroll 1
-    for (int j = 0; j < PAIR_B; j++) {
-      const uint64_t p = tile0 + (uint64_t)j * PAIR_THREADS + i, a = 2 * p;
-      uint32_t ka, kb, va, vb;
-      pair_entries(keys, vals, a, m, ka, kb, va, vb);
-      uint32_t code = ((ka & dmask) != 0) + ((kb & dmask) != 0);
-      if (ka == kb && (ka & dmask)) {
-        const Fq xa = fp_load<FqParams>(entry_point(bases, sums, va));
-        const Fq xb = fp_load<FqParams>(entry_point(bases, sums, vb));
-        const Fq d = fp_sub<FqParams>(xb, xa);
-        if (!fp_is_zero<FqParams>(xa) && !fp_is_zero<FqParams>(xb) && !fp_is_zero<FqParams>(d)) {
-          code = 4 | 1;
-          fp_store<FqParams>(prefix + p * 32, run);
-          run = fp_mul<FqParams>(run, d);
-        }
+  for (int j = 0; j < PAIR_B; j++) {
+    const uint64_t p = tile0 + (uint64_t)j * PAIR_THREADS + i, a = 2 * p;
+    uint32_t ka, kb, va, vb;
+    pair_entries(keys, vals, a, m, ka, kb, va, vb);
+    uint32_t code = ((ka & dmask) != 0) + ((kb & dmask) != 0);
+    if (ka == kb && (ka & dmask)) {
+      const Fq xa = fp_load<FqParams>(entry_point(bases, sums, va));
+      const Fq xb = fp_load<FqParams>(entry_point(bases, sums, vb));
+      const Fq d = fp_sub<FqParams>(xb, xa);
+      if (!fp_is_zero<FqParams>(xa) && !fp_is_zero<FqParams>(xb) && !fp_is_zero<FqParams>(d)) {
+        code = 4 | 1;
+        fp_store<FqParams>(prefix + p * 32, run);
+        run = fp_mul<FqParams>(run, d);
       }
-      codes[p] = (uint8_t)code;
-      n_out += code & 3;
-      n_sum += code >> 2;
     }
-    fp_store<FqParams>(totals + ((uint64_t)tile * PAIR_THREADS + i) * 32, run);
-    unsigned long long cnt = (unsigned long long)n_out | ((unsigned long long)n_sum << 32);
+    codes[p] = (uint8_t)code;
+    n_out += code & 3;
+    n_sum += code >> 2;
+  }
+  fp_store<FqParams>(totals + ((uint64_t)blockIdx.x * PAIR_THREADS + i) * 32, run);
+  unsigned long long cnt = (unsigned long long)n_out | ((unsigned long long)n_sum << 32);
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, off);
-    if ((i & 31) == 0) s_cnt[i >> 5] = cnt;
-    __syncthreads();
-    if (i == 0) {
-      unsigned long long total = 0;
-      for (int w = 0; w < PAIR_THREADS / 32; w++) total += s_cnt[w];
-      counts[tile] = total;
-    }
-    __syncthreads();  // s_cnt is reused by the block's next tile
+  for (int off = 16; off > 0; off >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, off);
+  if ((i & 31) == 0) s_cnt[i >> 5] = cnt;
+  __syncthreads();
+  if (i == 0) {
+    unsigned long long total = 0;
+    for (int w = 0; w < PAIR_THREADS / 32; w++) total += s_cnt[w];
+    counts[blockIdx.x] = total;
   }
 }
 // elements of the inversion tree at `depth` above the threads' totals (depth 0) for the list entering `level`
@@ -950,33 +944,13 @@ int msm_run(qz_ctx* ctx, const qz_srs* srs, uint4* scalars_dev, const void* scal
   }
   if (S > 1 && ctx->ensure_prep_stream()) return ctx->fail(QZ_ERR_CUDA, "prep stream");
   cudaStream_t ps = S > 1 ? ctx->prep_stream : st;
-  // Slices of the sorted list (pair levels of an unsegmented MSM only; QZ_MSM_PAIR_SPLIT = count, default 4): whole
-  // tiles each.  The scan pass of a level is bound by memory, the apply pass by the multiplier; as launches on one
-  // stream they run one after the other.  With slices, the scan + inversion tree of one slice run on a second,
-  // high-priority stream in a grid of two blocks per SM while the main stream applies another slice.
-  constexpr int MAX_SLICES = 8;
-  int H = 1;
-  uint64_t slice_lo[MAX_SLICES + 1] = {0, m};
-  if (pair_levels && S == 1) {
-    const char* env = getenv("QZ_MSM_PAIR_SPLIT");
-    H = env && *env ? atoi(env) : 4;
-    const uint64_t tiles_total = (m + 2 * PAIR_TILE - 1) / (2 * PAIR_TILE);
-    H = (int)std::max<uint64_t>(1, std::min<uint64_t>(std::min(H, MAX_SLICES), tiles_total / 8));
-    for (int h = 1; h < H; h++) slice_lo[h] = tiles_total * h / H * (2 * PAIR_TILE);
-    slice_lo[H] = m;
-    if (H > 1 && ctx->ensure_pair_stream()) return ctx->fail(QZ_ERR_CUDA, "pair stream");
-  }
-  uint64_t chunk_base[qz_ctx::MAX_SEGMENTS + 1], slice_chunk[MAX_SLICES + 1] = {0};
+  uint64_t chunk_base[qz_ctx::MAX_SEGMENTS + 1];
   chunk_base[0] = 0;
   size_t max_seg = 0;
   for (int s = 0; s < S; s++) {
     const uint64_t ms = (uint64_t)Wd * (seg_lo[s + 1] - seg_lo[s]);
     chunk_base[s + 1] = chunk_base[s] + (ms + chunk_len - 1) / chunk_len;
     max_seg = std::max(max_seg, seg_lo[s + 1] - seg_lo[s]);
-  }
-  if (H > 1) {  // every slice starts a chunk of its own
-    for (int h = 0; h < H; h++) slice_chunk[h + 1] = slice_chunk[h] + (slice_lo[h + 1] - slice_lo[h] + chunk_len - 1) / chunk_len;
-    chunk_base[1] = slice_chunk[H];
   }
   const uint64_t n_chunks = chunk_base[S];
 
@@ -1011,53 +985,42 @@ int msm_run(qz_ctx* ctx, const qz_srs* srs, uint4* scalars_dev, const void* scal
   if (!keys || !vals || !keys2 || !vals2 || !buckets || !ppts_a || !pkeys_a || !ppts_b || !pkeys_b || !fin_a || !fin_b || !partial ||
       !partial2 || !window_sums || !sort_tmp)
     return ctx->fail(QZ_ERR_ALLOC, "MSM scratch");
-  // pair levels (msm_pair_*): scratch for the longest segment, shared by the segments (they run in turn on `st`); the
-  // prefixes, codes and sums are indexed by position in the list, the control block, tile counts and inversion tree
-  // exist once per slice
-  struct PairSlice {
-    PairCtl* ctl;
-    unsigned long long *counts, *offs;
-    uint8_t *v[PAIR_TREE_MAX + 1], *pre[PAIR_TREE_MAX];  // inversion tree: elements / running products per depth
-  } pair_slice[MAX_SLICES] = {};
+  // pair levels (msm_pair_*): scratch for the longest segment, shared by the segments (they run in turn on `st`)
+  PairCtl* pair_ctl = nullptr;
   uint8_t *pair_sums = nullptr, *pair_prefix = nullptr, *pair_codes = nullptr;
+  uint8_t *pair_v[PAIR_TREE_MAX + 1] = {}, *pair_pre[PAIR_TREE_MAX] = {};  // inversion tree: elements / running products per depth
+  unsigned long long *pair_counts = nullptr, *pair_offs = nullptr;
   void* pair_scan_tmp = nullptr;
   size_t pair_scan_bytes = 0;
   if (pair_levels) {
     const uint64_t mmax = (uint64_t)Wd * max_seg;
     const uint64_t tiles = (mmax + 2 * PAIR_TILE - 1) / (2 * PAIR_TILE);
+    pair_ctl = (PairCtl*)ctx->arena_alloc(sizeof(PairCtl));
     pair_sums = (uint8_t*)ctx->arena_alloc(mmax * 64);
     pair_prefix = (uint8_t*)ctx->arena_alloc(tiles * PAIR_TILE * 32);
     pair_codes = (uint8_t*)ctx->arena_alloc(tiles * PAIR_TILE);
-    bool ok = pair_sums && pair_prefix && pair_codes;
-    uint64_t max_tiles = 0;
-    for (int h = 0; h < H && ok; h++) {
-      PairSlice& ps_ = pair_slice[h];
-      const uint64_t len = H > 1 ? slice_lo[h + 1] - slice_lo[h] : mmax;
-      const uint64_t tiles_h = (len + 2 * PAIR_TILE - 1) / (2 * PAIR_TILE);
-      max_tiles = std::max(max_tiles, tiles_h);
-      ps_.ctl = (PairCtl*)ctx->arena_alloc(sizeof(PairCtl));
-      ps_.counts = (unsigned long long*)ctx->arena_alloc((tiles_h + 1) * 8);
-      ps_.offs = (unsigned long long*)ctx->arena_alloc((tiles_h + 1) * 8);
-      ok = ps_.ctl && ps_.counts && ps_.offs;
-      uint64_t cnt = tiles_h * PAIR_THREADS;
-      for (int k = 0; k <= PAIR_TREE_MAX && ok; k++) {
-        ps_.v[k] = (uint8_t*)ctx->arena_alloc(cnt * 32);
-        ok = ok && ps_.v[k];
-        if (cnt == 1) break;
+    bool tree_ok = true;
+    {
+      uint64_t n = tiles * PAIR_THREADS;
+      for (int k = 0; k <= PAIR_TREE_MAX; k++) {
+        pair_v[k] = (uint8_t*)ctx->arena_alloc(n * 32);
+        tree_ok = tree_ok && pair_v[k];
+        if (n == 1) break;
         if (k == PAIR_TREE_MAX) {
-          ok = false;
+          tree_ok = false;
           break;
         }
-        ps_.pre[k] = (uint8_t*)ctx->arena_alloc(cnt * 32);
-        ok = ok && ps_.pre[k];
-        cnt = (cnt + PAIR_G - 1) / PAIR_G;
+        pair_pre[k] = (uint8_t*)ctx->arena_alloc(n * 32);
+        tree_ok = tree_ok && pair_pre[k];
+        n = (n + PAIR_G - 1) / PAIR_G;
       }
     }
-    if (ok) {
-      cub::DeviceScan::ExclusiveSum(nullptr, pair_scan_bytes, pair_slice[0].counts, pair_slice[0].offs, (int64_t)(max_tiles + 1), st);
-      pair_scan_tmp = ctx->arena_alloc(pair_scan_bytes);  // the slices' scans are serialised on one stream
-    }
-    if (!ok || !pair_scan_tmp) return ctx->fail(QZ_ERR_ALLOC, "MSM pair-level scratch");
+    pair_counts = (unsigned long long*)ctx->arena_alloc((tiles + 1) * 8);
+    pair_offs = (unsigned long long*)ctx->arena_alloc((tiles + 1) * 8);
+    cub::DeviceScan::ExclusiveSum(nullptr, pair_scan_bytes, pair_counts, pair_offs, (int64_t)(tiles + 1), st);
+    pair_scan_tmp = ctx->arena_alloc(pair_scan_bytes);
+    if (!pair_ctl || !pair_sums || !pair_prefix || !pair_codes || !tree_ok || !pair_counts || !pair_offs || !pair_scan_tmp)
+      return ctx->fail(QZ_ERR_ALLOC, "MSM pair-level scratch");
   }
 
   if (S > 1) {  // the prep stream starts where the main stream stands (earlier users of the scratch, the scalars)
@@ -1092,73 +1055,38 @@ int msm_run(qz_ctx* ctx, const qz_srs* srs, uint4* scalars_dev, const void* scal
     if (pair_levels) {
       uint32_t* kbuf[2] = {dk.Current(), dk.Alternate()};  // a level reads one buffer of the sort's pair and writes the other
       uint32_t* vbuf[2] = {dv.Current(), dv.Alternate()};
-      const uint32_t dmask = (1u << c) - 1;
-      // the memory-bound passes (scan, scan over tiles, inversion tree) go to `mem`, the apply passes to `st`; one stream
-      // when the list is not sliced
-      cudaStream_t mem = H > 1 ? ctx->pair_stream : st;
-      cudaEvent_t tree_done[MAX_SLICES] = {}, apply_done[MAX_SLICES] = {};
-      ctx->pair_events_used = 0;
-      if (H > 1) {
-        cudaEvent_t start = ctx->pair_event();
-        if (!start) return ctx->fail(QZ_ERR_CUDA, "pair event");
-        QZ_CUDA(ctx, cudaEventRecord(start, st));
-        QZ_CUDA(ctx, cudaStreamWaitEvent(mem, start, 0));
-      }
       int cur = 0;
+      const uint64_t tiles = (ms + 2 * PAIR_TILE - 1) / (2 * PAIR_TILE);  // of a level over the longest list possible
+      uint64_t tree_n[PAIR_TREE_MAX + 1];  // elements per depth over the longest list possible, down to ONE root
+      int tree_depth = 0;
+      tree_n[0] = tiles * PAIR_THREADS;
+      while (tree_n[tree_depth] > 1) {
+        tree_n[tree_depth + 1] = (tree_n[tree_depth] + PAIR_G - 1) / PAIR_G;
+        tree_depth++;
+      }
+      const uint32_t dmask = (1u << c) - 1;
+      QZ_LAUNCH(ctx, msm_pair_init, 1, 1, 0, pair_ctl, ms, pair_counts + tiles);
       for (int l = 0; l < pair_levels; l++) {
-        for (int h = 0; h < H; h++) {
-          PairSlice& sl = pair_slice[h];
-          const uint64_t lo_h = H > 1 ? slice_lo[h] : 0, len = H > 1 ? slice_lo[h + 1] - slice_lo[h] : ms;
-          const uint64_t tiles = (len + 2 * PAIR_TILE - 1) / (2 * PAIR_TILE);  // over the longest list possible
-          uint64_t tree_n[PAIR_TREE_MAX + 1];  // elements per depth, down to ONE root
-          int tree_depth = 0;
-          tree_n[0] = tiles * PAIR_THREADS;
-          while (tree_n[tree_depth] > 1) {
-            tree_n[tree_depth + 1] = (tree_n[tree_depth] + PAIR_G - 1) / PAIR_G;
-            tree_depth++;
-          }
-          const uint32_t* kc = kbuf[cur] + lo_h;
-          const uint32_t* vc = vbuf[cur] + lo_h;
-          uint8_t* prefix_h = pair_prefix + lo_h / 2 * 32;
-          uint8_t* codes_h = pair_codes + lo_h / 2;
-          if (l == 0) QZ_LAUNCH_ON(ctx, mem, msm_pair_init, 1, 1, 0, sl.ctl, len, lo_h, sl.counts + tiles);
-          if (H > 1 && l > 0) QZ_CUDA(ctx, cudaStreamWaitEvent(mem, apply_done[h], 0));  // the slice's list of this level
-          // the first scan has the machine to itself; the others share it with an apply pass and keep to two blocks per SM
-          const uint64_t scan_grid = (H > 1 && (l > 0 || h > 0)) ? std::min<uint64_t>(tiles, 2 * (uint64_t)ctx->sm_count) : tiles;
-          QZ_LAUNCH_ON(ctx, mem, msm_pair_scan, (unsigned)scan_grid, PAIR_THREADS, 0, kc, vc, sl.ctl, l, dmask, bases, pair_sums,
-                       prefix_h, sl.v[0], codes_h, sl.counts, (uint32_t)tiles);
-          QZ_CUDA(ctx, cub::DeviceScan::ExclusiveSum(pair_scan_tmp, pair_scan_bytes, sl.counts, sl.offs, (int64_t)(tiles + 1), mem));
-          ctx->launches += 2;
-          for (int k = 0; k < tree_depth; k++)
-            QZ_LAUNCH_ON(ctx, mem, msm_pair_tree_up, (unsigned)((tree_n[k + 1] + 127) / 128), 128, 0, sl.ctl, l, k, sl.v[k], sl.pre[k],
-                         sl.v[k + 1]);
-          QZ_LAUNCH_ON(ctx, mem, msm_pair_tree_root, 1, 1, 0, sl.ctl, l, sl.v[tree_depth]);
-          for (int k = tree_depth - 1; k >= 0; k--)
-            QZ_LAUNCH_ON(ctx, mem, msm_pair_tree_down, (unsigned)((tree_n[k + 1] + 127) / 128), 128, 0, sl.ctl, l, k, sl.v[k],
-                         sl.pre[k], sl.v[k + 1]);
-          if (H > 1) {
-            if (!(tree_done[h] = ctx->pair_event())) return ctx->fail(QZ_ERR_CUDA, "pair event");
-            QZ_CUDA(ctx, cudaEventRecord(tree_done[h], mem));
-            QZ_CUDA(ctx, cudaStreamWaitEvent(st, tree_done[h], 0));
-          }
-          QZ_LAUNCH(ctx, msm_pair_apply, (unsigned)tiles, PAIR_THREADS, 0, kc, vc, sl.ctl, l, dmask, bases, pair_sums, prefix_h,
-                    sl.v[0], codes_h, sl.offs, (uint32_t)tiles, kbuf[cur ^ 1] + lo_h, vbuf[cur ^ 1] + lo_h);
-          if (H > 1) {
-            if (!(apply_done[h] = ctx->pair_event())) return ctx->fail(QZ_ERR_CUDA, "pair event");
-            QZ_CUDA(ctx, cudaEventRecord(apply_done[h], st));
-          }
-        }
+        const uint32_t* kc = kbuf[cur];
+        const uint32_t* vc = vbuf[cur];
+        QZ_LAUNCH(ctx, msm_pair_scan, (unsigned)tiles, PAIR_THREADS, 0, kc, vc, pair_ctl, l, dmask, bases, pair_sums, pair_prefix,
+                  pair_v[0], pair_codes, pair_counts);
+        QZ_CUDA(ctx, cub::DeviceScan::ExclusiveSum(pair_scan_tmp, pair_scan_bytes, pair_counts, pair_offs, (int64_t)(tiles + 1), st));
+        ctx->launches += 2;
+        for (int k = 0; k < tree_depth; k++)
+          QZ_LAUNCH(ctx, msm_pair_tree_up, (unsigned)((tree_n[k + 1] + 127) / 128), 128, 0, pair_ctl, l, k, pair_v[k], pair_pre[k],
+                    pair_v[k + 1]);
+        QZ_LAUNCH(ctx, msm_pair_tree_root, 1, 1, 0, pair_ctl, l, pair_v[tree_depth]);
+        for (int k = tree_depth - 1; k >= 0; k--)
+          QZ_LAUNCH(ctx, msm_pair_tree_down, (unsigned)((tree_n[k + 1] + 127) / 128), 128, 0, pair_ctl, l, k, pair_v[k], pair_pre[k],
+                    pair_v[k + 1]);
+        QZ_LAUNCH(ctx, msm_pair_apply, (unsigned)tiles, PAIR_THREADS, 0, kc, vc, pair_ctl, l, dmask, bases, pair_sums, pair_prefix,
+                  pair_v[0], pair_codes, pair_offs, (uint32_t)tiles, kbuf[cur ^ 1], vbuf[cur ^ 1]);
         cur ^= 1;
       }
-      for (int h = 0; h < H; h++) {
-        const uint64_t lo_h = H > 1 ? slice_lo[h] : 0;
-        const uint64_t chunks_h = H > 1 ? slice_chunk[h + 1] - slice_chunk[h] : seg_chunks;
-        const uint64_t cb = chunk_base[s] + (H > 1 ? slice_chunk[h] : 0);
-        QZ_LAUNCH(ctx, msm_accumulate<true>, (unsigned)((chunks_h + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0,
-                  (const uint32_t*)kbuf[cur] + lo_h, (const uint32_t*)vbuf[cur] + lo_h, (uint64_t)0,
-                  (const uint64_t*)&pair_slice[h].ctl->m[pair_levels], chunks_h, chunk_len, bases, (const uint8_t*)pair_sums, c, buckets,
-                  ppts_a + cb * 256, pkeys_a + 2 * cb);
-      }
+      QZ_LAUNCH(ctx, msm_accumulate<true>, (unsigned)((seg_chunks + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0,
+                (const uint32_t*)kbuf[cur], (const uint32_t*)vbuf[cur], (uint64_t)0, &pair_ctl->m[pair_levels], seg_chunks, chunk_len, bases, pair_sums, c, buckets,
+                ppts_a + chunk_base[s] * 256, pkeys_a + 2 * chunk_base[s]);
     } else {
       QZ_LAUNCH(ctx, msm_accumulate<false>, (unsigned)((seg_chunks + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0,
                 dk.Current(), dv.Current(), ms, (const uint64_t*)nullptr, seg_chunks, chunk_len, bases,

@@ -1,7 +1,6 @@
 """Pair levels of the MSM (QZ_MSM_PAIR_LEVELS, csrc/msm.cu msm_pair_*): parity against the oracle at small sizes for
 several level counts (every case is reported, nothing stops at the first mismatch), then timings of KZG commit at
-2^log_n with precomputed windows, device-resident and host scalars, for 0..6 levels.
-  python tools/pair_levels_probe.py [--no-parity] [--split=H ...] LOG_N [LOG_N ...]     (--split: QZ_MSM_PAIR_SPLIT values)"""
+2^log_n with precomputed windows, device-resident and host scalars, for 0..6 levels."""
 import os
 import sys
 import time
@@ -81,13 +80,8 @@ def timings(ctx, stream, log_n):
         return ev0.elapsed_time(ev1) / steps, sum(acc) / len(acc), r
 
     ref = None
-    splits = [int(a.split("=")[1]) for a in sys.argv if a.startswith("--split=")] or [None]
-    for levels, split in [(0, None)] + [(lv, sp) for sp in splits for lv in (2, 3, 4, 5, 6)]:
+    for levels in (0, 2, 3, 4, 5, 6):
         os.environ["QZ_MSM_PAIR_LEVELS"] = str(levels)
-        if split is None:
-            os.environ.pop("QZ_MSM_PAIR_SPLIT", None)
-        else:
-            os.environ["QZ_MSM_PAIR_SPLIT"] = str(split)
         try:
             ms, acc, r = timed(lambda: kzg.commit(dev))
         except Exception as e:  # noqa: BLE001
@@ -96,13 +90,12 @@ def timings(ctx, stream, log_n):
         if ref is None:
             ref = r
         same = np.array_equal(r, ref)
-        line = f"2^{log_n} device scalars levels={levels} split={split}: {ms:8.3f} ms/commit  pair levels + accumulate {acc:7.3f} ms  same={same}"
+        line = f"2^{log_n} device scalars levels={levels}: {ms:8.3f} ms/commit  pair levels + accumulate {acc:7.3f} ms  same={same}"
         if levels in (0, 4):
             msh, _, rh = timed(lambda: kzg.commit(host))
             line += f"   host scalars {msh:8.3f} ms same={np.array_equal(rh, ref)}"
         print(line, flush=True)
     os.environ.pop("QZ_MSM_PAIR_LEVELS", None)
-    os.environ.pop("QZ_MSM_PAIR_SPLIT", None)
     dev.free()
     kzg.srs.free()
 
