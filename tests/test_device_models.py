@@ -12,6 +12,8 @@ is pinned independently of the GPU tests:
   * NTT passes as plain local transforms + one correction product per element (csrc/mlpcs.cu ntt_pass)
   * the K = 3 round polynomial from samples at X = 0, 1, -1, infinity with lazily added operands, X = 1 restored from the
     running claim (csrc/sumcheck.cu prod_core_toom3, csrc/sumcheck.cuh sc_expand_evals / sc_toom3_to_coeffs)
+  * the MSM's optional pair levels: equal-key neighbours of the sorted list added in affine coordinates with the
+    denominators inverted through a product tree, outputs placed by an exclusive scan (csrc/msm.cu msm_pair_*)
 """
 import os
 import random
