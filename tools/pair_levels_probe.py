@@ -80,7 +80,8 @@ def timings(ctx, stream, log_n):
         return ev0.elapsed_time(ev1) / steps, sum(acc) / len(acc), r
 
     ref = None
-    for levels in (0, 2, 3, 4, 5, 6):
+    level_list = [int(x) for a in sys.argv if a.startswith("--levels=") for x in a.split("=")[1].split(",")] or [0, 2, 3, 4, 5, 6]
+    for levels in level_list:
         os.environ["QZ_MSM_PAIR_LEVELS"] = str(levels)
         try:
             ms, acc, r = timed(lambda: kzg.commit(dev))
@@ -102,15 +103,20 @@ def timings(ctx, stream, log_n):
 
 def main():
     stream = torch.cuda.Stream()
-    ctx = q.Context(0, stream.cuda_stream)
-    t0 = time.time()
-    if "--no-parity" not in sys.argv:
-        parity(ctx)
-        print(f"parity part {time.time() - t0:.1f} s", flush=True)
-    for a in sys.argv[1:]:
-        if a.isdigit():
-            timings(ctx, stream, int(a))
-    ctx.close()
+    fetch = [a.split("=")[1] for a in sys.argv if a.startswith("--l2-fetch=")] or [None]
+    for f in fetch:  # QZ_L2_FETCH is read when a context is created (device-wide L2 fetch granularity hint)
+        if f is not None:
+            os.environ["QZ_L2_FETCH"] = f
+            print(f"== QZ_L2_FETCH={f}", flush=True)
+        ctx = q.Context(0, stream.cuda_stream)
+        t0 = time.time()
+        if "--no-parity" not in sys.argv:
+            parity(ctx)
+            print(f"parity part {time.time() - t0:.1f} s", flush=True)
+        for a in sys.argv[1:]:
+            if a.isdigit():
+                timings(ctx, stream, int(a))
+        ctx.close()
 
 
 if __name__ == "__main__":
