@@ -217,10 +217,6 @@ int qz_ctx_create(int device, void* stream, qz_ctx** out) {
     c->own_stream = true;
   }
   c->pdl = getenv("QZ_NO_PDL") == nullptr;
-  if (const char* e = getenv("QZ_L2_FETCH")) {  // measurement: the L2's DRAM fetch granularity (device-wide hint); unset = the driver's default
-    const int g = atoi(e);
-    if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g);
-  }
   cudaEventCreate(&c->ev_call0);
   cudaEventCreate(&c->ev_call1);
   cudaEventCreate(&c->ev_k0);

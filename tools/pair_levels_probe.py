@@ -103,20 +103,15 @@ def timings(ctx, stream, log_n):
 
 def main():
     stream = torch.cuda.Stream()
-    fetch = [a.split("=")[1] for a in sys.argv if a.startswith("--l2-fetch=")] or [None]
-    for f in fetch:  # QZ_L2_FETCH is read when a context is created (device-wide L2 fetch granularity hint)
-        if f is not None:
-            os.environ["QZ_L2_FETCH"] = f
-            print(f"== QZ_L2_FETCH={f}", flush=True)
-        ctx = q.Context(0, stream.cuda_stream)
-        t0 = time.time()
-        if "--no-parity" not in sys.argv:
-            parity(ctx)
-            print(f"parity part {time.time() - t0:.1f} s", flush=True)
-        for a in sys.argv[1:]:
-            if a.isdigit():
-                timings(ctx, stream, int(a))
-        ctx.close()
+    ctx = q.Context(0, stream.cuda_stream)
+    t0 = time.time()
+    if "--no-parity" not in sys.argv:
+        parity(ctx)
+        print(f"parity part {time.time() - t0:.1f} s", flush=True)
+    for a in sys.argv[1:]:
+        if a.isdigit():
+            timings(ctx, stream, int(a))
+    ctx.close()
 
 
 if __name__ == "__main__":
